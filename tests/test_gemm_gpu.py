@@ -1,0 +1,121 @@
+"""tcgen05 GEMM kernels through the C ABI vs a plain torch fp32 evaluation of the same sums."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _conv_ref(A, taps, W, cin, a_off):
+    rows = A.shape[0]
+    Af = A.float()
+    out = torch.zeros(rows, W.shape[0], device=A.device)
+    q = torch.arange(rows, device=A.device)
+    for t, sh in enumerate(taps):
+        idx = q + sh
+        ok = (idx >= 0) & (idx < rows)
+        g = Af[idx.clamp(0, rows - 1), a_off:a_off + cin] * ok[:, None]
+        out += g @ W[:, t * cin:(t + 1) * cin].float().t()
+    return out
+
+
+@pytest.mark.parametrize("rows,ld,a_off,cin,taps,n_out,fp32", [
+    (1000, 64, 0, 64, [0], 64, False),
+    (128 * 5 + 17, 192, 64, 128, [-11, -10, -9, -1, 0, 1, 9, 10, 11], 256, False),
+    (4096, 256, 0, 256, [-67, -66, -65, -1, 0, 1, 65, 66, 67], 256, False),
+    (3000, 128, 0, 128, [0, 1, 50, 51], 128, False),
+    (2000, 64, 0, 64, [-3, 0, 3], 32, True),
+    (150 * 128 + 5, 64, 0, 64, [-1, 0, 1], 192, False),
+    (2500, 512, 0, 512, [0, 1, 2, 3], 512, False),
+])
+def test_conv_gemm(rows, ld, a_off, cin, taps, n_out, fp32):
+    import irc_b200
+    from irc_b200 import _native as nat
+    nat.arch_check()
+    g = torch.Generator(device="cuda").manual_seed(rows + n_out)
+    A = torch.randn(rows, ld, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(n_out, len(taps) * cin, device="cuda", generator=g) * 0.05).bfloat16()
+    out = torch.full((rows, n_out), float("nan"), device="cuda", dtype=torch.float32 if fp32 else torch.bfloat16)
+    a = nat.ConvGemmArgs()
+    a.a = A.data_ptr(); a.a_rows = rows; a.a_ld = ld; a.a_chan_off = a_off; a.cin = cin
+    a.ntaps = len(taps)
+    for i, t in enumerate(taps):
+        a.taps[i] = t
+    a.w = W.data_ptr(); a.n_out = n_out
+    a.out = out.data_ptr(); a.out_ld = n_out; a.out_chan_off = 0; a.out_fp32 = int(fp32)
+    a.bias = None; a.act = 0; a.slope = 0.0; a.row_img = None; a.mask = None; a.bn = 0
+    nat.check(nat.lib().irc_conv_gemm(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    ref = _conv_ref(A, taps, W, cin, a_off)
+    err = (out.float() - ref).norm() / ref.norm()
+    assert torch.isfinite(out.float()).all()
+    assert err < (1e-5 if fp32 else 4e-3), err
+
+
+def test_conv_gemm_epilogue():
+    from irc_b200 import _native as nat
+    rows, cin, n_out = 1500, 64, 64
+    taps = [-1, 0, 1]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(rows, cin, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(n_out, 3 * cin, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(n_out, device="cuda", generator=g)
+    mask = torch.randn(rows, n_out, device="cuda", generator=g).bfloat16()
+    img = (torch.arange(rows, device="cuda") // 500).short()
+    img[::7] = -1
+    for mode in ("bias_lrelu_rows", "mask"):
+        out = torch.full((rows, n_out), float("nan"), device="cuda", dtype=torch.bfloat16)
+        a = nat.ConvGemmArgs()
+        a.a = A.data_ptr(); a.a_rows = rows; a.a_ld = cin; a.a_chan_off = 0; a.cin = cin; a.ntaps = 3
+        for i, t in enumerate(taps):
+            a.taps[i] = t
+        a.w = W.data_ptr(); a.n_out = n_out; a.out = out.data_ptr(); a.out_ld = n_out
+        ref = _conv_ref(A, taps, W, cin, 0)
+        if mode == "bias_lrelu_rows":
+            a.bias = bias.data_ptr(); a.act = 2; a.slope = 0.2; a.row_img = img.data_ptr()
+            ref = torch.nn.functional.leaky_relu(ref + bias, 0.2) * (img >= 0)[:, None]
+        else:
+            a.mask = mask.data_ptr(); a.mask_ld = n_out; a.mask_chan_off = 0; a.mask_slope = 0.2
+            ref = ref * torch.where(mask.float() > 0, 1.0, 0.2)
+        nat.check(nat.lib().irc_conv_gemm(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        err = (out.float() - ref).norm() / ref.norm()
+        assert err < 4e-3, (mode, err)
+        if mode == "bias_lrelu_rows":
+            assert (out[img < 0] == 0).all()
+
+
+@pytest.mark.parametrize("rows,m,n,lda,ldb,a_off,b_off,shifts,splits", [
+    (4096, 128, 64, 128, 64, 0, 0, [0], 1),
+    (5000, 256, 256, 256, 256, 0, 0, [-71, -70, -69, -1, 0, 1, 69, 70, 71], 3),
+    (3333, 64, 192, 64, 192, 0, 0, [-1, 0, 1], 2),
+    (2048, 21, 64, 64, 64, 0, 0, [-10, 0, 10], 4),
+    (3000, 128, 128, 384, 384, 256, 128, [0, 5], 2),
+])
+def test_tn_gemm(rows, m, n, lda, ldb, a_off, b_off, shifts, splits):
+    from irc_b200 import _native as nat
+    g = torch.Generator(device="cuda").manual_seed(rows + m)
+    A = torch.randn(rows, lda, device="cuda", generator=g).bfloat16()
+    B = torch.randn(rows, ldb, device="cuda", generator=g).bfloat16()
+    nt = len(shifts)
+    out = torch.full((splits, m, nt, n), float("nan"), device="cuda")
+    a = nat.TnGemmArgs()
+    a.a = A.data_ptr(); a.a_rows = rows; a.a_ld = lda; a.a_chan_off = a_off; a.m = m
+    a.b = B.data_ptr(); a.b_rows = rows; a.b_ld = ldb; a.b_chan_off = b_off; a.n = n
+    a.k_rows = rows; a.ntaps = nt
+    for i, s in enumerate(shifts):
+        a.a_shift[i] = 0; a.b_shift[i] = s
+    a.out = out.data_ptr(); a.out_tap_stride = n; a.out_m_stride = nt * n; a.out_n_stride = 1
+    a.out_split_stride = m * nt * n; a.splits = splits; a.bn = 0
+    nat.check(nat.lib().irc_tn_gemm(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    got = out.sum(0)
+    Af = A.float()[:, a_off:a_off + m]; Bf = B.float()[:, b_off:b_off + n]
+    q = torch.arange(rows, device="cuda")
+    for t, s in enumerate(shifts):
+        idx = q + s
+        ok = ((idx >= 0) & (idx < rows)).float()[:, None]
+        ref = Af.t() @ (Bf[idx.clamp(0, rows - 1)] * ok)
+        err = (got[:, t, :] - ref).norm() / ref.norm()
+        assert err < 1e-4, (t, err)
