@@ -72,6 +72,142 @@ typedef struct irc_tn_gemm_args {
 } irc_tn_gemm_args;
 int irc_tn_gemm(const irc_tn_gemm_args* args, void* stream);
 
+
+/* ---- memory-bound passes on NHWC bf16 frames ---------------------------------------- */
+
+/* An NHWC bf16 image set inside a flat [rows][ld] buffer: pixel (n,y,x), channel c lives at
+ * row (n*hp + y + oy)*wp + (x + ox), column chan_off + c. */
+typedef struct irc_view {
+    const void* ptr;
+    long long ld;
+    int chan_off, hp, wp, oy, ox;
+} irc_view;
+
+/* row_img[q] = image index for rows inside [y0,y1)x[x0,x1) of each hp x wp image, else -1. */
+int irc_row_index(short* row_img, int n_img, int hp, int wp, int y0, int y1, int x0, int x1, void* stream);
+
+/* InstanceNorm statistics (nn.InstanceNorm2d, irc:161): stats[n][c] = (sum, sum of squares)
+ * over the H x W pixels of view z. */
+int irc_in_stats(const irc_view* z, int C, int n_img, int H, int W, float* stats, void* stream);
+
+/* Separable table gather into a frame:
+ *   dst[n,Y,X,:] = halo( sum_ij ty_w[y][i] tx_w[x][j] * pre(src)[n, ty_idx[y][i], tx_idx[x][j], :] (+ src2[same]) + res[n,y,x,:] )
+ * pre = InstanceNorm with `stats` (if given) followed by `act`.  NULL tables = identity.
+ * With binomial / bilinear tables this is Downsample (irc:307-310) and UpsampleAA
+ * (irc:350-355) fused with the preceding norm+activation; with identity tables it is the
+ * InstanceNorm/ReLU/residual apply of ResnetBlock (irc:417-418); with fold tables it is the
+ * backward of ReflectionPad2d.  halo_mode: 0 zero ring, 1 reflect ring of width `pad`.
+ * dst_s2d: write the zero-padded image as 2x2 space-to-depth blocks (stride-2 conv operand). */
+typedef struct irc_gather_args {
+    irc_view src, src2, res, dst;
+    int C, n_img;
+    const float* stats; float cnt, eps; int act; float slope;
+    const int* ty_idx; const float* ty_w; int ky;
+    const int* tx_idx; const float* tx_w; int kx;
+    int H, W, pad, halo_mode, dst_s2d;
+} irc_gather_args;
+int irc_gather(const irc_gather_args* args, void* stream);
+
+/* InstanceNorm(+activation) backward (autograd of irc:161 + ReLU/LeakyReLU inside
+ * loss.backward()).  g = table gather of (g1 + g2); see elementwise.cu. */
+typedef struct irc_in_bwd_args {
+    irc_view z, g1, g2, dz;
+    int C, n_img, H, W;
+    const float* stats; float cnt, eps; int act; float slope;
+    const int* ty_idx; const float* ty_w; int ky;
+    const int* tx_idx; const float* tx_w; int kx;
+    float* bsum;            /* [n][C][2] workspace */
+} irc_in_bwd_args;
+int irc_in_bwd_reduce(const irc_in_bwd_args* args, void* stream);
+int irc_in_bwd_apply(const irc_in_bwd_args* args, void* stream);
+
+/* nn.MaxPool2d(2,2) of the VGG trunk (torchvision vgg16.features[4], [9]; irc:664) and its
+ * backward fused with the mask of the ReLU that precedes it. */
+int irc_maxpool2(const irc_view* src, const irc_view* dst, int C, int n_img, int Ho, int Wo, void* stream);
+int irc_maxpool2_bwd(const irc_view* src, const irc_view* g, const irc_view* dsrc, int C, int n_img, int Ho, int Wo, void* stream);
+
+/* out[c] = sum_rows a[row][chan_off + c]  (bias gradients) */
+int irc_colsum(const void* a, long long rows, long long ld, int chan_off, int C, float* out, void* stream);
+
+/* ---- degenerate convolutions (tiny K or tiny N) --------------------------------------- */
+
+/* im2col of a small-channel fp32 NCHW input (optionally two tensors concatenated on the
+ * channel axis, optionally a per-channel affine) into a bf16 [rows][64] operand, column
+ * (r*k+s)*C + c.  Feeds inc (irc:458-463), D model.0 on cat[ir,rgb] (irc:600, :1639-1643) and
+ * VGG conv1_1 incl. its input normalisation (irc:679-682) as one-tap GEMMs.
+ * row_mode: 0 rows=(n,oy,ox); 1 framed with a one-pixel ring; 2 ring + 2x2 sub-pixel order
+ * (so that the [rows][64] GEMM output is the space-to-depth operand of a stride-2 conv). */
+typedef struct irc_im2col_args {
+    const float* src1; int c1;
+    const float* src2; int c2;
+    const float* scale; const float* shift;
+    int n_img, H, W, k, stride, pad, pad_mode, Ho, Wo, row_mode;
+    void* dst;
+    short* row_img;         /* optional: receives the live-row table of this row order */
+} irc_im2col_args;
+long long irc_im2col_rows(int row_mode, int n_img, int Ho, int Wo);
+int irc_im2col(const irc_im2col_args* args, void* stream);
+
+/* Transpose of irc_im2col (zero padding only): out[n][c][y][x] (+)= sum de[row][(r*k+s)*C+c]. */
+typedef struct irc_col2im_args {
+    const void* de; long long ld;
+    int C, c_first, c_out, n_img, H, W, k, stride, pad, Ho, Wo, row_mode;
+    const float* scale;
+    float* out; int accumulate;
+} irc_col2im_args;
+int irc_col2im(const irc_col2im_args* args, void* stream);
+
+/* Shifted tap reduction / expansion around a GEMM over one kernel axis:
+ *   reduce: out[n][co][y][x] = act(bias[co] + sum_j P[q(n,y,x) + shifts[j]][j*nco + co]), act 3 = tanh
+ *   expand: E[q][j*nco + co] = g[pixel(q - shifts[j])][co] * (1 - y^2 if y given); dbias[co] = sum g'
+ * outc + tanh (irc:527-531) and D model.11 (irc:629), forward and backward. */
+typedef struct irc_tap_args {
+    int nshift, nco;
+    int shifts[IRC_MAX_TAPS];
+    int n_img, H, W, hp, wp, oy, ox;
+} irc_tap_args;
+int irc_tap_reduce(const irc_tap_args* t, const float* P, long long ldp, const float* bias, int act, float* out, void* stream);
+int irc_tap_expand(const irc_tap_args* t, const float* g, const float* y, void* E, float* dbias, void* stream);
+
+/* ---- losses (fp32 NCHW) --------------------------------------------------------------- */
+
+/* One pass over fake/target: sums[0..2] += (sum|f-t|, sum|d_rows f|, sum|d_cols f|) and
+ * dfake = w_l1*sign(f-t) + TV sign stencils scaled by w_tvv / w_tvh.  nn.L1Loss (irc:1664) and
+ * tv_loss (irc:686-694) with their autograd.  target NULL = TV only; dfake NULL = values only. */
+int irc_pixel_loss(const float* fake, const float* target, int n_img, int C, int H, int W, float w_l1, float w_tvv, float w_tvh,
+                   float* sums, float* dfake, void* stream);
+
+/* ssim_loss_torch (irc:714-750): 11-tap Gaussian separable window, zero padding 5.  Inputs are
+ * mapped x = img*scale + shift first (irc:1675-1676 uses (x+1)/2).  fwd: sums[n] += sum of the
+ * SSIM map of image n, and (if ga != NULL) the maps dS/dmu1, dS/dE[x^2], dS/dE[xy]; bwd:
+ * dimg1 (+)= coef*scale*(w*ga + 2x w*gb + y w*gc). */
+int irc_ssim_fwd(const float* img1, const float* img2, int n_img, int C, int H, int W, float scale, float shift, const float* window11,
+                 float* sums, float* ga, float* gb, float* gc, void* stream);
+int irc_ssim_bwd(const float* img1, const float* img2, int n_img, int C, int H, int W, float scale, float shift, const float* window11,
+                 const float* ga, const float* gb, const float* gc, float coef, float* dimg1, int accumulate, void* stream);
+
+/* Hinge discriminator loss (irc:1647-1649; mode 0) and generator GAN term (irc:1662; mode 1)
+ * with their gradients w.r.t. the score maps. */
+int irc_hinge(const float* pred, long long n_total, long long n_real, int mode, float w_real, float w_fake, float* sums, float* dpred, void* stream);
+
+/* F.l1_loss(vgg(fake), vgg(rgb)) (irc:1667-1669) on the bf16 feature frame holding both
+ * halves; writes the gradient w.r.t. the pre-ReLU conv3_3 output of the fake half. */
+int irc_feat_l1(const void* feat, long long rows_half, long long ld, int C, float w, float* sums, void* dz, long long ld_dz, void* stream);
+
+/* tensor_to_rgb_image + compute_metrics core (irc:865-876, irc:1197-1205), batched on device:
+ * u8[n][y][x][c] = trunc(clip((fake+1)/2,0,1)*255); sums[n] = (sum|u8/255-gt|, sum(u8/255-gt)^2). */
+int irc_quantize_metrics(const float* fake, const float* gt, int n_img, int C, int H, int W, unsigned char* u8, double* sums, void* stream);
+
+/* ---- optimizer / parameter layout ------------------------------------------------------ */
+
+/* torch.optim.Adam step (irc:1651, :1681) over a flat arena.
+ * hyper (device) = {lr, beta1, beta2, eps, 1-beta1^t, 1-beta2^t, grad_scale}. */
+int irc_adam(float* p, const float* g, float* m, float* v, long long n, const float* hyper, void* stream);
+/* dst[i] = bf16(map[i] >= 0 ? src[map[i]] : 0): OIHW fp32 parameters -> packed GEMM operands. */
+int irc_pack_bf16(const float* src, const int* map, long long n, void* dst, void* stream);
+/* dst[i] = sum_s src[s*split_stride + map[i]]: split weight-gradient partials -> OIHW fp32. */
+int irc_gather_sum(const float* src, const int* map, long long n, int splits, long long split_stride, float* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

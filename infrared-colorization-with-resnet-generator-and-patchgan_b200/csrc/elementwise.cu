@@ -1,0 +1,489 @@
+// Memory-bound passes on NHWC bf16 frames: InstanceNorm statistics / apply / backward,
+// separable table stencils (anti-aliased Downsample and UpsampleAA, halo folding), all
+// vectorised 8 channels (16 bytes) per thread and coalesced along the channel axis.
+#include "irc_common.cuh"
+#include "../../include/irc_b200.h"
+
+using namespace irc;
+
+namespace {
+
+struct View {
+    const bf16* p; long long ld; int off, hp, wp, oy, ox;
+    __device__ __forceinline__ long long row(int n, int y, int x) const {
+        return (long long)(n * hp + y + oy) * wp + (x + ox);
+    }
+    __device__ __forceinline__ const bf16* at(int n, int y, int x, int c) const {
+        return p + row(n, y, x) * ld + off + c;
+    }
+};
+
+inline View mk(const irc_view& v) {
+    View r; r.p = (const bf16*)v.ptr; r.ld = v.ld; r.off = v.chan_off; r.hp = v.hp; r.wp = v.wp; r.oy = v.oy; r.ox = v.ox;
+    return r;
+}
+
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    if (i < 0) i = -i;
+    if (i > n - 1) i = 2 * (n - 1) - i;
+    return i;
+}
+// mean / rstd of 8 channels from the (sum, sum of squares) pairs
+__device__ __forceinline__ void moments8(const float* stats, int n, int C, int c, float inv_cnt, float eps, float (&mu)[8], float (&rs)[8]) {
+    const float4* sp = reinterpret_cast<const float4*>(stats + ((long long)n * C + c) * 2);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float4 s = __ldg(sp + g);
+        const float m0 = s.x * inv_cnt, m1 = s.z * inv_cnt;
+        mu[g * 2] = m0; mu[g * 2 + 1] = m1;
+        rs[g * 2] = rsqrtf(fmaxf(s.y * inv_cnt - m0 * m0, 0.f) + eps);
+        rs[g * 2 + 1] = rsqrtf(fmaxf(s.w * inv_cnt - m1 * m1, 0.f) + eps);
+    }
+}
+__device__ __forceinline__ float actf(float v, int act, float slope) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v > 0.f ? v : v * slope;
+    return v;
+}
+__device__ __forceinline__ float dactf(float v, int act, float slope) {
+    if (act == 1) return v > 0.f ? 1.f : 0.f;
+    if (act == 2) return v > 0.f ? 1.f : slope;
+    return 1.f;
+}
+
+// ---------------------------------------------------------------------------------
+// row index table: row_img[q] = n for live rows, -1 for the padding ring
+// ---------------------------------------------------------------------------------
+__global__ void row_index_kernel(short* out, int n_img, int hp, int wp, int y0, int y1, int x0, int x1) {
+    const long long total = (long long)n_img * hp * wp;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(q % wp);
+        const int y = (int)((q / wp) % hp);
+        const int n = (int)(q / ((long long)wp * hp));
+        out[q] = (y >= y0 && y < y1 && x >= x0 && x < x1) ? (short)n : (short)-1;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// per-(image, channel) sum and sum of squares over the H x W pixels of a view
+// block = (C/8) channel vectors x L pixel lanes; grid = (chunks, N)
+// ---------------------------------------------------------------------------------
+__global__ void in_stats_kernel(View z, int C, int H, int W, float* stats) {
+    extern __shared__ float sh[];
+    const int C8 = C >> 3;
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int n = blockIdx.y;
+    const int P = H * W;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ss[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (lane < L) {
+        for (int pix = blockIdx.x * L + lane; pix < P; pix += gridDim.x * L) {
+            float v[8];
+            load8(z.at(n, pix / W, pix % W, cv * 8), v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s[j] += v[j]; ss[j] += v[j] * v[j]; }
+        }
+    }
+    // reduce over pixel lanes through shared memory
+    float* shs = sh;                          // [L][C8][16]
+    if (lane < L) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { shs[(lane * C8 + cv) * 16 + j * 2] = s[j]; shs[(lane * C8 + cv) * 16 + j * 2 + 1] = ss[j]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C8 * 16; i += blockDim.x) {
+        float a = 0.f;
+        for (int l = 0; l < L; ++l) a += shs[l * C8 * 16 + i];
+        atomicAdd(stats + (long long)n * C * 2 + i, a);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// gather: dst = halo( sum_ij wy_i wx_j * pre(src)[ty_i, tx_j] (+ src2[...]) + res )
+// ---------------------------------------------------------------------------------
+struct GatherP {
+    View src, src2, res, dst;
+    int has2, has_res, C, n_img;
+    const float* stats; float inv_cnt, eps; int act; float slope;
+    const int* ty_idx; const float* ty_w; int ky;
+    const int* tx_idx; const float* tx_w; int kx;
+    int H, W, pad, halo_mode, dst_s2d;
+};
+
+__global__ void gather_kernel(const GatherP p) {
+    const int C8 = p.C >> 3;
+    const int Hp = p.H + 2 * p.pad, Wp = p.W + 2 * p.pad;
+    const long long total = (long long)p.n_img * Hp * Wp * C8;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C8) * 8;
+        long long pix = idx / C8;
+        const int X = (int)(pix % Wp); pix /= Wp;
+        const int Y = (int)(pix % Hp);
+        const int n = (int)(pix / Hp);
+        int y = Y - p.pad, x = X - p.pad;
+        const bool halo = y < 0 || y >= p.H || x < 0 || x >= p.W;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (!halo || p.halo_mode == 1) {
+            if (halo) { y = reflect_idx(y, p.H); x = reflect_idx(x, p.W); }
+            float mu[8], rs[8];
+            if (p.stats) moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+            for (int i = 0; i < p.ky; ++i) {
+                const int iy = p.ty_idx ? __ldg(p.ty_idx + y * p.ky + i) : y;
+                const float wy = p.ty_w ? __ldg(p.ty_w + y * p.ky + i) : 1.f;
+                if (wy == 0.f) continue;
+                for (int j = 0; j < p.kx; ++j) {
+                    const int ix = p.tx_idx ? __ldg(p.tx_idx + x * p.kx + j) : x;
+                    const float w = wy * (p.tx_w ? __ldg(p.tx_w + x * p.kx + j) : 1.f);
+                    if (w == 0.f) continue;
+                    float v[8];
+                    load8(p.src.at(n, iy, ix, c), v);
+                    if (p.stats) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] = actf((v[k] - mu[k]) * rs[k], p.act, p.slope);
+                    } else if (p.act) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] = actf(v[k], p.act, p.slope);
+                    }
+                    if (p.has2) {
+                        float u[8];
+                        load8(p.src2.at(n, iy, ix, c), u);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] += u[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] += w * v[k];
+                }
+            }
+            if (p.has_res) {
+                float u[8];
+                load8(p.res.at(n, y, x, c), u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += u[k];
+            }
+        }
+        bf16* d;
+        if (p.dst_s2d) {
+            // padded pixel (Y, X) -> 2x2 block (Y/2, X/2), channel group (Y&1)*2 + (X&1)
+            const long long r = ((long long)n * (Hp >> 1) + (Y >> 1)) * (Wp >> 1) + (X >> 1);
+            d = const_cast<bf16*>(p.dst.p) + r * p.dst.ld + p.dst.off + ((Y & 1) * 2 + (X & 1)) * p.C + c;
+        } else {
+            d = const_cast<bf16*>(p.dst.p) + ((long long)(n * p.dst.hp + Y - p.pad + p.dst.oy) * p.dst.wp + (X - p.pad + p.dst.ox)) * p.dst.ld + p.dst.off + c;
+        }
+        store8(d, acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// InstanceNorm(+activation) backward.
+//   g      = sum_ij wy wx (gsrc + gsrc2)[ty_i, tx_j]      (gradient w.r.t. the activated output)
+//   gd     = g * act'(xhat),  xhat = (z - mu) * rstd
+//   reduce : bsum[n][c] = (sum gd, sum gd*xhat)
+//   apply  : dz = rstd * (gd - bsum0/cnt - xhat * bsum1/cnt)
+// Without stats: dz = g * act'(z) (layers without a norm).
+// ---------------------------------------------------------------------------------
+struct InBwdP {
+    View z, g1, g2, dz;
+    int has2, C, n_img, H, W;
+    const float* stats; float inv_cnt, eps; int act; float slope;
+    const int* ty_idx; const float* ty_w; int ky;
+    const int* tx_idx; const float* tx_w; int kx;
+    float* bsum;
+};
+
+__device__ __forceinline__ void bwd_gather(const InBwdP& p, int n, int y, int x, int c, float (&g)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = 0.f;
+    for (int i = 0; i < p.ky; ++i) {
+        const int iy = p.ty_idx ? __ldg(p.ty_idx + y * p.ky + i) : y;
+        const float wy = p.ty_w ? __ldg(p.ty_w + y * p.ky + i) : 1.f;
+        if (wy == 0.f) continue;
+        for (int j = 0; j < p.kx; ++j) {
+            const int ix = p.tx_idx ? __ldg(p.tx_idx + x * p.kx + j) : x;
+            const float w = wy * (p.tx_w ? __ldg(p.tx_w + x * p.kx + j) : 1.f);
+            if (w == 0.f) continue;
+            float v[8];
+            load8(p.g1.at(n, iy, ix, c), v);
+            if (p.has2) {
+                float u[8];
+                load8(p.g2.at(n, iy, ix, c), u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] += u[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] += w * v[k];
+        }
+    }
+}
+
+__global__ void in_bwd_reduce_kernel(const InBwdP p) {
+    extern __shared__ float sh[];
+    const int C8 = p.C >> 3;
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int n = blockIdx.y, c = cv * 8;
+    const int P = p.H * p.W;
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (lane < L) {
+        float mu[8], rs[8];
+        moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+        for (int pix = blockIdx.x * L + lane; pix < P; pix += gridDim.x * L) {
+            const int y = pix / p.W, x = pix % p.W;
+            float g[8], zv[8];
+            bwd_gather(p, n, y, x, c, g);
+            load8(p.z.at(n, y, x, c), zv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float xh = (zv[k] - mu[k]) * rs[k];
+                const float gd = g[k] * dactf(xh, p.act, p.slope);
+                s1[k] += gd; s2[k] += gd * xh;
+            }
+        }
+    }
+    if (lane < L) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sh[(lane * C8 + cv) * 16 + j * 2] = s1[j]; sh[(lane * C8 + cv) * 16 + j * 2 + 1] = s2[j]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C8 * 16; i += blockDim.x) {
+        float a = 0.f;
+        for (int l = 0; l < L; ++l) a += sh[l * C8 * 16 + i];
+        atomicAdd(p.bsum + (long long)n * p.C * 2 + i, a);
+    }
+}
+
+__global__ void in_bwd_apply_kernel(const InBwdP p) {
+    const int C8 = p.C >> 3;
+    const long long total = (long long)p.n_img * p.H * p.W * C8;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C8) * 8;
+        long long pix = idx / C8;
+        const int x = (int)(pix % p.W); pix /= p.W;
+        const int y = (int)(pix % p.H);
+        const int n = (int)(pix / p.H);
+        float g[8], zv[8], o[8];
+        bwd_gather(p, n, y, x, c, g);
+        load8(p.z.at(n, y, x, c), zv);
+        if (p.stats) {
+            float mu[8], rs[8];
+            moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+            const float4* bp = reinterpret_cast<const float4*>(p.bsum + ((long long)n * p.C + c) * 2);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 b = __ldg(bp + q);
+                const float bs1[2] = {b.x, b.z}, bs2[2] = {b.y, b.w};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = q * 2 + h;
+                    const float xh = (zv[k] - mu[k]) * rs[k];
+                    const float gd = g[k] * dactf(xh, p.act, p.slope);
+                    o[k] = rs[k] * (gd - bs1[h] * p.inv_cnt - xh * bs2[h] * p.inv_cnt);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = g[k] * dactf(zv[k], p.act, p.slope);
+        }
+        store8(const_cast<bf16*>(p.dz.at(n, y, x, c)), o);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// 2x2 max pool (VGG trunk, irc:664) on frames, and its backward fused with the ReLU mask
+// ---------------------------------------------------------------------------------
+__global__ void maxpool_kernel(View src, View dst, int C, int n_img, int Ho, int Wo) {
+    const int C8 = C >> 3;
+    const long long total = (long long)n_img * Ho * Wo * C8;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C8) * 8;
+        long long pix = idx / C8;
+        const int x = (int)(pix % Wo); pix /= Wo;
+        const int y = (int)(pix % Ho);
+        const int n = (int)(pix / Ho);
+        float m[8], v[8];
+        load8(src.at(n, 2 * y, 2 * x, c), m);
+#pragma unroll
+        for (int t = 1; t < 4; ++t) {
+            load8(src.at(n, 2 * y + (t >> 1), 2 * x + (t & 1), c), v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
+        }
+        store8(const_cast<bf16*>(dst.at(n, y, x, c)), m);
+    }
+}
+// dsrc[n, y, x] = g[n, y/2, x/2] if src[n,y,x] is the first maximum of its window and src > 0, else 0
+__global__ void maxpool_bwd_kernel(View src, View g, View dsrc, int C, int n_img, int Ho, int Wo) {
+    const int C8 = C >> 3;
+    const long long total = (long long)n_img * Ho * Wo * C8;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C8) * 8;
+        long long pix = idx / C8;
+        const int x = (int)(pix % Wo); pix /= Wo;
+        const int y = (int)(pix % Ho);
+        const int n = (int)(pix / Ho);
+        float v[4][8], gv[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) load8(src.at(n, 2 * y + (t >> 1), 2 * x + (t & 1), c), v[t]);
+        load8(g.at(n, y, x, c), gv);
+        int arg[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int a = 0; float m = v[0][k];
+#pragma unroll
+            for (int t = 1; t < 4; ++t) if (v[t][k] > m) { m = v[t][k]; a = t; }
+            arg[k] = m > 0.f ? a : -1;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = arg[k] == t ? gv[k] : 0.f;
+            store8(const_cast<bf16*>(dsrc.at(n, 2 * y + (t >> 1), 2 * x + (t & 1), c)), o);
+        }
+    }
+}
+
+// column sums of a bf16 [rows][ld] matrix slice -> fp32 [C] (bias gradients)
+__global__ void colsum_kernel(const bf16* a, long long rows, long long ld, int off, int C, float* out) {
+    const int c = blockIdx.y * 32 + (threadIdx.x & 31);
+    const int lane_r = threadIdx.x >> 5, R = blockDim.x >> 5;
+    float s = 0.f;
+    if (c < C)
+        for (long long r = blockIdx.x * (long long)R + lane_r; r < rows; r += (long long)gridDim.x * R) s += __bfloat162float(a[r * ld + off + c]);
+    __shared__ float sh[32][33];
+    sh[lane_r][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (lane_r == 0 && c < C) {
+        float t = 0.f;
+        for (int i = 0; i < R; ++i) t += sh[i][threadIdx.x & 31];
+        atomicAdd(out + c, t);
+    }
+}
+
+int grid_for(long long total, int threads) {
+    long long b = (total + threads - 1) / threads;
+    const long long cap = (long long)irc_num_sms() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+int check_view(const irc_view& v, const char* what) {
+    if (!v.ptr) return irc_set_error(IRC_ERR_BAD_ARG, "%s: null view", what);
+    if (((uintptr_t)v.ptr & 15) || (v.ld % 8) || (v.chan_off % 8)) return irc_set_error(IRC_ERR_BAD_ARG, "%s: view must be 16-byte aligned (ld %% 8, chan_off %% 8)", what);
+    return IRC_OK;
+}
+
+// block shape for the per-(n,c) reductions
+void reduce_shape(int C, int P, int n_img, int& threads, int& L, int& chunks, size_t& smem) {
+    const int C8 = C / 8;
+    L = 256 / C8; if (L < 1) L = 1;
+    threads = L * C8;
+    long long want = ((long long)irc_num_sms() * 4 + n_img - 1) / n_img;
+    long long maxc = (P + L - 1) / L;
+    chunks = (int)(want < maxc ? want : maxc);
+    if (chunks < 1) chunks = 1;
+    smem = (size_t)L * C8 * 16 * sizeof(float);
+}
+
+}  // namespace
+
+extern "C" int irc_row_index(short* row_img, int n_img, int hp, int wp, int y0, int y1, int x0, int x1, void* stream) {
+    if (!row_img) return irc_set_error(IRC_ERR_BAD_ARG, "irc_row_index: null");
+    const long long total = (long long)n_img * hp * wp;
+    row_index_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(row_img, n_img, hp, wp, y0, y1, x0, x1);
+    return irc_check_launch("irc_row_index");
+}
+
+extern "C" int irc_in_stats(const irc_view* z, int C, int n_img, int H, int W, float* stats, void* stream) {
+    int rc = check_view(*z, "irc_in_stats"); if (rc) return rc;
+    if (C % 8 || C > 2048) return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_stats: C must be a multiple of 8");
+    cudaMemsetAsync(stats, 0, sizeof(float) * 2 * C * n_img, (cudaStream_t)stream);
+    int threads, L, chunks; size_t smem;
+    reduce_shape(C, H * W, n_img, threads, L, chunks, smem);
+    in_stats_kernel<<<dim3(chunks, n_img), threads, smem, (cudaStream_t)stream>>>(mk(*z), C, H, W, stats);
+    return irc_check_launch("irc_in_stats");
+}
+
+extern "C" int irc_gather(const irc_gather_args* a, void* stream) {
+    int rc = check_view(a->src, "irc_gather src"); if (rc) return rc;
+    rc = check_view(a->dst, "irc_gather dst"); if (rc) return rc;
+    if (a->C % 8) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather: C %% 8");
+    GatherP p;
+    p.src = mk(a->src); p.dst = mk(a->dst);
+    p.has2 = a->src2.ptr != nullptr; if (p.has2) { rc = check_view(a->src2, "irc_gather src2"); if (rc) return rc; p.src2 = mk(a->src2); }
+    p.has_res = a->res.ptr != nullptr; if (p.has_res) { rc = check_view(a->res, "irc_gather res"); if (rc) return rc; p.res = mk(a->res); }
+    p.C = a->C; p.n_img = a->n_img;
+    p.stats = a->stats; p.inv_cnt = a->cnt > 0 ? 1.f / a->cnt : 0.f; p.eps = a->eps; p.act = a->act; p.slope = a->slope;
+    p.ty_idx = a->ty_idx; p.ty_w = a->ty_w; p.ky = a->ky > 0 ? a->ky : 1;
+    p.tx_idx = a->tx_idx; p.tx_w = a->tx_w; p.kx = a->kx > 0 ? a->kx : 1;
+    p.H = a->H; p.W = a->W; p.pad = a->pad; p.halo_mode = a->halo_mode; p.dst_s2d = a->dst_s2d;
+    if (p.dst_s2d && (((p.H + 2 * p.pad) | (p.W + 2 * p.pad)) & 1)) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather: space-to-depth needs even padded extents");
+    const long long total = (long long)p.n_img * (p.H + 2 * p.pad) * (p.W + 2 * p.pad) * (p.C / 8);
+    gather_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return irc_check_launch("irc_gather");
+}
+
+static int fill_bwd(const irc_in_bwd_args* a, InBwdP& p) {
+    int rc = check_view(a->z, "irc_in_bwd z"); if (rc) return rc;
+    rc = check_view(a->g1, "irc_in_bwd g1"); if (rc) return rc;
+    p.z = mk(a->z); p.g1 = mk(a->g1);
+    p.has2 = a->g2.ptr != nullptr; if (p.has2) { rc = check_view(a->g2, "irc_in_bwd g2"); if (rc) return rc; p.g2 = mk(a->g2); }
+    if (a->C % 8) return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_bwd: C %% 8");
+    p.C = a->C; p.n_img = a->n_img; p.H = a->H; p.W = a->W;
+    p.stats = a->stats; p.inv_cnt = a->cnt > 0 ? 1.f / a->cnt : 0.f; p.eps = a->eps; p.act = a->act; p.slope = a->slope;
+    p.ty_idx = a->ty_idx; p.ty_w = a->ty_w; p.ky = a->ky > 0 ? a->ky : 1;
+    p.tx_idx = a->tx_idx; p.tx_w = a->tx_w; p.kx = a->kx > 0 ? a->kx : 1;
+    p.bsum = a->bsum;
+    return IRC_OK;
+}
+
+extern "C" int irc_in_bwd_reduce(const irc_in_bwd_args* a, void* stream) {
+    InBwdP p; int rc = fill_bwd(a, p); if (rc) return rc;
+    if (!p.stats || !p.bsum) return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_bwd_reduce: stats and bsum required");
+    cudaMemsetAsync(p.bsum, 0, sizeof(float) * 2 * p.C * p.n_img, (cudaStream_t)stream);
+    int threads, L, chunks; size_t smem;
+    reduce_shape(p.C, p.H * p.W, p.n_img, threads, L, chunks, smem);
+    in_bwd_reduce_kernel<<<dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream>>>(p);
+    return irc_check_launch("irc_in_bwd_reduce");
+}
+
+extern "C" int irc_in_bwd_apply(const irc_in_bwd_args* a, void* stream) {
+    InBwdP p; int rc = fill_bwd(a, p); if (rc) return rc;
+    rc = check_view(a->dz, "irc_in_bwd dz"); if (rc) return rc;
+    p.dz = mk(a->dz);
+    if (p.stats && !p.bsum) return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_bwd_apply: bsum required with stats");
+    const long long total = (long long)p.n_img * p.H * p.W * (p.C / 8);
+    in_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return irc_check_launch("irc_in_bwd_apply");
+}
+
+extern "C" int irc_maxpool2(const irc_view* src, const irc_view* dst, int C, int n_img, int Ho, int Wo, void* stream) {
+    int rc = check_view(*src, "irc_maxpool2 src"); if (rc) return rc;
+    rc = check_view(*dst, "irc_maxpool2 dst"); if (rc) return rc;
+    const long long total = (long long)n_img * Ho * Wo * (C / 8);
+    maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(*src), mk(*dst), C, n_img, Ho, Wo);
+    return irc_check_launch("irc_maxpool2");
+}
+
+extern "C" int irc_maxpool2_bwd(const irc_view* src, const irc_view* g, const irc_view* dsrc, int C, int n_img, int Ho, int Wo, void* stream) {
+    int rc = check_view(*src, "irc_maxpool2_bwd src"); if (rc) return rc;
+    rc = check_view(*g, "irc_maxpool2_bwd g"); if (rc) return rc;
+    rc = check_view(*dsrc, "irc_maxpool2_bwd dsrc"); if (rc) return rc;
+    const long long total = (long long)n_img * Ho * Wo * (C / 8);
+    maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(*src), mk(*g), mk(*dsrc), C, n_img, Ho, Wo);
+    return irc_check_launch("irc_maxpool2_bwd");
+}
+
+extern "C" int irc_colsum(const void* a, long long rows, long long ld, int chan_off, int C, float* out, void* stream) {
+    if (!a || !out) return irc_set_error(IRC_ERR_BAD_ARG, "irc_colsum: null");
+    cudaMemsetAsync(out, 0, sizeof(float) * C, (cudaStream_t)stream);
+    long long bx = (rows + 31) / 32; if (bx > irc_num_sms() * 4) bx = irc_num_sms() * 4; if (bx < 1) bx = 1;
+    colsum_kernel<<<dim3((unsigned)bx, (C + 31) / 32), 1024, 0, (cudaStream_t)stream>>>((const bf16*)a, rows, ld, chan_off, C, out);
+    return irc_check_launch("irc_colsum");
+}

@@ -1,0 +1,270 @@
+// Loss kernels on fp32 NCHW images: fused L1 + TV (value and gradient in one pass),
+// Gaussian-window SSIM forward/backward as shared-memory separable stencils, hinge / GAN
+// terms, VGG feature L1, and the test-mode quantise + MAE/MSE pass.
+#include "irc_common.cuh"
+#include "../../include/irc_b200.h"
+
+using namespace irc;
+
+namespace {
+
+__device__ __forceinline__ float sgnf(float v) { return (v > 0.f) - (v < 0.f); }
+
+// ---------------------------------------------------------------- L1 + TV
+// sums[0] += sum|f-r|, sums[1] += sum|f[y+1]-f[y]|, sums[2] += sum|f[x+1]-f[x]|
+// dfake = w_l1*sign(f-r) + w_tvv*d(TV_v) + w_tvh*d(TV_h)      (irc:686-694, irc:1664, :1672)
+__global__ void pixel_loss_kernel(const float* __restrict__ f, const float* __restrict__ r, long long planes, int H, int W,
+                                  float w_l1, float w_tvv, float w_tvh, float* sums, float* dfake) {
+    __shared__ float sh[32];
+    const long long total = planes * H * W;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        const int y = (int)((i / W) % H);
+        const float v = f[i];
+        float g = 0.f;
+        if (r) { const float d = v - r[i]; a0 += fabsf(d); g += w_l1 * sgnf(d); }
+        if (y + 1 < H) { const float d = f[i + W] - v; a1 += fabsf(d); g -= w_tvv * sgnf(d); }
+        if (y > 0) g += w_tvv * sgnf(v - f[i - W]);
+        if (x + 1 < W) { const float d = f[i + 1] - v; a2 += fabsf(d); g -= w_tvh * sgnf(d); }
+        if (x > 0) g += w_tvh * sgnf(v - f[i - 1]);
+        if (dfake) dfake[i] = g;
+    }
+    a0 = block_sum(a0, sh); if (threadIdx.x == 0) atomicAdd(sums + 0, a0);
+    a1 = block_sum(a1, sh); if (threadIdx.x == 0) atomicAdd(sums + 1, a1);
+    a2 = block_sum(a2, sh); if (threadIdx.x == 0) atomicAdd(sums + 2, a2);
+}
+
+// ---------------------------------------------------------------- SSIM (irc:714-750)
+constexpr int TW = 32, TH = 16, R = 5, K = 11;
+constexpr int LW = TW + 2 * R, LH = TH + 2 * R;
+
+struct Win { float g[K]; };
+
+// pass 1: per-pixel SSIM value summed per image + the three sensitivity maps
+__global__ void __launch_bounds__(256)
+ssim_fwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int C, int H, int W, float scale, float shift,
+                Win win, float* sums, float* Ga, float* Gb, float* Gc) {
+    __shared__ float xs[LH][LW], ys[LH][LW];
+    __shared__ float hs[5][LH][TW];
+    __shared__ float red[32];
+    const int plane = blockIdx.z;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const float* p1 = img1 + (long long)plane * H * W;
+    const float* p2 = img2 + (long long)plane * H * W;
+    for (int i = threadIdx.x; i < LH * LW; i += blockDim.x) {
+        const int ly = i / LW, lx = i % LW;
+        const int y = y0 + ly - R, x = x0 + lx - R;
+        float a = 0.f, b = 0.f;
+        if (y >= 0 && y < H && x >= 0 && x < W) { a = p1[(long long)y * W + x] * scale + shift; b = p2[(long long)y * W + x] * scale + shift; }
+        xs[ly][lx] = a; ys[ly][lx] = b;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < LH * TW; i += blockDim.x) {
+        const int ly = i / TW, lx = i % TW;
+        float m1 = 0, m2 = 0, e11 = 0, e22 = 0, e12 = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float a = xs[ly][lx + k], b = ys[ly][lx + k], w = win.g[k];
+            m1 += w * a; m2 += w * b; e11 += w * a * a; e22 += w * b * b; e12 += w * a * b;
+        }
+        hs[0][ly][lx] = m1; hs[1][ly][lx] = m2; hs[2][ly][lx] = e11; hs[3][ly][lx] = e22; hs[4][ly][lx] = e12;
+    }
+    __syncthreads();
+    float local = 0.f;
+    for (int i = threadIdx.x; i < TH * TW; i += blockDim.x) {
+        const int ly = i / TW, lx = i % TW;
+        const int y = y0 + ly, x = x0 + lx;
+        if (y >= H || x >= W) continue;
+        float m1 = 0, m2 = 0, e11 = 0, e22 = 0, e12 = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float w = win.g[k];
+            m1 += w * hs[0][ly + k][lx]; m2 += w * hs[1][ly + k][lx]; e11 += w * hs[2][ly + k][lx];
+            e22 += w * hs[3][ly + k][lx]; e12 += w * hs[4][ly + k][lx];
+        }
+        const float C1 = 1e-4f, C2 = 9e-4f;
+        const float s1 = e11 - m1 * m1, s2 = e22 - m2 * m2, s12 = e12 - m1 * m2;
+        const float A1 = 2.f * m1 * m2 + C1, A2 = 2.f * s12 + C2, B1 = m1 * m1 + m2 * m2 + C1, B2 = s1 + s2 + C2;
+        const float inv = __fdiv_rn(1.f, B1 * B2);
+        const float S = A1 * A2 * inv;
+        local += S;
+        if (Ga) {
+            const long long o = (long long)plane * H * W + (long long)y * W + x;
+            const float dS_de11 = -__fdiv_rn(S, B2);
+            const float dS_de12 = 2.f * A1 * inv;
+            Ga[o] = 2.f * m2 * A2 * inv - 2.f * m1 * __fdiv_rn(S, B1) - 2.f * m1 * dS_de11 - m2 * dS_de12;
+            Gb[o] = dS_de11;
+            Gc[o] = dS_de12;
+        }
+    }
+    local = block_sum(local, red);
+    if (threadIdx.x == 0) atomicAdd(sums + plane / C, local);
+}
+
+// pass 2: dimg1 (+)= coef * ( w*Ga + 2 x (w*Gb) + y (w*Gc) )
+__global__ void __launch_bounds__(256)
+ssim_bwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int H, int W, float scale, float shift, Win win,
+                const float* __restrict__ Ga, const float* __restrict__ Gb, const float* __restrict__ Gc, float coef, float* dimg, int accumulate) {
+    __shared__ float gs[3][LH][LW];
+    __shared__ float hs[3][LH][TW];
+    const int plane = blockIdx.z;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const long long base = (long long)plane * H * W;
+    for (int i = threadIdx.x; i < LH * LW; i += blockDim.x) {
+        const int ly = i / LW, lx = i % LW;
+        const int y = y0 + ly - R, x = x0 + lx - R;
+        float a = 0.f, b = 0.f, c = 0.f;
+        if (y >= 0 && y < H && x >= 0 && x < W) { const long long o = base + (long long)y * W + x; a = Ga[o]; b = Gb[o]; c = Gc[o]; }
+        gs[0][ly][lx] = a; gs[1][ly][lx] = b; gs[2][ly][lx] = c;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < LH * TW; i += blockDim.x) {
+        const int ly = i / TW, lx = i % TW;
+        float a = 0, b = 0, c = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { const float w = win.g[k]; a += w * gs[0][ly][lx + k]; b += w * gs[1][ly][lx + k]; c += w * gs[2][ly][lx + k]; }
+        hs[0][ly][lx] = a; hs[1][ly][lx] = b; hs[2][ly][lx] = c;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TH * TW; i += blockDim.x) {
+        const int ly = i / TW, lx = i % TW;
+        const int y = y0 + ly, x = x0 + lx;
+        if (y >= H || x >= W) continue;
+        float a = 0, b = 0, c = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { const float w = win.g[k]; a += w * hs[0][ly + k][lx]; b += w * hs[1][ly + k][lx]; c += w * hs[2][ly + k][lx]; }
+        const long long o = base + (long long)y * W + x;
+        const float xv = img1[o] * scale + shift, yv = img2[o] * scale + shift;
+        const float g = coef * scale * (a + 2.f * xv * b + yv * c);
+        if (accumulate) dimg[o] += g; else dimg[o] = g;
+    }
+}
+
+// ---------------------------------------------------------------- hinge / GAN (irc:1647-1649, :1662)
+// mode 0: first n_real entries are D(real), the rest D(fake):
+//         sums[0] += relu(1-p), sums[1] += relu(1+p); dpred = -w_real*[1-p>0] | +w_fake*[1+p>0]
+// mode 1: sums[2] += p; dpred = -w_real
+__global__ void hinge_kernel(const float* __restrict__ pred, long long n_total, long long n_real, int mode, float w_real, float w_fake,
+                             float* sums, float* dpred) {
+    __shared__ float sh[32];
+    float a = 0.f, b = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_total; i += (long long)gridDim.x * blockDim.x) {
+        const float p = pred[i];
+        if (mode == 1) { a += p; if (dpred) dpred[i] = -w_real; }
+        else if (i < n_real) { const float t = 1.f - p; a += fmaxf(t, 0.f); if (dpred) dpred[i] = t > 0.f ? -w_real : 0.f; }
+        else { const float t = 1.f + p; b += fmaxf(t, 0.f); if (dpred) dpred[i] = t > 0.f ? w_fake : 0.f; }
+    }
+    a = block_sum(a, sh); if (threadIdx.x == 0) atomicAdd(sums + (mode == 1 ? 2 : 0), a);
+    if (mode == 0) { b = block_sum(b, sh); if (threadIdx.x == 0) atomicAdd(sums + 1, b); }
+}
+
+// ---------------------------------------------------------------- VGG feature L1 (irc:1667-1669)
+// feat rows [0,R) = features of fake, rows [R,2R) = features of the target (both post-ReLU)
+// dz[q][c] = w * sign(f - r) * [f > 0]
+__global__ void feat_l1_kernel(const bf16* __restrict__ feat, long long rows_half, long long ld, int C, float w, float* sums, bf16* dz, long long ld_dz) {
+    __shared__ float sh[32];
+    const int C8 = C >> 3;
+    const long long total = rows_half * C8;
+    float acc = 0.f;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C8) * 8;
+        const long long q = idx / C8;
+        const uint4 uf = __ldg(reinterpret_cast<const uint4*>(feat + q * ld + c));
+        const uint4 ur = __ldg(reinterpret_cast<const uint4*>(feat + (q + rows_half) * ld + c));
+        const uint32_t wf[4] = {uf.x, uf.y, uf.z, uf.w}, wr[4] = {ur.x, ur.y, ur.z, ur.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const float2 a = unpack_bf16x2(wf[h]), b = unpack_bf16x2(wr[h]);
+            const float d0 = a.x - b.x, d1 = a.y - b.y;
+            acc += fabsf(d0) + fabsf(d1);
+            o[h] = pack_bf16x2(a.x > 0.f ? w * sgnf(d0) : 0.f, a.y > 0.f ? w * sgnf(d1) : 0.f);
+        }
+        if (dz) *reinterpret_cast<uint4*>(dz + q * ld_dz + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(sums, acc);
+}
+
+// ---------------------------------------------------------------- test-mode core (irc:865-876, irc:1197-1205)
+// u8 = trunc(clip((x+1)/2, 0, 1) * 255) in HWC order; sums[n] = (sum |u8/255 - gt|, sum (u8/255 - gt)^2)
+__global__ void quantize_metrics_kernel(const float* __restrict__ fake, const float* __restrict__ gt, int C, int H, int W,
+                                        unsigned char* u8, double* sums) {
+    __shared__ float sh[32];
+    const int n = blockIdx.y;
+    const long long hw = (long long)H * W;
+    float a = 0.f, b = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hw * C; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i / hw);
+        const long long pix = i % hw;
+        float v = (fake[(long long)n * C * hw + i] + 1.0f) * 0.5f;
+        v = fminf(fmaxf(v, 0.f), 1.f);
+        const unsigned char q = (unsigned char)(v * 255.0f);
+        if (u8) u8[((long long)n * hw + pix) * C + c] = q;
+        if (gt) {
+            const float d = __fdiv_rn((float)q, 255.0f) - gt[(long long)n * C * hw + i];
+            a += fabsf(d); b += d * d;
+        }
+    }
+    if (gt) {
+        a = block_sum(a, sh); if (threadIdx.x == 0) atomicAdd(sums + n * 2, (double)a);
+        b = block_sum(b, sh); if (threadIdx.x == 0) atomicAdd(sums + n * 2 + 1, (double)b);
+    }
+}
+
+int grid_for(long long total, int threads, int per_sm) {
+    long long b = (total + threads - 1) / threads;
+    const long long cap = (long long)irc_num_sms() * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace
+
+extern "C" int irc_pixel_loss(const float* fake, const float* target, int n_img, int C, int H, int W, float w_l1, float w_tvv, float w_tvh,
+                              float* sums, float* dfake, void* stream) {
+    if (!fake || !sums) return irc_set_error(IRC_ERR_BAD_ARG, "irc_pixel_loss: null");
+    const long long planes = (long long)n_img * C;
+    pixel_loss_kernel<<<grid_for(planes * H * W, 256, 8), 256, 0, (cudaStream_t)stream>>>(fake, target, planes, H, W, w_l1, w_tvv, w_tvh, sums, dfake);
+    return irc_check_launch("irc_pixel_loss");
+}
+
+extern "C" int irc_ssim_fwd(const float* img1, const float* img2, int n_img, int C, int H, int W, float scale, float shift, const float* window11,
+                            float* sums, float* ga, float* gb, float* gc, void* stream) {
+    if (!img1 || !img2 || !sums || !window11) return irc_set_error(IRC_ERR_BAD_ARG, "irc_ssim_fwd: null");
+    Win w; for (int i = 0; i < K; ++i) w.g[i] = window11[i];
+    dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, n_img * C);
+    ssim_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img1, img2, C, H, W, scale, shift, w, sums, ga, gb, gc);
+    return irc_check_launch("irc_ssim_fwd");
+}
+
+extern "C" int irc_ssim_bwd(const float* img1, const float* img2, int n_img, int C, int H, int W, float scale, float shift, const float* window11,
+                            const float* ga, const float* gb, const float* gc, float coef, float* dimg1, int accumulate, void* stream) {
+    if (!img1 || !img2 || !ga || !gb || !gc || !dimg1) return irc_set_error(IRC_ERR_BAD_ARG, "irc_ssim_bwd: null");
+    Win w; for (int i = 0; i < K; ++i) w.g[i] = window11[i];
+    dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, n_img * C);
+    ssim_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img1, img2, H, W, scale, shift, w, ga, gb, gc, coef, dimg1, accumulate);
+    return irc_check_launch("irc_ssim_bwd");
+}
+
+extern "C" int irc_hinge(const float* pred, long long n_total, long long n_real, int mode, float w_real, float w_fake, float* sums, float* dpred, void* stream) {
+    if (!pred || !sums) return irc_set_error(IRC_ERR_BAD_ARG, "irc_hinge: null");
+    hinge_kernel<<<grid_for(n_total, 256, 1), 256, 0, (cudaStream_t)stream>>>(pred, n_total, n_real, mode, w_real, w_fake, sums, dpred);
+    return irc_check_launch("irc_hinge");
+}
+
+extern "C" int irc_feat_l1(const void* feat, long long rows_half, long long ld, int C, float w, float* sums, void* dz, long long ld_dz, void* stream) {
+    if (!feat || !sums || C % 8) return irc_set_error(IRC_ERR_BAD_ARG, "irc_feat_l1: bad args");
+    feat_l1_kernel<<<grid_for(rows_half * (C / 8), 256, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)feat, rows_half, ld, C, w, sums, (bf16*)dz, ld_dz);
+    return irc_check_launch("irc_feat_l1");
+}
+
+extern "C" int irc_quantize_metrics(const float* fake, const float* gt, int n_img, int C, int H, int W, unsigned char* u8, double* sums, void* stream) {
+    if (!fake || (gt && !sums)) return irc_set_error(IRC_ERR_BAD_ARG, "irc_quantize_metrics: null");
+    if (gt) cudaMemsetAsync(sums, 0, sizeof(double) * 2 * n_img, (cudaStream_t)stream);
+    int bx = grid_for((long long)C * H * W, 256, 4); 
+    quantize_metrics_kernel<<<dim3(bx, n_img), 256, 0, (cudaStream_t)stream>>>(fake, gt, C, H, W, u8, sums);
+    return irc_check_launch("irc_quantize_metrics");
+}

@@ -1,0 +1,83 @@
+// Fused multi-tensor Adam over one flat fp32 parameter arena (torch.optim.Adam defaults,
+// irc:1601-1604, :1651, :1681), weight packing for the GEMM operand layouts, and the
+// deterministic reduction of split weight-gradient partials back into OIHW order.
+#include "irc_common.cuh"
+#include "../../include/irc_b200.h"
+
+using namespace irc;
+
+namespace {
+
+// hyper = {lr, beta1, beta2, eps, 1-beta1^t, 1-beta2^t, grad_scale}
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                            const float* __restrict__ hyper) {
+    const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], bc1 = hyper[4], bc2 = hyper[5], gs = hyper[6];
+    const float step = __fdiv_rn(lr, bc1), inv_sqrt_bc2 = __fdiv_rn(1.f, sqrtf(bc2));
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 pp = reinterpret_cast<float4*>(p)[i];
+        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        float* pe = &pp.x; const float* ge = &gg.x; float* me = &mm.x; float* ve = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gk = ge[k] * gs;
+            me[k] = b1 * me[k] + (1.f - b1) * gk;
+            ve[k] = b2 * ve[k] + (1.f - b2) * gk * gk;
+            pe[k] -= step * __fdiv_rn(me[k], sqrtf(ve[k]) * inv_sqrt_bc2 + eps);
+        }
+        reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gk = g[i] * gs;
+        const float mk = b1 * m[i] + (1.f - b1) * gk, vk = b2 * v[i] + (1.f - b2) * gk * gk;
+        m[i] = mk; v[i] = vk;
+        p[i] -= step * __fdiv_rn(mk, sqrtf(vk) * inv_sqrt_bc2 + eps);
+    }
+}
+
+__global__ void pack_kernel(const float* __restrict__ src, const int* __restrict__ map, long long n, bf16* __restrict__ dst) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int j = map[i];
+        dst[i] = __float2bfloat16(j >= 0 ? src[j] : 0.f);
+    }
+}
+
+__global__ void gather_sum_kernel(const float* __restrict__ src, const int* __restrict__ map, long long n, int splits, long long split_stride,
+                                  float* __restrict__ dst) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int j = map[i];
+        float a = 0.f;
+        if (j >= 0) for (int s = 0; s < splits; ++s) a += src[(long long)s * split_stride + j];
+        dst[i] = a;
+    }
+}
+
+int grid_for(long long total, int threads) {
+    long long b = (total + threads - 1) / threads;
+    const long long cap = (long long)irc_num_sms() * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace
+
+extern "C" int irc_adam(float* p, const float* g, float* m, float* v, long long n, const float* hyper, void* stream) {
+    if (!p || !g || !m || !v || !hyper) return irc_set_error(IRC_ERR_BAD_ARG, "irc_adam: null");
+    if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return irc_set_error(IRC_ERR_BAD_ARG, "irc_adam: arenas must be 16-byte aligned");
+    adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper);
+    return irc_check_launch("irc_adam");
+}
+
+extern "C" int irc_pack_bf16(const float* src, const int* map, long long n, void* dst, void* stream) {
+    if (!src || !map || !dst) return irc_set_error(IRC_ERR_BAD_ARG, "irc_pack_bf16: null");
+    pack_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, map, n, (bf16*)dst);
+    return irc_check_launch("irc_pack_bf16");
+}
+
+extern "C" int irc_gather_sum(const float* src, const int* map, long long n, int splits, long long split_stride, float* dst, void* stream) {
+    if (!src || !map || !dst) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather_sum: null");
+    gather_sum_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, map, n, splits, split_stride, dst);
+    return irc_check_launch("irc_gather_sum");
+}

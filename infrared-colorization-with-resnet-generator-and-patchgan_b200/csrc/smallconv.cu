@@ -1,0 +1,274 @@
+// Layout passes around the degenerate convolutions: the layers whose GEMM
+// has a tiny K (inc 1->64 7x7, VGG conv1_1 3->64, D model.0 4->64) are fed by an im2col
+// operand of 64 columns; the layers with a tiny N (outc 64->3 7x7, D model.11 512->1) are
+// computed as a GEMM over one kernel axis followed by a shifted tap reduction.
+#include "irc_common.cuh"
+#include "../../include/irc_b200.h"
+
+using namespace irc;
+
+namespace {
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    if (i < 0) i = -i;
+    if (i > n - 1) i = 2 * (n - 1) - i;
+    return i;
+}
+
+struct RowMap {
+    int mode, n_img, Ho, Wo;
+    // decode flat row -> (n, oy, ox); returns false for padding rows
+    __device__ __forceinline__ bool decode(long long q, int& n, int& oy, int& ox) const {
+        if (mode == 0) {
+            ox = (int)(q % Wo); q /= Wo; oy = (int)(q % Ho); n = (int)(q / Ho);
+            return true;
+        } else if (mode == 1) {
+            const int wp = Wo + 2, hp = Ho + 2;
+            ox = (int)(q % wp) - 1; q /= wp; oy = (int)(q % hp) - 1; n = (int)(q / hp);
+            return oy >= 0 && oy < Ho && ox >= 0 && ox < Wo;
+        } else {
+            const int wb = (Wo + 2) >> 1, hb = (Ho + 2) >> 1;
+            const int sub = (int)(q & 3); q >>= 2;
+            const int xb = (int)(q % wb); q /= wb; const int yb = (int)(q % hb); n = (int)(q / hb);
+            oy = 2 * yb + (sub >> 1) - 1; ox = 2 * xb + (sub & 1) - 1;
+            return oy >= 0 && oy < Ho && ox >= 0 && ox < Wo;
+        }
+    }
+    __device__ __forceinline__ long long encode(int n, int oy, int ox) const {
+        if (mode == 0) return ((long long)n * Ho + oy) * Wo + ox;
+        if (mode == 1) return ((long long)n * (Ho + 2) + oy + 1) * (Wo + 2) + ox + 1;
+        const int wb = (Wo + 2) >> 1, hb = (Ho + 2) >> 1;
+        const int yp = oy + 1, xp = ox + 1;
+        return ((((long long)n * hb + (yp >> 1)) * wb + (xp >> 1)) << 2) + ((yp & 1) * 2 + (xp & 1));
+    }
+    __host__ __device__ long long rows() const {
+        if (mode == 0) return (long long)n_img * Ho * Wo;
+        return (long long)n_img * (Ho + 2) * (Wo + 2);
+    }
+};
+
+struct Im2colP {
+    const float* src1; const float* src2; int c1, c2;
+    const float* scale; const float* shift;
+    int H, W, k, stride, pad, pad_mode;
+    RowMap rm;
+    bf16* dst; short* row_img;
+};
+
+__global__ void im2col_kernel(const Im2colP p) {
+    const int C = p.c1 + p.c2;
+    const int K = p.k * p.k * C;
+    const long long total = p.rm.rows() * 8;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx & 7);
+        const long long q = idx >> 3;
+        int n, oy, ox;
+        const bool live = p.rm.decode(q, n, oy, ox);
+        if (g == 0 && p.row_img) p.row_img[q] = live ? (short)n : (short)-1;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = g * 8 + j;
+            float val = 0.f;
+            if (live && col < K) {
+                const int c = col % C, rs = col / C;
+                const int r = rs / p.k, s = rs % p.k;
+                int y = oy * p.stride - p.pad + r, x = ox * p.stride - p.pad + s;
+                bool ok = true;
+                if (p.pad_mode == 1) { y = reflect_idx(y, p.H); x = reflect_idx(x, p.W); }
+                else ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
+                if (ok) {
+                    const float raw = c < p.c1 ? __ldg(p.src1 + (((long long)n * p.c1 + c) * p.H + y) * p.W + x)
+                                               : __ldg(p.src2 + (((long long)n * p.c2 + (c - p.c1)) * p.H + y) * p.W + x);
+                    val = p.scale ? raw * __ldg(p.scale + c) + __ldg(p.shift + c) : raw;
+                }
+            }
+            v[j] = val;
+        }
+        *reinterpret_cast<uint4*>(p.dst + q * 64 + g * 8) =
+            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+}
+
+struct Col2imP {
+    const bf16* de; long long ld;
+    int C, c_first, c_out, H, W, k, stride, pad;
+    const float* scale;
+    RowMap rm;
+    float* out; int accumulate;
+};
+
+__global__ void col2im_kernel(const Col2imP p) {
+    const long long total = (long long)p.rm.n_img * p.c_out * p.H * p.W;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        long long t = idx;
+        const int x = (int)(t % p.W); t /= p.W;
+        const int y = (int)(t % p.H); t /= p.H;
+        const int co = (int)(t % p.c_out);
+        const int n = (int)(t / p.c_out);
+        const int c = p.c_first + co;
+        float acc = 0.f;
+        for (int r = 0; r < p.k; ++r) {
+            const int ty = y + p.pad - r;
+            if (ty < 0 || ty % p.stride) continue;
+            const int oy = ty / p.stride;
+            if (oy >= p.rm.Ho) continue;
+            for (int s = 0; s < p.k; ++s) {
+                const int tx = x + p.pad - s;
+                if (tx < 0 || tx % p.stride) continue;
+                const int ox = tx / p.stride;
+                if (ox >= p.rm.Wo) continue;
+                acc += __bfloat162float(p.de[p.rm.encode(n, oy, ox) * p.ld + (r * p.k + s) * p.C + c]);
+            }
+        }
+        if (p.scale) acc *= __ldg(p.scale + c);
+        if (p.accumulate) p.out[idx] += acc; else p.out[idx] = acc;
+    }
+}
+
+struct TapP {
+    int nshift, nco;
+    int shifts[IRC_MAX_TAPS];
+    int n_img, H, W, hp, wp, oy, ox;
+};
+
+// out[n][co][y][x] = act(bias[co] + sum_j P[q + shift_j][j*nco + co])
+__global__ void tap_reduce_kernel(const float* P, long long ldp, const float* bias, int act, float* out, const TapP t) {
+    const long long total = (long long)t.n_img * t.H * t.W;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % t.W);
+        const int y = (int)((idx / t.W) % t.H);
+        const int n = (int)(idx / ((long long)t.W * t.H));
+        const long long q = ((long long)n * t.hp + y + t.oy) * t.wp + x + t.ox;
+        for (int co = 0; co < t.nco; ++co) {
+            float acc = bias ? __ldg(bias + co) : 0.f;
+            for (int j = 0; j < t.nshift; ++j) acc += __ldg(P + (q + t.shifts[j]) * ldp + j * t.nco + co);
+            if (act == 3) acc = tanhf(acc);
+            out[(((long long)n * t.nco + co) * t.H + y) * t.W + x] = acc;
+        }
+    }
+}
+
+// E[q][j*nco + co] = g'[pixel(q - shift_j)][co];  g' = g * (1 - yv^2) when yv is given (tanh')
+__global__ void tap_expand_kernel(const float* g, const float* yv, bf16* E, const TapP t) {
+    const long long rows = (long long)t.n_img * t.hp * t.wp;
+    const long long total = rows * 8;
+    const int ncol = t.nshift * t.nco;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int grp = (int)(idx & 7);
+        const long long q = idx >> 3;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int col = grp * 8 + k;
+            float val = 0.f;
+            if (col < ncol) {
+                const int j = col / t.nco, co = col % t.nco;
+                const long long qq = q - t.shifts[j];
+                if (qq >= 0 && qq < rows) {
+                    const int x = (int)(qq % t.wp) - t.ox;
+                    const int y = (int)((qq / t.wp) % t.hp) - t.oy;
+                    const int n = (int)(qq / ((long long)t.wp * t.hp));
+                    if (x >= 0 && x < t.W && y >= 0 && y < t.H) {
+                        const long long o = (((long long)n * t.nco + co) * t.H + y) * t.W + x;
+                        val = __ldg(g + o);
+                        if (yv) { const float yy = __ldg(yv + o); val *= (1.f - yy * yy); }
+                    }
+                }
+            }
+            v[k] = val;
+        }
+        *reinterpret_cast<uint4*>(E + q * 64 + grp * 8) =
+            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+}
+
+// out[c] = sum_{n, pixels} g[n][c][.] * (1 - yv^2)
+__global__ void chan_sum_kernel(const float* g, const float* yv, int n_img, int C, long long hw, float* out) {
+    __shared__ float sh[32];
+    const int c = blockIdx.y;
+    float s = 0.f;
+    const long long total = (long long)n_img * hw;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / hw, r = i % hw;
+        const long long o = (n * C + c) * hw + r;
+        float v = __ldg(g + o);
+        if (yv) { const float yy = __ldg(yv + o); v *= (1.f - yy * yy); }
+        s += v;
+    }
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) atomicAdd(out + c, s);
+}
+
+int grid_for(long long total, int threads) {
+    long long b = (total + threads - 1) / threads;
+    const long long cap = (long long)irc_num_sms() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace
+
+extern "C" long long irc_im2col_rows(int row_mode, int n_img, int Ho, int Wo) {
+    RowMap rm; rm.mode = row_mode; rm.n_img = n_img; rm.Ho = Ho; rm.Wo = Wo;
+    return rm.rows();
+}
+
+extern "C" int irc_im2col(const irc_im2col_args* a, void* stream) {
+    if (!a->src1 || !a->dst) return irc_set_error(IRC_ERR_BAD_ARG, "irc_im2col: null");
+    const int C = a->c1 + (a->src2 ? a->c2 : 0);
+    if (a->k * a->k * C > 64) return irc_set_error(IRC_ERR_BAD_ARG, "irc_im2col: k*k*C must be <= 64");
+    if (a->row_mode == 2 && ((a->Ho | a->Wo) & 1)) return irc_set_error(IRC_ERR_BAD_ARG, "irc_im2col: row_mode 2 needs even output extents");
+    Im2colP p;
+    p.src1 = a->src1; p.src2 = a->src2; p.c1 = a->c1; p.c2 = a->src2 ? a->c2 : 0;
+    p.scale = a->scale; p.shift = a->shift;
+    p.H = a->H; p.W = a->W; p.k = a->k; p.stride = a->stride; p.pad = a->pad; p.pad_mode = a->pad_mode;
+    p.rm.mode = a->row_mode; p.rm.n_img = a->n_img; p.rm.Ho = a->Ho; p.rm.Wo = a->Wo;
+    p.dst = (bf16*)a->dst; p.row_img = a->row_img;
+    im2col_kernel<<<grid_for(p.rm.rows() * 8, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return irc_check_launch("irc_im2col");
+}
+
+extern "C" int irc_col2im(const irc_col2im_args* a, void* stream) {
+    if (!a->de || !a->out) return irc_set_error(IRC_ERR_BAD_ARG, "irc_col2im: null");
+    Col2imP p;
+    p.de = (const bf16*)a->de; p.ld = a->ld; p.C = a->C; p.c_first = a->c_first; p.c_out = a->c_out;
+    p.H = a->H; p.W = a->W; p.k = a->k; p.stride = a->stride; p.pad = a->pad; p.scale = a->scale;
+    p.rm.mode = a->row_mode; p.rm.n_img = a->n_img; p.rm.Ho = a->Ho; p.rm.Wo = a->Wo;
+    p.out = a->out; p.accumulate = a->accumulate;
+    const long long total = (long long)a->n_img * a->c_out * a->H * a->W;
+    col2im_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return irc_check_launch("irc_col2im");
+}
+
+static int fill_tap(const irc_tap_args* a, TapP& t) {
+    if (a->nshift <= 0 || a->nshift > IRC_MAX_TAPS || a->nshift * a->nco > 64) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tap: nshift*nco must be <= 64");
+    t.nshift = a->nshift; t.nco = a->nco;
+    for (int i = 0; i < a->nshift; ++i) t.shifts[i] = a->shifts[i];
+    t.n_img = a->n_img; t.H = a->H; t.W = a->W; t.hp = a->hp; t.wp = a->wp; t.oy = a->oy; t.ox = a->ox;
+    return IRC_OK;
+}
+
+extern "C" int irc_tap_reduce(const irc_tap_args* a, const float* P, long long ldp, const float* bias, int act, float* out, void* stream) {
+    TapP t; int rc = fill_tap(a, t); if (rc) return rc;
+    if (!P || !out) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tap_reduce: null");
+    tap_reduce_kernel<<<grid_for((long long)t.n_img * t.H * t.W, 256), 256, 0, (cudaStream_t)stream>>>(P, ldp, bias, act, out, t);
+    return irc_check_launch("irc_tap_reduce");
+}
+
+extern "C" int irc_tap_expand(const irc_tap_args* a, const float* g, const float* y, void* E, float* dbias, void* stream) {
+    TapP t; int rc = fill_tap(a, t); if (rc) return rc;
+    if (!g || !E) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tap_expand: null");
+    const long long rows = (long long)t.n_img * t.hp * t.wp;
+    tap_expand_kernel<<<grid_for(rows * 8, 256), 256, 0, (cudaStream_t)stream>>>(g, y, (bf16*)E, t);
+    rc = irc_check_launch("irc_tap_expand"); if (rc) return rc;
+    if (dbias) {
+        cudaMemsetAsync(dbias, 0, sizeof(float) * t.nco, (cudaStream_t)stream);
+        const long long hw = (long long)t.H * t.W;
+        int bx = grid_for((long long)t.n_img * hw, 256); if (bx > 256) bx = 256;
+        chan_sum_kernel<<<dim3(bx, t.nco), 256, 0, (cudaStream_t)stream>>>(g, y, t.n_img, t.nco, hw, dbias);
+        rc = irc_check_launch("irc_tap_expand(dbias)");
+    }
+    return rc;
+}
