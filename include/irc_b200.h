@@ -76,11 +76,13 @@ int irc_tn_gemm(const irc_tn_gemm_args* args, void* stream);
 /* ---- memory-bound passes on NHWC bf16 frames ---------------------------------------- */
 
 /* An NHWC bf16 image set inside a flat [rows][ld] buffer: pixel (n,y,x), channel c lives at
- * row (n*hp + y + oy)*wp + (x + ox), column chan_off + c. */
+ * row (n*hp + y + oy)*wp + (x + ox), column chan_off + c (unless s2d_c > 0, see below). */
 typedef struct irc_view {
     const void* ptr;
     long long ld;
     int chan_off, hp, wp, oy, ox;
+    int s2d_c;              /* >0: the buffer holds 2x2 space-to-depth blocks of an image with s2d_c
+                               channels (hp, wp count blocks; oy, ox offset the un-blocked pixel) */
 } irc_view;
 
 /* row_img[q] = image index for rows inside [y0,y1)x[x0,x1) of each hp x wp image, else -1. */
@@ -126,8 +128,8 @@ int irc_in_bwd_apply(const irc_in_bwd_args* args, void* stream);
 int irc_maxpool2(const irc_view* src, const irc_view* dst, int C, int n_img, int Ho, int Wo, void* stream);
 int irc_maxpool2_bwd(const irc_view* src, const irc_view* g, const irc_view* dsrc, int C, int n_img, int Ho, int Wo, void* stream);
 
-/* out[c] = sum_rows a[row][chan_off + c]  (bias gradients) */
-int irc_colsum(const void* a, long long rows, long long ld, int chan_off, int C, float* out, void* stream);
+/* out[c] = sum over rows (with row_img[row] >= 0 when given) of a[row][chan_off + c]  (bias gradients) */
+int irc_colsum(const void* a, long long rows, long long ld, int chan_off, int C, const short* row_img, float* out, void* stream);
 
 /* ---- degenerate convolutions (tiny K or tiny N) --------------------------------------- */
 

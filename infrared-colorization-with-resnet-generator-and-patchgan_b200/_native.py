@@ -1,4 +1,5 @@
-"""ctypes binding of libirc_sm100.so (include/irc_b200.h).
+"""ctypes binding of libirc_sm100.so (include/irc_b200.h) and the `CudaBackend` that the
+engine drives.
 
 There is no fallback: if the library is missing, or the device is not sm_100, every entry
 point raises.  Nothing here touches ``oracle/``."""
@@ -6,10 +7,22 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libirc_sm100.so")
 MAX_TAPS = 64
+
+EXPORTS = [
+    "irc_version", "irc_arch_check", "irc_last_error", "irc_conv_gemm", "irc_tn_gemm", "irc_row_index",
+    "irc_in_stats", "irc_gather", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_maxpool2", "irc_maxpool2_bwd",
+    "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
+    "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics",
+    "irc_adam", "irc_pack_bf16", "irc_gather_sum",
+]
 
 
 class IrcError(RuntimeError):
@@ -42,6 +55,58 @@ class TnGemmArgs(C.Structure):
     ]
 
 
+class CView(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("ld", C.c_longlong), ("chan_off", C.c_int), ("hp", C.c_int), ("wp", C.c_int),
+                ("oy", C.c_int), ("ox", C.c_int), ("s2d_c", C.c_int)]
+
+
+class GatherArgs(C.Structure):
+    _fields_ = [
+        ("src", CView), ("src2", CView), ("res", CView), ("dst", CView),
+        ("C", C.c_int), ("n_img", C.c_int),
+        ("stats", C.c_void_p), ("cnt", C.c_float), ("eps", C.c_float), ("act", C.c_int), ("slope", C.c_float),
+        ("ty_idx", C.c_void_p), ("ty_w", C.c_void_p), ("ky", C.c_int),
+        ("tx_idx", C.c_void_p), ("tx_w", C.c_void_p), ("kx", C.c_int),
+        ("H", C.c_int), ("W", C.c_int), ("pad", C.c_int), ("halo_mode", C.c_int), ("dst_s2d", C.c_int),
+    ]
+
+
+class InBwdArgs(C.Structure):
+    _fields_ = [
+        ("z", CView), ("g1", CView), ("g2", CView), ("dz", CView),
+        ("C", C.c_int), ("n_img", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("stats", C.c_void_p), ("cnt", C.c_float), ("eps", C.c_float), ("act", C.c_int), ("slope", C.c_float),
+        ("ty_idx", C.c_void_p), ("ty_w", C.c_void_p), ("ky", C.c_int),
+        ("tx_idx", C.c_void_p), ("tx_w", C.c_void_p), ("kx", C.c_int),
+        ("bsum", C.c_void_p),
+    ]
+
+
+class Im2colArgs(C.Structure):
+    _fields_ = [
+        ("src1", C.c_void_p), ("c1", C.c_int), ("src2", C.c_void_p), ("c2", C.c_int),
+        ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("n_img", C.c_int), ("H", C.c_int), ("W", C.c_int), ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
+        ("pad_mode", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int), ("row_mode", C.c_int),
+        ("dst", C.c_void_p), ("row_img", C.c_void_p),
+    ]
+
+
+class Col2imArgs(C.Structure):
+    _fields_ = [
+        ("de", C.c_void_p), ("ld", C.c_longlong),
+        ("C", C.c_int), ("c_first", C.c_int), ("c_out", C.c_int), ("n_img", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int), ("row_mode", C.c_int),
+        ("scale", C.c_void_p), ("out", C.c_void_p), ("accumulate", C.c_int),
+    ]
+
+
+class TapArgs(C.Structure):
+    _fields_ = [("nshift", C.c_int), ("nco", C.c_int), ("shifts", C.c_int * MAX_TAPS),
+                ("n_img", C.c_int), ("H", C.c_int), ("W", C.c_int), ("hp", C.c_int), ("wp", C.c_int),
+                ("oy", C.c_int), ("ox", C.c_int)]
+
+
 _lib = None
 
 
@@ -54,6 +119,7 @@ def lib() -> C.CDLL:
                            "(there is no CPU or PyTorch fallback for the hot path)")
         _lib = C.CDLL(LIB_PATH)
         _lib.irc_last_error.restype = C.c_char_p
+        _lib.irc_im2col_rows.restype = C.c_longlong
     return _lib
 
 
@@ -64,3 +130,237 @@ def check(rc: int) -> None:
 
 def arch_check() -> None:
     check(lib().irc_arch_check())
+
+
+# ------------------------------------------------------------------------------------------
+# engine-facing views and backend
+# ------------------------------------------------------------------------------------------
+@dataclass
+class View:
+    """Pixel (n,y,x), channel c of a bf16 [rows, ld] tensor ``t``: see irc_view in the header."""
+    t: torch.Tensor
+    chan_off: int
+    hp: int
+    wp: int
+    oy: int = 0
+    ox: int = 0
+    s2d_c: int = 0
+
+    def sub(self, chan_off: int) -> "View":
+        return View(self.t, self.chan_off + chan_off, self.hp, self.wp, self.oy, self.ox, self.s2d_c)
+
+    def shifted(self, oy: int, ox: int) -> "View":
+        return View(self.t, self.chan_off, self.hp, self.wp, oy, ox, self.s2d_c)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _cview(v: Optional[View]) -> CView:
+    c = CView()
+    if v is None:
+        c.ptr = None
+        return c
+    assert v.t.dim() == 2 and v.t.dtype == torch.bfloat16 and v.t.is_contiguous()
+    c.ptr = v.t.data_ptr(); c.ld = v.t.shape[1]; c.chan_off = v.chan_off
+    c.hp = v.hp; c.wp = v.wp; c.oy = v.oy; c.ox = v.ox; c.s2d_c = v.s2d_c
+    return c
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Tables:
+    """Separable sparse 1-D operators (idx[len,k], w[len,k]) for irc_gather / irc_in_bwd."""
+
+    def __init__(self, ty_idx=None, ty_w=None, tx_idx=None, tx_w=None):
+        self.ty_idx, self.ty_w, self.tx_idx, self.tx_w = ty_idx, ty_w, tx_idx, tx_w
+        self.ky = 1 if ty_idx is None else ty_idx.shape[1]
+        self.kx = 1 if tx_idx is None else tx_idx.shape[1]
+
+
+IDENTITY = Tables()
+
+
+class CudaBackend:
+    """Thin, allocation-free launcher of the C ABI on torch's current stream.  `launches`
+    counts kernel launches (bench.py reports it)."""
+
+    name = "cuda"
+
+    def __init__(self):
+        self.L = lib()
+        arch_check()
+        self.launches = 0
+
+    # ---- tensor-core GEMMs
+    def conv_gemm(self, a, a_chan_off, cin, taps: Sequence[int], w, n_out, out, out_chan_off=0, bias=None, act=0, slope=0.0,
+                  row_img=None, mask: Optional[View] = None, mask_slope=0.0):
+        g = ConvGemmArgs()
+        g.a = a.data_ptr(); g.a_rows = a.shape[0]; g.a_ld = a.shape[1]; g.a_chan_off = a_chan_off; g.cin = cin
+        g.ntaps = len(taps)
+        for i, t in enumerate(taps):
+            g.taps[i] = int(t)
+        assert w.dtype == torch.bfloat16 and w.shape == (n_out, len(taps) * cin), (w.shape, n_out, len(taps), cin)
+        g.w = w.data_ptr(); g.n_out = n_out
+        assert out.shape[0] == a.shape[0]
+        g.out = out.data_ptr(); g.out_ld = out.shape[1]; g.out_chan_off = out_chan_off
+        g.out_fp32 = int(out.dtype == torch.float32)
+        g.bias = None if bias is None else bias.data_ptr()
+        g.act = act; g.slope = slope
+        g.row_img = None if row_img is None else row_img.data_ptr()
+        if mask is not None:
+            assert mask.t.shape[0] == a.shape[0]
+            g.mask = mask.t.data_ptr(); g.mask_ld = mask.t.shape[1]; g.mask_chan_off = mask.chan_off; g.mask_slope = mask_slope
+        g.bn = 0
+        check(self.L.irc_conv_gemm(C.byref(g), _stream())); self.launches += 1
+
+    def tn_gemm(self, a, a_chan_off, m, b, b_chan_off, n, k_rows, a_shift, b_shift, out, tap_stride, m_stride, n_stride,
+                splits, split_stride):
+        g = TnGemmArgs()
+        g.a = a.data_ptr(); g.a_rows = a.shape[0]; g.a_ld = a.shape[1]; g.a_chan_off = a_chan_off; g.m = m
+        g.b = b.data_ptr(); g.b_rows = b.shape[0]; g.b_ld = b.shape[1]; g.b_chan_off = b_chan_off; g.n = n
+        g.k_rows = k_rows; g.ntaps = len(a_shift)
+        for i in range(len(a_shift)):
+            g.a_shift[i] = int(a_shift[i]); g.b_shift[i] = int(b_shift[i])
+        assert out.dtype == torch.float32
+        g.out = out.data_ptr(); g.out_tap_stride = tap_stride; g.out_m_stride = m_stride; g.out_n_stride = n_stride
+        g.out_split_stride = split_stride; g.splits = splits; g.bn = 0
+        check(self.L.irc_tn_gemm(C.byref(g), _stream())); self.launches += 1
+
+    # ---- frames
+    def row_index(self, row_img, n_img, hp, wp, y0, y1, x0, x1):
+        check(self.L.irc_row_index(_p(row_img), n_img, hp, wp, y0, y1, x0, x1, _stream())); self.launches += 1
+
+    def in_stats(self, z: View, C_, n_img, H, W, stats):
+        cv = _cview(z)
+        check(self.L.irc_in_stats(C.byref(cv), C_, n_img, H, W, _p(stats), _stream())); self.launches += 1
+
+    def gather(self, src: View, dst: View, C_, n_img, H, W, pad, halo_mode, tables: Tables = IDENTITY, src2=None, res=None,
+               stats=None, cnt=0.0, eps=1e-5, act=0, slope=0.0, dst_s2d=0):
+        g = GatherArgs()
+        g.src = _cview(src); g.src2 = _cview(src2); g.res = _cview(res); g.dst = _cview(dst)
+        g.C = C_; g.n_img = n_img
+        g.stats = None if stats is None else stats.data_ptr(); g.cnt = cnt; g.eps = eps; g.act = act; g.slope = slope
+        g.ty_idx = None if tables.ty_idx is None else tables.ty_idx.data_ptr()
+        g.ty_w = None if tables.ty_w is None else tables.ty_w.data_ptr(); g.ky = tables.ky
+        g.tx_idx = None if tables.tx_idx is None else tables.tx_idx.data_ptr()
+        g.tx_w = None if tables.tx_w is None else tables.tx_w.data_ptr(); g.kx = tables.kx
+        g.H = H; g.W = W; g.pad = pad; g.halo_mode = halo_mode; g.dst_s2d = dst_s2d
+        check(self.L.irc_gather(C.byref(g), _stream())); self.launches += 1
+
+    def _bwd_args(self, z, g1, g2, dz, C_, n_img, H, W, stats, cnt, eps, act, slope, tables, bsum):
+        g = InBwdArgs()
+        g.z = _cview(z); g.g1 = _cview(g1); g.g2 = _cview(g2); g.dz = _cview(dz)
+        g.C = C_; g.n_img = n_img; g.H = H; g.W = W
+        g.stats = None if stats is None else stats.data_ptr(); g.cnt = cnt; g.eps = eps; g.act = act; g.slope = slope
+        g.ty_idx = None if tables.ty_idx is None else tables.ty_idx.data_ptr()
+        g.ty_w = None if tables.ty_w is None else tables.ty_w.data_ptr(); g.ky = tables.ky
+        g.tx_idx = None if tables.tx_idx is None else tables.tx_idx.data_ptr()
+        g.tx_w = None if tables.tx_w is None else tables.tx_w.data_ptr(); g.kx = tables.kx
+        g.bsum = None if bsum is None else bsum.data_ptr()
+        return g
+
+    def in_bwd(self, z: View, g1: View, dz: View, C_, n_img, H, W, stats=None, cnt=0.0, eps=1e-5, act=0, slope=0.0,
+               tables: Tables = IDENTITY, g2=None, bsum=None):
+        """reduce (when normalised) + apply."""
+        g = self._bwd_args(z, g1, g2, dz, C_, n_img, H, W, stats, cnt, eps, act, slope, tables, bsum)
+        if stats is not None:
+            check(self.L.irc_in_bwd_reduce(C.byref(g), _stream())); self.launches += 1
+        check(self.L.irc_in_bwd_apply(C.byref(g), _stream())); self.launches += 1
+
+    def maxpool2(self, src: View, dst: View, C_, n_img, Ho, Wo):
+        a, b = _cview(src), _cview(dst)
+        check(self.L.irc_maxpool2(C.byref(a), C.byref(b), C_, n_img, Ho, Wo, _stream())); self.launches += 1
+
+    def maxpool2_bwd(self, src: View, g: View, dsrc: View, C_, n_img, Ho, Wo):
+        a, b, c = _cview(src), _cview(g), _cview(dsrc)
+        check(self.L.irc_maxpool2_bwd(C.byref(a), C.byref(b), C.byref(c), C_, n_img, Ho, Wo, _stream())); self.launches += 1
+
+    def colsum(self, a, chan_off, C_, out, row_img=None):
+        check(self.L.irc_colsum(_p(a), C.c_longlong(a.shape[0]), C.c_longlong(a.shape[1]), chan_off, C_, _p(row_img), _p(out), _stream()))
+        self.launches += 1
+
+    # ---- degenerate convolutions
+    def im2col_rows(self, row_mode, n_img, Ho, Wo):
+        return int(self.L.irc_im2col_rows(row_mode, n_img, Ho, Wo))
+
+    def im2col(self, src1, src2, scale, shift, n_img, H, W, k, stride, pad, pad_mode, Ho, Wo, row_mode, dst, row_img=None):
+        g = Im2colArgs()
+        g.src1 = src1.data_ptr(); g.c1 = src1.shape[1]
+        g.src2 = None if src2 is None else src2.data_ptr(); g.c2 = 0 if src2 is None else src2.shape[1]
+        g.scale = None if scale is None else scale.data_ptr(); g.shift = None if shift is None else shift.data_ptr()
+        g.n_img = n_img; g.H = H; g.W = W; g.k = k; g.stride = stride; g.pad = pad; g.pad_mode = pad_mode
+        g.Ho = Ho; g.Wo = Wo; g.row_mode = row_mode
+        assert dst.shape[1] == 64 and dst.shape[0] == self.im2col_rows(row_mode, n_img, Ho, Wo)
+        g.dst = dst.data_ptr(); g.row_img = None if row_img is None else row_img.data_ptr()
+        check(self.L.irc_im2col(C.byref(g), _stream())); self.launches += 1
+
+    def col2im(self, de, C_, c_first, c_out, n_img, H, W, k, stride, pad, Ho, Wo, row_mode, scale, out, accumulate):
+        g = Col2imArgs()
+        g.de = de.data_ptr(); g.ld = de.shape[1]; g.C = C_; g.c_first = c_first; g.c_out = c_out; g.n_img = n_img
+        g.H = H; g.W = W; g.k = k; g.stride = stride; g.pad = pad; g.Ho = Ho; g.Wo = Wo; g.row_mode = row_mode
+        g.scale = None if scale is None else scale.data_ptr(); g.out = out.data_ptr(); g.accumulate = int(accumulate)
+        check(self.L.irc_col2im(C.byref(g), _stream())); self.launches += 1
+
+    @staticmethod
+    def _tap(shifts, nco, n_img, H, W, hp, wp, oy, ox):
+        t = TapArgs(); t.nshift = len(shifts); t.nco = nco
+        for i, s in enumerate(shifts):
+            t.shifts[i] = int(s)
+        t.n_img = n_img; t.H = H; t.W = W; t.hp = hp; t.wp = wp; t.oy = oy; t.ox = ox
+        return t
+
+    def tap_reduce(self, P, shifts, nco, n_img, H, W, hp, wp, oy, ox, bias, act, out):
+        t = self._tap(shifts, nco, n_img, H, W, hp, wp, oy, ox)
+        check(self.L.irc_tap_reduce(C.byref(t), _p(P), C.c_longlong(P.shape[1]), _p(bias), act, _p(out), _stream())); self.launches += 1
+
+    def tap_expand(self, g, y, shifts, nco, n_img, H, W, hp, wp, oy, ox, E, dbias=None):
+        t = self._tap(shifts, nco, n_img, H, W, hp, wp, oy, ox)
+        assert E.shape == (n_img * hp * wp, 64)
+        check(self.L.irc_tap_expand(C.byref(t), _p(g), _p(y), _p(E), _p(dbias), _stream()))
+        self.launches += 1 if dbias is None else 2
+
+    # ---- losses
+    def pixel_loss(self, fake, target, w_l1, w_tvv, w_tvh, sums, dfake):
+        n, c, h, w = fake.shape
+        check(self.L.irc_pixel_loss(_p(fake), _p(target), n, c, h, w, C.c_float(w_l1), C.c_float(w_tvv), C.c_float(w_tvh),
+                                    _p(sums), _p(dfake), _stream())); self.launches += 1
+
+    def ssim_fwd(self, img1, img2, scale, shift, window, sums, ga=None, gb=None, gc=None):
+        n, c, h, w = img1.shape
+        check(self.L.irc_ssim_fwd(_p(img1), _p(img2), n, c, h, w, C.c_float(scale), C.c_float(shift), _p(window), _p(sums),
+                                  _p(ga), _p(gb), _p(gc), _stream())); self.launches += 1
+
+    def ssim_bwd(self, img1, img2, scale, shift, window, ga, gb, gc, coef, dimg1, accumulate):
+        n, c, h, w = img1.shape
+        check(self.L.irc_ssim_bwd(_p(img1), _p(img2), n, c, h, w, C.c_float(scale), C.c_float(shift), _p(window), _p(ga), _p(gb),
+                                  _p(gc), C.c_float(coef), _p(dimg1), int(accumulate), _stream())); self.launches += 1
+
+    def hinge(self, pred, n_real, mode, w_real, w_fake, sums, dpred):
+        check(self.L.irc_hinge(_p(pred), C.c_longlong(pred.numel()), C.c_longlong(n_real), mode, C.c_float(w_real),
+                               C.c_float(w_fake), _p(sums), _p(dpred), _stream())); self.launches += 1
+
+    def feat_l1(self, feat, rows_half, C_, w, sums, dz):
+        check(self.L.irc_feat_l1(_p(feat), C.c_longlong(rows_half), C.c_longlong(feat.shape[1]), C_, C.c_float(w), _p(sums),
+                                 _p(dz), C.c_longlong(0 if dz is None else dz.shape[1]), _stream())); self.launches += 1
+
+    def quantize_metrics(self, fake, gt, u8, sums):
+        n, c, h, w = fake.shape
+        check(self.L.irc_quantize_metrics(_p(fake), _p(gt), n, c, h, w, _p(u8), _p(sums), _stream())); self.launches += 1
+
+    # ---- optimizer / layout
+    def adam(self, p, g, m, v, hyper):
+        check(self.L.irc_adam(_p(p), _p(g), _p(m), _p(v), C.c_longlong(p.numel()), _p(hyper), _stream())); self.launches += 1
+
+    def pack_bf16(self, src, map_, dst):
+        check(self.L.irc_pack_bf16(_p(src), _p(map_), C.c_longlong(map_.numel()), _p(dst), _stream())); self.launches += 1
+
+    def gather_sum(self, src, map_, splits, split_stride, dst):
+        check(self.L.irc_gather_sum(_p(src), _p(map_), C.c_longlong(map_.numel()), splits, C.c_longlong(split_stride), _p(dst),
+                                    _stream())); self.launches += 1
+
+    def zero_(self, t):
+        t.zero_(); self.launches += 1

@@ -9,17 +9,19 @@ using namespace irc;
 namespace {
 
 struct View {
-    const bf16* p; long long ld; int off, hp, wp, oy, ox;
-    __device__ __forceinline__ long long row(int n, int y, int x) const {
-        return (long long)(n * hp + y + oy) * wp + (x + ox);
-    }
+    const bf16* p; long long ld; int off, hp, wp, oy, ox, s2d_c;
     __device__ __forceinline__ const bf16* at(int n, int y, int x, int c) const {
-        return p + row(n, y, x) * ld + off + c;
+        const int Y = y + oy, X = x + ox;
+        if (s2d_c) {
+            const long long r = (long long)(n * hp + (Y >> 1)) * wp + (X >> 1);
+            return p + r * ld + off + ((Y & 1) * 2 + (X & 1)) * s2d_c + c;
+        }
+        return p + ((long long)(n * hp + Y) * wp + X) * ld + off + c;
     }
 };
 
 inline View mk(const irc_view& v) {
-    View r; r.p = (const bf16*)v.ptr; r.ld = v.ld; r.off = v.chan_off; r.hp = v.hp; r.wp = v.wp; r.oy = v.oy; r.ox = v.ox;
+    View r; r.p = (const bf16*)v.ptr; r.ld = v.ld; r.off = v.chan_off; r.hp = v.hp; r.wp = v.wp; r.oy = v.oy; r.ox = v.ox; r.s2d_c = v.s2d_c;
     return r;
 }
 
@@ -349,12 +351,13 @@ __global__ void maxpool_bwd_kernel(View src, View g, View dsrc, int C, int n_img
 }
 
 // column sums of a bf16 [rows][ld] matrix slice -> fp32 [C] (bias gradients)
-__global__ void colsum_kernel(const bf16* a, long long rows, long long ld, int off, int C, float* out) {
+__global__ void colsum_kernel(const bf16* a, long long rows, long long ld, int off, int C, const short* row_img, float* out) {
     const int c = blockIdx.y * 32 + (threadIdx.x & 31);
     const int lane_r = threadIdx.x >> 5, R = blockDim.x >> 5;
     float s = 0.f;
     if (c < C)
-        for (long long r = blockIdx.x * (long long)R + lane_r; r < rows; r += (long long)gridDim.x * R) s += __bfloat162float(a[r * ld + off + c]);
+        for (long long r = blockIdx.x * (long long)R + lane_r; r < rows; r += (long long)gridDim.x * R)
+            if (!row_img || row_img[r] >= 0) s += __bfloat162float(a[r * ld + off + c]);
     __shared__ float sh[32][33];
     sh[lane_r][threadIdx.x & 31] = s;
     __syncthreads();
@@ -480,10 +483,10 @@ extern "C" int irc_maxpool2_bwd(const irc_view* src, const irc_view* g, const ir
     return irc_check_launch("irc_maxpool2_bwd");
 }
 
-extern "C" int irc_colsum(const void* a, long long rows, long long ld, int chan_off, int C, float* out, void* stream) {
+extern "C" int irc_colsum(const void* a, long long rows, long long ld, int chan_off, int C, const short* row_img, float* out, void* stream) {
     if (!a || !out) return irc_set_error(IRC_ERR_BAD_ARG, "irc_colsum: null");
     cudaMemsetAsync(out, 0, sizeof(float) * C, (cudaStream_t)stream);
     long long bx = (rows + 31) / 32; if (bx > irc_num_sms() * 4) bx = irc_num_sms() * 4; if (bx < 1) bx = 1;
-    colsum_kernel<<<dim3((unsigned)bx, (C + 31) / 32), 1024, 0, (cudaStream_t)stream>>>((const bf16*)a, rows, ld, chan_off, C, out);
+    colsum_kernel<<<dim3((unsigned)bx, (C + 31) / 32), 1024, 0, (cudaStream_t)stream>>>((const bf16*)a, rows, ld, chan_off, C, row_img, out);
     return irc_check_launch("irc_colsum");
 }

@@ -1,0 +1,516 @@
+"""Execution plans of the hot path: generator, discriminator and VGG trunk forward/backward as
+sequences of libirc_sm100 launches over pre-allocated NHWC bf16 frames.
+
+The engines own every buffer (nothing is allocated per step, so a step can be captured in a
+CUDA graph) and take a *backend* object that exposes one method per C-ABI entry point
+(`_native.CudaBackend` in the product).  Reference: irc = Code/ir_colorization.py."""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import layout as L
+from ._native import IDENTITY, Tables, View
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+EPS = 1e-5   # nn.InstanceNorm2d default (irc:161)
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)   # irc:667-668
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9) -> Dict[str, tuple]:
+    """state_dict parameter shapes of ResnetUNetGenerator with the default config (irc:457-531)"""
+    s = {"inc.1.weight": (ngf, input_nc, 7, 7), "inc.1.bias": (ngf,),
+         "down1.0.weight": (2 * ngf, ngf, 3, 3), "down1.0.bias": (2 * ngf,),
+         "down2.0.weight": (4 * ngf, 2 * ngf, 3, 3), "down2.0.bias": (4 * ngf,)}
+    for b in range(n_blocks):
+        for j in (1, 5):
+            s[f"resblocks.{b}.conv_block.{j}.weight"] = (4 * ngf, 4 * ngf, 3, 3)
+            s[f"resblocks.{b}.conv_block.{j}.bias"] = (4 * ngf,)
+    s["up1_conv.0.weight"] = (2 * ngf, 6 * ngf, 3, 3); s["up1_conv.0.bias"] = (2 * ngf,)
+    s["up2_conv.0.weight"] = (ngf, 3 * ngf, 3, 3); s["up2_conv.0.bias"] = (ngf,)
+    s["outc.1.weight"] = (output_nc, ngf, 7, 7); s["outc.1.bias"] = (output_nc,)
+    return s
+
+
+def discriminator_shapes(input_nc=4, ndf=64) -> Dict[str, tuple]:
+    """NLayerDiscriminator(n_layers=3) parameter shapes (irc:598-630)"""
+    chans = [(input_nc, ndf), (ndf, 2 * ndf), (2 * ndf, 4 * ndf), (4 * ndf, 8 * ndf), (8 * ndf, 1)]
+    s = {}
+    for idx, (ci, co) in zip((0, 2, 5, 8, 11), chans):
+        s[f"model.{idx}.weight"] = (co, ci, 4, 4); s[f"model.{idx}.bias"] = (co,)
+    return s
+
+
+VGG_CFG = [(0, 3, 64), (2, 64, 64), (5, 64, 128), (7, 128, 128), (10, 128, 256), (12, 256, 256), (14, 256, 256)]
+
+
+def vgg_shapes() -> Dict[str, tuple]:
+    s = {}
+    for idx, ci, co in VGG_CFG:
+        s[f"features.{idx}.weight"] = (co, ci, 3, 3); s[f"features.{idx}.bias"] = (co,)
+    return s
+
+
+def _splits_for(tiles: int, kb_total: int, sms: int = 148) -> int:
+    s = max(1, round(2 * sms / max(tiles, 1)))
+    return int(max(1, min(s, kb_total, 64)))
+
+
+class ConvOp:
+    """One convolution in its three GEMM roles over frame buffers."""
+
+    def __init__(self, be, lay: L.WeightLayout, taps: List[int], arena: L.ParamArena, max_rows: int, bias_name: Optional[str] = None):
+        self.be, self.lay, self.taps, self.arena = be, lay, list(taps), arena
+        self.bias_name = bias_name
+        N, T, K = lay.N, lay.T, lay.K
+        tiles = ((N + 127) // 128) * ((K + 255) // 256) * T
+        self.splits = _splits_for(tiles, (max_rows + 63) // 64)
+        self.partial = torch.zeros(self.splits * N * T * K, device=arena.device)
+        self.grad_flat = arena.grad[lay.param_offset:lay.param_offset + lay.param_numel]
+
+    def bias(self):
+        return self.arena.view(self.bias_name) if self.bias_name else None
+
+    def fwd(self, a, a_chan_off, out, **kw):
+        self.be.conv_gemm(a, a_chan_off, self.lay.K, self.taps, self.lay.w_f.t, self.lay.w_f.rows, out, **kw)
+
+    def dgrad(self, dz, out, **kw):
+        """out[q][k] = sum_t dz[q - tap_t][:] . W[:, t, k]   (gradient w.r.t. the conv input frame)"""
+        self.be.conv_gemm(dz, 0, self.lay.kd, [-t for t in self.taps], self.lay.w_d.t, self.lay.K, out, **kw)
+
+    def wgrad(self, dz, x, x_chan_off, k_rows):
+        lay = self.lay
+        self.be.tn_gemm(dz, 0, lay.N, x, x_chan_off, lay.K, k_rows, [0] * lay.T, self.taps, self.partial,
+                        lay.K, lay.T * lay.K, 1, self.splits, lay.N * lay.T * lay.K)
+        self.be.gather_sum(self.partial, lay.unpack, self.splits, lay.N * lay.T * lay.K, self.grad_flat)
+
+
+# ==========================================================================================
+# generator (irc:425-569)
+# ==========================================================================================
+class GeneratorEngine:
+    def __init__(self, be, B: int, H: int, W: int, device, ngf: int = 64, n_blocks: int = 9, training: bool = True):
+        if H % 4 or W % 4:
+            raise NotImplementedError("H and W must be multiples of 4 (the reference's odd-size bilinear fix-up, irc:555-563, is not built yet)")
+        if ngf != 64:
+            raise NotImplementedError("ngf must be 64 (channel counts are tiled in units of 64)")
+        self.be, self.B, self.H, self.W, self.dev, self.nb, self.training = be, B, H, W, device, n_blocks, training
+        self.arena = L.ParamArena(generator_shapes(1, 3, ngf, n_blocks), device)
+        self.packer = L.Packer(self.arena)
+        A, P = self.arena, self.packer
+        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        F = lambda h, w, p, c: L.Frame(B, h, w, p, c, device)
+        # ---- buffers (forward)
+        self.E_in = L.act_zeros(B * H * W, 64, device)
+        self.Z0 = F(H, W, 0, 64)
+        self.cat2 = F(H, W, 1, 192)       # [0:128) up2_up output, [128:192) x0
+        self.Z1 = F(H, W, 1, 128)
+        self.cat1 = F(H2, W2, 1, 384)     # [0:256) up1_up output, [256:384) x1
+        self.Z2 = F(H2, W2, 1, 256)
+        self.X = [F(H4, W4, 1, 256) for _ in range(n_blocks + 1)]
+        self.Za = [F(H4, W4, 1, 256) for _ in range(n_blocks)]
+        self.Hh = [F(H4, W4, 1, 256) for _ in range(n_blocks)]
+        self.Zb = [F(H4, W4, 1, 256) for _ in range(n_blocks)]
+        self.Z3 = F(H2, W2, 1, 128)
+        self.Z4 = F(H, W, 1, 64)
+        self.y4 = F(H, W, 3, 64)
+        self.P = torch.zeros(self.y4.rows, 32, device=device)
+        self.fake = torch.zeros(B, 3, H, W, device=device)
+        st = lambda c: torch.zeros(B, c, 2, device=device)
+        self.st0, self.st1, self.st2, self.st3, self.st4 = st(64), st(128), st(256), st(128), st(64)
+        self.sta = [st(256) for _ in range(n_blocks)]
+        self.stb = [st(256) for _ in range(n_blocks)]
+        self.bsum = st(256)
+        # ---- stencil tables
+        mk = lambda my, mx: L.make_tables(my, mx, device)
+        self.t_down1 = mk(L.down_matrix(H), L.down_matrix(W))
+        self.t_down2 = mk(L.down_matrix(H2), L.down_matrix(W2))
+        self.t_up1 = mk(L.up_matrix(H4), L.up_matrix(W4))
+        self.t_up2 = mk(L.up_matrix(H2), L.up_matrix(W2))
+        self.t_down1_T = mk(L.down_matrix(H).T, L.down_matrix(W).T)
+        self.t_down2_T = mk(L.down_matrix(H2).T, L.down_matrix(W2).T)
+        self.t_up1_T = mk(L.up_matrix(H4).T, L.up_matrix(W4).T)
+        self.t_up2_T = mk(L.up_matrix(H2).T, L.up_matrix(W2).T)
+        self.t_fold1 = mk(L.fold_matrix(H4, 1), L.fold_matrix(W4, 1))
+        self.t_fold3 = mk(L.fold_matrix(H, 3), L.fold_matrix(W, 3))
+        # ---- weights
+        wp1, wp2, wp4, wp3 = self.cat2.wp, self.cat1.wp, self.X[0].wp, self.y4.wp
+        self.inc = ConvOp(be, L.layout_im2col(P, A, "inc.1.weight", 64, 1, 7), [0], A, self.Z0.rows)
+        self.down1 = ConvOp(be, L.layout_std(P, A, "down1.0.weight", 128, 64, 3, 3), L.taps_centered(3, 3, wp1), A, self.Z1.rows)
+        self.down2 = ConvOp(be, L.layout_std(P, A, "down2.0.weight", 256, 128, 3, 3), L.taps_centered(3, 3, wp2), A, self.Z2.rows)
+        self.res = []
+        for b in range(n_blocks):
+            self.res.append(tuple(ConvOp(be, L.layout_std(P, A, f"resblocks.{b}.conv_block.{j}.weight", 256, 256, 3, 3),
+                                         L.taps_centered(3, 3, wp4), A, self.X[0].rows) for j in (1, 5)))
+        self.up1 = ConvOp(be, L.layout_std(P, A, "up1_conv.0.weight", 128, 384, 3, 3), L.taps_centered(3, 3, wp2), A, self.Z3.rows)
+        self.up2 = ConvOp(be, L.layout_std(P, A, "up2_conv.0.weight", 64, 192, 3, 3), L.taps_centered(3, 3, wp1), A, self.Z4.rows)
+        self.outc = ConvOp(be, L.layout_outc(P, A, "outc.1.weight", 3, 64, 7), [(r - 3) * wp3 for r in range(7)], A, self.y4.rows,
+                           bias_name="outc.1.bias")
+        self.outc_shifts = [s - 3 for s in range(7)]
+        P.finish()
+        if training:
+            self._alloc_backward()
+
+    def _alloc_backward(self):
+        B, H, W, dev = self.B, self.H, self.W, self.dev
+        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        F = lambda h, w, p, c: L.Frame(B, h, w, p, c, dev)
+        self.E_out = L.act_zeros(self.y4.rows, 64, dev)
+        self.G4 = F(H, W, 3, 64)
+        self.dZ4 = F(H, W, 1, 64)
+        self.Gcat2 = F(H, W, 1, 192)
+        self.dZ3 = F(H2, W2, 1, 128)
+        self.Gcat1 = F(H2, W2, 1, 384)
+        self.dOut = [F(H4, W4, 1, 256), F(H4, W4, 1, 256)]
+        self.dZb, self.Gh, self.dZa, self.Gx = (F(H4, W4, 1, 256) for _ in range(4))
+        self.dZ2 = F(H2, W2, 1, 256)
+        self.Gx1 = F(H2, W2, 1, 128)
+        self.dZ1 = F(H, W, 1, 128)
+        self.Gx0 = F(H, W, 1, 64)
+        self.dZ0 = F(H, W, 0, 64)
+
+    # ------------------------------------------------------------------ forward
+    def refresh_weights(self):
+        self.packer.refresh(self.be)
+
+    def forward(self, ir: torch.Tensor) -> torch.Tensor:
+        """ir: fp32 [B,1,H,W] -> fake fp32 [B,3,H,W] (irc:533-569)"""
+        be, B, H, W = self.be, self.B, self.H, self.W
+        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        assert ir.shape == (B, 1, H, W) and ir.dtype == torch.float32 and ir.is_contiguous()
+        # inc: reflect-pad 3 + 7x7 conv as im2col (49 of 64 slots) + one-tap GEMM, IN + ReLU into cat2[128:192)
+        be.im2col(ir, None, None, None, B, H, W, 7, 1, 3, 1, H, W, 0, self.E_in)
+        self.inc.fwd(self.E_in, 0, self.Z0.t)
+        be.in_stats(self.Z0.view(), 64, B, H, W, self.st0)
+        be.gather(self.Z0.view(), self.cat2.view(128), 64, B, H, W, 1, 0, stats=self.st0, cnt=H * W, eps=EPS, act=ACT_RELU)
+        # down1: 3x3 zero-pad conv at full resolution, then IN + ReLU + blur-downsample fused
+        self.down1.fwd(self.cat2.t, 128, self.Z1.t)
+        be.in_stats(self.Z1.view(), 128, B, H, W, self.st1)
+        be.gather(self.Z1.view(), self.cat1.view(256), 128, B, H2, W2, 1, 0, tables=self.t_down1, stats=self.st1, cnt=H * W, eps=EPS, act=ACT_RELU)
+        # down2
+        self.down2.fwd(self.cat1.t, 256, self.Z2.t)
+        be.in_stats(self.Z2.view(), 256, B, H2, W2, self.st2)
+        be.gather(self.Z2.view(), self.X[0].view(), 256, B, H4, W4, 1, 1, tables=self.t_down2, stats=self.st2, cnt=H2 * W2, eps=EPS, act=ACT_RELU)
+        # 9 ResNet blocks (irc:362-418): reflect halo written by the apply pass
+        n4 = H4 * W4
+        for b in range(self.nb):
+            c1, c2 = self.res[b]
+            c1.fwd(self.X[b].t, 0, self.Za[b].t)
+            be.in_stats(self.Za[b].view(), 256, B, H4, W4, self.sta[b])
+            be.gather(self.Za[b].view(), self.Hh[b].view(), 256, B, H4, W4, 1, 1, stats=self.sta[b], cnt=n4, eps=EPS, act=ACT_RELU)
+            c2.fwd(self.Hh[b].t, 0, self.Zb[b].t)
+            be.in_stats(self.Zb[b].view(), 256, B, H4, W4, self.stb[b])
+            be.gather(self.Zb[b].view(), self.X[b + 1].view(), 256, B, H4, W4, 1, 1, stats=self.stb[b], cnt=n4, eps=EPS, act=ACT_NONE,
+                      res=self.X[b].view())
+        # up1: UpsampleAA into cat1[0:256), conv on the concatenation
+        be.gather(self.X[self.nb].view(), self.cat1.view(0), 256, B, H2, W2, 1, 0, tables=self.t_up1)
+        self.up1.fwd(self.cat1.t, 0, self.Z3.t)
+        be.in_stats(self.Z3.view(), 128, B, H2, W2, self.st3)
+        # up2: IN + ReLU + UpsampleAA fused into cat2[0:128)
+        be.gather(self.Z3.view(), self.cat2.view(0), 128, B, H, W, 1, 0, tables=self.t_up2, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU)
+        self.up2.fwd(self.cat2.t, 0, self.Z4.t)
+        be.in_stats(self.Z4.view(), 64, B, H, W, self.st4)
+        be.gather(self.Z4.view(), self.y4.view(), 64, B, H, W, 3, 1, stats=self.st4, cnt=H * W, eps=EPS, act=ACT_RELU)
+        # outc: 7x7 reflect conv 64->3 as a GEMM over the 7 vertical taps (21 of 32 outputs), then the
+        # horizontal tap reduction + bias + tanh
+        self.outc.fwd(self.y4.t, 0, self.P)
+        be.tap_reduce(self.P, self.outc_shifts, 3, B, H, W, self.y4.hp, self.y4.wp, 3, 3, self.outc.bias(), ACT_TANH, self.fake)
+        return self.fake
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, dfake: torch.Tensor) -> None:
+        """dfake: fp32 [B,3,H,W] = dL/dfake.  Fills arena.grad for every generator parameter."""
+        be, B, H, W = self.be, self.B, self.H, self.W
+        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        y4 = self.y4
+        # outc: tanh' and horizontal tap expansion, then weight / data gradients over the vertical taps
+        be.tap_expand(dfake, self.fake, self.outc_shifts, 3, B, H, W, y4.hp, y4.wp, 3, 3, self.E_out,
+                      dbias=self.arena.view("outc.1.bias", self.arena.grad))
+        self.outc.wgrad(self.E_out, y4.t, 0, y4.rows)
+        self.outc.dgrad(self.E_out, self.G4.t)
+        # up2_conv
+        be.in_bwd(self.Z4.view(), self.G4.pview(), self.dZ4.view(), 64, B, H, W, stats=self.st4, cnt=H * W, eps=EPS, act=ACT_RELU,
+                  tables=self.t_fold3, bsum=self.bsum)
+        self.up2.wgrad(self.dZ4.t, self.cat2.t, 0, self.cat2.rows)
+        self.up2.dgrad(self.dZ4.t, self.Gcat2.t)
+        # up1_conv (through UpsampleAA^T)
+        be.in_bwd(self.Z3.view(), self.Gcat2.view(0), self.dZ3.view(), 128, B, H2, W2, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
+                  tables=self.t_up2_T, bsum=self.bsum)
+        self.up1.wgrad(self.dZ3.t, self.cat1.t, 0, self.cat1.rows)
+        self.up1.dgrad(self.dZ3.t, self.Gcat1.t)
+        # gradient w.r.t. the last ResNet block output = UpsampleAA^T of Gcat1[0:256)
+        cur = self.dOut[0]
+        be.gather(self.Gcat1.view(0), cur.view(), 256, B, H4, W4, 1, 0, tables=self.t_up1_T)
+        n4 = H4 * W4
+        for b in reversed(range(self.nb)):
+            c1, c2 = self.res[b]
+            be.in_bwd(self.Zb[b].view(), cur.view(), self.dZb.view(), 256, B, H4, W4, stats=self.stb[b], cnt=n4, eps=EPS, act=ACT_NONE, bsum=self.bsum)
+            c2.wgrad(self.dZb.t, self.Hh[b].t, 0, self.dZb.rows)
+            c2.dgrad(self.dZb.t, self.Gh.t)
+            be.in_bwd(self.Za[b].view(), self.Gh.pview(), self.dZa.view(), 256, B, H4, W4, stats=self.sta[b], cnt=n4, eps=EPS, act=ACT_RELU,
+                      tables=self.t_fold1, bsum=self.bsum)
+            c1.wgrad(self.dZa.t, self.X[b].t, 0, self.dZa.rows)
+            c1.dgrad(self.dZa.t, self.Gx.t)
+            nxt = self.dOut[1] if cur is self.dOut[0] else self.dOut[0]
+            be.gather(self.Gx.pview(), nxt.view(), 256, B, H4, W4, 1, 0, tables=self.t_fold1, res=cur.view())
+            cur = nxt
+        # down2 (through Downsample^T)
+        be.in_bwd(self.Z2.view(), cur.view(), self.dZ2.view(), 256, B, H2, W2, stats=self.st2, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
+                  tables=self.t_down2_T, bsum=self.bsum)
+        self.down2.wgrad(self.dZ2.t, self.cat1.t, 256, self.cat1.rows)
+        self.down2.dgrad(self.dZ2.t, self.Gx1.t)
+        # down1: x1 feeds down2 and the up1 skip connection
+        be.in_bwd(self.Z1.view(), self.Gcat1.view(256), self.dZ1.view(), 128, B, H, W, stats=self.st1, cnt=H * W, eps=EPS, act=ACT_RELU,
+                  tables=self.t_down1_T, g2=self.Gx1.view(), bsum=self.bsum)
+        self.down1.wgrad(self.dZ1.t, self.cat2.t, 128, self.cat2.rows)
+        self.down1.dgrad(self.dZ1.t, self.Gx0.t)
+        # inc: x0 feeds down1 and the up2 skip connection
+        be.in_bwd(self.Z0.view(), self.Gcat2.view(128), self.dZ0.view(), 64, B, H, W, stats=self.st0, cnt=H * W, eps=EPS, act=ACT_RELU,
+                  g2=self.Gx0.view(), bsum=self.bsum)
+        self.inc.wgrad(self.dZ0.t, self.E_in, 0, self.dZ0.rows)
+
+
+# ==========================================================================================
+# discriminator (irc:576-635)
+# ==========================================================================================
+class DiscriminatorEngine:
+    def __init__(self, be, n_img: int, H: int, W: int, device, arena: L.ParamArena = None, packer: L.Packer = None, layouts=None):
+        if H % 16 or W % 16:
+            raise NotImplementedError("discriminator engine needs H, W multiples of 16")
+        self.be, self.n, self.H, self.W, self.dev = be, n_img, H, W, device
+        own = arena is None
+        self.arena = arena or L.ParamArena(discriminator_shapes(4, 64), device)
+        self.packer = packer or L.Packer(self.arena)
+        A, P = self.arena, self.packer
+        n = n_img
+        H1, W1, H2, W2, H3, W3 = H // 2, W // 2, H // 4, W // 4, H // 8, W // 8
+        self.H1, self.W1, self.H2, self.W2, self.H3, self.W3 = H1, W1, H2, W2, H3, W3
+        self.hb0, self.wb0 = (H1 + 2) // 2, (W1 + 2) // 2          # s2d blocks of the padded model.0 output
+        self.hb2, self.wb2 = (H2 + 2) // 2, (W2 + 2) // 2          # s2d blocks of the padded model.2 output
+        bf = lambda r, c: L.act_zeros(r, c, device)
+        self.rows0 = n * (H1 + 2) * (W1 + 2)
+        self.E0 = bf(self.rows0, 64)
+        self.row_img0 = torch.zeros(self.rows0, device=device, dtype=torch.int16)
+        self.S0 = bf(self.rows0, 64)                                # == [n*hb0*wb0, 256] space-to-depth operand
+        self.S0v = self.S0.view(n * self.hb0 * self.wb0, 256)
+        self.Z2 = bf(n * self.hb0 * self.wb0, 128)
+        self.S2 = bf(n * self.hb2 * self.wb2, 512)
+        self.Z5 = bf(n * self.hb2 * self.wb2, 256)
+        self.X8 = L.Frame(n, H3, W3, 1, 256, device)
+        self.Z8 = bf(self.X8.rows, 512)
+        self.H8o, self.W8o = H3 - 1, W3 - 1                         # model.8 output (k4 s1 p1)
+        self.X11 = L.Frame(n, self.H8o, self.W8o, 1, 512, device)
+        self.Ho, self.Wo = self.H8o - 1, self.W8o - 1               # model.11 output
+        self.P11 = torch.zeros(self.X11.rows, 32, device=device)
+        self.pred = torch.zeros(n, 1, self.Ho, self.Wo, device=device)
+        st = lambda c: torch.zeros(n, c, 2, device=device)
+        self.st2, self.st5, self.st8, self.bsum = st(128), st(256), st(512), st(512)
+        # weights (shared between the 2B-image and B-image instances)
+        if layouts is None:
+            layouts = dict(
+                l0=L.layout_im2col(P, A, "model.0.weight", 64, 4, 4),
+                l2=L.layout_s2d(P, A, "model.2.weight", 128, 64),
+                l5=L.layout_s2d(P, A, "model.5.weight", 256, 128),
+                l8=L.layout_std(P, A, "model.8.weight", 512, 256, 4, 4),
+                l11=L.layout_pointwise_taps(P, A, "model.11.weight", 512, 4))
+        self.layouts = layouts
+        self.c0 = ConvOp(be, layouts["l0"], [0], A, self.rows0, bias_name="model.0.bias")
+        self.c2 = ConvOp(be, layouts["l2"], [0, 1, self.wb0, self.wb0 + 1], A, self.Z2.shape[0])
+        self.c5 = ConvOp(be, layouts["l5"], [0, 1, self.wb2, self.wb2 + 1], A, self.Z5.shape[0])
+        self.c8 = ConvOp(be, layouts["l8"], L.taps_topleft(4, 4, self.X8.wp), A, self.X8.rows)
+        self.c11 = ConvOp(be, layouts["l11"], [0], A, self.X11.rows, bias_name="model.11.bias")
+        self.shifts11 = L.taps_topleft(4, 4, self.X11.wp)
+        if own:
+            P.finish()
+        # backward buffers
+        self.dpred = torch.zeros_like(self.pred)
+        self.E11 = bf(self.X11.rows, 64)
+        self.G11 = L.Frame(n, self.H8o, self.W8o, 1, 512, device)
+        self.dZ8 = bf(self.X8.rows, 512)
+        self.G8 = L.Frame(n, H3, W3, 1, 256, device)
+        self.dZ5 = bf(n * self.hb2 * self.wb2, 256)
+        self.dS2 = bf(n * self.hb2 * self.wb2, 512)
+        self.dZ2 = bf(n * self.hb0 * self.wb0, 128)
+        self.dZ0 = bf(self.rows0, 64)
+        self.dZ0v = self.dZ0.view(n * self.hb0 * self.wb0, 256)
+        self.dE0 = bf(self.rows0, 64)
+
+    def refresh_weights(self):
+        self.packer.refresh(self.be)
+
+    def _vZ2(self, t):
+        return View(t, 0, self.hb0, self.wb0, 0, 0)
+
+    def _vZ5(self, t):
+        return View(t, 0, self.hb2, self.wb2, 0, 0)
+
+    def _vZ8(self, t):
+        return View(t, 0, self.X8.hp, self.X8.wp, 0, 0)
+
+    def forward(self, ir: torch.Tensor, img: torch.Tensor, ir_b: torch.Tensor = None, img_b: torch.Tensor = None) -> torch.Tensor:
+        """D(cat[ir, img]) -> fp32 [n,1,Ho,Wo] raw scores (irc:632-635).  (ir_b, img_b), if given, is a second
+        batch processed behind the first in the same launches (real and fake halves of the D step; InstanceNorm
+        is per sample, so batching is exact)."""
+        be, n, H, W = self.be, self.n, self.H, self.W
+        # model.0: 4x4 s2 conv on 4 channels = im2col with exactly 64 slots, rows in 2x2 sub-pixel order so the
+        # GEMM output *is* the space-to-depth operand of model.2; bias + LeakyReLU in the epilogue
+        n1 = ir.shape[0]
+        r1 = n1 * (self.H1 + 2) * (self.W1 + 2)
+        be.im2col(ir, img, None, None, n1, H, W, 4, 2, 1, 0, self.H1, self.W1, 2, self.E0[:r1], row_img=self.row_img0[:r1])
+        if ir_b is not None:
+            assert n1 + ir_b.shape[0] == n
+            be.im2col(ir_b, img_b, None, None, n - n1, H, W, 4, 2, 1, 0, self.H1, self.W1, 2, self.E0[r1:], row_img=self.row_img0[r1:])
+        else:
+            assert n1 == n
+        self.c0.fwd(self.E0, 0, self.S0, bias=self.c0.bias(), act=ACT_LRELU, slope=0.2, row_img=self.row_img0)
+        # model.2
+        self.c2.fwd(self.S0v, 0, self.Z2)
+        be.in_stats(self._vZ2(self.Z2), 128, n, self.H2, self.W2, self.st2)
+        be.gather(self._vZ2(self.Z2), View(self.S2, 0, self.hb2, self.wb2), 128, n, self.H2, self.W2, 1, 0, stats=self.st2,
+                  cnt=self.H2 * self.W2, eps=EPS, act=ACT_LRELU, slope=0.2, dst_s2d=1)
+        # model.5
+        self.c5.fwd(self.S2, 0, self.Z5)
+        be.in_stats(self._vZ5(self.Z5), 256, n, self.H3, self.W3, self.st5)
+        be.gather(self._vZ5(self.Z5), self.X8.view(), 256, n, self.H3, self.W3, 1, 0, stats=self.st5, cnt=self.H3 * self.W3, eps=EPS,
+                  act=ACT_LRELU, slope=0.2)
+        # model.8 (stride 1)
+        self.c8.fwd(self.X8.t, 0, self.Z8)
+        be.in_stats(self._vZ8(self.Z8), 512, n, self.H8o, self.W8o, self.st8)
+        be.gather(self._vZ8(self.Z8), self.X11.view(), 512, n, self.H8o, self.W8o, 1, 0, stats=self.st8, cnt=self.H8o * self.W8o, eps=EPS,
+                  act=ACT_LRELU, slope=0.2)
+        # model.11: 512->1, per-tap partial products then the 16-tap shifted reduction
+        self.c11.fwd(self.X11.t, 0, self.P11)
+        be.tap_reduce(self.P11, self.shifts11, 1, n, self.Ho, self.Wo, self.X11.hp, self.X11.wp, 0, 0, self.c11.bias(), ACT_NONE, self.pred)
+        return self.pred
+
+    def backward(self, dpred: torch.Tensor, want_wgrad: bool, dinput: Optional[torch.Tensor] = None) -> None:
+        """dpred = dL/dscores.  want_wgrad fills arena.grad; dinput (fp32 [n,3,H,W]) accumulates the
+        gradient w.r.t. the image half of the input (channels 1..3 of cat[ir, img])."""
+        be, n = self.be, self.n
+        G = self.arena.grad
+        be.tap_expand(dpred, None, self.shifts11, 1, n, self.Ho, self.Wo, self.X11.hp, self.X11.wp, 0, 0, self.E11,
+                      dbias=self.arena.view("model.11.bias", G) if want_wgrad else None)
+        if want_wgrad:
+            self.c11.wgrad(self.E11, self.X11.t, 0, self.X11.rows)
+        self.c11.dgrad(self.E11, self.G11.t)
+        be.in_bwd(self._vZ8(self.Z8), self.G11.view(), self._vZ8(self.dZ8), 512, n, self.H8o, self.W8o, stats=self.st8,
+                  cnt=self.H8o * self.W8o, eps=EPS, act=ACT_LRELU, slope=0.2, bsum=self.bsum)
+        if want_wgrad:
+            self.c8.wgrad(self.dZ8, self.X8.t, 0, self.X8.rows)
+        self.c8.dgrad(self.dZ8, self.G8.t)
+        be.in_bwd(self._vZ5(self.Z5), self.G8.view(), self._vZ5(self.dZ5), 256, n, self.H3, self.W3, stats=self.st5,
+                  cnt=self.H3 * self.W3, eps=EPS, act=ACT_LRELU, slope=0.2, bsum=self.bsum)
+        if want_wgrad:
+            self.c5.wgrad(self.dZ5, self.S2, 0, self.S2.shape[0])
+        self.c5.dgrad(self.dZ5, self.dS2)
+        be.in_bwd(self._vZ2(self.Z2), View(self.dS2, 0, self.hb2, self.wb2, 1, 1, 128), self._vZ2(self.dZ2), 128, n, self.H2, self.W2,
+                  stats=self.st2, cnt=self.H2 * self.W2, eps=EPS, act=ACT_LRELU, slope=0.2, bsum=self.bsum)
+        if want_wgrad:
+            self.c2.wgrad(self.dZ2, self.S0v, 0, self.S0v.shape[0])
+        # data gradient of model.2 lands in space-to-depth order == the row order of model.0's output; the
+        # LeakyReLU mask of model.0 is applied in the GEMM epilogue
+        self.c2.dgrad(self.dZ2, self.dZ0v, mask=View(self.S0v, 0, 0, 0), mask_slope=0.2)
+        if want_wgrad:
+            be.colsum(self.dZ0, 0, 64, self.arena.view("model.0.bias", G), row_img=self.row_img0)
+            self.c0.wgrad(self.dZ0, self.E0, 0, self.rows0)
+        if dinput is not None:
+            self.c0.dgrad(self.dZ0, self.dE0)
+            be.col2im(self.dE0, 4, 1, 3, n, self.H, self.W, 4, 2, 1, self.H1, self.W1, 2, None, dinput, True)
+
+
+# ==========================================================================================
+# VGG-16 features[:16] (irc:642-683)
+# ==========================================================================================
+class VggEngine:
+    """Frozen trunk.  n_img images go forward; backward (data gradient only) runs on the first
+    n_bwd of them (the `fake` half when fake and target are batched together)."""
+
+    def __init__(self, be, n_img: int, n_bwd: int, H: int, W: int, device):
+        if H % 4 or W % 4:
+            raise NotImplementedError("VGG engine needs H, W multiples of 4")
+        self.be, self.n, self.nb, self.H, self.W, self.dev = be, n_img, n_bwd, H, W, device
+        self.arena = L.ParamArena(vgg_shapes(), device)
+        self.packer = L.Packer(self.arena)
+        A, P = self.arena, self.packer
+        res = [(H, W), (H, W), (H // 2, W // 2), (H // 2, W // 2), (H // 4, W // 4), (H // 4, W // 4), (H // 4, W // 4)]
+        self.res = res
+        self.act: List[L.Frame] = []
+        self.convs: List[ConvOp] = []
+        for i, (idx, ci, co) in enumerate(VGG_CFG):
+            h, w = res[i]
+            fr = L.Frame(n_img, h, w, 1, co, device)
+            self.act.append(fr)
+            if i == 0:
+                lay = L.layout_im2col(P, A, f"features.{idx}.weight", co, ci, 3)
+                taps = [0]
+            else:
+                lay = L.layout_std(P, A, f"features.{idx}.weight", co, ci, 3, 3)
+                taps = L.taps_centered(3, 3, fr.wp)
+            self.convs.append(ConvOp(be, lay, taps, A, 64, bias_name=f"features.{idx}.bias"))
+        P.finish()
+        self.pool = {1: L.Frame(n_img, H // 2, W // 2, 1, 64, device), 3: L.Frame(n_img, H // 4, W // 4, 1, 128, device)}
+        self.E = L.act_zeros(self.act[0].rows, 64, device)
+        self.row_img = []
+        for (h, w) in ((H, W), (H // 2, W // 2), (H // 4, W // 4)):
+            ri = torch.zeros(n_img * (h + 2) * (w + 2), device=device, dtype=torch.int16)
+            be.row_index(ri, n_img, h + 2, w + 2, 1, h + 1, 1, w + 1)
+            self.row_img.append(ri)
+        mean = torch.tensor(IMAGENET_MEAN, device=device); std = torch.tensor(IMAGENET_STD, device=device)
+        self.scale = (0.5 / std).contiguous()                # ((x+1)/2 - mean)/std = x*scale + shift
+        self.shift = ((0.5 - mean) / std).contiguous()
+        if n_bwd:
+            self.dz = [L.Frame(n_bwd, h, w, 1, co, device) for (h, w), (_, _, co) in zip(res, VGG_CFG)]
+            self.dpool = {1: L.Frame(n_bwd, H // 2, W // 2, 1, 64, device), 3: L.Frame(n_bwd, H // 4, W // 4, 1, 128, device)}
+            self.dE = L.act_zeros(self.dz[0].rows, 64, device)
+
+    def refresh_weights(self):
+        self.packer.refresh(self.be)
+
+    def _ri(self, i):
+        return self.row_img[0 if i < 2 else (1 if i < 4 else 2)]
+
+    def forward(self, x1: torch.Tensor, x2: Optional[torch.Tensor] = None) -> L.Frame:
+        """images in [-1,1], fp32 NCHW; x2 (optional) is batched after x1.  Returns the relu3_3 frame."""
+        be = self.be
+        n1 = x1.shape[0]
+        H, W = self.H, self.W
+        rows1 = self.act[0].rows_of(n1)
+        be.im2col(x1, None, self.scale, self.shift, n1, H, W, 3, 1, 1, 0, H, W, 1, self.E[:rows1])
+        if x2 is not None:
+            be.im2col(x2, None, self.scale, self.shift, x2.shape[0], H, W, 3, 1, 1, 0, H, W, 1, self.E[rows1:])
+        src = self.E
+        for i, conv in enumerate(self.convs):
+            fr = self.act[i]
+            conv.fwd(src, 0, fr.t, bias=conv.bias(), act=ACT_RELU, row_img=self._ri(i))
+            if i in self.pool:
+                h, w = self.res[i + 1]
+                be.maxpool2(fr.view(), self.pool[i].view(), fr.C, self.n, h, w)
+                src = self.pool[i].t
+            else:
+                src = fr.t
+        return self.act[-1]
+
+    def backward(self, dfake: torch.Tensor) -> None:
+        """self.dz[-1] must hold dL/d(pre-ReLU conv3_3) of the first n_bwd images; accumulates into dfake."""
+        be, nb = self.be, self.nb
+        for i in range(len(self.convs) - 1, 0, -1):
+            conv = self.convs[i]
+            dz = self.dz[i].t
+            if (i - 1) in self.pool:
+                # input of conv i is the pooled frame: data gradient w.r.t. it, then route through the max-pool
+                # and the ReLU of conv i-1
+                conv.dgrad(dz, self.dpool[i - 1].t)
+                h, w = self.res[i]
+                src = self.act[i - 1]
+                be.maxpool2_bwd(View(src.t[:src.rows_of(nb)], 0, src.hp, src.wp, 1, 1), self.dpool[i - 1].view(), self.dz[i - 1].view(),
+                                src.C, nb, h, w)
+            else:
+                prev = self.act[i - 1]
+                conv.dgrad(dz, self.dz[i - 1].t, mask=View(prev.t[:prev.rows_of(nb)], 0, 0, 0), mask_slope=0.0)
+        self.convs[0].dgrad(self.dz[0].t, self.dE)
+        be.col2im(self.dE, 3, 0, 3, nb, self.H, self.W, 3, 1, 1, self.H, self.W, 1, self.scale, dfake, True)

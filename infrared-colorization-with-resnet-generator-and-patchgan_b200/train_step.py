@@ -1,0 +1,158 @@
+"""The fused D+G training iteration (irc:1629-1685) and the batched test-mode core
+(irc:1381-1389, :865-876, :1197-1205) on top of the engines.
+
+Result-preserving savings over the reference loop: the no-grad generator
+forward of the D update (irc:1638) and the generator forward of the G update (irc:1657) are
+the same computation (G is only updated at irc:1681), so it runs once; the G-step backward does
+not compute discriminator weight gradients (irc:1636 discards them); vgg(rgb) keeps no
+activations; D(real) and D(fake) of the D update run as one 2B-image pass."""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import layout as L
+from .engine import DiscriminatorEngine, GeneratorEngine, VggEngine
+
+LAMBDAS = dict(L1=30.0, perc=30.0, tv=1e-4, ssim=2.0, gan=0.1)   # irc:100-104
+
+
+def gaussian_window(device, n: int = 11, sigma: float = 1.5) -> torch.Tensor:
+    """irc:699-703, evaluated in fp32 exactly as the reference does"""
+    c = torch.arange(n, dtype=torch.float32) - (n - 1) / 2.0
+    g = torch.exp(-(c ** 2) / (2 * sigma ** 2))
+    return (g / g.sum()).to(device).contiguous()
+
+
+class AdamHyper:
+    """Host side of the fused Adam: step count, lr schedule factor, bias corrections (torch.optim.Adam
+    defaults of irc:1601-1604) staged into a 7-float device vector read by irc_adam."""
+
+    def __init__(self, device, lr: float, beta1: float, beta2: float, eps: float = 1e-8):
+        self.lr, self.b1, self.b2, self.eps, self.t = lr, beta1, beta2, eps, 0
+        self.dev = torch.zeros(8, device=device)
+        self.host = torch.zeros(8).pin_memory() if torch.device(device).type == "cuda" else torch.zeros(8)
+
+    def advance(self, lr_scale: float, grad_scale: float) -> None:
+        self.t += 1
+        h = self.host
+        h[0] = self.lr * lr_scale; h[1] = self.b1; h[2] = self.b2; h[3] = self.eps
+        h[4] = 1.0 - self.b1 ** self.t; h[5] = 1.0 - self.b2 ** self.t; h[6] = grad_scale
+        self.dev.copy_(h, non_blocking=True)
+
+
+class TrainStep:
+    """One process = one GPU = one replica.  With world_size > 1 the flat gradient arenas are
+    all-reduced (sum) over NCCL and the 1/world_size average is folded into the Adam kernel."""
+
+    def __init__(self, be, B: int, H: int, W: int, device, lr_G=2e-4, lr_D=2e-4, beta1=0.5, beta2=0.999, lambdas=LAMBDAS,
+                 world_size: int = 1, process_group=None, use_graph: bool = False):
+        self.be, self.B, self.H, self.W, self.dev = be, B, H, W, device
+        self.lam = dict(lambdas)
+        self.world, self.pg = world_size, process_group
+        self.G = GeneratorEngine(be, B, H, W, device)
+        self.D2 = DiscriminatorEngine(be, 2 * B, H, W, device)
+        self.D1 = DiscriminatorEngine(be, B, H, W, device, arena=self.D2.arena, packer=self.D2.packer, layouts=self.D2.layouts)
+        self.V = VggEngine(be, 2 * B, B, H, W, device)
+        self.optG = AdamHyper(device, lr_G, beta1, beta2)
+        self.optD = AdamHyper(device, lr_D, beta1, beta2)
+        self.window = gaussian_window(device)
+        self.sums = torch.zeros(8 + B, device=device)
+        self.dfake = torch.zeros(B, 3, H, W, device=device)
+        self.ga, self.gb, self.gc = (torch.zeros(B, 3, H, W, device=device) for _ in range(3))
+        self.ir = torch.zeros(B, 1, H, W, device=device)
+        self.rgb = torch.zeros(B, 3, H, W, device=device)
+        self.use_graph = use_graph and world_size == 1
+        self.graph = None
+        self._side = None
+        self.n_pred = self.D1.pred[0].numel()
+
+    # ------------------------------------------------------------------ parameters
+    def load(self, pG: Dict[str, torch.Tensor], pD: Dict[str, torch.Tensor], pV: Dict[str, torch.Tensor]) -> None:
+        self.G.arena.load(pG); self.D2.arena.load(pD); self.V.arena.load(pV)
+        self.refresh_weights()
+
+    def refresh_weights(self) -> None:
+        self.G.refresh_weights(); self.D2.refresh_weights(); self.V.refresh_weights()
+
+    # ------------------------------------------------------------------ the iteration
+    def _allreduce(self, arena: L.ParamArena) -> None:
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(arena.grad, group=self.pg)
+
+    def _body(self) -> None:
+        be, B, H, W, lam = self.be, self.B, self.H, self.W, self.lam
+        ir, rgb = self.ir, self.rgb
+        be.zero_(self.sums)
+        fake = self.G.forward(ir)                                             # irc:1638 and irc:1657
+        # ---------------- D update (irc:1636-1651)
+        pred = self.D2.forward(ir, rgb, ir, fake)                              # irc:1639-1643
+        cnt = B * self.n_pred
+        be.hinge(pred, cnt, 0, 0.5 / cnt, 0.5 / cnt, self.sums[0:3], self.D2.dpred)   # irc:1647-1649
+        self.D2.backward(self.D2.dpred, True)                                  # irc:1650
+        self._allreduce(self.D2.arena)
+        A = self.D2.arena
+        be.adam(A.flat, A.grad, A.m, A.v, self.optD.dev)                       # irc:1651
+        self.D2.refresh_weights()
+        # ---------------- G update (irc:1656-1681)
+        pred_f = self.D1.forward(ir, fake)                                     # irc:1659
+        be.hinge(pred_f, 0, 1, lam["gan"] / cnt, 0.0, self.sums[0:3], self.D1.dpred)   # irc:1662, :1679
+        npix = B * 3 * H * W
+        be.pixel_loss(fake, rgb, lam["L1"] / npix, lam["tv"] / (B * 3 * (H - 1) * W), lam["tv"] / (B * 3 * H * (W - 1)),
+                      self.sums[3:6], self.dfake)                              # irc:1664, :1672
+        be.ssim_fwd(fake, rgb, 0.5, 0.5, self.window, self.sums[8:8 + B], self.ga, self.gb, self.gc)   # irc:1675-1677
+        be.ssim_bwd(fake, rgb, 0.5, 0.5, self.window, self.ga, self.gb, self.gc, -lam["ssim"] / npix, self.dfake, True)
+        feat = self.V.forward(fake, rgb)                                       # irc:1667-1668
+        nfeat = B * 256 * (H // 4) * (W // 4)
+        be.feat_l1(feat.t, feat.rows_of(B), 256, lam["perc"] / nfeat, self.sums[6:7], self.V.dz[-1].t)   # irc:1669
+        self.V.backward(self.dfake)
+        self.D1.backward(self.D1.dpred, False, self.dfake)
+        self.G.backward(self.dfake)                                            # irc:1680
+        self._allreduce(self.G.arena)
+        A = self.G.arena
+        be.adam(A.flat, A.grad, A.m, A.v, self.optG.dev)                       # irc:1681
+        self.G.refresh_weights()
+
+    def step(self, ir: torch.Tensor, rgb: torch.Tensor, lr_scale: float = 1.0) -> None:
+        """One iteration on a device-resident batch (fp32 NCHW in [-1,1])."""
+        self.ir.copy_(ir, non_blocking=True); self.rgb.copy_(rgb, non_blocking=True)
+        gs = 1.0 / self.world
+        self.optD.advance(lr_scale, gs); self.optG.advance(lr_scale, gs)
+        if not self.use_graph:
+            self._body()
+            return
+        if self.graph is None:
+            # warm-up on a side stream (sets kernel attributes, primes allocators), undo its effect on
+            # the optimizer state, then capture
+            snap = [t.clone() for a in (self.G.arena, self.D2.arena) for t in (a.flat, a.m, a.v)]
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._body()
+            torch.cuda.current_stream().wait_stream(s)
+            for t, c in zip([t for a in (self.G.arena, self.D2.arena) for t in (a.flat, a.m, a.v)], snap):
+                t.copy_(c)
+            self.refresh_weights()
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = self.be.launches
+            with torch.cuda.graph(self.graph):
+                self._body()
+            self.launches_per_step = self.be.launches - n0
+        self.graph.replay()
+
+    def losses(self) -> Dict[str, float]:
+        """Loss terms of the last iteration, as printed by the reference (irc:1687-1694).  Synchronises."""
+        s = self.sums.tolist()
+        B, H, W, lam = self.B, self.H, self.W, self.lam
+        cnt = B * self.n_pred
+        npix = B * 3 * H * W
+        out = dict(D=0.5 * (s[0] / cnt + s[1] / cnt), GAN=-s[2] / cnt, L1=lam["L1"] * s[3] / npix,
+                   TV=lam["tv"] * (s[4] / (B * 3 * (H - 1) * W) + s[5] / (B * 3 * H * (W - 1))),
+                   perc=lam["perc"] * s[6] / (B * 256 * (H // 4) * (W // 4)),
+                   SSIM=lam["ssim"] * (1.0 - sum(s[8:8 + B]) / npix))
+        out["G"] = lam["gan"] * out["GAN"] + out["L1"] + out["perc"] + out["TV"] + out["SSIM"]
+        return out
