@@ -89,8 +89,9 @@ typedef struct irc_view {
 int irc_row_index(short* row_img, int n_img, int hp, int wp, int y0, int y1, int x0, int x1, void* stream);
 
 /* InstanceNorm statistics (nn.InstanceNorm2d, irc:161): stats[n][c] = (sum, sum of squares)
- * over the H x W pixels of view z. */
-int irc_in_stats(const irc_view* z, int C, int n_img, int H, int W, float* stats, void* stream);
+ * over the H x W pixels of view z.  Reductions here are two-stage and order-fixed (bit-reproducible):
+ * `work` (optional, work_floats floats) holds the per-chunk partials; without it one block per image runs. */
+int irc_in_stats(const irc_view* z, int C, int n_img, int H, int W, float* stats, float* work, long long work_floats, void* stream);
 
 /* Separable table gather into a frame:
  *   dst[n,Y,X,:] = halo( sum_ij ty_w[y][i] tx_w[x][j] * pre(src)[n, ty_idx[y][i], tx_idx[x][j], :] (+ src2[same]) + res[n,y,x,:] )
@@ -118,7 +119,9 @@ typedef struct irc_in_bwd_args {
     const float* stats; float cnt, eps; int act; float slope;
     const int* ty_idx; const float* ty_w; int ky;
     const int* tx_idx; const float* tx_w; int kx;
-    float* bsum;            /* [n][C][2] workspace */
+    float* bsum;            /* [n][C][2] result of the reduce pass */
+    float* work;            /* optional partials workspace of the reduce pass */
+    long long work_floats;
 } irc_in_bwd_args;
 int irc_in_bwd_reduce(const irc_in_bwd_args* args, void* stream);
 int irc_in_bwd_apply(const irc_in_bwd_args* args, void* stream);
@@ -129,7 +132,8 @@ int irc_maxpool2(const irc_view* src, const irc_view* dst, int C, int n_img, int
 int irc_maxpool2_bwd(const irc_view* src, const irc_view* g, const irc_view* dsrc, int C, int n_img, int Ho, int Wo, void* stream);
 
 /* out[c] = sum over rows (with row_img[row] >= 0 when given) of a[row][chan_off + c]  (bias gradients) */
-int irc_colsum(const void* a, long long rows, long long ld, int chan_off, int C, const short* row_img, float* out, void* stream);
+int irc_colsum(const void* a, long long rows, long long ld, int chan_off, int C, const short* row_img, float* out, float* work,
+               long long work_floats, void* stream);
 
 /* ---- degenerate convolutions (tiny K or tiny N) --------------------------------------- */
 
@@ -182,7 +186,7 @@ int irc_pixel_loss(const float* fake, const float* target, int n_img, int C, int
 /* ssim_loss_torch (irc:714-750): 11-tap Gaussian separable window, zero padding 5.  Inputs are
  * mapped x = img*scale + shift first (irc:1675-1676 uses (x+1)/2).  fwd: sums[n] += sum of the
  * SSIM map of image n, and (if ga != NULL) the maps dS/dmu1, dS/dE[x^2], dS/dE[xy]; bwd:
- * dimg1 (+)= coef*scale*(w*ga + 2x w*gb + y w*gc). */
+ * dimg1 (+)= coef*scale*(w*ga + 2x w*gb + y w*gc).  window11 is a HOST array of the 11 taps. */
 int irc_ssim_fwd(const float* img1, const float* img2, int n_img, int C, int H, int W, float scale, float shift, const float* window11,
                  float* sums, float* ga, float* gb, float* gc, void* stream);
 int irc_ssim_bwd(const float* img1, const float* img2, int n_img, int C, int H, int W, float scale, float shift, const float* window11,

@@ -78,7 +78,7 @@ class InBwdArgs(C.Structure):
         ("stats", C.c_void_p), ("cnt", C.c_float), ("eps", C.c_float), ("act", C.c_int), ("slope", C.c_float),
         ("ty_idx", C.c_void_p), ("ty_w", C.c_void_p), ("ky", C.c_int),
         ("tx_idx", C.c_void_p), ("tx_w", C.c_void_p), ("kx", C.c_int),
-        ("bsum", C.c_void_p),
+        ("bsum", C.c_void_p), ("work", C.c_void_p), ("work_floats", C.c_longlong),
     ]
 
 
@@ -194,6 +194,8 @@ class CudaBackend:
         self.L = lib()
         arch_check()
         self.launches = 0
+        # partials of the order-fixed two-stage reductions (InstanceNorm statistics, bias gradients)
+        self.work = torch.zeros(1 << 22, device="cuda")
 
     # ---- tensor-core GEMMs
     def conv_gemm(self, a, a_chan_off, cin, taps: Sequence[int], w, n_out, out, out_chan_off=0, bias=None, act=0, slope=0.0,
@@ -236,7 +238,8 @@ class CudaBackend:
 
     def in_stats(self, z: View, C_, n_img, H, W, stats):
         cv = _cview(z)
-        check(self.L.irc_in_stats(C.byref(cv), C_, n_img, H, W, _p(stats), _stream())); self.launches += 1
+        check(self.L.irc_in_stats(C.byref(cv), C_, n_img, H, W, _p(stats), _p(self.work), C.c_longlong(self.work.numel()), _stream()))
+        self.launches += 2
 
     def gather(self, src: View, dst: View, C_, n_img, H, W, pad, halo_mode, tables: Tables = IDENTITY, src2=None, res=None,
                stats=None, cnt=0.0, eps=1e-5, act=0, slope=0.0, dst_s2d=0):
@@ -261,6 +264,7 @@ class CudaBackend:
         g.tx_idx = None if tables.tx_idx is None else tables.tx_idx.data_ptr()
         g.tx_w = None if tables.tx_w is None else tables.tx_w.data_ptr(); g.kx = tables.kx
         g.bsum = None if bsum is None else bsum.data_ptr()
+        g.work = self.work.data_ptr(); g.work_floats = self.work.numel()
         return g
 
     def in_bwd(self, z: View, g1: View, dz: View, C_, n_img, H, W, stats=None, cnt=0.0, eps=1e-5, act=0, slope=0.0,
@@ -268,7 +272,7 @@ class CudaBackend:
         """reduce (when normalised) + apply."""
         g = self._bwd_args(z, g1, g2, dz, C_, n_img, H, W, stats, cnt, eps, act, slope, tables, bsum)
         if stats is not None:
-            check(self.L.irc_in_bwd_reduce(C.byref(g), _stream())); self.launches += 1
+            check(self.L.irc_in_bwd_reduce(C.byref(g), _stream())); self.launches += 2
         check(self.L.irc_in_bwd_apply(C.byref(g), _stream())); self.launches += 1
 
     def maxpool2(self, src: View, dst: View, C_, n_img, Ho, Wo):
@@ -280,7 +284,8 @@ class CudaBackend:
         check(self.L.irc_maxpool2_bwd(C.byref(a), C.byref(b), C.byref(c), C_, n_img, Ho, Wo, _stream())); self.launches += 1
 
     def colsum(self, a, chan_off, C_, out, row_img=None):
-        check(self.L.irc_colsum(_p(a), C.c_longlong(a.shape[0]), C.c_longlong(a.shape[1]), chan_off, C_, _p(row_img), _p(out), _stream()))
+        check(self.L.irc_colsum(_p(a), C.c_longlong(a.shape[0]), C.c_longlong(a.shape[1]), chan_off, C_, _p(row_img), _p(out),
+                                _p(self.work), C.c_longlong(self.work.numel()), _stream()))
         self.launches += 1
 
     # ---- degenerate convolutions
@@ -329,14 +334,20 @@ class CudaBackend:
         check(self.L.irc_pixel_loss(_p(fake), _p(target), n, c, h, w, C.c_float(w_l1), C.c_float(w_tvv), C.c_float(w_tvh),
                                     _p(sums), _p(dfake), _stream())); self.launches += 1
 
+    @staticmethod
+    def _win(window):
+        """the 11 window taps are a HOST array in the C ABI (they travel as a kernel argument)"""
+        assert window.device.type == "cpu" and window.numel() == 11
+        return (C.c_float * 11)(*[float(v) for v in window.tolist()])
+
     def ssim_fwd(self, img1, img2, scale, shift, window, sums, ga=None, gb=None, gc=None):
         n, c, h, w = img1.shape
-        check(self.L.irc_ssim_fwd(_p(img1), _p(img2), n, c, h, w, C.c_float(scale), C.c_float(shift), _p(window), _p(sums),
+        check(self.L.irc_ssim_fwd(_p(img1), _p(img2), n, c, h, w, C.c_float(scale), C.c_float(shift), self._win(window), _p(sums),
                                   _p(ga), _p(gb), _p(gc), _stream())); self.launches += 1
 
     def ssim_bwd(self, img1, img2, scale, shift, window, ga, gb, gc, coef, dimg1, accumulate):
         n, c, h, w = img1.shape
-        check(self.L.irc_ssim_bwd(_p(img1), _p(img2), n, c, h, w, C.c_float(scale), C.c_float(shift), _p(window), _p(ga), _p(gb),
+        check(self.L.irc_ssim_bwd(_p(img1), _p(img2), n, c, h, w, C.c_float(scale), C.c_float(shift), self._win(window), _p(ga), _p(gb),
                                   _p(gc), C.c_float(coef), _p(dimg1), int(accumulate), _stream())); self.launches += 1
 
     def hinge(self, pred, n_real, mode, w_real, w_fake, sums, dpred):

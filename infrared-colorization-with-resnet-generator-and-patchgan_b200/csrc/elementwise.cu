@@ -78,7 +78,7 @@ __global__ void row_index_kernel(short* out, int n_img, int hp, int wp, int y0, 
 // per-(image, channel) sum and sum of squares over the H x W pixels of a view
 // block = (C/8) channel vectors x L pixel lanes; grid = (chunks, N)
 // ---------------------------------------------------------------------------------
-__global__ void in_stats_kernel(View z, int C, int H, int W, float* stats) {
+__global__ void in_stats_kernel(View z, int C, int H, int W, float* part) {
     extern __shared__ float sh[];
     const int C8 = C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
@@ -103,7 +103,16 @@ __global__ void in_stats_kernel(View z, int C, int H, int W, float* stats) {
     for (int i = threadIdx.x; i < C8 * 16; i += blockDim.x) {
         float a = 0.f;
         for (int l = 0; l < L; ++l) a += shs[l * C8 * 16 + i];
-        atomicAdd(stats + (long long)n * C * 2 + i, a);
+        part[((long long)blockIdx.x * gridDim.y + n) * C * 2 + i] = a;
+    }
+}
+
+// out[j] = sum over chunks (fixed order) of part[chunk][j]: deterministic second stage of the reductions
+__global__ void sum_chunks_kernel(const float* __restrict__ part, int chunks, long long n, float* __restrict__ out) {
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+        float a = 0.f;
+        for (int c = 0; c < chunks; ++c) a += part[(long long)c * n + j];
+        out[j] = a;
     }
 }
 
@@ -197,6 +206,7 @@ struct InBwdP {
     const int* ty_idx; const float* ty_w; int ky;
     const int* tx_idx; const float* tx_w; int kx;
     float* bsum;
+    float* part;
 };
 
 __device__ __forceinline__ void bwd_gather(const InBwdP& p, int n, int y, int x, int c, float (&g)[8]) {
@@ -255,7 +265,7 @@ __global__ void in_bwd_reduce_kernel(const InBwdP p) {
     for (int i = threadIdx.x; i < C8 * 16; i += blockDim.x) {
         float a = 0.f;
         for (int l = 0; l < L; ++l) a += sh[l * C8 * 16 + i];
-        atomicAdd(p.bsum + (long long)n * p.C * 2 + i, a);
+        p.part[((long long)blockIdx.x * gridDim.y + n) * p.C * 2 + i] = a;
     }
 }
 
@@ -351,7 +361,7 @@ __global__ void maxpool_bwd_kernel(View src, View g, View dsrc, int C, int n_img
 }
 
 // column sums of a bf16 [rows][ld] matrix slice -> fp32 [C] (bias gradients)
-__global__ void colsum_kernel(const bf16* a, long long rows, long long ld, int off, int C, const short* row_img, float* out) {
+__global__ void colsum_kernel(const bf16* a, long long rows, long long ld, int off, int C, const short* row_img, float* part) {
     const int c = blockIdx.y * 32 + (threadIdx.x & 31);
     const int lane_r = threadIdx.x >> 5, R = blockDim.x >> 5;
     float s = 0.f;
@@ -364,7 +374,7 @@ __global__ void colsum_kernel(const bf16* a, long long rows, long long ld, int o
     if (lane_r == 0 && c < C) {
         float t = 0.f;
         for (int i = 0; i < R; ++i) t += sh[i][threadIdx.x & 31];
-        atomicAdd(out + c, t);
+        part[(long long)blockIdx.x * C + c] = t;
     }
 }
 
@@ -383,13 +393,15 @@ int check_view(const irc_view& v, const char* what) {
 }
 
 // block shape for the per-(n,c) reductions
-void reduce_shape(int C, int P, int n_img, int& threads, int& L, int& chunks, size_t& smem) {
+void reduce_shape(int C, int P, int n_img, long long work_floats, int& threads, int& L, int& chunks, size_t& smem) {
     const int C8 = C / 8;
     L = 256 / C8; if (L < 1) L = 1;
     threads = L * C8;
     long long want = ((long long)irc_num_sms() * 4 + n_img - 1) / n_img;
     long long maxc = (P + L - 1) / L;
     chunks = (int)(want < maxc ? want : maxc);
+    const long long cap = work_floats / ((long long)n_img * C * 2);
+    if (chunks > cap) chunks = (int)cap;
     if (chunks < 1) chunks = 1;
     smem = (size_t)L * C8 * 16 * sizeof(float);
 }
@@ -403,13 +415,18 @@ extern "C" int irc_row_index(short* row_img, int n_img, int hp, int wp, int y0, 
     return irc_check_launch("irc_row_index");
 }
 
-extern "C" int irc_in_stats(const irc_view* z, int C, int n_img, int H, int W, float* stats, void* stream) {
+extern "C" int irc_in_stats(const irc_view* z, int C, int n_img, int H, int W, float* stats, float* work, long long work_floats, void* stream) {
     int rc = check_view(*z, "irc_in_stats"); if (rc) return rc;
     if (C % 8 || C > 2048) return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_stats: C must be a multiple of 8");
-    cudaMemsetAsync(stats, 0, sizeof(float) * 2 * C * n_img, (cudaStream_t)stream);
     int threads, L, chunks; size_t smem;
-    reduce_shape(C, H * W, n_img, threads, L, chunks, smem);
-    in_stats_kernel<<<dim3(chunks, n_img), threads, smem, (cudaStream_t)stream>>>(mk(*z), C, H, W, stats);
+    reduce_shape(C, H * W, n_img, work ? work_floats : 0, threads, L, chunks, smem);
+    const long long n = (long long)n_img * C * 2;
+    if (chunks == 1) {
+        in_stats_kernel<<<dim3(1, n_img), threads, smem, (cudaStream_t)stream>>>(mk(*z), C, H, W, stats);
+        return irc_check_launch("irc_in_stats");
+    }
+    in_stats_kernel<<<dim3(chunks, n_img), threads, smem, (cudaStream_t)stream>>>(mk(*z), C, H, W, work);
+    sum_chunks_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(work, chunks, n, stats);
     return irc_check_launch("irc_in_stats");
 }
 
@@ -449,10 +466,12 @@ static int fill_bwd(const irc_in_bwd_args* a, InBwdP& p) {
 extern "C" int irc_in_bwd_reduce(const irc_in_bwd_args* a, void* stream) {
     InBwdP p; int rc = fill_bwd(a, p); if (rc) return rc;
     if (!p.stats || !p.bsum) return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_bwd_reduce: stats and bsum required");
-    cudaMemsetAsync(p.bsum, 0, sizeof(float) * 2 * p.C * p.n_img, (cudaStream_t)stream);
     int threads, L, chunks; size_t smem;
-    reduce_shape(p.C, p.H * p.W, p.n_img, threads, L, chunks, smem);
+    reduce_shape(p.C, p.H * p.W, p.n_img, a->work ? a->work_floats : 0, threads, L, chunks, smem);
+    const long long n = (long long)p.n_img * p.C * 2;
+    p.part = chunks == 1 ? p.bsum : a->work;
     in_bwd_reduce_kernel<<<dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream>>>(p);
+    if (chunks > 1) sum_chunks_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a->work, chunks, n, p.bsum);
     return irc_check_launch("irc_in_bwd_reduce");
 }
 
@@ -483,10 +502,17 @@ extern "C" int irc_maxpool2_bwd(const irc_view* src, const irc_view* g, const ir
     return irc_check_launch("irc_maxpool2_bwd");
 }
 
-extern "C" int irc_colsum(const void* a, long long rows, long long ld, int chan_off, int C, const short* row_img, float* out, void* stream) {
+extern "C" int irc_colsum(const void* a, long long rows, long long ld, int chan_off, int C, const short* row_img, float* out, float* work,
+                          long long work_floats, void* stream) {
     if (!a || !out) return irc_set_error(IRC_ERR_BAD_ARG, "irc_colsum: null");
-    cudaMemsetAsync(out, 0, sizeof(float) * C, (cudaStream_t)stream);
-    long long bx = (rows + 31) / 32; if (bx > irc_num_sms() * 4) bx = irc_num_sms() * 4; if (bx < 1) bx = 1;
-    colsum_kernel<<<dim3((unsigned)bx, (C + 31) / 32), 1024, 0, (cudaStream_t)stream>>>((const bf16*)a, rows, ld, chan_off, C, row_img, out);
+    long long bx = (rows + 31) / 32; if (bx > irc_num_sms() * 4) bx = irc_num_sms() * 4;
+    const long long cap = work ? work_floats / C : 0;
+    if (bx > cap) bx = cap;
+    if (bx <= 1) {
+        colsum_kernel<<<dim3(1, (C + 31) / 32), 1024, 0, (cudaStream_t)stream>>>((const bf16*)a, rows, ld, chan_off, C, row_img, out);
+        return irc_check_launch("irc_colsum");
+    }
+    colsum_kernel<<<dim3((unsigned)bx, (C + 31) / 32), 1024, 0, (cudaStream_t)stream>>>((const bf16*)a, rows, ld, chan_off, C, row_img, work);
+    sum_chunks_kernel<<<grid_for(C, 256), 256, 0, (cudaStream_t)stream>>>(work, (int)bx, C, out);
     return irc_check_launch("irc_colsum");
 }

@@ -197,7 +197,7 @@ __global__ void chan_sum_kernel(const float* g, const float* yv, int n_img, int 
         s += v;
     }
     s = block_sum(s, sh);
-    if (threadIdx.x == 0) atomicAdd(out + c, s);
+    if (threadIdx.x == 0) out[c] = s;     // one block per channel: deterministic
 }
 
 int grid_for(long long total, int threads) {
@@ -264,10 +264,8 @@ extern "C" int irc_tap_expand(const irc_tap_args* a, const float* g, const float
     tap_expand_kernel<<<grid_for(rows * 8, 256), 256, 0, (cudaStream_t)stream>>>(g, y, (bf16*)E, t);
     rc = irc_check_launch("irc_tap_expand"); if (rc) return rc;
     if (dbias) {
-        cudaMemsetAsync(dbias, 0, sizeof(float) * t.nco, (cudaStream_t)stream);
         const long long hw = (long long)t.H * t.W;
-        int bx = grid_for((long long)t.n_img * hw, 256); if (bx > 256) bx = 256;
-        chan_sum_kernel<<<dim3(bx, t.nco), 256, 0, (cudaStream_t)stream>>>(g, y, t.n_img, t.nco, hw, dbias);
+        chan_sum_kernel<<<dim3(1, t.nco), 1024, 0, (cudaStream_t)stream>>>(g, y, t.n_img, t.nco, hw, dbias);
         rc = irc_check_launch("irc_tap_expand(dbias)");
     }
     return rc;

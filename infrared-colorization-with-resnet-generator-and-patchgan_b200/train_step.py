@@ -19,11 +19,12 @@ from .engine import DiscriminatorEngine, GeneratorEngine, VggEngine
 LAMBDAS = dict(L1=30.0, perc=30.0, tv=1e-4, ssim=2.0, gan=0.1)   # irc:100-104
 
 
-def gaussian_window(device, n: int = 11, sigma: float = 1.5) -> torch.Tensor:
-    """irc:699-703, evaluated in fp32 exactly as the reference does"""
+def gaussian_window(n: int = 11, sigma: float = 1.5) -> torch.Tensor:
+    """irc:699-703, evaluated in fp32 exactly as the reference does.  Host tensor: the taps are passed to the
+    SSIM kernels by value."""
     c = torch.arange(n, dtype=torch.float32) - (n - 1) / 2.0
     g = torch.exp(-(c ** 2) / (2 * sigma ** 2))
-    return (g / g.sum()).to(device).contiguous()
+    return (g / g.sum()).contiguous()
 
 
 class AdamHyper:
@@ -58,7 +59,7 @@ class TrainStep:
         self.V = VggEngine(be, 2 * B, B, H, W, device)
         self.optG = AdamHyper(device, lr_G, beta1, beta2)
         self.optD = AdamHyper(device, lr_D, beta1, beta2)
-        self.window = gaussian_window(device)
+        self.window = gaussian_window()
         self.sums = torch.zeros(8 + B, device=device)
         self.dfake = torch.zeros(B, 3, H, W, device=device)
         self.ga, self.gb, self.gc = (torch.zeros(B, 3, H, W, device=device) for _ in range(3))

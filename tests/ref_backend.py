@@ -313,7 +313,7 @@ class RefBackend:
 
     @staticmethod
     def _ssim_map(x, y, window):
-        n = window.numel(); C = x.shape[1]
+        window = window.to(x.device); n = window.numel(); C = x.shape[1]
         kx = window.view(1, 1, 1, n).expand(C, 1, 1, n); ky = window.view(1, 1, n, 1).expand(C, 1, n, 1)
         f = lambda t: F.conv2d(F.conv2d(t, kx, padding=(0, n // 2), groups=C), ky, padding=(n // 2, 0), groups=C)
         m1, m2 = f(x), f(y)

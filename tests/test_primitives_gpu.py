@@ -1,0 +1,275 @@
+"""Every memory-bound primitive of the C ABI vs its torch restatement (tests/ref_backend.py) on the
+same device buffers, plus the golden vectors of the reference for the stencils / losses / metrics."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ref_small.npz")
+
+
+@pytest.fixture(scope="module")
+def bes():
+    import irc_b200
+    from irc_b200._native import CudaBackend
+    from ref_backend import RefBackend
+    return CudaBackend(), RefBackend()
+
+
+def gen(seed=0):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+def rnd(shape, g, dtype=torch.bfloat16, scale=1.0):
+    return (torch.randn(shape, device="cuda", generator=g) * scale).to(dtype)
+
+
+def close(a, b, tol, what=""):
+    a, b = a.float(), b.float()
+    err = (a - b).abs().max().item()
+    ref = max(b.abs().max().item(), 1e-6)
+    assert err <= tol * ref, f"{what}: max err {err} vs scale {ref}"
+
+
+def frame(n, h, w, p, c, g):
+    from irc_b200 import layout as L
+    f = L.Frame(n, h, w, p, c, "cuda")
+    f.t.copy_(rnd(f.t.shape, g))
+    return f
+
+
+def both(bes, fn, outs):
+    """run fn(backend) for both backends on clones of the output buffers; return the two output lists"""
+    res = []
+    for be in bes:
+        bufs = [o.clone() for o in outs]
+        fn(be, *bufs)
+        torch.cuda.synchronize()
+        res.append(bufs)
+    return res
+
+
+@pytest.mark.parametrize("C,H,W", [(64, 16, 12), (256, 8, 8), (192, 12, 20)])
+def test_in_stats(bes, C, H, W):
+    z = frame(3, H, W, 1, C, gen(1))
+    a, b = both(bes, lambda be, st: be.in_stats(z.view(), C, 3, H, W, st), [torch.zeros(3, C, 2, device="cuda")])
+    close(a[0], b[0], 2e-4, "in_stats")
+
+
+@pytest.mark.parametrize("mode", ["apply_reflect", "apply_res", "down", "up", "s2d", "fold"])
+def test_gather(bes, mode):
+    from irc_b200 import layout as L
+    from irc_b200._native import View
+    g = gen(2)
+    n, C, H, W = 2, 64, 12, 8
+    src = frame(n, H, W, 1, C, g)
+    st = torch.zeros(n, C, 2, device="cuda")
+    bes[1].in_stats(src.view(), C, n, H, W, st)
+    if mode == "apply_reflect":
+        dst = frame(n, H, W, 3, 128, g)
+        fn = lambda be, d: be.gather(src.view(), View(d, 64, dst.hp, dst.wp, 3, 3), C, n, H, W, 3, 1, stats=st, cnt=H * W, act=1)
+    elif mode == "apply_res":
+        dst = frame(n, H, W, 1, C, g); res = frame(n, H, W, 1, C, g)
+        fn = lambda be, d: be.gather(src.view(), View(d, 0, dst.hp, dst.wp, 1, 1), C, n, H, W, 1, 1, stats=st, cnt=H * W, act=0, res=res.view())
+    elif mode == "down":
+        dst = frame(n, H // 2, W // 2, 1, C, g)
+        t = L.make_tables(L.down_matrix(H), L.down_matrix(W), "cuda")
+        fn = lambda be, d: be.gather(src.view(), View(d, 0, dst.hp, dst.wp, 1, 1), C, n, H // 2, W // 2, 1, 0, tables=t, stats=st, cnt=H * W, act=1)
+    elif mode == "up":
+        dst = frame(n, 2 * H, 2 * W, 1, C, g)
+        t = L.make_tables(L.up_matrix(H), L.up_matrix(W), "cuda")
+        fn = lambda be, d: be.gather(src.view(), View(d, 0, dst.hp, dst.wp, 1, 1), C, n, 2 * H, 2 * W, 1, 0, tables=t)
+    elif mode == "s2d":
+        dst = frame(n, (H + 2) // 2, (W + 2) // 2, 0, 4 * C, g)
+        fn = lambda be, d: be.gather(src.view(), View(d, 0, dst.hp, dst.wp), C, n, H, W, 1, 0, stats=st, cnt=H * W, act=2, slope=0.2, dst_s2d=1)
+    else:
+        dst = frame(n, H, W, 1, C, g); src2 = frame(n, H, W, 1, C, g)
+        t = L.make_tables(L.fold_matrix(H, 1), L.fold_matrix(W, 1), "cuda")
+        fn = lambda be, d: be.gather(src.pview(), View(d, 0, dst.hp, dst.wp, 1, 1), C, n, H, W, 1, 0, tables=t, src2=src2.pview())
+    a, b = both(bes, fn, [dst.t])
+    close(a[0], b[0], 1e-2, mode)
+
+
+@pytest.mark.parametrize("mode", ["norm_relu_fold", "norm_none_two", "plain_lrelu", "upT", "s2d_src"])
+def test_in_bwd(bes, mode):
+    from irc_b200 import layout as L
+    from irc_b200._native import View
+    g = gen(3)
+    n, C, H, W = 2, 128, 8, 12
+    z = frame(n, H, W, 1, C, g)
+    st = torch.zeros(n, C, 2, device="cuda")
+    bes[1].in_stats(z.view(), C, n, H, W, st)
+    dz = frame(n, H, W, 1, C, g)
+    bs = torch.zeros(n, 512, 2, device="cuda")
+    kw = dict(stats=st, cnt=H * W, bsum=bs)
+    if mode == "norm_relu_fold":
+        gsrc = frame(n, H, W, 1, C, g)
+        t = L.make_tables(L.fold_matrix(H, 1), L.fold_matrix(W, 1), "cuda")
+        fn = lambda be, d: be.in_bwd(z.view(), gsrc.pview(), View(d, 0, dz.hp, dz.wp, 1, 1), C, n, H, W, act=1, tables=t, **kw)
+    elif mode == "norm_none_two":
+        g1 = frame(n, H, W, 1, 256, g); g2 = frame(n, H, W, 1, C, g)
+        fn = lambda be, d: be.in_bwd(z.view(), g1.view(128), View(d, 0, dz.hp, dz.wp, 1, 1), C, n, H, W, act=0, g2=g2.view(), **kw)
+    elif mode == "plain_lrelu":
+        g1 = frame(n, H, W, 1, C, g)
+        fn = lambda be, d: be.in_bwd(z.view(), g1.view(), View(d, 0, dz.hp, dz.wp, 1, 1), C, n, H, W, act=2, slope=0.2)
+    elif mode == "upT":
+        g1 = frame(n, 2 * H, 2 * W, 1, C, g)
+        t = L.make_tables(L.up_matrix(H).T, L.up_matrix(W).T, "cuda")
+        fn = lambda be, d: be.in_bwd(z.view(), g1.view(), View(d, 0, dz.hp, dz.wp, 1, 1), C, n, H, W, act=1, tables=t, **kw)
+    else:
+        g1 = frame(n, (H + 2) // 2, (W + 2) // 2, 0, 4 * C, g)
+        fn = lambda be, d: be.in_bwd(z.view(), View(g1.t, 0, g1.hp, g1.wp, 1, 1, C), View(d, 0, dz.hp, dz.wp, 1, 1), C, n, H, W, act=2, slope=0.2, **kw)
+    a, b = both(bes, fn, [dz.t])
+    close(a[0], b[0], 1.5e-2, mode)
+
+
+def test_maxpool(bes):
+    g = gen(4)
+    n, C, H, W = 3, 64, 8, 12
+    src = frame(n, H, W, 1, C, g); src.t.copy_(torch.relu(src.t))
+    from irc_b200._native import View
+    dst = frame(n, H // 2, W // 2, 1, C, g)
+    a, b = both(bes, lambda be, d: be.maxpool2(src.view(), View(d, 0, dst.hp, dst.wp, 1, 1), C, n, H // 2, W // 2), [dst.t])
+    assert torch.equal(a[0], b[0])
+    gg = frame(2, H // 2, W // 2, 1, C, g); dsrc = frame(2, H, W, 1, C, g)
+    sv = View(src.t[:src.rows_of(2)], 0, src.hp, src.wp, 1, 1)
+    a, b = both(bes, lambda be, d: be.maxpool2_bwd(sv, gg.view(), View(d, 0, dsrc.hp, dsrc.wp, 1, 1), C, 2, H // 2, W // 2), [dsrc.t])
+    assert torch.equal(a[0], b[0])
+
+
+def test_colsum(bes):
+    g = gen(5)
+    a_ = rnd((5000, 64), g)
+    ri = (torch.arange(5000, device="cuda") % 3 - 1).short()
+    for r in (None, ri):
+        a, b = both(bes, lambda be, o: be.colsum(a_, 0, 64, o, row_img=r), [torch.zeros(64, device="cuda")])
+        close(a[0], b[0], 1e-4, "colsum")
+
+
+@pytest.mark.parametrize("cfg", [dict(c1=1, c2=0, k=7, s=1, p=3, pm=1, rm=0), dict(c1=3, c2=0, k=3, s=1, p=1, pm=0, rm=1, aff=True),
+                                 dict(c1=1, c2=3, k=4, s=2, p=1, pm=0, rm=2)])
+def test_im2col_col2im(bes, cfg):
+    g = gen(6)
+    n, H, W = 2, 16, 24
+    s1 = torch.randn(n, cfg["c1"], H, W, device="cuda", generator=g)
+    s2 = torch.randn(n, cfg["c2"], H, W, device="cuda", generator=g) if cfg["c2"] else None
+    C = cfg["c1"] + cfg["c2"]
+    Ho, Wo = H // cfg["s"], W // cfg["s"]
+    sc = torch.rand(C, device="cuda", generator=g) + 0.5 if cfg.get("aff") else None
+    sh = torch.randn(C, device="cuda", generator=g) if cfg.get("aff") else None
+    rows = bes[0].im2col_rows(cfg["rm"], n, Ho, Wo)
+    assert rows == bes[1].im2col_rows(cfg["rm"], n, Ho, Wo)
+    fn = lambda be, d, ri: be.im2col(s1, s2, sc, sh, n, H, W, cfg["k"], cfg["s"], cfg["p"], cfg["pm"], Ho, Wo, cfg["rm"], d, row_img=ri)
+    a, b = both(bes, fn, [torch.full((rows, 64), 7.0, device="cuda", dtype=torch.bfloat16), torch.zeros(rows, device="cuda", dtype=torch.int16)])
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    if cfg["pm"] == 0:
+        de = rnd((rows, 64), g)
+        c_first, c_out = (1, 3) if C == 4 else (0, C)
+        out0 = torch.randn(n, c_out, H, W, device="cuda", generator=g)
+        fn = lambda be, o: be.col2im(de, C, c_first, c_out, n, H, W, cfg["k"], cfg["s"], cfg["p"], Ho, Wo, cfg["rm"], sc, o, True)
+        a, b = both(bes, fn, [out0])
+        close(a[0], b[0], 1e-5, "col2im")
+
+
+def test_taps(bes):
+    g = gen(7)
+    n, H, W, p = 2, 10, 12, 3
+    hp, wp = H + 2 * p, W + 2 * p
+    shifts = [s - 3 for s in range(7)]
+    P = torch.randn(n * hp * wp, 32, device="cuda", generator=g)
+    bias = torch.randn(3, device="cuda", generator=g)
+    a, b = both(bes, lambda be, o: be.tap_reduce(P, shifts, 3, n, H, W, hp, wp, p, p, bias, 3, o), [torch.zeros(n, 3, H, W, device="cuda")])
+    close(a[0], b[0], 1e-5, "tap_reduce")
+    gr = torch.randn(n, 3, H, W, device="cuda", generator=g); y = torch.tanh(torch.randn(n, 3, H, W, device="cuda", generator=g))
+    fn = lambda be, E, db: be.tap_expand(gr, y, shifts, 3, n, H, W, hp, wp, p, p, E, dbias=db)
+    a, b = both(bes, fn, [torch.full((n * hp * wp, 64), 3.0, device="cuda", dtype=torch.bfloat16), torch.zeros(3, device="cuda")])
+    assert torch.equal(a[0], b[0]); close(a[1], b[1], 1e-5, "dbias")
+
+
+def test_losses_vs_reference_golden(bes):
+    """L1/TV/SSIM values and gradients against the reference's own autograd (golden fixture)."""
+    from irc_b200.train_step import gaussian_window
+    be = bes[0]
+    gold = np.load(GOLD)
+    a = torch.from_numpy(gold["loss_a"]).cuda(); b = torch.from_numpy(gold["loss_b"]).cuda()
+    n, c, h, w = a.shape
+    sums = torch.zeros(3, device="cuda"); d = torch.zeros_like(a)
+    be.pixel_loss(a, None, 0.0, 1.0 / (n * c * (h - 1) * w), 1.0 / (n * c * h * (w - 1)), sums, d)
+    tv = sums[1].item() / (n * c * (h - 1) * w) + sums[2].item() / (n * c * h * (w - 1))
+    assert abs(tv - float(gold["tv"])) < 1e-6
+    close(d, torch.from_numpy(gold["tv_grad"]).cuda(), 1e-5, "tv grad")
+    win = gaussian_window()
+    ss = torch.zeros(n, device="cuda"); ga, gb, gc = (torch.zeros_like(a) for _ in range(3))
+    be.ssim_fwd(a, b, 1.0, 0.0, win, ss, ga, gb, gc)
+    per = 1.0 - ss / (c * h * w)
+    close(per, torch.from_numpy(gold["ssim_per_sample"]).cuda(), 2e-5, "ssim per sample")
+    assert abs(1.0 - ss.sum().item() / a.numel() - float(gold["ssim"])) < 2e-5
+    d.zero_()
+    be.ssim_bwd(a, b, 1.0, 0.0, win, ga, gb, gc, -1.0 / a.numel(), d, False)
+    close(d, torch.from_numpy(gold["ssim_grad"]).cuda(), 2e-3, "ssim grad")
+    # L1 value + sign gradient
+    sums.zero_()
+    be.pixel_loss(a, b, 1.0, 0.0, 0.0, sums, d)
+    assert abs(sums[0].item() - (a - b).abs().sum().item()) < 1e-2
+    assert torch.equal(d, torch.sign(a - b))
+
+
+def test_hinge_featl1(bes):
+    g = gen(8)
+    pred = torch.randn(4 * 900, device="cuda", generator=g) * 2
+    for mode in (0, 1):
+        a, b = both(bes, lambda be, s, d: be.hinge(pred, 1800, mode, 0.25, 0.5, s, d), [torch.zeros(3, device="cuda"), torch.zeros_like(pred)])
+        close(a[0], b[0], 1e-5, "hinge sums"); close(a[1], b[1], 1e-6, "hinge grad")
+    feat = torch.relu(rnd((2 * 300, 256), g))
+    a, b = both(bes, lambda be, s, d: be.feat_l1(feat, 300, 256, 0.125, s, d), [torch.zeros(1, device="cuda"), torch.zeros(300, 256, device="cuda", dtype=torch.bfloat16)])
+    close(a[0], b[0], 1e-4, "feat sum"); assert torch.equal(a[1], b[1])
+
+
+def test_quantize_metrics_bit_exact(bes):
+    """irc:865-876 truncation and irc:1197-1205 metrics against the reference's own output."""
+    be = bes[0]
+    gold = np.load(GOLD)
+    fake = torch.from_numpy(gold["fake"]).cuda()
+    gt = torch.from_numpy(gold["metrics_gt"]).permute(2, 0, 1).unsqueeze(0).contiguous().cuda()
+    u8 = torch.zeros(1, 32, 32, 3, device="cuda", dtype=torch.uint8); sums = torch.zeros(1, 2, device="cuda", dtype=torch.float64)
+    be.quantize_metrics(fake[:1].contiguous(), gt, u8, sums)
+    assert np.array_equal(u8[0].cpu().numpy(), gold["quant_u8"])
+    mae, mse = (sums[0] / (3 * 32 * 32)).tolist()
+    psnr = -10.0 * np.log10(mse + 1e-12)
+    for got, ref in zip((mae, mse, psnr), gold["metrics"]):
+        assert abs(got - ref) < 5e-7 * max(1, abs(ref)), (got, ref)
+    probe = torch.full((1, 3, 4, 4), 254.87 / 255.0 * 2 - 1, device="cuda")
+    u = torch.zeros(1, 4, 4, 3, device="cuda", dtype=torch.uint8)
+    be.quantize_metrics(probe, None, u, None)
+    assert (u == 254).all()
+
+
+def test_adam_pack_gather(bes):
+    g = gen(9)
+    n = 10007
+    p0 = torch.randn(n, device="cuda", generator=g); gr = torch.randn(n, device="cuda", generator=g) * 1e-3
+    m0 = torch.randn(n, device="cuda", generator=g) * 1e-3; v0 = torch.rand(n, device="cuda", generator=g) * 1e-6
+    hyper = torch.tensor([2e-4, 0.5, 0.999, 1e-8, 1 - 0.5 ** 3, 1 - 0.999 ** 3, 0.5, 0.0], device="cuda")
+    a, b = both(bes, lambda be, p, m, v: be.adam(p, gr, m, v, hyper), [p0, m0, v0])
+    for x, y in zip(a, b):
+        close(x, y, 2e-6, "adam")
+    # torch.optim.Adam itself
+    pt = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=2e-4, betas=(0.5, 0.999))
+    for _ in range(3):
+        pt.grad = gr.clone(); opt.step()
+    pc, mc, vc = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for t in (1, 2, 3):
+        h = torch.tensor([2e-4, 0.5, 0.999, 1e-8, 1 - 0.5 ** t, 1 - 0.999 ** t, 1.0, 0.0], device="cuda")
+        bes[0].adam(pc, gr, mc, vc, h)
+    close(pc, pt.detach(), 1e-6, "adam vs torch.optim.Adam")
+    src = torch.randn(5000, device="cuda", generator=g)
+    mp = torch.randint(-1, 5000, (7777,), device="cuda", generator=g, dtype=torch.int32)
+    a, b = both(bes, lambda be, d: be.pack_bf16(src, mp, d), [torch.zeros(7777, device="cuda", dtype=torch.bfloat16)])
+    assert torch.equal(a[0], b[0])
+    part = torch.randn(3 * 6000, device="cuda", generator=g)
+    mp2 = torch.randint(-1, 6000, (4000,), device="cuda", generator=g, dtype=torch.int32)
+    a, b = both(bes, lambda be, d: be.gather_sum(part, mp2, 3, 6000, d), [torch.zeros(4000, device="cuda")])
+    close(a[0], b[0], 1e-6, "gather_sum")
