@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one full GAN training iteration (D update + G update with hinge +
+L1 + VGG + TV + SSIM losses, irc:1636-1681) on synthetic 256x256 pairs, batch 16 per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §measurement for what each key means."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "gan_train_img_per_s_256x256_b16_per_gpu"
+UNIT = "img/s"
+GFLOP_PER_SAMPLE = 533.9          # minimal result-preserving conv work of one train step at 256^2
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(tf=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), hbm=float(p["hbm_gbs"]), src="measured")
+    except Exception:
+        return dict(tf=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+def oracle_step_time(B, H, W, steps, threads):
+    """seconds per reference-algorithm train step (oracle port of irc:1636-1681) on the host cores"""
+    import torch
+    import irc_oracle as O
+    torch.set_num_threads(threads)
+    pG = O.seeded_params(O.generator_shapes(), 1234)
+    pD = O.seeded_params(O.discriminator_shapes(), 1235)
+    pV = O.seeded_params(O.vgg_shapes(), 1236, kaiming=True)
+    aG, aD = O.AdamState(pG), O.AdamState(pD)
+    ir, rgb = O.synthetic_pair(B, H, W)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.train_step(pG, pD, pV, aG, aD, ir, rgb)
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's algorithm (oracle port; the reference itself is a Python script that
+    cannot travel to the GPU box) on all host cores, bounded sample B=2 per step."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    Bs = 2
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    ts = oracle_step_time(Bs, 256, 256, warm + steps, cores)[warm:]
+    sec = sum(ts) / len(ts)
+    val = Bs / sec
+    line = dict(impl="reference", metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warm,
+                ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="single GAN train step (G+D, hinge+L1+VGG+TV+SSIM) at 256x256, reference algorithm on CPU",
+                            sample=f"batch {Bs} per step instead of 16 (img/s is per image)", l2="n/a (CPU)"),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port",
+                                  sample=f"{steps} step(s) of batch {Bs} at 256x256, torch CPU fp32, {cores} threads"),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                iters_per_s=1.0 / sec, gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--size", type=int, nargs=2, default=[256, 256], metavar=("H", "W"))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", default=None, help="write the per-launch GEMM timing table to this file")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import irc_oracle as O          # weight / input recipes only; the timed path never touches it
+    import irc_b200  # noqa: F401
+    from irc_b200._native import CudaBackend
+    from irc_b200.train_step import TrainStep
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, (H, W) = args.batch, args.size
+    W_, K = max(args.warmup, 3), args.steps
+
+    be = CudaBackend()
+    ts = TrainStep(be, B, H, W, dev, world_size=world, use_graph=(world == 1 and not args.no_graph))
+    ts.load(O.seeded_params(O.generator_shapes(), 1234), O.seeded_params(O.discriminator_shapes(), 1235),
+            O.seeded_params(O.vgg_shapes(), 1236, kaiming=True))
+    ir_h, rgb_h = O.synthetic_pair(B, H, W, rank)
+    ir_h, rgb_h = ir_h.pin_memory(), rgb_h.pin_memory()
+    ir_d, rgb_d = ir_h.to(dev), rgb_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    # ---- device-resident throughput
+    for _ in range(W_):
+        ts.step(ir_d, rgb_d)
+    l0 = be.launches
+    ts.step(ir_d, rgb_d)
+    launches_per_step = getattr(ts, "launches_per_step", None) or (be.launches - l0)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = timed(lambda: ts.step(ir_d, rgb_d), K)
+    clocks = sampler.stop() if sampler else None
+    losses = ts.losses()
+
+    # ---- end to end through the public call with host buffers: H2D of the batch + D2H of the losses every step
+    def e2e_step():
+        ts.step(ir_h, rgb_h)
+        ts.losses()
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, K)
+
+    # ---- roofline of the dominant kernel: every tensor-core GEMM launch of one eager step bracketed by CUDA events
+    pk = peaks()
+    eager = ts if not ts.use_graph else None
+    if eager is None:
+        ts.use_graph = False
+    ts.step(ir_d, rgb_d)
+    be.timers = []
+    ts.step(ir_d, rgb_d)
+    torch.cuda.synchronize()
+    rows = [(kind, name, role, fl, e0.elapsed_time(e1)) for (kind, name, role, fl, e0, e1) in be.timers]
+    be.timers = None
+    conv = [r for r in rows if r[0] == "conv_gemm" and r[3] > 0]
+    tn = [r for r in rows if r[0] == "tn_gemm" and r[3] > 0]
+    conv_tf = sum(r[3] for r in conv) / (sum(r[4] for r in conv) * 1e-3) / 1e12
+    tn_tf = sum(r[3] for r in tn) / (sum(r[4] for r in tn) * 1e-3) / 1e12
+    gemm_ms = sum(r[4] for r in conv) + sum(r[4] for r in tn)
+    if args.breakdown and rank == 0:
+        agg = {}
+        for kind, name, role, fl, t in rows:
+            a = agg.setdefault((kind, name, role), [0, 0.0, 0.0]); a[0] += 1; a[1] += fl; a[2] += t
+        with open(args.breakdown, "w") as f:
+            f.write("kernel,layer,role,launches,gflop_per_launch,ms_per_launch,tflops,frac_of_peak\n")
+            for (kind, name, role), (n, fl, t) in sorted(agg.items(), key=lambda kv: -kv[1][2]):
+                f.write(f"{kind},{name},{role},{n},{fl / n / 1e9:.2f},{t / n:.4f},{fl / (t * 1e-3) / 1e12:.1f},{fl / (t * 1e-3) / 1e12 / pk['tf']:.3f}\n")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        t = oracle_step_time(2, H, W, 2, cores)[1:]
+        cpu_baseline = dict(value=2 / (sum(t) / len(t)), unit=UNIT, cores=cores, kind="port",
+                            sample=f"1 timed step (after 1 warm-up) of batch 2 at {H}x{W}, oracle/irc_oracle.py, torch CPU fp32")
+
+    sec = ms * 1e-3 / K
+    value = world * B / sec
+    step_tflop = GFLOP_PER_SAMPLE * B * (H * W) / (256 * 256) / 1e3
+    line = dict(
+        metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W_, ms_per_step=sec * 1e3, higher_is_better=True,
+        scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+        config=dict(workload=f"single GAN train step (G+D, hinge+L1+VGG+TV+SSIM losses) at {H}x{W} batch {B} per GPU "
+                             "(BASELINE.json configs[1]; configs[2] when n_gpus > 1)",
+                    global_batch=world * B, parallelism=f"dp{world}", cuda_graph=bool(ts.graph is not None),
+                    l2="per-step working set (several GB of activations) exceeds the 126 MB L2; no explicit flush"),
+        iters_per_s=1.0 / sec, step_tflop_algorithmic=step_tflop, step_tensor_frac=step_tflop / sec / pk["tf"],
+        e2e=dict(value=world * B / (ms_e2e * 1e-3 / K), unit=UNIT, h2d_bytes_per_step=ir_h.numel() * 4 + rgb_h.numel() * 4,
+                 d2h_bytes_per_step=ts.sums.numel() * 4),
+        gpu_launches=launches_per_step * K,
+        clocks=clocks,
+        roofline=dict(bound="tensor", kernel="conv_gemm_kernel (all forward + data-gradient convolutions of one step)",
+                      achieved=conv_tf, peak=pk["tf"], unit="TFLOP/s", frac=conv_tf / pk["tf"], traffic=None,
+                      peak_source=pk["src"] + " bf16_tflops_sustained", launches_per_step=len(conv),
+                      share_of_step=sum(r[4] for r in conv) / (sec * 1e3)),
+        roofline_wgrad=dict(bound="tensor", kernel="tn_gemm_kernel (all weight gradients of one step)", achieved=tn_tf, peak=pk["tf"],
+                            unit="TFLOP/s", frac=tn_tf / pk["tf"], launches_per_step=len(tn), share_of_step=sum(r[4] for r in tn) / (sec * 1e3)),
+        gemm_ms_per_step=gemm_ms,
+        cpu_baseline=cpu_baseline,
+        losses={k: round(v, 5) for k, v in losses.items()},
+    )
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

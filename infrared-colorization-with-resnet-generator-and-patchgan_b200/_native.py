@@ -196,6 +196,18 @@ class CudaBackend:
         self.launches = 0
         # partials of the order-fixed two-stage reductions (InstanceNorm statistics, bias gradients)
         self.work = torch.zeros(1 << 22, device="cuda")
+        # optional per-launch timing of the tensor-core kernels (bench.py's roofline pass): when `timers` is a
+        # list, every GEMM launch is bracketed by CUDA events on the launching stream
+        self.timers = None
+        self.note = ("", "", 0.0)
+
+    def _timed(self, kind, fn):
+        if self.timers is None:
+            fn()
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        self.timers.append((kind,) + tuple(self.note) + (e0, e1))
 
     # ---- tensor-core GEMMs
     def conv_gemm(self, a, a_chan_off, cin, taps: Sequence[int], w, n_out, out, out_chan_off=0, bias=None, act=0, slope=0.0,
@@ -217,7 +229,7 @@ class CudaBackend:
             assert mask.t.shape[0] == a.shape[0]
             g.mask = mask.t.data_ptr(); g.mask_ld = mask.t.shape[1]; g.mask_chan_off = mask.chan_off; g.mask_slope = mask_slope
         g.bn = 0
-        check(self.L.irc_conv_gemm(C.byref(g), _stream())); self.launches += 1
+        self._timed("conv_gemm", lambda: check(self.L.irc_conv_gemm(C.byref(g), _stream()))); self.launches += 1
 
     def tn_gemm(self, a, a_chan_off, m, b, b_chan_off, n, k_rows, a_shift, b_shift, out, tap_stride, m_stride, n_stride,
                 splits, split_stride):
@@ -230,7 +242,7 @@ class CudaBackend:
         assert out.dtype == torch.float32
         g.out = out.data_ptr(); g.out_tap_stride = tap_stride; g.out_m_stride = m_stride; g.out_n_stride = n_stride
         g.out_split_stride = split_stride; g.splits = splits; g.bn = 0
-        check(self.L.irc_tn_gemm(C.byref(g), _stream())); self.launches += 1
+        self._timed("tn_gemm", lambda: check(self.L.irc_tn_gemm(C.byref(g), _stream()))); self.launches += 1
 
     # ---- frames
     def row_index(self, row_img, n_img, hp, wp, y0, y1, x0, x1):

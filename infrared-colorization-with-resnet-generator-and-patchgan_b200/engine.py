@@ -64,9 +64,13 @@ def _splits_for(tiles: int, kb_total: int, sms: int = 148) -> int:
 class ConvOp:
     """One convolution in its three GEMM roles over frame buffers."""
 
-    def __init__(self, be, lay: L.WeightLayout, taps: List[int], arena: L.ParamArena, max_rows: int, bias_name: Optional[str] = None):
+    def __init__(self, be, lay: L.WeightLayout, taps: List[int], arena: L.ParamArena, max_rows: int, bias_name: Optional[str] = None,
+                 pixels: int = 0, name: str = ""):
         self.be, self.lay, self.taps, self.arena = be, lay, list(taps), arena
         self.bias_name = bias_name
+        self.name = name
+        # algorithmic work of one pass in any role: 2 * (true weight count) * (forward output pixels)  (SURVEY.md §8d)
+        self.flops = 2.0 * lay.param_numel * pixels
         N, T, K = lay.N, lay.T, lay.K
         tiles = ((N + 127) // 128) * ((K + 255) // 256) * T
         self.splits = _splits_for(tiles, (max_rows + 63) // 64)
@@ -77,14 +81,17 @@ class ConvOp:
         return self.arena.view(self.bias_name) if self.bias_name else None
 
     def fwd(self, a, a_chan_off, out, **kw):
+        self.be.note = (self.name, "fwd", self.flops)
         self.be.conv_gemm(a, a_chan_off, self.lay.K, self.taps, self.lay.w_f.t, self.lay.w_f.rows, out, **kw)
 
     def dgrad(self, dz, out, **kw):
         """out[q][k] = sum_t dz[q - tap_t][:] . W[:, t, k]   (gradient w.r.t. the conv input frame)"""
+        self.be.note = (self.name, "dgrad", getattr(self, "flops_bwd", self.flops))
         self.be.conv_gemm(dz, 0, self.lay.kd, [-t for t in self.taps], self.lay.w_d.t, self.lay.K, out, **kw)
 
     def wgrad(self, dz, x, x_chan_off, k_rows):
         lay = self.lay
+        self.be.note = (self.name, "wgrad", self.flops)
         self.be.tn_gemm(dz, 0, lay.N, x, x_chan_off, lay.K, k_rows, [0] * lay.T, self.taps, self.partial,
                         lay.K, lay.T * lay.K, 1, self.splits, lay.N * lay.T * lay.K)
         self.be.gather_sum(self.partial, lay.unpack, self.splits, lay.N * lay.T * lay.K, self.grad_flat)
@@ -140,17 +147,17 @@ class GeneratorEngine:
         self.t_fold3 = mk(L.fold_matrix(H, 3), L.fold_matrix(W, 3))
         # ---- weights
         wp1, wp2, wp4, wp3 = self.cat2.wp, self.cat1.wp, self.X[0].wp, self.y4.wp
-        self.inc = ConvOp(be, L.layout_im2col(P, A, "inc.1.weight", 64, 1, 7), [0], A, self.Z0.rows)
-        self.down1 = ConvOp(be, L.layout_std(P, A, "down1.0.weight", 128, 64, 3, 3), L.taps_centered(3, 3, wp1), A, self.Z1.rows)
-        self.down2 = ConvOp(be, L.layout_std(P, A, "down2.0.weight", 256, 128, 3, 3), L.taps_centered(3, 3, wp2), A, self.Z2.rows)
+        self.inc = ConvOp(be, L.layout_im2col(P, A, "inc.1.weight", 64, 1, 7), [0], A, self.Z0.rows, pixels=B * H * W, name="G.inc")
+        self.down1 = ConvOp(be, L.layout_std(P, A, "down1.0.weight", 128, 64, 3, 3), L.taps_centered(3, 3, wp1), A, self.Z1.rows, pixels=B * H * W, name="G.down1")
+        self.down2 = ConvOp(be, L.layout_std(P, A, "down2.0.weight", 256, 128, 3, 3), L.taps_centered(3, 3, wp2), A, self.Z2.rows, pixels=B * H2 * W2, name="G.down2")
         self.res = []
         for b in range(n_blocks):
             self.res.append(tuple(ConvOp(be, L.layout_std(P, A, f"resblocks.{b}.conv_block.{j}.weight", 256, 256, 3, 3),
-                                         L.taps_centered(3, 3, wp4), A, self.X[0].rows) for j in (1, 5)))
-        self.up1 = ConvOp(be, L.layout_std(P, A, "up1_conv.0.weight", 128, 384, 3, 3), L.taps_centered(3, 3, wp2), A, self.Z3.rows)
-        self.up2 = ConvOp(be, L.layout_std(P, A, "up2_conv.0.weight", 64, 192, 3, 3), L.taps_centered(3, 3, wp1), A, self.Z4.rows)
+                                         L.taps_centered(3, 3, wp4), A, self.X[0].rows, pixels=B * H4 * W4, name="G.res") for j in (1, 5)))
+        self.up1 = ConvOp(be, L.layout_std(P, A, "up1_conv.0.weight", 128, 384, 3, 3), L.taps_centered(3, 3, wp2), A, self.Z3.rows, pixels=B * H2 * W2, name="G.up1")
+        self.up2 = ConvOp(be, L.layout_std(P, A, "up2_conv.0.weight", 64, 192, 3, 3), L.taps_centered(3, 3, wp1), A, self.Z4.rows, pixels=B * H * W, name="G.up2")
         self.outc = ConvOp(be, L.layout_outc(P, A, "outc.1.weight", 3, 64, 7), [(r - 3) * wp3 for r in range(7)], A, self.y4.rows,
-                           bias_name="outc.1.bias")
+                           bias_name="outc.1.bias", pixels=B * H * W, name="G.outc")
         self.outc_shifts = [s - 3 for s in range(7)]
         P.finish()
         if training:
@@ -223,8 +230,9 @@ class GeneratorEngine:
         return self.fake
 
     # ------------------------------------------------------------------ backward
-    def backward(self, dfake: torch.Tensor) -> None:
-        """dfake: fp32 [B,3,H,W] = dL/dfake.  Fills arena.grad for every generator parameter."""
+    def backward(self, dfake: torch.Tensor, after_blocks=None) -> None:
+        """dfake: fp32 [B,3,H,W] = dL/dfake.  Fills arena.grad for every generator parameter.  `after_blocks`
+        (optional callable) runs once the gradients of outc, up2, up1 and all ResNet blocks are final."""
         be, B, H, W = self.be, self.B, self.H, self.W
         H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
         y4 = self.y4
@@ -259,6 +267,8 @@ class GeneratorEngine:
             nxt = self.dOut[1] if cur is self.dOut[0] else self.dOut[0]
             be.gather(self.Gx.pview(), nxt.view(), 256, B, H4, W4, 1, 0, tables=self.t_fold1, res=cur.view())
             cur = nxt
+        if after_blocks is not None:
+            after_blocks()
         # down2 (through Downsample^T)
         be.in_bwd(self.Z2.view(), cur.view(), self.dZ2.view(), 256, B, H2, W2, stats=self.st2, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
                   tables=self.t_down2_T, bsum=self.bsum)
@@ -319,11 +329,11 @@ class DiscriminatorEngine:
                 l8=L.layout_std(P, A, "model.8.weight", 512, 256, 4, 4),
                 l11=L.layout_pointwise_taps(P, A, "model.11.weight", 512, 4))
         self.layouts = layouts
-        self.c0 = ConvOp(be, layouts["l0"], [0], A, self.rows0, bias_name="model.0.bias")
-        self.c2 = ConvOp(be, layouts["l2"], [0, 1, self.wb0, self.wb0 + 1], A, self.Z2.shape[0])
-        self.c5 = ConvOp(be, layouts["l5"], [0, 1, self.wb2, self.wb2 + 1], A, self.Z5.shape[0])
-        self.c8 = ConvOp(be, layouts["l8"], L.taps_topleft(4, 4, self.X8.wp), A, self.X8.rows)
-        self.c11 = ConvOp(be, layouts["l11"], [0], A, self.X11.rows, bias_name="model.11.bias")
+        self.c0 = ConvOp(be, layouts["l0"], [0], A, self.rows0, bias_name="model.0.bias", pixels=n * H1 * W1, name="D.0")
+        self.c2 = ConvOp(be, layouts["l2"], [0, 1, self.wb0, self.wb0 + 1], A, self.Z2.shape[0], pixels=n * H2 * W2, name="D.2")
+        self.c5 = ConvOp(be, layouts["l5"], [0, 1, self.wb2, self.wb2 + 1], A, self.Z5.shape[0], pixels=n * H3 * W3, name="D.5")
+        self.c8 = ConvOp(be, layouts["l8"], L.taps_topleft(4, 4, self.X8.wp), A, self.X8.rows, pixels=n * self.H8o * self.W8o, name="D.8")
+        self.c11 = ConvOp(be, layouts["l11"], [0], A, self.X11.rows, bias_name="model.11.bias", pixels=n * self.Ho * self.Wo, name="D.11")
         self.shifts11 = L.taps_topleft(4, 4, self.X11.wp)
         if own:
             P.finish()
@@ -451,7 +461,8 @@ class VggEngine:
             else:
                 lay = L.layout_std(P, A, f"features.{idx}.weight", co, ci, 3, 3)
                 taps = L.taps_centered(3, 3, fr.wp)
-            self.convs.append(ConvOp(be, lay, taps, A, 64, bias_name=f"features.{idx}.bias"))
+            self.convs.append(ConvOp(be, lay, taps, A, 64, bias_name=f"features.{idx}.bias", pixels=n_img * h * w, name=f"V.{idx}"))
+            self.convs[-1].flops_bwd = 2.0 * lay.param_numel * n_bwd * h * w
         P.finish()
         self.pool = {1: L.Frame(n_img, H // 2, W // 2, 1, 64, device), 3: L.Frame(n_img, H // 4, W // 4, 1, 128, device)}
         self.E = L.act_zeros(self.act[0].rows, 64, device)

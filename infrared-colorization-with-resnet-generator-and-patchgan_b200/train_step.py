@@ -79,10 +79,18 @@ class TrainStep:
         self.G.refresh_weights(); self.D2.refresh_weights(); self.V.refresh_weights()
 
     # ------------------------------------------------------------------ the iteration
-    def _allreduce(self, arena: L.ParamArena) -> None:
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(arena.grad, group=self.pg)
+    def _allreduce_async(self, t: torch.Tensor):
+        """sum-allreduce over NCCL/NVLink on NCCL's own stream; returns a handle to wait on (None when single GPU)"""
+        if self.world == 1:
+            return None
+        import torch.distributed as dist
+        return dist.all_reduce(t, group=self.pg, async_op=True)
+
+    @staticmethod
+    def _wait(*works) -> None:
+        for w in works:
+            if w is not None:
+                w.wait()          # stream-level wait, the host does not block
 
     def _body(self) -> None:
         be, B, H, W, lam = self.be, self.B, self.H, self.W, self.lam
@@ -94,13 +102,8 @@ class TrainStep:
         cnt = B * self.n_pred
         be.hinge(pred, cnt, 0, 0.5 / cnt, 0.5 / cnt, self.sums[0:3], self.D2.dpred)   # irc:1647-1649
         self.D2.backward(self.D2.dpred, True)                                  # irc:1650
-        self._allreduce(self.D2.arena)
-        A = self.D2.arena
-        be.adam(A.flat, A.grad, A.m, A.v, self.optD.dev)                       # irc:1651
-        self.D2.refresh_weights()
-        # ---------------- G update (irc:1656-1681)
-        pred_f = self.D1.forward(ir, fake)                                     # irc:1659
-        be.hinge(pred_f, 0, 1, lam["gan"] / cnt, 0.0, self.sums[0:3], self.D1.dpred)   # irc:1662, :1679
+        wD = self._allreduce_async(self.D2.arena.grad)
+        # ---------------- G update, the part that does not involve D (overlaps the D-gradient all-reduce)
         npix = B * 3 * H * W
         be.pixel_loss(fake, rgb, lam["L1"] / npix, lam["tv"] / (B * 3 * (H - 1) * W), lam["tv"] / (B * 3 * H * (W - 1)),
                       self.sums[3:6], self.dfake)                              # irc:1664, :1672
@@ -110,10 +113,22 @@ class TrainStep:
         nfeat = B * 256 * (H // 4) * (W // 4)
         be.feat_l1(feat.t, feat.rows_of(B), 256, lam["perc"] / nfeat, self.sums[6:7], self.V.dz[-1].t)   # irc:1669
         self.V.backward(self.dfake)
+        # ---------------- D optimizer step, then the adversarial term with the updated D (irc:1651, :1659-1662)
+        self._wait(wD)
+        A = self.D2.arena
+        be.adam(A.flat, A.grad, A.m, A.v, self.optD.dev)                       # irc:1651
+        self.D2.refresh_weights()
+        pred_f = self.D1.forward(ir, fake)                                     # irc:1659
+        be.hinge(pred_f, 0, 1, lam["gan"] / cnt, 0.0, self.sums[0:3], self.D1.dpred)   # irc:1662, :1679
         self.D1.backward(self.D1.dpred, False, self.dfake)
-        self.G.backward(self.dfake)                                            # irc:1680
-        self._allreduce(self.G.arena)
+        # ---------------- generator backward (irc:1680); gradients of everything past the encoder are final once
+        # the ResNet blocks are done, so their all-reduce overlaps the full-resolution encoder backward
         A = self.G.arena
+        split = A.offset["resblocks.0.conv_block.1.weight"]
+        works = []
+        self.G.backward(self.dfake, after_blocks=lambda: works.append(self._allreduce_async(A.grad[split:])))
+        works.append(self._allreduce_async(A.grad[:split]))
+        self._wait(*works)
         be.adam(A.flat, A.grad, A.m, A.v, self.optG.dev)                       # irc:1681
         self.G.refresh_weights()
 

@@ -38,6 +38,7 @@ class RefBackend:
 
     def __init__(self):
         self.launches = 0
+        self.note = None
 
     # ------------------------------------------------------------------ addressing
     @staticmethod
