@@ -163,17 +163,19 @@ typedef struct irc_col2im_args {
 } irc_col2im_args;
 int irc_col2im(const irc_col2im_args* args, void* stream);
 
-/* Shifted tap reduction / expansion around a GEMM over one kernel axis:
- *   reduce: out[n][co][y][x] = act(bias[co] + sum_j P[q(n,y,x) + shifts[j]][j*nco + co]), act 3 = tanh
- *   expand: E[q][j*nco + co] = g[pixel(q - shifts[j])][co] * (1 - y^2 if y given); dbias[co] = sum g'
+/* Shifted tap reduction / expansion around a GEMM over one kernel axis (shift_j = dy[j]*wp + dx[j] rows; the
+ * padding ring of the frame must be at least max|dx| wide):
+ *   reduce: out[n][co][y][x] = act(bias[co] + sum_j P[q(n,y,x) + shift_j][j*nco + co]), act 3 = tanh
+ *   expand: E[q][j*nco + co] = g[pixel(q - shift_j)][co] * (1 - y^2 if y given); dbias[co] = sum g'
  * outc + tanh (irc:527-531) and D model.11 (irc:629), forward and backward. */
 typedef struct irc_tap_args {
     int nshift, nco;
-    int shifts[IRC_MAX_TAPS];
+    int dy[IRC_MAX_TAPS], dx[IRC_MAX_TAPS];
     int n_img, H, W, hp, wp, oy, ox;
 } irc_tap_args;
 int irc_tap_reduce(const irc_tap_args* t, const float* P, long long ldp, const float* bias, int act, float* out, void* stream);
-int irc_tap_expand(const irc_tap_args* t, const float* g, const float* y, void* E, float* dbias, void* stream);
+int irc_tap_expand(const irc_tap_args* t, const float* g, const float* y, void* E, float* dbias, float* work, long long work_floats,
+                   void* stream);
 
 /* ---- losses (fp32 NCHW) --------------------------------------------------------------- */
 
@@ -213,6 +215,14 @@ int irc_adam(float* p, const float* g, float* m, float* v, long long n, const fl
 int irc_pack_bf16(const float* src, const int* map, long long n, void* dst, void* stream);
 /* dst[i] = sum_s src[s*split_stride + map[i]]: split weight-gradient partials -> OIHW fp32. */
 int irc_gather_sum(const float* src, const int* map, long long n, int splits, long long split_stride, float* dst, void* stream);
+
+/* ---- stand-alone anti-aliased resampling on fp32 NCHW ---------------------------------- */
+
+/* out[p][Y][X] (+)= sum_ij ty_w[Y][i] tx_w[X][j] in[p][ty_idx[Y][i]][tx_idx[X][j]] over `planes` = N*C planes.
+ * With the binomial stride-2 tables this is Downsample.forward (irc:307-310); with blur*bilinear tables
+ * UpsampleAA.forward (irc:350-355); with the transposed tables their backward passes. */
+int irc_stencil_nchw(const float* in, float* out, int planes, int Hi, int Wi, int Ho, int Wo, const int* ty_idx, const float* ty_w, int ky,
+                     const int* tx_idx, const float* tx_w, int kx, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ EXPORTS = [
     "irc_in_stats", "irc_gather", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_maxpool2", "irc_maxpool2_bwd",
     "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
     "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics",
-    "irc_adam", "irc_pack_bf16", "irc_gather_sum",
+    "irc_adam", "irc_pack_bf16", "irc_gather_sum", "irc_stencil_nchw",
 ]
 
 
@@ -102,7 +102,7 @@ class Col2imArgs(C.Structure):
 
 
 class TapArgs(C.Structure):
-    _fields_ = [("nshift", C.c_int), ("nco", C.c_int), ("shifts", C.c_int * MAX_TAPS),
+    _fields_ = [("nshift", C.c_int), ("nco", C.c_int), ("dy", C.c_int * MAX_TAPS), ("dx", C.c_int * MAX_TAPS),
                 ("n_img", C.c_int), ("H", C.c_int), ("W", C.c_int), ("hp", C.c_int), ("wp", C.c_int),
                 ("oy", C.c_int), ("ox", C.c_int)]
 
@@ -325,8 +325,8 @@ class CudaBackend:
     @staticmethod
     def _tap(shifts, nco, n_img, H, W, hp, wp, oy, ox):
         t = TapArgs(); t.nshift = len(shifts); t.nco = nco
-        for i, s in enumerate(shifts):
-            t.shifts[i] = int(s)
+        for i, (dy, dx) in enumerate(shifts):
+            t.dy[i] = int(dy); t.dx[i] = int(dx)
         t.n_img = n_img; t.H = H; t.W = W; t.hp = hp; t.wp = wp; t.oy = oy; t.ox = ox
         return t
 
@@ -337,8 +337,8 @@ class CudaBackend:
     def tap_expand(self, g, y, shifts, nco, n_img, H, W, hp, wp, oy, ox, E, dbias=None):
         t = self._tap(shifts, nco, n_img, H, W, hp, wp, oy, ox)
         assert E.shape == (n_img * hp * wp, 64)
-        check(self.L.irc_tap_expand(C.byref(t), _p(g), _p(y), _p(E), _p(dbias), _stream()))
-        self.launches += 1 if dbias is None else 2
+        check(self.L.irc_tap_expand(C.byref(t), _p(g), _p(y), _p(E), _p(dbias), _p(self.work), C.c_longlong(self.work.numel()), _stream()))
+        self.launches += 1 if dbias is None else 3
 
     # ---- losses
     def pixel_loss(self, fake, target, w_l1, w_tvv, w_tvh, sums, dfake):
@@ -384,6 +384,13 @@ class CudaBackend:
     def gather_sum(self, src, map_, splits, split_stride, dst):
         check(self.L.irc_gather_sum(_p(src), _p(map_), C.c_longlong(map_.numel()), splits, C.c_longlong(split_stride), _p(dst),
                                     _stream())); self.launches += 1
+
+    def stencil_nchw(self, x, out, tables: Tables, accumulate=False):
+        n, c, hi, wi = x.shape
+        ho, wo = out.shape[2], out.shape[3]
+        assert x.dtype == torch.float32 and out.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+        check(self.L.irc_stencil_nchw(_p(x), _p(out), n * c, hi, wi, ho, wo, _p(tables.ty_idx), _p(tables.ty_w), tables.ky,
+                                      _p(tables.tx_idx), _p(tables.tx_w), tables.kx, int(accumulate), _stream())); self.launches += 1
 
     def zero_(self, t):
         t.zero_(); self.launches += 1

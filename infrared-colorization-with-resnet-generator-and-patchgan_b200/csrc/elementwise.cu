@@ -83,12 +83,11 @@ __global__ void in_stats_kernel(View z, int C, int H, int W, float* part) {
     const int C8 = C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
     const int n = blockIdx.y;
-    const int P = H * W;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ss[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (lane < L) {
-        for (int pix = blockIdx.x * L + lane; pix < P; pix += gridDim.x * L) {
+    for (int y = blockIdx.x; y < H; y += gridDim.x) {
+        for (int x = lane; x < W; x += L) {
             float v[8];
-            load8(z.at(n, pix / W, pix % W, cv * 8), v);
+            load8(z.at(n, y, x, cv * 8), v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { s[j] += v[j]; ss[j] += v[j] * v[j]; }
         }
@@ -129,65 +128,68 @@ struct GatherP {
 };
 
 __global__ void gather_kernel(const GatherP p) {
+    // one block per (image, padded row); thread = (channel vector, pixel lane): nothing is divided in the loops
     const int C8 = p.C >> 3;
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int c = cv * 8;
     const int Hp = p.H + 2 * p.pad, Wp = p.W + 2 * p.pad;
-    const long long total = (long long)p.n_img * Hp * Wp * C8;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % C8) * 8;
-        long long pix = idx / C8;
-        const int X = (int)(pix % Wp); pix /= Wp;
-        const int Y = (int)(pix % Hp);
-        const int n = (int)(pix / Hp);
-        int y = Y - p.pad, x = X - p.pad;
-        const bool halo = y < 0 || y >= p.H || x < 0 || x >= p.W;
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (!halo || p.halo_mode == 1) {
-            if (halo) { y = reflect_idx(y, p.H); x = reflect_idx(x, p.W); }
-            float mu[8], rs[8];
-            if (p.stats) moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
-            for (int i = 0; i < p.ky; ++i) {
-                const int iy = p.ty_idx ? __ldg(p.ty_idx + y * p.ky + i) : y;
-                const float wy = p.ty_w ? __ldg(p.ty_w + y * p.ky + i) : 1.f;
-                if (wy == 0.f) continue;
-                for (int j = 0; j < p.kx; ++j) {
-                    const int ix = p.tx_idx ? __ldg(p.tx_idx + x * p.kx + j) : x;
-                    const float w = wy * (p.tx_w ? __ldg(p.tx_w + x * p.kx + j) : 1.f);
-                    if (w == 0.f) continue;
-                    float v[8];
-                    load8(p.src.at(n, iy, ix, c), v);
-                    if (p.stats) {
+    for (int row = blockIdx.x; row < p.n_img * Hp; row += gridDim.x) {
+        const int n = row / Hp, Y = row - n * Hp;
+        int y = Y - p.pad;
+        const bool halo_y = y < 0 || y >= p.H;
+        if (halo_y) y = reflect_idx(y, p.H);
+        float mu[8], rs[8];
+        if (p.stats) moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+        for (int X = lane; X < Wp; X += L) {
+            int x = X - p.pad;
+            const bool halo = halo_y || x < 0 || x >= p.W;
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (!halo || p.halo_mode == 1) {
+                if (x < 0 || x >= p.W) x = reflect_idx(x, p.W);
+                for (int i = 0; i < p.ky; ++i) {
+                    const int iy = p.ty_idx ? __ldg(p.ty_idx + y * p.ky + i) : y;
+                    const float wy = p.ty_w ? __ldg(p.ty_w + y * p.ky + i) : 1.f;
+                    if (wy == 0.f) continue;
+                    for (int j = 0; j < p.kx; ++j) {
+                        const int ix = p.tx_idx ? __ldg(p.tx_idx + x * p.kx + j) : x;
+                        const float w = wy * (p.tx_w ? __ldg(p.tx_w + x * p.kx + j) : 1.f);
+                        if (w == 0.f) continue;
+                        float v[8];
+                        load8(p.src.at(n, iy, ix, c), v);
+                        if (p.stats) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] = actf((v[k] - mu[k]) * rs[k], p.act, p.slope);
-                    } else if (p.act) {
+                            for (int k = 0; k < 8; ++k) v[k] = actf((v[k] - mu[k]) * rs[k], p.act, p.slope);
+                        } else if (p.act) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] = actf(v[k], p.act, p.slope);
+                            for (int k = 0; k < 8; ++k) v[k] = actf(v[k], p.act, p.slope);
+                        }
+                        if (p.has2) {
+                            float u[8];
+                            load8(p.src2.at(n, iy, ix, c), u);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) v[k] += u[k];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[k] += w * v[k];
                     }
-                    if (p.has2) {
-                        float u[8];
-                        load8(p.src2.at(n, iy, ix, c), u);
+                }
+                if (p.has_res) {
+                    float u[8];
+                    load8(p.res.at(n, y, x, c), u);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] += u[k];
-                    }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) acc[k] += w * v[k];
+                    for (int k = 0; k < 8; ++k) acc[k] += u[k];
                 }
             }
-            if (p.has_res) {
-                float u[8];
-                load8(p.res.at(n, y, x, c), u);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += u[k];
+            bf16* d;
+            if (p.dst_s2d) {
+                // padded pixel (Y, X) -> 2x2 block (Y/2, X/2), channel group (Y&1)*2 + (X&1)
+                const long long r = ((long long)n * (Hp >> 1) + (Y >> 1)) * (Wp >> 1) + (X >> 1);
+                d = const_cast<bf16*>(p.dst.p) + r * p.dst.ld + p.dst.off + ((Y & 1) * 2 + (X & 1)) * p.C + c;
+            } else {
+                d = const_cast<bf16*>(p.dst.p) + ((long long)(n * p.dst.hp + Y - p.pad + p.dst.oy) * p.dst.wp + (X - p.pad + p.dst.ox)) * p.dst.ld + p.dst.off + c;
             }
+            store8(d, acc);
         }
-        bf16* d;
-        if (p.dst_s2d) {
-            // padded pixel (Y, X) -> 2x2 block (Y/2, X/2), channel group (Y&1)*2 + (X&1)
-            const long long r = ((long long)n * (Hp >> 1) + (Y >> 1)) * (Wp >> 1) + (X >> 1);
-            d = const_cast<bf16*>(p.dst.p) + r * p.dst.ld + p.dst.off + ((Y & 1) * 2 + (X & 1)) * p.C + c;
-        } else {
-            d = const_cast<bf16*>(p.dst.p) + ((long long)(n * p.dst.hp + Y - p.pad + p.dst.oy) * p.dst.wp + (X - p.pad + p.dst.ox)) * p.dst.ld + p.dst.off + c;
-        }
-        store8(d, acc);
     }
 }
 
@@ -239,21 +241,21 @@ __global__ void in_bwd_reduce_kernel(const InBwdP p) {
     const int C8 = p.C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
     const int n = blockIdx.y, c = cv * 8;
-    const int P = p.H * p.W;
     float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (lane < L) {
+    {
         float mu[8], rs[8];
         moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
-        for (int pix = blockIdx.x * L + lane; pix < P; pix += gridDim.x * L) {
-            const int y = pix / p.W, x = pix % p.W;
-            float g[8], zv[8];
-            bwd_gather(p, n, y, x, c, g);
-            load8(p.z.at(n, y, x, c), zv);
+        for (int y = blockIdx.x; y < p.H; y += gridDim.x) {
+            for (int x = lane; x < p.W; x += L) {
+                float g[8], zv[8];
+                bwd_gather(p, n, y, x, c, g);
+                load8(p.z.at(n, y, x, c), zv);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float xh = (zv[k] - mu[k]) * rs[k];
-                const float gd = g[k] * dactf(xh, p.act, p.slope);
-                s1[k] += gd; s2[k] += gd * xh;
+                for (int k = 0; k < 8; ++k) {
+                    const float xh = (zv[k] - mu[k]) * rs[k];
+                    const float gd = g[k] * dactf(xh, p.act, p.slope);
+                    s1[k] += gd; s2[k] += gd * xh;
+                }
             }
         }
     }
@@ -271,37 +273,37 @@ __global__ void in_bwd_reduce_kernel(const InBwdP p) {
 
 __global__ void in_bwd_apply_kernel(const InBwdP p) {
     const int C8 = p.C >> 3;
-    const long long total = (long long)p.n_img * p.H * p.W * C8;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % C8) * 8;
-        long long pix = idx / C8;
-        const int x = (int)(pix % p.W); pix /= p.W;
-        const int y = (int)(pix % p.H);
-        const int n = (int)(pix / p.H);
-        float g[8], zv[8], o[8];
-        bwd_gather(p, n, y, x, c, g);
-        load8(p.z.at(n, y, x, c), zv);
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int c = cv * 8;
+    for (int row = blockIdx.x; row < p.n_img * p.H; row += gridDim.x) {
+        const int n = row / p.H, y = row - n * p.H;
+        float mu[8], rs[8], b1[8], b2[8];
         if (p.stats) {
-            float mu[8], rs[8];
             moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
             const float4* bp = reinterpret_cast<const float4*>(p.bsum + ((long long)n * p.C + c) * 2);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 b = __ldg(bp + q);
-                const float bs1[2] = {b.x, b.z}, bs2[2] = {b.y, b.w};
+                b1[q * 2] = b.x * p.inv_cnt; b2[q * 2] = b.y * p.inv_cnt; b1[q * 2 + 1] = b.z * p.inv_cnt; b2[q * 2 + 1] = b.w * p.inv_cnt;
+            }
+        }
+        for (int x = lane; x < p.W; x += L) {
+            float g[8], zv[8], o[8];
+            bwd_gather(p, n, y, x, c, g);
+            load8(p.z.at(n, y, x, c), zv);
+            if (p.stats) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int k = q * 2 + h;
+                for (int k = 0; k < 8; ++k) {
                     const float xh = (zv[k] - mu[k]) * rs[k];
                     const float gd = g[k] * dactf(xh, p.act, p.slope);
-                    o[k] = rs[k] * (gd - bs1[h] * p.inv_cnt - xh * bs2[h] * p.inv_cnt);
+                    o[k] = rs[k] * (gd - b1[k] - xh * b2[k]);
                 }
-            }
-        } else {
+            } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = g[k] * dactf(zv[k], p.act, p.slope);
+                for (int k = 0; k < 8; ++k) o[k] = g[k] * dactf(zv[k], p.act, p.slope);
+            }
+            store8(const_cast<bf16*>(p.dz.at(n, y, x, c)), o);
         }
-        store8(const_cast<bf16*>(p.dz.at(n, y, x, c)), o);
     }
 }
 
@@ -393,12 +395,19 @@ int check_view(const irc_view& v, const char* what) {
 }
 
 // block shape for the per-(n,c) reductions
-void reduce_shape(int C, int P, int n_img, long long work_floats, int& threads, int& L, int& chunks, size_t& smem) {
+// block = (C/8 channel vectors) x L pixel lanes
+void row_block(int C, int W, int& threads, int& L) {
     const int C8 = C / 8;
     L = 256 / C8; if (L < 1) L = 1;
+    if (L > W) L = W;
     threads = L * C8;
+}
+
+void reduce_shape(int C, int H, int W, int n_img, long long work_floats, int& threads, int& L, int& chunks, size_t& smem) {
+    const int C8 = C / 8;
+    row_block(C, W, threads, L);
     long long want = ((long long)irc_num_sms() * 4 + n_img - 1) / n_img;
-    long long maxc = (P + L - 1) / L;
+    long long maxc = H;
     chunks = (int)(want < maxc ? want : maxc);
     const long long cap = work_floats / ((long long)n_img * C * 2);
     if (chunks > cap) chunks = (int)cap;
@@ -419,7 +428,7 @@ extern "C" int irc_in_stats(const irc_view* z, int C, int n_img, int H, int W, f
     int rc = check_view(*z, "irc_in_stats"); if (rc) return rc;
     if (C % 8 || C > 2048) return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_stats: C must be a multiple of 8");
     int threads, L, chunks; size_t smem;
-    reduce_shape(C, H * W, n_img, work ? work_floats : 0, threads, L, chunks, smem);
+    reduce_shape(C, H, W, n_img, work ? work_floats : 0, threads, L, chunks, smem);
     const long long n = (long long)n_img * C * 2;
     if (chunks == 1) {
         in_stats_kernel<<<dim3(1, n_img), threads, smem, (cudaStream_t)stream>>>(mk(*z), C, H, W, stats);
@@ -444,8 +453,10 @@ extern "C" int irc_gather(const irc_gather_args* a, void* stream) {
     p.tx_idx = a->tx_idx; p.tx_w = a->tx_w; p.kx = a->kx > 0 ? a->kx : 1;
     p.H = a->H; p.W = a->W; p.pad = a->pad; p.halo_mode = a->halo_mode; p.dst_s2d = a->dst_s2d;
     if (p.dst_s2d && (((p.H + 2 * p.pad) | (p.W + 2 * p.pad)) & 1)) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather: space-to-depth needs even padded extents");
-    const long long total = (long long)p.n_img * (p.H + 2 * p.pad) * (p.W + 2 * p.pad) * (p.C / 8);
-    gather_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    int threads, L;
+    row_block(p.C, p.W + 2 * p.pad, threads, L);
+    const long long rows = (long long)p.n_img * (p.H + 2 * p.pad);
+    gather_kernel<<<(unsigned)(rows < 65535 * 16 ? rows : 65535 * 16), threads, 0, (cudaStream_t)stream>>>(p);
     return irc_check_launch("irc_gather");
 }
 
@@ -467,7 +478,7 @@ extern "C" int irc_in_bwd_reduce(const irc_in_bwd_args* a, void* stream) {
     InBwdP p; int rc = fill_bwd(a, p); if (rc) return rc;
     if (!p.stats || !p.bsum) return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_bwd_reduce: stats and bsum required");
     int threads, L, chunks; size_t smem;
-    reduce_shape(p.C, p.H * p.W, p.n_img, a->work ? a->work_floats : 0, threads, L, chunks, smem);
+    reduce_shape(p.C, p.H, p.W, p.n_img, a->work ? a->work_floats : 0, threads, L, chunks, smem);
     const long long n = (long long)p.n_img * p.C * 2;
     p.part = chunks == 1 ? p.bsum : a->work;
     in_bwd_reduce_kernel<<<dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream>>>(p);
@@ -480,8 +491,10 @@ extern "C" int irc_in_bwd_apply(const irc_in_bwd_args* a, void* stream) {
     rc = check_view(a->dz, "irc_in_bwd dz"); if (rc) return rc;
     p.dz = mk(a->dz);
     if (p.stats && !p.bsum) return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_bwd_apply: bsum required with stats");
-    const long long total = (long long)p.n_img * p.H * p.W * (p.C / 8);
-    in_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    int threads, L;
+    row_block(p.C, p.W, threads, L);
+    const long long rows = (long long)p.n_img * p.H;
+    in_bwd_apply_kernel<<<(unsigned)(rows < 65535 * 16 ? rows : 65535 * 16), threads, 0, (cudaStream_t)stream>>>(p);
     return irc_check_launch("irc_in_bwd_apply");
 }
 

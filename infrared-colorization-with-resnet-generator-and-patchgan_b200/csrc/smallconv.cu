@@ -2,6 +2,8 @@
 // has a tiny K (inc 1->64 7x7, VGG conv1_1 3->64, D model.0 4->64) are fed by an im2col
 // operand of 64 columns; the layers with a tiny N (outc 64->3 7x7, D model.11 512->1) are
 // computed as a GEMM over one kernel axis followed by a shifted tap reduction.
+#include <math.h>
+
 #include "irc_common.cuh"
 #include "../../include/irc_b200.h"
 
@@ -45,6 +47,15 @@ struct RowMap {
         if (mode == 0) return (long long)n_img * Ho * Wo;
         return (long long)n_img * (Ho + 2) * (Wo + 2);
     }
+    // the flat rows of one image form `lines()` lines of `line_len()` consecutive rows
+    __host__ __device__ int lines() const { return mode == 0 ? Ho : (mode == 1 ? Ho + 2 : (Ho + 2) >> 1); }
+    __host__ __device__ int line_len() const { return mode == 0 ? Wo : (mode == 1 ? Wo + 2 : ((Wo + 2) >> 1) * 4); }
+    __device__ __forceinline__ bool decode_line(int line, int i, int& oy, int& ox) const {
+        if (mode == 0) { oy = line; ox = i; return true; }
+        if (mode == 1) { oy = line - 1; ox = i - 1; }
+        else { const int sub = i & 3; oy = 2 * line + (sub >> 1) - 1; ox = 2 * (i >> 2) + (sub & 1) - 1; }
+        return oy >= 0 && oy < Ho && ox >= 0 && ox < Wo;
+    }
 };
 
 struct Im2colP {
@@ -56,37 +67,48 @@ struct Im2colP {
 };
 
 __global__ void im2col_kernel(const Im2colP p) {
+    // one block per (image, line of the row order); thread = (item of the line, group of 8 columns)
+    __shared__ int lut[64];          // column -> (c, r, s) packed, -1 = zero padding column
     const int C = p.c1 + p.c2;
     const int K = p.k * p.k * C;
-    const long long total = p.rm.rows() * 8;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(idx & 7);
-        const long long q = idx >> 3;
-        int n, oy, ox;
-        const bool live = p.rm.decode(q, n, oy, ox);
-        if (g == 0 && p.row_img) p.row_img[q] = live ? (short)n : (short)-1;
-        float v[8];
+    if (threadIdx.x < 64) {
+        const int col = threadIdx.x;
+        int v = -1;
+        if (col < K) { const int c = col % C, rs = col / C; v = c | ((rs / p.k) << 8) | ((rs % p.k) << 16); }
+        lut[col] = v;
+    }
+    __syncthreads();
+    const int nl = p.rm.lines(), ll = p.rm.line_len();
+    const int g = threadIdx.x & 7;
+    for (int bl = blockIdx.x; bl < p.rm.n_img * nl; bl += gridDim.x) {
+        const int n = bl / nl, line = bl - n * nl;
+        for (int i = threadIdx.x >> 3; i < ll; i += blockDim.x >> 3) {
+            const long long q = (long long)bl * ll + i;
+            int oy, ox;
+            const bool live = p.rm.decode_line(line, i, oy, ox);
+            if (g == 0 && p.row_img) p.row_img[q] = live ? (short)n : (short)-1;
+            float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int col = g * 8 + j;
-            float val = 0.f;
-            if (live && col < K) {
-                const int c = col % C, rs = col / C;
-                const int r = rs / p.k, s = rs % p.k;
-                int y = oy * p.stride - p.pad + r, x = ox * p.stride - p.pad + s;
-                bool ok = true;
-                if (p.pad_mode == 1) { y = reflect_idx(y, p.H); x = reflect_idx(x, p.W); }
-                else ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
-                if (ok) {
-                    const float raw = c < p.c1 ? __ldg(p.src1 + (((long long)n * p.c1 + c) * p.H + y) * p.W + x)
-                                               : __ldg(p.src2 + (((long long)n * p.c2 + (c - p.c1)) * p.H + y) * p.W + x);
-                    val = p.scale ? raw * __ldg(p.scale + c) + __ldg(p.shift + c) : raw;
+            for (int j = 0; j < 8; ++j) {
+                const int e = lut[g * 8 + j];
+                float val = 0.f;
+                if (live && e >= 0) {
+                    const int c = e & 255, r = (e >> 8) & 255, s_ = e >> 16;
+                    int y = oy * p.stride - p.pad + r, x = ox * p.stride - p.pad + s_;
+                    bool ok = true;
+                    if (p.pad_mode == 1) { y = reflect_idx(y, p.H); x = reflect_idx(x, p.W); }
+                    else ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
+                    if (ok) {
+                        const float raw = c < p.c1 ? __ldg(p.src1 + (((long long)n * p.c1 + c) * p.H + y) * p.W + x)
+                                                   : __ldg(p.src2 + (((long long)n * p.c2 + (c - p.c1)) * p.H + y) * p.W + x);
+                        val = p.scale ? raw * __ldg(p.scale + c) + __ldg(p.shift + c) : raw;
+                    }
                 }
+                v[j] = val;
             }
-            v[j] = val;
+            *reinterpret_cast<uint4*>(p.dst + q * 64 + g * 8) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
-        *reinterpret_cast<uint4*>(p.dst + q * 64 + g * 8) =
-            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     }
 }
 
@@ -129,6 +151,7 @@ __global__ void col2im_kernel(const Col2imP p) {
 struct TapP {
     int nshift, nco;
     int shifts[IRC_MAX_TAPS];
+    signed char dy[IRC_MAX_TAPS], dx[IRC_MAX_TAPS];   // shift = dy*wp + dx with |dx| < wp/2
     int n_img, H, W, hp, wp, oy, ox;
 };
 
@@ -149,55 +172,57 @@ __global__ void tap_reduce_kernel(const float* P, long long ldp, const float* bi
     }
 }
 
-// E[q][j*nco + co] = g'[pixel(q - shift_j)][co];  g' = g * (1 - yv^2) when yv is given (tanh')
+// E[q][j*nco + co] = g'[pixel(q - shift_j)][co];  g' = g * (1 - yv^2) when yv is given (tanh').
+// A shifted position that leaves its frame line lands in the padding ring (the ring is at least as wide as the
+// largest horizontal shift), i.e. on a zero, so the (dy, dx) decomposition needs no wrap-around handling.
 __global__ void tap_expand_kernel(const float* g, const float* yv, bf16* E, const TapP t) {
-    const long long rows = (long long)t.n_img * t.hp * t.wp;
-    const long long total = rows * 8;
     const int ncol = t.nshift * t.nco;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int grp = (int)(idx & 7);
-        const long long q = idx >> 3;
-        float v[8];
+    const int grp = threadIdx.x & 7;
+    for (int row = blockIdx.x; row < t.n_img * t.hp; row += gridDim.x) {
+        const int n = row / t.hp, Y = row - n * t.hp;
+        for (int X = threadIdx.x >> 3; X < t.wp; X += blockDim.x >> 3) {
+            float v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int col = grp * 8 + k;
-            float val = 0.f;
-            if (col < ncol) {
-                const int j = col / t.nco, co = col % t.nco;
-                const long long qq = q - t.shifts[j];
-                if (qq >= 0 && qq < rows) {
-                    const int x = (int)(qq % t.wp) - t.ox;
-                    const int y = (int)((qq / t.wp) % t.hp) - t.oy;
-                    const int n = (int)(qq / ((long long)t.wp * t.hp));
+            for (int k = 0; k < 8; ++k) {
+                const int col = grp * 8 + k;
+                float val = 0.f;
+                if (col < ncol) {
+                    const int j = col / t.nco, co = col - j * t.nco;
+                    const int y = Y - t.dy[j] - t.oy, x = X - t.dx[j] - t.ox;
                     if (x >= 0 && x < t.W && y >= 0 && y < t.H) {
                         const long long o = (((long long)n * t.nco + co) * t.H + y) * t.W + x;
                         val = __ldg(g + o);
                         if (yv) { const float yy = __ldg(yv + o); val *= (1.f - yy * yy); }
                     }
                 }
+                v[k] = val;
             }
-            v[k] = val;
+            *reinterpret_cast<uint4*>(E + ((long long)row * t.wp + X) * 64 + grp * 8) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
-        *reinterpret_cast<uint4*>(E + q * 64 + grp * 8) =
-            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     }
 }
 
-// out[c] = sum_{n, pixels} g[n][c][.] * (1 - yv^2)
-__global__ void chan_sum_kernel(const float* g, const float* yv, int n_img, int C, long long hw, float* out) {
+// part[b][c] = partial sum over block b's slice of sum_{n, pixels} g[n][c][.] * (1 - yv^2); chan_sum_final adds the
+// partials in a fixed order (bit-reproducible)
+__global__ void chan_sum_kernel(const float* g, const float* yv, int n_img, int C, long long hw, float* part) {
     __shared__ float sh[32];
     const int c = blockIdx.y;
     float s = 0.f;
     const long long total = (long long)n_img * hw;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long n = i / hw, r = i % hw;
+        const long long n = i / hw, r = i - n * hw;
         const long long o = (n * C + c) * hw + r;
         float v = __ldg(g + o);
         if (yv) { const float yy = __ldg(yv + o); v *= (1.f - yy * yy); }
         s += v;
     }
     s = block_sum(s, sh);
-    if (threadIdx.x == 0) out[c] = s;     // one block per channel: deterministic
+    if (threadIdx.x == 0) part[(long long)blockIdx.x * C + c] = s;
+}
+__global__ void chan_sum_final(const float* part, int nb, int C, float* out) {
+    const int c = threadIdx.x;
+    if (c < C) { float a = 0.f; for (int b = 0; b < nb; ++b) a += part[(long long)b * C + c]; out[c] = a; }
 }
 
 int grid_for(long long total, int threads) {
@@ -226,7 +251,8 @@ extern "C" int irc_im2col(const irc_im2col_args* a, void* stream) {
     p.H = a->H; p.W = a->W; p.k = a->k; p.stride = a->stride; p.pad = a->pad; p.pad_mode = a->pad_mode;
     p.rm.mode = a->row_mode; p.rm.n_img = a->n_img; p.rm.Ho = a->Ho; p.rm.Wo = a->Wo;
     p.dst = (bf16*)a->dst; p.row_img = a->row_img;
-    im2col_kernel<<<grid_for(p.rm.rows() * 8, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    const long long nblk = (long long)p.rm.n_img * p.rm.lines();
+    im2col_kernel<<<(unsigned)(nblk < 1048576 ? nblk : 1048576), 256, 0, (cudaStream_t)stream>>>(p);
     return irc_check_launch("irc_im2col");
 }
 
@@ -245,7 +271,12 @@ extern "C" int irc_col2im(const irc_col2im_args* a, void* stream) {
 static int fill_tap(const irc_tap_args* a, TapP& t) {
     if (a->nshift <= 0 || a->nshift > IRC_MAX_TAPS || a->nshift * a->nco > 64) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tap: nshift*nco must be <= 64");
     t.nshift = a->nshift; t.nco = a->nco;
-    for (int i = 0; i < a->nshift; ++i) t.shifts[i] = a->shifts[i];
+    for (int i = 0; i < a->nshift; ++i) {
+        const int dy = a->dy[i], dx = a->dx[i];
+        if (dy < -127 || dy > 127 || dx < -127 || dx > 127) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tap: shift out of range");
+        t.shifts[i] = dy * a->wp + dx;
+        t.dy[i] = (signed char)dy; t.dx[i] = (signed char)dx;
+    }
     t.n_img = a->n_img; t.H = a->H; t.W = a->W; t.hp = a->hp; t.wp = a->wp; t.oy = a->oy; t.ox = a->ox;
     return IRC_OK;
 }
@@ -257,15 +288,21 @@ extern "C" int irc_tap_reduce(const irc_tap_args* a, const float* P, long long l
     return irc_check_launch("irc_tap_reduce");
 }
 
-extern "C" int irc_tap_expand(const irc_tap_args* a, const float* g, const float* y, void* E, float* dbias, void* stream) {
+extern "C" int irc_tap_expand(const irc_tap_args* a, const float* g, const float* y, void* E, float* dbias, float* work, long long work_floats,
+                              void* stream) {
     TapP t; int rc = fill_tap(a, t); if (rc) return rc;
     if (!g || !E) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tap_expand: null");
-    const long long rows = (long long)t.n_img * t.hp * t.wp;
-    tap_expand_kernel<<<grid_for(rows * 8, 256), 256, 0, (cudaStream_t)stream>>>(g, y, (bf16*)E, t);
+    const long long nrow = (long long)t.n_img * t.hp;
+    tap_expand_kernel<<<(unsigned)(nrow < 1048576 ? nrow : 1048576), 256, 0, (cudaStream_t)stream>>>(g, y, (bf16*)E, t);
     rc = irc_check_launch("irc_tap_expand"); if (rc) return rc;
     if (dbias) {
         const long long hw = (long long)t.H * t.W;
-        chan_sum_kernel<<<dim3(1, t.nco), 1024, 0, (cudaStream_t)stream>>>(g, y, t.n_img, t.nco, hw, dbias);
+        long long nb = ((long long)t.n_img * hw + 4095) / 4096;
+        if (nb > 512) nb = 512;
+        if (!work || work_floats < nb * t.nco) nb = 1;
+        float* part = nb == 1 ? dbias : work;
+        chan_sum_kernel<<<dim3((unsigned)nb, t.nco), 256, 0, (cudaStream_t)stream>>>(g, y, t.n_img, t.nco, hw, part);
+        if (nb > 1) chan_sum_final<<<1, 64, 0, (cudaStream_t)stream>>>(work, (int)nb, t.nco, dbias);
         rc = irc_check_launch("irc_tap_expand(dbias)");
     }
     return rc;

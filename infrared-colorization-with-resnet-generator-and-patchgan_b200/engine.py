@@ -101,13 +101,14 @@ class ConvOp:
 # generator (irc:425-569)
 # ==========================================================================================
 class GeneratorEngine:
-    def __init__(self, be, B: int, H: int, W: int, device, ngf: int = 64, n_blocks: int = 9, training: bool = True):
+    def __init__(self, be, B: int, H: int, W: int, device, ngf: int = 64, n_blocks: int = 9, training: bool = True,
+                 arena: L.ParamArena = None):
         if H % 4 or W % 4:
             raise NotImplementedError("H and W must be multiples of 4 (the reference's odd-size bilinear fix-up, irc:555-563, is not built yet)")
         if ngf != 64:
             raise NotImplementedError("ngf must be 64 (channel counts are tiled in units of 64)")
         self.be, self.B, self.H, self.W, self.dev, self.nb, self.training = be, B, H, W, device, n_blocks, training
-        self.arena = L.ParamArena(generator_shapes(1, 3, ngf, n_blocks), device)
+        self.arena = arena or L.ParamArena(generator_shapes(1, 3, ngf, n_blocks), device)
         self.packer = L.Packer(self.arena)
         A, P = self.arena, self.packer
         H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
@@ -141,8 +142,9 @@ class GeneratorEngine:
         self.t_up2 = mk(L.up_matrix(H2), L.up_matrix(W2))
         self.t_down1_T = mk(L.down_matrix(H).T, L.down_matrix(W).T)
         self.t_down2_T = mk(L.down_matrix(H2).T, L.down_matrix(W2).T)
-        self.t_up1_T = mk(L.up_matrix(H4).T, L.up_matrix(W4).T)
-        self.t_up2_T = mk(L.up_matrix(H2).T, L.up_matrix(W2).T)
+        # UpsampleAA^T has 6 taps per axis: applied as two separable passes (rows, then columns)
+        self.t_up1_Ty, self.t_up1_Tx = mk(L.up_matrix(H4).T, None), mk(None, L.up_matrix(W4).T)
+        self.t_up2_Ty, self.t_up2_Tx = mk(L.up_matrix(H2).T, None), mk(None, L.up_matrix(W2).T)
         self.t_fold1 = mk(L.fold_matrix(H4, 1), L.fold_matrix(W4, 1))
         self.t_fold3 = mk(L.fold_matrix(H, 3), L.fold_matrix(W, 3))
         # ---- weights
@@ -158,7 +160,7 @@ class GeneratorEngine:
         self.up2 = ConvOp(be, L.layout_std(P, A, "up2_conv.0.weight", 64, 192, 3, 3), L.taps_centered(3, 3, wp1), A, self.Z4.rows, pixels=B * H * W, name="G.up2")
         self.outc = ConvOp(be, L.layout_outc(P, A, "outc.1.weight", 3, 64, 7), [(r - 3) * wp3 for r in range(7)], A, self.y4.rows,
                            bias_name="outc.1.bias", pixels=B * H * W, name="G.outc")
-        self.outc_shifts = [s - 3 for s in range(7)]
+        self.outc_shifts = [(0, s - 3) for s in range(7)]      # (dy, dx) of the horizontal taps
         P.finish()
         if training:
             self._alloc_backward()
@@ -180,6 +182,8 @@ class GeneratorEngine:
         self.dZ1 = F(H, W, 1, 128)
         self.Gx0 = F(H, W, 1, 64)
         self.dZ0 = F(H, W, 0, 64)
+        self.gU2 = F(H2, W, 0, 128)       # rows pass of UpsampleAA^T on Gcat2[0:128)
+        self.gU1 = F(H4, W2, 0, 256)      # rows pass of UpsampleAA^T on Gcat1[0:256)
 
     # ------------------------------------------------------------------ forward
     def refresh_weights(self):
@@ -247,13 +251,15 @@ class GeneratorEngine:
         self.up2.wgrad(self.dZ4.t, self.cat2.t, 0, self.cat2.rows)
         self.up2.dgrad(self.dZ4.t, self.Gcat2.t)
         # up1_conv (through UpsampleAA^T)
-        be.in_bwd(self.Z3.view(), self.Gcat2.view(0), self.dZ3.view(), 128, B, H2, W2, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
-                  tables=self.t_up2_T, bsum=self.bsum)
+        be.gather(self.Gcat2.view(0), self.gU2.view(), 128, B, H2, W, 0, 0, tables=self.t_up2_Ty)
+        be.in_bwd(self.Z3.view(), self.gU2.view(), self.dZ3.view(), 128, B, H2, W2, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
+                  tables=self.t_up2_Tx, bsum=self.bsum)
         self.up1.wgrad(self.dZ3.t, self.cat1.t, 0, self.cat1.rows)
         self.up1.dgrad(self.dZ3.t, self.Gcat1.t)
         # gradient w.r.t. the last ResNet block output = UpsampleAA^T of Gcat1[0:256)
         cur = self.dOut[0]
-        be.gather(self.Gcat1.view(0), cur.view(), 256, B, H4, W4, 1, 0, tables=self.t_up1_T)
+        be.gather(self.Gcat1.view(0), self.gU1.view(), 256, B, H4, W2, 0, 0, tables=self.t_up1_Ty)
+        be.gather(self.gU1.view(), cur.view(), 256, B, H4, W4, 1, 0, tables=self.t_up1_Tx)
         n4 = H4 * W4
         for b in reversed(range(self.nb)):
             c1, c2 = self.res[b]
@@ -290,10 +296,10 @@ class GeneratorEngine:
 # ==========================================================================================
 class DiscriminatorEngine:
     def __init__(self, be, n_img: int, H: int, W: int, device, arena: L.ParamArena = None, packer: L.Packer = None, layouts=None):
-        if H % 16 or W % 16:
-            raise NotImplementedError("discriminator engine needs H, W multiples of 16")
+        if H % 16 or W % 16 or H < 32 or W < 32:
+            raise NotImplementedError("discriminator engine needs H, W multiples of 16 and >= 32 (70x70 PatchGAN receptive field)")
         self.be, self.n, self.H, self.W, self.dev = be, n_img, H, W, device
-        own = arena is None
+        own = packer is None
         self.arena = arena or L.ParamArena(discriminator_shapes(4, 64), device)
         self.packer = packer or L.Packer(self.arena)
         A, P = self.arena, self.packer
@@ -334,7 +340,7 @@ class DiscriminatorEngine:
         self.c5 = ConvOp(be, layouts["l5"], [0, 1, self.wb2, self.wb2 + 1], A, self.Z5.shape[0], pixels=n * H3 * W3, name="D.5")
         self.c8 = ConvOp(be, layouts["l8"], L.taps_topleft(4, 4, self.X8.wp), A, self.X8.rows, pixels=n * self.H8o * self.W8o, name="D.8")
         self.c11 = ConvOp(be, layouts["l11"], [0], A, self.X11.rows, bias_name="model.11.bias", pixels=n * self.Ho * self.Wo, name="D.11")
-        self.shifts11 = L.taps_topleft(4, 4, self.X11.wp)
+        self.shifts11 = [(r, s) for r in range(4) for s in range(4)]    # (dy, dx) of the 16 taps
         if own:
             P.finish()
         # backward buffers
@@ -398,9 +404,10 @@ class DiscriminatorEngine:
         be.tap_reduce(self.P11, self.shifts11, 1, n, self.Ho, self.Wo, self.X11.hp, self.X11.wp, 0, 0, self.c11.bias(), ACT_NONE, self.pred)
         return self.pred
 
-    def backward(self, dpred: torch.Tensor, want_wgrad: bool, dinput: Optional[torch.Tensor] = None) -> None:
-        """dpred = dL/dscores.  want_wgrad fills arena.grad; dinput (fp32 [n,3,H,W]) accumulates the
-        gradient w.r.t. the image half of the input (channels 1..3 of cat[ir, img])."""
+    def backward(self, dpred: torch.Tensor, want_wgrad: bool, dinput: Optional[torch.Tensor] = None, c_first: int = 1,
+                 accumulate: bool = True) -> None:
+        """dpred = dL/dscores.  want_wgrad fills arena.grad; dinput (fp32 [n,c,H,W]) receives the gradient w.r.t.
+        input channels [c_first, c_first+c) of cat[ir, img] (default: accumulate into the 3 image channels)."""
         be, n = self.be, self.n
         G = self.arena.grad
         be.tap_expand(dpred, None, self.shifts11, 1, n, self.Ho, self.Wo, self.X11.hp, self.X11.wp, 0, 0, self.E11,
@@ -430,7 +437,7 @@ class DiscriminatorEngine:
             self.c0.wgrad(self.dZ0, self.E0, 0, self.rows0)
         if dinput is not None:
             self.c0.dgrad(self.dZ0, self.dE0)
-            be.col2im(self.dE0, 4, 1, 3, n, self.H, self.W, 4, 2, 1, self.H1, self.W1, 2, None, dinput, True)
+            be.col2im(self.dE0, 4, c_first, dinput.shape[1], n, self.H, self.W, 4, 2, 1, self.H1, self.W1, 2, None, dinput, accumulate)
 
 
 # ==========================================================================================
@@ -440,11 +447,11 @@ class VggEngine:
     """Frozen trunk.  n_img images go forward; backward (data gradient only) runs on the first
     n_bwd of them (the `fake` half when fake and target are batched together)."""
 
-    def __init__(self, be, n_img: int, n_bwd: int, H: int, W: int, device):
+    def __init__(self, be, n_img: int, n_bwd: int, H: int, W: int, device, arena: L.ParamArena = None):
         if H % 4 or W % 4:
             raise NotImplementedError("VGG engine needs H, W multiples of 4")
         self.be, self.n, self.nb, self.H, self.W, self.dev = be, n_img, n_bwd, H, W, device
-        self.arena = L.ParamArena(vgg_shapes(), device)
+        self.arena = arena or L.ParamArena(vgg_shapes(), device)
         self.packer = L.Packer(self.arena)
         A, P = self.arena, self.packer
         res = [(H, W), (H, W), (H // 2, W // 2), (H // 2, W // 2), (H // 4, W // 4), (H // 4, W // 4), (H // 4, W // 4)]

@@ -119,11 +119,12 @@ def to_ell(m: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     return idx, w
 
 
-def make_tables(my: np.ndarray, mx: np.ndarray, device) -> Tables:
-    iy, wy = to_ell(my)
-    ix, wx = to_ell(mx)
+def make_tables(my, mx, device) -> Tables:
+    """either operator may be None (= identity along that axis)"""
     f = lambda a: torch.from_numpy(a).to(device).contiguous()
-    return Tables(f(iy), f(wy), f(ix), f(wx))
+    iy, wy = (None, None) if my is None else map(f, to_ell(my))
+    ix, wx = (None, None) if mx is None else map(f, to_ell(mx))
+    return Tables(iy, wy, ix, wx)
 
 
 # ----------------------------------------------------------------------------------------

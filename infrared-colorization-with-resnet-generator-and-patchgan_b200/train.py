@@ -1,0 +1,222 @@
+"""Train / test drivers of the hot path (irc:1333-1514 core, irc:1521-1542, irc:1549-1723, irc:1730-1748).
+
+The reference reads KAIST image files through cv2/PIL (irc:803-1177); that I/O layer is outside the
+accelerated path, so the drivers here take any iterable of `{'ir': Bx1xHxW, 'rgb': Bx3xHxW}`
+batches in [-1,1] (the reference's DataLoader output format) or, with `cfg.synthetic_steps > 0`, generate
+synthetic pairs of that format."""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, Iterable, List, Optional
+
+import numpy as np
+import torch
+
+from . import modules as M
+from .train_step import TrainStep
+
+
+class SyntheticPairs:
+    """Batches shaped and ranged like KAISTPairDataset + DataLoader (irc:1045-1177, :1576-1581)."""
+
+    def __init__(self, steps: int, B: int, H: int, W: int, seed: int = 7, with_names: bool = False):
+        self.steps, self.B, self.H, self.W, self.seed = steps, B, H, W, seed
+
+    def __len__(self):
+        return self.steps
+
+    def __iter__(self):
+        g = torch.Generator().manual_seed(self.seed)
+        for i in range(self.steps):
+            ir = torch.rand(self.B, 1, self.H, self.W, generator=g) * 2 - 1
+            rgb = torch.rand(self.B, 3, self.H, self.W, generator=g) * 2 - 1
+            yield {"ir": ir, "rgb": rgb, "name": [f"synthetic_{i:05d}_{j}.png" for j in range(self.B)]}
+
+
+def tensor_to_rgb_image(t: torch.Tensor) -> np.ndarray:
+    """irc:865-876 for one image (1x3xHxW or 3xHxW in [-1,1]) -> HxWx3 uint8, truncating; runs on the device."""
+    x = t if t.dim() == 4 else t.unsqueeze(0)
+    x = x[:1].contiguous().float()
+    u8 = torch.empty(1, x.shape[2], x.shape[3], 3, device=x.device, dtype=torch.uint8)
+    M.backend().quantize_metrics(x, None, u8, None)
+    return u8[0].cpu().numpy()
+
+
+def compute_metrics(pred_01, gt_01):
+    """irc:1184-1217 on host arrays (HxWx3 float32 in [0,1]).  The SSIM metric needs scikit-image, which is a
+    third-party dependency that is not vendored: None when it is not importable, exactly like the reference."""
+    diff = pred_01 - gt_01
+    mae = float(np.mean(np.abs(diff)))
+    mse = float(np.mean(diff ** 2))
+    psnr = float("inf") if mse == 0 else 20.0 * math.log10(1.0) - 10.0 * math.log10(mse + 1e-12)
+    try:
+        from skimage.metrics import structural_similarity as ssim
+        ssim_val = float(ssim(gt_01, pred_01, data_range=1.0, channel_axis=2))
+    except ImportError:
+        ssim_val = None
+    return mae, mse, psnr, ssim_val
+
+
+def batch_metrics(fake: torch.Tensor, gt_01: torch.Tensor):
+    """Batched device version of tensor_to_rgb_image + compute_metrics: fake Bx3xHxW in [-1,1], gt Bx3xHxW in [0,1].
+    Returns (uint8 BxHxWx3 predictions, per-image mae, mse, psnr lists)."""
+    B, C, H, W = fake.shape
+    u8 = torch.empty(B, H, W, C, device=fake.device, dtype=torch.uint8)
+    sums = torch.zeros(B, 2, device=fake.device, dtype=torch.float64)
+    M.backend().quantize_metrics(fake.contiguous().float(), gt_01.contiguous().float(), u8, sums)
+    s = (sums / (C * H * W)).cpu().numpy()
+    mae = [float(np.float32(v)) for v in s[:, 0]]
+    mse = [float(np.float32(v)) for v in s[:, 1]]
+    psnr = [float("inf") if m == 0 else -10.0 * math.log10(m + 1e-12) for m in mse]
+    return u8, mae, mse, psnr
+
+
+def validate_kaist(model: M.IRColorizationModel, val_loader: Iterable[Dict], device) -> float:
+    """irc:1521-1542: sample-weighted mean L1 over the validation loader"""
+    model.eval()
+    total, count = 0.0, 0
+    be = M.backend()
+    with torch.no_grad():
+        for batch in val_loader:
+            ir = batch["ir"].to(device); rgb = batch["rgb"].to(device)
+            fake = model(ir)
+            sums = torch.zeros(3, device=fake.device)
+            be.pixel_loss(fake.contiguous(), rgb.contiguous().float(), 0.0, 0.0, 0.0, sums, None)
+            total += sums[0].item() / fake.numel() * ir.size(0)
+            count += ir.size(0)
+    model.train()
+    return total / max(count, 1)
+
+
+def train_kaist(cfg: M.Config, train_loader=None, val_loader=None, use_graph: bool = True):
+    """irc:1549-1723 with the fused D+G iteration.  Returns the list of per-epoch (avg_D, avg_G, val_L1)."""
+    import torch.distributed as dist
+    device = torch.device(cfg.device)
+    H = W = cfg.img_size
+    if train_loader is None:
+        if getattr(cfg, "synthetic_steps", 0) <= 0:
+            raise RuntimeError("No training data: pass train_loader/val_loader yielding {'ir','rgb'} batches, or set "
+                               "cfg.synthetic_steps > 0 (the KAIST file reader, irc:1045-1177, is outside the accelerated path)")
+        train_loader = SyntheticPairs(cfg.synthetic_steps, cfg.batch_size, H, W, seed=7)
+        val_loader = SyntheticPairs(max(1, cfg.synthetic_steps // 10), cfg.batch_size, H, W, seed=8)
+    os.makedirs(cfg.save_dir, exist_ok=True)
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    model = M.IRColorizationModel(cfg)
+    if cfg.init_G_weights is not None and os.path.isfile(cfg.init_G_weights):
+        print(f"Loading initial generator weights from {cfg.init_G_weights}")
+        model.load_weights(cfg.init_G_weights)
+    netD = M.init_net(M.NLayerDiscriminator(cfg.input_nc + cfg.output_nc, 64, 3, M.get_norm_layer(cfg.norm)), "normal", 0.02, device)
+    vgg = M.VGGPerceptual(device)
+    lam = dict(L1=cfg.lambda_L1, perc=cfg.lambda_perc, tv=cfg.lambda_tv, ssim=cfg.lambda_ssim, gan=cfg.lambda_gan)
+    ts = TrainStep(M.backend(), cfg.batch_size, H, W, device, cfg.lr_G, cfg.lr_D, cfg.beta1, cfg.beta2, lam, world_size=world,
+                   use_graph=use_graph, arenas=(model.netG.arena, netD.arena, vgg.arena))
+    ts.refresh_weights()
+    lr_lambda = M.get_lr_lambda(cfg)
+    best_val, best_path = float("inf"), os.path.join(cfg.save_dir, "netG_best.pth")
+    history = []
+    for epoch in range(1, cfg.epochs + 1):
+        scale = lr_lambda(epoch - 1)
+        sum_g = sum_d = 0.0
+        steps = 0
+        acc = torch.zeros(2, device=device)
+        for i, batch in enumerate(train_loader, start=1):
+            ir = batch["ir"].to(device, non_blocking=True); rgb = batch["rgb"].to(device, non_blocking=True)
+            ts.step(ir, rgb, lr_scale=scale)
+            steps += 1
+            if i % 50 == 0 or i == 1:
+                l = ts.losses()          # the only host synchronisation of the loop
+                print(f"Epoch [{epoch}/{cfg.epochs}] Step [{i}/{len(train_loader)}] D: {l['D']:.4f} | G: {l['G']:.4f} "
+                      f"(GAN {l['GAN']:.4f} + L1 {l['L1']:.4f} + Perc {l['perc']:.4f} + TV {l['TV']:.6f} + SSIM {l['SSIM']:.4f})")
+                sum_g += l["G"]; sum_d += l["D"]
+        logged = max(1, (steps // 50) + 1)
+        val_l1 = validate_kaist(model, val_loader, device) if val_loader is not None else float("nan")
+        print(f"Epoch [{epoch}/{cfg.epochs}] DONE | avg D: {sum_d / logged:.4f} | avg G: {sum_g / logged:.4f} | val L1: {val_l1:.4f}")
+        history.append((sum_d / logged, sum_g / logged, val_l1))
+        rank0 = (not dist.is_initialized()) or dist.get_rank() == 0
+        if rank0 and ((epoch % cfg.save_every == 0) or (epoch == cfg.epochs)):
+            path = os.path.join(cfg.save_dir, f"netG_epoch_{epoch:03d}.pth")
+            torch.save(model.netG.state_dict(), path)
+            print(f"Saved generator checkpoint to {path}")
+        if rank0 and val_l1 < best_val:
+            best_val = val_l1
+            torch.save(model.netG.state_dict(), best_path)
+            print(f"New best model saved to {best_path} (val L1={best_val:.4f})")
+        print(f"Current LR (G): {cfg.lr_G * lr_lambda(epoch):.6e}")
+    print(f"Training finished. Best val L1: {best_val:.4f}, best model: {best_path}")
+    return history
+
+
+def run_test(cfg: M.Config, loader=None):
+    """Test-mode core of irc:1333-1514: batched generator inference, on-device truncating quantisation and
+    MAE/MSE/PSNR per image, `metrics_test.csv` in the reference's format.  Image files, collages and the top-K
+    copies (irc:945-1038, :1220-1330) are outside the accelerated path."""
+    device = torch.device(cfg.device)
+    H = W = cfg.img_size
+    if loader is None:
+        if getattr(cfg, "synthetic_steps", 0) <= 0:
+            raise RuntimeError("No test data: pass a loader yielding {'ir', optional 'rgb', optional 'name'} batches or set "
+                               "cfg.synthetic_steps > 0")
+        loader = SyntheticPairs(cfg.synthetic_steps, cfg.batch_size, H, W, seed=9)
+    os.makedirs(cfg.output_dir, exist_ok=True)
+    model = M.IRColorizationModel(cfg)
+    if cfg.test_G_weights and os.path.isfile(cfg.test_G_weights):
+        model.load_weights(cfg.test_G_weights)
+        print(f"Loaded generator weights from {cfg.test_G_weights}")
+    else:
+        print(f"Warning: generator weights not found at {cfg.test_G_weights}. Using randomly initialized model.")
+    model.eval()
+    rows: List[Dict] = []
+    preds = []
+    with torch.no_grad():
+        for bi, batch in enumerate(loader):
+            ir = batch["ir"].to(device)
+            fake = model(ir)
+            names = batch.get("name") or [f"img_{bi:05d}_{j}.png" for j in range(ir.shape[0])]
+            if "rgb" in batch and batch["rgb"] is not None:
+                gt01 = (batch["rgb"].to(device).float() + 1.0) * 0.5 if batch.get("rgb_range", "pm1") == "pm1" else batch["rgb"].to(device).float()
+                u8, mae, mse, psnr = batch_metrics(fake, gt01)
+                for n_, a, b, c in zip(names, mae, mse, psnr):
+                    rows.append({"file": n_, "mae": a, "mse": b, "psnr": c, "ssim": None})
+            else:
+                u8 = torch.empty(ir.shape[0], H, W, 3, device=device, dtype=torch.uint8)
+                M.backend().quantize_metrics(fake.contiguous().float(), None, u8, None)
+            preds.append(u8.cpu())
+    print("Test finished.")
+    summary = None
+    if rows:
+        count = len(rows)
+        mean_mae = sum(r["mae"] for r in rows) / count
+        mean_mse = sum(r["mse"] for r in rows) / count
+        mean_psnr = sum(r["psnr"] for r in rows if np.isfinite(r["psnr"])) / count
+        print("\n=== Test Metrics (on images with GT) ===")
+        print(f"Count      : {count}")
+        print(f"Mean MAE   : {mean_mae:.6f}")
+        print(f"Mean MSE   : {mean_mse:.6f}")
+        print(f"Mean PSNR  : {mean_psnr:.4f} dB")
+        print("Mean SSIM  : None (scikit-image not installed)")
+        path = os.path.join(cfg.output_dir, "metrics_test.csv")
+        with open(path, "w", encoding="utf-8") as f:
+            f.write("file,mae,mse,psnr,ssim\n")
+            for m in rows:
+                f.write(f"{m['file']},{m['mae']:.8f},{m['mse']:.8f},{m['psnr']:.6f},\n")
+            f.write("\n# Summary\n")
+            f.write(f"# count,{count}\n# mean_mae,{mean_mae:.8f}\n# mean_mse,{mean_mse:.8f}\n# mean_psnr,{mean_psnr:.6f}\n# mean_ssim,\n")
+        print(f"\nMetrics saved to: {path}")
+        summary = dict(count=count, mean_mae=mean_mae, mean_mse=mean_mse, mean_psnr=mean_psnr)
+    else:
+        print("No metrics were computed (no matching GT RGB images found).")
+    return summary, rows, preds
+
+
+def main(cfg: Optional[M.Config] = None):
+    """irc:1730-1748"""
+    cfg = cfg or M.Config()
+    print(f"Running in mode: {cfg.mode}")
+    print(f"Device: {cfg.device}")
+    if cfg.mode == "train":
+        return train_kaist(cfg)
+    if cfg.mode == "test":
+        return run_test(cfg)
+    raise ValueError(f"Unknown mode: {cfg.mode}")

@@ -274,8 +274,8 @@ class RefBackend:
         y = torch.arange(H, device=dev).view(1, -1, 1); x = torch.arange(W, device=dev).view(1, 1, -1)
         q = (n * hp + y + oy) * wp + x + ox
         acc = torch.zeros(n_img, H, W, nco, device=dev)
-        for j, s in enumerate(shifts):
-            acc += P[(q + int(s)).reshape(-1), j * nco:(j + 1) * nco].view(n_img, H, W, nco)
+        for j, (dy, dx) in enumerate(shifts):
+            acc += P[(q + int(dy) * wp + int(dx)).reshape(-1), j * nco:(j + 1) * nco].view(n_img, H, W, nco)
         if bias is not None:
             acc = acc + bias.view(1, 1, 1, -1)
         if act == 3:
@@ -296,18 +296,19 @@ class RefBackend:
         img[q] = gp.permute(0, 2, 3, 1).reshape(-1, nco)
         E.zero_()
         allq = torch.arange(rows, device=dev)
-        for j, s in enumerate(shifts):
-            idx = allq - int(s)
+        for j, (dy, dx) in enumerate(shifts):
+            idx = allq - (int(dy) * wp + int(dx))
             ok = ((idx >= 0) & (idx < rows)).float().unsqueeze(1)
             E[:, j * nco:(j + 1) * nco] = (img[idx.clamp(0, rows - 1)] * ok).to(E.dtype)
 
     # ------------------------------------------------------------------ losses
     def pixel_loss(self, fake, target, w_l1, w_tvv, w_tvh, sums, dfake):
         self.launches += 1
-        f = fake.detach().clone().requires_grad_(True)
-        l1 = (f - target).abs().sum() if target is not None else f.sum() * 0
-        tvv = (f[:, :, 1:] - f[:, :, :-1]).abs().sum(); tvh = (f[:, :, :, 1:] - f[:, :, :, :-1]).abs().sum()
-        (g,) = torch.autograd.grad(w_l1 * l1 + w_tvv * tvv + w_tvh * tvh, f)
+        with torch.enable_grad():       # may be called from inside an autograd.Function.forward
+            f = fake.detach().clone().requires_grad_(True)
+            l1 = (f - target).abs().sum() if target is not None else f.sum() * 0
+            tvv = (f[:, :, 1:] - f[:, :, :-1]).abs().sum(); tvh = (f[:, :, :, 1:] - f[:, :, :, :-1]).abs().sum()
+            (g,) = torch.autograd.grad(w_l1 * l1 + w_tvv * tvv + w_tvh * tvh, f)
         sums[0] += l1.detach(); sums[1] += tvv.detach(); sums[2] += tvh.detach()
         if dfake is not None:
             dfake.copy_(g)
@@ -329,9 +330,10 @@ class RefBackend:
 
     def ssim_bwd(self, img1, img2, scale, shift, window, ga, gb, gc, coef, dimg1, accumulate):
         self.launches += 1
-        a = img1.detach().clone().requires_grad_(True)
-        m = self._ssim_map(a * scale + shift, img2 * scale + shift, window)
-        (g,) = torch.autograd.grad(m.sum() * coef, a)
+        with torch.enable_grad():
+            a = img1.detach().clone().requires_grad_(True)
+            m = self._ssim_map(a * scale + shift, img2 * scale + shift, window)
+            (g,) = torch.autograd.grad(m.sum() * coef, a)
         if accumulate:
             dimg1 += g
         else:
@@ -390,6 +392,18 @@ class RefBackend:
         for s in range(splits):
             acc += src[s * split_stride + m.clamp_min(0)]
         dst.copy_(torch.where(m >= 0, acc, torch.zeros_like(acc)))
+
+    def stencil_nchw(self, x, out, tables, accumulate=False):
+        self.launches += 1
+        acc = torch.zeros_like(out)
+        for i in range(tables.ky):
+            for j in range(tables.kx):
+                w = tables.ty_w[:, i].view(1, 1, -1, 1) * tables.tx_w[:, j].view(1, 1, 1, -1)
+                acc += w * x[:, :, tables.ty_idx[:, i].long()][:, :, :, tables.tx_idx[:, j].long()]
+        if accumulate:
+            out += acc
+        else:
+            out.copy_(acc)
 
     def zero_(self, t):
         self.launches += 1

@@ -1,0 +1,69 @@
+"""Data-parallel path on CPU: world_size 2 over gloo.  Each rank runs the product's TrainStep (torch restatement of
+the primitives, float32 storage) on its shard; the all-reduced gradients, averaged, must equal the gradients of the
+single-process step on the concatenated batch (all losses are plain means and InstanceNorm is per sample)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import irc_oracle as O
+    import irc_b200  # noqa: F401
+    from irc_b200 import layout as L
+    from irc_b200.train_step import TrainStep
+    from ref_backend import RefBackend
+    L.ACT_DTYPE = torch.float32
+    H = W = 32
+    pG = O.seeded_params(O.generator_shapes(), 1, bias_std=0.02)
+    pD = O.seeded_params(O.discriminator_shapes(), 2, bias_std=0.02)
+    pV = O.seeded_params(O.vgg_shapes(), 3, kaiming=True, bias_std=0.05)
+    ir, rgb = O.synthetic_pair(world, H, W)
+    ts = TrainStep(RefBackend(), 1, H, W, "cpu", world_size=world)
+    ts.load(pG, pD, pV)
+    ts.step(ir[rank:rank + 1].contiguous(), rgb[rank:rank + 1].contiguous())
+    # every rank must hold identical parameters after the step
+    flat = ts.G.arena.flat.clone()
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    same = all(torch.equal(gathered[0], g) for g in gathered)
+    if rank == 0:
+        ref = TrainStep(RefBackend(), world, H, W, "cpu")
+        ref.load(pG, pD, pV)
+        # the D step of the DP run used all-reduced D gradients: same update => same D for the G step
+        ref.step(ir, rgb)
+        rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+        eG = rel(ts.G.arena.grad / world, ref.G.arena.grad)
+        eD = rel(ts.D2.arena.grad / world, ref.D2.arena.grad)
+        eP = (ts.G.arena.flat - ref.G.arena.flat).abs().max().item()
+        torch.save(dict(same=same, eG=eG, eD=eD, eP=eP, hyper=ts.optG.dev.tolist()), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_step_equals_single_process_on_concatenated_batch(tmp_path):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["same"], "ranks diverged"
+    assert r["eD"] < 1e-4 and r["eG"] < 1e-4, r
+    assert r["eP"] < 4.1e-4, r          # Adam's first step is +-lr wherever the gradient sign is numerically fragile
+    assert abs(r["hyper"][6] - 0.5) < 1e-7   # the 1/world average is folded into the Adam kernel

@@ -177,7 +177,7 @@ def test_taps(bes):
     g = gen(7)
     n, H, W, p = 2, 10, 12, 3
     hp, wp = H + 2 * p, W + 2 * p
-    shifts = [s - 3 for s in range(7)]
+    shifts = [(0, s - 3) for s in range(7)]
     P = torch.randn(n * hp * wp, 32, device="cuda", generator=g)
     bias = torch.randn(3, device="cuda", generator=g)
     a, b = both(bes, lambda be, o: be.tap_reduce(P, shifts, 3, n, H, W, hp, wp, p, p, bias, 3, o), [torch.zeros(n, 3, H, W, device="cuda")])
@@ -186,6 +186,16 @@ def test_taps(bes):
     fn = lambda be, E, db: be.tap_expand(gr, y, shifts, 3, n, H, W, hp, wp, p, p, E, dbias=db)
     a, b = both(bes, fn, [torch.full((n * hp * wp, 64), 3.0, device="cuda", dtype=torch.bfloat16), torch.zeros(3, device="cuda")])
     assert torch.equal(a[0], b[0]); close(a[1], b[1], 1e-5, "dbias")
+    # 4x4 taps on a small top-left anchored frame (D model.11 at the test size: horizontal shifts reach wp/2)
+    n, H, W, hp, wp = 3, 2, 2, 5, 5
+    sh = [(r, s) for r in range(4) for s in range(4)]
+    gr = torch.randn(n, 1, H, W, device="cuda", generator=g)
+    fn = lambda be, E: be.tap_expand(gr, None, sh, 1, n, H, W, hp, wp, 0, 0, E)
+    a, b = both(bes, fn, [torch.full((n * hp * wp, 64), 3.0, device="cuda", dtype=torch.bfloat16)])
+    assert torch.equal(a[0], b[0])
+    P = torch.randn(n * hp * wp, 32, device="cuda", generator=g)
+    a, b = both(bes, lambda be, o: be.tap_reduce(P, sh, 1, n, H, W, hp, wp, 0, 0, None, 0, o), [torch.zeros(n, 1, H, W, device="cuda")])
+    close(a[0], b[0], 1e-5, "tap_reduce 4x4")
 
 
 def test_losses_vs_reference_golden(bes):
