@@ -52,6 +52,7 @@ typedef struct irc_conv_gemm_args {
     int mask_chan_off;
     float mask_slope;
     int bn;                 /* tile width, 0 = auto */
+    int mt;                 /* 128-row sub-tiles per tile sharing each weight stage: 1, 2, 0 = auto */
 } irc_conv_gemm_args;
 int irc_conv_gemm(const irc_conv_gemm_args* args, void* stream);
 
@@ -108,6 +109,9 @@ typedef struct irc_gather_args {
     const int* ty_idx; const float* ty_w; int ky;
     const int* tx_idx; const float* tx_w; int kx;
     int H, W, pad, halo_mode, dst_s2d;
+    /* optional shared-memory tiling for real stencils: output tile tile_y x tile_x whose source bounding box is at
+     * most patch_y x patch_x (the caller knows its tables); 0 = one thread per output element */
+    int tile_y, tile_x, patch_y, patch_x;
 } irc_gather_args;
 int irc_gather(const irc_gather_args* args, void* stream);
 

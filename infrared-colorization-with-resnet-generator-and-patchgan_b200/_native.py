@@ -38,7 +38,7 @@ class ConvGemmArgs(C.Structure):
         ("bias", C.c_void_p), ("act", C.c_int), ("slope", C.c_float),
         ("row_img", C.c_void_p),
         ("mask", C.c_void_p), ("mask_ld", C.c_longlong), ("mask_chan_off", C.c_int), ("mask_slope", C.c_float),
-        ("bn", C.c_int),
+        ("bn", C.c_int), ("mt", C.c_int),
     ]
 
 
@@ -68,6 +68,7 @@ class GatherArgs(C.Structure):
         ("ty_idx", C.c_void_p), ("ty_w", C.c_void_p), ("ky", C.c_int),
         ("tx_idx", C.c_void_p), ("tx_w", C.c_void_p), ("kx", C.c_int),
         ("H", C.c_int), ("W", C.c_int), ("pad", C.c_int), ("halo_mode", C.c_int), ("dst_s2d", C.c_int),
+        ("tile_y", C.c_int), ("tile_x", C.c_int), ("patch_y", C.c_int), ("patch_x", C.c_int),
     ]
 
 
@@ -179,6 +180,49 @@ class Tables:
         self.ty_idx, self.ty_w, self.tx_idx, self.tx_w = ty_idx, ty_w, tx_idx, tx_w
         self.ky = 1 if ty_idx is None else ty_idx.shape[1]
         self.kx = 1 if tx_idx is None else tx_idx.shape[1]
+        self._host = None
+        self._tiling = {}
+
+    def _axis_extent(self, idx, w, n_out, pad, halo_mode, T):
+        """largest source index span needed by any T-wide tile of the padded output axis"""
+        import numpy as np
+        P = np.arange(n_out + 2 * pad) - pad
+        if halo_mode == 1:
+            v = np.abs(P); v = np.where(v > n_out - 1, 2 * (n_out - 1) - v, v); ok = np.ones_like(v, bool)
+        else:
+            v = P.copy(); ok = (v >= 0) & (v < n_out); v = np.clip(v, 0, n_out - 1)
+        if idx is None:
+            lo = hi = v
+        else:
+            big = np.where(w != 0, idx, 1 << 30).min(1); small = np.where(w != 0, idx, -1).max(1)
+            lo, hi = big[v], small[v]
+        ext = 1
+        for s in range(0, len(P), T):
+            m = ok[s:s + T]
+            if m.any():
+                ext = max(ext, int(hi[s:s + T][m].max() - lo[s:s + T][m].min() + 1))
+        return ext
+
+    def tiling(self, H, W, pad, halo_mode):
+        """(tile_y, tile_x, patch_y, patch_x) for the shared-memory tiled gather, or zeros for trivial tables"""
+        if self.ky * self.kx <= 1:
+            return (0, 0, 0, 0)
+        key = (H, W, pad, halo_mode)
+        if key not in self._tiling:
+            if self._host is None:
+                f = lambda t: None if t is None else t.cpu().numpy()
+                self._host = tuple(f(t) for t in (self.ty_idx, self.ty_w, self.tx_idx, self.tx_w))
+            iy, wy, ix, wx = self._host
+            best = None
+            for ty, tx in ((16, 16), (8, 32), (8, 16), (4, 32)):
+                py = self._axis_extent(iy, wy, H, pad, halo_mode, ty); px = self._axis_extent(ix, wx, W, pad, halo_mode, tx)
+                smem = py * px * 128
+                if smem <= 96 * 1024:
+                    cost = (py * px) / float(ty * tx)
+                    if best is None or cost < best[0]:
+                        best = (cost, (ty, tx, py, px))
+            self._tiling[key] = best[1] if best else (0, 0, 0, 0)
+        return self._tiling[key]
 
 
 IDENTITY = Tables()
@@ -200,6 +244,7 @@ class CudaBackend:
         # list, every GEMM launch is bracketed by CUDA events on the launching stream
         self.timers = None
         self.note = ("", "", 0.0)
+        self.conv_mt = 0          # 0 = let the library choose the M sub-tiling of conv_gemm
 
     def _timed(self, kind, fn):
         if self.timers is None:
@@ -228,7 +273,7 @@ class CudaBackend:
         if mask is not None:
             assert mask.t.shape[0] == a.shape[0]
             g.mask = mask.t.data_ptr(); g.mask_ld = mask.t.shape[1]; g.mask_chan_off = mask.chan_off; g.mask_slope = mask_slope
-        g.bn = 0
+        g.bn = 0; g.mt = self.conv_mt
         self._timed("conv_gemm", lambda: check(self.L.irc_conv_gemm(C.byref(g), _stream()))); self.launches += 1
 
     def tn_gemm(self, a, a_chan_off, m, b, b_chan_off, n, k_rows, a_shift, b_shift, out, tap_stride, m_stride, n_stride,
@@ -264,6 +309,7 @@ class CudaBackend:
         g.tx_idx = None if tables.tx_idx is None else tables.tx_idx.data_ptr()
         g.tx_w = None if tables.tx_w is None else tables.tx_w.data_ptr(); g.kx = tables.kx
         g.H = H; g.W = W; g.pad = pad; g.halo_mode = halo_mode; g.dst_s2d = dst_s2d
+        g.tile_y, g.tile_x, g.patch_y, g.patch_x = tables.tiling(H, W, pad, halo_mode) if C_ % 32 == 0 else (0, 0, 0, 0)
         check(self.L.irc_gather(C.byref(g), _stream())); self.launches += 1
 
     def _bwd_args(self, z, g1, g2, dz, C_, n_img, H, W, stats, cnt, eps, act, slope, tables, bsum):

@@ -78,13 +78,14 @@ __global__ void row_index_kernel(short* out, int n_img, int hp, int wp, int y0, 
 // per-(image, channel) sum and sum of squares over the H x W pixels of a view
 // block = (C/8) channel vectors x L pixel lanes; grid = (chunks, N)
 // ---------------------------------------------------------------------------------
-__global__ void in_stats_kernel(View z, int C, int H, int W, float* part) {
+__global__ void __launch_bounds__(256, 4) in_stats_kernel(View z, int C, int H, int W, float* part) {
     extern __shared__ float sh[];
     const int C8 = C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
     const int n = blockIdx.y;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ss[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int y = blockIdx.x; y < H; y += gridDim.x) {
+#pragma unroll 4
         for (int x = lane; x < W; x += L) {
             float v[8];
             load8(z.at(n, y, x, cv * 8), v);
@@ -127,7 +128,8 @@ struct GatherP {
     int H, W, pad, halo_mode, dst_s2d;
 };
 
-__global__ void gather_kernel(const GatherP p) {
+template <bool kIdent>
+__global__ void __launch_bounds__(256, 4) gather_kernel(const GatherP p) {
     // one block per (image, padded row); thread = (channel vector, pixel lane): nothing is divided in the loops
     const int C8 = p.C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
@@ -146,13 +148,14 @@ __global__ void gather_kernel(const GatherP p) {
             float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             if (!halo || p.halo_mode == 1) {
                 if (x < 0 || x >= p.W) x = reflect_idx(x, p.W);
-                for (int i = 0; i < p.ky; ++i) {
-                    const int iy = p.ty_idx ? __ldg(p.ty_idx + y * p.ky + i) : y;
-                    const float wy = p.ty_w ? __ldg(p.ty_w + y * p.ky + i) : 1.f;
+                const int ky = kIdent ? 1 : p.ky, kx = kIdent ? 1 : p.kx;
+                for (int i = 0; i < ky; ++i) {
+                    const int iy = (!kIdent && p.ty_idx) ? __ldg(p.ty_idx + y * p.ky + i) : y;
+                    const float wy = (!kIdent && p.ty_w) ? __ldg(p.ty_w + y * p.ky + i) : 1.f;
                     if (wy == 0.f) continue;
-                    for (int j = 0; j < p.kx; ++j) {
-                        const int ix = p.tx_idx ? __ldg(p.tx_idx + x * p.kx + j) : x;
-                        const float w = wy * (p.tx_w ? __ldg(p.tx_w + x * p.kx + j) : 1.f);
+                    for (int j = 0; j < kx; ++j) {
+                        const int ix = (!kIdent && p.tx_idx) ? __ldg(p.tx_idx + x * p.kx + j) : x;
+                        const float w = wy * ((!kIdent && p.tx_w) ? __ldg(p.tx_w + x * p.kx + j) : 1.f);
                         if (w == 0.f) continue;
                         float v[8];
                         load8(p.src.at(n, iy, ix, c), v);
@@ -194,6 +197,113 @@ __global__ void gather_kernel(const GatherP p) {
 }
 
 // ---------------------------------------------------------------------------------
+// Shared-memory tiled gather for real stencils (ky*kx > 1): one block = TY x TX output pixels x 32 channels.
+// The source patch the tile needs is loaded once (coalesced 16-byte loads), normalised / activated / summed with
+// src2 once per source pixel, kept in shared memory as fp32, and every output pixel then takes its taps from
+// shared memory.  Global traffic = patch + tile instead of taps x tile.
+// ---------------------------------------------------------------------------------
+constexpr int kTileCC = 32;   // channels per block
+
+__global__ void __launch_bounds__(256) gather_tiled_kernel(const GatherP p, int TY, int TX, int maxNy, int maxNx) {
+    extern __shared__ float patch[];                 // [ny*nx][kTileCC]
+    __shared__ int ys[64], xs[64];                   // interior coordinate of every tile row / column (-1 = zero ring, -2 = outside)
+    __shared__ int box[4];                           // lo_y, hi_y, lo_x, hi_x
+    const int CV = kTileCC / 8;
+    const int Hp = p.H + 2 * p.pad, Wp = p.W + 2 * p.pad;
+    const int cchunks = p.C / kTileCC;
+    const int n = blockIdx.z / cchunks, c0 = (blockIdx.z % cchunks) * kTileCC;
+    const int Y0 = blockIdx.y * TY, X0 = blockIdx.x * TX;
+    const int t = threadIdx.x;
+    if (t < 4) box[t] = (t & 1) ? -1 : 0x7fffffff;
+    __syncthreads();
+    if (t < TY + TX) {
+        const bool isy = t < TY;
+        const int P = isy ? Y0 + t : X0 + (t - TY);
+        const int lim = isy ? Hp : Wp, ext = isy ? p.H : p.W;
+        int v = -2;
+        if (P < lim) {
+            v = P - p.pad;
+            if (v < 0 || v >= ext) v = p.halo_mode == 1 ? reflect_idx(v, ext) : -1;
+        }
+        (isy ? ys : xs)[isy ? t : t - TY] = v;
+        if (v >= 0) {
+            const int* idx = isy ? p.ty_idx : p.tx_idx; const float* w = isy ? p.ty_w : p.tx_w; const int k = isy ? p.ky : p.kx;
+            int lo = 0x7fffffff, hi = -1;
+            if (!idx) { lo = hi = v; }
+            else for (int i = 0; i < k; ++i) if (__ldg(w + v * k + i) != 0.f) { const int q = __ldg(idx + v * k + i); lo = min(lo, q); hi = max(hi, q); }
+            if (hi >= 0) { atomicMin(&box[isy ? 0 : 2], lo); atomicMax(&box[isy ? 1 : 3], hi); }
+        }
+    }
+    __syncthreads();
+    const int lo_y = box[0], lo_x = box[2];
+    const int ny = box[1] - lo_y + 1, nx = box[3] - lo_x + 1;
+    const int cv = t % CV, c = c0 + cv * 8;
+    if (box[1] >= 0 && box[3] >= 0) {
+        if (ny > maxNy || nx > maxNx) { if (t == 0) printf("irc: gather tile patch %dx%d exceeds %dx%d\n", ny, nx, maxNy, maxNx); __trap(); }
+        float mu[8], rs[8];
+        if (p.stats) moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+        for (int item = t / CV; item < ny * nx; item += blockDim.x / CV) {
+            const int py = item / nx, px = item - py * nx;
+            float v[8];
+            load8(p.src.at(n, lo_y + py, lo_x + px, c), v);
+            if (p.stats) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = actf((v[k] - mu[k]) * rs[k], p.act, p.slope);
+            } else if (p.act) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = actf(v[k], p.act, p.slope);
+            }
+            if (p.has2) {
+                float u[8];
+                load8(p.src2.at(n, lo_y + py, lo_x + px, c), u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] += u[k];
+            }
+            float4* d = reinterpret_cast<float4*>(patch + (size_t)item * kTileCC + cv * 8);
+            d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    }
+    __syncthreads();
+    for (int item = t / CV; item < TY * TX; item += blockDim.x / CV) {
+        const int r = item / TX, q = item - r * TX;
+        const int y = ys[r], x = xs[q];
+        if (y == -2 || x == -2) continue;
+        const int Y = Y0 + r, X = X0 + q;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (y >= 0 && x >= 0) {
+            for (int i = 0; i < p.ky; ++i) {
+                const int iy = p.ty_idx ? __ldg(p.ty_idx + y * p.ky + i) : y;
+                const float wy = p.ty_w ? __ldg(p.ty_w + y * p.ky + i) : 1.f;
+                if (wy == 0.f) continue;
+                for (int j = 0; j < p.kx; ++j) {
+                    const int ix = p.tx_idx ? __ldg(p.tx_idx + x * p.kx + j) : x;
+                    const float w = wy * (p.tx_w ? __ldg(p.tx_w + x * p.kx + j) : 1.f);
+                    if (w == 0.f) continue;
+                    const float4* s4 = reinterpret_cast<const float4*>(patch + (size_t)((iy - lo_y) * nx + (ix - lo_x)) * kTileCC + cv * 8);
+                    const float4 a = s4[0], b = s4[1];
+                    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+                    acc[4] += w * b.x; acc[5] += w * b.y; acc[6] += w * b.z; acc[7] += w * b.w;
+                }
+            }
+            if (p.has_res) {
+                float u[8];
+                load8(p.res.at(n, y, x, c), u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += u[k];
+            }
+        }
+        bf16* d;
+        if (p.dst_s2d) {
+            const long long rr = ((long long)n * (Hp >> 1) + (Y >> 1)) * (Wp >> 1) + (X >> 1);
+            d = const_cast<bf16*>(p.dst.p) + rr * p.dst.ld + p.dst.off + ((Y & 1) * 2 + (X & 1)) * p.C + c;
+        } else {
+            d = const_cast<bf16*>(p.dst.p) + ((long long)(n * p.dst.hp + Y - p.pad + p.dst.oy) * p.dst.wp + (X - p.pad + p.dst.ox)) * p.dst.ld + p.dst.off + c;
+        }
+        store8(d, acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // InstanceNorm(+activation) backward.
 //   g      = sum_ij wy wx (gsrc + gsrc2)[ty_i, tx_j]      (gradient w.r.t. the activated output)
 //   gd     = g * act'(xhat),  xhat = (z - mu) * rstd
@@ -211,7 +321,18 @@ struct InBwdP {
     float* part;
 };
 
+template <bool kIdent>
 __device__ __forceinline__ void bwd_gather(const InBwdP& p, int n, int y, int x, int c, float (&g)[8]) {
+    if (kIdent) {
+        load8(p.g1.at(n, y, x, c), g);
+        if (p.has2) {
+            float u[8];
+            load8(p.g2.at(n, y, x, c), u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] += u[k];
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) g[k] = 0.f;
     for (int i = 0; i < p.ky; ++i) {
@@ -236,7 +357,8 @@ __device__ __forceinline__ void bwd_gather(const InBwdP& p, int n, int y, int x,
     }
 }
 
-__global__ void in_bwd_reduce_kernel(const InBwdP p) {
+template <bool kIdent>
+__global__ void __launch_bounds__(256, 4) in_bwd_reduce_kernel(const InBwdP p) {
     extern __shared__ float sh[];
     const int C8 = p.C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
@@ -248,7 +370,7 @@ __global__ void in_bwd_reduce_kernel(const InBwdP p) {
         for (int y = blockIdx.x; y < p.H; y += gridDim.x) {
             for (int x = lane; x < p.W; x += L) {
                 float g[8], zv[8];
-                bwd_gather(p, n, y, x, c, g);
+                bwd_gather<kIdent>(p, n, y, x, c, g);
                 load8(p.z.at(n, y, x, c), zv);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -271,7 +393,8 @@ __global__ void in_bwd_reduce_kernel(const InBwdP p) {
     }
 }
 
-__global__ void in_bwd_apply_kernel(const InBwdP p) {
+template <bool kIdent>
+__global__ void __launch_bounds__(256, 4) in_bwd_apply_kernel(const InBwdP p) {
     const int C8 = p.C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
     const int c = cv * 8;
@@ -289,7 +412,7 @@ __global__ void in_bwd_apply_kernel(const InBwdP p) {
         }
         for (int x = lane; x < p.W; x += L) {
             float g[8], zv[8], o[8];
-            bwd_gather(p, n, y, x, c, g);
+            bwd_gather<kIdent>(p, n, y, x, c, g);
             load8(p.z.at(n, y, x, c), zv);
             if (p.stats) {
 #pragma unroll
@@ -453,10 +576,23 @@ extern "C" int irc_gather(const irc_gather_args* a, void* stream) {
     p.tx_idx = a->tx_idx; p.tx_w = a->tx_w; p.kx = a->kx > 0 ? a->kx : 1;
     p.H = a->H; p.W = a->W; p.pad = a->pad; p.halo_mode = a->halo_mode; p.dst_s2d = a->dst_s2d;
     if (p.dst_s2d && (((p.H + 2 * p.pad) | (p.W + 2 * p.pad)) & 1)) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather: space-to-depth needs even padded extents");
+    if (a->tile_y > 0 && a->tile_x > 0 && (p.ty_idx || p.tx_idx) && p.C % kTileCC == 0) {
+        if (a->tile_y + a->tile_x > 64 || a->tile_y > 64 || a->tile_x > 64) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather: tile too large");
+        const size_t smem = (size_t)a->patch_y * a->patch_x * kTileCC * sizeof(float);
+        if (smem > 200 * 1024) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather: tile patch does not fit shared memory");
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(gather_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+        const int Hp = p.H + 2 * p.pad, Wp = p.W + 2 * p.pad;
+        dim3 grid((Wp + a->tile_x - 1) / a->tile_x, (Hp + a->tile_y - 1) / a->tile_y, p.n_img * (p.C / kTileCC));
+        gather_tiled_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, a->tile_y, a->tile_x, a->patch_y, a->patch_x);
+        return irc_check_launch("irc_gather(tiled)");
+    }
     int threads, L;
     row_block(p.C, p.W + 2 * p.pad, threads, L);
     const long long rows = (long long)p.n_img * (p.H + 2 * p.pad);
-    gather_kernel<<<(unsigned)(rows < 65535 * 16 ? rows : 65535 * 16), threads, 0, (cudaStream_t)stream>>>(p);
+    const unsigned grid = (unsigned)(rows < 65535 * 16 ? rows : 65535 * 16);
+    if (!p.ty_idx && !p.tx_idx) gather_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
+    else gather_kernel<false><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
     return irc_check_launch("irc_gather");
 }
 
@@ -481,7 +617,8 @@ extern "C" int irc_in_bwd_reduce(const irc_in_bwd_args* a, void* stream) {
     reduce_shape(p.C, p.H, p.W, p.n_img, a->work ? a->work_floats : 0, threads, L, chunks, smem);
     const long long n = (long long)p.n_img * p.C * 2;
     p.part = chunks == 1 ? p.bsum : a->work;
-    in_bwd_reduce_kernel<<<dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream>>>(p);
+    if (!p.ty_idx && !p.tx_idx) in_bwd_reduce_kernel<true><<<dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream>>>(p);
+    else in_bwd_reduce_kernel<false><<<dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream>>>(p);
     if (chunks > 1) sum_chunks_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a->work, chunks, n, p.bsum);
     return irc_check_launch("irc_in_bwd_reduce");
 }
@@ -494,7 +631,9 @@ extern "C" int irc_in_bwd_apply(const irc_in_bwd_args* a, void* stream) {
     int threads, L;
     row_block(p.C, p.W, threads, L);
     const long long rows = (long long)p.n_img * p.H;
-    in_bwd_apply_kernel<<<(unsigned)(rows < 65535 * 16 ? rows : 65535 * 16), threads, 0, (cudaStream_t)stream>>>(p);
+    const unsigned grid = (unsigned)(rows < 65535 * 16 ? rows : 65535 * 16);
+    if (!p.ty_idx && !p.tx_idx) in_bwd_apply_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
+    else in_bwd_apply_kernel<false><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
     return irc_check_launch("irc_in_bwd_apply");
 }
 

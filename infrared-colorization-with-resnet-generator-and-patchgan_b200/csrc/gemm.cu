@@ -66,6 +66,8 @@ int make_map(CUtensorMap* m, const void* base, long long rows, int ld, int box_r
 struct ConvParams {
     long long rows;
     int n_tiles, bn, k_chunks, a_chan_off, ntaps, stages;
+    int mt;          // M sub-tiles of 128 rows per tile (1 or 2): two sub-tiles share every B stage
+    int nbuf;        // TMEM accumulator buffers (2 = epilogue overlaps the next tile's MMAs)
     int taps[IRC_MAX_TAPS];
     void* out;
     long long out_ld;
@@ -92,7 +94,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int stage_a = kBM * 128;
+    const int tile_rows = kBM * p.mt;
+    const int stage_a = tile_rows * 128;
     const int stage_b = p.bn * 128;
     const int stage_bytes = stage_a + stage_b;
     const int S = p.stages;
@@ -104,7 +107,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long m_tiles = (p.rows + kBM - 1) / kBM;
+    const long long m_tiles = (p.rows + tile_rows - 1) / tile_rows;
+    const uint32_t acc_cols = (uint32_t)(p.mt * p.bn);      // TMEM columns of one accumulator buffer
     const long long total_tiles = m_tiles * p.n_tiles;
     const int num_kb = p.ntaps * p.k_chunks;
 
@@ -126,7 +130,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const long long row0 = (tile / p.n_tiles) * kBM;
+                const long long row0 = (tile / p.n_tiles) * tile_rows;
                 const int n0 = (int)(tile % p.n_tiles) * p.bn;
                 for (int t = 0; t < p.ntaps; ++t) {
                     const long long arow = row0 + p.taps[t];
@@ -150,21 +154,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t adesc = umma_desc_sw128(sa, 16);
                     const uint64_t bdesc = umma_desc_sw128(sa + stage_a, 16);
+                    for (int m = 0; m < p.mt; ++m) {
+                        const uint64_t adesc = umma_desc_sw128(sa + m * (kBM * 128), 16);
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k)
-                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                        for (int k = 0; k < kBK / 16; ++k)
+                            umma_bf16(d_tmem + (uint32_t)(m * p.bn), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    }
                     umma_commit(&empty[stage]);
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull[acc]);
-                acc ^= 1; if (acc == 0) acc_phase ^= 1;
+                if (++acc == p.nbuf) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -173,60 +179,62 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int r_in_tile = quarter * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const long long row = (tile / p.n_tiles) * kBM + r_in_tile;
             const int n0 = (int)(tile % p.n_tiles) * p.bn;
-            const bool in_range = row < p.rows;
-            int img = 0;
-            if (p.row_img) img = in_range ? (int)p.row_img[row] : -1;
-            const bool live = in_range && img >= 0;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256u;
-            for (int c0 = 0; c0 < p.bn; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c0, r);
-                tmem_ld_wait();
-                float v[32];
+            for (int m = 0; m < p.mt; ++m) {
+                const long long row = (tile / p.n_tiles) * tile_rows + m * kBM + r_in_tile;
+                const bool in_range = row < p.rows;
+                int img = 0;
+                if (p.row_img) img = in_range ? (int)p.row_img[row] : -1;
+                const bool live = in_range && img >= 0;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(m * p.bn);
+                for (int c0 = 0; c0 < p.bn; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+                    float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (p.bias) {
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (p.bias) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + c0 + j);
-                }
-                if (p.mask && live) {
-                    const uint4* mp = reinterpret_cast<const uint4*>(p.mask + row * p.mask_ld + p.mask_chan_off + n0 + c0);
+                        for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + c0 + j);
+                    }
+                    if (p.mask && live) {
+                        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + row * p.mask_ld + p.mask_chan_off + n0 + c0);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const uint4 mv = __ldg(mp + g);
-                        const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+                        for (int g = 0; g < 4; ++g) {
+                            const uint4 mv = __ldg(mp + g);
+                            const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const float2 f = unpack_bf16x2(w[h]);
-                            if (!(f.x > 0.f)) v[g * 8 + h * 2] *= p.mask_slope;
-                            if (!(f.y > 0.f)) v[g * 8 + h * 2 + 1] *= p.mask_slope;
+                            for (int h = 0; h < 4; ++h) {
+                                const float2 f = unpack_bf16x2(w[h]);
+                                if (!(f.x > 0.f)) v[g * 8 + h * 2] *= p.mask_slope;
+                                if (!(f.y > 0.f)) v[g * 8 + h * 2 + 1] *= p.mask_slope;
+                            }
                         }
                     }
-                }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = live ? apply_act(v[j], p.act, p.slope) : 0.f;
-                if (in_range) {
-                    if (p.out_fp32) {
-                        float4* op = reinterpret_cast<float4*>((float*)p.out + row * p.out_ld + p.out_chan_off + n0 + c0);
+                    for (int j = 0; j < 32; ++j) v[j] = live ? apply_act(v[j], p.act, p.slope) : 0.f;
+                    if (in_range) {
+                        if (p.out_fp32) {
+                            float4* op = reinterpret_cast<float4*>((float*)p.out + row * p.out_ld + p.out_chan_off + n0 + c0);
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) op[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-                    } else {
-                        uint4* op = reinterpret_cast<uint4*>((bf16*)p.out + row * p.out_ld + p.out_chan_off + n0 + c0);
+                            for (int g = 0; g < 8; ++g) op[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                        } else {
+                            uint4* op = reinterpret_cast<uint4*>((bf16*)p.out + row * p.out_ld + p.out_chan_off + n0 + c0);
 #pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            op[g] = make_uint4(pack_bf16x2(v[g * 8], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
-                                               pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+                            for (int g = 0; g < 4; ++g)
+                                op[g] = make_uint4(pack_bf16x2(v[g * 8], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                                                   pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+                        }
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
-            acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            if (++acc == p.nbuf) { acc = 0; acc_phase ^= 1; }
         }
     }
 
@@ -384,13 +392,22 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     if (a->mask && (((uintptr_t)a->mask & 15) || (a->mask_ld % 8) || (a->mask_chan_off % 8)))
         return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: mask rows must be 16-byte aligned");
 
+    // two 128-row sub-tiles per tile share each weight stage (halves the B bytes per MMA) whenever that still
+    // leaves at least one tile per SM
+    const int sms = irc_num_sms();
+    int mt = a->mt;
+    // ... and both accumulator buffers still fit TMEM (an exposed epilogue costs more than the saved bytes: measured)
+    if (mt <= 0) mt = (4 * bn <= 512 && ((a->a_rows + 2 * kBM - 1) / (2 * kBM)) * (a->n_out / bn) >= sms) ? 2 : 1;
+    if (mt != 1 && mt != 2) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: mt must be 0, 1 or 2");
     CUtensorMap tmA, tmB;
-    int rc = make_map(&tmA, a->a, a->a_rows, a->a_ld, kBM);
+    int rc = make_map(&tmA, a->a, a->a_rows, a->a_ld, kBM * mt);
     if (rc) return rc;
     rc = make_map(&tmB, a->w, a->n_out, a->ntaps * a->cin, bn);
     if (rc) return rc;
 
     ConvParams p;
+    p.mt = mt;
+    p.nbuf = (2 * mt * bn <= 512) ? 2 : 1;
     p.rows = a->a_rows;
     p.bn = bn;
     p.n_tiles = a->n_out / bn;
@@ -403,7 +420,7 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     p.row_img = a->row_img;
     p.mask = (const bf16*)a->mask; p.mask_ld = a->mask_ld; p.mask_chan_off = a->mask_chan_off; p.mask_slope = a->mask_slope;
     p.stats = nullptr; p.n_out = a->n_out;
-    const int stage_bytes = kBM * 128 + bn * 128;
+    const int stage_bytes = kBM * mt * 128 + bn * 128;
     int stages = (kMaxSmem - 2048) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: tile does not fit shared memory");
@@ -414,8 +431,7 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
             return irc_check_launch("cudaFuncSetAttribute(conv_gemm)");
         g_attr_conv = true;
     }
-    const long long tiles = ((a->a_rows + kBM - 1) / kBM) * p.n_tiles;
-    const int sms = irc_num_sms();
+    const long long tiles = ((a->a_rows + kBM * mt - 1) / (kBM * mt)) * p.n_tiles;
     const int grid = (int)(tiles < sms ? tiles : sms);
     conv_gemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
     return irc_check_launch("irc_conv_gemm");

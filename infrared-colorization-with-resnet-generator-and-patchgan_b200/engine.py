@@ -57,7 +57,9 @@ def vgg_shapes() -> Dict[str, tuple]:
 
 
 def _splits_for(tiles: int, kb_total: int, sms: int = 148) -> int:
-    s = max(1, round(2 * sms / max(tiles, 1)))
+    """split-K factor of a weight-gradient GEMM: fill exactly one wave of CTAs (measured: a second, partial wave
+    costs more than the longer main loop of a single one — scripts/prof_tn.py)"""
+    s = max(1, sms // max(tiles, 1))
     return int(max(1, min(s, kb_total, 64)))
 
 
@@ -142,9 +144,8 @@ class GeneratorEngine:
         self.t_up2 = mk(L.up_matrix(H2), L.up_matrix(W2))
         self.t_down1_T = mk(L.down_matrix(H).T, L.down_matrix(W).T)
         self.t_down2_T = mk(L.down_matrix(H2).T, L.down_matrix(W2).T)
-        # UpsampleAA^T has 6 taps per axis: applied as two separable passes (rows, then columns)
-        self.t_up1_Ty, self.t_up1_Tx = mk(L.up_matrix(H4).T, None), mk(None, L.up_matrix(W4).T)
-        self.t_up2_Ty, self.t_up2_Tx = mk(L.up_matrix(H2).T, None), mk(None, L.up_matrix(W2).T)
+        self.t_up1_T = mk(L.up_matrix(H4).T, L.up_matrix(W4).T)      # 6 x 6 taps, taken from a shared-memory patch
+        self.t_up2_T = mk(L.up_matrix(H2).T, L.up_matrix(W2).T)
         self.t_fold1 = mk(L.fold_matrix(H4, 1), L.fold_matrix(W4, 1))
         self.t_fold3 = mk(L.fold_matrix(H, 3), L.fold_matrix(W, 3))
         # ---- weights
@@ -182,8 +183,11 @@ class GeneratorEngine:
         self.dZ1 = F(H, W, 1, 128)
         self.Gx0 = F(H, W, 1, 64)
         self.dZ0 = F(H, W, 0, 64)
-        self.gU2 = F(H2, W, 0, 128)       # rows pass of UpsampleAA^T on Gcat2[0:128)
-        self.gU1 = F(H4, W2, 0, 256)      # rows pass of UpsampleAA^T on Gcat1[0:256)
+        # gradients w.r.t. the activated layer outputs, after the transposed stencil / reflection fold
+        self.g4 = F(H, W, 0, 64)
+        self.g3 = F(H2, W2, 0, 128)
+        self.g2 = F(H2, W2, 0, 256)
+        self.g1 = F(H, W, 0, 128)
 
     # ------------------------------------------------------------------ forward
     def refresh_weights(self):
@@ -246,20 +250,19 @@ class GeneratorEngine:
         self.outc.wgrad(self.E_out, y4.t, 0, y4.rows)
         self.outc.dgrad(self.E_out, self.G4.t)
         # up2_conv
-        be.in_bwd(self.Z4.view(), self.G4.pview(), self.dZ4.view(), 64, B, H, W, stats=self.st4, cnt=H * W, eps=EPS, act=ACT_RELU,
-                  tables=self.t_fold3, bsum=self.bsum)
+        be.gather(self.G4.pview(), self.g4.view(), 64, B, H, W, 0, 0, tables=self.t_fold3)
+        be.in_bwd(self.Z4.view(), self.g4.view(), self.dZ4.view(), 64, B, H, W, stats=self.st4, cnt=H * W, eps=EPS, act=ACT_RELU, bsum=self.bsum)
         self.up2.wgrad(self.dZ4.t, self.cat2.t, 0, self.cat2.rows)
         self.up2.dgrad(self.dZ4.t, self.Gcat2.t)
         # up1_conv (through UpsampleAA^T)
-        be.gather(self.Gcat2.view(0), self.gU2.view(), 128, B, H2, W, 0, 0, tables=self.t_up2_Ty)
-        be.in_bwd(self.Z3.view(), self.gU2.view(), self.dZ3.view(), 128, B, H2, W2, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
-                  tables=self.t_up2_Tx, bsum=self.bsum)
+        be.gather(self.Gcat2.view(0), self.g3.view(), 128, B, H2, W2, 0, 0, tables=self.t_up2_T)
+        be.in_bwd(self.Z3.view(), self.g3.view(), self.dZ3.view(), 128, B, H2, W2, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
+                  bsum=self.bsum)
         self.up1.wgrad(self.dZ3.t, self.cat1.t, 0, self.cat1.rows)
         self.up1.dgrad(self.dZ3.t, self.Gcat1.t)
         # gradient w.r.t. the last ResNet block output = UpsampleAA^T of Gcat1[0:256)
         cur = self.dOut[0]
-        be.gather(self.Gcat1.view(0), self.gU1.view(), 256, B, H4, W2, 0, 0, tables=self.t_up1_Ty)
-        be.gather(self.gU1.view(), cur.view(), 256, B, H4, W4, 1, 0, tables=self.t_up1_Tx)
+        be.gather(self.Gcat1.view(0), cur.view(), 256, B, H4, W4, 1, 0, tables=self.t_up1_T)
         n4 = H4 * W4
         for b in reversed(range(self.nb)):
             c1, c2 = self.res[b]
@@ -276,13 +279,15 @@ class GeneratorEngine:
         if after_blocks is not None:
             after_blocks()
         # down2 (through Downsample^T)
-        be.in_bwd(self.Z2.view(), cur.view(), self.dZ2.view(), 256, B, H2, W2, stats=self.st2, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
-                  tables=self.t_down2_T, bsum=self.bsum)
+        be.gather(cur.view(), self.g2.view(), 256, B, H2, W2, 0, 0, tables=self.t_down2_T)
+        be.in_bwd(self.Z2.view(), self.g2.view(), self.dZ2.view(), 256, B, H2, W2, stats=self.st2, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
+                  bsum=self.bsum)
         self.down2.wgrad(self.dZ2.t, self.cat1.t, 256, self.cat1.rows)
         self.down2.dgrad(self.dZ2.t, self.Gx1.t)
         # down1: x1 feeds down2 and the up1 skip connection
-        be.in_bwd(self.Z1.view(), self.Gcat1.view(256), self.dZ1.view(), 128, B, H, W, stats=self.st1, cnt=H * W, eps=EPS, act=ACT_RELU,
-                  tables=self.t_down1_T, g2=self.Gx1.view(), bsum=self.bsum)
+        be.gather(self.Gcat1.view(256), self.g1.view(), 128, B, H, W, 0, 0, tables=self.t_down1_T, src2=self.Gx1.view())
+        be.in_bwd(self.Z1.view(), self.g1.view(), self.dZ1.view(), 128, B, H, W, stats=self.st1, cnt=H * W, eps=EPS, act=ACT_RELU,
+                  bsum=self.bsum)
         self.down1.wgrad(self.dZ1.t, self.cat2.t, 128, self.cat2.rows)
         self.down1.dgrad(self.dZ1.t, self.Gx0.t)
         # inc: x0 feeds down1 and the up2 skip connection

@@ -28,8 +28,10 @@ def _conv_ref(A, taps, W, cin, a_off):
     (2000, 64, 0, 64, [-3, 0, 3], 32, True),
     (150 * 128 + 5, 64, 0, 64, [-1, 0, 1], 192, False),
     (2500, 512, 0, 512, [0, 1, 2, 3], 512, False),
+    (148 * 256 * 2 + 77, 64, 0, 64, [-1, 0, 1], 128, False),
 ])
-def test_conv_gemm(rows, ld, a_off, cin, taps, n_out, fp32):
+@pytest.mark.parametrize("mt", [1, 2])
+def test_conv_gemm(rows, ld, a_off, cin, taps, n_out, fp32, mt):
     import irc_b200
     from irc_b200 import _native as nat
     nat.arch_check()
@@ -44,7 +46,7 @@ def test_conv_gemm(rows, ld, a_off, cin, taps, n_out, fp32):
         a.taps[i] = t
     a.w = W.data_ptr(); a.n_out = n_out
     a.out = out.data_ptr(); a.out_ld = n_out; a.out_chan_off = 0; a.out_fp32 = int(fp32)
-    a.bias = None; a.act = 0; a.slope = 0.0; a.row_img = None; a.mask = None; a.bn = 0
+    a.bias = None; a.act = 0; a.slope = 0.0; a.row_img = None; a.mask = None; a.bn = 0; a.mt = mt
     nat.check(nat.lib().irc_conv_gemm(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     ref = _conv_ref(A, taps, W, cin, a_off)
