@@ -53,6 +53,10 @@ typedef struct irc_conv_gemm_args {
     float mask_slope;
     int bn;                 /* tile width, 0 = auto */
     int mt;                 /* 128-row sub-tiles per tile sharing each weight stage: 1, 2, 0 = auto */
+    int reuse;              /* taps with consecutive shifts share one staged A tile: 0 off, 1 on, -1 auto */
+    int epilogue_direct;    /* 1 = store rows straight from registers (default 0: swizzled smem staging + TMA stores) */
+    void* dbg;              /* optional: 8 int64 per CTA of pipeline wait-cycle counters (profiling aid), else NULL */
+    int dbg_mode;           /* profiling experiments (results invalid): 1 = skip TMA, 2 = skip MMA; 0 in production */
 } irc_conv_gemm_args;
 int irc_conv_gemm(const irc_conv_gemm_args* args, void* stream);
 

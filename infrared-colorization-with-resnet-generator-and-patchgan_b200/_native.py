@@ -38,7 +38,7 @@ class ConvGemmArgs(C.Structure):
         ("bias", C.c_void_p), ("act", C.c_int), ("slope", C.c_float),
         ("row_img", C.c_void_p),
         ("mask", C.c_void_p), ("mask_ld", C.c_longlong), ("mask_chan_off", C.c_int), ("mask_slope", C.c_float),
-        ("bn", C.c_int), ("mt", C.c_int),
+        ("bn", C.c_int), ("mt", C.c_int), ("reuse", C.c_int), ("epilogue_direct", C.c_int), ("dbg", C.c_void_p), ("dbg_mode", C.c_int),
     ]
 
 
@@ -244,7 +244,11 @@ class CudaBackend:
         # list, every GEMM launch is bracketed by CUDA events on the launching stream
         self.timers = None
         self.note = ("", "", 0.0)
-        self.conv_mt = 0          # 0 = let the library choose the M sub-tiling of conv_gemm
+        self.conv_mt = int(os.environ.get("IRC_CONV_MT", "0"))   # 0 = let the library choose the M sub-tiling of conv_gemm
+        self.conv_dbg = None
+        self.conv_epilogue_direct = int(os.environ.get("IRC_EPI_DIRECT", "0"))
+        self.conv_dbg_mode = 0
+        self.conv_reuse = int(os.environ.get("IRC_CONV_REUSE", "0"))
 
     def _timed(self, kind, fn):
         if self.timers is None:
@@ -273,7 +277,7 @@ class CudaBackend:
         if mask is not None:
             assert mask.t.shape[0] == a.shape[0]
             g.mask = mask.t.data_ptr(); g.mask_ld = mask.t.shape[1]; g.mask_chan_off = mask.chan_off; g.mask_slope = mask_slope
-        g.bn = 0; g.mt = self.conv_mt
+        g.bn = 0; g.mt = self.conv_mt; g.reuse = self.conv_reuse; g.epilogue_direct = self.conv_epilogue_direct; g.dbg = None if self.conv_dbg is None else self.conv_dbg.data_ptr(); g.dbg_mode = self.conv_dbg_mode
         self._timed("conv_gemm", lambda: check(self.L.irc_conv_gemm(C.byref(g), _stream()))); self.launches += 1
 
     def tn_gemm(self, a, a_chan_off, m, b, b_chan_off, n, k_rows, a_shift, b_shift, out, tap_stride, m_stride, n_stride,

@@ -19,7 +19,8 @@ using namespace irc;
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;          // tn_gemm / tap-run kernels: producer, MMA, 4 epilogue warps
+constexpr int kConvThreads = 320;      // conv_gemm: producer, MMA, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kBM = 128;          // rows (pixels) per tile = UMMA M
 constexpr int kBK = 64;           // bf16 elements per 128-byte swizzled row
 constexpr int kMaxSmem = 232448;  // 227 KB
@@ -82,7 +83,18 @@ struct ConvParams {
     float mask_slope;
     float* stats;   // [n_img][n_out][2] or null
     int n_out;
+    int nstg;       // staging tiles of the TMA-store epilogue (2, or 1 when shared memory is needed for pipeline stages)
+    int tma_store;  // 1: bf16 rows leave through a swizzled shared-memory staging tile and TMA stores (coalesced)
+    int dbg_mode;   // profiling experiments: 1 = no TMA traffic (MMA issue/execute rate only), 2 = TMA only (no MMAs)
+    long long* dbg; // optional per-CTA cycle counters {mma wait full, mma wait tmem-empty, producer wait empty, epilogue wait tmem-full, total}
 };
+
+__device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, long long& acc, bool on) {
+    if (!on) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     if (act == 1) return fmaxf(v, 0.f);
@@ -90,11 +102,123 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     return v;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+// ---- epilogue math: branch-free per element (one warp per SM sub-partition cannot hide branch / latency chains) ----
+struct EpiCtx {
+    float slope_eff;     // activation as max(v,0) + slope_eff * min(v,0): 1 = identity, 0 = ReLU, s = LeakyReLU(s)
+    const float* sbias;  // bias staged in shared memory, or null
+};
+
+__device__ __forceinline__ void epi_math32(const ConvParams& p, const EpiCtx& e, const uint32_t (&r)[32], float (&v)[32], long long row, int col,
+                                           bool live) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (e.sbias) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const float4 b = *reinterpret_cast<const float4*>(e.sbias + col + g * 4);
+            v[g * 4] += b.x; v[g * 4 + 1] += b.y; v[g * 4 + 2] += b.z; v[g * 4 + 3] += b.w;
+        }
+    }
+    if (p.mask && live) {
+        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + row * p.mask_ld + p.mask_chan_off + col);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint4 mv = __ldg(mp + g);
+            const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 f = unpack_bf16x2(w[q]);
+                v[g * 8 + q * 2] *= f.x > 0.f ? 1.f : p.mask_slope;
+                v[g * 8 + q * 2 + 1] *= f.y > 0.f ? 1.f : p.mask_slope;
+            }
+        }
+    }
+    if (p.act) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f) + e.slope_eff * fminf(v[j], 0.f);
+    }
+    if (!live) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+}
+
+// Direct epilogue (fp32 outputs, or tiles narrower than one 64-channel swizzle row): rows are stored straight from registers.
+// `half` selects which of the two warps of this TMEM lane quarter takes the 32-column chunk.
+__device__ __forceinline__ void epilogue_subtile(const ConvParams& p, const EpiCtx& e, long long row, int n0, uint32_t taddr, int half) {
+    const bool in_range = row < p.rows;
+    int img = 0;
+    if (p.row_img) img = in_range ? (int)p.row_img[row] : -1;
+    const bool live = in_range && img >= 0;
+    const int nchunk = p.bn >> 5;
+    for (int ci = (nchunk > 1 ? half : 0); ci < nchunk; ci += (nchunk > 1 ? 2 : 1)) {
+        if (nchunk == 1 && half) break;
+        const int c0 = ci * 32;
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+        float v[32];
+        epi_math32(p, e, r, v, row, n0 + c0, live);
+        if (in_range) {
+            if (p.out_fp32) {
+                float4* op = reinterpret_cast<float4*>((float*)p.out + row * p.out_ld + p.out_chan_off + n0 + c0);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) op[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+            } else {
+                uint4* op = reinterpret_cast<uint4*>((bf16*)p.out + row * p.out_ld + p.out_chan_off + n0 + c0);
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    op[g] = make_uint4(pack_bf16x2(v[g * 8], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                                       pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+            }
+        }
+    }
+}
+
+// Staged epilogue of one 128-row sub-tile (bf16 output, bn % 64 == 0): the eight epilogue warps convert 64 columns at a
+// time (two warps per 32-row quarter, 32 columns each) into a SWIZZLE_128B [128 rows][64 ch] shared-memory tile with
+// conflict-free 16-byte stores, and one thread hands it to the TMA store engine; two staging tiles alternate.
+__device__ __forceinline__ void epilogue_subtile_staged(const ConvParams& p, const EpiCtx& e, const CUtensorMap* tmOut, long long row0, int r_in_tile,
+                                                        int n0, uint32_t taddr, int half, uint8_t* stg, uint32_t& stg_iter, bool store_thread) {
+    const long long row = row0 + r_in_tile;
+    const bool in_range = row < p.rows;
+    int img = 0;
+    if (p.row_img) img = in_range ? (int)p.row_img[row] : -1;
+    const bool live = in_range && img >= 0;
+    for (int c0 = 0; c0 < p.bn; c0 += 64) {
+        uint8_t* buf = stg + (p.nstg == 2 ? (stg_iter & 1) : 0) * (kBM * 128);
+        const int cc = c0 + half * 32;
+        uint32_t r[32];
+        tmem_ld32(taddr + cc, r);                         // TMEM read overlaps the wait for the staging tile
+        if (store_thread) { if (p.nstg == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>(); }   // buffer drained by its last TMA store
+        named_bar_sync(1, 256);
+        tmem_ld_wait();
+        float v[32];
+        epi_math32(p, e, r, v, row, n0 + cc, live);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int chunk = (half * 4 + g) ^ (r_in_tile & 7);           // 128-byte swizzle: 16-byte chunk index XOR row % 8
+            *reinterpret_cast<uint4*>(buf + r_in_tile * 128 + chunk * 16) =
+                make_uint4(pack_bf16x2(v[g * 8], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                           pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 256);
+        if (store_thread) {
+            tma_store_2d(tmOut, buf, p.out_chan_off + n0 + c0, (int)row0);
+            bulk_commit_group();
+        }
+        ++stg_iter;
+    }
+}
+
+template <int MT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int tile_rows = kBM * p.mt;
+    constexpr int tile_rows = kBM * MT;
+    constexpr int a_box = tile_rows > 256 ? 256 : tile_rows;
     const int stage_a = tile_rows * 128;
     const int stage_b = p.bn * 128;
     const int stage_bytes = stage_a + stage_b;
@@ -105,29 +229,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tfull = bars + 2 * S;
     uint64_t* tempty = bars + 2 * S + 2;
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
+    uint8_t* stg = smem + (size_t)S * stage_bytes + 1024;      // 2 x 16 KB staging tiles of the TMA-store epilogue
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long m_tiles = (p.rows + tile_rows - 1) / tile_rows;
-    const uint32_t acc_cols = (uint32_t)(p.mt * p.bn);      // TMEM columns of one accumulator buffer
+    const uint32_t acc_cols = (uint32_t)(MT * p.bn);      // TMEM columns of one accumulator buffer
     const long long total_tiles = m_tiles * p.n_tiles;
     const int num_kb = p.ntaps * p.k_chunks;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (p.tma_store) tma_prefetch_desc(&tmOut);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         fence_barrier_init();
     }
+    __shared__ __align__(16) float sbias[512];
+    if (p.bias) for (int i = threadIdx.x; i < p.n_out; i += blockDim.x) sbias[i] = p.bias[i];
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const bool dbg = p.dbg != nullptr;
+    long long w0 = 0, w1 = 0, w2 = 0;
+    const long long tstart = clock64();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (p.dbg_mode != 1 && p.dbg_mode != 3 && p.dbg_mode != 4) {
             int stage = 0; uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const long long row0 = (tile / p.n_tiles) * tile_rows;
@@ -135,11 +266,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int t = 0; t < p.ntaps; ++t) {
                     const long long arow = row0 + p.taps[t];
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_expect_tx(&full[stage], stage_bytes);
-                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                        tma_load_2d(sa, &tmA, &full[stage], p.a_chan_off + kc * kBK, (int)arow);
-                        tma_load_2d(sa + stage_a, &tmB, &full[stage], (t * p.k_chunks + kc) * kBK, n0);
+                        timed_wait(&empty[stage], phase ^ 1, w0, dbg);
+                        if (elect_one()) {
+                            mbar_expect_tx(&full[stage], stage_bytes);
+                            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                            for (int r = 0; r < tile_rows; r += a_box)      // TMA boxes are at most 256 rows
+                                tma_load_2d(sa + r * 128, &tmA, &full[stage], p.a_chan_off + kc * kBK, (int)arow + r);
+                            tma_load_2d(sa + stage_a, &tmB, &full[stage], (t * p.k_chunks + kc) * kBK, n0);
+                        }
+                        __syncwarp();
                         if (++stage == S) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -147,97 +282,239 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        {
             const uint32_t idesc = umma_idesc_bf16(kBM, p.bn, 0, 0);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                timed_wait(&tempty[acc], acc_phase ^ 1, w1, dbg);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
+                    if (p.dbg_mode != 1 && p.dbg_mode != 3 && p.dbg_mode != 4) timed_wait(&full[stage], phase, w0, dbg);
+                    if (p.dbg_mode != 4) tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint64_t bdesc = umma_desc_sw128(sa + stage_a, 16);
-                    for (int m = 0; m < p.mt; ++m) {
-                        const uint64_t adesc = umma_desc_sw128(sa + m * (kBM * 128), 16);
+                    if (elect_one()) {
+                        // consecutive MMAs go to different accumulators: a chain of dependent accumulations into one
+                        // TMEM tile costs ~130 cycles per MMA regardless of N (measured, scripts/prof_mma.py), so narrow
+                        // tiles need 2-4 independent chains in flight to reach the tensor-pipe rate
+                        const uint64_t adesc = umma_desc_sw128(sa, 16);
+                        const uint32_t accum = kb != 0;
+                        if (p.dbg_mode != 2) {
 #pragma unroll
-                        for (int k = 0; k < kBK / 16; ++k)
-                            umma_bf16(d_tmem + (uint32_t)(m * p.bn), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                            for (int k = 0; k < kBK / 16; ++k) {
+#pragma unroll
+                                for (int m = 0; m < MT; ++m)
+                                    umma_bf16(d_tmem + (uint32_t)(m * p.bn), adesc + (uint64_t)(m * (kBM * 128 / 16) + k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                              k == 0 ? accum : 1u);
+                            }
+                        }
+                        if (p.dbg_mode != 3 && p.dbg_mode != 4) umma_commit(&empty[stage]);
                     }
-                    umma_commit(&empty[stage]);
+                    __syncwarp();
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[acc]);
+                if (elect_one()) umma_commit(&tfull[acc]);
+                __syncwarp();
                 if (++acc == p.nbuf) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
         // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;             // which of the two warps of the quarter
+        const int r_in_tile = quarter * 32 + lane;
+        EpiCtx e;
+        e.slope_eff = p.act == 1 ? 0.f : (p.act == 2 ? p.slope : 1.f);
+        e.sbias = p.bias ? sbias : nullptr;
+        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t stg_iter = 0;
+        const bool store_thread = warp == 2 && lane == 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n0 = (int)(tile % p.n_tiles) * p.bn;
+            timed_wait(&tfull[acc], acc_phase, w0, dbg);
+            tc_fence_after();
+            const long long tb0 = dbg ? clock64() : 0;
+#pragma unroll 1
+            for (int m = 0; m < MT; ++m) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(m * p.bn);
+                const long long srow0 = (tile / p.n_tiles) * tile_rows + m * kBM;
+                if (p.tma_store) epilogue_subtile_staged(p, e, &tmOut, srow0, r_in_tile, n0, taddr, half, stg, stg_iter, store_thread);
+                else epilogue_subtile(p, e, srow0 + r_in_tile, n0, taddr, half);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (dbg) w2 += clock64() - tb0;
+            if (++acc == p.nbuf) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    if (p.tma_store && warp == 2 && lane == 0) bulk_wait_group<0>();      // all output tiles have left shared memory
+    if (dbg && lane == 0) {
+        long long* d = p.dbg + (long long)blockIdx.x * 8;
+        if (warp == 0) d[2] = w0;
+        if (warp == 1) { d[0] = w0; d[1] = w1; d[4] = clock64() - tstart; }
+        if (warp == 2) { d[3] = w0; d[5] = w1; d[6] = w2; d[7] = clock64() - tstart; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+
+// ------------------------------------------------------------------------------------
+// conv_gemm with A-tile reuse across horizontal taps ("tap runs")
+// ------------------------------------------------------------------------------------
+// Taps whose row shifts are consecutive integers (the kw taps of one kernel row) read the same pixels shifted by one
+// frame row each.  One TMA box of 128 + L - 1 rows is staged per (run, channel chunk) and the L taps issue their MMAs
+// from it through descriptors whose start address is advanced by 128 bytes (one pixel row) per tap; the swizzle phase
+// of the shifted start goes into the descriptor's base-offset field.  A and B travel through separate rings.
+struct RunParams {
+    int nruns;
+    int run_first[IRC_MAX_TAPS];   // smallest row shift of the run
+    int run_len[IRC_MAX_TAPS];
+    int run_tap[IRC_MAX_TAPS][8];  // original tap index (-> weight K offset) of each member, ascending shift
+    int sa_stages, sb_stages, a_stage_bytes, a_box_rows, base_off_mode;
+};
+
+// Measured on B200 (scripts/try_reuse.py): the 128-byte swizzle phase is taken from the absolute shared-memory
+// address, so a descriptor whose start is advanced by whole 128-byte rows needs NO base-offset field (setting
+// base_offset = (addr >> 7) & 7 gives wrong products).
+__device__ __forceinline__ uint64_t umma_desc_sw128_shifted(uint32_t smem_addr, int base_off_mode) {
+    uint64_t d = umma_desc_sw128(smem_addr, 16);
+    if (base_off_mode == 1) d |= (uint64_t)((smem_addr >> 7) & 7) << 49;
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_runs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p,
+                      const RunParams rp) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int SA = rp.sa_stages, SB = rp.sb_stages;
+    const int stage_b = p.bn * 128;
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + (size_t)SA * rp.a_stage_bytes;
+    uint64_t* bars = (uint64_t*)(smB + (size_t)SB * stage_b);
+    uint64_t* fullA = bars;
+    uint64_t* emptyA = fullA + SA;
+    uint64_t* fullB = emptyA + SA;
+    uint64_t* emptyB = fullB + SB;
+    uint64_t* tfull = emptyB + SB;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m_tiles = (p.rows + kBM - 1) / kBM;
+    const long long total_tiles = m_tiles * p.n_tiles;
+    const uint32_t acc_cols = (uint32_t)p.bn;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        fence_barrier_init();
+    }
+    __shared__ __align__(16) float sbias[512];
+    if (p.bias) for (int i = threadIdx.x; i < p.n_out; i += blockDim.x) sbias[i] = p.bias[i];
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        {
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            const uint32_t a_bytes = (uint32_t)rp.a_box_rows * 128u;
+            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const long long row0 = (tile / p.n_tiles) * kBM;
+                const int n0 = (int)(tile % p.n_tiles) * p.bn;
+                for (int r = 0; r < rp.nruns; ++r) {
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&emptyA[sa], pa ^ 1);
+                        if (elect_one()) {
+                            mbar_expect_tx(&fullA[sa], a_bytes);
+                            tma_load_2d(smA + (size_t)sa * rp.a_stage_bytes, &tmA, &fullA[sa], p.a_chan_off + kc * kBK, (int)(row0 + rp.run_first[r]));
+                        }
+                        __syncwarp();
+                        if (++sa == SA) { sa = 0; pa ^= 1; }
+                        for (int j = 0; j < rp.run_len[r]; ++j) {
+                            mbar_wait(&emptyB[sb], pb ^ 1);
+                            if (elect_one()) {
+                                mbar_expect_tx(&fullB[sb], stage_b);
+                                tma_load_2d(smB + (size_t)sb * stage_b, &tmB, &fullB[sb], (rp.run_tap[r][j] * p.k_chunks + kc) * kBK, n0);
+                            }
+                            __syncwarp();
+                            if (++sb == SB) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        {
+            const uint32_t idesc = umma_idesc_bf16(kBM, p.bn, 0, 0);
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
+                uint32_t first = 1;
+                for (int r = 0; r < rp.nruns; ++r) {
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&fullA[sa], pa);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smA + (size_t)sa * rp.a_stage_bytes);
+                        for (int j = 0; j < rp.run_len[r]; ++j) {
+                            mbar_wait(&fullB[sb], pb);
+                            tc_fence_after();
+                            const uint64_t adesc = umma_desc_sw128_shifted(a_addr + (uint32_t)j * 128u, rp.base_off_mode);
+                            const uint64_t bdesc = umma_desc_sw128(smem_u32(smB + (size_t)sb * stage_b), 16);
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < kBK / 16; ++k)
+                                    umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (first && k == 0) ? 0u : 1u);
+                                umma_commit(&emptyB[sb]);
+                            }
+                            __syncwarp();
+                            first = 0;
+                            if (++sb == SB) { sb = 0; pb ^= 1; }
+                        }
+                        if (elect_one()) umma_commit(&emptyA[sa]);
+                        __syncwarp();
+                        if (++sa == SA) { sa = 0; pa ^= 1; }
+                    }
+                }
+                if (elect_one()) umma_commit(&tfull[acc]);
+                __syncwarp();
+                acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
         const int quarter = warp & 3;
         const int r_in_tile = quarter * 32 + lane;
+        EpiCtx e;
+        e.slope_eff = p.act == 1 ? 0.f : (p.act == 2 ? p.slope : 1.f);
+        e.sbias = p.bias ? sbias : nullptr;
         int acc = 0; uint32_t acc_phase = 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int n0 = (int)(tile % p.n_tiles) * p.bn;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            for (int m = 0; m < p.mt; ++m) {
-                const long long row = (tile / p.n_tiles) * tile_rows + m * kBM + r_in_tile;
-                const bool in_range = row < p.rows;
-                int img = 0;
-                if (p.row_img) img = in_range ? (int)p.row_img[row] : -1;
-                const bool live = in_range && img >= 0;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(m * p.bn);
-                for (int c0 = 0; c0 < p.bn; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + c0, r);
-                    tmem_ld_wait();
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (p.bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + c0 + j);
-                    }
-                    if (p.mask && live) {
-                        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + row * p.mask_ld + p.mask_chan_off + n0 + c0);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const uint4 mv = __ldg(mp + g);
-                            const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                const float2 f = unpack_bf16x2(w[h]);
-                                if (!(f.x > 0.f)) v[g * 8 + h * 2] *= p.mask_slope;
-                                if (!(f.y > 0.f)) v[g * 8 + h * 2 + 1] *= p.mask_slope;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = live ? apply_act(v[j], p.act, p.slope) : 0.f;
-                    if (in_range) {
-                        if (p.out_fp32) {
-                            float4* op = reinterpret_cast<float4*>((float*)p.out + row * p.out_ld + p.out_chan_off + n0 + c0);
-#pragma unroll
-                            for (int g = 0; g < 8; ++g) op[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-                        } else {
-                            uint4* op = reinterpret_cast<uint4*>((bf16*)p.out + row * p.out_ld + p.out_chan_off + n0 + c0);
-#pragma unroll
-                            for (int g = 0; g < 4; ++g)
-                                op[g] = make_uint4(pack_bf16x2(v[g * 8], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
-                                                   pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
-                        }
-                    }
-                }
-            }
+            epilogue_subtile(p, e, (tile / p.n_tiles) * kBM + r_in_tile, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols, 0);
+            if (p.bn > 32) epilogue_subtile(p, e, (tile / p.n_tiles) * kBM + r_in_tile, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols, 1);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (++acc == p.nbuf) { acc = 0; acc_phase ^= 1; }
+            acc ^= 1; if (acc == 0) acc_phase ^= 1;
         }
     }
-
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -301,10 +578,10 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (long long kb = kb_begin; kb < kb_begin + my_kb; ++kb) {
-                mbar_wait(&empty[stage], phase ^ 1);
+        int stage = 0; uint32_t phase = 0;
+        for (long long kb = kb_begin; kb < kb_begin + my_kb; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(&full[stage], stage_bytes);
                 uint8_t* sa = smem + (size_t)stage * stage_bytes;
                 const long long r0 = kb * kBK;
@@ -312,27 +589,30 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tma_load_2d(sa + g * (kBK * 128), &tmA, &full[stage], p.a_chan_off + m_tile * kBM + g * 64, (int)(r0 + p.a_shift[tap]));
                 for (int g = 0; g < groups_b; ++g)
                     tma_load_2d(sa + stage_a + g * (kBK * 128), &tmB, &full[stage], p.b_chan_off + n_tile * p.bn + g * 64, (int)(r0 + p.b_shift[tap]));
-                if (++stage == S) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == S) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(kBM, p.bn, 1, 1);
-            int stage = 0; uint32_t phase = 0;
-            for (long long kb = 0; kb < my_kb; ++kb) {
-                mbar_wait(&full[stage], phase);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint64_t adesc = umma_desc_sw128(sa, kBK * 128);
-                const uint64_t bdesc = umma_desc_sw128(sa + stage_a, kBK * 128);
+        const uint32_t idesc = umma_idesc_bf16(kBM, p.bn, 1, 1);
+        int stage = 0; uint32_t phase = 0;
+        for (long long kb = 0; kb < my_kb; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint64_t adesc = umma_desc_sw128(sa, kBK * 128);
+            const uint64_t bdesc = umma_desc_sw128(sa + stage_a, kBK * 128);
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k)   // 16 reduction rows = 2048 bytes per step
                     umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb | k) != 0);
                 umma_commit(&empty[stage]);
-                if (++stage == S) { stage = 0; phase ^= 1; }
             }
-            umma_commit(tfull);
+            __syncwarp();
+            if (++stage == S) { stage = 0; phase ^= 1; }
         }
+        if (elect_one()) umma_commit(tfull);
+        __syncwarp();
     } else {
         const int quarter = warp & 3;
         const int m = m_tile * kBM + quarter * 32 + lane;
@@ -365,7 +645,24 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
-bool g_attr_conv = false, g_attr_tn = false;
+bool g_attr_conv = false, g_attr_tn = false, g_attr_runs = false;
+
+// group the taps into runs of consecutive row shifts (ascending), at most 8 long
+void build_runs(const int* taps, int ntaps, RunParams& rp) {
+    int order[IRC_MAX_TAPS];
+    for (int i = 0; i < ntaps; ++i) order[i] = i;
+    for (int i = 1; i < ntaps; ++i) { int k = order[i], j = i; while (j > 0 && taps[order[j - 1]] > taps[k]) { order[j] = order[j - 1]; --j; } order[j] = k; }
+    rp.nruns = 0;
+    for (int i = 0; i < ntaps;) {
+        int len = 1;
+        while (i + len < ntaps && len < 8 && taps[order[i + len]] == taps[order[i]] + len) ++len;
+        rp.run_first[rp.nruns] = taps[order[i]];
+        rp.run_len[rp.nruns] = len;
+        for (int j = 0; j < len; ++j) rp.run_tap[rp.nruns][j] = order[i + j];
+        ++rp.nruns;
+        i += len;
+    }
+}
 
 }  // namespace
 
@@ -376,7 +673,7 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     if (!a || !a->a || !a->w || !a->out) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: null pointer");
     if (a->cin <= 0 || a->cin % 64) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: cin must be a positive multiple of 64 (got %d)", a->cin);
     if (a->ntaps <= 0 || a->ntaps > IRC_MAX_TAPS) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: ntaps out of range");
-    if (a->n_out <= 0 || a->n_out % 32) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: n_out must be a multiple of 32 (got %d)", a->n_out);
+    if (a->n_out <= 0 || a->n_out % 32 || a->n_out > 512) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: n_out must be a multiple of 32, at most 512 (got %d)", a->n_out);
     int bn = a->bn;
     if (bn <= 0) {
         bn = a->n_out;
@@ -397,10 +694,15 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     const int sms = irc_num_sms();
     int mt = a->mt;
     // ... and both accumulator buffers still fit TMEM (an exposed epilogue costs more than the saved bytes: measured)
-    if (mt <= 0) mt = (4 * bn <= 512 && ((a->a_rows + 2 * kBM - 1) / (2 * kBM)) * (a->n_out / bn) >= sms) ? 2 : 1;
-    if (mt != 1 && mt != 2) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: mt must be 0, 1 or 2");
+    if (mt <= 0) {
+        mt = 1;
+        for (int c = 4; c > 1; c >>= 1)
+            if (2 * c * bn <= 512 && ((a->a_rows + c * kBM - 1) / (c * kBM)) * (a->n_out / bn) >= sms) { mt = c; break; }
+    }
+    if (mt != 1 && mt != 2 && mt != 4) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: mt must be 0, 1, 2 or 4");
+    if (mt * bn > 512) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: mt * bn exceeds the 512 TMEM columns");
     CUtensorMap tmA, tmB;
-    int rc = make_map(&tmA, a->a, a->a_rows, a->a_ld, kBM * mt);
+    int rc = make_map(&tmA, a->a, a->a_rows, a->a_ld, kBM * mt > 256 ? 256 : kBM * mt);
     if (rc) return rc;
     rc = make_map(&tmB, a->w, a->n_out, a->ntaps * a->cin, bn);
     if (rc) return rc;
@@ -419,21 +721,71 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     p.bias = a->bias; p.act = a->act; p.slope = a->slope;
     p.row_img = a->row_img;
     p.mask = (const bf16*)a->mask; p.mask_ld = a->mask_ld; p.mask_chan_off = a->mask_chan_off; p.mask_slope = a->mask_slope;
-    p.stats = nullptr; p.n_out = a->n_out;
+    p.stats = nullptr; p.n_out = a->n_out; p.dbg = (long long*)a->dbg; p.dbg_mode = a->dbg_mode;
+    // coalesced TMA-store epilogue for bf16 outputs whose tile width is a multiple of one 64-channel swizzle row
+    p.tma_store = (!a->out_fp32 && bn % 64 == 0 && a->epilogue_direct == 0) ? 1 : 0;
+    CUtensorMap tmOut = tmB;
+    if (p.tma_store) {
+        rc = make_map(&tmOut, a->out, a->a_rows, (int)a->out_ld, kBM);
+        if (rc) return rc;
+    }
     const int stage_bytes = kBM * mt * 128 + bn * 128;
-    int stages = (kMaxSmem - 2048) / stage_bytes;
+    const int kStatic = 2048;                              // sbias
+    p.nstg = 2;
+    if (p.tma_store && (kMaxSmem - kStatic - 2048 - (2 * kBM * 128 + 1024)) / stage_bytes < 4 &&
+        (kMaxSmem - kStatic - 2048 - (kBM * 128 + 1024)) / stage_bytes >= 4) p.nstg = 1;
+    const int stg_bytes = p.tma_store ? p.nstg * kBM * 128 + 1024 : 0;
+    int stages = (kMaxSmem - kStatic - 2048 - stg_bytes) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: tile does not fit shared memory");
     p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + 2048;
+    const size_t smem = (size_t)stages * stage_bytes + 2048 + stg_bytes;
     if (!g_attr_conv) {
-        if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 2048) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 2048) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 2048) != cudaSuccess)
             return irc_check_launch("cudaFuncSetAttribute(conv_gemm)");
         g_attr_conv = true;
     }
     const long long tiles = ((a->a_rows + kBM * mt - 1) / (kBM * mt)) * p.n_tiles;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    conv_gemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+    // tap-run variant: worthwhile when taps form runs (kw > 1); reuse = 0 off, 1 on, -1/auto
+    RunParams rp;
+    build_runs(a->taps, a->ntaps, rp);
+    int max_len = 1;
+    for (int r = 0; r < rp.nruns; ++r) if (rp.run_len[r] > max_len) max_len = rp.run_len[r];
+    const int reuse = a->reuse < 0 ? (max_len > 1 ? 1 : 0) : a->reuse;
+    if (reuse && max_len > 1) {
+        rp.a_box_rows = kBM + max_len - 1;
+        rp.a_stage_bytes = ((rp.a_box_rows * 128 + 1023) / 1024) * 1024;
+        rp.base_off_mode = a->reuse == 3 ? 1 : 0;      // 3 = the (wrong) base-offset encoding, kept for the experiment script
+        const int stage_b = bn * 128;
+        // split shared memory: enough B stages for ~2 A stages worth of taps, the rest to A
+        int sb = 2 * max_len; if (sb > 8) sb = 8;
+        while (sb > 2 && (size_t)sb * stage_b + 2 * rp.a_stage_bytes > (size_t)kMaxSmem - 4096) --sb;
+        int sa = (int)(((size_t)kMaxSmem - 4096 - (size_t)sb * stage_b) / rp.a_stage_bytes);
+        if (sa > 6) sa = 6;
+        if (sa < 2) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: tap-run tile does not fit shared memory");
+        int extra = (int)(((size_t)kMaxSmem - 4096 - (size_t)sa * rp.a_stage_bytes) / stage_b);
+        if (extra > sb) sb = extra > 8 ? 8 : extra;
+        rp.sa_stages = sa; rp.sb_stages = sb;
+        CUtensorMap tmA2;
+        rc = make_map(&tmA2, a->a, a->a_rows, a->a_ld, rp.a_box_rows);
+        if (rc) return rc;
+        ConvParams q = p; q.mt = 1; q.nbuf = 2;
+        const size_t smem2 = (size_t)sa * rp.a_stage_bytes + (size_t)sb * stage_b + 2048;
+        if (!g_attr_runs) {
+            if (cudaFuncSetAttribute(conv_gemm_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 2048) != cudaSuccess)
+                return irc_check_launch("cudaFuncSetAttribute(conv_gemm_runs)");
+            g_attr_runs = true;
+        }
+        const long long tiles1 = ((a->a_rows + kBM - 1) / kBM) * p.n_tiles;
+        conv_gemm_runs_kernel<<<(int)(tiles1 < sms ? tiles1 : sms), kThreads, smem2, (cudaStream_t)stream>>>(tmA2, tmB, q, rp);
+        return irc_check_launch("irc_conv_gemm(runs)");
+    }
+    if (mt == 1) conv_gemm_kernel<1><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(tmOut, tmA, tmB, p);
+    else if (mt == 2) conv_gemm_kernel<2><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(tmOut, tmA, tmB, p);
+    else conv_gemm_kernel<4><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(tmOut, tmA, tmB, p);
     return irc_check_launch("irc_conv_gemm");
 }
 
