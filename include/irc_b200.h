@@ -62,7 +62,8 @@ int irc_conv_gemm(const irc_conv_gemm_args* args, void* stream);
 
 /* Weight-gradient GEMM: out[s][t][m][n] = sum_{q in split s} a[q + a_shift[t]][a_chan_off + m] *
  * b[q + b_shift[t]][b_chan_off + n].  Replaces the conv weight-gradient of loss.backward()
- * (irc:1650, irc:1680).  Split partial sums are reduced by irc_gather_sum. */
+ * (irc:1650, irc:1680).  Split partial sums are reduced by irc_gather_sum.  The launch uses
+ * ceil(m/128) * ceil(n/bn) * ceil(ntaps/tpc) * splits CTAs; irc_tn_gemm_ctas() returns that count for `splits` = 1. */
 typedef struct irc_tn_gemm_args {
     const void* a; long long a_rows; int a_ld, a_chan_off, m;
     const void* b; long long b_rows; int b_ld, b_chan_off, n;
@@ -74,8 +75,10 @@ typedef struct irc_tn_gemm_args {
     long long out_tap_stride, out_m_stride, out_n_stride, out_split_stride;
     int splits;
     int bn;                 /* tile width (multiple of 64), 0 = auto */
+    int tpc;                /* taps accumulated per CTA into independent TMEM tiles (1,2,3,4,8; tpc*bn <= 512), 0 = auto */
 } irc_tn_gemm_args;
 int irc_tn_gemm(const irc_tn_gemm_args* args, void* stream);
+int irc_tn_gemm_ctas(int m, int n, int ntaps, int same_a_shift);
 
 
 /* ---- memory-bound passes on NHWC bf16 frames ---------------------------------------- */

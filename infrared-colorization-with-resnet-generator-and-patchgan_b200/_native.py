@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libirc_sm100.so")
 MAX_TAPS = 64
 
 EXPORTS = [
-    "irc_version", "irc_arch_check", "irc_last_error", "irc_conv_gemm", "irc_tn_gemm", "irc_row_index",
+    "irc_version", "irc_arch_check", "irc_last_error", "irc_conv_gemm", "irc_tn_gemm", "irc_tn_gemm_ctas", "irc_row_index",
     "irc_in_stats", "irc_gather", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_maxpool2", "irc_maxpool2_bwd",
     "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
     "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics",
@@ -51,7 +51,7 @@ class TnGemmArgs(C.Structure):
         ("out", C.c_void_p),
         ("out_tap_stride", C.c_longlong), ("out_m_stride", C.c_longlong), ("out_n_stride", C.c_longlong),
         ("out_split_stride", C.c_longlong),
-        ("splits", C.c_int), ("bn", C.c_int),
+        ("splits", C.c_int), ("bn", C.c_int), ("tpc", C.c_int),
     ]
 
 
@@ -290,8 +290,11 @@ class CudaBackend:
             g.a_shift[i] = int(a_shift[i]); g.b_shift[i] = int(b_shift[i])
         assert out.dtype == torch.float32
         g.out = out.data_ptr(); g.out_tap_stride = tap_stride; g.out_m_stride = m_stride; g.out_n_stride = n_stride
-        g.out_split_stride = split_stride; g.splits = splits; g.bn = 0
+        g.out_split_stride = split_stride; g.splits = splits; g.bn = 0; g.tpc = 0
         self._timed("tn_gemm", lambda: check(self.L.irc_tn_gemm(C.byref(g), _stream()))); self.launches += 1
+
+    def tn_gemm_ctas(self, m, n, ntaps):
+        return int(self.L.irc_tn_gemm_ctas(m, n, ntaps, 1))
 
     # ---- frames
     def row_index(self, row_img, n_img, hp, wp, y0, y1, x0, x1):

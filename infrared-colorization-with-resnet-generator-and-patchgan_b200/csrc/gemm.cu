@@ -528,6 +528,8 @@ struct TnParams {
     int m, n;                // valid output extents
     int bn;                  // tile N (multiple of 64)
     int m_tiles, n_tiles, ntaps, splits, stages;
+    int groups;              // tap groups: one CTA accumulates TPC taps into TPC independent TMEM tiles
+    int tmem_cols;
     int a_chan_off, b_chan_off;
     int a_shift[IRC_MAX_TAPS];
     int b_shift[IRC_MAX_TAPS];
@@ -535,14 +537,18 @@ struct TnParams {
     long long out_tap_stride, out_m_stride, out_n_stride, out_split_stride;
 };
 
+// TPC taps per CTA: the A tile (output-gradient rows) is staged once per k-block and used by TPC MMAs chains that
+// accumulate into TPC different TMEM tiles, issued round-robin so that consecutive MMAs never depend on each other
+// (a single chain of narrow MMAs is latency-bound at ~130 cycles each, scripts/prof_mma.py).
+template <int TPC>
 __global__ void __launch_bounds__(kThreads, 1)
 tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int stage_a = kBK * 128 * 2;             // 2 groups of 64 channels x 64 rows
     const int groups_b = p.bn / 64;
-    const int stage_b = kBK * 128 * groups_b;
-    const int stage_bytes = stage_a + stage_b;
+    const int tile_b = kBK * 128 * groups_b;       // one tap's B tile
+    const int stage_bytes = stage_a + TPC * tile_b;
     const int S = p.stages;
     uint64_t* bars = (uint64_t*)(smem + (size_t)S * stage_bytes);
     uint64_t* full = bars;
@@ -552,12 +558,14 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // work decomposition: blockIdx.x -> (split, tap, m_tile, n_tile)
+    // work decomposition: blockIdx.x -> (split, tap group, m_tile, n_tile)
     int w = blockIdx.x;
     const int n_tile = w % p.n_tiles; w /= p.n_tiles;
     const int m_tile = w % p.m_tiles; w /= p.m_tiles;
-    const int tap = w % p.ntaps; w /= p.ntaps;
+    const int group = w % p.groups; w /= p.groups;
     const int split = w;
+    const int tap0 = group * TPC;
+    const int ntap = (p.ntaps - tap0) < TPC ? (p.ntaps - tap0) : TPC;      // active taps of this group
     const long long kb_total = (p.k_rows + kBK - 1) / kBK;
     const long long kb_per = (kb_total + p.splits - 1) / p.splits;
     const long long kb_begin = (long long)split * kb_per;
@@ -571,7 +579,7 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(tfull, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -579,16 +587,19 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         int stage = 0; uint32_t phase = 0;
+        const uint32_t bytes = (uint32_t)(stage_a + ntap * tile_b);
         for (long long kb = kb_begin; kb < kb_begin + my_kb; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
             if (elect_one()) {
-                mbar_expect_tx(&full[stage], stage_bytes);
+                mbar_expect_tx(&full[stage], bytes);
                 uint8_t* sa = smem + (size_t)stage * stage_bytes;
                 const long long r0 = kb * kBK;
                 for (int g = 0; g < 2; ++g)
-                    tma_load_2d(sa + g * (kBK * 128), &tmA, &full[stage], p.a_chan_off + m_tile * kBM + g * 64, (int)(r0 + p.a_shift[tap]));
-                for (int g = 0; g < groups_b; ++g)
-                    tma_load_2d(sa + stage_a + g * (kBK * 128), &tmB, &full[stage], p.b_chan_off + n_tile * p.bn + g * 64, (int)(r0 + p.b_shift[tap]));
+                    tma_load_2d(sa + g * (kBK * 128), &tmA, &full[stage], p.a_chan_off + m_tile * kBM + g * 64, (int)(r0 + p.a_shift[tap0]));
+                for (int t = 0; t < ntap; ++t)
+                    for (int g = 0; g < groups_b; ++g)
+                        tma_load_2d(sa + stage_a + t * tile_b + g * (kBK * 128), &tmB, &full[stage], p.b_chan_off + n_tile * p.bn + g * 64,
+                                    (int)(r0 + p.b_shift[tap0 + t]));
             }
             __syncwarp();
             if (++stage == S) { stage = 0; phase ^= 1; }
@@ -601,11 +612,18 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
             const uint64_t adesc = umma_desc_sw128(sa, kBK * 128);
-            const uint64_t bdesc = umma_desc_sw128(sa + stage_a, kBK * 128);
+            const uint32_t accum = kb != 0;
             if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k)   // 16 reduction rows = 2048 bytes per step
-                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb | k) != 0);
+                for (int k = 0; k < kBK / 16; ++k) {   // 16 reduction rows = 2048 bytes per step
+#pragma unroll
+                    for (int t = 0; t < TPC; ++t) {
+                        if (t < ntap) {
+                            const uint64_t bdesc = umma_desc_sw128(sa + stage_a + t * tile_b, kBK * 128);
+                            umma_bf16(tmem_base + (uint32_t)(t * p.bn), adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, k == 0 ? accum : 1u);
+                        }
+                    }
+                }
                 umma_commit(&empty[stage]);
             }
             __syncwarp();
@@ -616,36 +634,57 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         const int quarter = warp & 3;
         const int m = m_tile * kBM + quarter * 32 + lane;
-        float* obase = p.out + (long long)split * p.out_split_stride + (long long)tap * p.out_tap_stride + (long long)m * p.out_m_stride;
         if (my_kb > 0) {
             mbar_wait(tfull, 0);
             tc_fence_after();
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        for (int c0 = 0; c0 < p.bn; c0 += 32) {
-            uint32_t r[32];
-            if (my_kb > 0) {
-                tmem_ld32(taddr + c0, r);
-                tmem_ld_wait();
-            } else {
+        for (int t = 0; t < ntap; ++t) {
+            float* obase = p.out + (long long)split * p.out_split_stride + (long long)(tap0 + t) * p.out_tap_stride + (long long)m * p.out_m_stride;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * p.bn);
+            for (int c0 = 0; c0 < p.bn; c0 += 32) {
+                uint32_t r[32];
+                if (my_kb > 0) {
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+                } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
-            }
-            if (m < p.m) {
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+                if (m < p.m) {
+                    const int nb = n_tile * p.bn + c0;
+                    if (p.out_n_stride == 1 && nb + 32 <= p.n && ((((uintptr_t)(obase + nb)) & 15) == 0)) {
+                        float4* o4 = reinterpret_cast<float4*>(obase + nb);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n_tile * p.bn + c0 + j;
-                    if (n < p.n) obase[(long long)n * p.out_n_stride] = __uint_as_float(r[j]);
+                        for (int g = 0; g < 8; ++g)
+                            o4[g] = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]), __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = nb + j;
+                            if (n < p.n) obase[(long long)n * p.out_n_stride] = __uint_as_float(r[j]);
+                        }
+                    }
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 256);
+    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 bool g_attr_conv = false, g_attr_tn = false, g_attr_runs = false;
+
+// taps per CTA of the weight-gradient GEMM: as many independent accumulation chains as keep >= 4 pipeline stages
+// (16 KB + tpc * bn * 128 B per stage), preferring an exact divisor of the tap count
+int auto_tpc(int bn, int ntaps) {
+    const int cap = 320 / bn;
+    const int cand[3] = {4, 3, 2};
+    if (ntaps <= 1 || cap < 2) return 1;
+    for (int c : cand) if (c <= cap && ntaps % c == 0) return c;
+    for (int c : cand) if (c <= cap) return c;      // ragged last group
+    return 1;
+}
 
 // group the taps into runs of consecutive row shifts (ascending), at most 8 long
 void build_runs(const int* taps, int ntaps, RunParams& rp) {
@@ -810,17 +849,48 @@ extern "C" int irc_tn_gemm(const irc_tn_gemm_args* a, void* stream) {
     for (int i = 0; i < a->ntaps; ++i) { p.a_shift[i] = a->a_shift[i]; p.b_shift[i] = a->b_shift[i]; }
     p.out = a->out; p.out_tap_stride = a->out_tap_stride; p.out_m_stride = a->out_m_stride;
     p.out_n_stride = a->out_n_stride; p.out_split_stride = a->out_split_stride;
-    const int stage_bytes = kBK * 128 * 2 + kBK * 128 * (bn / 64);
+    // taps per CTA: all taps of a group must share the A shift (true for weight gradients: a_shift == 0)
+    int tpc = a->tpc;
+    bool same_a = true;
+    for (int i = 1; i < a->ntaps; ++i) same_a = same_a && a->a_shift[i] == a->a_shift[0];
+    if (tpc <= 0) {
+        tpc = same_a ? auto_tpc(bn, a->ntaps) : 1;
+    }
+    if (!(tpc == 1 || tpc == 2 || tpc == 3 || tpc == 4 || tpc == 8) || tpc * bn > 512 || (tpc > 1 && !same_a))
+        return irc_set_error(IRC_ERR_BAD_ARG, "irc_tn_gemm: unsupported taps-per-CTA %d for tile width %d", tpc, bn);
+    p.groups = (a->ntaps + tpc - 1) / tpc;
+    int cols = 32; while (cols < tpc * bn) cols <<= 1;
+    p.tmem_cols = cols;
+    const int stage_bytes = kBK * 128 * 2 + tpc * kBK * 128 * (bn / 64);
     int stages = (kMaxSmem - 2048) / stage_bytes;
     if (stages > 8) stages = 8;
+    if (stages < 2) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tn_gemm: stage does not fit shared memory");
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + 2048;
     if (!g_attr_tn) {
-        if (cudaFuncSetAttribute(tn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess)
+        if (cudaFuncSetAttribute(tn_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
+            cudaFuncSetAttribute(tn_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
+            cudaFuncSetAttribute(tn_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
+            cudaFuncSetAttribute(tn_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
+            cudaFuncSetAttribute(tn_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess)
             return irc_check_launch("cudaFuncSetAttribute(tn_gemm)");
         g_attr_tn = true;
     }
-    const long long grid = (long long)p.m_tiles * p.n_tiles * p.ntaps * p.splits;
-    tn_gemm_kernel<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+    const unsigned grid = (unsigned)((long long)p.m_tiles * p.n_tiles * p.groups * p.splits);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (tpc) {
+        case 1: tn_gemm_kernel<1><<<grid, kThreads, smem, st>>>(tmA, tmB, p); break;
+        case 2: tn_gemm_kernel<2><<<grid, kThreads, smem, st>>>(tmA, tmB, p); break;
+        case 3: tn_gemm_kernel<3><<<grid, kThreads, smem, st>>>(tmA, tmB, p); break;
+        case 4: tn_gemm_kernel<4><<<grid, kThreads, smem, st>>>(tmA, tmB, p); break;
+        default: tn_gemm_kernel<8><<<grid, kThreads, smem, st>>>(tmA, tmB, p); break;
+    }
     return irc_check_launch("irc_tn_gemm");
+}
+
+// number of CTAs irc_tn_gemm launches per split with the automatic tiling (lets the caller pick `splits` for one wave)
+extern "C" int irc_tn_gemm_ctas(int m, int n, int ntaps, int same_a_shift) {
+    int bn = ((n + 63) / 64) * 64; if (bn > 256) bn = 256;
+    const int tpc = same_a_shift ? auto_tpc(bn, ntaps) : 1;
+    return ((m + kBM - 1) / kBM) * ((n + bn - 1) / bn) * ((ntaps + tpc - 1) / tpc);
 }

@@ -60,7 +60,7 @@ def _splits_for(tiles: int, kb_total: int, sms: int = 148) -> int:
     """split-K factor of a weight-gradient GEMM: fill exactly one wave of CTAs (measured: a second, partial wave
     costs more than the longer main loop of a single one — scripts/prof_tn.py)"""
     s = max(1, sms // max(tiles, 1))
-    return int(max(1, min(s, kb_total, 64)))
+    return int(max(1, min(s, kb_total, sms)))
 
 
 class ConvOp:
@@ -74,8 +74,7 @@ class ConvOp:
         # algorithmic work of one pass in any role: 2 * (true weight count) * (forward output pixels)  
         self.flops = 2.0 * lay.param_numel * pixels
         N, T, K = lay.N, lay.T, lay.K
-        tiles = ((N + 127) // 128) * ((K + 255) // 256) * T
-        self.splits = _splits_for(tiles, (max_rows + 63) // 64)
+        self.splits = _splits_for(be.tn_gemm_ctas(N, K, T), (max_rows + 63) // 64)
         self.partial = torch.zeros(self.splits * N * T * K, device=arena.device)
         self.grad_flat = arena.grad[lay.param_offset:lay.param_offset + lay.param_numel]
 

@@ -126,6 +126,9 @@ class RefBackend:
                 idx = s * split_stride + t * tap_stride + mi * m_stride + ni * n_stride
                 flat[idx.reshape(-1)] = (r if s == 0 else torch.zeros_like(r)).reshape(-1)
 
+    def tn_gemm_ctas(self, m, n, ntaps):
+        return ((m + 127) // 128) * ((n + 255) // 256) * ntaps
+
     # ------------------------------------------------------------------ frames
     def row_index(self, row_img, n_img, hp, wp, y0, y1, x0, x1):
         self.launches += 1

@@ -96,6 +96,9 @@ def test_conv_gemm_epilogue():
     (3333, 64, 192, 64, 192, 0, 0, [-1, 0, 1], 2),
     (2048, 21, 64, 64, 64, 0, 0, [-10, 0, 10], 4),
     (3000, 128, 128, 384, 384, 256, 128, [0, 5], 2),
+    (6000, 128, 64, 128, 64, 0, 0, [-71, -70, -69, -1, 0, 1, 69, 70, 71], 5),       # 3 taps per CTA
+    (6000, 21, 64, 64, 64, 0, 0, [-210, -140, -70, 0, 70, 140, 210], 4),            # 7 taps in one ragged group of 8
+    (4000, 512, 256, 512, 256, 0, 0, [r * 34 + s for r in range(4) for s in range(4)], 2),   # 2 taps per CTA, 4 M tiles
 ])
 def test_tn_gemm(rows, m, n, lda, ldb, a_off, b_off, shifts, splits):
     from irc_b200 import _native as nat
