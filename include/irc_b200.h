@@ -31,7 +31,7 @@ const char* irc_last_error(void);
  * Replaces nn.Conv2d forward (irc:458-531 generator, irc:598-630 discriminator, irc:664 VGG
  * trunk) and, with negated taps and transposed weights, the conv data-gradient that
  * loss.backward() (irc:1650, irc:1680) runs through cuDNN/oneDNN.
- * Epilogue: +bias, * (mask>0 ? 1 : mask_slope), activation, rows with row_img<0 zeroed. */
+ * Epilogue: +bias, * (mask>0 ? 1 : mask_slope), +addend, activation, rows with row_img<0 zeroed. */
 typedef struct irc_conv_gemm_args {
     const void* a;          /* bf16 [a_rows][a_ld] */
     long long a_rows;
@@ -51,6 +51,9 @@ typedef struct irc_conv_gemm_args {
     long long mask_ld;
     int mask_chan_off;
     float mask_slope;
+    const void* addend;     /* bf16 [a_rows][addend_ld] or NULL: added to the accumulator before the activation */
+    long long addend_ld;
+    int addend_chan_off;
     int bn;                 /* tile width, 0 = auto */
     int mt;                 /* 128-row sub-tiles per tile sharing each weight stage: 1, 2, 0 = auto */
     int reuse;              /* taps with consecutive shifts share one staged A tile: 0 off, 1 on, -1 auto */
@@ -136,6 +139,10 @@ typedef struct irc_in_bwd_args {
 } irc_in_bwd_args;
 int irc_in_bwd_reduce(const irc_in_bwd_args* args, void* stream);
 int irc_in_bwd_apply(const irc_in_bwd_args* args, void* stream);
+
+/* Backward of nn.ReflectionPad2d(p) in place on a frame holding the gradient w.r.t. the padded tensor: interior pixels
+ * within p of the border receive the ring pixels that mirror onto them; the ring is cleared. */
+int irc_fold_inplace(void* g, long long ld, int chan_off, int C, int n_img, int H, int W, int p, void* stream);
 
 /* nn.MaxPool2d(2,2) of the VGG trunk (torchvision vgg16.features[4], [9]; irc:664) and its
  * backward fused with the mask of the ReLU that precedes it. */

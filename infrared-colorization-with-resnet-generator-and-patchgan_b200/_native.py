@@ -21,7 +21,7 @@ EXPORTS = [
     "irc_in_stats", "irc_gather", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_maxpool2", "irc_maxpool2_bwd",
     "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
     "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics",
-    "irc_adam", "irc_pack_bf16", "irc_gather_sum", "irc_stencil_nchw",
+    "irc_adam", "irc_pack_bf16", "irc_gather_sum", "irc_stencil_nchw", "irc_fold_inplace",
 ]
 
 
@@ -38,6 +38,7 @@ class ConvGemmArgs(C.Structure):
         ("bias", C.c_void_p), ("act", C.c_int), ("slope", C.c_float),
         ("row_img", C.c_void_p),
         ("mask", C.c_void_p), ("mask_ld", C.c_longlong), ("mask_chan_off", C.c_int), ("mask_slope", C.c_float),
+        ("addend", C.c_void_p), ("addend_ld", C.c_longlong), ("addend_chan_off", C.c_int),
         ("bn", C.c_int), ("mt", C.c_int), ("reuse", C.c_int), ("epilogue_direct", C.c_int), ("dbg", C.c_void_p), ("dbg_mode", C.c_int),
     ]
 
@@ -260,7 +261,7 @@ class CudaBackend:
 
     # ---- tensor-core GEMMs
     def conv_gemm(self, a, a_chan_off, cin, taps: Sequence[int], w, n_out, out, out_chan_off=0, bias=None, act=0, slope=0.0,
-                  row_img=None, mask: Optional[View] = None, mask_slope=0.0):
+                  row_img=None, mask: Optional[View] = None, mask_slope=0.0, addend: Optional[View] = None):
         g = ConvGemmArgs()
         g.a = a.data_ptr(); g.a_rows = a.shape[0]; g.a_ld = a.shape[1]; g.a_chan_off = a_chan_off; g.cin = cin
         g.ntaps = len(taps)
@@ -277,6 +278,9 @@ class CudaBackend:
         if mask is not None:
             assert mask.t.shape[0] == a.shape[0]
             g.mask = mask.t.data_ptr(); g.mask_ld = mask.t.shape[1]; g.mask_chan_off = mask.chan_off; g.mask_slope = mask_slope
+        if addend is not None:
+            assert addend.t.shape[0] == a.shape[0]
+            g.addend = addend.t.data_ptr(); g.addend_ld = addend.t.shape[1]; g.addend_chan_off = addend.chan_off
         g.bn = 0; g.mt = self.conv_mt; g.reuse = self.conv_reuse; g.epilogue_direct = self.conv_epilogue_direct; g.dbg = None if self.conv_dbg is None else self.conv_dbg.data_ptr(); g.dbg_mode = self.conv_dbg_mode
         self._timed("conv_gemm", lambda: check(self.L.irc_conv_gemm(C.byref(g), _stream()))); self.launches += 1
 
@@ -339,6 +343,10 @@ class CudaBackend:
         if stats is not None:
             check(self.L.irc_in_bwd_reduce(C.byref(g), _stream())); self.launches += 2
         check(self.L.irc_in_bwd_apply(C.byref(g), _stream())); self.launches += 1
+
+    def fold_inplace(self, fr_t, chan_off, C_, n_img, H, W, p):
+        """fr_t: the [rows, ld] tensor of a frame with pad p"""
+        check(self.L.irc_fold_inplace(_p(fr_t), C.c_longlong(fr_t.shape[1]), chan_off, C_, n_img, H, W, p, _stream())); self.launches += 1
 
     def maxpool2(self, src: View, dst: View, C_, n_img, Ho, Wo):
         a, b = _cview(src), _cview(dst)

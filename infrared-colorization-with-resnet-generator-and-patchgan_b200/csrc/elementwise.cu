@@ -503,6 +503,44 @@ __global__ void colsum_kernel(const bf16* a, long long rows, long long ld, int o
     }
 }
 
+// In-place transpose of ReflectionPad2d(p) on a frame that holds the gradient w.r.t. the padded tensor: every interior
+// pixel within p of the border adds the ring pixels that mirror onto it (ring pixels are only read, each thread writes
+// its own pixel: race-free) and clears them.  Touches O(p * perimeter) pixels instead of a full pass.
+__global__ void fold_inplace_kernel(bf16* g, long long ld, int off, int C, int n_img, int H, int W, int p) {
+    const int C8 = C >> 3;
+    const int Hp = H + 2 * p, Wp = W + 2 * p;
+    // border pixels: rows y in [1,p] U [H-1-p, H-2] (all x), and for the other rows only x in [1,p] U [W-1-p, W-2]
+    const long long per_img = (long long)H * W;
+    const long long total = (long long)n_img * per_img * C8;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C8) * 8;
+        long long pix = idx / C8;
+        const int x = (int)(pix % W); pix /= W;
+        const int y = (int)(pix % H);
+        const int n = (int)(pix / H);
+        const int my = (y >= 1 && y <= p) ? p - y : ((y >= H - 1 - p && y <= H - 2) ? 2 * (H - 1) - y + p : -1);   // mirrored padded row
+        const int mx = (x >= 1 && x <= p) ? p - x : ((x >= W - 1 - p && x <= W - 2) ? 2 * (W - 1) - x + p : -1);
+        if (my < 0 && mx < 0) continue;
+        bf16* base = g + (long long)n * Hp * Wp * ld + off + c;
+        float acc[8], v[8];
+        bf16* self = base + ((long long)(y + p) * Wp + (x + p)) * ld;
+        load8(self, acc);
+        const float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        // every ring pixel mirrors onto exactly one interior pixel, so the thread that consumes it also clears it
+        // (the folded frame can then serve as a zero-ring addend / operand)
+        if (my >= 0) { bf16* q = base + ((long long)my * Wp + (x + p)) * ld; load8(q, v); store8(q, zero);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
+        if (mx >= 0) { bf16* q = base + ((long long)(y + p) * Wp + mx) * ld; load8(q, v); store8(q, zero);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
+        if (my >= 0 && mx >= 0) { bf16* q = base + ((long long)my * Wp + mx) * ld; load8(q, v); store8(q, zero);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
+        store8(self, acc);
+    }
+}
+
 int grid_for(long long total, int threads) {
     long long b = (total + threads - 1) / threads;
     const long long cap = (long long)irc_num_sms() * 16;
@@ -667,4 +705,12 @@ extern "C" int irc_colsum(const void* a, long long rows, long long ld, int chan_
     colsum_kernel<<<dim3((unsigned)bx, (C + 31) / 32), 1024, 0, (cudaStream_t)stream>>>((const bf16*)a, rows, ld, chan_off, C, row_img, work);
     sum_chunks_kernel<<<grid_for(C, 256), 256, 0, (cudaStream_t)stream>>>(work, (int)bx, C, out);
     return irc_check_launch("irc_colsum");
+}
+
+extern "C" int irc_fold_inplace(void* g, long long ld, int chan_off, int C, int n_img, int H, int W, int p, void* stream) {
+    if (!g || C % 8 || ((uintptr_t)g & 15) || ld % 8 || chan_off % 8) return irc_set_error(IRC_ERR_BAD_ARG, "irc_fold_inplace: bad args");
+    if (p < 1 || 2 * p + 2 > H || 2 * p + 2 > W) return irc_set_error(IRC_ERR_BAD_ARG, "irc_fold_inplace: image too small for the pad width");
+    const long long total = (long long)n_img * H * W * (C / 8);
+    fold_inplace_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((bf16*)g, ld, chan_off, C, n_img, H, W, p);
+    return irc_check_launch("irc_fold_inplace");
 }

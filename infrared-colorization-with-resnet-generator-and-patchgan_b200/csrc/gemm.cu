@@ -81,6 +81,9 @@ struct ConvParams {
     long long mask_ld;
     int mask_chan_off;
     float mask_slope;
+    const bf16* addend;      // optional bf16 [rows][addend_ld]: added to the accumulator (residual-stream gradient)
+    long long addend_ld;
+    int addend_chan_off;
     float* stats;   // [n_img][n_out][2] or null
     int n_out;
     int nstg;       // staging tiles of the TMA-store epilogue (2, or 1 when shared memory is needed for pipeline stages)
@@ -130,6 +133,19 @@ __device__ __forceinline__ void epi_math32(const ConvParams& p, const EpiCtx& e,
                 const float2 f = unpack_bf16x2(w[q]);
                 v[g * 8 + q * 2] *= f.x > 0.f ? 1.f : p.mask_slope;
                 v[g * 8 + q * 2 + 1] *= f.y > 0.f ? 1.f : p.mask_slope;
+            }
+        }
+    }
+    if (p.addend && live) {
+        const uint4* ap = reinterpret_cast<const uint4*>(p.addend + row * p.addend_ld + p.addend_chan_off + col);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint4 av = __ldg(ap + g);
+            const uint32_t w[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 f = unpack_bf16x2(w[q]);
+                v[g * 8 + q * 2] += f.x; v[g * 8 + q * 2 + 1] += f.y;
             }
         }
     }
@@ -760,6 +776,9 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     p.bias = a->bias; p.act = a->act; p.slope = a->slope;
     p.row_img = a->row_img;
     p.mask = (const bf16*)a->mask; p.mask_ld = a->mask_ld; p.mask_chan_off = a->mask_chan_off; p.mask_slope = a->mask_slope;
+    p.addend = (const bf16*)a->addend; p.addend_ld = a->addend_ld; p.addend_chan_off = a->addend_chan_off;
+    if (a->addend && (((uintptr_t)a->addend & 15) || (a->addend_ld % 8) || (a->addend_chan_off % 8)))
+        return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: addend rows must be 16-byte aligned");
     p.stats = nullptr; p.n_out = a->n_out; p.dbg = (long long*)a->dbg; p.dbg_mode = a->dbg_mode;
     // coalesced TMA-store epilogue for bf16 outputs whose tile width is a multiple of one 64-channel swizzle row
     p.tma_store = (!a->out_fp32 && bn % 64 == 0 && a->epilogue_direct == 0) ? 1 : 0;

@@ -183,7 +183,6 @@ class GeneratorEngine:
         self.Gx0 = F(H, W, 1, 64)
         self.dZ0 = F(H, W, 0, 64)
         # gradients w.r.t. the activated layer outputs, after the transposed stencil / reflection fold
-        self.g4 = F(H, W, 0, 64)
         self.g3 = F(H2, W2, 0, 128)
         self.g2 = F(H2, W2, 0, 256)
         self.g1 = F(H, W, 0, 128)
@@ -249,8 +248,8 @@ class GeneratorEngine:
         self.outc.wgrad(self.E_out, y4.t, 0, y4.rows)
         self.outc.dgrad(self.E_out, self.G4.t)
         # up2_conv
-        be.gather(self.G4.pview(), self.g4.view(), 64, B, H, W, 0, 0, tables=self.t_fold3)
-        be.in_bwd(self.Z4.view(), self.g4.view(), self.dZ4.view(), 64, B, H, W, stats=self.st4, cnt=H * W, eps=EPS, act=ACT_RELU, bsum=self.bsum)
+        be.fold_inplace(self.G4.t, 0, 64, B, H, W, 3)             # ReflectionPad2d(3)^T on the border pixels only
+        be.in_bwd(self.Z4.view(), self.G4.view(), self.dZ4.view(), 64, B, H, W, stats=self.st4, cnt=H * W, eps=EPS, act=ACT_RELU, bsum=self.bsum)
         self.up2.wgrad(self.dZ4.t, self.cat2.t, 0, self.cat2.rows)
         self.up2.dgrad(self.dZ4.t, self.Gcat2.t)
         # up1_conv (through UpsampleAA^T)
@@ -268,12 +267,14 @@ class GeneratorEngine:
             be.in_bwd(self.Zb[b].view(), cur.view(), self.dZb.view(), 256, B, H4, W4, stats=self.stb[b], cnt=n4, eps=EPS, act=ACT_NONE, bsum=self.bsum)
             c2.wgrad(self.dZb.t, self.Hh[b].t, 0, self.dZb.rows)
             c2.dgrad(self.dZb.t, self.Gh.t)
-            be.in_bwd(self.Za[b].view(), self.Gh.pview(), self.dZa.view(), 256, B, H4, W4, stats=self.sta[b], cnt=n4, eps=EPS, act=ACT_RELU,
-                      tables=self.t_fold1, bsum=self.bsum)
+            be.fold_inplace(self.Gh.t, 0, 256, B, H4, W4, 1)
+            be.in_bwd(self.Za[b].view(), self.Gh.view(), self.dZa.view(), 256, B, H4, W4, stats=self.sta[b], cnt=n4, eps=EPS, act=ACT_RELU,
+                      bsum=self.bsum)
             c1.wgrad(self.dZa.t, self.X[b].t, 0, self.dZa.rows)
-            c1.dgrad(self.dZa.t, self.Gx.t)
+            # data gradient of conv1 + the residual-stream gradient (its frame ring is zero), then the reflection fold
             nxt = self.dOut[1] if cur is self.dOut[0] else self.dOut[0]
-            be.gather(self.Gx.pview(), nxt.view(), 256, B, H4, W4, 1, 0, tables=self.t_fold1, res=cur.view())
+            c1.dgrad(self.dZa.t, nxt.t, addend=View(cur.t, 0, 0, 0))
+            be.fold_inplace(nxt.t, 0, 256, B, H4, W4, 1)
             cur = nxt
         if after_blocks is not None:
             after_blocks()

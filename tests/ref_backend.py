@@ -91,7 +91,7 @@ class RefBackend:
 
     # ------------------------------------------------------------------ GEMMs
     def conv_gemm(self, a, a_chan_off, cin, taps, w, n_out, out, out_chan_off=0, bias=None, act=0, slope=0.0,
-                  row_img=None, mask=None, mask_slope=0.0):
+                  row_img=None, mask=None, mask_slope=0.0, addend=None):
         self.launches += 1
         rows = a.shape[0]
         A = a[:, a_chan_off:a_chan_off + cin].float()
@@ -106,6 +106,8 @@ class RefBackend:
         if mask is not None:
             m = mask.t[:, mask.chan_off:mask.chan_off + n_out].float()
             acc = acc * torch.where(m > 0, torch.ones_like(m), torch.full_like(m, mask_slope))
+        if addend is not None:
+            acc = acc + addend.t[:, addend.chan_off:addend.chan_off + n_out].float()
         acc = _act(acc, act, slope)
         if row_img is not None:
             acc = acc * (row_img >= 0).float().unsqueeze(1)
@@ -197,6 +199,18 @@ class RefBackend:
         else:
             o = g * _dact(zv, act, slope)
         self._write(dz, n_img, ys, xs, C, o)
+
+    def fold_inplace(self, fr_t, chan_off, C, n_img, H, W, p):
+        self.launches += 1
+        Hp, Wp = H + 2 * p, W + 2 * p
+        g = fr_t.view(n_img, Hp, Wp, -1)[..., chan_off:chan_off + C].float()
+        dev = fr_t.device
+        ry = _reflect(torch.arange(Hp, device=dev) - p, H); rx = _reflect(torch.arange(Wp, device=dev) - p, W)
+        out = torch.zeros(n_img, H, W, C, device=dev)
+        out.index_put_((torch.arange(n_img, device=dev).view(-1, 1, 1).expand(n_img, Hp, Wp), ry.view(1, -1, 1).expand(n_img, Hp, Wp),
+                        rx.view(1, 1, -1).expand(n_img, Hp, Wp)), g, accumulate=True)
+        fr_t.view(n_img, Hp, Wp, -1)[..., chan_off:chan_off + C] = 0
+        fr_t.view(n_img, Hp, Wp, -1)[:, p:p + H, p:p + W, chan_off:chan_off + C] = out.to(fr_t.dtype)
 
     def maxpool2(self, src, dst, C, n_img, Ho, Wo):
         self.launches += 1

@@ -68,7 +68,8 @@ def test_conv_gemm_epilogue():
     mask = torch.randn(rows, n_out, device="cuda", generator=g).bfloat16()
     img = (torch.arange(rows, device="cuda") // 500).short()
     img[::7] = -1
-    for mode in ("bias_lrelu_rows", "mask"):
+    addend = torch.randn(rows, 128, device="cuda", generator=g).bfloat16()
+    for mode in ("bias_lrelu_rows", "mask", "addend"):
         out = torch.full((rows, n_out), float("nan"), device="cuda", dtype=torch.bfloat16)
         a = nat.ConvGemmArgs()
         a.a = A.data_ptr(); a.a_rows = rows; a.a_ld = cin; a.a_chan_off = 0; a.cin = cin; a.ntaps = 3
@@ -79,9 +80,12 @@ def test_conv_gemm_epilogue():
         if mode == "bias_lrelu_rows":
             a.bias = bias.data_ptr(); a.act = 2; a.slope = 0.2; a.row_img = img.data_ptr()
             ref = torch.nn.functional.leaky_relu(ref + bias, 0.2) * (img >= 0)[:, None]
-        else:
+        elif mode == "mask":
             a.mask = mask.data_ptr(); a.mask_ld = n_out; a.mask_chan_off = 0; a.mask_slope = 0.2
             ref = ref * torch.where(mask.float() > 0, 1.0, 0.2)
+        else:
+            a.addend = addend.data_ptr(); a.addend_ld = 128; a.addend_chan_off = 64
+            ref = ref + addend[:, 64:].float()
         nat.check(nat.lib().irc_conv_gemm(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         torch.cuda.synchronize()
         err = (out.float() - ref).norm() / ref.norm()

@@ -125,6 +125,19 @@ def test_in_bwd(bes, mode):
     close(a[0], b[0], 1.5e-2, mode)
 
 
+@pytest.mark.parametrize("p,C,H,W", [(1, 64, 8, 10), (3, 64, 12, 16), (1, 256, 64, 64)])
+def test_fold_inplace(bes, p, C, H, W):
+    g = gen(11)
+    n = 2
+    fr = frame(n, H, W, p, C + 64, g)
+    a, b = both(bes, lambda be, t: be.fold_inplace(t, 64, C, n, H, W, p), [fr.t])
+    close(a[0], b[0], 1e-2, "fold_inplace")
+    ring = a[0].view(n, H + 2 * p, W + 2 * p, -1)[..., 64:].clone()
+    ring[:, p:p + H, p:p + W] = 0
+    assert (ring == 0).all()
+    assert torch.equal(a[0][:, :64], fr.t[:, :64])          # other channels untouched
+
+
 def test_maxpool(bes):
     g = gen(4)
     n, C, H, W = 3, 64, 8, 12
