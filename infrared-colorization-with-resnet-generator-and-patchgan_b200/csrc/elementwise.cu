@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(256, 4) gather_kernel(const GatherP p) {
 // ---------------------------------------------------------------------------------
 constexpr int kTileCC = 32;   // channels per block
 
+template <int K>
 __global__ void __launch_bounds__(256) gather_tiled_kernel(const GatherP p, int TY, int TX, int maxNy, int maxNx) {
     extern __shared__ float patch[];                 // [ny*nx][kTileCC]
     __shared__ int ys[64], xs[64];                   // interior coordinate of every tile row / column (-1 = zero ring, -2 = outside)
@@ -271,15 +272,24 @@ __global__ void __launch_bounds__(256) gather_tiled_kernel(const GatherP p, int 
         const int Y = Y0 + r, X = X0 + q;
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (y >= 0 && x >= 0) {
-            for (int i = 0; i < p.ky; ++i) {
-                const int iy = p.ty_idx ? __ldg(p.ty_idx + y * p.ky + i) : y;
-                const float wy = p.ty_w ? __ldg(p.ty_w + y * p.ky + i) : 1.f;
-                if (wy == 0.f) continue;
-                for (int j = 0; j < p.kx; ++j) {
-                    const int ix = p.tx_idx ? __ldg(p.tx_idx + x * p.kx + j) : x;
-                    const float w = wy * (p.tx_w ? __ldg(p.tx_w + x * p.kx + j) : 1.f);
-                    if (w == 0.f) continue;
-                    const float4* s4 = reinterpret_cast<const float4*>(patch + (size_t)((iy - lo_y) * nx + (ix - lo_x)) * kTileCC + cv * 8);
+            // the K (index, weight) pairs of this output row / column live in registers; zero weights mark padding entries
+            int oy[K], ox[K]; float wy[K], wx[K];
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const bool hy = p.ty_idx && i < p.ky, hx = p.tx_idx && i < p.kx;
+                wy[i] = hy ? __ldg(p.ty_w + y * p.ky + i) : ((!p.ty_idx && i == 0) ? 1.f : 0.f);
+                wx[i] = hx ? __ldg(p.tx_w + x * p.kx + i) : ((!p.tx_idx && i == 0) ? 1.f : 0.f);
+                oy[i] = ((hy ? __ldg(p.ty_idx + y * p.ky + i) : y) - lo_y) * nx;
+                ox[i] = (hx ? __ldg(p.tx_idx + x * p.kx + i) : x) - lo_x;
+            }
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                if (wy[i] == 0.f) continue;
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    if (wx[j] == 0.f) continue;
+                    const float w = wy[i] * wx[j];
+                    const float4* s4 = reinterpret_cast<const float4*>(patch + (size_t)(oy[i] + ox[j]) * kTileCC + cv * 8);
                     const float4 a = s4[0], b = s4[1];
                     acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
                     acc[4] += w * b.x; acc[5] += w * b.y; acc[6] += w * b.z; acc[7] += w * b.w;
@@ -508,36 +518,36 @@ __global__ void colsum_kernel(const bf16* a, long long rows, long long ld, int o
 // its own pixel: race-free) and clears them.  Touches O(p * perimeter) pixels instead of a full pass.
 __global__ void fold_inplace_kernel(bf16* g, long long ld, int off, int C, int n_img, int H, int W, int p) {
     const int C8 = C >> 3;
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int c = cv * 8;
     const int Hp = H + 2 * p, Wp = W + 2 * p;
-    // border pixels: rows y in [1,p] U [H-1-p, H-2] (all x), and for the other rows only x in [1,p] U [W-1-p, W-2]
-    const long long per_img = (long long)H * W;
-    const long long total = (long long)n_img * per_img * C8;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % C8) * 8;
-        long long pix = idx / C8;
-        const int x = (int)(pix % W); pix /= W;
-        const int y = (int)(pix % H);
-        const int n = (int)(pix / H);
+    for (int row = blockIdx.x; row < n_img * H; row += gridDim.x) {
+        const int n = row / H, y = row - n * H;
         const int my = (y >= 1 && y <= p) ? p - y : ((y >= H - 1 - p && y <= H - 2) ? 2 * (H - 1) - y + p : -1);   // mirrored padded row
-        const int mx = (x >= 1 && x <= p) ? p - x : ((x >= W - 1 - p && x <= W - 2) ? 2 * (W - 1) - x + p : -1);
-        if (my < 0 && mx < 0) continue;
+        // rows that receive a mirrored row visit every column; the others only the 2p columns next to the side borders
+        const int count = my >= 0 ? W : 2 * p;
         bf16* base = g + (long long)n * Hp * Wp * ld + off + c;
-        float acc[8], v[8];
-        bf16* self = base + ((long long)(y + p) * Wp + (x + p)) * ld;
-        load8(self, acc);
-        const float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        // every ring pixel mirrors onto exactly one interior pixel, so the thread that consumes it also clears it
-        // (the folded frame can then serve as a zero-ring addend / operand)
-        if (my >= 0) { bf16* q = base + ((long long)my * Wp + (x + p)) * ld; load8(q, v); store8(q, zero);
+        for (int i = lane; i < count; i += L) {
+            const int x = my >= 0 ? i : (i < p ? 1 + i : W - 1 - p + (i - p));
+            const int mx = (x >= 1 && x <= p) ? p - x : ((x >= W - 1 - p && x <= W - 2) ? 2 * (W - 1) - x + p : -1);
+            if (my < 0 && mx < 0) continue;
+            float acc[8], v[8];
+            const float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            bf16* self = base + ((long long)(y + p) * Wp + (x + p)) * ld;
+            load8(self, acc);
+            // every ring pixel mirrors onto exactly one interior pixel, so the thread that consumes it also clears it
+            // (the folded frame can then serve as a zero-ring addend / operand)
+            if (my >= 0) { bf16* q = base + ((long long)my * Wp + (x + p)) * ld; load8(q, v); store8(q, zero);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
-        if (mx >= 0) { bf16* q = base + ((long long)(y + p) * Wp + mx) * ld; load8(q, v); store8(q, zero);
+                for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
+            if (mx >= 0) { bf16* q = base + ((long long)(y + p) * Wp + mx) * ld; load8(q, v); store8(q, zero);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
-        if (my >= 0 && mx >= 0) { bf16* q = base + ((long long)my * Wp + mx) * ld; load8(q, v); store8(q, zero);
+                for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
+            if (my >= 0 && mx >= 0) { bf16* q = base + ((long long)my * Wp + mx) * ld; load8(q, v); store8(q, zero);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
-        store8(self, acc);
+                for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
+            store8(self, acc);
+        }
     }
 }
 
@@ -619,10 +629,22 @@ extern "C" int irc_gather(const irc_gather_args* a, void* stream) {
         const size_t smem = (size_t)a->patch_y * a->patch_x * kTileCC * sizeof(float);
         if (smem > 200 * 1024) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather: tile patch does not fit shared memory");
         static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(gather_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+        if (!attr) {
+            cudaFuncSetAttribute(gather_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(gather_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(gather_tiled_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(gather_tiled_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr = true;
+        }
         const int Hp = p.H + 2 * p.pad, Wp = p.W + 2 * p.pad;
         dim3 grid((Wp + a->tile_x - 1) / a->tile_x, (Hp + a->tile_y - 1) / a->tile_y, p.n_img * (p.C / kTileCC));
-        gather_tiled_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, a->tile_y, a->tile_x, a->patch_y, a->patch_x);
+        const int kmax = p.ky > p.kx ? p.ky : p.kx;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (kmax <= 2) gather_tiled_kernel<2><<<grid, 256, smem, st>>>(p, a->tile_y, a->tile_x, a->patch_y, a->patch_x);
+        else if (kmax <= 3) gather_tiled_kernel<3><<<grid, 256, smem, st>>>(p, a->tile_y, a->tile_x, a->patch_y, a->patch_x);
+        else if (kmax <= 6) gather_tiled_kernel<6><<<grid, 256, smem, st>>>(p, a->tile_y, a->tile_x, a->patch_y, a->patch_x);
+        else if (kmax <= 8) gather_tiled_kernel<8><<<grid, 256, smem, st>>>(p, a->tile_y, a->tile_x, a->patch_y, a->patch_x);
+        else return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather: tables wider than 8 entries");
         return irc_check_launch("irc_gather(tiled)");
     }
     int threads, L;
@@ -710,7 +732,8 @@ extern "C" int irc_colsum(const void* a, long long rows, long long ld, int chan_
 extern "C" int irc_fold_inplace(void* g, long long ld, int chan_off, int C, int n_img, int H, int W, int p, void* stream) {
     if (!g || C % 8 || ((uintptr_t)g & 15) || ld % 8 || chan_off % 8) return irc_set_error(IRC_ERR_BAD_ARG, "irc_fold_inplace: bad args");
     if (p < 1 || 2 * p + 2 > H || 2 * p + 2 > W) return irc_set_error(IRC_ERR_BAD_ARG, "irc_fold_inplace: image too small for the pad width");
-    const long long total = (long long)n_img * H * W * (C / 8);
-    fold_inplace_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((bf16*)g, ld, chan_off, C, n_img, H, W, p);
+    int threads, L;
+    row_block(C, W, threads, L);
+    fold_inplace_kernel<<<n_img * H, threads, 0, (cudaStream_t)stream>>>((bf16*)g, ld, chan_off, C, n_img, H, W, p);
     return irc_check_launch("irc_fold_inplace");
 }
