@@ -101,7 +101,9 @@ int irc_row_index(short* row_img, int n_img, int hp, int wp, int y0, int y1, int
 
 /* InstanceNorm statistics (nn.InstanceNorm2d, irc:161): stats[n][c] = (sum, sum of squares)
  * over the H x W pixels of view z.  Reductions here are two-stage and order-fixed (bit-reproducible):
- * `work` (optional, work_floats floats) holds the per-chunk partials; without it one block per image runs. */
+ * `work` (optional, work_floats floats, ZERO-INITIALISED by the caller once) holds the per-chunk partials and, in its
+ * last 256 floats, self re-arming ticket counters: the last block of an image adds the partials in chunk order.
+ * Without it one block per image runs. */
 int irc_in_stats(const irc_view* z, int C, int n_img, int H, int W, float* stats, float* work, long long work_floats, void* stream);
 
 /* Separable table gather into a frame:
@@ -120,7 +122,8 @@ typedef struct irc_gather_args {
     const int* tx_idx; const float* tx_w; int kx;
     int H, W, pad, halo_mode, dst_s2d;
     /* optional shared-memory tiling for real stencils: output tile tile_y x tile_x whose source bounding box is at
-     * most patch_y x patch_x (the caller knows its tables); 0 = one thread per output element */
+     * most patch_y x patch_x (the caller knows its tables); tile_y = 0: register-table kernel (one thread per output
+     * vector, taps from L1/L2); tile_y = -2: generic fallback */
     int tile_y, tile_x, patch_y, patch_x;
 } irc_gather_args;
 int irc_gather(const irc_gather_args* args, void* stream);

@@ -247,6 +247,7 @@ class CudaBackend:
         self.note = ("", "", 0.0)
         self.conv_mt = int(os.environ.get("IRC_CONV_MT", "0"))   # 0 = let the library choose the M sub-tiling of conv_gemm
         self.conv_dbg = None
+        self.gather_mode = os.environ.get("IRC_GATHER", "auto")     # lean | tiled | generic (stencil gather kernel choice)
         self.conv_epilogue_direct = int(os.environ.get("IRC_EPI_DIRECT", "0"))
         self.conv_dbg_mode = 0
         self.conv_reuse = int(os.environ.get("IRC_CONV_REUSE", "0"))
@@ -307,7 +308,7 @@ class CudaBackend:
     def in_stats(self, z: View, C_, n_img, H, W, stats):
         cv = _cview(z)
         check(self.L.irc_in_stats(C.byref(cv), C_, n_img, H, W, _p(stats), _p(self.work), C.c_longlong(self.work.numel()), _stream()))
-        self.launches += 2
+        self.launches += 1
 
     def gather(self, src: View, dst: View, C_, n_img, H, W, pad, halo_mode, tables: Tables = IDENTITY, src2=None, res=None,
                stats=None, cnt=0.0, eps=1e-5, act=0, slope=0.0, dst_s2d=0):
@@ -320,7 +321,13 @@ class CudaBackend:
         g.tx_idx = None if tables.tx_idx is None else tables.tx_idx.data_ptr()
         g.tx_w = None if tables.tx_w is None else tables.tx_w.data_ptr(); g.kx = tables.kx
         g.H = H; g.W = W; g.pad = pad; g.halo_mode = halo_mode; g.dst_s2d = dst_s2d
-        g.tile_y, g.tile_x, g.patch_y, g.patch_x = tables.tiling(H, W, pad, halo_mode) if C_ % 32 == 0 else (0, 0, 0, 0)
+        mode = self.gather_mode
+        if mode == "auto":
+            # measured (scripts/bench_elem.py): the shared-memory tiled kernel wins for the up-sampling stencils and the
+            # transposed ones with many taps / two sources; the register-table kernel wins for stride-2 down-sampling
+            mode = "tiled" if (tables.ky >= 6 or src2 is not None or H > src.hp) else "lean"
+        g.tile_y, g.tile_x, g.patch_y, g.patch_x = (tables.tiling(H, W, pad, halo_mode) if (C_ % 32 == 0 and mode == "tiled") else
+                                                    ((-2, 0, 0, 0) if mode == "generic" else (0, 0, 0, 0)))
         check(self.L.irc_gather(C.byref(g), _stream())); self.launches += 1
 
     def _bwd_args(self, z, g1, g2, dz, C_, n_img, H, W, stats, cnt, eps, act, slope, tables, bsum):
@@ -341,7 +348,7 @@ class CudaBackend:
         """reduce (when normalised) + apply."""
         g = self._bwd_args(z, g1, g2, dz, C_, n_img, H, W, stats, cnt, eps, act, slope, tables, bsum)
         if stats is not None:
-            check(self.L.irc_in_bwd_reduce(C.byref(g), _stream())); self.launches += 2
+            check(self.L.irc_in_bwd_reduce(C.byref(g), _stream())); self.launches += 1
         check(self.L.irc_in_bwd_apply(C.byref(g), _stream())); self.launches += 1
 
     def fold_inplace(self, fr_t, chan_off, C_, n_img, H, W, p):

@@ -74,11 +74,29 @@ __global__ void row_index_kernel(short* out, int n_img, int hp, int wp, int y0, 
     }
 }
 
+// Second stage of the order-fixed reductions, folded into the first kernel: the last block of image n to finish (ticket
+// counter) adds the per-chunk partials in chunk order (bit-reproducible) and re-arms the counter for the next launch.
+__device__ __forceinline__ void finalize_by_last_block(const float* part, float* out, int n, int C2, unsigned* counters) {
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&counters[n], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < C2; i += blockDim.x) {
+        float a = 0.f;
+        for (unsigned c = 0; c < gridDim.x; ++c) a += __ldcg(part + ((long long)c * gridDim.y + n) * C2 + i);
+        out[(long long)n * C2 + i] = a;
+    }
+    if (threadIdx.x == 0) counters[n] = 0u;
+}
+
 // ---------------------------------------------------------------------------------
 // per-(image, channel) sum and sum of squares over the H x W pixels of a view
 // block = (C/8) channel vectors x L pixel lanes; grid = (chunks, N)
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 4) in_stats_kernel(View z, int C, int H, int W, float* part) {
+__global__ void __launch_bounds__(256, 4) in_stats_kernel(View z, int C, int H, int W, float* part, float* out, unsigned* counters) {
     extern __shared__ float sh[];
     const int C8 = C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
@@ -105,6 +123,7 @@ __global__ void __launch_bounds__(256, 4) in_stats_kernel(View z, int C, int H, 
         for (int l = 0; l < L; ++l) a += shs[l * C8 * 16 + i];
         part[((long long)blockIdx.x * gridDim.y + n) * C * 2 + i] = a;
     }
+    if (counters) finalize_by_last_block(part, out, n, C * 2, counters);
 }
 
 // out[j] = sum over chunks (fixed order) of part[chunk][j]: deterministic second stage of the reductions
@@ -126,6 +145,7 @@ struct GatherP {
     const int* ty_idx; const float* ty_w; int ky;
     const int* tx_idx; const float* tx_w; int kx;
     int H, W, pad, halo_mode, dst_s2d;
+    float slope_eff;     // activation as max(v,0) + slope_eff*min(v,0)
 };
 
 template <bool kIdent>
@@ -197,6 +217,100 @@ __global__ void __launch_bounds__(256, 4) gather_kernel(const GatherP p) {
 }
 
 // ---------------------------------------------------------------------------------
+// Lean table gather: K x K taps with K a compile-time constant (2: reflection fold / Downsample^T, 3: Downsample and
+// UpsampleAA, 6: UpsampleAA^T).  One block per output row: the row's y-entries and source row pointers are computed once,
+// the x-entries of a pixel sit in registers, and the K*K 16-byte loads per output vector hit L1/L2 (every source pixel
+// is shared by neighbouring outputs).  No per-element integer division, no per-tap table reads.
+// ---------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256, 3) gather_lean_kernel(const GatherP p) {
+    const int C8 = p.C >> 3;
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int c = cv * 8;
+    const int Hp = p.H + 2 * p.pad, Wp = p.W + 2 * p.pad;
+    for (int row = blockIdx.x; row < p.n_img * Hp; row += gridDim.x) {
+        const int n = row / Hp, Y = row - n * Hp;
+        int y = Y - p.pad;
+        const bool halo_y = y < 0 || y >= p.H;
+        if (halo_y) y = reflect_idx(y, p.H);
+        bf16* drow = const_cast<bf16*>(p.dst.p) + ((long long)(n * p.dst.hp + Y - p.pad + p.dst.oy) * p.dst.wp + (p.dst.ox - p.pad)) * p.dst.ld + p.dst.off + c;
+        if (halo_y && p.halo_mode == 0) {
+            const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int X = lane; X < Wp; X += L) store8(drow + (long long)X * p.dst.ld, z);
+            continue;
+        }
+        float mu[8], rs[8];
+        if (p.stats) {
+            moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mu[k] = -mu[k] * rs[k];
+        }
+        // y entries and source row base pointers of this output row
+        float wy[K]; const bf16* r1[K]; const bf16* r2[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const bool h = p.ty_idx && i < p.ky;
+            wy[i] = h ? __ldg(p.ty_w + y * p.ky + i) : ((!p.ty_idx && i == 0) ? 1.f : 0.f);
+            const int iy = h ? __ldg(p.ty_idx + y * p.ky + i) : y;
+            r1[i] = p.src.at(n, iy, 0, c);
+            r2[i] = p.has2 ? p.src2.at(n, iy, 0, c) : nullptr;
+        }
+        for (int X = lane; X < Wp; X += L) {
+            int x = X - p.pad;
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const bool halo_x = x < 0 || x >= p.W;
+            if (!halo_x || p.halo_mode == 1) {
+                if (halo_x) x = reflect_idx(x, p.W);
+                float wx[K]; long long ox[K], ox2[K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const bool h = p.tx_idx && j < p.kx;
+                    wx[j] = h ? __ldg(p.tx_w + x * p.kx + j) : ((!p.tx_idx && j == 0) ? 1.f : 0.f);
+                    const int ix = h ? __ldg(p.tx_idx + x * p.kx + j) : x;
+                    ox[j] = (long long)ix * p.src.ld;
+                    ox2[j] = (long long)ix * p.src2.ld;
+                }
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    if (wy[i] == 0.f) continue;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        if (wx[j] == 0.f) continue;
+                        const float w = wy[i] * wx[j];
+                        float v[8];
+                        load8(r1[i] + ox[j], v);
+                        if (p.stats) {          // mu[] holds -mean*rstd here: one FFMA per element, ReLU = one FMNMX
+                            if (p.act == 1) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], rs[k], mu[k]), 0.f);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) { const float t = fmaf(v[k], rs[k], mu[k]); v[k] = fmaxf(t, 0.f) + p.slope_eff * fminf(t, 0.f); }
+                            }
+                        }
+                        if (p.has2) {
+                            float u[8];
+                            load8(r2[i] + ox2[j], u);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) v[k] += u[k];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[k] += w * v[k];
+                    }
+                }
+                if (p.has_res) {
+                    float u[8];
+                    load8(p.res.at(n, y, x, c), u);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] += u[k];
+                }
+            }
+            store8(drow + (long long)X * p.dst.ld, acc);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // Shared-memory tiled gather for real stencils (ky*kx > 1): one block = TY x TX output pixels x 32 channels.
 // The source patch the tile needs is loaded once (coalesced 16-byte loads), normalised / activated / summed with
 // src2 once per source pixel, kept in shared memory as fp32, and every output pixel then takes its taps from
@@ -242,14 +356,18 @@ __global__ void __launch_bounds__(256) gather_tiled_kernel(const GatherP p, int 
     if (box[1] >= 0 && box[3] >= 0) {
         if (ny > maxNy || nx > maxNx) { if (t == 0) printf("irc: gather tile patch %dx%d exceeds %dx%d\n", ny, nx, maxNy, maxNx); __trap(); }
         float mu[8], rs[8];
-        if (p.stats) moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+        if (p.stats) {
+            moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mu[k] = -mu[k] * rs[k];
+        }
         for (int item = t / CV; item < ny * nx; item += blockDim.x / CV) {
             const int py = item / nx, px = item - py * nx;
             float v[8];
             load8(p.src.at(n, lo_y + py, lo_x + px, c), v);
             if (p.stats) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = actf((v[k] - mu[k]) * rs[k], p.act, p.slope);
+                for (int k = 0; k < 8; ++k) { const float tt = fmaf(v[k], rs[k], mu[k]); v[k] = fmaxf(tt, 0.f) + p.slope_eff * fminf(tt, 0.f); }
             } else if (p.act) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) v[k] = actf(v[k], p.act, p.slope);
@@ -329,6 +447,7 @@ struct InBwdP {
     const int* tx_idx; const float* tx_w; int kx;
     float* bsum;
     float* part;
+    unsigned* counters;
 };
 
 template <bool kIdent>
@@ -401,6 +520,7 @@ __global__ void __launch_bounds__(256, 4) in_bwd_reduce_kernel(const InBwdP p) {
         for (int l = 0; l < L; ++l) a += sh[l * C8 * 16 + i];
         p.part[((long long)blockIdx.x * gridDim.y + n) * p.C * 2 + i] = a;
     }
+    if (p.counters) finalize_by_last_block(p.part, p.bsum, n, p.C * 2, p.counters);
 }
 
 template <bool kIdent>
@@ -566,6 +686,8 @@ int check_view(const irc_view& v, const char* what) {
 }
 
 // block shape for the per-(n,c) reductions
+constexpr int kCounterFloats = 256;     // tail of the reduction workspace reserved for per-image ticket counters
+
 // block = (C/8 channel vectors) x L pixel lanes
 void row_block(int C, int W, int& threads, int& L) {
     const int C8 = C / 8;
@@ -599,14 +721,15 @@ extern "C" int irc_in_stats(const irc_view* z, int C, int n_img, int H, int W, f
     int rc = check_view(*z, "irc_in_stats"); if (rc) return rc;
     if (C % 8 || C > 2048) return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_stats: C must be a multiple of 8");
     int threads, L, chunks; size_t smem;
-    reduce_shape(C, H, W, n_img, work ? work_floats : 0, threads, L, chunks, smem);
-    const long long n = (long long)n_img * C * 2;
+    // the last kCounterFloats floats of `work` are the (zero-initialised, self re-arming) ticket counters
+    const bool staged = work && work_floats > kCounterFloats && n_img <= kCounterFloats;
+    reduce_shape(C, H, W, n_img, staged ? work_floats - kCounterFloats : 0, threads, L, chunks, smem);
     if (chunks == 1) {
-        in_stats_kernel<<<dim3(1, n_img), threads, smem, (cudaStream_t)stream>>>(mk(*z), C, H, W, stats);
+        in_stats_kernel<<<dim3(1, n_img), threads, smem, (cudaStream_t)stream>>>(mk(*z), C, H, W, stats, nullptr, nullptr);
         return irc_check_launch("irc_in_stats");
     }
-    in_stats_kernel<<<dim3(chunks, n_img), threads, smem, (cudaStream_t)stream>>>(mk(*z), C, H, W, work);
-    sum_chunks_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(work, chunks, n, stats);
+    in_stats_kernel<<<dim3(chunks, n_img), threads, smem, (cudaStream_t)stream>>>(mk(*z), C, H, W, work, stats,
+                                                                                 (unsigned*)(work + work_floats - kCounterFloats));
     return irc_check_launch("irc_in_stats");
 }
 
@@ -623,7 +746,21 @@ extern "C" int irc_gather(const irc_gather_args* a, void* stream) {
     p.ty_idx = a->ty_idx; p.ty_w = a->ty_w; p.ky = a->ky > 0 ? a->ky : 1;
     p.tx_idx = a->tx_idx; p.tx_w = a->tx_w; p.kx = a->kx > 0 ? a->kx : 1;
     p.H = a->H; p.W = a->W; p.pad = a->pad; p.halo_mode = a->halo_mode; p.dst_s2d = a->dst_s2d;
+    p.slope_eff = a->act == 1 ? 0.f : (a->act == 2 ? a->slope : 1.f);
     if (p.dst_s2d && (((p.H + 2 * p.pad) | (p.W + 2 * p.pad)) & 1)) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather: space-to-depth needs even padded extents");
+    const int kmax0 = p.ky > p.kx ? p.ky : p.kx;
+    if (a->tile_y <= 0 && (p.ty_idx || p.tx_idx) && !p.dst_s2d && !p.src.s2d_c && !(p.has2 && p.src2.s2d_c) && (p.stats || !p.act) && kmax0 <= 6 &&
+        a->tile_y != -2) {
+        int threads, L;
+        row_block(p.C, p.W + 2 * p.pad, threads, L);
+        const long long rows = (long long)p.n_img * (p.H + 2 * p.pad);
+        const unsigned grid = (unsigned)(rows < 65535 * 16 ? rows : 65535 * 16);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (kmax0 <= 2) gather_lean_kernel<2><<<grid, threads, 0, st>>>(p);
+        else if (kmax0 <= 3) gather_lean_kernel<3><<<grid, threads, 0, st>>>(p);
+        else gather_lean_kernel<6><<<grid, threads, 0, st>>>(p);
+        return irc_check_launch("irc_gather(lean)");
+    }
     if (a->tile_y > 0 && a->tile_x > 0 && (p.ty_idx || p.tx_idx) && p.C % kTileCC == 0) {
         if (a->tile_y + a->tile_x > 64 || a->tile_y > 64 || a->tile_x > 64) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather: tile too large");
         const size_t smem = (size_t)a->patch_y * a->patch_x * kTileCC * sizeof(float);
@@ -674,12 +811,12 @@ extern "C" int irc_in_bwd_reduce(const irc_in_bwd_args* a, void* stream) {
     InBwdP p; int rc = fill_bwd(a, p); if (rc) return rc;
     if (!p.stats || !p.bsum) return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_bwd_reduce: stats and bsum required");
     int threads, L, chunks; size_t smem;
-    reduce_shape(p.C, p.H, p.W, p.n_img, a->work ? a->work_floats : 0, threads, L, chunks, smem);
-    const long long n = (long long)p.n_img * p.C * 2;
+    const bool staged = a->work && a->work_floats > kCounterFloats && p.n_img <= kCounterFloats;
+    reduce_shape(p.C, p.H, p.W, p.n_img, staged ? a->work_floats - kCounterFloats : 0, threads, L, chunks, smem);
     p.part = chunks == 1 ? p.bsum : a->work;
+    p.counters = chunks == 1 ? nullptr : (unsigned*)(a->work + a->work_floats - kCounterFloats);
     if (!p.ty_idx && !p.tx_idx) in_bwd_reduce_kernel<true><<<dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream>>>(p);
     else in_bwd_reduce_kernel<false><<<dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream>>>(p);
-    if (chunks > 1) sum_chunks_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a->work, chunks, n, p.bsum);
     return irc_check_launch("irc_in_bwd_reduce");
 }
 
@@ -718,7 +855,7 @@ extern "C" int irc_colsum(const void* a, long long rows, long long ld, int chan_
                           long long work_floats, void* stream) {
     if (!a || !out) return irc_set_error(IRC_ERR_BAD_ARG, "irc_colsum: null");
     long long bx = (rows + 31) / 32; if (bx > irc_num_sms() * 4) bx = irc_num_sms() * 4;
-    const long long cap = work ? work_floats / C : 0;
+    const long long cap = work && work_floats > kCounterFloats ? (work_floats - kCounterFloats) / C : 0;
     if (bx > cap) bx = cap;
     if (bx <= 1) {
         colsum_kernel<<<dim3(1, (C + 31) / 32), 1024, 0, (cudaStream_t)stream>>>((const bf16*)a, rows, ld, chan_off, C, row_img, out);
