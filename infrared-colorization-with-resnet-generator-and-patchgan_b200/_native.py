@@ -183,6 +183,31 @@ class Tables:
         self.kx = 1 if tx_idx is None else tx_idx.shape[1]
         self._host = None
         self._tiling = {}
+        self._stream = None
+
+    def _load_host(self):
+        if self._host is None:
+            f = lambda t: None if t is None else t.cpu().numpy()
+            self._host = tuple(f(t) for t in (self.ty_idx, self.ty_w, self.tx_idx, self.tx_w))
+        return self._host
+
+    def stream_window(self) -> int:
+        """Window K (rows of source kept in registers) for the streaming stencil kernel, or 0 when the tables do not
+        qualify: both axes tabulated, the last source row of consecutive output rows non-decreasing, every row's
+        non-zero entries within K <= 6 consecutive source rows and at most K x-entries."""
+        if self._stream is None:
+            import numpy as np
+            k = 0
+            if self.ty_idx is not None and self.tx_idx is not None:
+                iy, wy, _, _ = self._load_host()
+                nz = wy != 0
+                if nz.any(1).all():
+                    lo = np.where(nz, iy, 1 << 30).min(1); hi = np.where(nz, iy, -1).max(1)
+                    span = int((hi - lo + 1).max())
+                    if (np.diff(hi) >= 0).all() and max(span, self.kx, self.ky) <= 6:
+                        k = max(span, self.kx, self.ky)
+            self._stream = k
+        return self._stream
 
     def _axis_extent(self, idx, w, n_out, pad, halo_mode, T):
         """largest source index span needed by any T-wide tile of the padded output axis"""
@@ -210,10 +235,7 @@ class Tables:
             return (0, 0, 0, 0)
         key = (H, W, pad, halo_mode)
         if key not in self._tiling:
-            if self._host is None:
-                f = lambda t: None if t is None else t.cpu().numpy()
-                self._host = tuple(f(t) for t in (self.ty_idx, self.ty_w, self.tx_idx, self.tx_w))
-            iy, wy, ix, wx = self._host
+            iy, wy, ix, wx = self._load_host()
             best = None
             for ty, tx in ((16, 16), (8, 32), (8, 16), (4, 32)):
                 py = self._axis_extent(iy, wy, H, pad, halo_mode, ty); px = self._axis_extent(ix, wx, W, pad, halo_mode, tx)
@@ -322,7 +344,18 @@ class CudaBackend:
         g.tx_w = None if tables.tx_w is None else tables.tx_w.data_ptr(); g.kx = tables.kx
         g.H = H; g.W = W; g.pad = pad; g.halo_mode = halo_mode; g.dst_s2d = dst_s2d
         mode = self.gather_mode
-        if mode == "auto":
+        if mode in ("auto", "stream"):
+            k = tables.stream_window()
+            ok = (k > 0 and not dst_s2d and not src.s2d_c and res is None and (stats is not None or not act) and
+                  (src2 is None or (stats is None and not src2.s2d_c)) and (pad == 0 or (H > 2 * pad + 1 and W > 2 * pad + 1)))
+            if ok:
+                # rows per strip: enough blocks for >= ~4 waves of 2 x 148 resident blocks, at most 32 rows
+                lanes = max(1, 256 // (C_ // 8))
+                blocks_per_row = n_img * ((W + lanes - 1) // lanes)
+                strip = max(4, min(32, (blocks_per_row * H) // 1184))
+                g.tile_y, g.tile_x, g.patch_y, g.patch_x = -3, k, strip, 0
+                check(self.L.irc_gather(C.byref(g), _stream())); self.launches += 1
+                return
             # measured (scripts/bench_elem.py): the shared-memory tiled kernel wins for the up-sampling stencils and the
             # transposed ones with many taps / two sources; the register-table kernel wins for stride-2 down-sampling
             mode = "tiled" if (tables.ky >= 6 or src2 is not None or H > src.hp) else "lean"

@@ -25,10 +25,12 @@ inline View mk(const irc_view& v) {
     return r;
 }
 
-__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
     float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p)), v);
 }
 __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
     *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
@@ -306,6 +308,162 @@ __global__ void __launch_bounds__(256, 3) gather_lean_kernel(const GatherP p) {
                 }
             }
             store8(drow + (long long)X * p.dst.ld, acc);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Streaming separable gather (the anti-aliased Downsample / UpsampleAA stencils and their transposes).
+// One thread = 8 channels of one output column; it walks down a strip of output rows keeping the last K horizontally
+// filtered source rows in registers.  Source rows enter strictly in order (the host checks that the last source row
+// of the y-table is non-decreasing), each is read, normalised and x-filtered ONCE per output column, the raw 16-byte
+// loads of the next source row are in flight while the current output row is y-filtered and stored.  Per output vector
+// this costs (kx loads + kx x-taps) per NEW source row + K y-taps, instead of ky*kx loads/normalisations.
+// The padding ring of the destination is written by the threads that own the bordering pixels (zeros, or the
+// reflected value when halo_mode == 1).
+// ---------------------------------------------------------------------------------
+constexpr int kMaxStrip = 32;
+
+template <int K, bool kNorm, bool kTwo>
+__global__ void __launch_bounds__(256, 2) gather_stream_kernel(const GatherP p, int strip) {
+    __shared__ int s_hi[kMaxStrip];
+    __shared__ int s_lo0;
+    __shared__ float s_wd[kMaxStrip][K];
+    const int C8 = p.C >> 3;
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int c = cv * 8;
+    const int n = blockIdx.z;
+    const int ya = blockIdx.y * strip;
+    const int rows = min(strip, p.H - ya);
+    const int x = blockIdx.x * L + lane;
+    if ((int)threadIdx.x < rows) {
+        // dense y-weights of output row y over the window [hi+1-K, hi] of source rows
+        const int y = ya + threadIdx.x;
+        int lo = 0x7fffffff, hi = -1;
+        for (int i = 0; i < p.ky; ++i)
+            if (__ldg(p.ty_w + y * p.ky + i) != 0.f) { const int q = __ldg(p.ty_idx + y * p.ky + i); lo = min(lo, q); hi = max(hi, q); }
+        s_hi[threadIdx.x] = hi;
+        if (threadIdx.x == 0) s_lo0 = lo;
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+            const int r = hi + 1 - K + s;
+            float w = 0.f;
+            for (int i = 0; i < p.ky; ++i) {
+                const float wi = __ldg(p.ty_w + y * p.ky + i);
+                if (wi != 0.f && __ldg(p.ty_idx + y * p.ky + i) == r) w += wi;
+            }
+            s_wd[threadIdx.x][s] = w;
+        }
+    }
+    __syncthreads();
+    if (x >= p.W) return;
+    // x entries of this output column
+    float wx[K]; int ox[K], ox2[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const bool h = j < p.kx;
+        wx[j] = h ? __ldg(p.tx_w + x * p.kx + j) : 0.f;
+        const int ix = h ? __ldg(p.tx_idx + x * p.kx + j) : 0;
+        ox[j] = ix * (int)p.src.ld;
+        ox2[j] = kTwo ? ix * (int)p.src2.ld : 0;
+    }
+    float mu[8], rs[8];
+    if (kNorm) {
+        moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mu[k] = -mu[k] * rs[k];
+    }
+    const bf16* srow = p.src.at(n, 0, 0, c);
+    const long long sstep = (long long)p.src.wp * p.src.ld;
+    const bf16* srow2 = kTwo ? p.src2.at(n, 0, 0, c) : nullptr;
+    const long long sstep2 = kTwo ? (long long)p.src2.wp * p.src2.ld : 0;
+    // destination: interior pixel (y, x) -> padded (y + pad, x + pad); extra ring column / row owned by this thread
+    const int pad = p.pad, W = p.W, H = p.H;
+    int eX = -1;
+    if (pad) {
+        if (p.halo_mode == 1) eX = (x >= 1 && x <= pad) ? pad - x : ((x >= W - 1 - pad && x <= W - 2) ? pad + 2 * (W - 1) - x : -1);
+        else eX = x < pad ? x : (x >= W - pad ? x + 2 * pad : -1);
+    }
+    bf16* dbase = const_cast<bf16*>(p.dst.p) + ((long long)(n * p.dst.hp + p.dst.oy - pad) * p.dst.wp + (p.dst.ox - pad)) * p.dst.ld + p.dst.off + c;
+    const long long dstep = (long long)p.dst.wp * p.dst.ld;
+
+    float hb[K][8];
+#pragma unroll
+    for (int s = 0; s < K; ++s)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hb[s][k] = 0.f;
+    int top = s_lo0;
+    const int last = s_hi[rows - 1];
+    uint4 raw[K], raw2[K];
+    auto fetch = [&](int r) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (wx[j] != 0.f) {
+                raw[j] = __ldg(reinterpret_cast<const uint4*>(srow + r * sstep + ox[j]));
+                if (kTwo) raw2[j] = __ldg(reinterpret_cast<const uint4*>(srow2 + r * sstep2 + ox2[j]));
+            }
+        }
+    };
+    if (top <= last) fetch(top);
+    for (int t = 0; t < rows; ++t) {
+        const int hi = s_hi[t];
+        while (top <= hi) {
+            float h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                if (wx[j] != 0.f) {
+                    float v[8];
+                    unpack8(raw[j], v);
+                    if (kNorm) {
+                        if (p.act == 1) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], rs[k], mu[k]), 0.f);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) { const float u = fmaf(v[k], rs[k], mu[k]); v[k] = fmaxf(u, 0.f) + p.slope_eff * fminf(u, 0.f); }
+                        }
+                    }
+                    if (kTwo) {
+                        float u[8];
+                        unpack8(raw2[j], u);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] += u[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) h[k] = fmaf(wx[j], v[k], h[k]);
+                }
+            }
+            ++top;
+            if (top <= last) fetch(top);
+#pragma unroll
+            for (int s = 0; s + 1 < K; ++s)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) hb[s][k] = hb[s + 1][k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) hb[K - 1][k] = h[k];
+        }
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+            const float w = s_wd[t][s];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fmaf(w, hb[s][k], acc[k]);
+        }
+        const int y = ya + t;
+        const uint4 val = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+        bf16* drow = dbase + (y + pad) * dstep;
+        *reinterpret_cast<uint4*>(drow + (long long)(x + pad) * p.dst.ld) = val;
+        if (pad) {
+            const uint4 ring = p.halo_mode == 1 ? val : make_uint4(0, 0, 0, 0);
+            int eY;
+            if (p.halo_mode == 1) eY = (y >= 1 && y <= pad) ? pad - y : ((y >= H - 1 - pad && y <= H - 2) ? pad + 2 * (H - 1) - y : -1);
+            else eY = y < pad ? y : (y >= H - pad ? y + 2 * pad : -1);
+            if (eX >= 0) *reinterpret_cast<uint4*>(drow + (long long)eX * p.dst.ld) = ring;
+            if (eY >= 0) {
+                bf16* erow = dbase + eY * dstep;
+                *reinterpret_cast<uint4*>(erow + (long long)(x + pad) * p.dst.ld) = ring;
+                if (eX >= 0) *reinterpret_cast<uint4*>(erow + (long long)eX * p.dst.ld) = ring;
+            }
         }
     }
 }
@@ -748,6 +906,26 @@ extern "C" int irc_gather(const irc_gather_args* a, void* stream) {
     p.H = a->H; p.W = a->W; p.pad = a->pad; p.halo_mode = a->halo_mode; p.dst_s2d = a->dst_s2d;
     p.slope_eff = a->act == 1 ? 0.f : (a->act == 2 ? a->slope : 1.f);
     if (p.dst_s2d && (((p.H + 2 * p.pad) | (p.W + 2 * p.pad)) & 1)) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather: space-to-depth needs even padded extents");
+    if (a->tile_y == -3) {
+        // streaming separable kernel: tile_x = window of source rows (span of the y-table), patch_y = rows per strip
+        const int K = a->tile_x, strip = a->patch_y;
+        if (!p.ty_idx || !p.tx_idx || p.dst_s2d || p.src.s2d_c || (p.has2 && p.src2.s2d_c) || p.has_res || (p.act && !p.stats) ||
+            K < p.ky || K < p.kx || K > 6 || strip < 1 || strip > kMaxStrip || (p.pad && (p.W <= 2 * p.pad + 1 || p.H <= 2 * p.pad + 1)) ||
+            (p.has2 && p.stats))
+            return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather(stream): unsupported combination");
+        int threads, L;
+        row_block(p.C, p.W, threads, L);
+        dim3 grid((p.W + L - 1) / L, (p.H + strip - 1) / strip, p.n_img);
+        cudaStream_t st = (cudaStream_t)stream;
+        const bool nrm = p.stats != nullptr;
+#define IRC_STREAM(KK) do { \
+            if (p.has2) gather_stream_kernel<KK, false, true><<<grid, threads, 0, st>>>(p, strip); \
+            else if (nrm) gather_stream_kernel<KK, true, false><<<grid, threads, 0, st>>>(p, strip); \
+            else gather_stream_kernel<KK, false, false><<<grid, threads, 0, st>>>(p, strip); } while (0)
+        if (K <= 2) IRC_STREAM(2); else if (K <= 3) IRC_STREAM(3); else if (K <= 4) IRC_STREAM(4); else IRC_STREAM(6);
+#undef IRC_STREAM
+        return irc_check_launch("irc_gather(stream)");
+    }
     const int kmax0 = p.ky > p.kx ? p.ky : p.kx;
     if (a->tile_y <= 0 && (p.ty_idx || p.tx_idx) && !p.dst_s2d && !p.src.s2d_c && !(p.has2 && p.src2.s2d_c) && (p.stats || !p.act) && kmax0 <= 6 &&
         a->tile_y != -2) {

@@ -92,6 +92,53 @@ def test_gather(bes, mode):
     close(a[0], b[0], 1e-2, mode)
 
 
+@pytest.mark.parametrize("mode", ["down_zero", "down_reflect", "up_plain", "up_norm", "upT", "upT_pad", "downT", "downT_two"])
+@pytest.mark.parametrize("C,H,W", [(128, 24, 40), (256, 16, 12), (64, 36, 20)])
+def test_gather_stream(bes, mode, C, H, W):
+    """the streaming separable kernel (anti-aliased Downsample / UpsampleAA and their transposes, irc:307-310, :350-355) in
+    every configuration the generator plans use, over several strips and column chunks, against the torch restatement"""
+    from irc_b200 import layout as L
+    from irc_b200._native import View
+    g = gen(5)
+    n = 2
+    h2, w2 = H // 2, W // 2
+    mk = lambda my, mx: L.make_tables(my, mx, "cuda")
+    if mode.startswith("down") and not mode.startswith("downT"):
+        src = frame(n, H, W, 1, C, g); dst = frame(n, h2, w2, 1, C + 64, g)
+        st = torch.zeros(n, C, 2, device="cuda"); bes[1].in_stats(src.view(), C, n, H, W, st)
+        t = mk(L.down_matrix(H), L.down_matrix(W))
+        halo = 1 if mode == "down_reflect" else 0
+        fn = lambda be, d: be.gather(src.view(), View(d, 64, dst.hp, dst.wp, 1, 1), C, n, h2, w2, 1, halo, tables=t, stats=st, cnt=H * W, act=1)
+    elif mode in ("up_plain", "up_norm"):
+        src = frame(n, h2, w2, 1, C, g); dst = frame(n, H, W, 1, C, g)
+        st = torch.zeros(n, C, 2, device="cuda"); bes[1].in_stats(src.view(), C, n, h2, w2, st)
+        t = mk(L.up_matrix(h2), L.up_matrix(w2))
+        kw = dict(stats=st, cnt=h2 * w2, act=2, slope=0.2) if mode == "up_norm" else {}
+        fn = lambda be, d: be.gather(src.view(), View(d, 0, dst.hp, dst.wp, 1, 1), C, n, H, W, 1, 0, tables=t, **kw)
+    elif mode in ("upT", "upT_pad"):
+        p = 1 if mode == "upT_pad" else 0
+        src = frame(n, H, W, 1, C + 64, g); dst = frame(n, h2, w2, p, C, g)
+        t = mk(L.up_matrix(h2).T, L.up_matrix(w2).T)
+        fn = lambda be, d: be.gather(src.view(64), View(d, 0, dst.hp, dst.wp, p, p), C, n, h2, w2, p, 0, tables=t)
+    else:
+        src = frame(n, h2, w2, 1, C, g); src2 = frame(n, h2, w2, 1, C, g); dst = frame(n, H, W, 0, C, g)
+        t = mk(L.down_matrix(H).T, L.down_matrix(W).T)
+        kw = dict(src2=src2.view()) if mode == "downT_two" else {}
+        fn = lambda be, d: be.gather(src.view(), View(d, 0, dst.hp, dst.wp, 0, 0), C, n, H, W, 0, 0, tables=t, **kw)
+    assert t.stream_window() > 0
+    a, b = both(bes, fn, [dst.t])
+    close(a[0], b[0], 1e-2, mode)
+    # the same call through the other kernels of irc_gather gives the same frame (ring included)
+    be = bes[0]
+    old = be.gather_mode
+    try:
+        be.gather_mode = "lean"
+        d2 = dst.t.clone(); fn(be, d2); torch.cuda.synchronize()
+    finally:
+        be.gather_mode = old
+    close(a[0], d2, 1e-2, mode + " vs lean")
+
+
 @pytest.mark.parametrize("mode", ["norm_relu_fold", "norm_none_two", "plain_lrelu", "upT", "s2d_src"])
 def test_in_bwd(bes, mode):
     from irc_b200 import layout as L
