@@ -245,6 +245,12 @@ int irc_gather_sum(const float* src, const int* map, long long n, int splits, lo
 int irc_stencil_nchw(const float* in, float* out, int planes, int Hi, int Wi, int Ho, int Wo, const int* ty_idx, const float* ty_w, int ky,
                      const int* tx_idx, const float* tx_w, int kx, int accumulate, void* stream);
 
+/* Same contract, streaming kernel (rolling register window over the source rows, input and output touched once in
+ * DRAM).  Requires tables whose last contributing source row is non-decreasing in Y and whose rows span at most
+ * `window` <= 8 consecutive source rows / x-entries: the binomial and blur*bilinear tables and their transposes do. */
+int irc_stencil_nchw_stream(const float* in, float* out, int planes, int Hi, int Wi, int Ho, int Wo, const int* ty_idx, const float* ty_w,
+                            int ky, const int* tx_idx, const float* tx_w, int kx, int window, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

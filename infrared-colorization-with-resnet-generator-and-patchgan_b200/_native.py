@@ -21,7 +21,7 @@ EXPORTS = [
     "irc_in_stats", "irc_gather", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_maxpool2", "irc_maxpool2_bwd",
     "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
     "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics",
-    "irc_adam", "irc_pack_bf16", "irc_gather_sum", "irc_stencil_nchw", "irc_fold_inplace",
+    "irc_adam", "irc_pack_bf16", "irc_gather_sum", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
 ]
 
 
@@ -191,11 +191,11 @@ class Tables:
             self._host = tuple(f(t) for t in (self.ty_idx, self.ty_w, self.tx_idx, self.tx_w))
         return self._host
 
-    def stream_window(self) -> int:
+    def stream_window(self, kmax: int = 6) -> int:
         """Window K (rows of source kept in registers) for the streaming stencil kernel, or 0 when the tables do not
         qualify: both axes tabulated, the last source row of consecutive output rows non-decreasing, every row's
         non-zero entries within K <= 6 consecutive source rows and at most K x-entries."""
-        if self._stream is None:
+        if self._stream is None or self._stream[0] != kmax:
             import numpy as np
             k = 0
             if self.ty_idx is not None and self.tx_idx is not None:
@@ -204,10 +204,10 @@ class Tables:
                 if nz.any(1).all():
                     lo = np.where(nz, iy, 1 << 30).min(1); hi = np.where(nz, iy, -1).max(1)
                     span = int((hi - lo + 1).max())
-                    if (np.diff(hi) >= 0).all() and max(span, self.kx, self.ky) <= 6:
+                    if (np.diff(hi) >= 0).all() and max(span, self.kx, self.ky) <= kmax:
                         k = max(span, self.kx, self.ky)
-            self._stream = k
-        return self._stream
+            self._stream = (kmax, k)
+        return self._stream[1]
 
     def _axis_extent(self, idx, w, n_out, pad, halo_mode, T):
         """largest source index span needed by any T-wide tile of the padded output axis"""
@@ -490,6 +490,12 @@ class CudaBackend:
         n, c, hi, wi = x.shape
         ho, wo = out.shape[2], out.shape[3]
         assert x.dtype == torch.float32 and out.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+        k = tables.stream_window(8) if self.gather_mode in ("auto", "stream") else 0
+        if k:
+            check(self.L.irc_stencil_nchw_stream(_p(x), _p(out), n * c, hi, wi, ho, wo, _p(tables.ty_idx), _p(tables.ty_w), tables.ky,
+                                                 _p(tables.tx_idx), _p(tables.tx_w), tables.kx, k, int(accumulate), _stream()))
+            self.launches += 1
+            return
         check(self.L.irc_stencil_nchw(_p(x), _p(out), n * c, hi, wi, ho, wo, _p(tables.ty_idx), _p(tables.ty_w), tables.ky,
                                       _p(tables.tx_idx), _p(tables.tx_w), tables.kx, int(accumulate), _stream())); self.launches += 1
 

@@ -67,6 +67,7 @@ __device__ __forceinline__ float dactf(float v, int act, float slope) {
 // row index table: row_img[q] = n for live rows, -1 for the padding ring
 // ---------------------------------------------------------------------------------
 __global__ void row_index_kernel(short* out, int n_img, int hp, int wp, int y0, int y1, int x0, int x1) {
+    irc::pdl_prologue();
     const long long total = (long long)n_img * hp * wp;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(q % wp);
@@ -99,6 +100,7 @@ __device__ __forceinline__ void finalize_by_last_block(const float* part, float*
 // block = (C/8) channel vectors x L pixel lanes; grid = (chunks, N)
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 4) in_stats_kernel(View z, int C, int H, int W, float* part, float* out, unsigned* counters) {
+    irc::pdl_prologue();
     extern __shared__ float sh[];
     const int C8 = C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(256, 4) in_stats_kernel(View z, int C, int H, 
 
 // out[j] = sum over chunks (fixed order) of part[chunk][j]: deterministic second stage of the reductions
 __global__ void sum_chunks_kernel(const float* __restrict__ part, int chunks, long long n, float* __restrict__ out) {
+    irc::pdl_prologue();
     for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
         float a = 0.f;
         for (int c = 0; c < chunks; ++c) a += part[(long long)c * n + j];
@@ -152,6 +155,7 @@ struct GatherP {
 
 template <bool kIdent>
 __global__ void __launch_bounds__(256, 4) gather_kernel(const GatherP p) {
+    irc::pdl_prologue();
     // one block per (image, padded row); thread = (channel vector, pixel lane): nothing is divided in the loops
     const int C8 = p.C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
@@ -226,6 +230,7 @@ __global__ void __launch_bounds__(256, 4) gather_kernel(const GatherP p) {
 // ---------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(256, 3) gather_lean_kernel(const GatherP p) {
+    irc::pdl_prologue();
     const int C8 = p.C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
     const int c = cv * 8;
@@ -325,7 +330,8 @@ __global__ void __launch_bounds__(256, 3) gather_lean_kernel(const GatherP p) {
 constexpr int kMaxStrip = 32;
 
 template <int K, bool kNorm, bool kTwo>
-__global__ void __launch_bounds__(256, 2) gather_stream_kernel(const GatherP p, int strip) {
+__global__ void __launch_bounds__(256, K <= 3 ? 3 : 2) gather_stream_kernel(const GatherP p, int strip) {
+    irc::pdl_prologue();
     __shared__ int s_hi[kMaxStrip];
     __shared__ int s_lo0;
     __shared__ float s_wd[kMaxStrip][K];
@@ -478,6 +484,7 @@ constexpr int kTileCC = 32;   // channels per block
 
 template <int K>
 __global__ void __launch_bounds__(256) gather_tiled_kernel(const GatherP p, int TY, int TX, int maxNy, int maxNx) {
+    irc::pdl_prologue();
     extern __shared__ float patch[];                 // [ny*nx][kTileCC]
     __shared__ int ys[64], xs[64];                   // interior coordinate of every tile row / column (-1 = zero ring, -2 = outside)
     __shared__ int box[4];                           // lo_y, hi_y, lo_x, hi_x
@@ -646,6 +653,7 @@ __device__ __forceinline__ void bwd_gather(const InBwdP& p, int n, int y, int x,
 
 template <bool kIdent>
 __global__ void __launch_bounds__(256, 4) in_bwd_reduce_kernel(const InBwdP p) {
+    irc::pdl_prologue();
     extern __shared__ float sh[];
     const int C8 = p.C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
@@ -683,6 +691,7 @@ __global__ void __launch_bounds__(256, 4) in_bwd_reduce_kernel(const InBwdP p) {
 
 template <bool kIdent>
 __global__ void __launch_bounds__(256, 4) in_bwd_apply_kernel(const InBwdP p) {
+    irc::pdl_prologue();
     const int C8 = p.C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
     const int c = cv * 8;
@@ -722,6 +731,7 @@ __global__ void __launch_bounds__(256, 4) in_bwd_apply_kernel(const InBwdP p) {
 // 2x2 max pool (VGG trunk, irc:664) on frames, and its backward fused with the ReLU mask
 // ---------------------------------------------------------------------------------
 __global__ void maxpool_kernel(View src, View dst, int C, int n_img, int Ho, int Wo) {
+    irc::pdl_prologue();
     const int C8 = C >> 3;
     const long long total = (long long)n_img * Ho * Wo * C8;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -743,6 +753,7 @@ __global__ void maxpool_kernel(View src, View dst, int C, int n_img, int Ho, int
 }
 // dsrc[n, y, x] = g[n, y/2, x/2] if src[n,y,x] is the first maximum of its window and src > 0, else 0
 __global__ void maxpool_bwd_kernel(View src, View g, View dsrc, int C, int n_img, int Ho, int Wo) {
+    irc::pdl_prologue();
     const int C8 = C >> 3;
     const long long total = (long long)n_img * Ho * Wo * C8;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -775,6 +786,7 @@ __global__ void maxpool_bwd_kernel(View src, View g, View dsrc, int C, int n_img
 
 // column sums of a bf16 [rows][ld] matrix slice -> fp32 [C] (bias gradients)
 __global__ void colsum_kernel(const bf16* a, long long rows, long long ld, int off, int C, const short* row_img, float* part) {
+    irc::pdl_prologue();
     const int c = blockIdx.y * 32 + (threadIdx.x & 31);
     const int lane_r = threadIdx.x >> 5, R = blockDim.x >> 5;
     float s = 0.f;
@@ -795,6 +807,7 @@ __global__ void colsum_kernel(const bf16* a, long long rows, long long ld, int o
 // pixel within p of the border adds the ring pixels that mirror onto it (ring pixels are only read, each thread writes
 // its own pixel: race-free) and clears them.  Touches O(p * perimeter) pixels instead of a full pass.
 __global__ void fold_inplace_kernel(bf16* g, long long ld, int off, int C, int n_img, int H, int W, int p) {
+    irc::pdl_prologue();
     const int C8 = C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
     const int c = cv * 8;
@@ -871,7 +884,7 @@ void reduce_shape(int C, int H, int W, int n_img, long long work_floats, int& th
 extern "C" int irc_row_index(short* row_img, int n_img, int hp, int wp, int y0, int y1, int x0, int x1, void* stream) {
     if (!row_img) return irc_set_error(IRC_ERR_BAD_ARG, "irc_row_index: null");
     const long long total = (long long)n_img * hp * wp;
-    row_index_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(row_img, n_img, hp, wp, y0, y1, x0, x1);
+    irc::launch(row_index_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, row_img, n_img, hp, wp, y0, y1, x0, x1);
     return irc_check_launch("irc_row_index");
 }
 
@@ -883,10 +896,10 @@ extern "C" int irc_in_stats(const irc_view* z, int C, int n_img, int H, int W, f
     const bool staged = work && work_floats > kCounterFloats && n_img <= kCounterFloats;
     reduce_shape(C, H, W, n_img, staged ? work_floats - kCounterFloats : 0, threads, L, chunks, smem);
     if (chunks == 1) {
-        in_stats_kernel<<<dim3(1, n_img), threads, smem, (cudaStream_t)stream>>>(mk(*z), C, H, W, stats, nullptr, nullptr);
+        irc::launch(in_stats_kernel, dim3(1, n_img), threads, smem, (cudaStream_t)stream, mk(*z), C, H, W, stats, nullptr, nullptr);
         return irc_check_launch("irc_in_stats");
     }
-    in_stats_kernel<<<dim3(chunks, n_img), threads, smem, (cudaStream_t)stream>>>(mk(*z), C, H, W, work, stats,
+    irc::launch(in_stats_kernel, dim3(chunks, n_img), threads, smem, (cudaStream_t)stream, mk(*z), C, H, W, work, stats,
                                                                                  (unsigned*)(work + work_floats - kCounterFloats));
     return irc_check_launch("irc_in_stats");
 }
@@ -919,9 +932,9 @@ extern "C" int irc_gather(const irc_gather_args* a, void* stream) {
         cudaStream_t st = (cudaStream_t)stream;
         const bool nrm = p.stats != nullptr;
 #define IRC_STREAM(KK) do { \
-            if (p.has2) gather_stream_kernel<KK, false, true><<<grid, threads, 0, st>>>(p, strip); \
-            else if (nrm) gather_stream_kernel<KK, true, false><<<grid, threads, 0, st>>>(p, strip); \
-            else gather_stream_kernel<KK, false, false><<<grid, threads, 0, st>>>(p, strip); } while (0)
+            if (p.has2) irc::launch(gather_stream_kernel<KK, false, true>, grid, threads, 0, st, p, strip); \
+            else if (nrm) irc::launch(gather_stream_kernel<KK, true, false>, grid, threads, 0, st, p, strip); \
+            else irc::launch(gather_stream_kernel<KK, false, false>, grid, threads, 0, st, p, strip); } while (0)
         if (K <= 2) IRC_STREAM(2); else if (K <= 3) IRC_STREAM(3); else if (K <= 4) IRC_STREAM(4); else IRC_STREAM(6);
 #undef IRC_STREAM
         return irc_check_launch("irc_gather(stream)");
@@ -934,9 +947,9 @@ extern "C" int irc_gather(const irc_gather_args* a, void* stream) {
         const long long rows = (long long)p.n_img * (p.H + 2 * p.pad);
         const unsigned grid = (unsigned)(rows < 65535 * 16 ? rows : 65535 * 16);
         cudaStream_t st = (cudaStream_t)stream;
-        if (kmax0 <= 2) gather_lean_kernel<2><<<grid, threads, 0, st>>>(p);
-        else if (kmax0 <= 3) gather_lean_kernel<3><<<grid, threads, 0, st>>>(p);
-        else gather_lean_kernel<6><<<grid, threads, 0, st>>>(p);
+        if (kmax0 <= 2) irc::launch(gather_lean_kernel<2>, grid, threads, 0, st, p);
+        else if (kmax0 <= 3) irc::launch(gather_lean_kernel<3>, grid, threads, 0, st, p);
+        else irc::launch(gather_lean_kernel<6>, grid, threads, 0, st, p);
         return irc_check_launch("irc_gather(lean)");
     }
     if (a->tile_y > 0 && a->tile_x > 0 && (p.ty_idx || p.tx_idx) && p.C % kTileCC == 0) {
@@ -955,10 +968,10 @@ extern "C" int irc_gather(const irc_gather_args* a, void* stream) {
         dim3 grid((Wp + a->tile_x - 1) / a->tile_x, (Hp + a->tile_y - 1) / a->tile_y, p.n_img * (p.C / kTileCC));
         const int kmax = p.ky > p.kx ? p.ky : p.kx;
         cudaStream_t st = (cudaStream_t)stream;
-        if (kmax <= 2) gather_tiled_kernel<2><<<grid, 256, smem, st>>>(p, a->tile_y, a->tile_x, a->patch_y, a->patch_x);
-        else if (kmax <= 3) gather_tiled_kernel<3><<<grid, 256, smem, st>>>(p, a->tile_y, a->tile_x, a->patch_y, a->patch_x);
-        else if (kmax <= 6) gather_tiled_kernel<6><<<grid, 256, smem, st>>>(p, a->tile_y, a->tile_x, a->patch_y, a->patch_x);
-        else if (kmax <= 8) gather_tiled_kernel<8><<<grid, 256, smem, st>>>(p, a->tile_y, a->tile_x, a->patch_y, a->patch_x);
+        if (kmax <= 2) irc::launch(gather_tiled_kernel<2>, grid, 256, smem, st, p, a->tile_y, a->tile_x, a->patch_y, a->patch_x);
+        else if (kmax <= 3) irc::launch(gather_tiled_kernel<3>, grid, 256, smem, st, p, a->tile_y, a->tile_x, a->patch_y, a->patch_x);
+        else if (kmax <= 6) irc::launch(gather_tiled_kernel<6>, grid, 256, smem, st, p, a->tile_y, a->tile_x, a->patch_y, a->patch_x);
+        else if (kmax <= 8) irc::launch(gather_tiled_kernel<8>, grid, 256, smem, st, p, a->tile_y, a->tile_x, a->patch_y, a->patch_x);
         else return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather: tables wider than 8 entries");
         return irc_check_launch("irc_gather(tiled)");
     }
@@ -966,8 +979,8 @@ extern "C" int irc_gather(const irc_gather_args* a, void* stream) {
     row_block(p.C, p.W + 2 * p.pad, threads, L);
     const long long rows = (long long)p.n_img * (p.H + 2 * p.pad);
     const unsigned grid = (unsigned)(rows < 65535 * 16 ? rows : 65535 * 16);
-    if (!p.ty_idx && !p.tx_idx) gather_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
-    else gather_kernel<false><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
+    if (!p.ty_idx && !p.tx_idx) irc::launch(gather_kernel<true>, grid, threads, 0, (cudaStream_t)stream, p);
+    else irc::launch(gather_kernel<false>, grid, threads, 0, (cudaStream_t)stream, p);
     return irc_check_launch("irc_gather");
 }
 
@@ -993,8 +1006,8 @@ extern "C" int irc_in_bwd_reduce(const irc_in_bwd_args* a, void* stream) {
     reduce_shape(p.C, p.H, p.W, p.n_img, staged ? a->work_floats - kCounterFloats : 0, threads, L, chunks, smem);
     p.part = chunks == 1 ? p.bsum : a->work;
     p.counters = chunks == 1 ? nullptr : (unsigned*)(a->work + a->work_floats - kCounterFloats);
-    if (!p.ty_idx && !p.tx_idx) in_bwd_reduce_kernel<true><<<dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream>>>(p);
-    else in_bwd_reduce_kernel<false><<<dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream>>>(p);
+    if (!p.ty_idx && !p.tx_idx) irc::launch(in_bwd_reduce_kernel<true>, dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream, p);
+    else irc::launch(in_bwd_reduce_kernel<false>, dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream, p);
     return irc_check_launch("irc_in_bwd_reduce");
 }
 
@@ -1007,8 +1020,8 @@ extern "C" int irc_in_bwd_apply(const irc_in_bwd_args* a, void* stream) {
     row_block(p.C, p.W, threads, L);
     const long long rows = (long long)p.n_img * p.H;
     const unsigned grid = (unsigned)(rows < 65535 * 16 ? rows : 65535 * 16);
-    if (!p.ty_idx && !p.tx_idx) in_bwd_apply_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
-    else in_bwd_apply_kernel<false><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
+    if (!p.ty_idx && !p.tx_idx) irc::launch(in_bwd_apply_kernel<true>, grid, threads, 0, (cudaStream_t)stream, p);
+    else irc::launch(in_bwd_apply_kernel<false>, grid, threads, 0, (cudaStream_t)stream, p);
     return irc_check_launch("irc_in_bwd_apply");
 }
 
@@ -1016,7 +1029,7 @@ extern "C" int irc_maxpool2(const irc_view* src, const irc_view* dst, int C, int
     int rc = check_view(*src, "irc_maxpool2 src"); if (rc) return rc;
     rc = check_view(*dst, "irc_maxpool2 dst"); if (rc) return rc;
     const long long total = (long long)n_img * Ho * Wo * (C / 8);
-    maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(*src), mk(*dst), C, n_img, Ho, Wo);
+    irc::launch(maxpool_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, mk(*src), mk(*dst), C, n_img, Ho, Wo);
     return irc_check_launch("irc_maxpool2");
 }
 
@@ -1025,7 +1038,7 @@ extern "C" int irc_maxpool2_bwd(const irc_view* src, const irc_view* g, const ir
     rc = check_view(*g, "irc_maxpool2_bwd g"); if (rc) return rc;
     rc = check_view(*dsrc, "irc_maxpool2_bwd dsrc"); if (rc) return rc;
     const long long total = (long long)n_img * Ho * Wo * (C / 8);
-    maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(*src), mk(*g), mk(*dsrc), C, n_img, Ho, Wo);
+    irc::launch(maxpool_bwd_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, mk(*src), mk(*g), mk(*dsrc), C, n_img, Ho, Wo);
     return irc_check_launch("irc_maxpool2_bwd");
 }
 
@@ -1036,11 +1049,11 @@ extern "C" int irc_colsum(const void* a, long long rows, long long ld, int chan_
     const long long cap = work && work_floats > kCounterFloats ? (work_floats - kCounterFloats) / C : 0;
     if (bx > cap) bx = cap;
     if (bx <= 1) {
-        colsum_kernel<<<dim3(1, (C + 31) / 32), 1024, 0, (cudaStream_t)stream>>>((const bf16*)a, rows, ld, chan_off, C, row_img, out);
+        irc::launch(colsum_kernel, dim3(1, (C + 31) / 32), 1024, 0, (cudaStream_t)stream, (const bf16*)a, rows, ld, chan_off, C, row_img, out);
         return irc_check_launch("irc_colsum");
     }
-    colsum_kernel<<<dim3((unsigned)bx, (C + 31) / 32), 1024, 0, (cudaStream_t)stream>>>((const bf16*)a, rows, ld, chan_off, C, row_img, work);
-    sum_chunks_kernel<<<grid_for(C, 256), 256, 0, (cudaStream_t)stream>>>(work, (int)bx, C, out);
+    irc::launch(colsum_kernel, dim3((unsigned)bx, (C + 31) / 32), 1024, 0, (cudaStream_t)stream, (const bf16*)a, rows, ld, chan_off, C, row_img, work);
+    irc::launch(sum_chunks_kernel, grid_for(C, 256), 256, 0, (cudaStream_t)stream, work, (int)bx, C, out);
     return irc_check_launch("irc_colsum");
 }
 
@@ -1049,6 +1062,6 @@ extern "C" int irc_fold_inplace(void* g, long long ld, int chan_off, int C, int 
     if (p < 1 || 2 * p + 2 > H || 2 * p + 2 > W) return irc_set_error(IRC_ERR_BAD_ARG, "irc_fold_inplace: image too small for the pad width");
     int threads, L;
     row_block(C, W, threads, L);
-    fold_inplace_kernel<<<n_img * H, threads, 0, (cudaStream_t)stream>>>((bf16*)g, ld, chan_off, C, n_img, H, W, p);
+    irc::launch(fold_inplace_kernel, n_img * H, threads, 0, (cudaStream_t)stream, (bf16*)g, ld, chan_off, C, n_img, H, W, p);
     return irc_check_launch("irc_fold_inplace");
 }

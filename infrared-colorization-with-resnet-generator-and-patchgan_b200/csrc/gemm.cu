@@ -231,6 +231,7 @@ __device__ __forceinline__ void epilogue_subtile_staged(const ConvParams& p, con
 template <int MT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+    irc::pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int tile_rows = kBM * MT;
@@ -407,6 +408,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_shifted(uint32_t smem_addr, 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_runs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p,
                       const RunParams rp) {
+    irc::pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int SA = rp.sa_stages, SB = rp.sb_stages;
@@ -559,6 +561,7 @@ struct TnParams {
 template <int TPC>
 __global__ void __launch_bounds__(kThreads, 1)
 tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnParams p) {
+    irc::pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int stage_a = kBK * 128 * 2;             // 2 groups of 64 channels x 64 rows
@@ -838,12 +841,12 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
             g_attr_runs = true;
         }
         const long long tiles1 = ((a->a_rows + kBM - 1) / kBM) * p.n_tiles;
-        conv_gemm_runs_kernel<<<(int)(tiles1 < sms ? tiles1 : sms), kThreads, smem2, (cudaStream_t)stream>>>(tmA2, tmB, q, rp);
+        irc::launch<1>(conv_gemm_runs_kernel, (int)(tiles1 < sms ? tiles1 : sms), kThreads, smem2, (cudaStream_t)stream, tmA2, tmB, q, rp);
         return irc_check_launch("irc_conv_gemm(runs)");
     }
-    if (mt == 1) conv_gemm_kernel<1><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(tmOut, tmA, tmB, p);
-    else if (mt == 2) conv_gemm_kernel<2><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(tmOut, tmA, tmB, p);
-    else conv_gemm_kernel<4><<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(tmOut, tmA, tmB, p);
+    if (mt == 1) irc::launch<1>(conv_gemm_kernel<1>, grid, kConvThreads, smem, (cudaStream_t)stream, tmOut, tmA, tmB, p);
+    else if (mt == 2) irc::launch<1>(conv_gemm_kernel<2>, grid, kConvThreads, smem, (cudaStream_t)stream, tmOut, tmA, tmB, p);
+    else irc::launch<1>(conv_gemm_kernel<4>, grid, kConvThreads, smem, (cudaStream_t)stream, tmOut, tmA, tmB, p);
     return irc_check_launch("irc_conv_gemm");
 }
 
@@ -898,11 +901,11 @@ extern "C" int irc_tn_gemm(const irc_tn_gemm_args* a, void* stream) {
     const unsigned grid = (unsigned)((long long)p.m_tiles * p.n_tiles * p.groups * p.splits);
     cudaStream_t st = (cudaStream_t)stream;
     switch (tpc) {
-        case 1: tn_gemm_kernel<1><<<grid, kThreads, smem, st>>>(tmA, tmB, p); break;
-        case 2: tn_gemm_kernel<2><<<grid, kThreads, smem, st>>>(tmA, tmB, p); break;
-        case 3: tn_gemm_kernel<3><<<grid, kThreads, smem, st>>>(tmA, tmB, p); break;
-        case 4: tn_gemm_kernel<4><<<grid, kThreads, smem, st>>>(tmA, tmB, p); break;
-        default: tn_gemm_kernel<8><<<grid, kThreads, smem, st>>>(tmA, tmB, p); break;
+        case 1: irc::launch<1>(tn_gemm_kernel<1>, grid, kThreads, smem, st, tmA, tmB, p); break;
+        case 2: irc::launch<1>(tn_gemm_kernel<2>, grid, kThreads, smem, st, tmA, tmB, p); break;
+        case 3: irc::launch<1>(tn_gemm_kernel<3>, grid, kThreads, smem, st, tmA, tmB, p); break;
+        case 4: irc::launch<1>(tn_gemm_kernel<4>, grid, kThreads, smem, st, tmA, tmB, p); break;
+        default: irc::launch<1>(tn_gemm_kernel<8>, grid, kThreads, smem, st, tmA, tmB, p); break;
     }
     return irc_check_launch("irc_tn_gemm");
 }

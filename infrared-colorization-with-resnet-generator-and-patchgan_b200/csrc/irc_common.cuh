@@ -19,8 +19,32 @@ typedef __nv_bfloat16 bf16;
 int irc_set_error(int code, const char* fmt, ...);
 int irc_check_launch(const char* what);
 int irc_num_sms();
+int irc_pdl_enabled();
 
 namespace irc {
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library starts with pdl_prologue(): `griddepcontrol.wait` blocks until the preceding grid of the
+// stream has completed and its writes are visible (so nothing below it can race with the producer), and
+// `griddepcontrol.launch_dependents` lets the NEXT grid's CTAs be placed on the SMs this grid's tail leaves idle, where
+// they park on their own wait.  Launch latency, CTA scheduling and the ramp-down of one kernel overlap the ramp-up of the
+// next; the dependency chain itself is unchanged (each grid still waits for the full completion of its predecessor).
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// cls: 0 = memory-bound kernels, 1 = tensor-core GEMMs (bit `cls` of IRC_PDL enables the attribute for that class)
+template <int cls = 0, typename... Exp, typename... Act>
+inline void launch(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Act&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (irc_pdl_enabled() >> cls) & 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<Exp>(args)...);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -180,8 +204,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
-    __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
-    return __bfloat1622float2(h);
+    // bf16 -> fp32 is a 16-bit shift: one SHL for the low element, one LOP for the high one
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
 }  // namespace irc

@@ -11,6 +11,7 @@ namespace {
 // hyper = {lr, beta1, beta2, eps, 1-beta1^t, 1-beta2^t, grad_scale}
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
                             const float* __restrict__ hyper) {
+    irc::pdl_prologue();
     const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], bc1 = hyper[4], bc2 = hyper[5], gs = hyper[6];
     const float step = __fdiv_rn(lr, bc1), inv_sqrt_bc2 = __fdiv_rn(1.f, sqrtf(bc2));
     const long long n4 = n >> 2;
@@ -37,6 +38,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 __global__ void pack_kernel(const float* __restrict__ src, const int* __restrict__ map, long long n, bf16* __restrict__ dst) {
+    irc::pdl_prologue();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int j = map[i];
         dst[i] = __float2bfloat16(j >= 0 ? src[j] : 0.f);
@@ -45,6 +47,7 @@ __global__ void pack_kernel(const float* __restrict__ src, const int* __restrict
 
 __global__ void gather_sum_kernel(const float* __restrict__ src, const int* __restrict__ map, long long n, int splits, long long split_stride,
                                   float* __restrict__ dst) {
+    irc::pdl_prologue();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int j = map[i];
         float a = 0.f;
@@ -66,18 +69,18 @@ int grid_for(long long total, int threads) {
 extern "C" int irc_adam(float* p, const float* g, float* m, float* v, long long n, const float* hyper, void* stream) {
     if (!p || !g || !m || !v || !hyper) return irc_set_error(IRC_ERR_BAD_ARG, "irc_adam: null");
     if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return irc_set_error(IRC_ERR_BAD_ARG, "irc_adam: arenas must be 16-byte aligned");
-    adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper);
+    irc::launch(adam_kernel, grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream, p, g, m, v, n, hyper);
     return irc_check_launch("irc_adam");
 }
 
 extern "C" int irc_pack_bf16(const float* src, const int* map, long long n, void* dst, void* stream) {
     if (!src || !map || !dst) return irc_set_error(IRC_ERR_BAD_ARG, "irc_pack_bf16: null");
-    pack_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, map, n, (bf16*)dst);
+    irc::launch(pack_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, src, map, n, (bf16*)dst);
     return irc_check_launch("irc_pack_bf16");
 }
 
 extern "C" int irc_gather_sum(const float* src, const int* map, long long n, int splits, long long split_stride, float* dst, void* stream) {
     if (!src || !map || !dst) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather_sum: null");
-    gather_sum_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, map, n, splits, split_stride, dst);
+    irc::launch(gather_sum_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, src, map, n, splits, split_stride, dst);
     return irc_check_launch("irc_gather_sum");
 }

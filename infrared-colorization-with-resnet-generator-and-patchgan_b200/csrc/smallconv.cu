@@ -66,45 +66,62 @@ struct Im2colP {
     bf16* dst; short* row_img;
 };
 
-__global__ void im2col_kernel(const Im2colP p) {
-    // one block per (image, line of the row order); thread = (item of the line, group of 8 columns)
-    __shared__ int lut[64];          // column -> (c, r, s) packed, -1 = zero padding column
+__global__ void __launch_bounds__(256) im2col_kernel(const Im2colP p) {
+    irc::pdl_prologue();
+    // one block per (image, line of the row order); thread = (item of the line, group of 8 columns).  The 8 columns of a
+    // thread never change, so their (source, element offset, scale, shift) live in registers: a row whose k x k window is
+    // interior costs one add + one load per element; only border rows decode (r, s) and reflect / zero-fill.
     const int C = p.c1 + p.c2;
     const int K = p.k * p.k * C;
-    if (threadIdx.x < 64) {
-        const int col = threadIdx.x;
-        int v = -1;
-        if (col < K) { const int c = col % C, rs = col / C; v = c | ((rs / p.k) << 8) | ((rs % p.k) << 16); }
-        lut[col] = v;
-    }
-    __syncthreads();
-    const int nl = p.rm.lines(), ll = p.rm.line_len();
     const int g = threadIdx.x & 7;
+    int off[8], rs_[8]; float sc[8], sh[8]; unsigned sel = 0, valid = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int col = g * 8 + j;
+        off[j] = 0; rs_[j] = 0; sc[j] = 1.f; sh[j] = 0.f;
+        if (col < K) {
+            const int c = col % C, rs = col / C, r = rs / p.k, s_ = rs % p.k;
+            valid |= 1u << j;
+            const int cc = c < p.c1 ? c : c - p.c1;
+            if (c >= p.c1) sel |= 1u << j;
+            off[j] = (cc * p.H + r) * p.W + s_;
+            rs_[j] = cc | (r << 8) | (s_ << 16);
+            if (p.scale) { sc[j] = __ldg(p.scale + c); sh[j] = __ldg(p.shift + c); }
+        }
+    }
+    const int nl = p.rm.lines(), ll = p.rm.line_len();
+    const long long hw = (long long)p.H * p.W;
     for (int bl = blockIdx.x; bl < p.rm.n_img * nl; bl += gridDim.x) {
         const int n = bl / nl, line = bl - n * nl;
+        const float* b1 = p.src1 + (long long)n * p.c1 * hw;
+        const float* b2 = p.src2 ? p.src2 + (long long)n * p.c2 * hw : b1;
         for (int i = threadIdx.x >> 3; i < ll; i += blockDim.x >> 3) {
             const long long q = (long long)bl * ll + i;
             int oy, ox;
             const bool live = p.rm.decode_line(line, i, oy, ox);
             if (g == 0 && p.row_img) p.row_img[q] = live ? (short)n : (short)-1;
-            float v[8];
+            float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (live) {
+                const int y0 = oy * p.stride - p.pad, x0 = ox * p.stride - p.pad;
+                if (y0 >= 0 && x0 >= 0 && y0 + p.k <= p.H && x0 + p.k <= p.W) {
+                    const int pix = y0 * p.W + x0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int e = lut[g * 8 + j];
-                float val = 0.f;
-                if (live && e >= 0) {
-                    const int c = e & 255, r = (e >> 8) & 255, s_ = e >> 16;
-                    int y = oy * p.stride - p.pad + r, x = ox * p.stride - p.pad + s_;
-                    bool ok = true;
-                    if (p.pad_mode == 1) { y = reflect_idx(y, p.H); x = reflect_idx(x, p.W); }
-                    else ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
-                    if (ok) {
-                        const float raw = c < p.c1 ? __ldg(p.src1 + (((long long)n * p.c1 + c) * p.H + y) * p.W + x)
-                                                   : __ldg(p.src2 + (((long long)n * p.c2 + (c - p.c1)) * p.H + y) * p.W + x);
-                        val = p.scale ? raw * __ldg(p.scale + c) + __ldg(p.shift + c) : raw;
+                    for (int j = 0; j < 8; ++j) {
+                        const float raw = __ldg(((sel >> j) & 1 ? b2 : b1) + pix + off[j]);
+                        v[j] = (valid >> j) & 1 ? fmaf(raw, sc[j], sh[j]) : 0.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (!((valid >> j) & 1)) continue;
+                        const int cc = rs_[j] & 255;
+                        int y = y0 + ((rs_[j] >> 8) & 255), x = x0 + (rs_[j] >> 16);
+                        bool ok = true;
+                        if (p.pad_mode == 1) { y = reflect_idx(y, p.H); x = reflect_idx(x, p.W); }
+                        else ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
+                        if (ok) v[j] = fmaf(__ldg(((sel >> j) & 1 ? b2 : b1) + ((long long)cc * p.H + y) * p.W + x), sc[j], sh[j]);
                     }
                 }
-                v[j] = val;
             }
             *reinterpret_cast<uint4*>(p.dst + q * 64 + g * 8) =
                 make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
@@ -121,6 +138,7 @@ struct Col2imP {
 };
 
 __global__ void col2im_kernel(const Col2imP p) {
+    irc::pdl_prologue();
     const long long total = (long long)p.rm.n_img * p.c_out * p.H * p.W;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         long long t = idx;
@@ -157,6 +175,7 @@ struct TapP {
 
 // out[n][co][y][x] = act(bias[co] + sum_j P[q + shift_j][j*nco + co])
 __global__ void tap_reduce_kernel(const float* P, long long ldp, const float* bias, int act, float* out, const TapP t) {
+    irc::pdl_prologue();
     const long long total = (long long)t.n_img * t.H * t.W;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(idx % t.W);
@@ -175,25 +194,32 @@ __global__ void tap_reduce_kernel(const float* P, long long ldp, const float* bi
 // E[q][j*nco + co] = g'[pixel(q - shift_j)][co];  g' = g * (1 - yv^2) when yv is given (tanh').
 // A shifted position that leaves its frame line lands in the padding ring (the ring is at least as wide as the
 // largest horizontal shift), i.e. on a zero, so the (dy, dx) decomposition needs no wrap-around handling.
-__global__ void tap_expand_kernel(const float* g, const float* yv, bf16* E, const TapP t) {
+__global__ void __launch_bounds__(256) tap_expand_kernel(const float* g, const float* yv, bf16* E, const TapP t) {
+    irc::pdl_prologue();
     const int ncol = t.nshift * t.nco;
     const int grp = threadIdx.x & 7;
+    // the 8 columns of a thread are fixed: their (tap shift, output channel) decode once
+    int cdy[8], cdx[8], cco[8]; unsigned valid = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int col = grp * 8 + k;
+        cdy[k] = cdx[k] = cco[k] = 0;
+        if (col < ncol) { const int j = col / t.nco; valid |= 1u << k; cco[k] = col - j * t.nco; cdy[k] = t.dy[j] + t.oy; cdx[k] = t.dx[j] + t.ox; }
+    }
+    const long long hw = (long long)t.H * t.W;
     for (int row = blockIdx.x; row < t.n_img * t.hp; row += gridDim.x) {
         const int n = row / t.hp, Y = row - n * t.hp;
+        const long long nb = (long long)n * t.nco * hw;
         for (int X = threadIdx.x >> 3; X < t.wp; X += blockDim.x >> 3) {
             float v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const int col = grp * 8 + k;
                 float val = 0.f;
-                if (col < ncol) {
-                    const int j = col / t.nco, co = col - j * t.nco;
-                    const int y = Y - t.dy[j] - t.oy, x = X - t.dx[j] - t.ox;
-                    if (x >= 0 && x < t.W && y >= 0 && y < t.H) {
-                        const long long o = (((long long)n * t.nco + co) * t.H + y) * t.W + x;
-                        val = __ldg(g + o);
-                        if (yv) { const float yy = __ldg(yv + o); val *= (1.f - yy * yy); }
-                    }
+                const int y = Y - cdy[k], x = X - cdx[k];
+                if (((valid >> k) & 1) && x >= 0 && x < t.W && y >= 0 && y < t.H) {
+                    const long long o = nb + cco[k] * hw + y * t.W + x;
+                    val = __ldg(g + o);
+                    if (yv) { const float yy = __ldg(yv + o); val *= (1.f - yy * yy); }
                 }
                 v[k] = val;
             }
@@ -206,6 +232,7 @@ __global__ void tap_expand_kernel(const float* g, const float* yv, bf16* E, cons
 // part[b][c] = partial sum over block b's slice of sum_{n, pixels} g[n][c][.] * (1 - yv^2); chan_sum_final adds the
 // partials in a fixed order (bit-reproducible)
 __global__ void chan_sum_kernel(const float* g, const float* yv, int n_img, int C, long long hw, float* part) {
+    irc::pdl_prologue();
     __shared__ float sh[32];
     const int c = blockIdx.y;
     float s = 0.f;
@@ -221,6 +248,7 @@ __global__ void chan_sum_kernel(const float* g, const float* yv, int n_img, int 
     if (threadIdx.x == 0) part[(long long)blockIdx.x * C + c] = s;
 }
 __global__ void chan_sum_final(const float* part, int nb, int C, float* out) {
+    irc::pdl_prologue();
     const int c = threadIdx.x;
     if (c < C) { float a = 0.f; for (int b = 0; b < nb; ++b) a += part[(long long)b * C + c]; out[c] = a; }
 }
@@ -252,7 +280,7 @@ extern "C" int irc_im2col(const irc_im2col_args* a, void* stream) {
     p.rm.mode = a->row_mode; p.rm.n_img = a->n_img; p.rm.Ho = a->Ho; p.rm.Wo = a->Wo;
     p.dst = (bf16*)a->dst; p.row_img = a->row_img;
     const long long nblk = (long long)p.rm.n_img * p.rm.lines();
-    im2col_kernel<<<(unsigned)(nblk < 1048576 ? nblk : 1048576), 256, 0, (cudaStream_t)stream>>>(p);
+    irc::launch(im2col_kernel, (unsigned)(nblk < 1048576 ? nblk : 1048576), 256, 0, (cudaStream_t)stream, p);
     return irc_check_launch("irc_im2col");
 }
 
@@ -264,7 +292,7 @@ extern "C" int irc_col2im(const irc_col2im_args* a, void* stream) {
     p.rm.mode = a->row_mode; p.rm.n_img = a->n_img; p.rm.Ho = a->Ho; p.rm.Wo = a->Wo;
     p.out = a->out; p.accumulate = a->accumulate;
     const long long total = (long long)a->n_img * a->c_out * a->H * a->W;
-    col2im_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    irc::launch(col2im_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, p);
     return irc_check_launch("irc_col2im");
 }
 
@@ -284,7 +312,7 @@ static int fill_tap(const irc_tap_args* a, TapP& t) {
 extern "C" int irc_tap_reduce(const irc_tap_args* a, const float* P, long long ldp, const float* bias, int act, float* out, void* stream) {
     TapP t; int rc = fill_tap(a, t); if (rc) return rc;
     if (!P || !out) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tap_reduce: null");
-    tap_reduce_kernel<<<grid_for((long long)t.n_img * t.H * t.W, 256), 256, 0, (cudaStream_t)stream>>>(P, ldp, bias, act, out, t);
+    irc::launch(tap_reduce_kernel, grid_for((long long)t.n_img * t.H * t.W, 256), 256, 0, (cudaStream_t)stream, P, ldp, bias, act, out, t);
     return irc_check_launch("irc_tap_reduce");
 }
 
@@ -293,7 +321,7 @@ extern "C" int irc_tap_expand(const irc_tap_args* a, const float* g, const float
     TapP t; int rc = fill_tap(a, t); if (rc) return rc;
     if (!g || !E) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tap_expand: null");
     const long long nrow = (long long)t.n_img * t.hp;
-    tap_expand_kernel<<<(unsigned)(nrow < 1048576 ? nrow : 1048576), 256, 0, (cudaStream_t)stream>>>(g, y, (bf16*)E, t);
+    irc::launch(tap_expand_kernel, (unsigned)(nrow < 1048576 ? nrow : 1048576), 256, 0, (cudaStream_t)stream, g, y, (bf16*)E, t);
     rc = irc_check_launch("irc_tap_expand"); if (rc) return rc;
     if (dbias) {
         const long long hw = (long long)t.H * t.W;
@@ -301,8 +329,8 @@ extern "C" int irc_tap_expand(const irc_tap_args* a, const float* g, const float
         if (nb > 512) nb = 512;
         if (!work || work_floats < nb * t.nco) nb = 1;
         float* part = nb == 1 ? dbias : work;
-        chan_sum_kernel<<<dim3((unsigned)nb, t.nco), 256, 0, (cudaStream_t)stream>>>(g, y, t.n_img, t.nco, hw, part);
-        if (nb > 1) chan_sum_final<<<1, 64, 0, (cudaStream_t)stream>>>(work, (int)nb, t.nco, dbias);
+        irc::launch(chan_sum_kernel, dim3((unsigned)nb, t.nco), 256, 0, (cudaStream_t)stream, g, y, t.n_img, t.nco, hw, part);
+        if (nb > 1) irc::launch(chan_sum_final, 1, 64, 0, (cudaStream_t)stream, work, (int)nb, t.nco, dbias);
         rc = irc_check_launch("irc_tap_expand(dbias)");
     }
     return rc;

@@ -9,14 +9,14 @@ from irc_b200 import layout as L
 be = CudaBackend()
 B = 16
 dev = "cuda"
-flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+flush = torch.zeros(512 << 20, dtype=torch.uint8, device=dev)
 
 
 def timeit(name, fn, bytes_, reps=5):
     fn(); torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
-        flush.zero_()
+        flush.sum()          # evict L2 with clean lines (a write flush would leave dirty lines the timed kernel has to write back)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
@@ -72,16 +72,16 @@ dZb = F(64, 64, 1, 256)
 timeit("in_bwd identity 256ch 64^2 (resblock)", lambda: be.in_bwd(Zb.view(), X.view(), dZb.view(), 256, B, 64, 64, stats=s256, cnt=4096, act=0, bsum=bs), B * 4096 * 256 * 2 * 5)
 # transposed stencils (backward), materialised by the tiled gather
 g1 = F(H, W, 0, 128)
-timeit("gather down^T 2src 128ch ->256^2 (tiled)", lambda: be.gather(Gc1.view(256), g1.view(), 128, B, H, W, 0, 0, tables=tdT, src2=Gx1.view()),
+timeit("gather down^T 2src 128ch ->256^2 ", lambda: be.gather(Gc1.view(256), g1.view(), 128, B, H, W, 0, 0, tables=tdT, src2=Gx1.view()),
        n * 128 * 2 + 2 * n // 4 * 128 * 2)
 timeit("in_bwd identity 1src 128ch 256^2", lambda: be.in_bwd(Z1.view(), g1.view(), dZ1.view(), 128, B, H, W, stats=s128, cnt=H * W, act=1, bsum=bs),
        n * 128 * 2 * 5)
 g3 = F(H // 2, W // 2, 0, 128)
 tupT = L.make_tables(L.up_matrix(H // 2).T, L.up_matrix(W // 2).T, dev)
-timeit("gather up^T 128ch 256^2->128^2 (tiled)", lambda: be.gather(cat2.view(0), g3.view(), 128, B, H // 2, W // 2, 0, 0, tables=tupT),
+timeit("gather up^T 128ch 256^2->128^2 ", lambda: be.gather(cat2.view(0), g3.view(), 128, B, H // 2, W // 2, 0, 0, tables=tupT),
        n * 128 * 2 + n // 4 * 128 * 2)
 g4 = F(H, W, 0, 64)
-timeit("gather fold3 64ch 256^2 (tiled)", lambda: be.gather(G4.pview(), g4.view(), 64, B, H, W, 0, 0, tables=tf3), n * 64 * 2 * 2)
+timeit("gather fold3 64ch 256^2 ", lambda: be.gather(G4.pview(), g4.view(), 64, B, H, W, 0, 0, tables=tf3), n * 64 * 2 * 2)
 Gh = F(64, 64, 1, 256); dZa = F(64, 64, 1, 256)
 tf1 = L.make_tables(L.fold_matrix(64, 1), L.fold_matrix(64, 1), dev)
 timeit("in_bwd fold1 256ch 64^2 (resblock, fused)", lambda: be.in_bwd(Zb.view(), Gh.pview(), dZa.view(), 256, B, 64, 64, stats=s256, cnt=4096, act=1, tables=tf1, bsum=bs), B * 4096 * 256 * 2 * 5)

@@ -139,6 +139,37 @@ def test_gather_stream(bes, mode, C, H, W):
     close(a[0], d2, 1e-2, mode + " vs lean")
 
 
+@pytest.mark.parametrize("kind", ["down", "up", "downT", "upT"])
+@pytest.mark.parametrize("n,c,h,w", [(2, 3, 16, 24), (1, 5, 40, 72), (3, 2, 10, 300)])
+def test_stencil_nchw_stream(bes, kind, n, c, h, w):
+    """stand-alone fp32 Downsample / UpsampleAA (irc:307-310, :350-355) and their transposes: streaming kernel == row kernel ==
+    torch restatement; odd plane counts, several strips / column chunks, accumulate mode"""
+    from irc_b200 import layout as L
+    g = gen(11)
+    if kind == "down":
+        t = L.make_tables(L.down_matrix(h), L.down_matrix(w), "cuda"); ho, wo, hi, wi = h // 2, w // 2, h, w
+    elif kind == "up":
+        t = L.make_tables(L.up_matrix(h), L.up_matrix(w), "cuda"); ho, wo, hi, wi = 2 * h, 2 * w, h, w
+    elif kind == "downT":
+        t = L.make_tables(L.down_matrix(h).T, L.down_matrix(w).T, "cuda"); ho, wo, hi, wi = h, w, h // 2, w // 2
+    else:
+        t = L.make_tables(L.up_matrix(h).T, L.up_matrix(w).T, "cuda"); ho, wo, hi, wi = h, w, 2 * h, 2 * w
+    assert t.stream_window(8) > 0
+    x = torch.randn(n, c, hi, wi, device="cuda", generator=g)
+    o0 = torch.randn(n, c, ho, wo, device="cuda", generator=g)
+    for acc in (False, True):
+        a, b = both(bes, lambda be, o: be.stencil_nchw(x, o, t, accumulate=acc), [o0])
+        close(a[0], b[0], 1e-5, f"{kind} stream acc={acc}")
+        be = bes[0]
+        old = be.gather_mode
+        try:
+            be.gather_mode = "lean"
+            o2 = o0.clone(); be.stencil_nchw(x, o2, t, accumulate=acc); torch.cuda.synchronize()
+        finally:
+            be.gather_mode = old
+        close(a[0], o2, 1e-5, f"{kind} stream vs row kernel acc={acc}")
+
+
 @pytest.mark.parametrize("mode", ["norm_relu_fold", "norm_none_two", "plain_lrelu", "upT", "s2d_src"])
 def test_in_bwd(bes, mode):
     from irc_b200 import layout as L
@@ -284,6 +315,22 @@ def test_losses_vs_reference_golden(bes):
     be.pixel_loss(a, b, 1.0, 0.0, 0.0, sums, d)
     assert abs(sums[0].item() - (a - b).abs().sum().item()) < 1e-2
     assert torch.equal(d, torch.sign(a - b))
+
+
+@pytest.mark.parametrize("h,w", [(20, 32), (17, 30), (64, 260)])
+def test_pixel_loss_paths(bes, h, w):
+    """fused L1 + TV (irc:686-694, :1664): the float4 kernel (W % 4 == 0) and the scalar one against torch autograd"""
+    be = bes[0]
+    g = gen(9)
+    a = torch.randn(3, 3, h, w, device="cuda", generator=g); b = torch.randn(3, 3, h, w, device="cuda", generator=g)
+    x = a.clone().requires_grad_(True)
+    l1 = (x - b).abs().sum(); tvv = (x[:, :, 1:] - x[:, :, :-1]).abs().sum(); tvh = (x[:, :, :, 1:] - x[:, :, :, :-1]).abs().sum()
+    (0.7 * l1 + 0.3 * tvv + 0.2 * tvh).backward()
+    sums = torch.zeros(3, device="cuda"); d = torch.zeros_like(a)
+    be.pixel_loss(a, b, 0.7, 0.3, 0.2, sums, d)
+    for got, ref in zip(sums.tolist(), (l1.item(), tvv.item(), tvh.item())):
+        assert abs(got - ref) <= 1e-4 * abs(ref)
+    close(d, x.grad, 1e-6, "pixel_loss grad")
 
 
 def test_hinge_featl1(bes):
