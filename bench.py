@@ -149,12 +149,13 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     B, (H, W) = args.batch, args.size
     W_, K = max(args.warmup, 3), args.steps
 
     be = CudaBackend()
-    ts = TrainStep(be, B, H, W, dev, world_size=world, use_graph=(world == 1 and not args.no_graph))
+    ts = TrainStep(be, B, H, W, dev, world_size=world, use_graph=(not args.no_graph))
     ts.load(O.seeded_params(O.generator_shapes(), 1234), O.seeded_params(O.discriminator_shapes(), 1235),
             O.seeded_params(O.vgg_shapes(), 1236, kaiming=True))
     ir_h, rgb_h = O.synthetic_pair(B, H, W, rank)
@@ -225,9 +226,16 @@ def main():
             for (kind, name, role), (n, fl, t) in sorted(agg.items(), key=lambda kv: -kv[1][2]):
                 f.write(f"{kind},{name},{role},{n},{fl / n / 1e9:.2f},{t / n:.4f},{fl / (t * 1e-3) / 1e12:.1f},{fl / (t * 1e-3) / 1e12 / pk['tf']:.3f}\n")
 
-    if rank != 0:
+    def shutdown():
+        # a captured graph that contains NCCL kernels must be released before the communicator goes away
+        ts.graph = None
+        torch.cuda.synchronize()
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
+
+    if rank != 0:
+        shutdown()
         return
 
     cpu_baseline = None
@@ -263,8 +271,7 @@ def main():
         losses={k: round(v, 5) for k, v in losses.items()},
     )
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 if __name__ == "__main__":

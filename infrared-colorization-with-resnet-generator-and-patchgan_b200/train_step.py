@@ -65,7 +65,9 @@ class TrainStep:
         self.ga, self.gb, self.gc = (torch.zeros(B, 3, H, W, device=device) for _ in range(3))
         self.ir = torch.zeros(B, 1, H, W, device=device)
         self.rgb = torch.zeros(B, 3, H, W, device=device)
-        self.use_graph = use_graph and world_size == 1
+        # NCCL collectives are capturable (torch's ProcessGroupNCCL records them on its own stream with event edges), so the
+        # data-parallel step replays as one graph too
+        self.use_graph = use_graph
         self.graph = None
         self._side = None
         self.n_pred = self.D1.pred[0].numel()
