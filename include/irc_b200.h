@@ -142,6 +142,11 @@ typedef struct irc_in_bwd_args {
 } irc_in_bwd_args;
 int irc_in_bwd_reduce(const irc_in_bwd_args* args, void* stream);
 int irc_in_bwd_apply(const irc_in_bwd_args* args, void* stream);
+/* reduce + apply in ONE launch for small maps (H*W <= 4096, C % 32 == 0, one source, no tables, stats given): a
+ * thread-block cluster per (image, 32 channels) keeps g and z in registers and exchanges the sums through distributed
+ * shared memory.  fold_pad > 0: g1 views a frame that holds the gradient w.r.t. ReflectionPad2d(fold_pad) of the map;
+ * the ring pixels are folded onto the interior while loading (the ring itself is left untouched).  bsum is optional. */
+int irc_in_bwd_fused(const irc_in_bwd_args* args, int fold_pad, void* stream);
 
 /* Backward of nn.ReflectionPad2d(p) in place on a frame holding the gradient w.r.t. the padded tensor: interior pixels
  * within p of the border receive the ring pixels that mirror onto them; the ring is cleared. */

@@ -18,7 +18,7 @@ MAX_TAPS = 64
 
 EXPORTS = [
     "irc_version", "irc_arch_check", "irc_last_error", "irc_conv_gemm", "irc_tn_gemm", "irc_tn_gemm_ctas", "irc_row_index",
-    "irc_in_stats", "irc_gather", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_maxpool2", "irc_maxpool2_bwd",
+    "irc_in_stats", "irc_gather", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_in_bwd_fused", "irc_maxpool2", "irc_maxpool2_bwd",
     "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
     "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics",
     "irc_adam", "irc_pack_bf16", "irc_gather_sum", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
@@ -269,10 +269,16 @@ class CudaBackend:
         self.note = ("", "", 0.0)
         self.conv_mt = int(os.environ.get("IRC_CONV_MT", "0"))   # 0 = let the library choose the M sub-tiling of conv_gemm
         self.conv_dbg = None
+        self.fused_in_bwd = os.environ.get("IRC_FUSED_IN_BWD", "1") != "0"   # cluster-resident single-pass InstanceNorm backward
         self.gather_mode = os.environ.get("IRC_GATHER", "auto")     # lean | tiled | generic (stencil gather kernel choice)
         self.conv_epilogue_direct = int(os.environ.get("IRC_EPI_DIRECT", "0"))
         self.conv_dbg_mode = 0
         self.conv_reuse = int(os.environ.get("IRC_CONV_REUSE", "0"))
+        # timing ablation only (results become wrong): IRC_SKIP=fold_inplace,in_stats,... turns those launchers into
+        # no-ops so that a captured step shows their real cost inside the graph (scripts/ablate.sh)
+        for name in filter(None, os.environ.get("IRC_SKIP", "").split(",")):
+            assert hasattr(self, name), name
+            setattr(self, name, lambda *a, **k: None)
 
     def _timed(self, kind, fn):
         if self.timers is None:
@@ -377,9 +383,17 @@ class CudaBackend:
         return g
 
     def in_bwd(self, z: View, g1: View, dz: View, C_, n_img, H, W, stats=None, cnt=0.0, eps=1e-5, act=0, slope=0.0,
-               tables: Tables = IDENTITY, g2=None, bsum=None):
-        """reduce (when normalised) + apply."""
+               tables: Tables = IDENTITY, g2=None, bsum=None, fold_pad=0):
+        """reduce (when normalised) + apply.  fold_pad > 0: g1 is the view of a frame holding the gradient w.r.t. the
+        reflection-padded map (ring included); the fold happens inside (fused kernel) or as a separate in-place pass."""
         g = self._bwd_args(z, g1, g2, dz, C_, n_img, H, W, stats, cnt, eps, act, slope, tables, bsum)
+        fused = (self.fused_in_bwd and stats is not None and g2 is None and tables.ty_idx is None and tables.tx_idx is None
+                 and C_ % 32 == 0 and H * W <= 4096)
+        if fused:
+            check(self.L.irc_in_bwd_fused(C.byref(g), fold_pad, _stream())); self.launches += 1
+            return
+        if fold_pad:
+            self.fold_inplace(g1.t, g1.chan_off, C_, n_img, H, W, fold_pad)
         if stats is not None:
             check(self.L.irc_in_bwd_reduce(C.byref(g), _stream())); self.launches += 1
         check(self.L.irc_in_bwd_apply(C.byref(g), _stream())); self.launches += 1

@@ -1,10 +1,13 @@
 // Memory-bound passes on NHWC bf16 frames: InstanceNorm statistics / apply / backward,
 // separable table stencils (anti-aliased Downsample and UpsampleAA, halo folding), all
 // vectorised 8 channels (16 bytes) per thread and coalesced along the channel axis.
+#include <cooperative_groups.h>
+
 #include "irc_common.cuh"
 #include "../../include/irc_b200.h"
 
 using namespace irc;
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -728,6 +731,151 @@ __global__ void __launch_bounds__(256, 4) in_bwd_apply_kernel(const InBwdP p) {
 }
 
 // ---------------------------------------------------------------------------------
+// Single-pass InstanceNorm(+activation) backward for small feature maps (H*W <= 4096: the ResNet bottleneck and the
+// PatchGAN layers).  One thread-block CLUSTER owns one (image, 32-channel group): its CTAs split the pixels, every thread
+// keeps its <= 8 pixels of g and z (16 bytes each) in REGISTERS, the (sum gd, sum gd*xhat) partials are combined inside
+// the CTA by shuffles + shared memory and across the cluster through distributed shared memory (fixed order:
+// bit-reproducible), and dz is produced from the registers.  g and z are read once, dz written once: 3 passes over the
+// tensor instead of 5, one launch instead of two; with fold_pad > 0 the transpose of ReflectionPad2d(fold_pad) is applied
+// while g is loaded (border pixels add the ring pixels that mirror onto them), replacing a third launch.
+// ---------------------------------------------------------------------------------
+constexpr int kFusedNP = 8;      // pixels per thread
+constexpr int kFusedCC = 32;     // channels per cluster
+constexpr int kFusedLanes = 64;  // pixel lanes per CTA (256 threads = 64 lanes x 4 channel vectors)
+
+__device__ __forceinline__ int mirror_src(int v, int n, int p) {
+    // interior coordinate v of an axis of length n: the ring coordinate (in interior units, < 0 or >= n) that
+    // ReflectionPad2d(p) mirrors onto v, or INT_MIN when there is none
+    if (v >= 1 && v <= p) return -v;
+    if (v >= n - 1 - p && v <= n - 2) return 2 * (n - 1) - v;
+    return INT_MIN;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <bool kFold>
+__global__ void __launch_bounds__(256, 3) in_bwd_fused_kernel(const InBwdP p, int fold_pad) {
+    irc::pdl_prologue();
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned CL = cluster.num_blocks(), rank = cluster.block_rank();
+    extern __shared__ uint4 raw[];      // [2][kFusedNP][256]: g then z, slot [i][tid] is private to thread tid
+    __shared__ float part[64];          // this CTA's sums: [cv][k][2]
+    __shared__ float wsum[8][64];
+    __shared__ float tot[64];
+    const int tid = threadIdx.x, cv = tid & 3, lane = tid >> 2;
+    const int n = blockIdx.z, c = blockIdx.y * kFusedCC + cv * 8;
+    const int HW = p.H * p.W;
+    const int P = (HW + CL - 1) / CL;
+    const int p0 = rank * P, p1 = min(p0 + P, HW);
+    uint4* gs = raw + tid;
+    uint4* zs = raw + kFusedNP * 256 + tid;
+    // all loads of the thread go straight to its shared-memory slots (no register staging): 16 x 16 bytes in flight
+#pragma unroll
+    for (int i = 0; i < kFusedNP; ++i) {
+        const int pix = p0 + lane + i * kFusedLanes;
+        if (pix < p1) {
+            const int y = pix / p.W, x = pix - y * p.W;
+            cp_async16(gs + i * 256, p.g1.at(n, y, x, c));
+            cp_async16(zs + i * 256, p.z.at(n, y, x, c));
+        } else {
+            gs[i * 256] = make_uint4(0, 0, 0, 0); zs[i * 256] = make_uint4(0, 0, 0, 0);     // g = 0 adds nothing
+        }
+    }
+    float mu[8], rs[8];
+    moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mu[k] = -mu[k] * rs[k];
+    cp_async_wait_all();
+    if (kFold) {
+        for (int i = 0; i < kFusedNP; ++i) {
+            const int pix = p0 + lane + i * kFusedLanes;
+            if (pix >= p1) break;
+            const int y = pix / p.W, x = pix - y * p.W;
+            const int my = mirror_src(y, p.H, fold_pad), mx = mirror_src(x, p.W, fold_pad);
+            if (my == INT_MIN && mx == INT_MIN) continue;
+            float a[8], v[8];
+            unpack8(gs[i * 256], a);
+            if (my != INT_MIN) { load8(p.g1.at(n, my, x, c), v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] += v[k]; }
+            if (mx != INT_MIN) { load8(p.g1.at(n, y, mx, c), v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] += v[k]; }
+            if (my != INT_MIN && mx != INT_MIN) { load8(p.g1.at(n, my, mx, c), v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] += v[k]; }
+            // rounded to bf16 like the stand-alone fold, so both paths give the same bits
+            gs[i * 256] = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+        }
+    }
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 2
+    for (int i = 0; i < kFusedNP; ++i) {
+        float g[8], zv[8];
+        unpack8(gs[i * 256], g); unpack8(zs[i * 256], zv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float xh = fmaf(zv[k], rs[k], mu[k]);
+            const float gd = g[k] * dactf(xh, p.act, p.slope);
+            s1[k] += gd; s2[k] = fmaf(gd, xh, s2[k]);
+        }
+    }
+    // lanes of a warp that share a channel vector differ in bits 2..4 of the lane id
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], off);
+            s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], off);
+        }
+    }
+    if ((tid & 31) < 4) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { wsum[tid >> 5][cv * 16 + k * 2] = s1[k]; wsum[tid >> 5][cv * 16 + k * 2 + 1] = s2[k]; }
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += wsum[w][tid];
+        part[tid] = a;
+    }
+    cluster.sync();
+    if (tid < 64) {
+        float a = 0.f;
+        for (unsigned r = 0; r < CL; ++r) a += cluster.map_shared_rank(part, r)[tid];
+        tot[tid] = a;
+        if (rank == 0 && p.bsum) p.bsum[((long long)n * p.C + blockIdx.y * kFusedCC) * 2 + tid] = a;
+    }
+    __syncthreads();
+    float b1[8], b2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { b1[k] = tot[cv * 16 + k * 2] * p.inv_cnt; b2[k] = tot[cv * 16 + k * 2 + 1] * p.inv_cnt; }
+#pragma unroll 2
+    for (int i = 0; i < kFusedNP; ++i) {
+        const int pix = p0 + lane + i * kFusedLanes;
+        if (pix < p1) {
+            const int y = pix / p.W, x = pix - y * p.W;
+            float g[8], zv[8], o[8];
+            unpack8(gs[i * 256], g); unpack8(zs[i * 256], zv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float xh = fmaf(zv[k], rs[k], mu[k]);
+                const float gd = g[k] * dactf(xh, p.act, p.slope);
+                o[k] = rs[k] * (gd - b1[k] - xh * b2[k]);
+            }
+            store8(const_cast<bf16*>(p.dz.at(n, y, x, c)), o);
+        }
+    }
+    cluster.sync();      // `part` must outlive the remote reads of every peer
+}
+
+// ---------------------------------------------------------------------------------
 // 2x2 max pool (VGG trunk, irc:664) on frames, and its backward fused with the ReLU mask
 // ---------------------------------------------------------------------------------
 __global__ void maxpool_kernel(View src, View dst, int C, int n_img, int Ho, int Wo) {
@@ -1023,6 +1171,29 @@ extern "C" int irc_in_bwd_apply(const irc_in_bwd_args* a, void* stream) {
     if (!p.ty_idx && !p.tx_idx) irc::launch(in_bwd_apply_kernel<true>, grid, threads, 0, (cudaStream_t)stream, p);
     else irc::launch(in_bwd_apply_kernel<false>, grid, threads, 0, (cudaStream_t)stream, p);
     return irc_check_launch("irc_in_bwd_apply");
+}
+
+extern "C" int irc_in_bwd_fused(const irc_in_bwd_args* a, int fold_pad, void* stream) {
+    InBwdP p; int rc = fill_bwd(a, p); if (rc) return rc;
+    rc = check_view(a->dz, "irc_in_bwd_fused dz"); if (rc) return rc;
+    p.dz = mk(a->dz);
+    const long long hw = (long long)p.H * p.W;
+    if (!p.stats || p.has2 || p.ty_idx || p.tx_idx || p.C % kFusedCC || hw > 8 * kFusedNP * kFusedLanes || fold_pad < 0 ||
+        (fold_pad && (2 * fold_pad + 2 > p.H || 2 * fold_pad + 2 > p.W)))
+        return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_bwd_fused: needs stats, one source, identity tables, C %% 32 == 0 and H*W <= 4096");
+    unsigned cl = 1;
+    while ((long long)cl * kFusedNP * kFusedLanes < hw) cl *= 2;
+    const dim3 grid(cl, p.C / kFusedCC, p.n_img);
+    const size_t smem = 2 * kFusedNP * 256 * sizeof(uint4);       // 64 KB
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(in_bwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(in_bwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    if (fold_pad) irc::launch_cluster(in_bwd_fused_kernel<true>, grid, 256, smem, (cudaStream_t)stream, cl, p, fold_pad);
+    else irc::launch_cluster(in_bwd_fused_kernel<false>, grid, 256, smem, (cudaStream_t)stream, cl, p, fold_pad);
+    return irc_check_launch("irc_in_bwd_fused");
 }
 
 extern "C" int irc_maxpool2(const irc_view* src, const irc_view* dst, int C, int n_img, int Ho, int Wo, void* stream) {

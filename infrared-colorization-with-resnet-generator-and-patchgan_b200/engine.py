@@ -267,9 +267,10 @@ class GeneratorEngine:
             be.in_bwd(self.Zb[b].view(), cur.view(), self.dZb.view(), 256, B, H4, W4, stats=self.stb[b], cnt=n4, eps=EPS, act=ACT_NONE, bsum=self.bsum)
             c2.wgrad(self.dZb.t, self.Hh[b].t, 0, self.dZb.rows)
             c2.dgrad(self.dZb.t, self.Gh.t)
-            be.fold_inplace(self.Gh.t, 0, 256, B, H4, W4, 1)
+            # ReflectionPad2d(1)^T of Gh is folded inside the backward pass (or by a separate in-place pass when the map is
+            # too large for the single-pass cluster kernel)
             be.in_bwd(self.Za[b].view(), self.Gh.view(), self.dZa.view(), 256, B, H4, W4, stats=self.sta[b], cnt=n4, eps=EPS, act=ACT_RELU,
-                      bsum=self.bsum)
+                      bsum=self.bsum, fold_pad=1)
             c1.wgrad(self.dZa.t, self.X[b].t, 0, self.dZa.rows)
             # data gradient of conv1 + the residual-stream gradient (its frame ring is zero), then the reflection fold
             nxt = self.dOut[1] if cur is self.dOut[0] else self.dOut[0]

@@ -180,9 +180,12 @@ class RefBackend:
         else:
             self._write(dst, n_img, Yp, Xp, C, full)
 
-    def in_bwd(self, z, g1, dz, C, n_img, H, W, stats=None, cnt=0.0, eps=1e-5, act=0, slope=0.0, tables=None, g2=None, bsum=None):
+    def in_bwd(self, z, g1, dz, C, n_img, H, W, stats=None, cnt=0.0, eps=1e-5, act=0, slope=0.0, tables=None, g2=None, bsum=None,
+               fold_pad=0):
         from irc_b200._native import IDENTITY
         tables = tables or IDENTITY
+        if fold_pad:
+            self.fold_inplace(g1.t, g1.chan_off, C, n_img, H, W, fold_pad)
         self.launches += 2 if stats is not None else 1
         dev = z.t.device
         ys = torch.arange(H, device=dev); xs = torch.arange(W, device=dev)

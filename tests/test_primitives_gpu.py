@@ -170,6 +170,47 @@ def test_stencil_nchw_stream(bes, kind, n, c, h, w):
         close(a[0], o2, 1e-5, f"{kind} stream vs row kernel acc={acc}")
 
 
+@pytest.mark.parametrize("C,H,W,act,fold", [(256, 64, 64, 1, 1), (256, 64, 64, 0, 0), (512, 31, 31, 2, 0), (128, 24, 40, 1, 1),
+                                             (64, 8, 12, 2, 3), (32, 5, 7, 1, 0)])
+def test_in_bwd_fused_cluster(bes, C, H, W, act, fold):
+    """single-pass cluster kernel (InstanceNorm + activation backward, optional ReflectionPad^T on load) == the two-pass
+    kernels (+ in-place fold) == the torch restatement; cluster sizes 1..8, ragged tails, LeakyReLU / ReLU / none"""
+    from irc_b200._native import View
+    g = gen(13)
+    n = 3
+    pz = 1
+    pg = max(fold, 1)
+    z = frame(n, H, W, pz, C, g)
+    st = torch.zeros(n, C, 2, device="cuda")
+    bes[1].in_stats(z.view(), C, n, H, W, st)
+    gsrc = frame(n, H, W, pg, C, g)
+    if not fold:
+        gsrc.t.view(n, gsrc.hp, gsrc.wp, C)[:, :pg] = 7.0       # ring garbage must be ignored without a fold
+    dz = frame(n, H, W, 1, C, g)
+    bs = torch.zeros(n, 512, 2, device="cuda")
+
+    def run(be, d, fused):
+        gc = gsrc.t.clone()                                       # the two-pass path folds in place
+        gv = View(gc, 0, gsrc.hp, gsrc.wp, pg, pg)
+        old = getattr(be, "fused_in_bwd", None)
+        if old is not None:
+            be.fused_in_bwd = fused
+        try:
+            be.in_bwd(z.view(), gv, View(d, 0, dz.hp, dz.wp, 1, 1), C, n, H, W, stats=st, cnt=H * W, act=act, slope=0.2, bsum=bs,
+                      fold_pad=fold)
+        finally:
+            if old is not None:
+                be.fused_in_bwd = old
+        torch.cuda.synchronize()
+
+    outs = []
+    for be, fused in ((bes[0], True), (bes[0], False), (bes[1], False)):
+        d = dz.t.clone(); run(be, d, fused); outs.append(d)
+    close(outs[0], outs[2], 1e-2, "fused vs torch")
+    close(outs[0], outs[1], 4e-3, "fused vs two-pass")
+    assert torch.equal(outs[0].view(n, dz.hp, dz.wp, C)[:, 0], dz.t.view(n, dz.hp, dz.wp, C)[:, 0])     # ring of dz untouched
+
+
 @pytest.mark.parametrize("mode", ["norm_relu_fold", "norm_none_two", "plain_lrelu", "upT", "s2d_src"])
 def test_in_bwd(bes, mode):
     from irc_b200 import layout as L
