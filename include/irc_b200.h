@@ -127,6 +127,11 @@ typedef struct irc_gather_args {
     int tile_y, tile_x, patch_y, patch_x;
 } irc_gather_args;
 int irc_gather(const irc_gather_args* args, void* stream);
+/* InstanceNorm statistics + irc_gather's normalise / activate / residual / ring in ONE launch for small maps (H*W <= 4096,
+ * C % 32 == 0, identity tables, one source, cnt == H*W): a thread-block cluster per (image, 32 channels) stages z once,
+ * reduces through distributed shared memory and writes both stats_out[n][c] = (sum, sum of squares) and the frame.
+ * args->stats is ignored. */
+int irc_in_apply_fused(const irc_gather_args* args, float* stats_out, void* stream);
 
 /* InstanceNorm(+activation) backward (autograd of irc:161 + ReLU/LeakyReLU inside
  * loss.backward()).  g = table gather of (g1 + g2); see elementwise.cu. */

@@ -18,7 +18,7 @@ MAX_TAPS = 64
 
 EXPORTS = [
     "irc_version", "irc_arch_check", "irc_last_error", "irc_conv_gemm", "irc_tn_gemm", "irc_tn_gemm_ctas", "irc_row_index",
-    "irc_in_stats", "irc_gather", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_in_bwd_fused", "irc_maxpool2", "irc_maxpool2_bwd",
+    "irc_in_stats", "irc_gather", "irc_in_apply_fused", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_in_bwd_fused", "irc_maxpool2", "irc_maxpool2_bwd",
     "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
     "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics",
     "irc_adam", "irc_pack_bf16", "irc_gather_sum", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
@@ -270,6 +270,7 @@ class CudaBackend:
         self.conv_mt = int(os.environ.get("IRC_CONV_MT", "0"))   # 0 = let the library choose the M sub-tiling of conv_gemm
         self.conv_dbg = None
         self.fused_in_bwd = os.environ.get("IRC_FUSED_IN_BWD", "1") != "0"   # cluster-resident single-pass InstanceNorm backward
+        self.fused_in_apply = os.environ.get("IRC_FUSED_IN_APPLY", "1") != "0"
         self.gather_mode = os.environ.get("IRC_GATHER", "auto")     # lean | tiled | generic (stencil gather kernel choice)
         self.conv_epilogue_direct = int(os.environ.get("IRC_EPI_DIRECT", "0"))
         self.conv_dbg_mode = 0
@@ -368,6 +369,19 @@ class CudaBackend:
         g.tile_y, g.tile_x, g.patch_y, g.patch_x = (tables.tiling(H, W, pad, halo_mode) if (C_ % 32 == 0 and mode == "tiled") else
                                                     ((-2, 0, 0, 0) if mode == "generic" else (0, 0, 0, 0)))
         check(self.L.irc_gather(C.byref(g), _stream())); self.launches += 1
+
+    def in_apply(self, z: View, dst: View, C_, n_img, H, W, pad, halo_mode, stats, eps=1e-5, act=0, slope=0.0, res=None, dst_s2d=0):
+        """InstanceNorm of the map z (statistics written to `stats` for the backward pass) + activation (+ residual) into the
+        frame dst, ring included: one cluster launch for small maps, irc_in_stats + irc_gather otherwise."""
+        if self.fused_in_apply and not dst_s2d and not z.s2d_c and C_ % 32 == 0 and H * W <= 4096 and (pad == 0 or min(H, W) > 2 * pad + 1):
+            g = GatherArgs()
+            g.src = _cview(z); g.src2 = _cview(None); g.res = _cview(res); g.dst = _cview(dst)
+            g.C = C_; g.n_img = n_img; g.cnt = float(H * W); g.eps = eps; g.act = act; g.slope = slope
+            g.H = H; g.W = W; g.pad = pad; g.halo_mode = halo_mode
+            check(self.L.irc_in_apply_fused(C.byref(g), _p(stats), _stream())); self.launches += 1
+            return
+        self.in_stats(z, C_, n_img, H, W, stats)
+        self.gather(z, dst, C_, n_img, H, W, pad, halo_mode, stats=stats, cnt=H * W, eps=eps, act=act, slope=slope, res=res, dst_s2d=dst_s2d)
 
     def _bwd_args(self, z, g1, g2, dz, C_, n_img, H, W, stats, cnt, eps, act, slope, tables, bsum):
         g = InBwdArgs()

@@ -876,6 +876,124 @@ __global__ void __launch_bounds__(256, 3) in_bwd_fused_kernel(const InBwdP p, in
 }
 
 // ---------------------------------------------------------------------------------
+// Forward twin of the kernel above: InstanceNorm statistics + normalise + activation (+ residual) + padding ring in ONE
+// pass for small maps.  The cluster of an (image, 32-channel group) loads z once (cp.async into per-thread shared-memory
+// slots), reduces (sum, sum of squares) through distributed shared memory in a fixed order, writes the statistics the
+// backward pass needs, and produces the activated frame - interior and ring - from the staged values.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 3) in_apply_fused_kernel(const GatherP p, float* stats_out) {
+    irc::pdl_prologue();
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned CL = cluster.num_blocks(), rank = cluster.block_rank();
+    extern __shared__ uint4 raw[];      // [2][kFusedNP][256]: z then the residual
+    __shared__ float part[64];
+    __shared__ float wsum[8][64];
+    __shared__ float tot[64];
+    const int tid = threadIdx.x, cv = tid & 3, lane = tid >> 2;
+    const int n = blockIdx.z, c = blockIdx.y * kFusedCC + cv * 8;
+    const int HW = p.H * p.W;
+    const int P = (HW + CL - 1) / CL;
+    const int p0 = rank * P, p1 = min(p0 + P, HW);
+    uint4* zs = raw + tid;
+    uint4* rsd = raw + kFusedNP * 256 + tid;
+#pragma unroll
+    for (int i = 0; i < kFusedNP; ++i) {
+        const int pix = p0 + lane + i * kFusedLanes;
+        if (pix < p1) {
+            const int y = pix / p.W, x = pix - y * p.W;
+            cp_async16(zs + i * 256, p.src.at(n, y, x, c));
+            if (p.has_res) cp_async16(rsd + i * 256, p.res.at(n, y, x, c));
+        } else {
+            zs[i * 256] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    cp_async_wait_all();
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 2
+    for (int i = 0; i < kFusedNP; ++i) {
+        float v[8];
+        unpack8(zs[i * 256], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s1[k] += v[k]; s2[k] = fmaf(v[k], v[k], s2[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], off);
+            s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], off);
+        }
+    }
+    if ((tid & 31) < 4) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { wsum[tid >> 5][cv * 16 + k * 2] = s1[k]; wsum[tid >> 5][cv * 16 + k * 2 + 1] = s2[k]; }
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += wsum[w][tid];
+        part[tid] = a;
+    }
+    cluster.sync();
+    if (tid < 64) {
+        float a = 0.f;
+        for (unsigned r = 0; r < CL; ++r) a += cluster.map_shared_rank(part, r)[tid];
+        tot[tid] = a;
+        if (rank == 0) stats_out[((long long)n * p.C + blockIdx.y * kFusedCC) * 2 + tid] = a;     // (sum, sum of squares) pairs
+    }
+    __syncthreads();
+    float mu[8], rs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float m = tot[cv * 16 + k * 2] * p.inv_cnt;
+        rs[k] = rsqrtf(fmaxf(tot[cv * 16 + k * 2 + 1] * p.inv_cnt - m * m, 0.f) + p.eps);
+        mu[k] = -m * rs[k];
+    }
+    const int pad = p.pad, W = p.W, H = p.H;
+    bf16* dbase = const_cast<bf16*>(p.dst.p) + ((long long)(n * p.dst.hp + p.dst.oy - pad) * p.dst.wp + (p.dst.ox - pad)) * p.dst.ld + p.dst.off + c;
+    const long long dstep = (long long)p.dst.wp * p.dst.ld;
+#pragma unroll 2
+    for (int i = 0; i < kFusedNP; ++i) {
+        const int pix = p0 + lane + i * kFusedLanes;
+        if (pix >= p1) continue;
+        const int y = pix / W, x = pix - y * W;
+        float v[8];
+        unpack8(zs[i * 256], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float t = fmaf(v[k], rs[k], mu[k]); v[k] = fmaxf(t, 0.f) + p.slope_eff * fminf(t, 0.f); }
+        if (p.has_res) {
+            float u[8];
+            unpack8(rsd[i * 256], u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += u[k];
+        }
+        const uint4 val = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        bf16* drow = dbase + (y + pad) * dstep;
+        *reinterpret_cast<uint4*>(drow + (long long)(x + pad) * p.dst.ld) = val;
+        if (pad) {
+            // ring pixels owned by this interior pixel: the reflected copies (halo_mode 1) or zeros (halo_mode 0)
+            const uint4 ring = p.halo_mode == 1 ? val : make_uint4(0, 0, 0, 0);
+            int eX, eY;
+            if (p.halo_mode == 1) {
+                eX = (x >= 1 && x <= pad) ? pad - x : ((x >= W - 1 - pad && x <= W - 2) ? pad + 2 * (W - 1) - x : -1);
+                eY = (y >= 1 && y <= pad) ? pad - y : ((y >= H - 1 - pad && y <= H - 2) ? pad + 2 * (H - 1) - y : -1);
+            } else {
+                eX = x < pad ? x : (x >= W - pad ? x + 2 * pad : -1);
+                eY = y < pad ? y : (y >= H - pad ? y + 2 * pad : -1);
+            }
+            if (eX >= 0) *reinterpret_cast<uint4*>(drow + (long long)eX * p.dst.ld) = ring;
+            if (eY >= 0) {
+                bf16* erow = dbase + eY * dstep;
+                *reinterpret_cast<uint4*>(erow + (long long)(x + pad) * p.dst.ld) = ring;
+                if (eX >= 0) *reinterpret_cast<uint4*>(erow + (long long)eX * p.dst.ld) = ring;
+            }
+        }
+    }
+    cluster.sync();
+}
+
+// ---------------------------------------------------------------------------------
 // 2x2 max pool (VGG trunk, irc:664) on frames, and its backward fused with the ReLU mask
 // ---------------------------------------------------------------------------------
 __global__ void maxpool_kernel(View src, View dst, int C, int n_img, int Ho, int Wo) {
@@ -1130,6 +1248,32 @@ extern "C" int irc_gather(const irc_gather_args* a, void* stream) {
     if (!p.ty_idx && !p.tx_idx) irc::launch(gather_kernel<true>, grid, threads, 0, (cudaStream_t)stream, p);
     else irc::launch(gather_kernel<false>, grid, threads, 0, (cudaStream_t)stream, p);
     return irc_check_launch("irc_gather");
+}
+
+extern "C" int irc_in_apply_fused(const irc_gather_args* a, float* stats_out, void* stream) {
+    int rc = check_view(a->src, "irc_in_apply_fused src"); if (rc) return rc;
+    rc = check_view(a->dst, "irc_in_apply_fused dst"); if (rc) return rc;
+    GatherP p;
+    p.src = mk(a->src); p.dst = mk(a->dst);
+    p.has2 = 0;
+    p.has_res = a->res.ptr != nullptr; if (p.has_res) { rc = check_view(a->res, "irc_in_apply_fused res"); if (rc) return rc; p.res = mk(a->res); }
+    p.C = a->C; p.n_img = a->n_img;
+    p.stats = nullptr; p.inv_cnt = a->cnt > 0 ? 1.f / a->cnt : 0.f; p.eps = a->eps; p.act = a->act; p.slope = a->slope;
+    p.ty_idx = nullptr; p.ty_w = nullptr; p.ky = 1; p.tx_idx = nullptr; p.tx_w = nullptr; p.kx = 1;
+    p.H = a->H; p.W = a->W; p.pad = a->pad; p.halo_mode = a->halo_mode; p.dst_s2d = 0;
+    p.slope_eff = a->act == 1 ? 0.f : (a->act == 2 ? a->slope : 1.f);
+    const long long hw = (long long)p.H * p.W;
+    if (!stats_out || a->src2.ptr || a->ty_idx || a->tx_idx || a->dst_s2d || p.src.s2d_c || p.C % kFusedCC || hw > 8 * kFusedNP * kFusedLanes ||
+        a->act < 0 || a->act > 2 || (p.pad && (p.W <= 2 * p.pad + 1 || p.H <= 2 * p.pad + 1)) || a->cnt != (float)hw)
+        return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_apply_fused: needs identity tables, one source, C %% 32 == 0, H*W <= 4096, cnt == H*W");
+    unsigned cl = 1;
+    while ((long long)cl * kFusedNP * kFusedLanes < hw) cl *= 2;
+    const dim3 grid(cl, p.C / kFusedCC, p.n_img);
+    const size_t smem = 2 * kFusedNP * 256 * sizeof(uint4);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(in_apply_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    irc::launch_cluster(in_apply_fused_kernel, grid, 256, smem, (cudaStream_t)stream, cl, p, stats_out);
+    return irc_check_launch("irc_in_apply_fused");
 }
 
 static int fill_bwd(const irc_in_bwd_args* a, InBwdP& p) {

@@ -214,12 +214,9 @@ class GeneratorEngine:
         for b in range(self.nb):
             c1, c2 = self.res[b]
             c1.fwd(self.X[b].t, 0, self.Za[b].t)
-            be.in_stats(self.Za[b].view(), 256, B, H4, W4, self.sta[b])
-            be.gather(self.Za[b].view(), self.Hh[b].view(), 256, B, H4, W4, 1, 1, stats=self.sta[b], cnt=n4, eps=EPS, act=ACT_RELU)
+            be.in_apply(self.Za[b].view(), self.Hh[b].view(), 256, B, H4, W4, 1, 1, self.sta[b], eps=EPS, act=ACT_RELU)
             c2.fwd(self.Hh[b].t, 0, self.Zb[b].t)
-            be.in_stats(self.Zb[b].view(), 256, B, H4, W4, self.stb[b])
-            be.gather(self.Zb[b].view(), self.X[b + 1].view(), 256, B, H4, W4, 1, 1, stats=self.stb[b], cnt=n4, eps=EPS, act=ACT_NONE,
-                      res=self.X[b].view())
+            be.in_apply(self.Zb[b].view(), self.X[b + 1].view(), 256, B, H4, W4, 1, 1, self.stb[b], eps=EPS, act=ACT_NONE, res=self.X[b].view())
         # up1: UpsampleAA into cat1[0:256), conv on the concatenation
         be.gather(self.X[self.nb].view(), self.cat1.view(0), 256, B, H2, W2, 1, 0, tables=self.t_up1)
         self.up1.fwd(self.cat1.t, 0, self.Z3.t)
@@ -397,14 +394,10 @@ class DiscriminatorEngine:
                   cnt=self.H2 * self.W2, eps=EPS, act=ACT_LRELU, slope=0.2, dst_s2d=1)
         # model.5
         self.c5.fwd(self.S2, 0, self.Z5)
-        be.in_stats(self._vZ5(self.Z5), 256, n, self.H3, self.W3, self.st5)
-        be.gather(self._vZ5(self.Z5), self.X8.view(), 256, n, self.H3, self.W3, 1, 0, stats=self.st5, cnt=self.H3 * self.W3, eps=EPS,
-                  act=ACT_LRELU, slope=0.2)
+        be.in_apply(self._vZ5(self.Z5), self.X8.view(), 256, n, self.H3, self.W3, 1, 0, self.st5, eps=EPS, act=ACT_LRELU, slope=0.2)
         # model.8 (stride 1)
         self.c8.fwd(self.X8.t, 0, self.Z8)
-        be.in_stats(self._vZ8(self.Z8), 512, n, self.H8o, self.W8o, self.st8)
-        be.gather(self._vZ8(self.Z8), self.X11.view(), 512, n, self.H8o, self.W8o, 1, 0, stats=self.st8, cnt=self.H8o * self.W8o, eps=EPS,
-                  act=ACT_LRELU, slope=0.2)
+        be.in_apply(self._vZ8(self.Z8), self.X11.view(), 512, n, self.H8o, self.W8o, 1, 0, self.st8, eps=EPS, act=ACT_LRELU, slope=0.2)
         # model.11: 512->1, per-tap partial products then the 16-tap shifted reduction
         self.c11.fwd(self.X11.t, 0, self.P11)
         be.tap_reduce(self.P11, self.shifts11, 1, n, self.Ho, self.Wo, self.X11.hp, self.X11.wp, 0, 0, self.c11.bias(), ACT_NONE, self.pred)

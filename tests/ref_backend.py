@@ -180,6 +180,10 @@ class RefBackend:
         else:
             self._write(dst, n_img, Yp, Xp, C, full)
 
+    def in_apply(self, z, dst, C, n_img, H, W, pad, halo_mode, stats, eps=1e-5, act=0, slope=0.0, res=None, dst_s2d=0):
+        self.in_stats(z, C, n_img, H, W, stats)
+        self.gather(z, dst, C, n_img, H, W, pad, halo_mode, stats=stats, cnt=H * W, eps=eps, act=act, slope=slope, res=res, dst_s2d=dst_s2d)
+
     def in_bwd(self, z, g1, dz, C, n_img, H, W, stats=None, cnt=0.0, eps=1e-5, act=0, slope=0.0, tables=None, g2=None, bsum=None,
                fold_pad=0):
         from irc_b200._native import IDENTITY

@@ -170,6 +170,37 @@ def test_stencil_nchw_stream(bes, kind, n, c, h, w):
         close(a[0], o2, 1e-5, f"{kind} stream vs row kernel acc={acc}")
 
 
+@pytest.mark.parametrize("C,H,W,act,pad,halo,with_res", [(256, 64, 64, 1, 1, 1, False), (256, 64, 64, 0, 1, 1, True), (512, 31, 31, 2, 1, 0, False),
+                                                        (128, 24, 40, 1, 3, 1, False), (64, 8, 12, 2, 0, 0, True), (32, 5, 7, 1, 1, 0, False)])
+def test_in_apply_fused_cluster(bes, C, H, W, act, pad, halo, with_res):
+    """single-pass InstanceNorm statistics + apply (+ residual, + ring) == irc_in_stats + irc_gather == torch restatement"""
+    from irc_b200._native import View
+    g = gen(14)
+    n = 3
+    z = frame(n, H, W, 1, C, g)
+    res = frame(n, H, W, 1, C, g) if with_res else None
+    dst = frame(n, H, W, pad, C + 32, g)
+    outs = []
+    for be, fused in ((bes[0], True), (bes[0], False), (bes[1], False)):
+        d = dst.t.clone(); st = torch.zeros(n, C, 2, device="cuda")
+        old = getattr(be, "fused_in_apply", None)
+        if old is not None:
+            be.fused_in_apply = fused
+        try:
+            be.in_apply(z.view(), View(d, 32, dst.hp, dst.wp, pad, pad), C, n, H, W, pad, halo, st, act=act, slope=0.2,
+                        res=None if res is None else res.view())
+        finally:
+            if old is not None:
+                be.fused_in_apply = old
+        torch.cuda.synchronize()
+        outs.append((d, st))
+    close(outs[0][1], outs[2][1], 2e-4, "stats fused vs torch")
+    close(outs[0][1], outs[1][1], 2e-4, "stats fused vs two-pass")
+    close(outs[0][0], outs[2][0], 1e-2, "frame fused vs torch")
+    close(outs[0][0], outs[1][0], 8e-3, "frame fused vs two-pass")
+    assert torch.equal(outs[0][0][:, :32], dst.t[:, :32])          # channels outside the view untouched
+
+
 @pytest.mark.parametrize("C,H,W,act,fold", [(256, 64, 64, 1, 1), (256, 64, 64, 0, 0), (512, 31, 31, 2, 0), (128, 24, 40, 1, 1),
                                              (64, 8, 12, 2, 3), (32, 5, 7, 1, 0)])
 def test_in_bwd_fused_cluster(bes, C, H, W, act, fold):
