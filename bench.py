@@ -128,6 +128,7 @@ def main():
     ap.add_argument("--size", type=int, nargs=2, default=[256, 256], metavar=("H", "W"))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown-all", default=None, help="write a per-launcher CUDA-event table of one eager step (all kernels) to this file")
     ap.add_argument("--breakdown", default=None, help="write the per-launch GEMM timing table to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,6 +234,22 @@ def main():
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
+
+    if args.breakdown_all and rank == 0:
+        be.time_all_launchers()
+        ts.step(ir_d, rgb_d)
+        be.timers_all = []
+        ts.step(ir_d, rgb_d)
+        torch.cuda.synchronize()
+        agg = {}
+        for name, tag, e0, e1 in be.timers_all:
+            a = agg.setdefault((name, tag), [0, 0.0]); a[0] += 1; a[1] += e0.elapsed_time(e1)
+        be.timers_all = None
+        tot = sum(v[1] for v in agg.values())
+        with open(args.breakdown_all, "w") as f:
+            f.write(f"launcher,args,calls,ms_total,ms_per_call,share   # one eager step, CUDA events per call, total {tot:.3f} ms\n")
+            for (name, tag), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                f.write(f"{name},\"{tag}\",{n},{t:.4f},{t / n:.4f},{t / tot:.3f}\n")
 
     if rank != 0:
         shutdown()

@@ -281,6 +281,28 @@ class CudaBackend:
             assert hasattr(self, name), name
             setattr(self, name, lambda *a, **k: None)
 
+    def time_all_launchers(self):
+        """bench.py --breakdown-all: bracket EVERY launcher call with CUDA events (eager mode) so that the memory-bound
+        kernels get the same per-call table as the GEMMs.  Appends (name, tag, e0, e1) to self.timers_all."""
+        self.timers_all = []
+        names = ["in_stats", "gather", "in_apply", "in_bwd", "fold_inplace", "maxpool2", "maxpool2_bwd", "colsum", "im2col", "col2im",
+                 "tap_reduce", "tap_expand", "pixel_loss", "ssim_fwd", "ssim_bwd", "hinge", "feat_l1", "adam", "pack_bf16", "gather_sum",
+                 "conv_gemm", "tn_gemm", "zero_"]
+        for name in names:
+            orig = getattr(self, name)
+
+            def wrapped(*a, _orig=orig, _name=name, **k):
+                if self.timers_all is None:
+                    return _orig(*a, **k)
+                tag = ",".join(str(v) for v in a if isinstance(v, int) and not isinstance(v, bool))[:40]
+                if _name in ("conv_gemm", "tn_gemm"):
+                    tag = self.note[0] + ":" + self.note[1]
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); r = _orig(*a, **k); e1.record()
+                self.timers_all.append((_name, tag, e0, e1))
+                return r
+            setattr(self, name, wrapped)
+
     def _timed(self, kind, fn):
         if self.timers is None:
             fn()
@@ -402,12 +424,14 @@ class CudaBackend:
         reflection-padded map (ring included); the fold happens inside (fused kernel) or as a separate in-place pass."""
         g = self._bwd_args(z, g1, g2, dz, C_, n_img, H, W, stats, cnt, eps, act, slope, tables, bsum)
         fused = (self.fused_in_bwd and stats is not None and g2 is None and tables.ty_idx is None and tables.tx_idx is None
-                 and C_ % 32 == 0 and H * W <= 4096)
+                 and C_ % 32 == 0 and H * W <= 4096 and not (z.s2d_c or g1.s2d_c or dz.s2d_c))
         if fused:
             check(self.L.irc_in_bwd_fused(C.byref(g), fold_pad, _stream())); self.launches += 1
             return
         if fold_pad:
             self.fold_inplace(g1.t, g1.chan_off, C_, n_img, H, W, fold_pad)
+        # (running the two passes over L2-sized groups of images was measured: 14.50 ms/step unchunked vs 14.67 / 15.11 /
+        # 15.67 ms with 64 / 40 / 24 MB groups - the extra launches cost more than the L2 hits save)
         if stats is not None:
             check(self.L.irc_in_bwd_reduce(C.byref(g), _stream())); self.launches += 1
         check(self.L.irc_in_bwd_apply(C.byref(g), _stream())); self.launches += 1

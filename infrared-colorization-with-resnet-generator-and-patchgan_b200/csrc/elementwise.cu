@@ -758,7 +758,82 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-template <bool kFold>
+// Sum 16 per-thread values over the 8 lanes of a warp that share (lane & 3) - lane bits 2..4 - as a reduce-scatter:
+// every step halves the number of values a thread carries (8 + 4 + 2 shuffles instead of 3 x 16).  On return the thread
+// holds the complete sums of values idx and idx + 1 in (r0, r1).  Fixed order: bit-reproducible.
+__device__ __forceinline__ void reduce16_scatter(const float (&v)[16], float& r0, float& r1, int& idx) {
+    const int l = threadIdx.x & 31;
+    const bool b4 = l & 16, b3 = l & 8, b2 = l & 4;
+    float a[8], b[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float keep = b4 ? v[8 + j] : v[j], give = b4 ? v[j] : v[8 + j];
+        a[j] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float keep = b3 ? a[4 + j] : a[j], give = b3 ? a[j] : a[4 + j];
+        b[j] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+    }
+    {
+        const float k0 = b2 ? b[2] : b[0], g0 = b2 ? b[0] : b[2], k1 = b2 ? b[3] : b[1], g1 = b2 ? b[1] : b[3];
+        r0 = k0 + __shfl_xor_sync(0xffffffffu, g0, 4);
+        r1 = k1 + __shfl_xor_sync(0xffffffffu, g1, 4);
+    }
+    idx = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0);
+}
+
+// CTA + cluster stage of the fused kernels: v = this thread's 16 partial sums, layout [k][2] for its channel vector.
+// Returns with tot[cv*16 + j] = sum over the whole cluster.  part must stay alive until the final cluster.sync().
+__device__ __forceinline__ void cluster_sum16(cg::cluster_group& cluster, const float (&v)[16], float (*wsum)[64], float* part, float* tot) {
+    const int tid = threadIdx.x, cv = tid & 3;
+    float r0, r1; int idx;
+    reduce16_scatter(v, r0, r1, idx);
+    wsum[tid >> 5][cv * 16 + idx] = r0; wsum[tid >> 5][cv * 16 + idx + 1] = r1;
+    __syncthreads();
+    if (tid < 64) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += wsum[w][tid];
+        part[tid] = a;
+    }
+    cluster.sync();
+    if (tid < 64) {
+        const unsigned CL = cluster.num_blocks();
+        float a = 0.f;
+        for (unsigned r = 0; r < CL; ++r) a += cluster.map_shared_rank(part, r)[tid];
+        tot[tid] = a;
+    }
+    __syncthreads();
+}
+
+// pixel walk of a thread of the fused kernels: pixel p0 + lane + i*64 as (y, x) plus the 32-bit element offsets of that
+// pixel in up to three (non space-to-depth) views, advanced without divisions or 64-bit multiplies
+struct VStep {
+    const bf16* base; int dx, wrap;      // pointer of pixel (0,0), elements per x step, extra elements when a row wraps
+    __device__ __forceinline__ void init(const View& v, int n, int c, int W) { base = v.at(n, 0, 0, c); dx = (int)v.ld; wrap = (v.wp - W) * (int)v.ld; }
+    __device__ __forceinline__ int at(int y, int x, int W) const { return y * (W * dx + wrap) + x * dx; }
+};
+struct PixWalk {
+    int y, x, W, o0, o1, o2;
+    __device__ __forceinline__ PixWalk(int pix, int W_, const VStep& a, const VStep& b, const VStep& c) : W(W_) {
+        y = pix / W_; x = pix - y * W_;
+        o0 = a.at(y, x, W_); o1 = b.at(y, x, W_); o2 = c.at(y, x, W_);
+    }
+    __device__ __forceinline__ void next(const VStep& a, const VStep& b, const VStep& c) {
+        x += kFusedLanes; o0 += kFusedLanes * a.dx; o1 += kFusedLanes * b.dx; o2 += kFusedLanes * c.dx;
+        while (x >= W) { x -= W; ++y; o0 += a.wrap; o1 += b.wrap; o2 += c.wrap; }
+    }
+};
+
+template <int kAct>
+__device__ __forceinline__ float dact_t(float xh, float slope) {
+    if (kAct == 1) return xh > 0.f ? 1.f : 0.f;
+    if (kAct == 2) return xh > 0.f ? 1.f : slope;
+    return 1.f;
+}
+
+template <bool kFold, int kAct>
 __global__ void __launch_bounds__(256, 3) in_bwd_fused_kernel(const InBwdP p, int fold_pad) {
     irc::pdl_prologue();
     cg::cluster_group cluster = cg::this_cluster();
@@ -772,18 +847,23 @@ __global__ void __launch_bounds__(256, 3) in_bwd_fused_kernel(const InBwdP p, in
     const int HW = p.H * p.W;
     const int P = (HW + CL - 1) / CL;
     const int p0 = rank * P, p1 = min(p0 + P, HW);
+    const int np = p0 + lane < p1 ? (p1 - p0 - lane + kFusedLanes - 1) / kFusedLanes : 0;     // pixels of this thread
     uint4* gs = raw + tid;
     uint4* zs = raw + kFusedNP * 256 + tid;
     // all loads of the thread go straight to its shared-memory slots (no register staging): 16 x 16 bytes in flight
+    VStep vg, vz, vd;
+    vg.init(p.g1, n, c, p.W); vz.init(p.z, n, c, p.W); vd.init(p.dz, n, c, p.W);
+    {
+        PixWalk w(p0 + lane, p.W, vg, vz, vd);
 #pragma unroll
-    for (int i = 0; i < kFusedNP; ++i) {
-        const int pix = p0 + lane + i * kFusedLanes;
-        if (pix < p1) {
-            const int y = pix / p.W, x = pix - y * p.W;
-            cp_async16(gs + i * 256, p.g1.at(n, y, x, c));
-            cp_async16(zs + i * 256, p.z.at(n, y, x, c));
-        } else {
-            gs[i * 256] = make_uint4(0, 0, 0, 0); zs[i * 256] = make_uint4(0, 0, 0, 0);     // g = 0 adds nothing
+        for (int i = 0; i < kFusedNP; ++i) {
+            if (i < np) {
+                cp_async16(gs + i * 256, vg.base + w.o0);
+                cp_async16(zs + i * 256, vz.base + w.o1);
+            } else {
+                gs[i * 256] = make_uint4(0, 0, 0, 0); zs[i * 256] = make_uint4(0, 0, 0, 0);     // g = 0 adds nothing
+            }
+            w.next(vg, vz, vd);
         }
     }
     float mu[8], rs[8];
@@ -792,10 +872,10 @@ __global__ void __launch_bounds__(256, 3) in_bwd_fused_kernel(const InBwdP p, in
     for (int k = 0; k < 8; ++k) mu[k] = -mu[k] * rs[k];
     cp_async_wait_all();
     if (kFold) {
-        for (int i = 0; i < kFusedNP; ++i) {
-            const int pix = p0 + lane + i * kFusedLanes;
-            if (pix >= p1) break;
-            const int y = pix / p.W, x = pix - y * p.W;
+        PixWalk w(p0 + lane, p.W, vg, vz, vd);
+        for (int i = 0; i < np; ++i, w.next(vg, vz, vd)) {
+            const int y = w.y, x = w.x;
+            if (y > fold_pad && y < p.H - 1 - fold_pad && x > fold_pad && x < p.W - 1 - fold_pad) continue;
             const int my = mirror_src(y, p.H, fold_pad), mx = mirror_src(x, p.W, fold_pad);
             if (my == INT_MIN && mx == INT_MIN) continue;
             float a[8], v[8];
@@ -813,7 +893,9 @@ __global__ void __launch_bounds__(256, 3) in_bwd_fused_kernel(const InBwdP p, in
             gs[i * 256] = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
         }
     }
-    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
 #pragma unroll 2
     for (int i = 0; i < kFusedNP; ++i) {
         float g[8], zv[8];
@@ -821,55 +903,31 @@ __global__ void __launch_bounds__(256, 3) in_bwd_fused_kernel(const InBwdP p, in
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const float xh = fmaf(zv[k], rs[k], mu[k]);
-            const float gd = g[k] * dactf(xh, p.act, p.slope);
-            s1[k] += gd; s2[k] = fmaf(gd, xh, s2[k]);
+            const float gd = g[k] * dact_t<kAct>(xh, p.slope);
+            acc[2 * k] += gd; acc[2 * k + 1] = fmaf(gd, xh, acc[2 * k + 1]);
         }
     }
-    // lanes of a warp that share a channel vector differ in bits 2..4 of the lane id
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-#pragma unroll
-        for (int off = 4; off < 32; off <<= 1) {
-            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], off);
-            s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], off);
-        }
-    }
-    if ((tid & 31) < 4) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { wsum[tid >> 5][cv * 16 + k * 2] = s1[k]; wsum[tid >> 5][cv * 16 + k * 2 + 1] = s2[k]; }
-    }
-    __syncthreads();
-    if (tid < 64) {
-        float a = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) a += wsum[w][tid];
-        part[tid] = a;
-    }
-    cluster.sync();
-    if (tid < 64) {
-        float a = 0.f;
-        for (unsigned r = 0; r < CL; ++r) a += cluster.map_shared_rank(part, r)[tid];
-        tot[tid] = a;
-        if (rank == 0 && p.bsum) p.bsum[((long long)n * p.C + blockIdx.y * kFusedCC) * 2 + tid] = a;
-    }
-    __syncthreads();
+    cluster_sum16(cluster, acc, wsum, part, tot);
+    if (rank == 0 && tid < 64 && p.bsum) p.bsum[((long long)n * p.C + blockIdx.y * kFusedCC) * 2 + tid] = tot[tid];
     float b1[8], b2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { b1[k] = tot[cv * 16 + k * 2] * p.inv_cnt; b2[k] = tot[cv * 16 + k * 2 + 1] * p.inv_cnt; }
+    {
+        PixWalk w(p0 + lane, p.W, vg, vz, vd);
 #pragma unroll 2
-    for (int i = 0; i < kFusedNP; ++i) {
-        const int pix = p0 + lane + i * kFusedLanes;
-        if (pix < p1) {
-            const int y = pix / p.W, x = pix - y * p.W;
-            float g[8], zv[8], o[8];
-            unpack8(gs[i * 256], g); unpack8(zs[i * 256], zv);
+        for (int i = 0; i < kFusedNP; ++i) {
+            if (i < np) {
+                float g[8], zv[8], o[8];
+                unpack8(gs[i * 256], g); unpack8(zs[i * 256], zv);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float xh = fmaf(zv[k], rs[k], mu[k]);
-                const float gd = g[k] * dactf(xh, p.act, p.slope);
-                o[k] = rs[k] * (gd - b1[k] - xh * b2[k]);
+                for (int k = 0; k < 8; ++k) {
+                    const float xh = fmaf(zv[k], rs[k], mu[k]);
+                    const float gd = g[k] * dact_t<kAct>(xh, p.slope);
+                    o[k] = rs[k] * (gd - b1[k] - xh * b2[k]);
+                }
+                store8(const_cast<bf16*>(vd.base) + w.o2, o);
             }
-            store8(const_cast<bf16*>(p.dz.at(n, y, x, c)), o);
+            w.next(vg, vz, vd);
         }
     }
     cluster.sync();      // `part` must outlive the remote reads of every peer
@@ -881,6 +939,7 @@ __global__ void __launch_bounds__(256, 3) in_bwd_fused_kernel(const InBwdP p, in
 // slots), reduces (sum, sum of squares) through distributed shared memory in a fixed order, writes the statistics the
 // backward pass needs, and produces the activated frame - interior and ring - from the staged values.
 // ---------------------------------------------------------------------------------
+template <int kAct>
 __global__ void __launch_bounds__(256, 3) in_apply_fused_kernel(const GatherP p, float* stats_out) {
     irc::pdl_prologue();
     cg::cluster_group cluster = cg::this_cluster();
@@ -894,55 +953,38 @@ __global__ void __launch_bounds__(256, 3) in_apply_fused_kernel(const GatherP p,
     const int HW = p.H * p.W;
     const int P = (HW + CL - 1) / CL;
     const int p0 = rank * P, p1 = min(p0 + P, HW);
+    const int np = p0 + lane < p1 ? (p1 - p0 - lane + kFusedLanes - 1) / kFusedLanes : 0;
     uint4* zs = raw + tid;
     uint4* rsd = raw + kFusedNP * 256 + tid;
+    const int pad = p.pad, W = p.W, H = p.H;
+    VStep vs, vr, vd;
+    vs.init(p.src, n, c, W); vr.init(p.has_res ? p.res : p.src, n, c, W); vd.init(p.dst, n, c, W);
+    {
+        PixWalk w(p0 + lane, W, vs, vr, vd);
 #pragma unroll
-    for (int i = 0; i < kFusedNP; ++i) {
-        const int pix = p0 + lane + i * kFusedLanes;
-        if (pix < p1) {
-            const int y = pix / p.W, x = pix - y * p.W;
-            cp_async16(zs + i * 256, p.src.at(n, y, x, c));
-            if (p.has_res) cp_async16(rsd + i * 256, p.res.at(n, y, x, c));
-        } else {
-            zs[i * 256] = make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < kFusedNP; ++i) {
+            if (i < np) {
+                cp_async16(zs + i * 256, vs.base + w.o0);
+                if (p.has_res) cp_async16(rsd + i * 256, vr.base + w.o1);
+            } else {
+                zs[i * 256] = make_uint4(0, 0, 0, 0);
+            }
+            w.next(vs, vr, vd);
         }
     }
     cp_async_wait_all();
-    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
 #pragma unroll 2
     for (int i = 0; i < kFusedNP; ++i) {
         float v[8];
         unpack8(zs[i * 256], v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { s1[k] += v[k]; s2[k] = fmaf(v[k], v[k], s2[k]); }
+        for (int k = 0; k < 8; ++k) { acc[2 * k] += v[k]; acc[2 * k + 1] = fmaf(v[k], v[k], acc[2 * k + 1]); }
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-#pragma unroll
-        for (int off = 4; off < 32; off <<= 1) {
-            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], off);
-            s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], off);
-        }
-    }
-    if ((tid & 31) < 4) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { wsum[tid >> 5][cv * 16 + k * 2] = s1[k]; wsum[tid >> 5][cv * 16 + k * 2 + 1] = s2[k]; }
-    }
-    __syncthreads();
-    if (tid < 64) {
-        float a = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) a += wsum[w][tid];
-        part[tid] = a;
-    }
-    cluster.sync();
-    if (tid < 64) {
-        float a = 0.f;
-        for (unsigned r = 0; r < CL; ++r) a += cluster.map_shared_rank(part, r)[tid];
-        tot[tid] = a;
-        if (rank == 0) stats_out[((long long)n * p.C + blockIdx.y * kFusedCC) * 2 + tid] = a;     // (sum, sum of squares) pairs
-    }
-    __syncthreads();
+    cluster_sum16(cluster, acc, wsum, part, tot);
+    if (rank == 0 && tid < 64) stats_out[((long long)n * p.C + blockIdx.y * kFusedCC) * 2 + tid] = tot[tid];     // (sum, sum of squares) pairs
     float mu[8], rs[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -950,18 +992,20 @@ __global__ void __launch_bounds__(256, 3) in_apply_fused_kernel(const GatherP p,
         rs[k] = rsqrtf(fmaxf(tot[cv * 16 + k * 2 + 1] * p.inv_cnt - m * m, 0.f) + p.eps);
         mu[k] = -m * rs[k];
     }
-    const int pad = p.pad, W = p.W, H = p.H;
-    bf16* dbase = const_cast<bf16*>(p.dst.p) + ((long long)(n * p.dst.hp + p.dst.oy - pad) * p.dst.wp + (p.dst.ox - pad)) * p.dst.ld + p.dst.off + c;
-    const long long dstep = (long long)p.dst.wp * p.dst.ld;
+    bf16* dbase = const_cast<bf16*>(vd.base);          // interior pixel (0,0) of the destination view
+    const int dld = (int)p.dst.ld, dstep = p.dst.wp * dld;
+    PixWalk w(p0 + lane, W, vs, vr, vd);
 #pragma unroll 2
-    for (int i = 0; i < kFusedNP; ++i) {
-        const int pix = p0 + lane + i * kFusedLanes;
-        if (pix >= p1) continue;
-        const int y = pix / W, x = pix - y * W;
+    for (int i = 0; i < kFusedNP; ++i, w.next(vs, vr, vd)) {
+        if (i >= np) continue;
+        const int y = w.y, x = w.x;
         float v[8];
         unpack8(zs[i * 256], v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const float t = fmaf(v[k], rs[k], mu[k]); v[k] = fmaxf(t, 0.f) + p.slope_eff * fminf(t, 0.f); }
+        for (int k = 0; k < 8; ++k) {
+            const float t = fmaf(v[k], rs[k], mu[k]);
+            v[k] = kAct == 1 ? fmaxf(t, 0.f) : (kAct == 2 ? fmaxf(t, 0.f) + p.slope * fminf(t, 0.f) : t);
+        }
         if (p.has_res) {
             float u[8];
             unpack8(rsd[i * 256], u);
@@ -969,10 +1013,10 @@ __global__ void __launch_bounds__(256, 3) in_apply_fused_kernel(const GatherP p,
             for (int k = 0; k < 8; ++k) v[k] += u[k];
         }
         const uint4 val = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        bf16* drow = dbase + (y + pad) * dstep;
-        *reinterpret_cast<uint4*>(drow + (long long)(x + pad) * p.dst.ld) = val;
-        if (pad) {
-            // ring pixels owned by this interior pixel: the reflected copies (halo_mode 1) or zeros (halo_mode 0)
+        bf16* dpix = dbase + w.o2;
+        *reinterpret_cast<uint4*>(dpix) = val;
+        if (pad && (y <= pad || y >= H - 1 - pad || x <= pad || x >= W - 1 - pad)) {
+            // ring pixels owned by this border pixel: the reflected copies (halo_mode 1) or zeros (halo_mode 0)
             const uint4 ring = p.halo_mode == 1 ? val : make_uint4(0, 0, 0, 0);
             int eX, eY;
             if (p.halo_mode == 1) {
@@ -982,11 +1026,12 @@ __global__ void __launch_bounds__(256, 3) in_apply_fused_kernel(const GatherP p,
                 eX = x < pad ? x : (x >= W - pad ? x + 2 * pad : -1);
                 eY = y < pad ? y : (y >= H - pad ? y + 2 * pad : -1);
             }
-            if (eX >= 0) *reinterpret_cast<uint4*>(drow + (long long)eX * p.dst.ld) = ring;
+            // eX / eY are padded coordinates; the interior pixel sits at padded (y + pad, x + pad)
+            const int ddx = (eX - (x + pad)) * dld, ddy = (eY - (y + pad)) * dstep;
+            if (eX >= 0) *reinterpret_cast<uint4*>(dpix + ddx) = ring;
             if (eY >= 0) {
-                bf16* erow = dbase + eY * dstep;
-                *reinterpret_cast<uint4*>(erow + (long long)(x + pad) * p.dst.ld) = ring;
-                if (eX >= 0) *reinterpret_cast<uint4*>(erow + (long long)eX * p.dst.ld) = ring;
+                *reinterpret_cast<uint4*>(dpix + ddy) = ring;
+                if (eX >= 0) *reinterpret_cast<uint4*>(dpix + ddy + ddx) = ring;
             }
         }
     }
@@ -1263,16 +1308,24 @@ extern "C" int irc_in_apply_fused(const irc_gather_args* a, float* stats_out, vo
     p.H = a->H; p.W = a->W; p.pad = a->pad; p.halo_mode = a->halo_mode; p.dst_s2d = 0;
     p.slope_eff = a->act == 1 ? 0.f : (a->act == 2 ? a->slope : 1.f);
     const long long hw = (long long)p.H * p.W;
-    if (!stats_out || a->src2.ptr || a->ty_idx || a->tx_idx || a->dst_s2d || p.src.s2d_c || p.C % kFusedCC || hw > 8 * kFusedNP * kFusedLanes ||
-        a->act < 0 || a->act > 2 || (p.pad && (p.W <= 2 * p.pad + 1 || p.H <= 2 * p.pad + 1)) || a->cnt != (float)hw)
+    if (!stats_out || a->src2.ptr || a->ty_idx || a->tx_idx || a->dst_s2d || p.src.s2d_c || p.dst.s2d_c || (p.has_res && p.res.s2d_c) || p.C % kFusedCC ||
+        hw > 8 * kFusedNP * kFusedLanes || a->act < 0 || a->act > 2 || (p.pad && (p.W <= 2 * p.pad + 1 || p.H <= 2 * p.pad + 1)) || a->cnt != (float)hw)
         return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_apply_fused: needs identity tables, one source, C %% 32 == 0, H*W <= 4096, cnt == H*W");
     unsigned cl = 1;
     while ((long long)cl * kFusedNP * kFusedLanes < hw) cl *= 2;
     const dim3 grid(cl, p.C / kFusedCC, p.n_img);
     const size_t smem = 2 * kFusedNP * 256 * sizeof(uint4);
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(in_apply_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    irc::launch_cluster(in_apply_fused_kernel, grid, 256, smem, (cudaStream_t)stream, cl, p, stats_out);
+    if (!attr) {
+        cudaFuncSetAttribute(in_apply_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(in_apply_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(in_apply_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->act == 1) irc::launch_cluster(in_apply_fused_kernel<1>, grid, 256, smem, st, cl, p, stats_out);
+    else if (a->act == 2) irc::launch_cluster(in_apply_fused_kernel<2>, grid, 256, smem, st, cl, p, stats_out);
+    else irc::launch_cluster(in_apply_fused_kernel<0>, grid, 256, smem, st, cl, p, stats_out);
     return irc_check_launch("irc_in_apply_fused");
 }
 
@@ -1322,7 +1375,7 @@ extern "C" int irc_in_bwd_fused(const irc_in_bwd_args* a, int fold_pad, void* st
     rc = check_view(a->dz, "irc_in_bwd_fused dz"); if (rc) return rc;
     p.dz = mk(a->dz);
     const long long hw = (long long)p.H * p.W;
-    if (!p.stats || p.has2 || p.ty_idx || p.tx_idx || p.C % kFusedCC || hw > 8 * kFusedNP * kFusedLanes || fold_pad < 0 ||
+    if (!p.stats || p.has2 || p.ty_idx || p.tx_idx || p.g1.s2d_c || p.z.s2d_c || p.dz.s2d_c || p.C % kFusedCC || hw > 8 * kFusedNP * kFusedLanes || fold_pad < 0 ||
         (fold_pad && (2 * fold_pad + 2 > p.H || 2 * fold_pad + 2 > p.W)))
         return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_bwd_fused: needs stats, one source, identity tables, C %% 32 == 0 and H*W <= 4096");
     unsigned cl = 1;
@@ -1331,12 +1384,17 @@ extern "C" int irc_in_bwd_fused(const irc_in_bwd_args* a, int fold_pad, void* st
     const size_t smem = 2 * kFusedNP * 256 * sizeof(uint4);       // 64 KB
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(in_bwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(in_bwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#define IRC_ATTR(F, A) cudaFuncSetAttribute(in_bwd_fused_kernel<F, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        IRC_ATTR(true, 0); IRC_ATTR(true, 1); IRC_ATTR(true, 2); IRC_ATTR(false, 0); IRC_ATTR(false, 1); IRC_ATTR(false, 2);
+#undef IRC_ATTR
         attr = true;
     }
-    if (fold_pad) irc::launch_cluster(in_bwd_fused_kernel<true>, grid, 256, smem, (cudaStream_t)stream, cl, p, fold_pad);
-    else irc::launch_cluster(in_bwd_fused_kernel<false>, grid, 256, smem, (cudaStream_t)stream, cl, p, fold_pad);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.act < 0 || p.act > 2) return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_bwd_fused: act must be 0, 1 or 2");
+#define IRC_GO(F, A) irc::launch_cluster(in_bwd_fused_kernel<F, A>, grid, 256, smem, st, cl, p, fold_pad)
+    if (fold_pad) { if (p.act == 1) IRC_GO(true, 1); else if (p.act == 2) IRC_GO(true, 2); else IRC_GO(true, 0); }
+    else { if (p.act == 1) IRC_GO(false, 1); else if (p.act == 2) IRC_GO(false, 2); else IRC_GO(false, 0); }
+#undef IRC_GO
     return irc_check_launch("irc_in_bwd_fused");
 }
 

@@ -66,35 +66,53 @@ struct Im2colP {
     bf16* dst; short* row_img;
 };
 
-__global__ void __launch_bounds__(256) im2col_kernel(const Im2colP p) {
+__global__ void __launch_bounds__(256) im2col_kernel(const Im2colP p, int R, int Wp) {
+    // One block per (image, line of the row order).  The R input rows the line needs are staged once in shared memory
+    // - all channels, padding / reflection and the per-channel affine resolved while filling, with coalesced loads -
+    // so a thread (one item of the line x one group of 8 columns) assembles its 16 bytes with 8 shared-memory reads at
+    // register-resident offsets: no border cases, no scattered global loads.
     irc::pdl_prologue();
-    // one block per (image, line of the row order); thread = (item of the line, group of 8 columns).  The 8 columns of a
-    // thread never change, so their (source, element offset, scale, shift) live in registers: a row whose k x k window is
-    // interior costs one add + one load per element; only border rows decode (r, s) and reflect / zero-fill.
+    extern __shared__ float tile[];                 // [C][R][Wp]
     const int C = p.c1 + p.c2;
     const int K = p.k * p.k * C;
     const int g = threadIdx.x & 7;
-    int off[8], rs_[8]; float sc[8], sh[8]; unsigned sel = 0, valid = 0;
+    int off[8]; unsigned valid = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int col = g * 8 + j;
-        off[j] = 0; rs_[j] = 0; sc[j] = 1.f; sh[j] = 0.f;
+        off[j] = 0;
         if (col < K) {
             const int c = col % C, rs = col / C, r = rs / p.k, s_ = rs % p.k;
             valid |= 1u << j;
-            const int cc = c < p.c1 ? c : c - p.c1;
-            if (c >= p.c1) sel |= 1u << j;
-            off[j] = (cc * p.H + r) * p.W + s_;
-            rs_[j] = cc | (r << 8) | (s_ << 16);
-            if (p.scale) { sc[j] = __ldg(p.scale + c); sh[j] = __ldg(p.shift + c); }
+            off[j] = (c * R + r) * Wp + s_;
         }
     }
     const int nl = p.rm.lines(), ll = p.rm.line_len();
     const long long hw = (long long)p.H * p.W;
     for (int bl = blockIdx.x; bl < p.rm.n_img * nl; bl += gridDim.x) {
         const int n = bl / nl, line = bl - n * nl;
-        const float* b1 = p.src1 + (long long)n * p.c1 * hw;
-        const float* b2 = p.src2 ? p.src2 + (long long)n * p.c2 * hw : b1;
+        // first output row of the line and the input row it starts at
+        const int oy0 = p.rm.mode == 0 ? line : (p.rm.mode == 1 ? line - 1 : 2 * line - 1);
+        const int y_lo = oy0 * p.stride - p.pad;
+        __syncthreads();                            // the previous line's readers are done with the tile
+        // one warp per staged row (channel c, input row r): the row decode happens once, lanes run along x
+        for (int t = threadIdx.x >> 5; t < C * R; t += blockDim.x >> 5) {
+            const int c = t / R, r = t - c * R;
+            int y = y_lo + r;
+            if (p.pad_mode == 1) y = reflect_idx(y, p.H);
+            const bool oky = y >= 0 && y < p.H;
+            const float* srow = (c < p.c1 ? p.src1 + ((long long)n * p.c1 + c) * hw : p.src2 + ((long long)n * p.c2 + (c - p.c1)) * hw) + (long long)(oky ? y : 0) * p.W;
+            const float sc = p.scale ? __ldg(p.scale + c) : 1.f, sh = p.scale ? __ldg(p.shift + c) : 0.f;
+            float* trow = tile + t * Wp;
+            for (int xx = threadIdx.x & 31; xx < Wp; xx += 32) {
+                int x = xx - p.pad;
+                if (p.pad_mode == 1) x = reflect_idx(x, p.W);
+                float v = 0.f;
+                if (oky && x >= 0 && x < p.W) v = fmaf(__ldg(srow + x), sc, sh);
+                trow[xx] = v;
+            }
+        }
+        __syncthreads();
         for (int i = threadIdx.x >> 3; i < ll; i += blockDim.x >> 3) {
             const long long q = (long long)bl * ll + i;
             int oy, ox;
@@ -102,26 +120,9 @@ __global__ void __launch_bounds__(256) im2col_kernel(const Im2colP p) {
             if (g == 0 && p.row_img) p.row_img[q] = live ? (short)n : (short)-1;
             float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             if (live) {
-                const int y0 = oy * p.stride - p.pad, x0 = ox * p.stride - p.pad;
-                if (y0 >= 0 && x0 >= 0 && y0 + p.k <= p.H && x0 + p.k <= p.W) {
-                    const int pix = y0 * p.W + x0;
+                const int base = (oy - oy0) * p.stride * Wp + ox * p.stride;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float raw = __ldg(((sel >> j) & 1 ? b2 : b1) + pix + off[j]);
-                        v[j] = (valid >> j) & 1 ? fmaf(raw, sc[j], sh[j]) : 0.f;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (!((valid >> j) & 1)) continue;
-                        const int cc = rs_[j] & 255;
-                        int y = y0 + ((rs_[j] >> 8) & 255), x = x0 + (rs_[j] >> 16);
-                        bool ok = true;
-                        if (p.pad_mode == 1) { y = reflect_idx(y, p.H); x = reflect_idx(x, p.W); }
-                        else ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
-                        if (ok) v[j] = fmaf(__ldg(((sel >> j) & 1 ? b2 : b1) + ((long long)cc * p.H + y) * p.W + x), sc[j], sh[j]);
-                    }
-                }
+                for (int j = 0; j < 8; ++j) v[j] = (valid >> j) & 1 ? tile[base + off[j]] : 0.f;
             }
             *reinterpret_cast<uint4*>(p.dst + q * 64 + g * 8) =
                 make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
@@ -280,7 +281,13 @@ extern "C" int irc_im2col(const irc_im2col_args* a, void* stream) {
     p.rm.mode = a->row_mode; p.rm.n_img = a->n_img; p.rm.Ho = a->Ho; p.rm.Wo = a->Wo;
     p.dst = (bf16*)a->dst; p.row_img = a->row_img;
     const long long nblk = (long long)p.rm.n_img * p.rm.lines();
-    irc::launch(im2col_kernel, (unsigned)(nblk < 1048576 ? nblk : 1048576), 256, 0, (cudaStream_t)stream, p);
+    // input rows per line (mode 2 lines hold two output rows) and padded row width of the staged tile
+    const int R = (a->row_mode == 2 ? a->stride : 0) + a->k, Wp = a->W + 2 * a->pad;
+    const size_t smem = (size_t)C * R * Wp * sizeof(float);
+    if (smem > 200 * 1024) return irc_set_error(IRC_ERR_BAD_ARG, "irc_im2col: line tile does not fit shared memory");
+    static size_t attr = 48 * 1024;
+    if (smem > attr) { cudaFuncSetAttribute(im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = 200 * 1024; }
+    irc::launch(im2col_kernel, (unsigned)(nblk < 1048576 ? nblk : 1048576), 256, smem, (cudaStream_t)stream, p, R, Wp);
     return irc_check_launch("irc_im2col");
 }
 
