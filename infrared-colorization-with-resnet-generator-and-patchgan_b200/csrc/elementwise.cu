@@ -98,6 +98,22 @@ __device__ __forceinline__ void finalize_by_last_block(const float* part, float*
     if (threadIdx.x == 0) counters[n] = 0u;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The row-walking reductions below are latency-bound with plain loads (ncu: 32 warps/SM x 2 x 512 B in flight = 3.3 TB/s,
+// long-scoreboard stalls 15 per issue).  They therefore prefetch kPipeD pixels ahead per thread with cp.async into
+// PRIVATE shared-memory slots (slot [stage][tensor][thread]: no barrier needed, only cp.async.wait_group), which puts
+// 4x the bytes in flight without a single extra register.
+constexpr int kPipeD = 4;
+
 // ---------------------------------------------------------------------------------
 // per-(image, channel) sum and sum of squares over the H x W pixels of a view
 // block = (C/8) channel vectors x L pixel lanes; grid = (chunks, N)
@@ -124,6 +140,52 @@ __global__ void __launch_bounds__(256, 4) in_stats_kernel(View z, int C, int H, 
 #pragma unroll
         for (int j = 0; j < 8; ++j) { shs[(lane * C8 + cv) * 16 + j * 2] = s[j]; shs[(lane * C8 + cv) * 16 + j * 2 + 1] = ss[j]; }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C8 * 16; i += blockDim.x) {
+        float a = 0.f;
+        for (int l = 0; l < L; ++l) a += shs[l * C8 * 16 + i];
+        part[((long long)blockIdx.x * gridDim.y + n) * C * 2 + i] = a;
+    }
+    if (counters) finalize_by_last_block(part, out, n, C * 2, counters);
+}
+
+// pipelined variant for plain (non space-to-depth) views
+__global__ void __launch_bounds__(256, 4) in_stats_pipe_kernel(View z, int C, int H, int W, float* part, float* out, unsigned* counters) {
+    irc::pdl_prologue();
+    extern __shared__ float sh[];             // [kPipeD][threads] uint4 slots, then reused as [L][C8][16] floats
+    const int nt = blockDim.x;
+    uint4* slot = reinterpret_cast<uint4*>(sh) + threadIdx.x;
+    const int C8 = C >> 3;
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int n = blockIdx.y;
+    const bf16* base = z.at(n, 0, 0, cv * 8);
+    const long long rstride = (long long)z.wp * z.ld;
+    const int pstride = (int)z.ld;
+    int iy = blockIdx.x, ix = lane, cy = blockIdx.x, cx = lane;
+#pragma unroll
+    for (int st = 0; st < kPipeD; ++st) {
+        if (iy < H) { cp_async16(slot + st * nt, base + iy * rstride + ix * pstride); ix += L; if (ix >= W) { ix = lane; iy += gridDim.x; } }
+        cp_async_commit();
+    }
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ss[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int st = 0;
+    while (cy < H) {
+        cp_async_wait<kPipeD - 1>();
+        const uint4 r = slot[st * nt];
+        if (iy < H) { cp_async16(slot + st * nt, base + iy * rstride + ix * pstride); ix += L; if (ix >= W) { ix = lane; iy += gridDim.x; } }
+        cp_async_commit();
+        float v[8];
+        unpack8(r, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
+        cx += L; if (cx >= W) { cx = lane; cy += gridDim.x; }
+        st = st + 1 == kPipeD ? 0 : st + 1;
+    }
+    cp_async_wait<0>();
+    __syncthreads();                          // every thread is done with its slots: the buffer becomes the reduction scratch
+    float* shs = sh;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { shs[(lane * C8 + cv) * 16 + j * 2] = s[j]; shs[(lane * C8 + cv) * 16 + j * 2 + 1] = ss[j]; }
     __syncthreads();
     for (int i = threadIdx.x; i < C8 * 16; i += blockDim.x) {
         float a = 0.f;
@@ -731,6 +793,147 @@ __global__ void __launch_bounds__(256, 4) in_bwd_apply_kernel(const InBwdP p) {
 }
 
 // ---------------------------------------------------------------------------------
+// Pipelined identity-table versions of the two passes (plain views; one or two gradient sources)
+// ---------------------------------------------------------------------------------
+template <bool kTwo>
+__global__ void __launch_bounds__(256, 4) in_bwd_reduce_pipe_kernel(const InBwdP p) {
+    irc::pdl_prologue();
+    extern __shared__ float sh[];
+    constexpr int NT = kTwo ? 3 : 2;
+    const int nt = blockDim.x;
+    uint4* slot = reinterpret_cast<uint4*>(sh) + threadIdx.x;         // [kPipeD][NT][nt]
+    const int C8 = p.C >> 3;
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int n = blockIdx.y, c = cv * 8;
+    const bf16* gb = p.g1.at(n, 0, 0, c); const long long grs = (long long)p.g1.wp * p.g1.ld; const int gps = (int)p.g1.ld;
+    const bf16* zb = p.z.at(n, 0, 0, c); const long long zrs = (long long)p.z.wp * p.z.ld; const int zps = (int)p.z.ld;
+    const bf16* hb = kTwo ? p.g2.at(n, 0, 0, c) : nullptr; const long long hrs = kTwo ? (long long)p.g2.wp * p.g2.ld : 0; const int hps = kTwo ? (int)p.g2.ld : 0;
+    int iy = blockIdx.x, ix = lane, cy = blockIdx.x, cx = lane;
+    auto issue = [&](int st) {
+        if (iy < p.H) {
+            cp_async16(slot + (st * NT + 0) * nt, gb + iy * grs + ix * gps);
+            cp_async16(slot + (st * NT + 1) * nt, zb + iy * zrs + ix * zps);
+            if (kTwo) cp_async16(slot + (st * NT + 2) * nt, hb + iy * hrs + ix * hps);
+            ix += L; if (ix >= p.W) { ix = lane; iy += gridDim.x; }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int st = 0; st < kPipeD; ++st) issue(st);
+    float mu[8], rs[8];
+    moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mu[k] = -mu[k] * rs[k];
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int st = 0;
+    while (cy < p.H) {
+        cp_async_wait<kPipeD - 1>();
+        const uint4 gr = slot[(st * NT + 0) * nt], zr = slot[(st * NT + 1) * nt];
+        uint4 hr = make_uint4(0, 0, 0, 0);
+        if (kTwo) hr = slot[(st * NT + 2) * nt];
+        issue(st);
+        float g[8], zv[8];
+        unpack8(gr, g); unpack8(zr, zv);
+        if (kTwo) {
+            float u[8];
+            unpack8(hr, u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] += u[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float xh = fmaf(zv[k], rs[k], mu[k]);
+            const float gd = g[k] * dactf(xh, p.act, p.slope);
+            s1[k] += gd; s2[k] = fmaf(gd, xh, s2[k]);
+        }
+        cx += L; if (cx >= p.W) { cx = lane; cy += gridDim.x; }
+        st = st + 1 == kPipeD ? 0 : st + 1;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sh[(lane * C8 + cv) * 16 + j * 2] = s1[j]; sh[(lane * C8 + cv) * 16 + j * 2 + 1] = s2[j]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C8 * 16; i += blockDim.x) {
+        float a = 0.f;
+        for (int l = 0; l < L; ++l) a += sh[l * C8 * 16 + i];
+        p.part[((long long)blockIdx.x * gridDim.y + n) * p.C * 2 + i] = a;
+    }
+    if (p.counters) finalize_by_last_block(p.part, p.bsum, n, p.C * 2, p.counters);
+}
+
+template <bool kTwo>
+__global__ void __launch_bounds__(256, 4) in_bwd_apply_pipe_kernel(const InBwdP p) {
+    irc::pdl_prologue();
+    extern __shared__ float sh[];
+    constexpr int NT = kTwo ? 3 : 2;
+    const int nt = blockDim.x;
+    uint4* slot = reinterpret_cast<uint4*>(sh) + threadIdx.x;
+    const int C8 = p.C >> 3;
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int c = cv * 8;
+    const int rows = p.n_img * p.H;
+    int irow = blockIdx.x, ix = lane, crow = blockIdx.x, cx = lane;
+    auto issue = [&](int st) {
+        if (irow < rows) {
+            const int n = irow / p.H, y = irow - n * p.H;
+            cp_async16(slot + (st * NT + 0) * nt, p.g1.at(n, y, ix, c));
+            cp_async16(slot + (st * NT + 1) * nt, p.z.at(n, y, ix, c));
+            if (kTwo) cp_async16(slot + (st * NT + 2) * nt, p.g2.at(n, y, ix, c));
+            ix += L; if (ix >= p.W) { ix = lane; irow += gridDim.x; }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int st = 0; st < kPipeD; ++st) issue(st);
+    float mu[8], rs[8], b1[8], b2[8];
+    int cur_n = -1, st = 0;
+    while (crow < rows) {
+        const int n = crow / p.H, y = crow - n * p.H;
+        if (n != cur_n && p.stats) {
+            cur_n = n;
+            moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+            const float4* bp = reinterpret_cast<const float4*>(p.bsum + ((long long)n * p.C + c) * 2);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 b = __ldg(bp + q);
+                b1[q * 2] = b.x * p.inv_cnt; b2[q * 2] = b.y * p.inv_cnt; b1[q * 2 + 1] = b.z * p.inv_cnt; b2[q * 2 + 1] = b.w * p.inv_cnt;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mu[k] = -mu[k] * rs[k];
+        }
+        cp_async_wait<kPipeD - 1>();
+        const uint4 gr = slot[(st * NT + 0) * nt], zr = slot[(st * NT + 1) * nt];
+        uint4 hr = make_uint4(0, 0, 0, 0);
+        if (kTwo) hr = slot[(st * NT + 2) * nt];
+        issue(st);
+        float g[8], zv[8], o[8];
+        unpack8(gr, g); unpack8(zr, zv);
+        if (kTwo) {
+            float u[8];
+            unpack8(hr, u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] += u[k];
+        }
+        if (p.stats) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float xh = fmaf(zv[k], rs[k], mu[k]);
+                const float gd = g[k] * dactf(xh, p.act, p.slope);
+                o[k] = rs[k] * (gd - b1[k] - xh * b2[k]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = g[k] * dactf(zv[k], p.act, p.slope);
+        }
+        store8(const_cast<bf16*>(p.dz.at(n, y, cx, c)), o);
+        cx += L; if (cx >= p.W) { cx = lane; crow += gridDim.x; }
+        st = st + 1 == kPipeD ? 0 : st + 1;
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------
 // Single-pass InstanceNorm(+activation) backward for small feature maps (H*W <= 4096: the ResNet bottleneck and the
 // PatchGAN layers).  One thread-block CLUSTER owns one (image, 32-channel group): its CTAs split the pixels, every thread
 // keeps its <= 8 pixels of g and z (16 bytes each) in REGISTERS, the (sum gd, sum gd*xhat) partials are combined inside
@@ -751,12 +954,6 @@ __device__ __forceinline__ int mirror_src(int v, int n, int p) {
     return INT_MIN;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
 
 // Sum 16 per-thread values over the 8 lanes of a warp that share (lane & 3) - lane bits 2..4 - as a reduce-scatter:
 // every step halves the number of values a thread carries (8 + 4 + 2 shuffles instead of 3 x 16).  On return the thread
@@ -1210,6 +1407,12 @@ extern "C" int irc_in_stats(const irc_view* z, int C, int n_img, int H, int W, f
         irc::launch(in_stats_kernel, dim3(1, n_img), threads, smem, (cudaStream_t)stream, mk(*z), C, H, W, stats, nullptr, nullptr);
         return irc_check_launch("irc_in_stats");
     }
+    if (!z->s2d_c) {
+        const size_t smem_p = smem > (size_t)kPipeD * threads * 16 ? smem : (size_t)kPipeD * threads * 16;
+        irc::launch(in_stats_pipe_kernel, dim3(chunks, n_img), threads, smem_p, (cudaStream_t)stream, mk(*z), C, H, W, work, stats,
+                    (unsigned*)(work + work_floats - kCounterFloats));
+        return irc_check_launch("irc_in_stats");
+    }
     irc::launch(in_stats_kernel, dim3(chunks, n_img), threads, smem, (cudaStream_t)stream, mk(*z), C, H, W, work, stats,
                                                                                  (unsigned*)(work + work_floats - kCounterFloats));
     return irc_check_launch("irc_in_stats");
@@ -1351,7 +1554,19 @@ extern "C" int irc_in_bwd_reduce(const irc_in_bwd_args* a, void* stream) {
     reduce_shape(p.C, p.H, p.W, p.n_img, staged ? a->work_floats - kCounterFloats : 0, threads, L, chunks, smem);
     p.part = chunks == 1 ? p.bsum : a->work;
     p.counters = chunks == 1 ? nullptr : (unsigned*)(a->work + a->work_floats - kCounterFloats);
-    if (!p.ty_idx && !p.tx_idx) irc::launch(in_bwd_reduce_kernel<true>, dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream, p);
+    const bool plain = !p.ty_idx && !p.tx_idx && !p.z.s2d_c && !p.g1.s2d_c && !(p.has2 && p.g2.s2d_c);
+    static bool attr = false;
+    if (!attr) {       // 48 KB of slots + the static ticket flag exceed the default limit
+        cudaFuncSetAttribute(in_bwd_reduce_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        cudaFuncSetAttribute(in_bwd_reduce_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        attr = true;
+    }
+    if (plain) {
+        const size_t need = (size_t)kPipeD * (p.has2 ? 3 : 2) * threads * 16;
+        const size_t smem_p = smem > need ? smem : need;
+        if (p.has2) irc::launch(in_bwd_reduce_pipe_kernel<true>, dim3(chunks, p.n_img), threads, smem_p, (cudaStream_t)stream, p);
+        else irc::launch(in_bwd_reduce_pipe_kernel<false>, dim3(chunks, p.n_img), threads, smem_p, (cudaStream_t)stream, p);
+    } else if (!p.ty_idx && !p.tx_idx) irc::launch(in_bwd_reduce_kernel<true>, dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream, p);
     else irc::launch(in_bwd_reduce_kernel<false>, dim3(chunks, p.n_img), threads, smem, (cudaStream_t)stream, p);
     return irc_check_launch("irc_in_bwd_reduce");
 }
@@ -1365,7 +1580,14 @@ extern "C" int irc_in_bwd_apply(const irc_in_bwd_args* a, void* stream) {
     row_block(p.C, p.W, threads, L);
     const long long rows = (long long)p.n_img * p.H;
     const unsigned grid = (unsigned)(rows < 65535 * 16 ? rows : 65535 * 16);
-    if (!p.ty_idx && !p.tx_idx) irc::launch(in_bwd_apply_kernel<true>, grid, threads, 0, (cudaStream_t)stream, p);
+    const bool plain = !p.ty_idx && !p.tx_idx && !p.z.s2d_c && !p.g1.s2d_c && !(p.has2 && p.g2.s2d_c) && !p.dz.s2d_c;
+    if (plain) {
+        const size_t smem_p = (size_t)kPipeD * (p.has2 ? 3 : 2) * threads * 16;
+        // a few rows per block so that the prefetch pipeline runs across row boundaries
+        const unsigned gp = (unsigned)(rows < (long long)irc_num_sms() * 16 ? rows : (long long)irc_num_sms() * 16);
+        if (p.has2) irc::launch(in_bwd_apply_pipe_kernel<true>, gp, threads, smem_p, (cudaStream_t)stream, p);
+        else irc::launch(in_bwd_apply_pipe_kernel<false>, gp, threads, smem_p, (cudaStream_t)stream, p);
+    } else if (!p.ty_idx && !p.tx_idx) irc::launch(in_bwd_apply_kernel<true>, grid, threads, 0, (cudaStream_t)stream, p);
     else irc::launch(in_bwd_apply_kernel<false>, grid, threads, 0, (cudaStream_t)stream, p);
     return irc_check_launch("irc_in_bwd_apply");
 }
