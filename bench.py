@@ -235,21 +235,54 @@ def main():
             dist.barrier()
             dist.destroy_process_group()
 
+    # ---- every launcher of one eager step bracketed by CUDA events: the HBM-bound kernels against the measured copy peak
+    # (all ranks run the steps - they contain the gradient all-reduces - rank 0 reports)
+    hbm_kernels, dom = [], None
+    be.time_all_launchers()
+    ts.step(ir_d, rgb_d)
+    be.timers_all = []
+    ts.step(ir_d, rgb_d)
+    torch.cuda.synchronize()
+    agg = {}
+    for name, tag, e0, e1 in be.timers_all:
+        a = agg.setdefault((name, tag), [0, 0.0]); a[0] += 1; a[1] += e0.elapsed_time(e1)
+    be.timers_all = None
+    tot = sum(v[1] for v in agg.values())
     if args.breakdown_all and rank == 0:
-        be.time_all_launchers()
-        ts.step(ir_d, rgb_d)
-        be.timers_all = []
-        ts.step(ir_d, rgb_d)
-        torch.cuda.synchronize()
-        agg = {}
-        for name, tag, e0, e1 in be.timers_all:
-            a = agg.setdefault((name, tag), [0, 0.0]); a[0] += 1; a[1] += e0.elapsed_time(e1)
-        be.timers_all = None
-        tot = sum(v[1] for v in agg.values())
         with open(args.breakdown_all, "w") as f:
             f.write(f"launcher,args,calls,ms_total,ms_per_call,share   # one eager step, CUDA events per call, total {tot:.3f} ms\n")
             for (name, tag), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 f.write(f"{name},\"{tag}\",{n},{t:.4f},{t / n:.4f},{t / tot:.3f}\n")
+    # algorithmic bytes (SURVEY.md §8d, bf16 frames / fp32 images): what one ideal pass has to move
+    px = B * H * W
+    nG, nD = ts.G.arena.size, ts.D2.arena.size
+    want = [
+        ("Downsample fused with IN+ReLU (down1, 128 ch)", "gather", f"128,{B},{H // 2},{W // 2},1,0", (px + px // 4) * 128 * 2),
+        ("UpsampleAA fused with IN+ReLU (up2, 128 ch)", "gather", f"128,{B},{H},{W},1,0", (px + px // 4) * 128 * 2),
+        ("UpsampleAA^T (up2 backward)", "gather", f"128,{B},{H // 2},{W // 2},0,0", (px + px // 4) * 128 * 2),
+        ("Downsample^T, two sources (down1 backward)", "gather", f"128,{B},{H},{W},0,0", (px + 2 * (px // 4)) * 128 * 2),
+        ("InstanceNorm+ReLU backward, 128 ch full res (two passes move 5 units, 3 are algorithmic)", "in_bwd", f"128,{B},{H},{W}", 3 * px * 128 * 2),
+        ("InstanceNorm statistics, 128 ch full res", "in_stats", f"128,{B},{H},{W}", px * 128 * 2),
+        ("L1 + TV value and gradient", "pixel_loss", "", 3 * B * 3 * H * W * 4),
+        ("SSIM forward (2 reads; the 3 saved maps are extra)", "ssim_fwd", "", 2 * B * 3 * H * W * 4),
+        ("SSIM backward", "ssim_bwd", "", 3 * B * 3 * H * W * 4),
+        ("Adam (G + D arenas, 28 B/param)", "adam", "", 28 * (nG + nD)),
+    ]
+    for label, name, tag, nbytes in want:
+        if (name, tag) in agg:
+            n, t = agg[(name, tag)]
+            gbs = nbytes / (t * 1e-3) / 1e9
+            hbm_kernels.append(dict(kernel=label, launches=n, algorithmic_mb=round(nbytes / 1e6, 1), us=round(t * 1e3, 1), gb_s=round(gbs, 0),
+                                    frac=round(gbs / pk["hbm"], 3)))
+    if ("conv_gemm", "G.res:fwd") in agg:
+        n, t = agg[("conv_gemm", "G.res:fwd")]
+        fl = 2.0 * 256 * 256 * 9 * B * (H // 4) * (W // 4)
+        dom = dict(kernel="conv_gemm_kernel, ResNet-block shape (M=B*H/4*W/4, N=256, K=2304): 18 of the 80 conv launches, same shape as the "
+                          "18 data-gradient launches", launches=n, gflop_per_launch=fl / 1e9, us_per_launch=t / n * 1e3,
+                   achieved=fl / (t / n * 1e-3) / 1e12, peak=pk["tf"], unit="TFLOP/s", frac=fl / (t / n * 1e-3) / 1e12 / pk["tf"],
+                   traffic=38.09e6 if (B, H, W) == (16, 256, 256) else None,
+                   traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of this launch, profiles/ncu_full_gemm_r1_final_raw.csv "
+                                  "(algorithmic: 35.7 MB operand frame + 1.2 MB weights read; the 35.7 MB output stays in L2)")
 
     if rank != 0:
         shutdown()
@@ -278,11 +311,15 @@ def main():
         gpu_launches=launches_per_step * K,
         clocks=clocks,
         roofline=dict(bound="tensor", kernel="conv_gemm_kernel (all forward + data-gradient convolutions of one step)",
-                      achieved=conv_tf, peak=pk["tf"], unit="TFLOP/s", frac=conv_tf / pk["tf"], traffic=None,
+                      achieved=conv_tf, peak=pk["tf"], unit="TFLOP/s", frac=conv_tf / pk["tf"],
+                      traffic=(dom or {}).get("traffic"), traffic_note="per launch of the ResNet-block shape, see roofline_dominant_launch",
                       peak_source=pk["src"] + " bf16_tflops_sustained", launches_per_step=len(conv),
                       share_of_step=sum(r[4] for r in conv) / (sec * 1e3)),
         roofline_wgrad=dict(bound="tensor", kernel="tn_gemm_kernel (all weight gradients of one step)", achieved=tn_tf, peak=pk["tf"],
                             unit="TFLOP/s", frac=tn_tf / pk["tf"], launches_per_step=len(tn), share_of_step=sum(r[4] for r in tn) / (sec * 1e3)),
+        roofline_dominant_launch=dom,
+        hbm_kernels=hbm_kernels,
+        hbm_peak_gb_s=pk["hbm"],
         gemm_ms_per_step=gemm_ms,
         cpu_baseline=cpu_baseline,
         losses={k: round(v, 5) for k, v in losses.items()},
