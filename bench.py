@@ -148,9 +148,14 @@ def main():
         raise SystemExit("bench.py needs a B200: there is no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line: whatever native libraries print while the job runs (NCCL's version banner ...)
+    # goes to stderr; file descriptor 1 is restored for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B, (H, W) = args.batch, args.size
     W_, K = max(args.warmup, 3), args.steps
@@ -324,7 +329,10 @@ def main():
         cpu_baseline=cpu_baseline,
         losses={k: round(v, 5) for k, v in losses.items()},
     )
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     shutdown()
 
 
