@@ -246,6 +246,14 @@ int irc_adam(float* p, const float* g, float* m, float* v, long long n, const fl
 int irc_pack_bf16(const float* src, const int* map, long long n, void* dst, void* stream);
 /* dst[i] = sum_s src[s*split_stride + map[i]]: split weight-gradient partials -> OIHW fp32. */
 int irc_gather_sum(const float* src, const int* map, long long n, int splits, long long split_stride, float* dst, void* stream);
+/* The same for a table of jobs in ONE launch (all weight gradients of a network, irc:1650 / :1680).  `jobs_dev` is a DEVICE
+ * array of njobs entries whose `start` fields are the exclusive prefix sums of `n`; total = sum of n. */
+typedef struct irc_sum_job {
+    const float* src; const int* map; float* dst;
+    long long n, split_stride, start;
+    int splits, pad_;
+} irc_sum_job;
+int irc_gather_sum_multi(const irc_sum_job* jobs_dev, int njobs, long long total, void* stream);
 
 /* ---- stand-alone anti-aliased resampling on fp32 NCHW ---------------------------------- */
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "irc_in_stats", "irc_gather", "irc_in_apply_fused", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_in_bwd_fused", "irc_maxpool2", "irc_maxpool2_bwd",
     "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
     "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics",
-    "irc_adam", "irc_pack_bf16", "irc_gather_sum", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
+    "irc_adam", "irc_pack_bf16", "irc_gather_sum", "irc_gather_sum_multi", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
 ]
 
 
@@ -101,6 +101,11 @@ class Col2imArgs(C.Structure):
         ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int), ("row_mode", C.c_int),
         ("scale", C.c_void_p), ("out", C.c_void_p), ("accumulate", C.c_int),
     ]
+
+
+class SumJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("map", C.c_void_p), ("dst", C.c_void_p), ("n", C.c_longlong), ("split_stride", C.c_longlong),
+                ("start", C.c_longlong), ("splits", C.c_int), ("pad_", C.c_int)]
 
 
 class TapArgs(C.Structure):
@@ -271,6 +276,8 @@ class CudaBackend:
         self.conv_dbg = None
         self.fused_in_bwd = os.environ.get("IRC_FUSED_IN_BWD", "1") != "0"   # cluster-resident single-pass InstanceNorm backward
         self.fused_in_apply = os.environ.get("IRC_FUSED_IN_APPLY", "1") != "0"
+        self.batch_sums = os.environ.get("IRC_BATCH_SUMS", "1") != "0"      # one launch for all split-K weight-gradient reductions
+        self._pending, self._sum_tables = [], {}
         self.gather_mode = os.environ.get("IRC_GATHER", "auto")     # lean | tiled | generic (stencil gather kernel choice)
         self.conv_epilogue_direct = int(os.environ.get("IRC_EPI_DIRECT", "0"))
         self.conv_dbg_mode = 0
@@ -537,6 +544,29 @@ class CudaBackend:
     def gather_sum(self, src, map_, splits, split_stride, dst):
         check(self.L.irc_gather_sum(_p(src), _p(map_), C.c_longlong(map_.numel()), splits, C.c_longlong(split_stride), _p(dst),
                                     _stream())); self.launches += 1
+
+    def gather_sum_deferred(self, src, map_, splits, split_stride, dst):
+        """queue a gather_sum; flush_sums() runs everything queued since the last flush in ONE launch"""
+        if not self.batch_sums:
+            return self.gather_sum(src, map_, splits, split_stride, dst)
+        self._pending.append((src, map_, int(splits), int(split_stride), dst))
+
+    def flush_sums(self):
+        if not self._pending:
+            return
+        key = tuple((a.data_ptr(), m.data_ptr(), s, st, d.data_ptr(), m.numel()) for a, m, s, st, d in self._pending)
+        ent = self._sum_tables.get(key)
+        if ent is None:
+            arr = (SumJob * len(key))()
+            start = 0
+            for j, (a, m, s, st, d, n) in zip(arr, key):
+                j.src, j.map, j.dst, j.n, j.split_stride, j.start, j.splits = a, m, d, n, st, start, s
+                start += n
+            dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).cuda()
+            ent = self._sum_tables[key] = (dev, len(key), start, list(self._pending))      # keeps the buffers alive
+        dev, nj, total, _ = ent
+        self._pending = []
+        check(self.L.irc_gather_sum_multi(_p(dev), nj, C.c_longlong(total), _stream())); self.launches += 1
 
     def stencil_nchw(self, x, out, tables: Tables, accumulate=False):
         n, c, hi, wi = x.shape

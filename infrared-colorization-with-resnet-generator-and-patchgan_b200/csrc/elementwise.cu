@@ -1316,38 +1316,34 @@ __global__ void colsum_kernel(const bf16* a, long long rows, long long ld, int o
 // its own pixel: race-free) and clears them.  Touches O(p * perimeter) pixels instead of a full pass.
 __global__ void fold_inplace_kernel(bf16* g, long long ld, int off, int C, int n_img, int H, int W, int p) {
     irc::pdl_prologue();
+    // grid = (column chunks, rows, images): one pixel per thread, so the few border pixels that have work are spread over
+    // many blocks and the pass costs one load-add-store round trip instead of a serial walk along the border rows
     const int C8 = C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
     const int c = cv * 8;
     const int Hp = H + 2 * p, Wp = W + 2 * p;
-    for (int row = blockIdx.x; row < n_img * H; row += gridDim.x) {
-        const int n = row / H, y = row - n * H;
-        const int my = (y >= 1 && y <= p) ? p - y : ((y >= H - 1 - p && y <= H - 2) ? 2 * (H - 1) - y + p : -1);   // mirrored padded row
-        // rows that receive a mirrored row visit every column; the others only the 2p columns next to the side borders
-        const int count = my >= 0 ? W : 2 * p;
-        bf16* base = g + (long long)n * Hp * Wp * ld + off + c;
-        for (int i = lane; i < count; i += L) {
-            const int x = my >= 0 ? i : (i < p ? 1 + i : W - 1 - p + (i - p));
-            const int mx = (x >= 1 && x <= p) ? p - x : ((x >= W - 1 - p && x <= W - 2) ? 2 * (W - 1) - x + p : -1);
-            if (my < 0 && mx < 0) continue;
-            float acc[8], v[8];
-            const float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            bf16* self = base + ((long long)(y + p) * Wp + (x + p)) * ld;
-            load8(self, acc);
-            // every ring pixel mirrors onto exactly one interior pixel, so the thread that consumes it also clears it
-            // (the folded frame can then serve as a zero-ring addend / operand)
-            if (my >= 0) { bf16* q = base + ((long long)my * Wp + (x + p)) * ld; load8(q, v); store8(q, zero);
+    const int n = blockIdx.z, y = blockIdx.y, x = blockIdx.x * L + lane;
+    if (x >= W) return;
+    const int my = (y >= 1 && y <= p) ? p - y : ((y >= H - 1 - p && y <= H - 2) ? 2 * (H - 1) - y + p : -1);   // mirrored padded row
+    const int mx = (x >= 1 && x <= p) ? p - x : ((x >= W - 1 - p && x <= W - 2) ? 2 * (W - 1) - x + p : -1);
+    if (my < 0 && mx < 0) return;
+    bf16* base = g + (long long)n * Hp * Wp * ld + off + c;
+    float acc[8], v[8];
+    const float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bf16* self = base + ((long long)(y + p) * Wp + (x + p)) * ld;
+    load8(self, acc);
+    // every ring pixel mirrors onto exactly one interior pixel, so the thread that consumes it also clears it
+    // (the folded frame can then serve as a zero-ring addend / operand)
+    if (my >= 0) { bf16* q = base + ((long long)my * Wp + (x + p)) * ld; load8(q, v); store8(q, zero);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
-            if (mx >= 0) { bf16* q = base + ((long long)(y + p) * Wp + mx) * ld; load8(q, v); store8(q, zero);
+        for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
+    if (mx >= 0) { bf16* q = base + ((long long)(y + p) * Wp + mx) * ld; load8(q, v); store8(q, zero);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
-            if (my >= 0 && mx >= 0) { bf16* q = base + ((long long)my * Wp + mx) * ld; load8(q, v); store8(q, zero);
+        for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
+    if (my >= 0 && mx >= 0) { bf16* q = base + ((long long)my * Wp + mx) * ld; load8(q, v); store8(q, zero);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
-            store8(self, acc);
-        }
-    }
+        for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
+    store8(self, acc);
 }
 
 int grid_for(long long total, int threads) {
@@ -1657,6 +1653,7 @@ extern "C" int irc_fold_inplace(void* g, long long ld, int chan_off, int C, int 
     if (p < 1 || 2 * p + 2 > H || 2 * p + 2 > W) return irc_set_error(IRC_ERR_BAD_ARG, "irc_fold_inplace: image too small for the pad width");
     int threads, L;
     row_block(C, W, threads, L);
-    irc::launch(fold_inplace_kernel, n_img * H, threads, 0, (cudaStream_t)stream, (bf16*)g, ld, chan_off, C, n_img, H, W, p);
+    if (H > 65535 || n_img > 65535) return irc_set_error(IRC_ERR_BAD_ARG, "irc_fold_inplace: extent too large");
+    irc::launch(fold_inplace_kernel, dim3((W + L - 1) / L, H, n_img), threads, 0, (cudaStream_t)stream, (bf16*)g, ld, chan_off, C, n_img, H, W, p);
     return irc_check_launch("irc_fold_inplace");
 }

@@ -56,6 +56,25 @@ __global__ void gather_sum_kernel(const float* __restrict__ src, const int* __re
     }
 }
 
+// several gather_sum jobs in one launch: element i of the concatenated index space belongs to the job whose
+// [start, start + n) range contains it (binary search over <= a few dozen jobs; the table sits in L1 / constant cache)
+__global__ void gather_sum_multi_kernel(const irc_sum_job* __restrict__ jobs, int njobs, long long total) {
+    irc::pdl_prologue();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = njobs - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (jobs[mid].start <= i) lo = mid; else hi = mid - 1;
+        }
+        const irc_sum_job jb = jobs[lo];
+        const long long e = i - jb.start;
+        const int j = jb.map[e];
+        float a = 0.f;
+        if (j >= 0) for (int s = 0; s < jb.splits; ++s) a += jb.src[(long long)s * jb.split_stride + j];
+        jb.dst[e] = a;
+    }
+}
+
 int grid_for(long long total, int threads) {
     long long b = (total + threads - 1) / threads;
     const long long cap = (long long)irc_num_sms() * 8;
@@ -83,4 +102,10 @@ extern "C" int irc_gather_sum(const float* src, const int* map, long long n, int
     if (!src || !map || !dst) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather_sum: null");
     irc::launch(gather_sum_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, src, map, n, splits, split_stride, dst);
     return irc_check_launch("irc_gather_sum");
+}
+
+extern "C" int irc_gather_sum_multi(const irc_sum_job* jobs_dev, int njobs, long long total, void* stream) {
+    if (!jobs_dev || njobs <= 0 || total <= 0) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather_sum_multi: empty job table");
+    irc::launch(gather_sum_multi_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, jobs_dev, njobs, total);
+    return irc_check_launch("irc_gather_sum_multi");
 }

@@ -167,6 +167,58 @@ __global__ void col2im_kernel(const Col2imP p) {
     }
 }
 
+// Row-staged version: one block per (image, output row).  The (at most k) operand rows that contribute are read with
+// coalesced 16-byte loads - only the 16-byte chunks that hold the k*C columns of that kernel row - and transposed into
+// shared memory as T[kernel row][column][ox] (fp32), so that the k*k taps of an output pixel are conflict-free reads with
+// lanes running along x.  Same summation order as col2im_kernel (r outer, s inner): identical bits.
+__global__ void __launch_bounds__(256) col2im_rows_kernel(const Col2imP p, int pitch) {
+    irc::pdl_prologue();
+    extern __shared__ float T[];                  // [k][k*C][pitch]
+    const int n = blockIdx.y, y = blockIdx.x;
+    const int kC = p.k * p.C, Wo = p.rm.Wo;
+    for (int r = 0; r < p.k; ++r) {
+        const int ty = y + p.pad - r;
+        if (ty < 0 || ty % p.stride || ty / p.stride >= p.rm.Ho) continue;          // uniform over the block
+        const int oy = ty / p.stride;
+        const int ch_lo = (r * kC) >> 3, nch = (((r + 1) * kC - 1) >> 3) - ch_lo + 1;
+        float* Tr = T + (size_t)r * kC * pitch;
+        for (int idx = threadIdx.x; idx < Wo * nch; idx += blockDim.x) {
+            const int ox = idx / nch, g = ch_lo + (idx - ox * nch);
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.de + p.rm.encode(n, oy, ox) * p.ld + g * 8));
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = g * 8 + j - r * kC;
+                if (col >= 0 && col < kC) {
+                    const uint32_t h = (j & 1) ? (w[j >> 1] & 0xffff0000u) : (w[j >> 1] << 16);
+                    Tr[col * pitch + ox] = __uint_as_float(h);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < p.c_out * p.W; idx += blockDim.x) {
+        const int co = idx / p.W, x = idx - co * p.W;
+        const int c = p.c_first + co;
+        float acc = 0.f;
+        for (int r = 0; r < p.k; ++r) {
+            const int ty = y + p.pad - r;
+            if (ty < 0 || ty % p.stride || ty / p.stride >= p.rm.Ho) continue;
+            const float* Tr = T + ((size_t)r * kC + c) * pitch;
+            for (int s_ = 0; s_ < p.k; ++s_) {
+                const int tx = x + p.pad - s_;
+                if (tx < 0 || tx % p.stride) continue;
+                const int ox = tx / p.stride;
+                if (ox >= Wo) continue;
+                acc += Tr[(size_t)s_ * p.C * pitch + ox];
+            }
+        }
+        if (p.scale) acc *= __ldg(p.scale + c);
+        const long long o = (((long long)n * p.c_out + co) * p.H + y) * p.W + x;
+        if (p.accumulate) p.out[o] += acc; else p.out[o] = acc;
+    }
+}
+
 struct TapP {
     int nshift, nco;
     int shifts[IRC_MAX_TAPS];
@@ -299,6 +351,14 @@ extern "C" int irc_col2im(const irc_col2im_args* a, void* stream) {
     p.rm.mode = a->row_mode; p.rm.n_img = a->n_img; p.rm.Ho = a->Ho; p.rm.Wo = a->Wo;
     p.out = a->out; p.accumulate = a->accumulate;
     const long long total = (long long)a->n_img * a->c_out * a->H * a->W;
+    const int pitch = a->Wo | 1;                                  // odd pitch: the transposing stores spread over the banks
+    const size_t smem = (size_t)a->k * a->k * a->C * pitch * sizeof(float);
+    if (a->k * a->k * a->C <= 64 && !(a->ld % 8) && !((uintptr_t)a->de & 15) && smem <= 160 * 1024 && a->H <= 65535 && a->n_img <= 65535) {
+        static size_t attr = 48 * 1024;
+        if (smem > attr) { cudaFuncSetAttribute(col2im_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = 160 * 1024; }
+        irc::launch(col2im_rows_kernel, dim3(a->H, a->n_img), 256, smem, (cudaStream_t)stream, p, pitch);
+        return irc_check_launch("irc_col2im(rows)");
+    }
     irc::launch(col2im_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, p);
     return irc_check_launch("irc_col2im");
 }

@@ -95,7 +95,8 @@ class ConvOp:
         self.be.note = (self.name, "wgrad", self.flops)
         self.be.tn_gemm(dz, 0, lay.N, x, x_chan_off, lay.K, k_rows, [0] * lay.T, self.taps, self.partial,
                         lay.K, lay.T * lay.K, 1, self.splits, lay.N * lay.T * lay.K)
-        self.be.gather_sum(self.partial, lay.unpack, self.splits, lay.N * lay.T * lay.K, self.grad_flat)
+        # queued: the network's backward pass flushes all its split-K reductions in one launch (be.flush_sums)
+        self.be.gather_sum_deferred(self.partial, lay.unpack, self.splits, lay.N * lay.T * lay.K, self.grad_flat)
 
 
 # ==========================================================================================
@@ -274,6 +275,7 @@ class GeneratorEngine:
             c1.dgrad(self.dZa.t, nxt.t, addend=View(cur.t, 0, 0, 0))
             be.fold_inplace(nxt.t, 0, 256, B, H4, W4, 1)
             cur = nxt
+        be.flush_sums()                   # weight gradients of outc, up2, up1 and the ResNet blocks are final
         if after_blocks is not None:
             after_blocks()
         # down2 (through Downsample^T)
@@ -292,6 +294,7 @@ class GeneratorEngine:
         be.in_bwd(self.Z0.view(), self.Gcat2.view(128), self.dZ0.view(), 64, B, H, W, stats=self.st0, cnt=H * W, eps=EPS, act=ACT_RELU,
                   g2=self.Gx0.view(), bsum=self.bsum)
         self.inc.wgrad(self.dZ0.t, self.E_in, 0, self.dZ0.rows)
+        be.flush_sums()
 
 
 # ==========================================================================================
@@ -434,6 +437,7 @@ class DiscriminatorEngine:
         if want_wgrad:
             be.colsum(self.dZ0, 0, 64, self.arena.view("model.0.bias", G), row_img=self.row_img0)
             self.c0.wgrad(self.dZ0, self.E0, 0, self.rows0)
+        be.flush_sums()
         if dinput is not None:
             self.c0.dgrad(self.dZ0, self.dE0)
             be.col2im(self.dE0, 4, c_first, dinput.shape[1], n, self.H, self.W, 4, 2, 1, self.H1, self.W1, 2, None, dinput, accumulate)

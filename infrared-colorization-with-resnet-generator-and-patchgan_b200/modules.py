@@ -386,6 +386,7 @@ class _ResBlockEngine:
         be.in_bwd(self.Za.view(), self.Gh.pview(), self.dZa.view(), C, B, H, W, stats=self.sta, cnt=n, eps=E.EPS, act=E.ACT_RELU,
                   tables=self.fold, bsum=self.bsum)
         self.c1.wgrad(self.dZa.t, self.X.t, 0, self.dZa.rows)
+        be.flush_sums()
         self.c1.dgrad(self.dZa.t, self.Gx.t)
         be.gather(self.Gx.pview(), self.dX.view(), C, B, H, W, 1, 0, tables=self.fold, res=self.dY.view())
         return self._interior(self.dX)

@@ -417,6 +417,12 @@ class RefBackend:
             acc += src[s * split_stride + m.clamp_min(0)]
         dst.copy_(torch.where(m >= 0, acc, torch.zeros_like(acc)))
 
+    def gather_sum_deferred(self, src, map_, splits, split_stride, dst):
+        self.gather_sum(src, map_, splits, split_stride, dst)
+
+    def flush_sums(self):
+        pass
+
     def stencil_nchw(self, x, out, tables, accumulate=False):
         self.launches += 1
         acc = torch.zeros_like(out)
