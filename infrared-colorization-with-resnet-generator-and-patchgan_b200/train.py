@@ -148,6 +148,28 @@ def train_kaist(cfg: M.Config, train_loader=None, val_loader=None, use_graph: bo
     return history
 
 
+def merge_test_rows(rows: List[Dict]) -> List[Dict]:
+    """Data-parallel test mode (BASELINE config 5): every rank has evaluated the batches with
+    index % world == rank; gather the per-image rows on all ranks in the loader's order.  Identity without a process group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return rows
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, rows)
+    merged = [r for part in parts for r in part]
+    merged.sort(key=lambda r: r["_order"])
+    return merged
+
+
+def summarize_rows(rows: List[Dict]) -> Optional[Dict]:
+    """running means of irc:1425-1431 / :1467-1480 over the per-image rows"""
+    if not rows:
+        return None
+    count = len(rows)
+    return dict(count=count, mean_mae=sum(r["mae"] for r in rows) / count, mean_mse=sum(r["mse"] for r in rows) / count,
+                mean_psnr=sum(r["psnr"] for r in rows if np.isfinite(r["psnr"])) / count)
+
+
 def run_test(cfg: M.Config, loader=None):
     """Test-mode core of irc:1333-1514: batched generator inference, on-device truncating quantisation and
     MAE/MSE/PSNR per image, `metrics_test.csv` in the reference's format.  Image files, collages and the top-K
@@ -167,29 +189,32 @@ def run_test(cfg: M.Config, loader=None):
     else:
         print(f"Warning: generator weights not found at {cfg.test_G_weights}. Using randomly initialized model.")
     model.eval()
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
     rows: List[Dict] = []
     preds = []
     with torch.no_grad():
         for bi, batch in enumerate(loader):
+            if bi % world != rank:            # images are independent: shard the batches, no data-path collective
+                continue
             ir = batch["ir"].to(device)
             fake = model(ir)
             names = batch.get("name") or [f"img_{bi:05d}_{j}.png" for j in range(ir.shape[0])]
             if "rgb" in batch and batch["rgb"] is not None:
                 gt01 = (batch["rgb"].to(device).float() + 1.0) * 0.5 if batch.get("rgb_range", "pm1") == "pm1" else batch["rgb"].to(device).float()
                 u8, mae, mse, psnr = batch_metrics(fake, gt01)
-                for n_, a, b, c in zip(names, mae, mse, psnr):
-                    rows.append({"file": n_, "mae": a, "mse": b, "psnr": c, "ssim": None})
+                for j, (n_, a, b, c) in enumerate(zip(names, mae, mse, psnr)):
+                    rows.append({"file": n_, "mae": a, "mse": b, "psnr": c, "ssim": None, "_order": (bi, j)})
             else:
                 u8 = torch.empty(ir.shape[0], H, W, 3, device=device, dtype=torch.uint8)
                 M.backend().quantize_metrics(fake.contiguous().float(), None, u8, None)
             preds.append(u8.cpu())
+    rows = merge_test_rows(rows)
     print("Test finished.")
-    summary = None
-    if rows:
-        count = len(rows)
-        mean_mae = sum(r["mae"] for r in rows) / count
-        mean_mse = sum(r["mse"] for r in rows) / count
-        mean_psnr = sum(r["psnr"] for r in rows if np.isfinite(r["psnr"])) / count
+    summary = summarize_rows(rows)
+    if summary is not None and rank == 0:
+        count, mean_mae, mean_mse, mean_psnr = summary["count"], summary["mean_mae"], summary["mean_mse"], summary["mean_psnr"]
         print("\n=== Test Metrics (on images with GT) ===")
         print(f"Count      : {count}")
         print(f"Mean MAE   : {mean_mae:.6f}")
@@ -204,8 +229,7 @@ def run_test(cfg: M.Config, loader=None):
             f.write("\n# Summary\n")
             f.write(f"# count,{count}\n# mean_mae,{mean_mae:.8f}\n# mean_mse,{mean_mse:.8f}\n# mean_psnr,{mean_psnr:.6f}\n# mean_ssim,\n")
         print(f"\nMetrics saved to: {path}")
-        summary = dict(count=count, mean_mae=mean_mae, mean_mse=mean_mse, mean_psnr=mean_psnr)
-    else:
+    elif summary is None:
         print("No metrics were computed (no matching GT RGB images found).")
     return summary, rows, preds
 

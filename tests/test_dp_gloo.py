@@ -67,3 +67,48 @@ def test_two_rank_step_equals_single_process_on_concatenated_batch(tmp_path):
     assert r["eD"] < 1e-4 and r["eG"] < 1e-4, r
     assert r["eP"] < 4.1e-4, r          # Adam's first step is +-lr wherever the gradient sign is numerically fragile
     assert abs(r["hyper"][6] - 0.5) < 1e-7   # the 1/world average is folded into the Adam kernel
+
+
+def _merge_worker(rank, world, port, out):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import irc_b200  # noqa: F401
+    from irc_b200.train import merge_test_rows, summarize_rows
+    allrows = _fake_rows()
+    mine = [r for r in allrows if r["_order"][0] % world == rank]        # run_test's sharding rule
+    merged = merge_test_rows(mine)
+    if rank == 0:
+        torch.save(dict(files=[r["file"] for r in merged], summary=summarize_rows(merged)), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _fake_rows():
+    g = torch.Generator().manual_seed(3)
+    rows = []
+    for bi in range(5):
+        for j in range(3):
+            mse = float(torch.rand(1, generator=g)) * 0.1 + 1e-3
+            rows.append({"file": f"img_{bi}_{j}.png", "mae": float(torch.rand(1, generator=g)), "mse": mse,
+                         "psnr": -10.0 * __import__("math").log10(mse), "ssim": None, "_order": (bi, j)})
+    return rows
+
+
+@pytest.mark.timeout(300)
+def test_sharded_test_mode_metrics_merge_to_the_single_process_summary(tmp_path):
+    """config 5 across ranks: batches are sharded round-robin, the per-image rows are gathered in loader order and the
+    running means (irc:1425-1431) equal those of one process over all images"""
+    sys.path.insert(0, ROOT)
+    import irc_b200  # noqa: F401
+    from irc_b200.train import summarize_rows
+    out = str(tmp_path / "merge.pt")
+    mp.spawn(_merge_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    ref = _fake_rows()
+    assert r["files"] == [x["file"] for x in ref]
+    want = summarize_rows(ref)
+    for k in want:
+        assert abs(r["summary"][k] - want[k]) < 1e-12, k
