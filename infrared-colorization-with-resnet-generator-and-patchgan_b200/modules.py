@@ -276,11 +276,15 @@ class _GenFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, x, *params):
         B, _, H, W = x.shape
-        key = (B, H, W)
-        eng = mod._acquire(key, lambda: E.GeneratorEngine(backend(), B, H, W, x.device, arena=mod.arena))
+        # needs_input_grad stays True for parameters under torch.no_grad() and forward() itself always runs with grad mode
+        # off, so the module records the caller's grad mode (mod._grad_on); without it the engine would never return to
+        # the pool in inference and be rebuilt (0.3 s of host work) on every call
+        grad = mod._grad_on and any(ctx.needs_input_grad)
+        key = (B, H, W, grad)                  # inference engines carry no backward buffers
+        eng = mod._acquire(key, lambda: E.GeneratorEngine(backend(), B, H, W, x.device, arena=mod.arena, training=grad))
         eng.refresh_weights()
         out = eng.forward(x.contiguous().float()).clone()
-        if any(ctx.needs_input_grad):          # False under torch.no_grad()
+        if grad:
             ctx.mod, ctx.eng, ctx.key = mod, eng, key
             ctx.needs = [(k, p.requires_grad) for k, p in zip(_param_order(mod), params)]
         else:
@@ -337,6 +341,7 @@ class ResnetUNetGenerator(_ArenaModule):
         """irc:533-569: returns (image, None).  `encode_only` feature taps are not part of the hot path."""
         if encode_only or layers:
             raise NotImplementedError("encode_only / layers feature taps are never used by the reference's train/test path")
+        self._grad_on = torch.is_grad_enabled()
         return _GenFn.apply(self, x, *self._params()), None
 
 
@@ -399,7 +404,7 @@ class _ResFn(torch.autograd.Function):
         key = (B, H, W)
         eng = mod._acquire(key, lambda: _ResBlockEngine(backend(), B, H, W, C, x.device, mod.arena))
         out = eng.forward(x.contiguous().float())
-        if any(ctx.needs_input_grad):
+        if mod._grad_on and any(ctx.needs_input_grad):
             ctx.mod, ctx.eng, ctx.key = mod, eng, key
             ctx.needs = [(k, p.requires_grad) for k, p in zip(_param_order(mod), params)]
         else:
@@ -433,6 +438,7 @@ class ResnetBlock(_ArenaModule):
             yield f"conv_block.{j}", self.conv_block[j]
 
     def forward(self, x):
+        self._grad_on = torch.is_grad_enabled()
         return _ResFn.apply(self, x, *self._params())
 
 
@@ -449,7 +455,7 @@ class _DiscFn(torch.autograd.Function):
         xf = x.float()
         out = eng.forward(xf[:, 0:1].contiguous(), xf[:, 1:4].contiguous()).clone()
         need_p = any(ctx.needs_input_grad[2:])
-        if any(ctx.needs_input_grad):
+        if mod._grad_on and any(ctx.needs_input_grad):
             ctx.mod, ctx.eng, ctx.key, ctx.need_p, ctx.need_x = mod, eng, key, need_p, ctx.needs_input_grad[1]
             ctx.needs = [(k, p.requires_grad) for k, p in zip(_param_order(mod), params)]
             ctx.xshape = x.shape
@@ -481,6 +487,7 @@ class NLayerDiscriminator(_ArenaModule):
             yield f"model.{i}", self.model[i]
 
     def forward(self, x):
+        self._grad_on = torch.is_grad_enabled()
         return _DiscFn.apply(self, x, *self._params())
 
 
@@ -496,7 +503,7 @@ class _VggFn(torch.autograd.Function):
         eng.refresh_weights()
         fr = eng.forward(x.contiguous().float())
         out = fr.t.view(n, fr.hp, fr.wp, fr.C)[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().contiguous()
-        if ctx.needs_input_grad[1]:
+        if mod._grad_on and ctx.needs_input_grad[1]:
             ctx.mod, ctx.eng, ctx.key, ctx.shape = mod, eng, key, x.shape
             ctx.save_for_backward(out)
         else:
@@ -557,6 +564,7 @@ class VGGPerceptual(_ArenaModule):
             yield f"features.{i}", self.features[str(i)]
 
     def forward(self, x):
+        self._grad_on = torch.is_grad_enabled()
         return _VggFn.apply(self, x)
 
 

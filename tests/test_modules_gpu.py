@@ -118,3 +118,25 @@ def test_drivers_run_on_synthetic_pairs(tmp_path):
     m = R.compute_metrics(preds[0][0].numpy().astype(np.float32) / 255.0,
                           ((next(iter(R.train.SyntheticPairs(3, 2, 32, 32, seed=9)))["rgb"][0] + 1) * 0.5).permute(1, 2, 0).numpy())
     assert abs(m[0] - rows[0]["mae"]) < 1e-6 and abs(m[1] - rows[0]["mse"]) < 1e-6 and abs(m[2] - rows[0]["psnr"]) < 1e-4
+
+
+def test_inference_reuses_its_engine():
+    """under torch.no_grad() the generator module must hand its execution plan back to the pool (an engine rebuild costs
+    0.3 s of host work: test-mode throughput, BASELINE configs 1 and 5, depends on it) and build it without backward buffers"""
+    import irc_b200 as R
+    cfg = R.Config(); cfg.device = "cuda"
+    model = R.IRColorizationModel(cfg).eval()
+    ir = torch.rand(2, 1, 32, 48, device="cuda") * 2 - 1
+    with torch.no_grad():
+        a = model(ir)
+        pool = model.netG._free[(2, 32, 48, False)]
+        assert len(pool) == 1
+        eng = pool[0]
+        assert not eng.training and not hasattr(eng, "dZ0")
+        b = model(ir)
+        assert model.netG._free[(2, 32, 48, False)] == [eng]
+    assert torch.equal(a, b)
+    out = model(ir)                      # grad mode: a training engine, kept alive by the autograd graph until backward
+    assert (2, 32, 48, True) not in model.netG._free or model.netG._free[(2, 32, 48, True)] == []
+    out.sum().backward()
+    assert len(model.netG._free[(2, 32, 48, True)]) == 1
