@@ -195,13 +195,19 @@ __global__ void __launch_bounds__(256, 4) in_stats_pipe_kernel(View z, int C, in
     if (counters) finalize_by_last_block(part, out, n, C * 2, counters);
 }
 
-// out[j] = sum over chunks (fixed order) of part[chunk][j]: deterministic second stage of the reductions
+// out[j] = sum over chunks of part[chunk][j]: deterministic second stage of the reductions.  One warp per output: lane l
+// adds chunks l, l + 32, ... in order, then a fixed shuffle tree combines the lanes (bit-reproducible, and not a single
+// block walking hundreds of chunks serially)
 __global__ void sum_chunks_kernel(const float* __restrict__ part, int chunks, long long n, float* __restrict__ out) {
     irc::pdl_prologue();
-    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long j = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += warps) {
         float a = 0.f;
-        for (int c = 0; c < chunks; ++c) a += part[(long long)c * n + j];
-        out[j] = a;
+        for (int c = lane; c < chunks; c += 32) a += part[(long long)c * n + j];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (lane == 0) out[j] = a;
     }
 }
 
@@ -1644,7 +1650,7 @@ extern "C" int irc_colsum(const void* a, long long rows, long long ld, int chan_
         return irc_check_launch("irc_colsum");
     }
     irc::launch(colsum_kernel, dim3((unsigned)bx, (C + 31) / 32), 1024, 0, (cudaStream_t)stream, (const bf16*)a, rows, ld, chan_off, C, row_img, work);
-    irc::launch(sum_chunks_kernel, grid_for(C, 256), 256, 0, (cudaStream_t)stream, work, (int)bx, C, out);
+    irc::launch(sum_chunks_kernel, grid_for((long long)C * 32, 256), 256, 0, (cudaStream_t)stream, work, (int)bx, C, out);
     return irc_check_launch("irc_colsum");
 }
 

@@ -247,34 +247,58 @@ __global__ void tap_reduce_kernel(const float* P, long long ldp, const float* bi
 // E[q][j*nco + co] = g'[pixel(q - shift_j)][co];  g' = g * (1 - yv^2) when yv is given (tanh').
 // A shifted position that leaves its frame line lands in the padding ring (the ring is at least as wide as the
 // largest horizontal shift), i.e. on a zero, so the (dy, dx) decomposition needs no wrap-around handling.
-__global__ void __launch_bounds__(256) tap_expand_kernel(const float* g, const float* yv, bf16* E, const TapP t) {
+__global__ void __launch_bounds__(256) tap_expand_kernel(const float* g, const float* yv, bf16* E, const TapP t, int ndy) {
     irc::pdl_prologue();
+    // One block per (image, padded row).  The <= 8 distinct source rows the taps of this row read (one per distinct dy) are
+    // staged in shared memory as g' = g * (1 - y^2), all channels, zero where the row falls outside the image; a thread
+    // (pixel X, group of 8 columns) then assembles its 16 bytes from shared memory at register-resident offsets.
+    extern __shared__ float T[];                 // [ndy][nco][W]
+    __shared__ int s_dy[8];
     const int ncol = t.nshift * t.nco;
     const int grp = threadIdx.x & 7;
-    // the 8 columns of a thread are fixed: their (tap shift, output channel) decode once
-    int cdy[8], cdx[8], cco[8]; unsigned valid = 0;
+    if (threadIdx.x == 0) {                      // distinct dy values in first-appearance order (same rule as below)
+        int m = 0;
+        for (int j = 0; j < t.nshift; ++j) {
+            bool seen = false;
+            for (int i = 0; i < m; ++i) seen |= s_dy[i] == t.dy[j];
+            if (!seen && m < 8) s_dy[m++] = t.dy[j];
+        }
+    }
+    __syncthreads();
+    int cdx[8], cbase[8]; unsigned valid = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int col = grp * 8 + k;
-        cdy[k] = cdx[k] = cco[k] = 0;
-        if (col < ncol) { const int j = col / t.nco; valid |= 1u << k; cco[k] = col - j * t.nco; cdy[k] = t.dy[j] + t.oy; cdx[k] = t.dx[j] + t.ox; }
+        cdx[k] = cbase[k] = 0;
+        if (col < ncol) {
+            const int j = col / t.nco, co = col - j * t.nco;
+            int sl = 0;
+            for (int i = 0; i < ndy; ++i) if (s_dy[i] == t.dy[j]) sl = i;
+            valid |= 1u << k; cdx[k] = t.dx[j] + t.ox; cbase[k] = (sl * t.nco + co) * t.W;
+        }
     }
     const long long hw = (long long)t.H * t.W;
     for (int row = blockIdx.x; row < t.n_img * t.hp; row += gridDim.x) {
         const int n = row / t.hp, Y = row - n * t.hp;
-        const long long nb = (long long)n * t.nco * hw;
+        __syncthreads();
+        for (int r = threadIdx.x >> 5; r < ndy * t.nco; r += blockDim.x >> 5) {
+            const int sl = r / t.nco, co = r - sl * t.nco;
+            const int y = Y - s_dy[sl] - t.oy;
+            const bool ok = y >= 0 && y < t.H;
+            const long long o = ((long long)n * t.nco + co) * hw + (long long)(ok ? y : 0) * t.W;
+            for (int x = threadIdx.x & 31; x < t.W; x += 32) {
+                float v = 0.f;
+                if (ok) { v = __ldg(g + o + x); if (yv) { const float yy = __ldg(yv + o + x); v *= (1.f - yy * yy); } }
+                T[r * t.W + x] = v;
+            }
+        }
+        __syncthreads();
         for (int X = threadIdx.x >> 3; X < t.wp; X += blockDim.x >> 3) {
             float v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                float val = 0.f;
-                const int y = Y - cdy[k], x = X - cdx[k];
-                if (((valid >> k) & 1) && x >= 0 && x < t.W && y >= 0 && y < t.H) {
-                    const long long o = nb + cco[k] * hw + y * t.W + x;
-                    val = __ldg(g + o);
-                    if (yv) { const float yy = __ldg(yv + o); val *= (1.f - yy * yy); }
-                }
-                v[k] = val;
+                const int x = X - cdx[k];
+                v[k] = (((valid >> k) & 1) && x >= 0 && x < t.W) ? T[cbase[k] + x] : 0.f;
             }
             *reinterpret_cast<uint4*>(E + ((long long)row * t.wp + X) * 64 + grp * 8) =
                 make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
@@ -388,7 +412,15 @@ extern "C" int irc_tap_expand(const irc_tap_args* a, const float* g, const float
     TapP t; int rc = fill_tap(a, t); if (rc) return rc;
     if (!g || !E) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tap_expand: null");
     const long long nrow = (long long)t.n_img * t.hp;
-    irc::launch(tap_expand_kernel, (unsigned)(nrow < 1048576 ? nrow : 1048576), 256, 0, (cudaStream_t)stream, g, y, (bf16*)E, t);
+    int ndy = 0, seen_dy[8];
+    for (int j = 0; j < t.nshift; ++j) {
+        bool seen = false;
+        for (int i = 0; i < ndy; ++i) seen |= seen_dy[i] == t.dy[j];
+        if (!seen) { if (ndy == 8) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tap_expand: more than 8 distinct vertical shifts"); seen_dy[ndy++] = t.dy[j]; }
+    }
+    const size_t smem = (size_t)ndy * t.nco * t.W * sizeof(float);
+    if (smem > 48 * 1024) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tap_expand: row tile does not fit shared memory");
+    irc::launch(tap_expand_kernel, (unsigned)(nrow < 1048576 ? nrow : 1048576), 256, smem, (cudaStream_t)stream, g, y, (bf16*)E, t, ndy);
     rc = irc_check_launch("irc_tap_expand"); if (rc) return rc;
     if (dbias) {
         const long long hw = (long long)t.H * t.W;
