@@ -262,7 +262,10 @@ class GeneratorEngine:
         n4 = H4 * W4
         for b in reversed(range(self.nb)):
             c1, c2 = self.res[b]
-            be.in_bwd(self.Zb[b].view(), cur.view(), self.dZb.view(), 256, B, H4, W4, stats=self.stb[b], cnt=n4, eps=EPS, act=ACT_NONE, bsum=self.bsum)
+            # `cur` (gradient w.r.t. the reflection-padded X[b+1]) still carries its ring: the fold is linear, so it is applied
+            # where the gradient is consumed (here, on load) and once more when the stream leaves the blocks
+            be.in_bwd(self.Zb[b].view(), cur.view(), self.dZb.view(), 256, B, H4, W4, stats=self.stb[b], cnt=n4, eps=EPS, act=ACT_NONE, bsum=self.bsum,
+                      fold_pad=1)
             c2.wgrad(self.dZb.t, self.Hh[b].t, 0, self.dZb.rows)
             c2.dgrad(self.dZb.t, self.Gh.t)
             # ReflectionPad2d(1)^T of Gh is folded inside the backward pass (or by a separate in-place pass when the map is
@@ -270,11 +273,11 @@ class GeneratorEngine:
             be.in_bwd(self.Za[b].view(), self.Gh.view(), self.dZa.view(), 256, B, H4, W4, stats=self.sta[b], cnt=n4, eps=EPS, act=ACT_RELU,
                       bsum=self.bsum, fold_pad=1)
             c1.wgrad(self.dZa.t, self.X[b].t, 0, self.dZa.rows)
-            # data gradient of conv1 + the residual-stream gradient (its frame ring is zero), then the reflection fold
+            # data gradient of conv1 + the residual-stream gradient, ring included (unfolded: fold(a + b) = fold(a) + fold(b))
             nxt = self.dOut[1] if cur is self.dOut[0] else self.dOut[0]
             c1.dgrad(self.dZa.t, nxt.t, addend=View(cur.t, 0, 0, 0))
-            be.fold_inplace(nxt.t, 0, 256, B, H4, W4, 1)
             cur = nxt
+        be.fold_inplace(cur.t, 0, 256, B, H4, W4, 1)
         be.flush_sums()                   # weight gradients of outc, up2, up1 and the ResNet blocks are final
         if after_blocks is not None:
             after_blocks()
