@@ -464,6 +464,8 @@ __global__ void __launch_bounds__(256, K <= 3 ? 3 : 2) gather_stream_kernel(cons
     bf16* dbase = const_cast<bf16*>(p.dst.p) + ((long long)(n * p.dst.hp + p.dst.oy - pad) * p.dst.wp + (p.dst.ox - pad)) * p.dst.ld + p.dst.off + c;
     const long long dstep = (long long)p.dst.wp * p.dst.ld;
 
+    bf16* dptr = dbase + (ya + pad) * dstep + (long long)(x + pad) * p.dst.ld;      // advances one frame row per output row
+    const long long dex = eX >= 0 ? (long long)(eX - (x + pad)) * p.dst.ld : 0;
     float hb[K][8];
 #pragma unroll
     for (int s = 0; s < K; ++s)
@@ -472,23 +474,27 @@ __global__ void __launch_bounds__(256, K <= 3 ? 3 : 2) gather_stream_kernel(cons
     int top = s_lo0;
     const int last = s_hi[rows - 1];
     uint4 raw[K], raw2[K];
-    auto fetch = [&](int r) {
+    // unused table slots have weight 0 and index 0: they load pixel 0 of the row and add nothing, which is cheaper than a
+    // branch per tap; the row pointers advance by one frame row per fetch (rows enter in order)
+    const bf16* rp = srow + top * sstep;
+    const bf16* rp2 = kTwo ? srow2 + top * sstep2 : nullptr;
+    auto fetch = [&]() {
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            if (wx[j] != 0.f) {
-                raw[j] = __ldg(reinterpret_cast<const uint4*>(srow + r * sstep + ox[j]));
-                if (kTwo) raw2[j] = __ldg(reinterpret_cast<const uint4*>(srow2 + r * sstep2 + ox2[j]));
-            }
+            raw[j] = __ldg(reinterpret_cast<const uint4*>(rp + ox[j]));
+            if (kTwo) raw2[j] = __ldg(reinterpret_cast<const uint4*>(rp2 + ox2[j]));
         }
+        rp += sstep;
+        if (kTwo) rp2 += sstep2;
     };
-    if (top <= last) fetch(top);
+    if (top <= last) fetch();
     for (int t = 0; t < rows; ++t) {
         const int hi = s_hi[t];
         while (top <= hi) {
             float h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int j = 0; j < K; ++j) {
-                if (wx[j] != 0.f) {
+                {
                     float v[8];
                     unpack8(raw[j], v);
                     if (kNorm) {
@@ -511,7 +517,7 @@ __global__ void __launch_bounds__(256, K <= 3 ? 3 : 2) gather_stream_kernel(cons
                 }
             }
             ++top;
-            if (top <= last) fetch(top);
+            if (top <= last) fetch();
 #pragma unroll
             for (int s = 0; s + 1 < K; ++s)
 #pragma unroll
@@ -528,20 +534,20 @@ __global__ void __launch_bounds__(256, K <= 3 ? 3 : 2) gather_stream_kernel(cons
         }
         const int y = ya + t;
         const uint4 val = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
-        bf16* drow = dbase + (y + pad) * dstep;
-        *reinterpret_cast<uint4*>(drow + (long long)(x + pad) * p.dst.ld) = val;
-        if (pad) {
+        *reinterpret_cast<uint4*>(dptr) = val;
+        if (pad && (eX >= 0 || y <= pad || y >= H - 1 - pad)) {
             const uint4 ring = p.halo_mode == 1 ? val : make_uint4(0, 0, 0, 0);
             int eY;
             if (p.halo_mode == 1) eY = (y >= 1 && y <= pad) ? pad - y : ((y >= H - 1 - pad && y <= H - 2) ? pad + 2 * (H - 1) - y : -1);
             else eY = y < pad ? y : (y >= H - pad ? y + 2 * pad : -1);
-            if (eX >= 0) *reinterpret_cast<uint4*>(drow + (long long)eX * p.dst.ld) = ring;
+            if (eX >= 0) *reinterpret_cast<uint4*>(dptr + dex) = ring;
             if (eY >= 0) {
-                bf16* erow = dbase + eY * dstep;
-                *reinterpret_cast<uint4*>(erow + (long long)(x + pad) * p.dst.ld) = ring;
-                if (eX >= 0) *reinterpret_cast<uint4*>(erow + (long long)eX * p.dst.ld) = ring;
+                bf16* erow = dptr + (long long)(eY - (y + pad)) * dstep;
+                *reinterpret_cast<uint4*>(erow) = ring;
+                if (eX >= 0) *reinterpret_cast<uint4*>(erow + dex) = ring;
             }
         }
+        dptr += dstep;
     }
 }
 
