@@ -12,6 +12,8 @@
 //
 // Both: one CTA = 192 threads = TMA producer warp, MMA issuer warp, 4 epilogue warps;
 // operands staged by TMA into SWIZZLE_128B shared memory, accumulators in TMEM.
+#include <stdlib.h>
+
 #include "irc_common.cuh"
 #include "../../include/irc_b200.h"
 
@@ -692,6 +694,161 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// Weight gradients of layers with at most 64 output channels (up2_conv, inc, model.0): a 64-row A tile would leave half of
+// every M=128 MMA idle.  Since  dW_t[m][n] = sum_q dz[q][m] x[q + s_t][n] = sum_q' dz[q' - s_t][m] x[q'][n],  the shift can be
+// put on dz instead of x: the two 64-channel groups of one A tile are then loaded at the (negated) shifts of TWO taps, the
+// B tile (x, unshifted) is shared by all taps, and accumulator rows 0..63 / 64..127 hold taps 2i / 2i+1.  P pairs per CTA
+// accumulate into P independent TMEM tiles (same latency argument as TPC above).
+template <int P>
+__global__ void __launch_bounds__(kThreads, 1)
+tn_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnParams p) {
+    irc::pdl_prologue();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int tile_a = kBK * 128 * 2;              // one pair: 2 taps x 64 channels x 64 rows
+    const int groups_b = p.bn / 64;
+    const int tile_b = kBK * 128 * groups_b;
+    const int stage_bytes = P * tile_a + tile_b;
+    const int S = p.stages;
+    uint64_t* bars = (uint64_t*)(smem + (size_t)S * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tfull = bars + 2 * S;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int w = blockIdx.x;
+    const int n_tile = w % p.n_tiles; w /= p.n_tiles;
+    const int group = w % p.groups; w /= p.groups;
+    const int split = w;
+    const int npairs = (p.ntaps + 1) / 2;
+    const int pair0 = group * P;
+    const int np = (npairs - pair0) < P ? (npairs - pair0) : P;
+    const long long kb_total = (p.k_rows + kBK - 1) / kBK;
+    const long long kb_per = (kb_total + p.splits - 1) / p.splits;
+    const long long kb_begin = (long long)split * kb_per;
+    long long kb_end = kb_begin + kb_per; if (kb_end > kb_total) kb_end = kb_total;
+    const long long my_kb = kb_end > kb_begin ? kb_end - kb_begin : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t bytes = (uint32_t)(np * tile_a + tile_b);
+        for (long long kb = kb_begin; kb < kb_begin + my_kb; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(&full[stage], bytes);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                const long long r0 = kb * kBK;
+                for (int i = 0; i < np; ++i)
+                    for (int g = 0; g < 2; ++g) {
+                        // an odd tap count leaves the last half pair without a tap: load it far outside the tensor (zero fill)
+                        const int tap = 2 * (pair0 + i) + g;
+                        const long long row = tap < p.ntaps ? r0 - p.b_shift[tap] : -(1LL << 30);
+                        tma_load_2d(sa + i * tile_a + g * (kBK * 128), &tmA, &full[stage], p.a_chan_off, (int)row);
+                    }
+                for (int g = 0; g < groups_b; ++g)
+                    tma_load_2d(sa + P * tile_a + g * (kBK * 128), &tmB, &full[stage], p.b_chan_off + n_tile * p.bn + g * 64, (int)r0);
+            }
+            __syncwarp();
+            if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = umma_idesc_bf16(kBM, p.bn, 1, 1);
+        int stage = 0; uint32_t phase = 0;
+        for (long long kb = 0; kb < my_kb; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint64_t bdesc = umma_desc_sw128(sa + P * tile_a, kBK * 128);
+            const uint32_t accum = kb != 0;
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+#pragma unroll
+                    for (int i = 0; i < P; ++i) {
+                        if (i < np) {
+                            const uint64_t adesc = umma_desc_sw128(sa + i * tile_a, kBK * 128);
+                            umma_bf16(tmem_base + (uint32_t)(i * p.bn), adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, k == 0 ? accum : 1u);
+                        }
+                    }
+                }
+                umma_commit(&empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(tfull);
+        __syncwarp();
+    } else {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;            // accumulator row: tap (row >> 6) of the pair, channel row & 63
+        const int m = row & 63;
+        if (my_kb > 0) {
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+        }
+        for (int i = 0; i < np; ++i) {
+            const int tap = 2 * (pair0 + i) + (row >> 6);
+            float* obase = p.out + (long long)split * p.out_split_stride + (long long)tap * p.out_tap_stride + (long long)m * p.out_m_stride;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * p.bn);
+            for (int c0 = 0; c0 < p.bn; c0 += 32) {
+                uint32_t r[32];
+                if (my_kb > 0) {
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+                if (m < p.m && tap < p.ntaps) {
+                    const int nb = n_tile * p.bn + c0;
+                    if (p.out_n_stride == 1 && nb + 32 <= p.n && ((((uintptr_t)(obase + nb)) & 15) == 0)) {
+                        float4* o4 = reinterpret_cast<float4*>(obase + nb);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            o4[g] = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]), __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = nb + j;
+                            if (n < p.n) obase[(long long)n * p.out_n_stride] = __uint_as_float(r[j]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// pairs per CTA of the paired weight-gradient GEMM: as many as keep >= 4 pipeline stages and fit the 512 TMEM columns
+int auto_pairs(int bn, int ntaps) {
+    const int npairs = (ntaps + 1) / 2;
+    int best = 1;
+    for (int c = 1; c <= 4; ++c) {
+        if (c > npairs || c * bn > 512) break;
+        const int stage = c * kBK * 128 * 2 + kBK * 128 * (bn / 64);
+        if ((kMaxSmem - 2048) / stage >= 4) best = c;
+    }
+    return best;
+}
+bool tn_pair_mode(int m, int ntaps, bool zero_a_shift) { return m <= 64 && ntaps >= 2 && zero_a_shift; }
+
 bool g_attr_conv = false, g_attr_tn = false, g_attr_runs = false;
 
 // taps per CTA of the weight-gradient GEMM: as many independent accumulation chains as keep >= 4 pipeline stages
@@ -871,6 +1028,37 @@ extern "C" int irc_tn_gemm(const irc_tn_gemm_args* a, void* stream) {
     for (int i = 0; i < a->ntaps; ++i) { p.a_shift[i] = a->a_shift[i]; p.b_shift[i] = a->b_shift[i]; }
     p.out = a->out; p.out_tap_stride = a->out_tap_stride; p.out_m_stride = a->out_m_stride;
     p.out_n_stride = a->out_n_stride; p.out_split_stride = a->out_split_stride;
+    bool zero_a = true;
+    for (int i = 0; i < a->ntaps; ++i) zero_a = zero_a && a->a_shift[i] == 0;
+    if (a->tpc <= 0 && tn_pair_mode(a->m, a->ntaps, zero_a) && !getenv("IRC_TN_NOPAIR")) {
+        const int P = auto_pairs(bn, a->ntaps);
+        p.groups = ((a->ntaps + 1) / 2 + P - 1) / P;
+        p.m_tiles = 1;
+        int cols = 32; while (cols < P * bn) cols <<= 1;
+        p.tmem_cols = cols;
+        const int stage_bytes = P * kBK * 128 * 2 + kBK * 128 * (bn / 64);
+        int stages = (kMaxSmem - 2048) / stage_bytes;
+        if (stages > 8) stages = 8;
+        p.stages = stages;
+        const size_t smem = (size_t)stages * stage_bytes + 2048;
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(tn_gemm_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            cudaFuncSetAttribute(tn_gemm_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            cudaFuncSetAttribute(tn_gemm_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            cudaFuncSetAttribute(tn_gemm_pair_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            attr = true;
+        }
+        const unsigned grid = (unsigned)((long long)p.n_tiles * p.groups * p.splits);
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (P) {
+            case 1: irc::launch<1>(tn_gemm_pair_kernel<1>, grid, kThreads, smem, st, tmA, tmB, p); break;
+            case 2: irc::launch<1>(tn_gemm_pair_kernel<2>, grid, kThreads, smem, st, tmA, tmB, p); break;
+            case 3: irc::launch<1>(tn_gemm_pair_kernel<3>, grid, kThreads, smem, st, tmA, tmB, p); break;
+            default: irc::launch<1>(tn_gemm_pair_kernel<4>, grid, kThreads, smem, st, tmA, tmB, p); break;
+        }
+        return irc_check_launch("irc_tn_gemm(pair)");
+    }
     // taps per CTA: all taps of a group must share the A shift (true for weight gradients: a_shift == 0)
     int tpc = a->tpc;
     bool same_a = true;
@@ -913,6 +1101,10 @@ extern "C" int irc_tn_gemm(const irc_tn_gemm_args* a, void* stream) {
 // number of CTAs irc_tn_gemm launches per split with the automatic tiling (lets the caller pick `splits` for one wave)
 extern "C" int irc_tn_gemm_ctas(int m, int n, int ntaps, int same_a_shift) {
     int bn = ((n + 63) / 64) * 64; if (bn > 256) bn = 256;
+    if (tn_pair_mode(m, ntaps, same_a_shift != 0) && !getenv("IRC_TN_NOPAIR")) {
+        const int P = auto_pairs(bn, ntaps);
+        return ((n + bn - 1) / bn) * (((ntaps + 1) / 2 + P - 1) / P);
+    }
     const int tpc = same_a_shift ? auto_tpc(bn, ntaps) : 1;
     return ((m + kBM - 1) / kBM) * ((n + bn - 1) / bn) * ((ntaps + tpc - 1) / tpc);
 }

@@ -103,6 +103,8 @@ def test_conv_gemm_epilogue():
     (6000, 128, 64, 128, 64, 0, 0, [-71, -70, -69, -1, 0, 1, 69, 70, 71], 5),       # 3 taps per CTA
     (6000, 21, 64, 64, 64, 0, 0, [-210, -140, -70, 0, 70, 140, 210], 4),            # 7 taps in one ragged group of 8
     (4000, 512, 256, 512, 256, 0, 0, [r * 34 + s for r in range(4) for s in range(4)], 2),   # 2 taps per CTA, 4 M tiles
+    (7000, 64, 192, 64, 192, 0, 0, [-259, -258, -257, -1, 0, 1, 257, 258, 259], 3),          # paired taps (m <= 64): 5 pairs, last one half empty
+    (2500, 64, 128, 192, 320, 128, 64, [-3, 4], 1),                                          # paired taps, channel offsets, one pair
 ])
 def test_tn_gemm(rows, m, n, lda, ldb, a_off, b_off, shifts, splits):
     from irc_b200 import _native as nat
