@@ -2,6 +2,7 @@
 // separable table stencils (anti-aliased Downsample and UpsampleAA, halo folding), all
 // vectorised 8 channels (16 bytes) per thread and coalesced along the channel axis.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "irc_common.cuh"
 #include "../../include/irc_b200.h"
@@ -1592,7 +1593,8 @@ extern "C" int irc_in_bwd_apply(const irc_in_bwd_args* a, void* stream) {
     if (plain) {
         const size_t smem_p = (size_t)kPipeD * (p.has2 ? 3 : 2) * threads * 16;
         // a few rows per block so that the prefetch pipeline runs across row boundaries
-        const unsigned gp = (unsigned)(rows < (long long)irc_num_sms() * 16 ? rows : (long long)irc_num_sms() * 16);
+        const long long gcap = (long long)irc_num_sms() * 16;          // (4..32 blocks per SM measured: no difference)
+        const unsigned gp = (unsigned)(rows < gcap ? rows : gcap);
         if (p.has2) irc::launch(in_bwd_apply_pipe_kernel<true>, gp, threads, smem_p, (cudaStream_t)stream, p);
         else irc::launch(in_bwd_apply_pipe_kernel<false>, gp, threads, smem_p, (cudaStream_t)stream, p);
     } else if (!p.ty_idx && !p.tx_idx) irc::launch(in_bwd_apply_kernel<true>, grid, threads, 0, (cudaStream_t)stream, p);

@@ -113,10 +113,17 @@ def train_kaist(cfg: M.Config, train_loader=None, val_loader=None, use_graph: bo
     ts = TrainStep(M.backend(), cfg.batch_size, H, W, device, cfg.lr_G, cfg.lr_D, cfg.beta1, cfg.beta2, lam, world_size=world,
                    use_graph=use_graph, arenas=(model.netG.arena, netD.arena, vgg.arena))
     ts.refresh_weights()
+    start_epoch = 1
+    resume = getattr(cfg, "resume_from", None)          # not in the reference: full-state checkpoints (D + both Adam states + epoch)
+    if resume and os.path.isfile(resume):
+        st = torch.load(resume, map_location=device)
+        ts.load_state_dict(st)
+        start_epoch = int(st.get("epoch", 0)) + 1
+        print(f"Resumed training state from {resume} (epoch {start_epoch - 1})")
     lr_lambda = M.get_lr_lambda(cfg)
     best_val, best_path = float("inf"), os.path.join(cfg.save_dir, "netG_best.pth")
     history = []
-    for epoch in range(1, cfg.epochs + 1):
+    for epoch in range(start_epoch, cfg.epochs + 1):
         scale = lr_lambda(epoch - 1)
         sum_g = sum_d = 0.0
         steps = 0
@@ -139,6 +146,9 @@ def train_kaist(cfg: M.Config, train_loader=None, val_loader=None, use_graph: bo
             path = os.path.join(cfg.save_dir, f"netG_epoch_{epoch:03d}.pth")
             torch.save(model.netG.state_dict(), path)
             print(f"Saved generator checkpoint to {path}")
+            if getattr(cfg, "save_full_state", False):
+                full = ts.state_dict(); full["epoch"] = epoch
+                torch.save(full, os.path.join(cfg.save_dir, "train_state_latest.pth"))
         if rank0 and val_l1 < best_val:
             best_val = val_l1
             torch.save(model.netG.state_dict(), best_path)

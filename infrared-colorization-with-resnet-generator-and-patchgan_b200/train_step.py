@@ -80,6 +80,31 @@ class TrainStep:
     def refresh_weights(self) -> None:
         self.G.refresh_weights(); self.D2.refresh_weights(); self.V.refresh_weights()
 
+    # ------------------------------------------------------------------ full-state checkpoints (resume)
+    def state_dict(self) -> Dict:
+        """Everything needed to resume training bit-exactly: generator and discriminator parameters under the reference's
+        state_dict keys (`netG` alone is what irc:1706-1715 saves), both Adam states and step counters.  The reference has no
+        resume path; `netG` stays loadable by its `load_weights` (irc:781-789)."""
+        out = {"format": "irc_b200.train_state.v1",
+               "netG": {k: v.detach().clone() for k, v in self.G.arena.state_dict().items()},
+               "netD": {k: v.detach().clone() for k, v in self.D2.arena.state_dict().items()}}
+        for name, arena, opt in (("optG", self.G.arena, self.optG), ("optD", self.D2.arena, self.optD)):
+            out[name] = dict(step=opt.t, lr=opt.lr, betas=(opt.b1, opt.b2), eps=opt.eps, exp_avg=arena.m.detach().clone(),
+                             exp_avg_sq=arena.v.detach().clone())
+        return out
+
+    def load_state_dict(self, state: Dict) -> None:
+        if state.get("format") != "irc_b200.train_state.v1":
+            raise ValueError("not an irc_b200 training-state checkpoint (for generator-only checkpoints use IRColorizationModel.load_weights)")
+        self.G.arena.load(state["netG"]); self.D2.arena.load(state["netD"])
+        for name, arena, opt in (("optG", self.G.arena, self.optG), ("optD", self.D2.arena, self.optD)):
+            st = state[name]
+            if st["exp_avg"].numel() != arena.m.numel():
+                raise ValueError(f"{name}: optimizer state of {st['exp_avg'].numel()} elements does not fit the arena ({arena.m.numel()})")
+            arena.m.copy_(st["exp_avg"]); arena.v.copy_(st["exp_avg_sq"])
+            opt.t = int(st["step"]); opt.lr = float(st["lr"]); opt.b1, opt.b2 = (float(b) for b in st["betas"]); opt.eps = float(st["eps"])
+        self.refresh_weights()
+
     # ------------------------------------------------------------------ the iteration
     def _allreduce_async(self, t: torch.Tensor):
         """sum-allreduce over NCCL/NVLink on NCCL's own stream; returns a handle to wait on (None when single GPU)"""

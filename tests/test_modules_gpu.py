@@ -109,6 +109,15 @@ def test_drivers_run_on_synthetic_pairs(tmp_path):
         hist = R.main(cfg)
     assert len(hist) == 2 and all(np.isfinite(h[2]) for h in hist)
     assert os.path.isfile(os.path.join(cfg.save_dir, "netG_best.pth")) and os.path.isfile(os.path.join(cfg.save_dir, "netG_epoch_002.pth"))
+    # resume from the full-state checkpoint: one more epoch on top of the two
+    cfg.save_full_state = True; cfg.epochs = 3
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        R.main(cfg)                                                     # writes train_state_latest.pth (epoch 3)
+        cfg.resume_from = os.path.join(cfg.save_dir, "train_state_latest.pth"); cfg.epochs = 4
+        hist2 = R.main(cfg)
+    assert len(hist2) == 1 and np.isfinite(hist2[0][2])                 # only epoch 4 ran
+    cfg.resume_from = None
     cfg.mode = "test"; cfg.test_G_weights = os.path.join(cfg.save_dir, "netG_best.pth")
     summary, rows, preds = R.main(cfg)
     assert summary["count"] == 6 and len(rows) == 6 and preds[0].dtype == torch.uint8
