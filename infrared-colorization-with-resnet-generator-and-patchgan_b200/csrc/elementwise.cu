@@ -1329,14 +1329,27 @@ __global__ void colsum_kernel(const bf16* a, long long rows, long long ld, int o
 // its own pixel: race-free) and clears them.  Touches O(p * perimeter) pixels instead of a full pass.
 __global__ void fold_inplace_kernel(bf16* g, long long ld, int off, int C, int n_img, int H, int W, int p) {
     irc::pdl_prologue();
-    // grid = (column chunks, rows, images): one pixel per thread, so the few border pixels that have work are spread over
-    // many blocks and the pass costs one load-add-store round trip instead of a serial walk along the border rows
+    // Only pixels within p of the border receive anything: the 2p rows next to the top / bottom border (all columns) and,
+    // on every other row, the 2p columns next to the side borders.  grid = (chunks of that work list, images); one pixel
+    // per thread, so the pass costs one load-add-store round trip.
     const int C8 = C >> 3;
     const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
     const int c = cv * 8;
     const int Hp = H + 2 * p, Wp = W + 2 * p;
-    const int n = blockIdx.z, y = blockIdx.y, x = blockIdx.x * L + lane;
-    if (x >= W) return;
+    const int n = blockIdx.y;
+    const int NA = 2 * p * W, NB = (H - 2 * p) * 2 * p;
+    const int item = blockIdx.x * L + lane;
+    if (item >= NA + NB) return;
+    int y, x;
+    if (item < NA) {
+        const int r = item / W;
+        x = item - r * W;
+        y = r < p ? 1 + r : H - 1 - p + (r - p);
+    } else {
+        const int j = item - NA, jr = j / (2 * p), k = j - jr * 2 * p;
+        y = jr == 0 ? 0 : (jr == H - 2 * p - 1 ? H - 1 : p + jr);        // the rows that are not among the 2p border rows
+        x = k < p ? 1 + k : W - 1 - p + (k - p);
+    }
     const int my = (y >= 1 && y <= p) ? p - y : ((y >= H - 1 - p && y <= H - 2) ? 2 * (H - 1) - y + p : -1);   // mirrored padded row
     const int mx = (x >= 1 && x <= p) ? p - x : ((x >= W - 1 - p && x <= W - 2) ? 2 * (W - 1) - x + p : -1);
     if (my < 0 && mx < 0) return;
@@ -1667,7 +1680,8 @@ extern "C" int irc_fold_inplace(void* g, long long ld, int chan_off, int C, int 
     if (p < 1 || 2 * p + 2 > H || 2 * p + 2 > W) return irc_set_error(IRC_ERR_BAD_ARG, "irc_fold_inplace: image too small for the pad width");
     int threads, L;
     row_block(C, W, threads, L);
-    if (H > 65535 || n_img > 65535) return irc_set_error(IRC_ERR_BAD_ARG, "irc_fold_inplace: extent too large");
-    irc::launch(fold_inplace_kernel, dim3((W + L - 1) / L, H, n_img), threads, 0, (cudaStream_t)stream, (bf16*)g, ld, chan_off, C, n_img, H, W, p);
+    if (n_img > 65535) return irc_set_error(IRC_ERR_BAD_ARG, "irc_fold_inplace: extent too large");
+    const long long items = 2LL * p * W + (long long)(H - 2 * p) * 2 * p;
+    irc::launch(fold_inplace_kernel, dim3((unsigned)((items + L - 1) / L), n_img), threads, 0, (cudaStream_t)stream, (bf16*)g, ld, chan_off, C, n_img, H, W, p);
     return irc_check_launch("irc_fold_inplace");
 }
