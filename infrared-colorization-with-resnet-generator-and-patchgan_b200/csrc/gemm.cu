@@ -549,7 +549,6 @@ struct TnParams {
     int bn;                  // tile N (multiple of 64)
     int m_tiles, n_tiles, ntaps, splits, stages;
     int groups;              // tap groups: one CTA accumulates TPC taps into TPC independent TMEM tiles
-    int pack;                // taps packed along N in one B tile (narrow inputs: n = 64 -> 4 taps, n = 128 -> 2 taps per 256-wide MMA)
     int tmem_cols;
     int a_chan_off, b_chan_off;
     int a_shift[IRC_MAX_TAPS];
@@ -586,12 +585,8 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int m_tile = w % p.m_tiles; w /= p.m_tiles;
     const int group = w % p.groups; w /= p.groups;
     const int split = w;
-    // a "tap" below is a super-tap of p.pack real taps whose B tiles sit side by side along N (group g of the tile belongs
-    // to real tap g / gpn and holds its channels (g % gpn) * 64 ...); with pack == 1 it is the real tap
-    const int nsup = (p.ntaps + p.pack - 1) / p.pack;
-    const int gpn = (p.bn / 64) / p.pack;                                  // 64-channel groups per real tap
     const int tap0 = group * TPC;
-    const int ntap = (nsup - tap0) < TPC ? (nsup - tap0) : TPC;            // active super-taps of this group
+    const int ntap = (p.ntaps - tap0) < TPC ? (p.ntaps - tap0) : TPC;      // active taps of this group
     const long long kb_total = (p.k_rows + kBK - 1) / kBK;
     const long long kb_per = (kb_total + p.splits - 1) / p.splits;
     const long long kb_begin = (long long)split * kb_per;
@@ -621,14 +616,11 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint8_t* sa = smem + (size_t)stage * stage_bytes;
                 const long long r0 = kb * kBK;
                 for (int g = 0; g < 2; ++g)
-                    tma_load_2d(sa + g * (kBK * 128), &tmA, &full[stage], p.a_chan_off + m_tile * kBM + g * 64, (int)(r0 + p.a_shift[tap0 * p.pack]));
+                    tma_load_2d(sa + g * (kBK * 128), &tmA, &full[stage], p.a_chan_off + m_tile * kBM + g * 64, (int)(r0 + p.a_shift[tap0]));
                 for (int t = 0; t < ntap; ++t)
-                    for (int g = 0; g < groups_b; ++g) {
-                        const int tap = (tap0 + t) * p.pack + g / gpn;          // a ragged last super-tap loads zeros (far out of bounds)
-                        const long long row = tap < p.ntaps ? r0 + p.b_shift[tap] : -(1LL << 30);
-                        const int chan = p.pack > 1 ? p.b_chan_off + (g % gpn) * 64 : p.b_chan_off + n_tile * p.bn + g * 64;
-                        tma_load_2d(sa + stage_a + t * tile_b + g * (kBK * 128), &tmB, &full[stage], chan, (int)row);
-                    }
+                    for (int g = 0; g < groups_b; ++g)
+                        tma_load_2d(sa + stage_a + t * tile_b + g * (kBK * 128), &tmB, &full[stage], p.b_chan_off + n_tile * p.bn + g * 64,
+                                    (int)(r0 + p.b_shift[tap0 + t]));
             }
             __syncwarp();
             if (++stage == S) { stage = 0; phase ^= 1; }
@@ -668,11 +660,9 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
         }
         for (int t = 0; t < ntap; ++t) {
+            float* obase = p.out + (long long)split * p.out_split_stride + (long long)(tap0 + t) * p.out_tap_stride + (long long)m * p.out_m_stride;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * p.bn);
             for (int c0 = 0; c0 < p.bn; c0 += 32) {
-                // packed tiles: columns [j*n, (j+1)*n) of the accumulator are real tap j of the super-tap (n % 32 == 0)
-                const int tap = p.pack > 1 ? (tap0 + t) * p.pack + c0 / p.n : tap0 + t;
-                float* obase = p.out + (long long)split * p.out_split_stride + (long long)tap * p.out_tap_stride + (long long)m * p.out_m_stride;
                 uint32_t r[32];
                 if (my_kb > 0) {
                     tmem_ld32(taddr + c0, r);
@@ -681,8 +671,8 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = 0u;
                 }
-                if (m < p.m && tap < p.ntaps) {
-                    const int nb = p.pack > 1 ? c0 % p.n : n_tile * p.bn + c0;
+                if (m < p.m) {
+                    const int nb = n_tile * p.bn + c0;
                     if (p.out_n_stride == 1 && nb + 32 <= p.n && ((((uintptr_t)(obase + nb)) & 15) == 0)) {
                         float4* o4 = reinterpret_cast<float4*>(obase + nb);
 #pragma unroll
@@ -1069,25 +1059,16 @@ extern "C" int irc_tn_gemm(const irc_tn_gemm_args* a, void* stream) {
         }
         return irc_check_launch("irc_tn_gemm(pair)");
     }
-    // narrow inputs (n = 64 / 128): pack 4 / 2 taps side by side into one 256-wide B tile, so that the A tile is read from
-    // shared memory once per 256 output columns instead of once per 64 / 128 (the N = 64 MMA is bound by that port)
-    p.pack = 1;
-    int ntaps_eff = a->ntaps;
-    if (a->tpc <= 0 && a->bn <= 0 && zero_a && a->ntaps >= 2 && (a->n == 64 || a->n == 128) && !getenv("IRC_TN_NOPACK")) {
-        int pack = 256 / a->n; if (pack > a->ntaps) pack = a->ntaps;
-        p.pack = pack; bn = pack * a->n; p.bn = bn; p.n_tiles = 1;
-        ntaps_eff = (a->ntaps + pack - 1) / pack;
-    }
     // taps per CTA: all taps of a group must share the A shift (true for weight gradients: a_shift == 0)
     int tpc = a->tpc;
     bool same_a = true;
     for (int i = 1; i < a->ntaps; ++i) same_a = same_a && a->a_shift[i] == a->a_shift[0];
     if (tpc <= 0) {
-        tpc = same_a ? auto_tpc(bn, ntaps_eff) : 1;
+        tpc = same_a ? auto_tpc(bn, a->ntaps) : 1;
     }
     if (!(tpc == 1 || tpc == 2 || tpc == 3 || tpc == 4 || tpc == 8) || tpc * bn > 512 || (tpc > 1 && !same_a))
         return irc_set_error(IRC_ERR_BAD_ARG, "irc_tn_gemm: unsupported taps-per-CTA %d for tile width %d", tpc, bn);
-    p.groups = (ntaps_eff + tpc - 1) / tpc;
+    p.groups = (a->ntaps + tpc - 1) / tpc;
     int cols = 32; while (cols < tpc * bn) cols <<= 1;
     p.tmem_cols = cols;
     const int stage_bytes = kBK * 128 * 2 + tpc * kBK * 128 * (bn / 64);
@@ -1123,11 +1104,6 @@ extern "C" int irc_tn_gemm_ctas(int m, int n, int ntaps, int same_a_shift) {
     if (tn_pair_mode(m, ntaps, same_a_shift != 0) && !getenv("IRC_TN_NOPAIR")) {
         const int P = auto_pairs(bn, ntaps);
         return ((n + bn - 1) / bn) * (((ntaps + 1) / 2 + P - 1) / P);
-    }
-    if (same_a_shift && ntaps >= 2 && (n == 64 || n == 128) && !getenv("IRC_TN_NOPACK")) {
-        int pack = 256 / n; if (pack > ntaps) pack = ntaps;
-        const int nsup = (ntaps + pack - 1) / pack, tp = auto_tpc(pack * n, nsup);
-        return ((m + kBM - 1) / kBM) * ((nsup + tp - 1) / tp);
     }
     const int tpc = same_a_shift ? auto_tpc(bn, ntaps) : 1;
     return ((m + kBM - 1) / kBM) * ((n + bn - 1) / bn) * ((ntaps + tpc - 1) / tpc);
