@@ -171,6 +171,7 @@ __global__ void col2im_kernel(const Col2imP p) {
 // coalesced 16-byte loads - only the 16-byte chunks that hold the k*C columns of that kernel row - and transposed into
 // shared memory as T[kernel row][column][ox] (fp32), so that the k*k taps of an output pixel are conflict-free reads with
 // lanes running along x.  Same summation order as col2im_kernel (r outer, s inner): identical bits.
+template <int S>      // stride as a compile-time constant: the tap tests below are shifts and masks, not integer divisions
 __global__ void __launch_bounds__(256) col2im_rows_kernel(const Col2imP p, int pitch) {
     irc::pdl_prologue();
     extern __shared__ float T[];                  // [k][k*C][pitch]
@@ -178,8 +179,8 @@ __global__ void __launch_bounds__(256) col2im_rows_kernel(const Col2imP p, int p
     const int kC = p.k * p.C, Wo = p.rm.Wo;
     for (int r = 0; r < p.k; ++r) {
         const int ty = y + p.pad - r;
-        if (ty < 0 || ty % p.stride || ty / p.stride >= p.rm.Ho) continue;          // uniform over the block
-        const int oy = ty / p.stride;
+        if (ty < 0 || ty % S || ty / S >= p.rm.Ho) continue;          // uniform over the block
+        const int oy = ty / S;
         const int ch_lo = (r * kC) >> 3, nch = (((r + 1) * kC - 1) >> 3) - ch_lo + 1;
         float* Tr = T + (size_t)r * kC * pitch;
         for (int idx = threadIdx.x; idx < Wo * nch; idx += blockDim.x) {
@@ -203,12 +204,12 @@ __global__ void __launch_bounds__(256) col2im_rows_kernel(const Col2imP p, int p
         float acc = 0.f;
         for (int r = 0; r < p.k; ++r) {
             const int ty = y + p.pad - r;
-            if (ty < 0 || ty % p.stride || ty / p.stride >= p.rm.Ho) continue;
+            if (ty < 0 || ty % S || ty / S >= p.rm.Ho) continue;
             const float* Tr = T + ((size_t)r * kC + c) * pitch;
             for (int s_ = 0; s_ < p.k; ++s_) {
                 const int tx = x + p.pad - s_;
-                if (tx < 0 || tx % p.stride) continue;
-                const int ox = tx / p.stride;
+                if (tx < 0 || tx % S) continue;
+                const int ox = tx / S;
                 if (ox >= Wo) continue;
                 acc += Tr[(size_t)s_ * p.C * pitch + ox];
             }
@@ -227,20 +228,17 @@ struct TapP {
 };
 
 // out[n][co][y][x] = act(bias[co] + sum_j P[q + shift_j][j*nco + co])
-__global__ void tap_reduce_kernel(const float* P, long long ldp, const float* bias, int act, float* out, const TapP t) {
+__global__ void __launch_bounds__(256) tap_reduce_kernel(const float* P, long long ldp, const float* bias, int act, float* out, const TapP t) {
     irc::pdl_prologue();
-    const long long total = (long long)t.n_img * t.H * t.W;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % t.W);
-        const int y = (int)((idx / t.W) % t.H);
-        const int n = (int)(idx / ((long long)t.W * t.H));
-        const long long q = ((long long)n * t.hp + y + t.oy) * t.wp + x + t.ox;
-        for (int co = 0; co < t.nco; ++co) {
-            float acc = bias ? __ldg(bias + co) : 0.f;
-            for (int j = 0; j < t.nshift; ++j) acc += __ldg(P + (q + t.shifts[j]) * ldp + j * t.nco + co);
-            if (act == 3) acc = tanhf(acc);
-            out[(((long long)n * t.nco + co) * t.H + y) * t.W + x] = acc;
-        }
+    // grid = (x chunks, rows, images): no per-element index arithmetic
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, n = blockIdx.z;
+    if (x >= t.W) return;
+    const long long q = ((long long)n * t.hp + y + t.oy) * t.wp + x + t.ox;
+    for (int co = 0; co < t.nco; ++co) {
+        float acc = bias ? __ldg(bias + co) : 0.f;
+        for (int j = 0; j < t.nshift; ++j) acc += __ldg(P + (q + t.shifts[j]) * ldp + j * t.nco + co);
+        if (act == 3) acc = tanhf(acc);
+        out[(((long long)n * t.nco + co) * t.H + y) * t.W + x] = acc;
     }
 }
 
@@ -377,10 +375,16 @@ extern "C" int irc_col2im(const irc_col2im_args* a, void* stream) {
     const long long total = (long long)a->n_img * a->c_out * a->H * a->W;
     const int pitch = a->Wo | 1;                                  // odd pitch: the transposing stores spread over the banks
     const size_t smem = (size_t)a->k * a->k * a->C * pitch * sizeof(float);
-    if (a->k * a->k * a->C <= 64 && !(a->ld % 8) && !((uintptr_t)a->de & 15) && smem <= 160 * 1024 && a->H <= 65535 && a->n_img <= 65535) {
+    if (a->k * a->k * a->C <= 64 && !(a->ld % 8) && !((uintptr_t)a->de & 15) && smem <= 160 * 1024 && a->H <= 65535 && a->n_img <= 65535 &&
+        (a->stride == 1 || a->stride == 2)) {
         static size_t attr = 48 * 1024;
-        if (smem > attr) { cudaFuncSetAttribute(col2im_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = 160 * 1024; }
-        irc::launch(col2im_rows_kernel, dim3(a->H, a->n_img), 256, smem, (cudaStream_t)stream, p, pitch);
+        if (smem > attr) {
+            cudaFuncSetAttribute(col2im_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(col2im_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            attr = 160 * 1024;
+        }
+        if (a->stride == 1) irc::launch(col2im_rows_kernel<1>, dim3(a->H, a->n_img), 256, smem, (cudaStream_t)stream, p, pitch);
+        else irc::launch(col2im_rows_kernel<2>, dim3(a->H, a->n_img), 256, smem, (cudaStream_t)stream, p, pitch);
         return irc_check_launch("irc_col2im(rows)");
     }
     irc::launch(col2im_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, p);
@@ -403,7 +407,9 @@ static int fill_tap(const irc_tap_args* a, TapP& t) {
 extern "C" int irc_tap_reduce(const irc_tap_args* a, const float* P, long long ldp, const float* bias, int act, float* out, void* stream) {
     TapP t; int rc = fill_tap(a, t); if (rc) return rc;
     if (!P || !out) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tap_reduce: null");
-    irc::launch(tap_reduce_kernel, grid_for((long long)t.n_img * t.H * t.W, 256), 256, 0, (cudaStream_t)stream, P, ldp, bias, act, out, t);
+    if (t.H > 65535 || t.n_img > 65535) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tap_reduce: extent too large");
+    const int tb = t.W >= 256 ? 256 : ((t.W + 31) / 32) * 32;
+    irc::launch(tap_reduce_kernel, dim3((t.W + tb - 1) / tb, t.H, t.n_img), tb, 0, (cudaStream_t)stream, P, ldp, bias, act, out, t);
     return irc_check_launch("irc_tap_reduce");
 }
 
