@@ -45,6 +45,19 @@ __global__ void pack_kernel(const float* __restrict__ src, const int* __restrict
     }
 }
 
+// 8 outputs per thread: two 16-byte map loads, eight gathers in flight, one 16-byte store (n % 8 == 0, aligned buffers)
+__global__ void pack8_kernel(const float* __restrict__ src, const int* __restrict__ map, long long n8, bf16* __restrict__ dst) {
+    irc::pdl_prologue();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const int4 a = __ldg(reinterpret_cast<const int4*>(map) + 2 * i), b = __ldg(reinterpret_cast<const int4*>(map) + 2 * i + 1);
+        const int j[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = j[k] >= 0 ? __ldg(src + j[k]) : 0.f;
+        reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+}
+
 __global__ void gather_sum_kernel(const float* __restrict__ src, const int* __restrict__ map, long long n, int splits, long long split_stride,
                                   float* __restrict__ dst) {
     irc::pdl_prologue();
@@ -70,7 +83,16 @@ __global__ void gather_sum_multi_kernel(const irc_sum_job* __restrict__ jobs, in
         const long long e = i - jb.start;
         const int j = jb.map[e];
         float a = 0.f;
-        if (j >= 0) for (int s = 0; s < jb.splits; ++s) a += jb.src[(long long)s * jb.split_stride + j];
+        if (j >= 0) {
+            const float* sp = jb.src + j;
+            int s = 0;
+            for (; s + 4 <= jb.splits; s += 4) {          // four independent loads in flight, added in split order
+                const float v0 = __ldg(sp), v1 = __ldg(sp + jb.split_stride), v2 = __ldg(sp + 2 * jb.split_stride), v3 = __ldg(sp + 3 * jb.split_stride);
+                a += v0; a += v1; a += v2; a += v3;
+                sp += 4 * jb.split_stride;
+            }
+            for (; s < jb.splits; ++s) { a += __ldg(sp); sp += jb.split_stride; }
+        }
         jb.dst[e] = a;
     }
 }
@@ -94,7 +116,10 @@ extern "C" int irc_adam(float* p, const float* g, float* m, float* v, long long 
 
 extern "C" int irc_pack_bf16(const float* src, const int* map, long long n, void* dst, void* stream) {
     if (!src || !map || !dst) return irc_set_error(IRC_ERR_BAD_ARG, "irc_pack_bf16: null");
-    irc::launch(pack_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, src, map, n, (bf16*)dst);
+    if (n % 8 == 0 && !((uintptr_t)map & 15) && !((uintptr_t)dst & 15))
+        irc::launch(pack8_kernel, grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream, src, map, n / 8, (bf16*)dst);
+    else
+        irc::launch(pack_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, src, map, n, (bf16*)dst);
     return irc_check_launch("irc_pack_bf16");
 }
 

@@ -180,3 +180,19 @@ def test_vgg_module_and_test_mode(fp32_frames):
     assert np.allclose([mae[0], mse[0], psnr[0]], GOLD["metrics"], rtol=1e-6)
     m = R.compute_metrics(GOLD["quant_u8"].astype(np.float32) / 255.0, GOLD["metrics_gt"])
     assert np.allclose(m[:3], GOLD["metrics"], rtol=0, atol=0) and m[3] is None
+
+
+def test_stream_window_classifies_the_stencil_tables():
+    """host-side gate of the streaming stencil kernels: the anti-aliased down/up-sampling operators and their transposes have
+    a non-decreasing last source row and a bounded window; the reflection-fold operator does not (it falls back)"""
+    from irc_b200 import layout as L
+    for n in (8, 12, 64):
+        cases = {"down": (L.down_matrix(n), 3), "up": (L.up_matrix(n), 3), "downT": (L.down_matrix(n).T, 2), "upT": (L.up_matrix(n).T, 6)}
+        for name, (m, k) in cases.items():
+            t = L.make_tables(m, m, "cpu")
+            assert t.stream_window() == k, (name, n, t.stream_window())
+            assert t.stream_window(8) == k
+        fold = L.make_tables(L.fold_matrix(n, 1), L.fold_matrix(n, 1), "cpu")
+        assert fold.stream_window() == 0
+        # identity along one axis: not a streaming case
+        assert L.make_tables(L.down_matrix(n), None, "cpu").stream_window() == 0
