@@ -48,9 +48,10 @@ __global__ void __launch_bounds__(256) pixel_loss_vec_kernel(const float* __rest
     const float4* r4 = reinterpret_cast<const float4*>(r);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
-        const long long row = v / W4;
-        const int x4 = (int)(v - row * W4);
-        const int y = (int)(row % H);
+        // 32-bit index arithmetic (the host checks total < 2^31): a 64-bit division costs ~100 instructions per vector
+        const unsigned row = (unsigned)v / (unsigned)W4;
+        const int x4 = (int)((unsigned)v - row * (unsigned)W4);
+        const int y = (int)(row % (unsigned)H);
         const float4 c4 = __ldg(f4 + v);
         const float c[4] = {c4.x, c4.y, c4.z, c4.w};
         float g[4] = {0.f, 0.f, 0.f, 0.f};
@@ -280,7 +281,8 @@ extern "C" int irc_pixel_loss(const float* fake, const float* target, int n_img,
                               float* sums, float* dfake, void* stream) {
     if (!fake || !sums) return irc_set_error(IRC_ERR_BAD_ARG, "irc_pixel_loss: null");
     const long long planes = (long long)n_img * C;
-    const bool vec = W % 4 == 0 && !((uintptr_t)fake & 15) && !((uintptr_t)target & 15) && !((uintptr_t)dfake & 15);
+    const bool vec = W % 4 == 0 && !((uintptr_t)fake & 15) && !((uintptr_t)target & 15) && !((uintptr_t)dfake & 15) &&
+                     planes * H * (W / 4) < (1LL << 31);
     if (vec) irc::launch(pixel_loss_vec_kernel, grid_for(planes * H * (W / 4), 256, 8), 256, 0, (cudaStream_t)stream, fake, target, planes, H, W, w_l1, w_tvv, w_tvh, sums, dfake);
     else irc::launch(pixel_loss_kernel, grid_for(planes * H * W, 256, 8), 256, 0, (cudaStream_t)stream, fake, target, planes, H, W, w_l1, w_tvv, w_tvh, sums, dfake);
     return irc_check_launch("irc_pixel_loss");
