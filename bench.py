@@ -109,8 +109,10 @@ def run_reference(args, rank, world):
     val = Bs / sec
     line = dict(impl="reference", metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warm,
                 ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="single GAN train step (G+D, hinge+L1+VGG+TV+SSIM) at 256x256, reference algorithm on CPU",
-                            sample=f"batch {Bs} per step instead of 16 (img/s is per image)", l2="n/a (CPU)"),
+                config=dict(workload="single GAN train step (G+D, hinge+L1+VGG+TV+SSIM losses) at 256x256 batch 16 per GPU "
+                                     "(BASELINE.json configs[1]; configs[2] when n_gpus > 1)",
+                            global_batch=16 * args.gpus, parallelism=f"dp{args.gpus}", cuda_graph=False,
+                            sample=f"reference algorithm on the host CPU, batch {Bs} per step instead of 16 (img/s is per image)", l2="n/a (CPU)"),
                 cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port",
                                   sample=f"{steps} step(s) of batch {Bs} at 256x256, torch CPU fp32, {cores} threads"),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
