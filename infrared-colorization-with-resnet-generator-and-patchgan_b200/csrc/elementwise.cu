@@ -295,6 +295,87 @@ __global__ void __launch_bounds__(256, 4) gather_kernel(const GatherP p) {
 }
 
 // ---------------------------------------------------------------------------------
+// Identity-table gather (InstanceNorm apply + activation (+ residual) into a frame with its ring) with the source pixels
+// prefetched kPipeD ahead per thread through private cp.async slots: same latency argument as the reductions.
+// ---------------------------------------------------------------------------------
+template <bool kRes>
+__global__ void __launch_bounds__(256, 4) gather_ident_pipe_kernel(const GatherP p) {
+    irc::pdl_prologue();
+    extern __shared__ uint4 gpslots[];
+    constexpr int NT = kRes ? 2 : 1;
+    const int nt = blockDim.x;
+    uint4* slot = gpslots + threadIdx.x;
+    const int C8 = p.C >> 3;
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int c = cv * 8;
+    const int Hp = p.H + 2 * p.pad, Wp = p.W + 2 * p.pad;
+    const int rows = p.n_img * Hp;
+    // decode of padded pixel (row, X): source coordinates, or live = false for the zero ring
+    auto decode = [&](int row, int X, int& n, int& y, int& x) -> bool {
+        n = row / Hp;
+        const int Y = row - n * Hp;
+        y = Y - p.pad; x = X - p.pad;
+        const bool halo = y < 0 || y >= p.H || x < 0 || x >= p.W;
+        if (halo) {
+            if (p.halo_mode != 1) return false;
+            y = reflect_idx(y, p.H); x = reflect_idx(x, p.W);
+        }
+        return true;
+    };
+    int irow = blockIdx.x, iX = lane, crow = blockIdx.x, cX = lane;
+    auto issue = [&](int st) {
+        if (irow < rows) {
+            int n, y, x;
+            if (decode(irow, iX, n, y, x)) {
+                cp_async16(slot + (st * NT + 0) * nt, p.src.at(n, y, x, c));
+                if (kRes) cp_async16(slot + (st * NT + 1) * nt, p.res.at(n, y, x, c));
+            }
+            iX += L; if (iX >= Wp) { iX = lane; irow += gridDim.x; }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int st = 0; st < kPipeD; ++st) issue(st);
+    float mu[8], rs[8];
+    int cur_n = -1, st = 0;
+    while (crow < rows) {
+        int n, y, x;
+        const bool live = decode(crow, cX, n, y, x);
+        if (n != cur_n && p.stats) {
+            cur_n = n;
+            moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mu[k] = -mu[k] * rs[k];
+        }
+        cp_async_wait<kPipeD - 1>();
+        const uint4 zr = slot[(st * NT + 0) * nt];
+        uint4 rr = make_uint4(0, 0, 0, 0);
+        if (kRes) rr = slot[(st * NT + 1) * nt];
+        issue(st);
+        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (live) {
+            unpack8(zr, v);
+            if (p.stats) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const float t = fmaf(v[k], rs[k], mu[k]); v[k] = fmaxf(t, 0.f) + p.slope_eff * fminf(t, 0.f); }
+            }
+            if (kRes) {
+                float u[8];
+                unpack8(rr, u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] += u[k];
+            }
+        }
+        const int Y = crow - n * Hp;
+        bf16* d = const_cast<bf16*>(p.dst.p) + ((long long)(n * p.dst.hp + Y - p.pad + p.dst.oy) * p.dst.wp + (cX - p.pad + p.dst.ox)) * p.dst.ld + p.dst.off + c;
+        store8(d, v);
+        cX += L; if (cX >= Wp) { cX = lane; crow += gridDim.x; }
+        st = st + 1 == kPipeD ? 0 : st + 1;
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------
 // Lean table gather: K x K taps with K a compile-time constant (2: reflection fold / Downsample^T, 3: Downsample and
 // UpsampleAA, 6: UpsampleAA^T).  One block per output row: the row's y-entries and source row pointers are computed once,
 // the x-entries of a pixel sit in registers, and the K*K 16-byte loads per output vector hit L1/L2 (every source pixel
@@ -1515,6 +1596,13 @@ extern "C" int irc_gather(const irc_gather_args* a, void* stream) {
     row_block(p.C, p.W + 2 * p.pad, threads, L);
     const long long rows = (long long)p.n_img * (p.H + 2 * p.pad);
     const unsigned grid = (unsigned)(rows < 65535 * 16 ? rows : 65535 * 16);
+    if (!p.ty_idx && !p.tx_idx && !p.has2 && !p.dst_s2d && !p.src.s2d_c && !(p.has_res && p.res.s2d_c) && (p.stats || !p.act) && !getenv("IRC_NO_GATHER_PIPE")) {
+        const size_t smem = (size_t)kPipeD * (p.has_res ? 2 : 1) * threads * 16;
+        const unsigned gp = (unsigned)(rows < (long long)irc_num_sms() * 16 ? rows : (long long)irc_num_sms() * 16);
+        if (p.has_res) irc::launch(gather_ident_pipe_kernel<true>, gp, threads, smem, (cudaStream_t)stream, p);
+        else irc::launch(gather_ident_pipe_kernel<false>, gp, threads, smem, (cudaStream_t)stream, p);
+        return irc_check_launch("irc_gather(pipe)");
+    }
     if (!p.ty_idx && !p.tx_idx) irc::launch(gather_kernel<true>, grid, threads, 0, (cudaStream_t)stream, p);
     else irc::launch(gather_kernel<false>, grid, threads, 0, (cudaStream_t)stream, p);
     return irc_check_launch("irc_gather");
