@@ -66,11 +66,11 @@ struct Im2colP {
     bf16* dst; short* row_img;
 };
 
-__global__ void __launch_bounds__(256) im2col_kernel(const Im2colP p, int R, int Wp) {
-    // One block per (image, line of the row order).  The R input rows the line needs are staged once in shared memory
-    // - all channels, padding / reflection and the per-channel affine resolved while filling, with coalesced loads -
-    // so a thread (one item of the line x one group of 8 columns) assembles its 16 bytes with 8 shared-memory reads at
-    // register-resident offsets: no border cases, no scattered global loads.
+__global__ void __launch_bounds__(256) im2col_kernel(const Im2colP p, int R, int Wp, int LPB) {
+    // One block per (image, group of LPB consecutive lines of the row order).  The R input rows the group needs are staged
+    // once in shared memory - all channels, padding / reflection and the per-channel affine resolved while filling, with
+    // coalesced loads - so a thread (one item of a line x one group of 8 columns) assembles its 16 bytes with 8
+    // shared-memory reads at register-resident offsets: no border cases, no scattered global loads.
     irc::pdl_prologue();
     extern __shared__ float tile[];                 // [C][R][Wp]
     const int C = p.c1 + p.c2;
@@ -88,13 +88,15 @@ __global__ void __launch_bounds__(256) im2col_kernel(const Im2colP p, int R, int
         }
     }
     const int nl = p.rm.lines(), ll = p.rm.line_len();
+    const int ngrp = (nl + LPB - 1) / LPB;
     const long long hw = (long long)p.H * p.W;
-    for (int bl = blockIdx.x; bl < p.rm.n_img * nl; bl += gridDim.x) {
-        const int n = bl / nl, line = bl - n * nl;
-        // first output row of the line and the input row it starts at
-        const int oy0 = p.rm.mode == 0 ? line : (p.rm.mode == 1 ? line - 1 : 2 * line - 1);
+    for (int bg = blockIdx.x; bg < p.rm.n_img * ngrp; bg += gridDim.x) {
+        const int n = bg / ngrp, line0 = (bg - n * ngrp) * LPB;
+        const int nlines = min(LPB, nl - line0);
+        // first output row of the group and the input row it starts at
+        const int oy0 = p.rm.mode == 0 ? line0 : (p.rm.mode == 1 ? line0 - 1 : 2 * line0 - 1);
         const int y_lo = oy0 * p.stride - p.pad;
-        __syncthreads();                            // the previous line's readers are done with the tile
+        __syncthreads();                            // the previous group's readers are done with the tile
         // one warp per staged row (channel c, input row r): the row decode happens once, lanes run along x
         for (int t = threadIdx.x >> 5; t < C * R; t += blockDim.x >> 5) {
             const int c = t / R, r = t - c * R;
@@ -113,19 +115,23 @@ __global__ void __launch_bounds__(256) im2col_kernel(const Im2colP p, int R, int
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x >> 3; i < ll; i += blockDim.x >> 3) {
-            const long long q = (long long)bl * ll + i;
-            int oy, ox;
-            const bool live = p.rm.decode_line(line, i, oy, ox);
-            if (g == 0 && p.row_img) p.row_img[q] = live ? (short)n : (short)-1;
-            float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (live) {
-                const int base = (oy - oy0) * p.stride * Wp + ox * p.stride;
+        for (int l = 0; l < nlines; ++l) {
+            const int line = line0 + l;
+            const long long qbase = ((long long)n * nl + line) * ll;
+            for (int i = threadIdx.x >> 3; i < ll; i += blockDim.x >> 3) {
+                const long long q = qbase + i;
+                int oy, ox;
+                const bool live = p.rm.decode_line(line, i, oy, ox);
+                if (g == 0 && p.row_img) p.row_img[q] = live ? (short)n : (short)-1;
+                float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (live) {
+                    const int base = (oy - oy0) * p.stride * Wp + ox * p.stride;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = (valid >> j) & 1 ? tile[base + off[j]] : 0.f;
+                    for (int j = 0; j < 8; ++j) v[j] = (valid >> j) & 1 ? tile[base + off[j]] : 0.f;
+                }
+                *reinterpret_cast<uint4*>(p.dst + q * 64 + g * 8) =
+                    make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
             }
-            *reinterpret_cast<uint4*>(p.dst + q * 64 + g * 8) =
-                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
     }
 }
@@ -354,14 +360,17 @@ extern "C" int irc_im2col(const irc_im2col_args* a, void* stream) {
     p.H = a->H; p.W = a->W; p.k = a->k; p.stride = a->stride; p.pad = a->pad; p.pad_mode = a->pad_mode;
     p.rm.mode = a->row_mode; p.rm.n_img = a->n_img; p.rm.Ho = a->Ho; p.rm.Wo = a->Wo;
     p.dst = (bf16*)a->dst; p.row_img = a->row_img;
-    const long long nblk = (long long)p.rm.n_img * p.rm.lines();
-    // input rows per line (mode 2 lines hold two output rows) and padded row width of the staged tile
-    const int R = (a->row_mode == 2 ? a->stride : 0) + a->k, Wp = a->W + 2 * a->pad;
+    // LPB consecutive lines share one staged tile (amortises the fill and its two barriers); a line holds one output row
+    // (two in the space-to-depth order), so the tile needs (rows_out - 1) * stride + k input rows
+    const int LPB = 4;
+    const int rows_out = LPB * (a->row_mode == 2 ? 2 : 1);
+    const int R = (rows_out - 1) * a->stride + a->k, Wp = a->W + 2 * a->pad;
     const size_t smem = (size_t)C * R * Wp * sizeof(float);
     if (smem > 200 * 1024) return irc_set_error(IRC_ERR_BAD_ARG, "irc_im2col: line tile does not fit shared memory");
     static size_t attr = 48 * 1024;
     if (smem > attr) { cudaFuncSetAttribute(im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = 200 * 1024; }
-    irc::launch(im2col_kernel, (unsigned)(nblk < 1048576 ? nblk : 1048576), 256, smem, (cudaStream_t)stream, p, R, Wp);
+    const long long nblk = (long long)p.rm.n_img * ((p.rm.lines() + LPB - 1) / LPB);
+    irc::launch(im2col_kernel, (unsigned)(nblk < 1048576 ? nblk : 1048576), 256, smem, (cudaStream_t)stream, p, R, Wp, LPB);
     return irc_check_launch("irc_im2col");
 }
 
