@@ -362,7 +362,7 @@ extern "C" int irc_im2col(const irc_im2col_args* a, void* stream) {
     p.dst = (bf16*)a->dst; p.row_img = a->row_img;
     // LPB consecutive lines share one staged tile (amortises the fill and its two barriers); a line holds one output row
     // (two in the space-to-depth order), so the tile needs (rows_out - 1) * stride + k input rows
-    const int LPB = 4;
+    const int LPB = a->row_mode == 2 ? 2 : 8;
     const int rows_out = LPB * (a->row_mode == 2 ? 2 : 1);
     const int R = (rows_out - 1) * a->stride + a->k, Wp = a->W + 2 * a->pad;
     const size_t smem = (size_t)C * R * Wp * sizeof(float);
