@@ -58,8 +58,6 @@ typedef struct irc_conv_gemm_args {
     int mt;                 /* 128-row sub-tiles per tile sharing each weight stage: 1, 2, 0 = auto */
     int reuse;              /* taps with consecutive shifts share one staged A tile: 0 off, 1 on, -1 auto */
     int epilogue_direct;    /* 1 = store rows straight from registers (default 0: swizzled smem staging + TMA stores) */
-    void* dbg;              /* optional: 8 int64 per CTA of pipeline wait-cycle counters (profiling aid), else NULL */
-    int dbg_mode;           /* profiling experiments (results invalid): 1 = skip TMA, 2 = skip MMA; 0 in production */
 } irc_conv_gemm_args;
 int irc_conv_gemm(const irc_conv_gemm_args* args, void* stream);
 
@@ -237,11 +235,18 @@ int irc_feat_l1(const void* feat, long long rows_half, long long ld, int C, floa
  * u8[n][y][x][c] = trunc(clip((fake+1)/2,0,1)*255); sums[n] = (sum|u8/255-gt|, sum(u8/255-gt)^2). */
 int irc_quantize_metrics(const float* fake, const float* gt, int n_img, int C, int H, int W, unsigned char* u8, double* sums, void* stream);
 
+/* Running loss sums on the device (irc:1683-1697 averages every step of an epoch; this removes the per-step .item()
+ * synchronisation): acc[j] += coef[j][n] + sum_i coef[j][i] * s[i], coef is [rows][n+1] fp32, rows <= 32. */
+int irc_accumulate(const float* s, int n, const float* coef, int rows, double* acc, void* stream);
+
 /* ---- optimizer / parameter layout ------------------------------------------------------ */
 
-/* torch.optim.Adam step (irc:1651, :1681) over a flat arena.
- * hyper (device) = {lr, beta1, beta2, eps, 1-beta1^t, 1-beta2^t, grad_scale}. */
-int irc_adam(float* p, const float* g, float* m, float* v, long long n, const float* hyper, void* stream);
+/* torch.optim.Adam step (irc:1651, :1681; defaults of irc:1601-1604) over a flat arena.
+ * hyper (device, fp64) = {lr, beta1, beta2, eps, lr_scale, grad_scale}: the step uses lr*lr_scale (LambdaLR factor,
+ * irc:1606-1609) and g*grad_scale (1/world_size when the gradients were sum-all-reduced).
+ * step_count (device): optimizer steps taken so far; the bias corrections use *step_count + 1 and a second tiny launch
+ * on the same stream advances it, so a captured CUDA graph replays correctly without host writes. */
+int irc_adam(float* p, const float* g, float* m, float* v, long long n, const double* hyper, long long* step_count, void* stream);
 /* dst[i] = bf16(map[i] >= 0 ? src[map[i]] : 0): OIHW fp32 parameters -> packed GEMM operands. */
 int irc_pack_bf16(const float* src, const int* map, long long n, void* dst, void* stream);
 /* dst[i] = sum_s src[s*split_stride + map[i]]: split weight-gradient partials -> OIHW fp32. */

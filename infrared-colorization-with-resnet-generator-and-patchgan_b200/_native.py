@@ -21,7 +21,7 @@ EXPORTS = [
     "irc_in_stats", "irc_gather", "irc_in_apply_fused", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_in_bwd_fused", "irc_maxpool2", "irc_maxpool2_bwd",
     "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
     "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics",
-    "irc_adam", "irc_pack_bf16", "irc_gather_sum", "irc_gather_sum_multi", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
+    "irc_adam", "irc_accumulate", "irc_pack_bf16", "irc_gather_sum", "irc_gather_sum_multi", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
 ]
 
 
@@ -39,7 +39,7 @@ class ConvGemmArgs(C.Structure):
         ("row_img", C.c_void_p),
         ("mask", C.c_void_p), ("mask_ld", C.c_longlong), ("mask_chan_off", C.c_int), ("mask_slope", C.c_float),
         ("addend", C.c_void_p), ("addend_ld", C.c_longlong), ("addend_chan_off", C.c_int),
-        ("bn", C.c_int), ("mt", C.c_int), ("reuse", C.c_int), ("epilogue_direct", C.c_int), ("dbg", C.c_void_p), ("dbg_mode", C.c_int),
+        ("bn", C.c_int), ("mt", C.c_int), ("reuse", C.c_int), ("epilogue_direct", C.c_int),
     ]
 
 
@@ -273,20 +273,13 @@ class CudaBackend:
         self.timers = None
         self.note = ("", "", 0.0)
         self.conv_mt = int(os.environ.get("IRC_CONV_MT", "0"))   # 0 = let the library choose the M sub-tiling of conv_gemm
-        self.conv_dbg = None
         self.fused_in_bwd = os.environ.get("IRC_FUSED_IN_BWD", "1") != "0"   # cluster-resident single-pass InstanceNorm backward
         self.fused_in_apply = os.environ.get("IRC_FUSED_IN_APPLY", "1") != "0"
         self.batch_sums = os.environ.get("IRC_BATCH_SUMS", "1") != "0"      # one launch for all split-K weight-gradient reductions
         self._pending, self._sum_tables = [], {}
         self.gather_mode = os.environ.get("IRC_GATHER", "auto")     # lean | tiled | generic (stencil gather kernel choice)
         self.conv_epilogue_direct = int(os.environ.get("IRC_EPI_DIRECT", "0"))
-        self.conv_dbg_mode = 0
         self.conv_reuse = int(os.environ.get("IRC_CONV_REUSE", "0"))
-        # timing ablation only (results become wrong): IRC_SKIP=fold_inplace,in_stats,... turns those launchers into
-        # no-ops so that a captured step shows their real cost inside the graph (scripts/ablate.sh)
-        for name in filter(None, os.environ.get("IRC_SKIP", "").split(",")):
-            assert hasattr(self, name), name
-            setattr(self, name, lambda *a, **k: None)
 
     def time_all_launchers(self):
         """bench.py --breakdown-all: bracket EVERY launcher call with CUDA events (eager mode) so that the memory-bound
@@ -340,7 +333,7 @@ class CudaBackend:
         if addend is not None:
             assert addend.t.shape[0] == a.shape[0]
             g.addend = addend.t.data_ptr(); g.addend_ld = addend.t.shape[1]; g.addend_chan_off = addend.chan_off
-        g.bn = 0; g.mt = self.conv_mt; g.reuse = self.conv_reuse; g.epilogue_direct = self.conv_epilogue_direct; g.dbg = None if self.conv_dbg is None else self.conv_dbg.data_ptr(); g.dbg_mode = self.conv_dbg_mode
+        g.bn = 0; g.mt = self.conv_mt; g.reuse = self.conv_reuse; g.epilogue_direct = self.conv_epilogue_direct;
         self._timed("conv_gemm", lambda: check(self.L.irc_conv_gemm(C.byref(g), _stream()))); self.launches += 1
 
     def tn_gemm(self, a, a_chan_off, m, b, b_chan_off, n, k_rows, a_shift, b_shift, out, tap_stride, m_stride, n_stride,
@@ -535,8 +528,14 @@ class CudaBackend:
         check(self.L.irc_quantize_metrics(_p(fake), _p(gt), n, c, h, w, _p(u8), _p(sums), _stream())); self.launches += 1
 
     # ---- optimizer / layout
-    def adam(self, p, g, m, v, hyper):
-        check(self.L.irc_adam(_p(p), _p(g), _p(m), _p(v), C.c_longlong(p.numel()), _p(hyper), _stream())); self.launches += 1
+    def adam(self, p, g, m, v, hyper, step_dev):
+        """hyper: fp64 device vector {lr, b1, b2, eps, lr_scale, grad_scale}; step_dev: int64 device step counter (advanced here)"""
+        assert hyper.dtype == torch.float64 and step_dev.dtype == torch.int64
+        check(self.L.irc_adam(_p(p), _p(g), _p(m), _p(v), C.c_longlong(p.numel()), _p(hyper), _p(step_dev), _stream())); self.launches += 2
+
+    def accumulate(self, sums, coef, acc):
+        assert sums.dtype == torch.float32 and coef.dtype == torch.float32 and acc.dtype == torch.float64 and coef.shape[1] == sums.numel() + 1
+        check(self.L.irc_accumulate(_p(sums), sums.numel(), _p(coef), coef.shape[0], _p(acc), _stream())); self.launches += 1
 
     def pack_bf16(self, src, map_, dst):
         check(self.L.irc_pack_bf16(_p(src), _p(map_), C.c_longlong(map_.numel()), _p(dst), _stream())); self.launches += 1

@@ -90,16 +90,7 @@ struct ConvParams {
     int n_out;
     int nstg;       // staging tiles of the TMA-store epilogue (2, or 1 when shared memory is needed for pipeline stages)
     int tma_store;  // 1: bf16 rows leave through a swizzled shared-memory staging tile and TMA stores (coalesced)
-    int dbg_mode;   // profiling experiments: 1 = no TMA traffic (MMA issue/execute rate only), 2 = TMA only (no MMAs)
-    long long* dbg; // optional per-CTA cycle counters {mma wait full, mma wait tmem-empty, producer wait empty, epilogue wait tmem-full, total}
 };
-
-__device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, long long& acc, bool on) {
-    if (!on) { mbar_wait(bar, parity); return; }
-    const long long t0 = clock64();
-    mbar_wait(bar, parity);
-    acc += clock64() - t0;
-}
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     if (act == 1) return fmaxf(v, 0.f);
@@ -271,13 +262,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const bool dbg = p.dbg != nullptr;
-    long long w0 = 0, w1 = 0, w2 = 0;
-    const long long tstart = clock64();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (p.dbg_mode != 1 && p.dbg_mode != 3 && p.dbg_mode != 4) {
+        {
             int stage = 0; uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const long long row0 = (tile / p.n_tiles) * tile_rows;
@@ -285,7 +273,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constan
                 for (int t = 0; t < p.ntaps; ++t) {
                     const long long arow = row0 + p.taps[t];
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        timed_wait(&empty[stage], phase ^ 1, w0, dbg);
+                        mbar_wait(&empty[stage], phase ^ 1);
                         if (elect_one()) {
                             mbar_expect_tx(&full[stage], stage_bytes);
                             uint8_t* sa = smem + (size_t)stage * stage_bytes;
@@ -306,12 +294,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constan
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                timed_wait(&tempty[acc], acc_phase ^ 1, w1, dbg);
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    if (p.dbg_mode != 1 && p.dbg_mode != 3 && p.dbg_mode != 4) timed_wait(&full[stage], phase, w0, dbg);
-                    if (p.dbg_mode != 4) tc_fence_after();
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint64_t bdesc = umma_desc_sw128(sa + stage_a, 16);
                     if (elect_one()) {
@@ -320,16 +308,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constan
                         // tiles need 2-4 independent chains in flight to reach the tensor-pipe rate
                         const uint64_t adesc = umma_desc_sw128(sa, 16);
                         const uint32_t accum = kb != 0;
-                        if (p.dbg_mode != 2) {
 #pragma unroll
-                            for (int k = 0; k < kBK / 16; ++k) {
+                        for (int k = 0; k < kBK / 16; ++k) {
 #pragma unroll
-                                for (int m = 0; m < MT; ++m)
-                                    umma_bf16(d_tmem + (uint32_t)(m * p.bn), adesc + (uint64_t)(m * (kBM * 128 / 16) + k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                              k == 0 ? accum : 1u);
-                            }
+                            for (int m = 0; m < MT; ++m)
+                                umma_bf16(d_tmem + (uint32_t)(m * p.bn), adesc + (uint64_t)(m * (kBM * 128 / 16) + k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                          k == 0 ? accum : 1u);
                         }
-                        if (p.dbg_mode != 3 && p.dbg_mode != 4) umma_commit(&empty[stage]);
+                        umma_commit(&empty[stage]);
                     }
                     __syncwarp();
                     if (++stage == S) { stage = 0; phase ^= 1; }
@@ -352,9 +338,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constan
         const bool store_thread = warp == 2 && lane == 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int n0 = (int)(tile % p.n_tiles) * p.bn;
-            timed_wait(&tfull[acc], acc_phase, w0, dbg);
+            mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const long long tb0 = dbg ? clock64() : 0;
 #pragma unroll 1
             for (int m = 0; m < MT; ++m) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(m * p.bn);
@@ -365,18 +350,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (dbg) w2 += clock64() - tb0;
             if (++acc == p.nbuf) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     if (p.tma_store && warp == 2 && lane == 0) bulk_wait_group<0>();      // all output tiles have left shared memory
-    if (dbg && lane == 0) {
-        long long* d = p.dbg + (long long)blockIdx.x * 8;
-        if (warp == 0) d[2] = w0;
-        if (warp == 1) { d[0] = w0; d[1] = w1; d[4] = clock64() - tstart; }
-        if (warp == 2) { d[3] = w0; d[5] = w1; d[6] = w2; d[7] = clock64() - tstart; }
-    }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -939,7 +917,7 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     p.addend = (const bf16*)a->addend; p.addend_ld = a->addend_ld; p.addend_chan_off = a->addend_chan_off;
     if (a->addend && (((uintptr_t)a->addend & 15) || (a->addend_ld % 8) || (a->addend_chan_off % 8)))
         return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: addend rows must be 16-byte aligned");
-    p.stats = nullptr; p.n_out = a->n_out; p.dbg = (long long*)a->dbg; p.dbg_mode = a->dbg_mode;
+    p.stats = nullptr; p.n_out = a->n_out;
     // coalesced TMA-store epilogue for bf16 outputs whose tile width is a multiple of one 64-channel swizzle row
     p.tma_store = (!a->out_fp32 && bn % 64 == 0 && a->epilogue_direct == 0) ? 1 : 0;
     CUtensorMap tmOut = tmB;

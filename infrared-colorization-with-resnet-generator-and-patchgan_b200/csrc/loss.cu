@@ -267,6 +267,19 @@ __global__ void quantize_metrics_kernel(const float* __restrict__ fake, const fl
     }
 }
 
+// acc[j] += coef[j][n] + sum_i coef[j][i] * s[i]   (rows <= 32, one warp per row; fixed summation order)
+__global__ void accumulate_kernel(const float* __restrict__ s, int n, const float* __restrict__ coef, int rows, double* __restrict__ acc) {
+    irc::pdl_prologue();
+    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (j >= rows) return;
+    const float* c = coef + (long long)j * (n + 1);
+    double a = 0.0;
+    for (int i = lane; i < n; i += 32) a += (double)c[i] * (double)s[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) acc[j] += a + (double)c[n];
+}
+
 int grid_for(long long total, int threads, int per_sm) {
     long long b = (total + threads - 1) / threads;
     const long long cap = (long long)irc_num_sms() * per_sm;
@@ -324,4 +337,10 @@ extern "C" int irc_quantize_metrics(const float* fake, const float* gt, int n_im
     int bx = grid_for((long long)C * H * W, 256, 4); 
     irc::launch(quantize_metrics_kernel, dim3(bx, n_img), 256, 0, (cudaStream_t)stream, fake, gt, C, H, W, u8, sums);
     return irc_check_launch("irc_quantize_metrics");
+}
+
+extern "C" int irc_accumulate(const float* s, int n, const float* coef, int rows, double* acc, void* stream) {
+    if (!s || !coef || !acc || n <= 0 || rows <= 0 || rows > 32) return irc_set_error(IRC_ERR_BAD_ARG, "irc_accumulate: bad args");
+    irc::launch(accumulate_kernel, 1, rows * 32, 0, (cudaStream_t)stream, s, n, coef, rows, acc);
+    return irc_check_launch("irc_accumulate");
 }

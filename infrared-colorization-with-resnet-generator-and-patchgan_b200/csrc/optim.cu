@@ -8,12 +8,17 @@ using namespace irc;
 
 namespace {
 
-// hyper = {lr, beta1, beta2, eps, 1-beta1^t, 1-beta2^t, grad_scale}
+// hyper (device, fp64) = {lr, beta1, beta2, eps, lr_scale, grad_scale}; *step = optimizer steps taken so far.
+// The step counter lives on the device and is advanced by adam_bump_kernel right behind this kernel on the same stream, so a
+// replayed CUDA graph computes the right bias corrections 1 - beta^t without any per-step host write (a pinned staging
+// buffer rewritten by a host that runs ahead of the GPU would race with its own earlier copies).
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-                            const float* __restrict__ hyper) {
+                            const double* __restrict__ hyper, const long long* __restrict__ step_count) {
     irc::pdl_prologue();
-    const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], bc1 = hyper[4], bc2 = hyper[5], gs = hyper[6];
-    const float step = __fdiv_rn(lr, bc1), inv_sqrt_bc2 = __fdiv_rn(1.f, sqrtf(bc2));
+    const double t = (double)(*step_count + 1);
+    const double bc1d = 1.0 - pow(hyper[1], t), bc2d = 1.0 - pow(hyper[2], t);
+    const float b1 = (float)hyper[1], b2 = (float)hyper[2], eps = (float)hyper[3], gs = (float)hyper[5];
+    const float step = (float)(hyper[0] * hyper[4] / bc1d), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2d));
     const long long n4 = n >> 2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -35,6 +40,11 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         m[i] = mk; v[i] = vk;
         p[i] -= step * __fdiv_rn(mk, sqrtf(vk) * inv_sqrt_bc2 + eps);
     }
+}
+
+__global__ void adam_bump_kernel(long long* step_count) {
+    irc::pdl_prologue();
+    if (threadIdx.x == 0 && blockIdx.x == 0) *step_count += 1;
 }
 
 __global__ void pack_kernel(const float* __restrict__ src, const int* __restrict__ map, long long n, bf16* __restrict__ dst) {
@@ -107,10 +117,11 @@ int grid_for(long long total, int threads) {
 
 }  // namespace
 
-extern "C" int irc_adam(float* p, const float* g, float* m, float* v, long long n, const float* hyper, void* stream) {
-    if (!p || !g || !m || !v || !hyper) return irc_set_error(IRC_ERR_BAD_ARG, "irc_adam: null");
+extern "C" int irc_adam(float* p, const float* g, float* m, float* v, long long n, const double* hyper, long long* step_count, void* stream) {
+    if (!p || !g || !m || !v || !hyper || !step_count) return irc_set_error(IRC_ERR_BAD_ARG, "irc_adam: null");
     if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return irc_set_error(IRC_ERR_BAD_ARG, "irc_adam: arenas must be 16-byte aligned");
-    irc::launch(adam_kernel, grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream, p, g, m, v, n, hyper);
+    irc::launch(adam_kernel, grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream, p, g, m, v, n, hyper, (const long long*)step_count);
+    irc::launch(adam_bump_kernel, 1, 32, 0, (cudaStream_t)stream, step_count);
     return irc_check_launch("irc_adam");
 }
 

@@ -18,20 +18,89 @@ from .train_step import TrainStep
 
 
 class SyntheticPairs:
-    """Batches shaped and ranged like KAISTPairDataset + DataLoader (irc:1045-1177, :1576-1581)."""
+    """Batches shaped and ranged like KAISTPairDataset + DataLoader (irc:1045-1177, :1576-1581).  Data-parallel: every
+    step draws ONE global batch of world*B pairs from the seed and each rank yields its B-sample slice, so that an N-rank
+    run sees exactly the batches of a single-process run with batch N*B (the property the DP parity tests rely on)."""
 
-    def __init__(self, steps: int, B: int, H: int, W: int, seed: int = 7, with_names: bool = False):
-        self.steps, self.B, self.H, self.W, self.seed = steps, B, H, W, seed
+    sharded = True        # train_kaist must not stride this loader again
+
+    def __init__(self, steps: int, B: int, H: int, W: int, seed: int = 7, rank: int = 0, world: int = 1):
+        self.steps, self.B, self.H, self.W, self.seed, self.rank, self.world = steps, B, H, W, seed, rank, world
 
     def __len__(self):
         return self.steps
 
     def __iter__(self):
         g = torch.Generator().manual_seed(self.seed)
+        B, r = self.B, self.rank
         for i in range(self.steps):
-            ir = torch.rand(self.B, 1, self.H, self.W, generator=g) * 2 - 1
-            rgb = torch.rand(self.B, 3, self.H, self.W, generator=g) * 2 - 1
-            yield {"ir": ir, "rgb": rgb, "name": [f"synthetic_{i:05d}_{j}.png" for j in range(self.B)]}
+            ir = torch.rand(self.world * B, 1, self.H, self.W, generator=g) * 2 - 1
+            rgb = torch.rand(self.world * B, 3, self.H, self.W, generator=g) * 2 - 1
+            yield {"ir": ir[r * B:(r + 1) * B].contiguous(), "rgb": rgb[r * B:(r + 1) * B].contiguous(),
+                   "name": [f"synthetic_{i:05d}_{r * B + j}.png" for j in range(B)]}
+
+
+class _Strided:
+    """rank-strided view of a caller-supplied loader: batch i goes to rank i % world; the tail that does not fill a whole
+    round is dropped so that every rank takes the same number of steps (each step ends in collective calls)"""
+
+    sharded = True
+
+    def __init__(self, loader, rank: int, world: int):
+        self.loader, self.rank, self.world = loader, rank, world
+
+    def __len__(self):
+        return len(self.loader) // self.world
+
+    def __iter__(self):
+        n, pending = len(self), None
+        it = iter(self.loader)
+        for _ in range(n):
+            for r in range(self.world):
+                b = next(it)
+                if r == self.rank:
+                    pending = b
+            yield pending
+
+
+def init_distributed(cfg):
+    """One process per GPU under torchrun: joins the NCCL (CUDA) / gloo (CPU) group from the RANK /
+    WORLD_SIZE / LOCAL_RANK / MASTER_* environment, selects cuda:LOCAL_RANK and returns (rank, world).  A group the caller
+    has already initialised is used as is.  Single process: (0, 1) and nothing is touched."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(), dist.get_world_size()
+    else:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        rank = int(os.environ.get("RANK", "0"))
+        if world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            cuda = str(cfg.device).startswith("cuda")
+            if cuda:
+                local = int(os.environ.get("LOCAL_RANK", str(rank % max(torch.cuda.device_count(), 1))))
+                torch.cuda.set_device(local)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            else:
+                dist.init_process_group("gloo")
+    if world > 1 and str(cfg.device).startswith("cuda"):
+        cfg.device = f"cuda:{torch.cuda.current_device()}"
+    cfg.world_size = world
+    return rank, world
+
+
+def broadcast_state(ts: TrainStep, src: int = 0) -> None:
+    """Replicas must start from identical parameters and optimizer state (each rank draws its own init_weights sample,
+    irc:168-209): rank `src` wins.  Also covers warm starts / resumes loaded on every rank."""
+    import torch.distributed as dist
+    if ts.world == 1:
+        return
+    for a in (ts.G.arena, ts.D2.arena, ts.V.arena):
+        for t in (a.flat, a.m, a.v):
+            dist.broadcast(t, src, group=ts.pg)
+    for opt in (ts.optG, ts.optD):
+        dist.broadcast(opt.step_dev, src, group=ts.pg)
+        opt.t = int(opt.step_dev.item())
+    ts.refresh_weights()
 
 
 def tensor_to_rgb_image(t: torch.Tensor) -> np.ndarray:
@@ -73,7 +142,8 @@ def batch_metrics(fake: torch.Tensor, gt_01: torch.Tensor):
 
 
 def validate_kaist(model: M.IRColorizationModel, val_loader: Iterable[Dict], device) -> float:
-    """irc:1521-1542: sample-weighted mean L1 over the validation loader"""
+    """irc:1521-1542: sample-weighted mean L1 over the validation loader (over all ranks' shards when data-parallel)"""
+    import torch.distributed as dist
     model.eval()
     total, count = 0.0, 0
     be = M.backend()
@@ -85,33 +155,49 @@ def validate_kaist(model: M.IRColorizationModel, val_loader: Iterable[Dict], dev
             be.pixel_loss(fake.contiguous(), rgb.contiguous().float(), 0.0, 0.0, 0.0, sums, None)
             total += sums[0].item() / fake.numel() * ir.size(0)
             count += ir.size(0)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([total, float(count)], dtype=torch.float64, device=device)
+        dist.all_reduce(t)
+        total, count = t[0].item(), int(t[1].item())
     model.train()
     return total / max(count, 1)
 
 
 def train_kaist(cfg: M.Config, train_loader=None, val_loader=None, use_graph: bool = True):
-    """irc:1549-1723 with the fused D+G iteration.  Returns the list of per-epoch (avg_D, avg_G, val_L1)."""
+    """irc:1549-1723 with the fused D+G iteration.  Returns the list of per-epoch (avg_D, avg_G, val_L1).
+
+    Data-parallel when launched by torchrun (one process per GPU): the process group is joined here, rank 0's initial
+    weights are broadcast, the batches are sharded (synthetic: one global batch per step, sliced; caller-supplied loaders:
+    rank-strided), gradients are all-reduced inside the step, the epoch means are averaged over the ranks, and only rank 0
+    prints and writes checkpoints."""
     import torch.distributed as dist
+    rank, world = init_distributed(cfg)
     device = torch.device(cfg.device)
     H = W = cfg.img_size
+    say = print if rank == 0 else (lambda *a, **k: None)
     if train_loader is None:
         if getattr(cfg, "synthetic_steps", 0) <= 0:
             raise RuntimeError("No training data: pass train_loader/val_loader yielding {'ir','rgb'} batches, or set "
                                "cfg.synthetic_steps > 0 (the KAIST file reader, irc:1045-1177, is outside the accelerated path)")
-        train_loader = SyntheticPairs(cfg.synthetic_steps, cfg.batch_size, H, W, seed=7)
-        val_loader = SyntheticPairs(max(1, cfg.synthetic_steps // 10), cfg.batch_size, H, W, seed=8)
-    os.makedirs(cfg.save_dir, exist_ok=True)
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        train_loader = SyntheticPairs(cfg.synthetic_steps, cfg.batch_size, H, W, seed=7, rank=rank, world=world)
+        val_loader = SyntheticPairs(max(1, cfg.synthetic_steps // 10), cfg.batch_size, H, W, seed=8, rank=rank, world=world)
+    elif world > 1:
+        if not getattr(train_loader, "sharded", False):
+            train_loader = _Strided(train_loader, rank, world)
+        if val_loader is not None and not getattr(val_loader, "sharded", False):
+            val_loader = _Strided(val_loader, rank, world)
+    if rank == 0:
+        os.makedirs(cfg.save_dir, exist_ok=True)
 
     model = M.IRColorizationModel(cfg)
     if cfg.init_G_weights is not None and os.path.isfile(cfg.init_G_weights):
-        print(f"Loading initial generator weights from {cfg.init_G_weights}")
+        say(f"Loading initial generator weights from {cfg.init_G_weights}")
         model.load_weights(cfg.init_G_weights)
     netD = M.init_net(M.NLayerDiscriminator(cfg.input_nc + cfg.output_nc, 64, 3, M.get_norm_layer(cfg.norm)), "normal", 0.02, device)
     vgg = M.VGGPerceptual(device)
     lam = dict(L1=cfg.lambda_L1, perc=cfg.lambda_perc, tv=cfg.lambda_tv, ssim=cfg.lambda_ssim, gan=cfg.lambda_gan)
     ts = TrainStep(M.backend(), cfg.batch_size, H, W, device, cfg.lr_G, cfg.lr_D, cfg.beta1, cfg.beta2, lam, world_size=world,
-                   use_graph=use_graph, arenas=(model.netG.arena, netD.arena, vgg.arena))
+                   use_graph=use_graph and device.type == "cuda", arenas=(model.netG.arena, netD.arena, vgg.arena))
     ts.refresh_weights()
     start_epoch = 1
     resume = getattr(cfg, "resume_from", None)          # not in the reference: full-state checkpoints (D + both Adam states + epoch)
@@ -119,42 +205,43 @@ def train_kaist(cfg: M.Config, train_loader=None, val_loader=None, use_graph: bo
         st = torch.load(resume, map_location=device)
         ts.load_state_dict(st)
         start_epoch = int(st.get("epoch", 0)) + 1
-        print(f"Resumed training state from {resume} (epoch {start_epoch - 1})")
+        say(f"Resumed training state from {resume} (epoch {start_epoch - 1})")
+    broadcast_state(ts)
     lr_lambda = M.get_lr_lambda(cfg)
     best_val, best_path = float("inf"), os.path.join(cfg.save_dir, "netG_best.pth")
     history = []
     for epoch in range(start_epoch, cfg.epochs + 1):
         scale = lr_lambda(epoch - 1)
-        sum_g = sum_d = 0.0
-        steps = 0
-        acc = torch.zeros(2, device=device)
+        ts.reset_epoch_sums()
         for i, batch in enumerate(train_loader, start=1):
             ir = batch["ir"].to(device, non_blocking=True); rgb = batch["rgb"].to(device, non_blocking=True)
             ts.step(ir, rgb, lr_scale=scale)
-            steps += 1
             if i % 50 == 0 or i == 1:
-                l = ts.losses()          # the only host synchronisation of the loop
-                print(f"Epoch [{epoch}/{cfg.epochs}] Step [{i}/{len(train_loader)}] D: {l['D']:.4f} | G: {l['G']:.4f} "
-                      f"(GAN {l['GAN']:.4f} + L1 {l['L1']:.4f} + Perc {l['perc']:.4f} + TV {l['TV']:.6f} + SSIM {l['SSIM']:.4f})")
-                sum_g += l["G"]; sum_d += l["D"]
-        logged = max(1, (steps // 50) + 1)
+                l = ts.losses()          # the only host synchronisation of the loop (rank-local values, like a per-rank print)
+                say(f"Epoch [{epoch}/{cfg.epochs}] Step [{i}/{len(train_loader)}] D: {l['D']:.4f} | G: {l['G']:.4f} "
+                    f"(GAN {l['GAN']:.4f} + L1 {l['L1']:.4f} + Perc {l['perc']:.4f} + TV {l['TV']:.6f} + SSIM {l['SSIM']:.4f})")
+        avg_d, avg_g, _ = ts.epoch_means()      # every step of the epoch, accumulated on the device (irc:1683-1697)
         val_l1 = validate_kaist(model, val_loader, device) if val_loader is not None else float("nan")
-        print(f"Epoch [{epoch}/{cfg.epochs}] DONE | avg D: {sum_d / logged:.4f} | avg G: {sum_g / logged:.4f} | val L1: {val_l1:.4f}")
-        history.append((sum_d / logged, sum_g / logged, val_l1))
-        rank0 = (not dist.is_initialized()) or dist.get_rank() == 0
-        if rank0 and ((epoch % cfg.save_every == 0) or (epoch == cfg.epochs)):
+        say(f"Epoch [{epoch}/{cfg.epochs}] DONE | avg D: {avg_d:.4f} | avg G: {avg_g:.4f} | val L1: {val_l1:.4f}")
+        history.append((avg_d, avg_g, val_l1))
+        if rank == 0 and ((epoch % cfg.save_every == 0) or (epoch == cfg.epochs)):
             path = os.path.join(cfg.save_dir, f"netG_epoch_{epoch:03d}.pth")
             torch.save(model.netG.state_dict(), path)
-            print(f"Saved generator checkpoint to {path}")
+            say(f"Saved generator checkpoint to {path}")
             if getattr(cfg, "save_full_state", False):
                 full = ts.state_dict(); full["epoch"] = epoch
                 torch.save(full, os.path.join(cfg.save_dir, "train_state_latest.pth"))
-        if rank0 and val_l1 < best_val:
+        if val_l1 < best_val:
             best_val = val_l1
-            torch.save(model.netG.state_dict(), best_path)
-            print(f"New best model saved to {best_path} (val L1={best_val:.4f})")
-        print(f"Current LR (G): {cfg.lr_G * lr_lambda(epoch):.6e}")
-    print(f"Training finished. Best val L1: {best_val:.4f}, best model: {best_path}")
+            if rank == 0:
+                torch.save(model.netG.state_dict(), best_path)
+            say(f"New best model saved to {best_path} (val L1={best_val:.4f})")
+        say(f"Current LR (G): {cfg.lr_G * lr_lambda(epoch):.6e}")
+    say(f"Training finished. Best val L1: {best_val:.4f}, best model: {best_path}")
+    train_kaist.last_step = ts          # handle for tests / callers that want the final state
+    if ts.graph is not None and world > 1:
+        ts.graph = None                 # a captured graph holding NCCL kernels must go before the communicator does
+        torch.cuda.synchronize()
     return history
 
 
@@ -180,10 +267,37 @@ def summarize_rows(rows: List[Dict]) -> Optional[Dict]:
                 mean_psnr=sum(r["psnr"] for r in rows if np.isfinite(r["psnr"])) / count)
 
 
+def write_topk_ranking(cfg: M.Config, rows: List[Dict]) -> Optional[str]:
+    """The ranking CSV of save_best_k_outputs (irc:1236-1278): rows sorted by SSIM when any was computed, else by PSNR,
+    descending (stable, like list.sort), top `cfg.topk`, same columns and number formats.  The file copies of
+    irc:1280-1330 belong to the image-file layer that is outside the accelerated path."""
+    if not rows:
+        print("[TOP-K] metrics_list empty, skipping top-K save.")
+        return None
+    key = "ssim" if any(r.get("ssim") is not None for r in rows) else "psnr"
+    valid = [r for r in rows if r.get(key) is not None and np.isfinite(r[key])]
+    if not valid:
+        print(f"[TOP-K] No valid '{key}' values, skipping top-K save.")
+        return None
+    valid.sort(key=lambda r: r[key], reverse=True)
+    top = valid[:max(1, int(cfg.topk))]
+    best_dir = os.path.join(cfg.output_dir, cfg.best50_dirname)
+    os.makedirs(best_dir, exist_ok=True)
+    path = os.path.join(best_dir, f"top_{len(top)}_ranking.csv")
+    with open(path, "w", encoding="utf-8") as f:
+        f.write("rank,file,mae,mse,psnr,ssim,metric_used\n")
+        for i, m in enumerate(top, start=1):
+            ssim_str = "" if m.get("ssim") is None else f"{m['ssim']:.6f}"
+            f.write(f"{i},{m['file']},{m['mae']:.8f},{m['mse']:.8f},{m['psnr']:.6f},{ssim_str},{key}\n")
+    print(f"[TOP-K] Ranking file   : {path}")
+    return path
+
+
 def run_test(cfg: M.Config, loader=None):
     """Test-mode core of irc:1333-1514: batched generator inference, on-device truncating quantisation and
     MAE/MSE/PSNR per image, `metrics_test.csv` in the reference's format.  Image files, collages and the top-K
     copies (irc:945-1038, :1220-1330) are outside the accelerated path."""
+    rank, world = init_distributed(cfg)
     device = torch.device(cfg.device)
     H = W = cfg.img_size
     if loader is None:
@@ -199,9 +313,6 @@ def run_test(cfg: M.Config, loader=None):
     else:
         print(f"Warning: generator weights not found at {cfg.test_G_weights}. Using randomly initialized model.")
     model.eval()
-    import torch.distributed as dist
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank() if world > 1 else 0
     rows: List[Dict] = []
     preds = []
     with torch.no_grad():
@@ -231,6 +342,10 @@ def run_test(cfg: M.Config, loader=None):
         print(f"Mean MSE   : {mean_mse:.6f}")
         print(f"Mean PSNR  : {mean_psnr:.4f} dB")
         print("Mean SSIM  : None (scikit-image not installed)")
+        finite = [r for r in rows if np.isfinite(r["psnr"])]
+        best = max(finite, key=lambda r: r["psnr"]) if finite else None        # first maximum, like the running `>` of irc:1437-1439
+        print(f"Best PSNR  : {best['psnr']:.4f} ({best['file']})" if best else "Best PSNR  : N/A")
+        print("Best SSIM  : N/A")
         path = os.path.join(cfg.output_dir, "metrics_test.csv")
         with open(path, "w", encoding="utf-8") as f:
             f.write("file,mae,mse,psnr,ssim\n")
@@ -239,6 +354,7 @@ def run_test(cfg: M.Config, loader=None):
             f.write("\n# Summary\n")
             f.write(f"# count,{count}\n# mean_mae,{mean_mae:.8f}\n# mean_mse,{mean_mse:.8f}\n# mean_psnr,{mean_psnr:.6f}\n# mean_ssim,\n")
         print(f"\nMetrics saved to: {path}")
+        write_topk_ranking(cfg, rows)
     elif summary is None:
         print("No metrics were computed (no matching GT RGB images found).")
     return summary, rows, preds

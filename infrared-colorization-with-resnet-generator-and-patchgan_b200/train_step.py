@@ -28,20 +28,29 @@ def gaussian_window(n: int = 11, sigma: float = 1.5) -> torch.Tensor:
 
 
 class AdamHyper:
-    """Host side of the fused Adam: step count, lr schedule factor, bias corrections (torch.optim.Adam
-    defaults of irc:1601-1604) staged into a 7-float device vector read by irc_adam."""
+    """Host side of the fused Adam (torch.optim.Adam defaults of irc:1601-1604).  The step counter lives on the DEVICE
+    (`step_dev`, advanced by irc_adam itself), so a replayed CUDA graph needs no per-step host write; only the LambdaLR
+    factor and the 1/world_size gradient scale travel from the host, and only when they change (per epoch), through a
+    pageable staging tensor (the copy is staged by the driver before the call returns: the host cannot overwrite a buffer
+    that an earlier, still queued copy has yet to read).  `t` mirrors the device counter on the host."""
 
     def __init__(self, device, lr: float, beta1: float, beta2: float, eps: float = 1e-8):
         self.lr, self.b1, self.b2, self.eps, self.t = lr, beta1, beta2, eps, 0
-        self.dev = torch.zeros(8, device=device)
-        self.host = torch.zeros(8).pin_memory() if torch.device(device).type == "cuda" else torch.zeros(8)
+        self.dev = torch.zeros(8, device=device, dtype=torch.float64)       # {lr, b1, b2, eps, lr_scale, grad_scale}
+        self.step_dev = torch.zeros(1, device=device, dtype=torch.int64)
+        self._staged = None
 
     def advance(self, lr_scale: float, grad_scale: float) -> None:
+        """call once per optimizer step, before the step is enqueued"""
         self.t += 1
-        h = self.host
-        h[0] = self.lr * lr_scale; h[1] = self.b1; h[2] = self.b2; h[3] = self.eps
-        h[4] = 1.0 - self.b1 ** self.t; h[5] = 1.0 - self.b2 ** self.t; h[6] = grad_scale
-        self.dev.copy_(h, non_blocking=True)
+        want = (self.lr, self.b1, self.b2, self.eps, float(lr_scale), float(grad_scale))
+        if want != self._staged:
+            self.dev.copy_(torch.tensor(want + (0.0, 0.0), dtype=torch.float64))
+            self._staged = want
+
+    def set_step(self, t: int) -> None:
+        self.t = int(t)
+        self.step_dev.fill_(self.t)
 
 
 class TrainStep:
@@ -61,6 +70,10 @@ class TrainStep:
         self.optD = AdamHyper(device, lr_D, beta1, beta2)
         self.window = gaussian_window()
         self.sums = torch.zeros(8 + B, device=device)
+        # running sums of the D and G losses over the steps since reset_epoch_sums(): the reference averages EVERY step of an
+        # epoch (irc:1683-1697); accumulating on the device keeps the loop free of per-step host synchronisation
+        self.acc = torch.zeros(4, device=device, dtype=torch.float64)          # {sum D, sum G, steps, -}
+        self.coef = self._loss_coefficients().to(device)
         self.dfake = torch.zeros(B, 3, H, W, device=device)
         self.ga, self.gb, self.gc = (torch.zeros(B, 3, H, W, device=device) for _ in range(3))
         self.ir = torch.zeros(B, 1, H, W, device=device)
@@ -71,6 +84,37 @@ class TrainStep:
         self.graph = None
         self._side = None
         self.n_pred = self.D1.pred[0].numel()
+
+    def _loss_coefficients(self) -> torch.Tensor:
+        """D and G losses are affine in the raw sums of one iteration: row j = (coefficients of sums[0:8+B], constant).
+        Third row counts the steps."""
+        B, H, W, lam = self.B, self.H, self.W, self.lam
+        n = 8 + B
+        cnt = B * self.D1.pred[0].numel()
+        npix = B * 3 * H * W
+        c = torch.zeros(3, n + 1, dtype=torch.float32)
+        c[0, 0] = c[0, 1] = 0.5 / cnt                                      # irc:1647-1649
+        c[1, 2] = -lam["gan"] / cnt                                        # irc:1662, :1679
+        c[1, 3] = lam["L1"] / npix                                         # irc:1664
+        c[1, 4] = lam["tv"] / (B * 3 * (H - 1) * W); c[1, 5] = lam["tv"] / (B * 3 * H * (W - 1))     # irc:686-694
+        c[1, 6] = lam["perc"] / (B * 256 * (H // 4) * (W // 4))            # irc:1669
+        c[1, 8:8 + B] = -lam["ssim"] / npix; c[1, n] = lam["ssim"]         # irc:1675-1677
+        c[2, n] = 1.0
+        return c.contiguous()
+
+    def reset_epoch_sums(self) -> None:
+        self.acc.zero_()
+
+    def epoch_means(self):
+        """(mean D loss, mean G loss, steps) over the iterations since reset_epoch_sums(), averaged over the ranks
+        (irc:1683-1697).  Synchronises."""
+        acc = self.acc.clone()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(acc, group=self.pg)
+        a = acc.tolist()
+        steps = max(a[2], 1.0)
+        return a[0] / steps, a[1] / steps, int(round(a[2] / self.world))
 
     # ------------------------------------------------------------------ parameters
     def load(self, pG: Dict[str, torch.Tensor], pD: Dict[str, torch.Tensor], pV: Dict[str, torch.Tensor]) -> None:
@@ -102,7 +146,7 @@ class TrainStep:
             if st["exp_avg"].numel() != arena.m.numel():
                 raise ValueError(f"{name}: optimizer state of {st['exp_avg'].numel()} elements does not fit the arena ({arena.m.numel()})")
             arena.m.copy_(st["exp_avg"]); arena.v.copy_(st["exp_avg_sq"])
-            opt.t = int(st["step"]); opt.lr = float(st["lr"]); opt.b1, opt.b2 = (float(b) for b in st["betas"]); opt.eps = float(st["eps"])
+            opt.set_step(int(st["step"])); opt._staged = None; opt.lr = float(st["lr"]); opt.b1, opt.b2 = (float(b) for b in st["betas"]); opt.eps = float(st["eps"])
         self.refresh_weights()
 
     # ------------------------------------------------------------------ the iteration
@@ -143,7 +187,7 @@ class TrainStep:
         # ---------------- D optimizer step, then the adversarial term with the updated D (irc:1651, :1659-1662)
         self._wait(wD)
         A = self.D2.arena
-        be.adam(A.flat, A.grad, A.m, A.v, self.optD.dev)                       # irc:1651
+        be.adam(A.flat, A.grad, A.m, A.v, self.optD.dev, self.optD.step_dev)                       # irc:1651
         self.D2.refresh_weights()
         pred_f = self.D1.forward(ir, fake)                                     # irc:1659
         be.hinge(pred_f, 0, 1, lam["gan"] / cnt, 0.0, self.sums[0:3], self.D1.dpred)   # irc:1662, :1679
@@ -156,8 +200,9 @@ class TrainStep:
         self.G.backward(self.dfake, after_blocks=lambda: works.append(self._allreduce_async(A.grad[split:])))
         works.append(self._allreduce_async(A.grad[:split]))
         self._wait(*works)
-        be.adam(A.flat, A.grad, A.m, A.v, self.optG.dev)                       # irc:1681
+        be.adam(A.flat, A.grad, A.m, A.v, self.optG.dev, self.optG.step_dev)                       # irc:1681
         self.G.refresh_weights()
+        be.accumulate(self.sums, self.coef, self.acc)                          # irc:1683-1685
 
     def step(self, ir: torch.Tensor, rgb: torch.Tensor, lr_scale: float = 1.0) -> None:
         """One iteration on a device-resident batch (fp32 NCHW in [-1,1])."""
@@ -170,13 +215,14 @@ class TrainStep:
         if self.graph is None:
             # warm-up on a side stream (sets kernel attributes, primes allocators), undo its effect on
             # the optimizer state, then capture
-            snap = [t.clone() for a in (self.G.arena, self.D2.arena) for t in (a.flat, a.m, a.v)]
+            state = [t for a in (self.G.arena, self.D2.arena) for t in (a.flat, a.m, a.v)] + [self.optG.step_dev, self.optD.step_dev, self.acc]
+            snap = [t.clone() for t in state]
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 self._body()
             torch.cuda.current_stream().wait_stream(s)
-            for t, c in zip([t for a in (self.G.arena, self.D2.arena) for t in (a.flat, a.m, a.v)], snap):
+            for t, c in zip(state, snap):
                 t.copy_(c)
             self.refresh_weights()
             torch.cuda.synchronize()

@@ -396,9 +396,17 @@ class RefBackend:
             sums.copy_(torch.stack([d.abs().double().sum((1, 2, 3)), (d * d).double().sum((1, 2, 3))], -1))
 
     # ------------------------------------------------------------------ optimizer / layout
-    def adam(self, p, g, m, v, hyper):
+    def accumulate(self, sums, coef, acc):
         self.launches += 1
-        lr, b1, b2, eps, bc1, bc2, gs = [float(t) for t in hyper.tolist()[:7]]
+        n = sums.numel()
+        acc[:coef.shape[0]] += coef[:, :n].double() @ sums.double() + coef[:, n].double()
+
+    def adam(self, p, g, m, v, hyper, step_dev):
+        self.launches += 1
+        lr, b1, b2, eps, lrs, gs = [float(t) for t in hyper.tolist()[:6]]
+        step_dev += 1
+        t = int(step_dev.item())
+        lr, bc1, bc2 = lr * lrs, 1.0 - b1 ** t, 1.0 - b2 ** t
         gg = g * gs
         m.mul_(b1).add_(gg, alpha=1 - b1)
         v.mul_(b2).addcmul_(gg, gg, value=1 - b2)

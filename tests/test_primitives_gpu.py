@@ -440,19 +440,22 @@ def test_adam_pack_gather(bes):
     n = 10007
     p0 = torch.randn(n, device="cuda", generator=g); gr = torch.randn(n, device="cuda", generator=g) * 1e-3
     m0 = torch.randn(n, device="cuda", generator=g) * 1e-3; v0 = torch.rand(n, device="cuda", generator=g) * 1e-6
-    hyper = torch.tensor([2e-4, 0.5, 0.999, 1e-8, 1 - 0.5 ** 3, 1 - 0.999 ** 3, 0.5, 0.0], device="cuda")
-    a, b = both(bes, lambda be, p, m, v: be.adam(p, gr, m, v, hyper), [p0, m0, v0])
-    for x, y in zip(a, b):
+    hyper = torch.tensor([2e-4, 0.5, 0.999, 1e-8, 0.7, 0.5, 0.0, 0.0], device="cuda", dtype=torch.float64)
+    a, b = both(bes, lambda be, p, m, v, t: be.adam(p, gr, m, v, hyper, t), [p0, m0, v0, torch.full((1,), 2, device="cuda", dtype=torch.int64)])
+    for x, y in zip(a[:3], b[:3]):
         close(x, y, 2e-6, "adam")
+    assert int(a[3].item()) == 3 and int(b[3].item()) == 3          # the device step counter advances inside the call
     # torch.optim.Adam itself
     pt = p0.clone().requires_grad_(True)
     opt = torch.optim.Adam([pt], lr=2e-4, betas=(0.5, 0.999))
     for _ in range(3):
         pt.grad = gr.clone(); opt.step()
     pc, mc, vc = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
-    for t in (1, 2, 3):
-        h = torch.tensor([2e-4, 0.5, 0.999, 1e-8, 1 - 0.5 ** t, 1 - 0.999 ** t, 1.0, 0.0], device="cuda")
-        bes[0].adam(pc, gr, mc, vc, h)
+    h = torch.tensor([2e-4, 0.5, 0.999, 1e-8, 1.0, 1.0, 0.0, 0.0], device="cuda", dtype=torch.float64)
+    tdev = torch.zeros(1, device="cuda", dtype=torch.int64)
+    for _ in range(3):
+        bes[0].adam(pc, gr, mc, vc, h, tdev)          # back to back, no host involvement between the steps
+    assert int(tdev.item()) == 3
     close(pc, pt.detach(), 1e-6, "adam vs torch.optim.Adam")
     src = torch.randn(5000, device="cuda", generator=g)
     mp = torch.randint(-1, 5000, (7777,), device="cuda", generator=g, dtype=torch.int32)
