@@ -20,7 +20,6 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-METRIC = "gan_train_img_per_s_256x256_b16_per_gpu"
 UNIT = "img/s"
 GFLOP_PER_SAMPLE = 533.9          # minimal result-preserving conv work of one train step at 256^2
 
@@ -95,29 +94,78 @@ def oracle_step_time(B, H, W, steps, threads):
     return ts
 
 
+WORKLOAD = ("single GAN train step (G+D, hinge+L1+VGG+TV+SSIM losses) at {H}x{W} batch {B} per GPU "
+            "(BASELINE.json configs[1]; configs[2] when n_gpus > 1)")
+
+
+def bench_config(args, world):
+    """identical in both arms: what is measured, not how"""
+    H, W = args.size
+    return dict(workload=WORKLOAD.format(H=H, W=W, B=args.batch), global_batch=args.batch * world, parallelism=f"dp{world}")
+
+
+def metric_name(args):
+    H, W = args.size
+    return f"gan_train_img_per_s_{H}x{W}_b{args.batch}_per_gpu"
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's algorithm (oracle port; the reference itself is a Python script that
-    cannot travel to the GPU box) on all host cores, bounded sample B=2 per step."""
+    """--impl reference: the reference's algorithm (oracle port; the reference itself is a Python script that cannot
+    travel to the GPU box) on all host cores.  EXACTLY --warmup + --steps steps are run; each step is a bounded sample of
+    the workload (batch 2 instead of 16 - img/s is per image, and oneDNN's per-image cost does not fall with the batch), so
+    that the default 5 + 20 steps end within a few minutes."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     Bs = 2
-    steps = max(1, min(args.steps, 3))
-    warm = 1 if args.warmup > 0 else 0
-    ts = oracle_step_time(Bs, 256, 256, warm + steps, cores)[warm:]
+    H, W = args.size
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    ts = oracle_step_time(Bs, H, W, warm + steps, cores)[warm:]
     sec = sum(ts) / len(ts)
     val = Bs / sec
-    line = dict(impl="reference", metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warm,
+    line = dict(impl="reference", metric=metric_name(args), value=val, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warm,
                 ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="single GAN train step (G+D, hinge+L1+VGG+TV+SSIM losses) at 256x256 batch 16 per GPU "
-                                     "(BASELINE.json configs[1]; configs[2] when n_gpus > 1)",
-                            global_batch=16 * args.gpus, parallelism=f"dp{args.gpus}", cuda_graph=False,
-                            sample=f"reference algorithm on the host CPU, batch {Bs} per step instead of 16 (img/s is per image)", l2="n/a (CPU)"),
+                config=bench_config(args, args.gpus),
                 cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port",
-                                  sample=f"{steps} step(s) of batch {Bs} at 256x256, torch CPU fp32, {cores} threads"),
+                                  sample=f"{steps} step(s) (after {warm} warm-up) of batch {Bs} at {H}x{W}: the reference algorithm "
+                                         f"(oracle/irc_oracle.py) on torch CPU fp32, {cores} threads; img/s is per image"),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                iters_per_s=1.0 / sec, gpu_launches=0)
+                iters_per_s_at_sample_batch=1.0 / sec, gpu_launches=0)
     print(json.dumps(line), flush=True)
+
+
+def eager_gpu_baseline(B, H, W, dev, steps=5, warm=2):
+    """the stated kernel to beat: the reference's own op sequence in PyTorch eager + cuDNN on this
+    GPU (oracle/eager_baseline.py), fp32 storage with the default TF32 convolutions, and bf16 autocast + channels_last"""
+    import torch
+    import irc_oracle as O
+    import eager_baseline as EB
+    pG = O.seeded_params(O.generator_shapes(), 1234); pD = O.seeded_params(O.discriminator_shapes(), 1235)
+    pV = O.seeded_params(O.vgg_shapes(), 1236, kaiming=True)
+    ir, rgb = O.synthetic_pair(B, H, W)
+    ir, rgb = ir.to(dev), rgb.to(dev)
+    out = {}
+    for name, kw in (("tf32", dict()), ("bf16_autocast_channels_last", dict(channels_last=True, autocast=torch.bfloat16))):
+        try:
+            tr = EB.EagerTrainer(pG, pD, pV, dev, **kw)
+            for _ in range(warm):
+                tr.step(ir, rgb)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                tr.step(ir, rgb)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = dict(ms_per_step=ms, img_per_s=B / (ms * 1e-3), steps=steps, warmup=warm)
+            del tr
+            torch.cuda.empty_cache()
+        except Exception as ex:      # an out-of-memory eager baseline must not take the bench line with it
+            out[name] = dict(error=str(ex)[:200])
+            torch.cuda.empty_cache()
+    out["note"] = ("PyTorch eager + cuDNN on the same GPU, the reference's op sequence as written (two generator forwards, D gradients also in "
+                   "the G step): cudnn.allow_tf32 default (True) for 'tf32'; device-resident inputs, CUDA events")
+    return out
 
 
 def main():
@@ -130,6 +178,8 @@ def main():
     ap.add_argument("--size", type=int, nargs=2, default=[256, 256], metavar=("H", "W"))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip timing the PyTorch eager + cuDNN restatement on the GPU")
+    ap.add_argument("--skip", default="", help="timing ablation (results become wrong): comma-separated backend launchers turned into no-ops")
     ap.add_argument("--breakdown-all", default=None, help="write a per-launcher CUDA-event table of one eager step (all kernels) to this file")
     ap.add_argument("--breakdown", default=None, help="write the per-launch GEMM timing table to this file")
     args = ap.parse_args()
@@ -163,6 +213,9 @@ def main():
     W_, K = max(args.warmup, 3), args.steps
 
     be = CudaBackend()
+    for name in filter(None, args.skip.split(",")):
+        assert hasattr(be, name), name
+        setattr(be, name, lambda *a, **k: None)
     ts = TrainStep(be, B, H, W, dev, world_size=world, use_graph=(not args.no_graph))
     ts.load(O.seeded_params(O.generator_shapes(), 1234), O.seeded_params(O.discriminator_shapes(), 1235),
             O.seeded_params(O.vgg_shapes(), 1236, kaiming=True))
@@ -211,20 +264,24 @@ def main():
 
     # ---- roofline of the dominant kernel: every tensor-core GEMM launch of one eager step bracketed by CUDA events
     pk = peaks()
-    eager = ts if not ts.use_graph else None
-    if eager is None:
-        ts.use_graph = False
+    ts.use_graph = False
     ts.step(ir_d, rgb_d)
     be.timers = []
     ts.step(ir_d, rgb_d)
     torch.cuda.synchronize()
     rows = [(kind, name, role, fl, e0.elapsed_time(e1)) for (kind, name, role, fl, e0, e1) in be.timers]
     be.timers = None
-    conv = [r for r in rows if r[0] == "conv_gemm" and r[3] > 0]
-    tn = [r for r in rows if r[0] == "tn_gemm" and r[3] > 0]
-    conv_tf = sum(r[3] for r in conv) / (sum(r[4] for r in conv) * 1e-3) / 1e12
-    tn_tf = sum(r[3] for r in tn) / (sum(r[4] for r in tn) * 1e-3) / 1e12
-    gemm_ms = sum(r[4] for r in conv) + sum(r[4] for r in tn)
+    # SURVEY.md §8d classes: tensor-bound = every dense contraction (G down1/down2/resblocks/up1/up2, D model.2/5/8, VGG
+    # conv1_2..conv3_3, in all three roles); the degenerate shapes (inc K=49, outc N=3, D model.0 K=64 / model.11 N=1, VGG
+    # conv1_1 K=27) are HBM-bound layout passes and are reported against the HBM roofline instead
+    DEGENERATE = {"G.inc", "G.outc", "D.0", "D.11", "V.0"}
+    conv_all = [r for r in rows if r[0] == "conv_gemm" and r[3] > 0]
+    conv = [r for r in conv_all if r[1] not in DEGENERATE]
+    tn = [r for r in rows if r[0] == "tn_gemm" and r[3] > 0 and r[1] not in DEGENERATE]
+    degen = [r for r in rows if r[1] in DEGENERATE]
+    tfl = lambda rs: (sum(r[3] for r in rs) / (sum(r[4] for r in rs) * 1e-3) / 1e12) if rs else 0.0
+    conv_tf, tn_tf, conv_all_tf = tfl(conv), tfl(tn), tfl(conv_all)
+    gemm_ms = sum(r[4] for r in rows if r[0] in ("conv_gemm", "tn_gemm"))
     if args.breakdown and rank == 0:
         agg = {}
         for kind, name, role, fl, t in rows:
@@ -233,6 +290,8 @@ def main():
             f.write("kernel,layer,role,launches,gflop_per_launch,ms_per_launch,tflops,frac_of_peak\n")
             for (kind, name, role), (n, fl, t) in sorted(agg.items(), key=lambda kv: -kv[1][2]):
                 f.write(f"{kind},{name},{role},{n},{fl / n / 1e9:.2f},{t / n:.4f},{fl / (t * 1e-3) / 1e12:.1f},{fl / (t * 1e-3) / 1e12 / pk['tf']:.3f}\n")
+
+    graph_used = not args.no_graph
 
     def shutdown():
         # a captured graph that contains NCCL kernels must be released before the communicator goes away
@@ -287,48 +346,66 @@ def main():
         dom = dict(kernel="conv_gemm_kernel, ResNet-block shape (M=B*H/4*W/4, N=256, K=2304): 18 of the 80 conv launches, same shape as the "
                           "18 data-gradient launches", launches=n, gflop_per_launch=fl / 1e9, us_per_launch=t / n * 1e3,
                    achieved=fl / (t / n * 1e-3) / 1e12, peak=pk["tf"], unit="TFLOP/s", frac=fl / (t / n * 1e-3) / 1e12 / pk["tf"],
-                   traffic=38.09e6 if (B, H, W) == (16, 256, 256) else None,
-                   traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of this launch, profiles/ncu_full_gemm_r1_final_raw.csv "
-                                  "(algorithmic: 35.7 MB operand frame + 1.2 MB weights read; the 35.7 MB output stays in L2)")
+                   traffic=None,
+                   traffic_note="not measured in this run (DRAM counters need ncu): see profiles/ for the ncu --set full capture of this shape")
 
     if rank != 0:
         shutdown()
         return
 
+    d2h_bytes = ts.sums.numel() * 4
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        t = oracle_step_time(2, H, W, 2, cores)[1:]
-        cpu_baseline = dict(value=2 / (sum(t) / len(t)), unit=UNIT, cores=cores, kind="port",
-                            sample=f"1 timed step (after 1 warm-up) of batch 2 at {H}x{W}, oracle/irc_oracle.py, torch CPU fp32")
+        oracle_step_time(2, H, W, 1, cores)                      # warm-up (oneDNN primitive caches)
+        t = oracle_step_time(B, H, W, 1, cores)
+        cpu_baseline = dict(value=B / t[0], unit=UNIT, cores=cores, kind="port",
+                            sample=f"1 step of the full batch {B} at {H}x{W} (after a batch-2 warm-up step), oracle/irc_oracle.py, torch CPU fp32, "
+                                   f"{cores} threads: {t[0]:.1f} s")
+    eager = None
+    if world == 1 and not args.no_eager_baseline:
+        # release this repo's ~6 GB of frames first: the eager autograd graph of a batch-16 step needs tens of GB
+        ts.graph = None
+        ts.G = ts.D1 = ts.D2 = ts.V = None
+        be._pending, be._sum_tables = [], {}
+        torch.cuda.synchronize(); torch.cuda.empty_cache()
+        eager = eager_gpu_baseline(B, H, W, dev)
 
     sec = ms * 1e-3 / K
     value = world * B / sec
     step_tflop = GFLOP_PER_SAMPLE * B * (H * W) / (256 * 256) / 1e3
+    if eager:
+        for k in ("tf32", "bf16_autocast_channels_last"):
+            if "ms_per_step" in eager.get(k, {}):
+                eager[k]["speedup_of_this_repo"] = eager[k]["ms_per_step"] / (sec * 1e3)
     line = dict(
-        metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W_, ms_per_step=sec * 1e3, higher_is_better=True,
+        metric=metric_name(args), value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W_, ms_per_step=sec * 1e3, higher_is_better=True,
         scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-        config=dict(workload=f"single GAN train step (G+D, hinge+L1+VGG+TV+SSIM losses) at {H}x{W} batch {B} per GPU "
-                             "(BASELINE.json configs[1]; configs[2] when n_gpus > 1)",
-                    global_batch=world * B, parallelism=f"dp{world}", cuda_graph=bool(ts.graph is not None),
+        config=bench_config(args, world),
+        timing=dict(cuda_graph=bool(graph_used), events="CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks",
                     l2="per-step working set (several GB of activations) exceeds the 126 MB L2; no explicit flush"),
         iters_per_s=1.0 / sec, step_tflop_algorithmic=step_tflop, step_tensor_frac=step_tflop / sec / pk["tf"],
         e2e=dict(value=world * B / (ms_e2e * 1e-3 / K), unit=UNIT, h2d_bytes_per_step=ir_h.numel() * 4 + rgb_h.numel() * 4,
-                 d2h_bytes_per_step=ts.sums.numel() * 4),
+                 d2h_bytes_per_step=d2h_bytes),
         gpu_launches=launches_per_step * K,
         clocks=clocks,
-        roofline=dict(bound="tensor", kernel="conv_gemm_kernel (all forward + data-gradient convolutions of one step)",
+        roofline=dict(bound="tensor", kernel="conv_gemm_kernel: every forward + data-gradient launch of the tensor-bound layers (SURVEY.md §8d classes)",
                       achieved=conv_tf, peak=pk["tf"], unit="TFLOP/s", frac=conv_tf / pk["tf"],
-                      traffic=(dom or {}).get("traffic"), traffic_note="per launch of the ResNet-block shape, see roofline_dominant_launch",
+                      traffic=None, traffic_note="DRAM bytes are not observable from inside the run; ncu --set full captures are under profiles/",
                       peak_source=pk["src"] + " bf16_tflops_sustained", launches_per_step=len(conv),
-                      share_of_step=sum(r[4] for r in conv) / (sec * 1e3)),
-        roofline_wgrad=dict(bound="tensor", kernel="tn_gemm_kernel (all weight gradients of one step)", achieved=tn_tf, peak=pk["tf"],
+                      share_of_step=sum(r[4] for r in conv) / (sec * 1e3),
+                      all_conv_gemm_launches=dict(achieved=conv_all_tf, frac=conv_all_tf / pk["tf"], launches_per_step=len(conv_all),
+                                                  note="same figure as round 1: includes the degenerate (HBM-bound) one-tap GEMMs")),
+        roofline_wgrad=dict(bound="tensor", kernel="tn_gemm_kernel (weight gradients of the tensor-bound layers)", achieved=tn_tf, peak=pk["tf"],
                             unit="TFLOP/s", frac=tn_tf / pk["tf"], launches_per_step=len(tn), share_of_step=sum(r[4] for r in tn) / (sec * 1e3)),
+        degenerate_convs=dict(layers=sorted(DEGENERATE), launches_per_step=len(degen), ms_per_step=sum(r[4] for r in degen),
+                              note="HBM-bound by construction (K or N of a few units); GEMM launches only - their layout passes are in hbm_kernels"),
         roofline_dominant_launch=dom,
         hbm_kernels=hbm_kernels,
         hbm_peak_gb_s=pk["hbm"],
         gemm_ms_per_step=gemm_ms,
         cpu_baseline=cpu_baseline,
+        gpu_eager_baseline=eager,
         losses={k: round(v, 5) for k, v in losses.items()},
     )
     sys.stdout.flush()

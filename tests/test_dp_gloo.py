@@ -112,3 +112,82 @@ def test_sharded_test_mode_metrics_merge_to_the_single_process_summary(tmp_path)
     want = summarize_rows(ref)
     for k in want:
         assert abs(r["summary"][k] - want[k]) < 1e-12, k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# data parallelism through the PRODUCT entry point (train_kaist), as torchrun would launch it
+# ---------------------------------------------------------------------------------------------------------------
+def _train_cfg(tmp, steps=3, batch=1):
+    import irc_b200 as R
+    cfg = R.Config()
+    cfg.mode, cfg.device, cfg.img_size, cfg.batch_size, cfg.epochs, cfg.synthetic_steps = "train", "cpu", 32, batch, 1, steps
+    cfg.save_dir = os.path.join(tmp, "ckpt"); cfg.output_dir = os.path.join(tmp, "out")
+    return cfg
+
+
+def _kaist_worker(rank, world, port, tmp):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    # exactly the environment torchrun provides; train_kaist joins the group itself
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(2)
+    import irc_b200 as R
+    from irc_b200 import layout as L, modules as M
+    from irc_b200.train import train_kaist
+    from ref_backend import RefBackend
+    L.ACT_DTYPE = torch.float32
+    M.set_backend(RefBackend())
+    torch.manual_seed(100 + rank)            # every rank draws DIFFERENT initial weights: the broadcast must fix that
+    cfg = _train_cfg(os.path.join(tmp, f"r{rank}"))
+    hist = train_kaist(cfg, use_graph=False)
+    ts = train_kaist.last_step
+    assert dist.is_initialized() and dist.get_world_size() == world and cfg.world_size == world
+    flats = [ts.G.arena.flat, ts.D2.arena.flat, ts.G.arena.m, ts.D2.arena.v]
+    same = True
+    for f in flats:
+        parts = [torch.zeros_like(f) for _ in range(world)]
+        dist.all_gather(parts, f.clone())
+        same = same and all(torch.equal(parts[0], q) for q in parts)
+    wrote = os.path.isdir(cfg.save_dir) and any(n.endswith(".pth") for n in os.listdir(cfg.save_dir))
+    torch.save(dict(same=same, hist=hist, flatG=ts.G.arena.flat.clone(), flatD=ts.D2.arena.flat.clone(), wrote=wrote, steps=ts.optG.t,
+                    step_dev=int(ts.optG.step_dev.item())), os.path.join(tmp, f"res{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_train_kaist_data_parallel_equals_single_process_on_the_global_batch(tmp_path):
+    """2 ranks x batch 1 through train_kaist (process group joined from the torchrun environment, rank-0 weights broadcast,
+    one global synthetic batch per step sliced across the ranks) == 1 process x batch 2 from rank 0's initial weights"""
+    tmp = str(tmp_path)
+    mp.spawn(_kaist_worker, args=(2, _free_port(), tmp), nprocs=2, join=True)
+    r0, r1 = torch.load(os.path.join(tmp, "res0.pt")), torch.load(os.path.join(tmp, "res1.pt"))
+    assert r0["same"] and r1["same"], "replicas diverged"
+    assert r0["wrote"] and not r1["wrote"], "only rank 0 writes checkpoints"
+    assert r0["steps"] == 3 and r0["step_dev"] == 3
+    assert r0["hist"] == r1["hist"]                       # epoch means are all-reduced
+    # single process, batch 2, same initial weights as rank 0
+    sys.path.insert(0, ROOT)
+    import irc_b200 as R
+    from irc_b200 import layout as L, modules as M
+    from irc_b200.train import train_kaist
+    from ref_backend import RefBackend
+    old, oldbe = L.ACT_DTYPE, M._BACKEND
+    L.ACT_DTYPE = torch.float32
+    M.set_backend(RefBackend())
+    try:
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            os.environ.pop(k, None)
+        torch.manual_seed(100)
+        cfg = _train_cfg(os.path.join(tmp, "single"), batch=2)
+        hist = train_kaist(cfg, use_graph=False)
+        ts = train_kaist.last_step
+    finally:
+        L.ACT_DTYPE = old
+        M.set_backend(oldbe)
+    # three Adam steps of size lr = 2e-4: identical up to elements whose gradient sign is numerically fragile
+    dG = (ts.G.arena.flat - r0["flatG"]).abs(); dD = (ts.D2.arena.flat - r0["flatD"]).abs()
+    assert (dG > 1e-4).float().mean() < 2e-3 and (dD > 1e-4).float().mean() < 2e-3, ((dG > 1e-4).float().mean(), (dD > 1e-4).float().mean())
+    for a, b in zip(hist[0], r0["hist"][0]):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (hist, r0["hist"])

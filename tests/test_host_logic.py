@@ -196,3 +196,52 @@ def test_stream_window_classifies_the_stencil_tables():
         assert fold.stream_window() == 0
         # identity along one axis: not a streaming case
         assert L.make_tables(L.down_matrix(n), None, "cpu").stream_window() == 0
+
+
+def test_epoch_means_average_every_step_and_adam_counter_lives_on_the_device(fp32_frames):
+    """irc:1683-1697 averages the D and G losses of EVERY iteration; the step accumulates them on the device.  The Adam
+    step counter is a device tensor advanced by the optimizer launch itself (no per-step host write)."""
+    from irc_b200.train_step import TrainStep
+    pG = O.seeded_params(O.generator_shapes(), 1234, bias_std=0.02)
+    pD = O.seeded_params(O.discriminator_shapes(), 1235, bias_std=0.02)
+    pV = O.seeded_params(O.vgg_shapes(), 1236, kaiming=True, bias_std=0.05)
+    ts = TrainStep(fp32_frames, 1, H, W, "cpu")
+    ts.load(pG, pD, pV)
+    ts.reset_epoch_sums()
+    ds, gs = [], []
+    for r in range(3):
+        ir, rgb = O.synthetic_pair(1, H, W, rank=r)
+        ts.step(ir, rgb, lr_scale=1.0 if r < 2 else 0.5)
+        l = ts.losses(); ds.append(l["D"]); gs.append(l["G"])
+    d, g, n = ts.epoch_means()
+    assert n == 3 and abs(d - sum(ds) / 3) < 1e-5 and abs(g - sum(gs) / 3) < 1e-4
+    assert int(ts.optG.step_dev.item()) == 3 and int(ts.optD.step_dev.item()) == 3 and ts.optG.t == 3
+    assert ts.optG.dev.dtype == torch.float64 and abs(ts.optG.dev[4].item() - 0.5) < 1e-15     # LambdaLR factor of the last step
+    # against the oracle's Adam over the same three batches
+    oG = {k: v.clone() for k, v in pG.items()}; oD = {k: v.clone() for k, v in pD.items()}
+    aG, aD = O.AdamState(oG), O.AdamState(oD)
+    for r in range(3):
+        ir, rgb = O.synthetic_pair(1, H, W, rank=r)
+        O.train_step(oG, oD, pV, aG, aD, ir, rgb, lr_scale=1.0 if r < 2 else 0.5)
+    k = "outc.1.weight"
+    assert ((ts.G.arena.view(k) - oG[k]).abs() > 1e-4).float().mean() < 0.02
+
+
+def test_topk_ranking_csv_matches_the_reference_file(tmp_path):
+    """irc:1220-1278: the ranking CSV written by the reference's save_best_k_outputs for the same rows (golden file
+    tests/golden/top_5_ranking.csv, produced by oracle/make_golden_256.py)"""
+    import irc_b200 as R
+    from irc_b200.train import write_topk_ranking
+    g = torch.Generator().manual_seed(11)
+    rows = []
+    for i in range(9):
+        mse = float(torch.rand(1, generator=g)) * 0.05 + 1e-3
+        rows.append({"file": os.path.join(f"set0{i % 2}", f"V00{i % 3}", f"I{i:05d}.jpg"), "mae": float(torch.rand(1, generator=g)) * 0.2,
+                     "mse": mse, "psnr": -10.0 * float(np.log10(mse + 1e-12)), "ssim": None})
+    rows[4]["psnr"] = rows[2]["psnr"]
+    rows[6]["psnr"] = float("inf")
+    cfg = R.Config(); cfg.output_dir = str(tmp_path); cfg.topk = 5
+    path = write_topk_ranking(cfg, rows)
+    assert os.path.basename(path) == "top_5_ranking.csv" and os.path.basename(os.path.dirname(path)) == cfg.best50_dirname
+    want = open(os.path.join(os.path.dirname(__file__), "golden", "top_5_ranking.csv"), encoding="utf-8").read()
+    assert open(path, encoding="utf-8").read() == want
