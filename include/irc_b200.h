@@ -58,8 +58,25 @@ typedef struct irc_conv_gemm_args {
     int mt;                 /* 128-row sub-tiles per tile sharing each weight stage: 1, 2, 0 = auto */
     int reuse;              /* taps with consecutive shifts share one staged A tile: 0 off, 1 on, -1 auto */
     int epilogue_direct;    /* 1 = store rows straight from registers (default 0: swizzled smem staging + TMA stores) */
+    /* InstanceNorm statistics from the epilogue (nn.InstanceNorm2d after the convolution, irc:161): per 128-row sub-tile and
+     * output channel the (sum, sum of squares) of the stored bf16 values; needs row_img (ring rows are stored as zeros) and
+     * bf16 output with a tile width that is a multiple of 64.  stats_part: irc_conv_stats_workspace_floats(a_rows, n_out)
+     * floats; stats_edge: (n_img + 1) * n_out * 2 floats; rows_per_img = hp * wp of the output frame.  NULL = off.
+     * irc_conv_stats_finalize turns the partials into stats[n][c] = (sum, sum of squares) in a fixed order. */
+    float* stats_part;
+    float* stats_edge;
+    int rows_per_img;
+    /* Horizontal tap reduction + bias + tanh fused into the epilogue, for k x k convolutions with a tiny Cout computed as a
+     * GEMM over the k kernel ROWS (n_out = 32 columns = (kernel column j, output channel co) -> j * tap_nco + co):
+     *   tap_out[n][co][y][x] = act(bias[co] + sum_j acc[q + j - (tap_nshift-1)/2][j * tap_nco + co]),  q = frame row of (n, y, x)
+     * fp32 NCHW out (the generator's output head, irc:527-531: 7 x 7 reflect conv 64 -> 3 + tanh).  Tiles overlap by
+     * tap_nshift - 1 rows; `out` is not written.  tap_act: 0 none, 3 tanh.  NULL = off. */
+    float* tap_out;
+    int tap_nshift, tap_nco, tap_H, tap_W, tap_hp, tap_wp, tap_oy, tap_ox, tap_act;
 } irc_conv_gemm_args;
 int irc_conv_gemm(const irc_conv_gemm_args* args, void* stream);
+long long irc_conv_stats_workspace_floats(long long rows, int n_out);
+int irc_conv_stats_finalize(const float* part, const float* edge, int n_img, int rows_per_img, int n_out, float* stats, void* stream);
 
 /* Weight-gradient GEMM: out[s][t][m][n] = sum_{q in split s} a[q + a_shift[t]][a_chan_off + m] *
  * b[q + b_shift[t]][b_chan_off + n].  Replaces the conv weight-gradient of loss.backward()
@@ -150,6 +167,11 @@ int irc_in_bwd_apply(const irc_in_bwd_args* args, void* stream);
  * shared memory.  fold_pad > 0: g1 views a frame that holds the gradient w.r.t. ReflectionPad2d(fold_pad) of the map;
  * the ring pixels are folded onto the interior while loading (the ring itself is left untouched).  bsum is optional. */
 int irc_in_bwd_fused(const irc_in_bwd_args* args, int fold_pad, void* stream);
+/* Same result as irc_in_bwd_reduce + irc_in_bwd_apply in ONE launch for maps larger than the cluster kernel takes: the CTAs
+ * form `groups` groups, each group walks its images one at a time (partial sums, a group barrier, apply), so that the second
+ * read of g and z hits the L2 and HBM sees every tensor once (3 units instead of 5).  Identity tables, plain views,
+ * C in {64, 128, 256}; args->work must hold 4 * groups * ctas_per_group * C floats + 512 (zero-initialised once). */
+int irc_in_bwd_l2(const irc_in_bwd_args* args, int groups, void* stream);
 
 /* Backward of nn.ReflectionPad2d(p) in place on a frame holding the gradient w.r.t. the padded tensor: interior pixels
  * within p of the border receive the ring pixels that mirror onto them; the ring is cleared. */

@@ -17,8 +17,8 @@ LIB_PATH = os.path.join(_HERE, "libirc_sm100.so")
 MAX_TAPS = 64
 
 EXPORTS = [
-    "irc_version", "irc_arch_check", "irc_last_error", "irc_conv_gemm", "irc_tn_gemm", "irc_tn_gemm_ctas", "irc_row_index",
-    "irc_in_stats", "irc_gather", "irc_in_apply_fused", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_in_bwd_fused", "irc_maxpool2", "irc_maxpool2_bwd",
+    "irc_version", "irc_arch_check", "irc_last_error", "irc_conv_gemm", "irc_conv_stats_workspace_floats", "irc_conv_stats_finalize", "irc_tn_gemm", "irc_tn_gemm_ctas", "irc_row_index",
+    "irc_in_stats", "irc_gather", "irc_in_apply_fused", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_in_bwd_fused", "irc_in_bwd_l2", "irc_maxpool2", "irc_maxpool2_bwd",
     "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
     "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics",
     "irc_adam", "irc_accumulate", "irc_pack_bf16", "irc_gather_sum", "irc_gather_sum_multi", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
@@ -40,6 +40,9 @@ class ConvGemmArgs(C.Structure):
         ("mask", C.c_void_p), ("mask_ld", C.c_longlong), ("mask_chan_off", C.c_int), ("mask_slope", C.c_float),
         ("addend", C.c_void_p), ("addend_ld", C.c_longlong), ("addend_chan_off", C.c_int),
         ("bn", C.c_int), ("mt", C.c_int), ("reuse", C.c_int), ("epilogue_direct", C.c_int),
+        ("stats_part", C.c_void_p), ("stats_edge", C.c_void_p), ("rows_per_img", C.c_int),
+        ("tap_out", C.c_void_p), ("tap_nshift", C.c_int), ("tap_nco", C.c_int), ("tap_H", C.c_int), ("tap_W", C.c_int), ("tap_hp", C.c_int),
+        ("tap_wp", C.c_int), ("tap_oy", C.c_int), ("tap_ox", C.c_int), ("tap_act", C.c_int),
     ]
 
 
@@ -127,6 +130,7 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(LIB_PATH)
         _lib.irc_last_error.restype = C.c_char_p
         _lib.irc_im2col_rows.restype = C.c_longlong
+        _lib.irc_conv_stats_workspace_floats.restype = C.c_longlong
     return _lib
 
 
@@ -275,8 +279,14 @@ class CudaBackend:
         self.conv_mt = int(os.environ.get("IRC_CONV_MT", "0"))   # 0 = let the library choose the M sub-tiling of conv_gemm
         self.fused_in_bwd = os.environ.get("IRC_FUSED_IN_BWD", "1") != "0"   # cluster-resident single-pass InstanceNorm backward
         self.fused_in_apply = os.environ.get("IRC_FUSED_IN_APPLY", "1") != "0"
+        self.inbwd_l2_groups = int(os.environ.get("IRC_INBWD_L2", "16"))      # image groups in flight of the L2-resident InstanceNorm backward (0 = two-pass)
         self.batch_sums = os.environ.get("IRC_BATCH_SUMS", "1") != "0"      # one launch for all split-K weight-gradient reductions
         self._pending, self._sum_tables = [], {}
+        self._stats_ws = {}
+        # InstanceNorm statistics in the conv epilogue for layers with at least this many reduction elements per output (below it
+        # the epilogue is on the critical path of the tile loop): IRC_STATS_EPI=0 all layers, =1000000 none
+        self.stats_epilogue_min_k = int(os.environ.get("IRC_STATS_EPI", "1024"))
+        self.fused_outc = os.environ.get("IRC_FUSED_OUTC", "1") != "0"      # tap reduction + bias + tanh in the GEMM epilogue of the output head
         self.gather_mode = os.environ.get("IRC_GATHER", "auto")     # lean | tiled | generic (stencil gather kernel choice)
         self.conv_epilogue_direct = int(os.environ.get("IRC_EPI_DIRECT", "0"))
         self.conv_reuse = int(os.environ.get("IRC_CONV_REUSE", "0"))
@@ -313,7 +323,10 @@ class CudaBackend:
 
     # ---- tensor-core GEMMs
     def conv_gemm(self, a, a_chan_off, cin, taps: Sequence[int], w, n_out, out, out_chan_off=0, bias=None, act=0, slope=0.0,
-                  row_img=None, mask: Optional[View] = None, mask_slope=0.0, addend: Optional[View] = None):
+                  row_img=None, mask: Optional[View] = None, mask_slope=0.0, addend: Optional[View] = None, in_stats=None, tap=None):
+        """in_stats = (stats [n_img, n_out, 2], n_img, rows_per_img): InstanceNorm statistics of the output from the epilogue
+        (needs row_img); tap = dict(out, nshift, nco, H, W, hp, wp, oy, ox, act): horizontal tap reduction + bias + activation
+        fused into the epilogue, fp32 NCHW result in tap['out'] (`out` is then only a placeholder)."""
         g = ConvGemmArgs()
         g.a = a.data_ptr(); g.a_rows = a.shape[0]; g.a_ld = a.shape[1]; g.a_chan_off = a_chan_off; g.cin = cin
         g.ntaps = len(taps)
@@ -321,7 +334,7 @@ class CudaBackend:
             g.taps[i] = int(t)
         assert w.dtype == torch.bfloat16 and w.shape == (n_out, len(taps) * cin), (w.shape, n_out, len(taps), cin)
         g.w = w.data_ptr(); g.n_out = n_out
-        assert out.shape[0] == a.shape[0]
+        assert tap is not None or out.shape[0] == a.shape[0]
         g.out = out.data_ptr(); g.out_ld = out.shape[1]; g.out_chan_off = out_chan_off
         g.out_fp32 = int(out.dtype == torch.float32)
         g.bias = None if bias is None else bias.data_ptr()
@@ -333,8 +346,30 @@ class CudaBackend:
         if addend is not None:
             assert addend.t.shape[0] == a.shape[0]
             g.addend = addend.t.data_ptr(); g.addend_ld = addend.t.shape[1]; g.addend_chan_off = addend.chan_off
-        g.bn = 0; g.mt = self.conv_mt; g.reuse = self.conv_reuse; g.epilogue_direct = self.conv_epilogue_direct;
+        g.bn = 0; g.mt = self.conv_mt; g.reuse = self.conv_reuse; g.epilogue_direct = self.conv_epilogue_direct
+        fin = None
+        if in_stats is not None:
+            stats, n_img, rows_per_img = in_stats
+            assert row_img is not None and stats.shape == (n_img, n_out, 2) and stats.dtype == torch.float32
+            part, edge = self._stats_workspace(a.shape[0], n_out, n_img)
+            g.stats_part = part.data_ptr(); g.stats_edge = edge.data_ptr(); g.rows_per_img = rows_per_img
+            fin = (part, edge, n_img, rows_per_img, n_out, stats)
+        if tap is not None:
+            g.tap_out = tap["out"].data_ptr(); g.tap_nshift = tap["nshift"]; g.tap_nco = tap["nco"]; g.tap_H = tap["H"]; g.tap_W = tap["W"]
+            g.tap_hp = tap["hp"]; g.tap_wp = tap["wp"]; g.tap_oy = tap["oy"]; g.tap_ox = tap["ox"]; g.tap_act = tap["act"]
         self._timed("conv_gemm", lambda: check(self.L.irc_conv_gemm(C.byref(g), _stream()))); self.launches += 1
+        if fin is not None:
+            part, edge, n_img, rows_per_img, n_out_, stats = fin
+            check(self.L.irc_conv_stats_finalize(_p(part), _p(edge), n_img, rows_per_img, n_out_, _p(stats), _stream())); self.launches += 1
+
+    def _stats_workspace(self, rows, n_out, n_img):
+        """partials of the epilogue statistics: one buffer per (rows, n_out) shape, allocated on first use (before any capture)"""
+        key = (rows, n_out, n_img)
+        ws = self._stats_ws.get(key)
+        if ws is None:
+            nf = int(self.L.irc_conv_stats_workspace_floats(C.c_longlong(rows), n_out))
+            ws = self._stats_ws[key] = (torch.zeros(nf, device="cuda"), torch.zeros((n_img + 1) * n_out * 2, device="cuda"))
+        return ws
 
     def tn_gemm(self, a, a_chan_off, m, b, b_chan_off, n, k_rows, a_shift, b_shift, out, tap_stride, m_stride, n_stride,
                 splits, split_stride):
@@ -430,6 +465,11 @@ class CudaBackend:
             return
         if fold_pad:
             self.fold_inplace(g1.t, g1.chan_off, C_, n_img, H, W, fold_pad)
+        if (self.inbwd_l2_groups > 0 and stats is not None and tables.ty_idx is None and tables.tx_idx is None and C_ in (64, 128, 256)
+                and W >= 2048 // C_ and not (z.s2d_c or g1.s2d_c or dz.s2d_c or (g2 is not None and g2.s2d_c))):
+            # large maps: one launch, every image's second read served by the L2 (3 tensor units over HBM instead of 5)
+            check(self.L.irc_in_bwd_l2(C.byref(g), self.inbwd_l2_groups, _stream())); self.launches += 1
+            return
         # (running the two passes over L2-sized groups of images was measured: 14.50 ms/step unchunked vs 14.67 / 15.11 /
         # 15.67 ms with 64 / 40 / 24 MB groups - the extra launches cost more than the L2 hits save)
         if stats is not None:

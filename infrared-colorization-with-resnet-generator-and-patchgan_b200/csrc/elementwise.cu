@@ -1028,6 +1028,193 @@ __global__ void __launch_bounds__(256, 4) in_bwd_apply_pipe_kernel(const InBwdP 
 }
 
 // ---------------------------------------------------------------------------------
+// L2-resident single-launch InstanceNorm(+activation) backward for LARGE maps (identity tables, plain views).
+// The two-pass version reads g and z twice from HBM (5 tensor units moved for 3 algorithmic: both tensors are several
+// times the L2).  Here the CTAs form K groups; a group walks its images one at a time: phase 1 streams the image's g and z
+// (a few MB: they stay in the 126 MB L2) into the (sum gd, sum gd*xhat) partials, the group meets at a counter barrier,
+// every CTA adds the group's partials in a fixed order (bit-reproducible), and phase 2 re-reads the same pixels - now L2
+// hits - and writes dz.  Only K images are in flight, so HBM sees g and z once: 3 units.  The grid never exceeds what is
+// co-resident (checked on the host with the occupancy API), so the spin barrier cannot starve; it is also bounded.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool kTwo, int kD>
+__global__ void __launch_bounds__(256, 2) in_bwd_l2_kernel(const InBwdP p, int K, int Gc, float* part, unsigned* sync) {
+    irc::pdl_prologue();
+    extern __shared__ float sh[];
+    constexpr int NT = kTwo ? 3 : 2;
+    const int nt = blockDim.x;
+    uint4* slot = reinterpret_cast<uint4*>(sh) + threadIdx.x;         // [kD][NT][nt]
+    __shared__ float tot[512];                                         // group totals of the current image: [C][2]
+    const int C8 = p.C >> 3, C2 = p.C * 2;
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int c = cv * 8;
+    const int group = blockIdx.x % K, j = blockIdx.x / K;              // CTA j of its group
+    unsigned* bar = sync + group;
+    unsigned* exitc = sync + 32 + group;
+    const long long grs = (long long)p.g1.wp * p.g1.ld, zrs = (long long)p.z.wp * p.z.ld, drs = (long long)p.dz.wp * p.dz.ld;
+    const long long hrs = kTwo ? (long long)p.g2.wp * p.g2.ld : 0;
+    const int gps = (int)p.g1.ld, zps = (int)p.z.ld, dps = (int)p.dz.ld, hps = kTwo ? (int)p.g2.ld : 0;
+    unsigned it = 0;
+    for (int n = group; n < p.n_img; n += K, ++it) {
+        const bf16* gb = p.g1.at(n, 0, 0, c);
+        const bf16* zb = p.z.at(n, 0, 0, c);
+        const bf16* hb = kTwo ? p.g2.at(n, 0, 0, c) : nullptr;
+        bf16* db = const_cast<bf16*>(p.dz.at(n, 0, 0, c));
+        float mu[8], rs[8];
+        moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mu[k] = -mu[k] * rs[k];
+        // ---------------- phase 1: partial sums over this CTA's rows (j, j + Gc, ...)
+        float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        {
+            int iy = j, ix = lane, cy = j, cx = lane;
+            auto issue = [&](int st) {
+                if (iy < p.H) {
+                    cp_async16(slot + (st * NT + 0) * nt, gb + iy * grs + ix * gps);
+                    cp_async16(slot + (st * NT + 1) * nt, zb + iy * zrs + ix * zps);
+                    if (kTwo) cp_async16(slot + (st * NT + 2) * nt, hb + iy * hrs + ix * hps);
+                    ix += L; if (ix >= p.W) { ix = lane; iy += Gc; }
+                }
+                cp_async_commit();
+            };
+#pragma unroll
+            for (int st = 0; st < kD; ++st) issue(st);
+            int st = 0;
+            while (cy < p.H) {
+                cp_async_wait<kD - 1>();
+                const uint4 gr = slot[(st * NT + 0) * nt], zr = slot[(st * NT + 1) * nt];
+                uint4 hr = make_uint4(0, 0, 0, 0);
+                if (kTwo) hr = slot[(st * NT + 2) * nt];
+                issue(st);
+                float g[8], zv[8];
+                unpack8(gr, g); unpack8(zr, zv);
+                if (kTwo) {
+                    float u[8];
+                    unpack8(hr, u);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) g[k] += u[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float xh = fmaf(zv[k], rs[k], mu[k]);
+                    const float gd = g[k] * dactf(xh, p.act, p.slope);
+                    s1[k] += gd; s2[k] = fmaf(gd, xh, s2[k]);
+                }
+                cx += L; if (cx >= p.W) { cx = lane; cy += Gc; }
+                st = st + 1 == kD ? 0 : st + 1;
+            }
+            cp_async_wait<0>();
+        }
+        __syncthreads();                                  // slots are reused as the lane-reduction scratch
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { sh[(lane * C8 + cv) * 16 + q * 2] = s1[q]; sh[(lane * C8 + cv) * 16 + q * 2 + 1] = s2[q]; }
+        __syncthreads();
+        float* mine = part + ((long long)((it & 1) * K + group) * Gc + j) * C2;
+        for (int i = threadIdx.x; i < C2; i += blockDim.x) {
+            float a = 0.f;
+            for (int l = 0; l < L; ++l) a += sh[l * C8 * 16 + i];
+            __stcg(mine + i, a);
+        }
+        // ---------------- group barrier (monotonic counter; all CTAs of the grid are co-resident)
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(bar, 1u);
+            const unsigned target = (it + 1) * (unsigned)Gc;
+            const long long t0 = clock64();
+            while (ld_acquire_u32(bar) < target) {
+                __nanosleep(64);
+                if (clock64() - t0 > 4000000000LL) { printf("irc: in_bwd_l2 group barrier timed out (block %d)\n", (int)blockIdx.x); __trap(); }
+            }
+        }
+        __syncthreads();
+        // every CTA adds the group's partials itself, in a fixed order: the 256 threads split the Gc partials of each value
+        // into 256 / C2 interleaved subsets (independent loads, 8 in flight), the subsets are combined in subset order
+        const float* gp = part + (long long)((it & 1) * K + group) * Gc * C2;
+        {
+            const int nh = blockDim.x / C2 > 0 ? blockDim.x / C2 : 1;      // 2 (C = 64), 1 (C >= 128)
+            const int i0 = threadIdx.x % C2, h = threadIdx.x / C2;
+            for (int i = i0; i < C2; i += blockDim.x) {                     // one trip unless C2 > 256
+                float a = 0.f;
+                int q = h;
+                for (; q + 7 * nh < Gc; q += 8 * nh) {
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = __ldcg(gp + (long long)(q + u * nh) * C2 + i);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) a += v[u];
+                }
+                for (; q < Gc; q += nh) a += __ldcg(gp + (long long)q * C2 + i);
+                sh[h * C2 + i] = a;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < C2; i += blockDim.x) {
+                float a = 0.f;
+                for (int hh = 0; hh < nh; ++hh) a += sh[hh * C2 + i];
+                tot[i] = a;
+                if (j == 0 && p.bsum) p.bsum[(long long)n * C2 + i] = a;
+            }
+        }
+        __syncthreads();
+        float b1[8], b2[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { b1[k] = tot[(c + k) * 2] * p.inv_cnt; b2[k] = tot[(c + k) * 2 + 1] * p.inv_cnt; }
+        // ---------------- phase 2: the same pixels again (L2 hits), dz out
+        {
+            int iy = j, ix = lane, cy = j, cx = lane;
+            auto issue = [&](int st) {
+                if (iy < p.H) {
+                    cp_async16(slot + (st * NT + 0) * nt, gb + iy * grs + ix * gps);
+                    cp_async16(slot + (st * NT + 1) * nt, zb + iy * zrs + ix * zps);
+                    if (kTwo) cp_async16(slot + (st * NT + 2) * nt, hb + iy * hrs + ix * hps);
+                    ix += L; if (ix >= p.W) { ix = lane; iy += Gc; }
+                }
+                cp_async_commit();
+            };
+#pragma unroll
+            for (int st = 0; st < kD; ++st) issue(st);
+            int st = 0;
+            while (cy < p.H) {
+                cp_async_wait<kD - 1>();
+                const uint4 gr = slot[(st * NT + 0) * nt], zr = slot[(st * NT + 1) * nt];
+                uint4 hr = make_uint4(0, 0, 0, 0);
+                if (kTwo) hr = slot[(st * NT + 2) * nt];
+                issue(st);
+                float g[8], zv[8], o[8];
+                unpack8(gr, g); unpack8(zr, zv);
+                if (kTwo) {
+                    float u[8];
+                    unpack8(hr, u);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) g[k] += u[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float xh = fmaf(zv[k], rs[k], mu[k]);
+                    const float gd = g[k] * dactf(xh, p.act, p.slope);
+                    o[k] = rs[k] * (gd - b1[k] - xh * b2[k]);
+                }
+                store8(db + cy * drs + cx * dps, o);
+                cx += L; if (cx >= p.W) { cx = lane; cy += Gc; }
+                st = st + 1 == kD ? 0 : st + 1;
+            }
+            cp_async_wait<0>();
+        }
+        __syncthreads();                                  // `tot` and the slots are rewritten by the next image
+    }
+    // re-arm the counters for the next launch: the last CTA of the group to leave resets them
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(exitc, 1u) == (unsigned)Gc - 1) { *bar = 0u; *exitc = 0u; __threadfence(); }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // Single-pass InstanceNorm(+activation) backward for small feature maps (H*W <= 4096: the ResNet bottleneck and the
 // PatchGAN layers).  One thread-block CLUSTER owns one (image, 32-channel group): its CTAs split the pixels, every thread
 // keeps its <= 8 pixels of g and z (16 bytes each) in REGISTERS, the (sum gd, sum gd*xhat) partials are combined inside
@@ -1124,6 +1311,23 @@ __device__ __forceinline__ float dact_t(float xh, float slope) {
     return 1.f;
 }
 
+// Pixel i (0..7) of a thread: group i covers the 64 consecutive pixels [p0 + 64 i, p0 + 64 i + 64) and the thread's lane is
+// ROTATED by 8 per group.  With a fixed lane the threads that sit on a mirrored column (x = 1, x = W - 2 when W == 64) would
+// carry the reflection fold of all eight of their pixels - eight dependent trips to L2 while everyone else waits at the
+// cluster barrier; rotated, every thread owns at most one or two border pixels.  Any permutation inside a group keeps the
+// accesses of a warp contiguous (8 consecutive lanes, possibly wrapped once).
+struct RotPix {
+    int y, x, o0, o1, o2;
+    bool ok;
+    __device__ __forceinline__ RotPix(int i, int p0, int p1, int lane, int W, float invW, const VStep& a, const VStep& b, const VStep& c) {
+        const int pix = p0 + i * kFusedLanes + ((lane + 8 * i) & (kFusedLanes - 1));
+        ok = pix < p1;
+        y = __float2int_rd(((float)pix + 0.5f) * invW);        // exact for pix < 2^20 (H * W <= 4096 here)
+        x = pix - y * W;
+        o0 = a.at(y, x, W); o1 = b.at(y, x, W); o2 = c.at(y, x, W);
+    }
+};
+
 template <bool kFold, int kAct>
 __global__ void __launch_bounds__(256, 3) in_bwd_fused_kernel(const InBwdP p, int fold_pad) {
     irc::pdl_prologue();
@@ -1138,52 +1342,57 @@ __global__ void __launch_bounds__(256, 3) in_bwd_fused_kernel(const InBwdP p, in
     const int HW = p.H * p.W;
     const int P = (HW + CL - 1) / CL;
     const int p0 = rank * P, p1 = min(p0 + P, HW);
-    const int np = p0 + lane < p1 ? (p1 - p0 - lane + kFusedLanes - 1) / kFusedLanes : 0;     // pixels of this thread
+    const float invW = 1.f / (float)p.W;
     uint4* gs = raw + tid;
     uint4* zs = raw + kFusedNP * 256 + tid;
     // all loads of the thread go straight to its shared-memory slots (no register staging): 16 x 16 bytes in flight
     VStep vg, vz, vd;
     vg.init(p.g1, n, c, p.W); vz.init(p.z, n, c, p.W); vd.init(p.dz, n, c, p.W);
-    {
-        PixWalk w(p0 + lane, p.W, vg, vz, vd);
 #pragma unroll
-        for (int i = 0; i < kFusedNP; ++i) {
-            if (i < np) {
-                cp_async16(gs + i * 256, vg.base + w.o0);
-                cp_async16(zs + i * 256, vz.base + w.o1);
-            } else {
-                gs[i * 256] = make_uint4(0, 0, 0, 0); zs[i * 256] = make_uint4(0, 0, 0, 0);     // g = 0 adds nothing
-            }
-            w.next(vg, vz, vd);
+    for (int i = 0; i < kFusedNP; ++i) {
+        const RotPix w(i, p0, p1, lane, p.W, invW, vg, vz, vd);
+        if (w.ok) {
+            cp_async16(gs + i * 256, vg.base + w.o0);
+            cp_async16(zs + i * 256, vz.base + w.o1);
+        } else {
+            gs[i * 256] = make_uint4(0, 0, 0, 0); zs[i * 256] = make_uint4(0, 0, 0, 0);     // g = 0 adds nothing
         }
     }
     float mu[8], rs[8];
     moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
 #pragma unroll
     for (int k = 0; k < 8; ++k) mu[k] = -mu[k] * rs[k];
-    cp_async_wait_all();
     if (kFold) {
-        PixWalk w(p0 + lane, p.W, vg, vz, vd);
-        for (int i = 0; i < np; ++i, w.next(vg, vz, vd)) {
+        // transpose of ReflectionPad2d(fold_pad): border pixels add the ring pixels that mirror onto them.  The (up to three)
+        // ring reads of a pixel are independent and issued together, while the cp.async of the interior are still in flight.
+#pragma unroll 2
+        for (int i = 0; i < kFusedNP; ++i) {
+            const RotPix w(i, p0, p1, lane, p.W, invW, vg, vz, vd);
             const int y = w.y, x = w.x;
-            if (y > fold_pad && y < p.H - 1 - fold_pad && x > fold_pad && x < p.W - 1 - fold_pad) continue;
+            if (!w.ok || (y > fold_pad && y < p.H - 1 - fold_pad && x > fold_pad && x < p.W - 1 - fold_pad)) continue;
             const int my = mirror_src(y, p.H, fold_pad), mx = mirror_src(x, p.W, fold_pad);
             if (my == INT_MIN && mx == INT_MIN) continue;
+            const uint4 zero = make_uint4(0, 0, 0, 0);
+            const uint4 u0 = my != INT_MIN ? __ldg(reinterpret_cast<const uint4*>(p.g1.at(n, my, x, c))) : zero;
+            const uint4 u1 = mx != INT_MIN ? __ldg(reinterpret_cast<const uint4*>(p.g1.at(n, y, mx, c))) : zero;
+            const uint4 u2 = (my != INT_MIN && mx != INT_MIN) ? __ldg(reinterpret_cast<const uint4*>(p.g1.at(n, my, mx, c))) : zero;
+            cp_async_wait_all();              // the thread's own interior values (a no-op after the first border pixel)
             float a[8], v[8];
             unpack8(gs[i * 256], a);
-            if (my != INT_MIN) { load8(p.g1.at(n, my, x, c), v);
+            unpack8(u0, v);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) a[k] += v[k]; }
-            if (mx != INT_MIN) { load8(p.g1.at(n, y, mx, c), v);
+            for (int k = 0; k < 8; ++k) a[k] += v[k];
+            unpack8(u1, v);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) a[k] += v[k]; }
-            if (my != INT_MIN && mx != INT_MIN) { load8(p.g1.at(n, my, mx, c), v);
+            for (int k = 0; k < 8; ++k) a[k] += v[k];
+            unpack8(u2, v);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) a[k] += v[k]; }
+            for (int k = 0; k < 8; ++k) a[k] += v[k];
             // rounded to bf16 like the stand-alone fold, so both paths give the same bits
             gs[i * 256] = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
         }
     }
+    cp_async_wait_all();
     float acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
@@ -1203,22 +1412,19 @@ __global__ void __launch_bounds__(256, 3) in_bwd_fused_kernel(const InBwdP p, in
     float b1[8], b2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { b1[k] = tot[cv * 16 + k * 2] * p.inv_cnt; b2[k] = tot[cv * 16 + k * 2 + 1] * p.inv_cnt; }
-    {
-        PixWalk w(p0 + lane, p.W, vg, vz, vd);
 #pragma unroll 2
-        for (int i = 0; i < kFusedNP; ++i) {
-            if (i < np) {
-                float g[8], zv[8], o[8];
-                unpack8(gs[i * 256], g); unpack8(zs[i * 256], zv);
+    for (int i = 0; i < kFusedNP; ++i) {
+        const RotPix w(i, p0, p1, lane, p.W, invW, vg, vz, vd);
+        if (w.ok) {
+            float g[8], zv[8], o[8];
+            unpack8(gs[i * 256], g); unpack8(zs[i * 256], zv);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float xh = fmaf(zv[k], rs[k], mu[k]);
-                    const float gd = g[k] * dact_t<kAct>(xh, p.slope);
-                    o[k] = rs[k] * (gd - b1[k] - xh * b2[k]);
-                }
-                store8(const_cast<bf16*>(vd.base) + w.o2, o);
+            for (int k = 0; k < 8; ++k) {
+                const float xh = fmaf(zv[k], rs[k], mu[k]);
+                const float gd = g[k] * dact_t<kAct>(xh, p.slope);
+                o[k] = rs[k] * (gd - b1[k] - xh * b2[k]);
             }
-            w.next(vg, vz, vd);
+            store8(const_cast<bf16*>(vd.base) + w.o2, o);
         }
     }
     cluster.sync();      // `part` must outlive the remote reads of every peer
@@ -1468,7 +1674,7 @@ int check_view(const irc_view& v, const char* what) {
 }
 
 // block shape for the per-(n,c) reductions
-constexpr int kCounterFloats = 256;     // tail of the reduction workspace reserved for per-image ticket counters
+constexpr int kCounterFloats = 512;     // tail of the reduction workspace: 256 per-image ticket counters + 256 words of group-barrier state
 
 // block = (C/8 channel vectors) x L pixel lanes
 void row_block(int C, int W, int& threads, int& L) {
@@ -1701,6 +1907,53 @@ extern "C" int irc_in_bwd_apply(const irc_in_bwd_args* a, void* stream) {
     } else if (!p.ty_idx && !p.tx_idx) irc::launch(in_bwd_apply_kernel<true>, grid, threads, 0, (cudaStream_t)stream, p);
     else irc::launch(in_bwd_apply_kernel<false>, grid, threads, 0, (cudaStream_t)stream, p);
     return irc_check_launch("irc_in_bwd_apply");
+}
+
+extern "C" int irc_in_bwd_l2(const irc_in_bwd_args* a, int groups, void* stream) {
+    InBwdP p; int rc = fill_bwd(a, p); if (rc) return rc;
+    rc = check_view(a->dz, "irc_in_bwd_l2 dz"); if (rc) return rc;
+    p.dz = mk(a->dz);
+    const int C8 = p.C / 8;
+    if (!p.stats || p.ty_idx || p.tx_idx || p.z.s2d_c || p.g1.s2d_c || p.dz.s2d_c || (p.has2 && p.g2.s2d_c) || p.C > 256 || 256 % C8 || p.W < 256 / C8 ||
+        !a->work || groups < 1)
+        return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_bwd_l2: needs stats, identity tables, plain views, C in {64,128,256}, W >= 2048/C, a workspace, groups >= 1");
+    // prefetch depth: 4 pixels per thread in flight (8 measured no faster: IRC_INBWD_L2_DEPTH=8)
+    static int depth = 0;
+    if (!depth) { const char* e = getenv("IRC_INBWD_L2_DEPTH"); depth = e ? atoi(e) : 4; if (depth != 8) depth = 4; }
+    const size_t smem = (size_t)depth * (p.has2 ? 3 : 2) * 256 * 16;
+    static int per_sm[2] = {0, 0};
+    if (!per_sm[p.has2]) {
+        cudaFuncSetAttribute(in_bwd_l2_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(in_bwd_l2_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(in_bwd_l2_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(in_bwd_l2_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        int n0 = 0;
+        cudaError_t e;
+        if (depth == 8) e = p.has2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n0, in_bwd_l2_kernel<true, 8>, 256, smem)
+                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n0, in_bwd_l2_kernel<false, 8>, 256, smem);
+        else e = p.has2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n0, in_bwd_l2_kernel<true, 4>, 256, smem)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n0, in_bwd_l2_kernel<false, 4>, 256, smem);
+        if (e != cudaSuccess || n0 < 1) return irc_check_launch("cudaOccupancyMaxActiveBlocksPerMultiprocessor(in_bwd_l2)");
+        per_sm[p.has2] = n0 > 2 ? 2 : n0;
+    }
+    // K image groups, K a divisor of the image count (every group then walks the same number of images)
+    int K = groups < p.n_img ? groups : p.n_img;
+    if (K > 32) K = 32;
+    while (p.n_img % K) --K;
+    int Gc = irc_num_sms() * per_sm[p.has2] / K;           // the whole grid must be co-resident (spin barrier)
+    if (Gc > p.H) Gc = p.H;
+    const long long need = 2LL * K * Gc * p.C * 2;
+    if (Gc < 1 || a->work_floats < need + kCounterFloats) return irc_set_error(IRC_ERR_BAD_ARG, "irc_in_bwd_l2: workspace too small (%lld floats needed)", need + kCounterFloats);
+    unsigned* sync = (unsigned*)(a->work + a->work_floats - kCounterFloats) + 256;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (depth == 8) {
+        if (p.has2) irc::launch(in_bwd_l2_kernel<true, 8>, K * Gc, 256, smem, st, p, K, Gc, a->work, sync);
+        else irc::launch(in_bwd_l2_kernel<false, 8>, K * Gc, 256, smem, st, p, K, Gc, a->work, sync);
+    } else {
+        if (p.has2) irc::launch(in_bwd_l2_kernel<true, 4>, K * Gc, 256, smem, st, p, K, Gc, a->work, sync);
+        else irc::launch(in_bwd_l2_kernel<false, 4>, K * Gc, 256, smem, st, p, K, Gc, a->work, sync);
+    }
+    return irc_check_launch("irc_in_bwd_l2");
 }
 
 extern "C" int irc_in_bwd_fused(const irc_in_bwd_args* a, int fold_pad, void* stream) {

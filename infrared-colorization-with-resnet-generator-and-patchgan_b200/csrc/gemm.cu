@@ -86,8 +86,20 @@ struct ConvParams {
     const bf16* addend;      // optional bf16 [rows][addend_ld]: added to the accumulator (residual-stream gradient)
     long long addend_ld;
     int addend_chan_off;
-    float* stats;   // [n_img][n_out][2] or null
+    // InstanceNorm statistics from the epilogue (staged bf16 path only): per 128-row sub-tile and output channel the (sum, sum of
+    // squares) of the bf16-ROUNDED values of the sub-tile's live rows, image slot 0 -> stats_part[subtile][n_out][2]; the rows of
+    // a sub-tile that already belong to the next image -> stats_edge[image][n_out][2].  irc_conv_stats_finalize adds them up in
+    // sub-tile order (bit-reproducible).  Null = off.
+    float* stats_part;
+    float* stats_edge;
+    int rows_per_img;
     int n_out;
+    // tile geometry: tile t covers rows [t * tile_stride + row_bias, ... + 128 * mt); stride < 128 * mt = overlapping tiles
+    int tile_stride, row_bias;
+    // horizontal tap reduction fused into the epilogue (tiny-Cout k x k convolutions computed as a GEMM over the kernel rows):
+    // out[n][co][y][x] = act(bias[co] + sum_j acc[q + j - halo][j * nco + co]); tiles overlap by 2 * halo rows
+    float* tap_out;
+    int tap_nshift, tap_nco, tap_H, tap_W, tap_hp, tap_wp, tap_oy, tap_ox, tap_act;
     int nstg;       // staging tiles of the TMA-store epilogue (2, or 1 when shared memory is needed for pipeline stages)
     int tma_store;  // 1: bf16 rows leave through a swizzled shared-memory staging tile and TMA stores (coalesced)
 };
@@ -217,7 +229,77 @@ __device__ __forceinline__ void epilogue_subtile_staged(const ConvParams& p, con
             tma_store_2d(tmOut, buf, p.out_chan_off + n0 + c0, (int)row0);
             bulk_commit_group();
         }
+        if (p.stats_part) {
+            // column sums of the staged tile (the values the consumer will read back, i.e. after the bf16 rounding; dead rows
+            // were stored as zeros).  Warp w takes columns 8w..8w+7; lane = (row quarter << 3) | column; the quarters walk their
+            // 32 rows from different offsets so that the four rows read together sit in different 16-byte swizzle chunks.
+            const int et = (int)threadIdx.x - 64;
+            const int col = (et >> 5) * 8 + (et & 7), rq = (et >> 3) & 3;
+            const int rb = p.rows_per_img - (int)((unsigned)row0 % (unsigned)p.rows_per_img);      // tile-local rows >= rb belong to the next image
+            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                const int r = rq * 32 + ((i + 2 * rq) & 31);
+                const unsigned short u = *reinterpret_cast<const unsigned short*>(buf + r * 128 + (((col >> 3) ^ (r & 7)) << 4) + ((col & 7) << 1));
+                const float f = __uint_as_float((uint32_t)u << 16);
+                if (r < rb) { s0 += f; q0 = fmaf(f, f, q0); } else { s1 += f; q1 = fmaf(f, f, q1); }
+            }
+            // quarters combined in a fixed order: (q0 + q1) + (q2 + q3)
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 8); q0 += __shfl_xor_sync(0xffffffffu, q0, 8);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 8); q1 += __shfl_xor_sync(0xffffffffu, q1, 8);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 16); q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+            if (rq == 0 && row0 < p.rows) {
+                const int ch = n0 + c0 + col;
+                *reinterpret_cast<float2*>(p.stats_part + ((row0 >> 7) * p.n_out + ch) * 2) = make_float2(s0, q0);
+                if (rb < kBM) {
+                    const long long img1 = (unsigned)row0 / (unsigned)p.rows_per_img + 1;
+                    *reinterpret_cast<float2*>(p.stats_edge + (img1 * p.n_out + ch) * 2) = make_float2(s1, q1);
+                }
+            }
+        }
         ++stg_iter;
+    }
+}
+
+// Epilogue of the horizontal-tap mode (fp32, bn = 32): all sub-tiles of the tile are copied from TMEM to a shared-memory
+// strip (row stride 21..: odd, conflict-free), the accumulator is released, and every thread then reduces the taps of its
+// output rows, adds the bias, applies tanh and writes fp32 NCHW planes (consecutive rows = consecutive x: coalesced).
+template <int MT>
+__device__ __forceinline__ void epilogue_tapsum(const ConvParams& p, long long row0, uint32_t tmem_acc, int quarter, int half, float* strip, uint64_t* tempty_bar) {
+    const int ncol = p.tap_nshift * p.tap_nco;           // <= 32
+    const int ld = ncol | 1;                             // odd row stride
+    const int lane = threadIdx.x & 31;
+    named_bar_sync(2, 256);                              // the strip of the previous tile has been consumed
+#pragma unroll 1
+    for (int m = half; m < MT; m += 2) {
+        uint32_t r[32];
+        tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(m * p.bn), r);
+        tmem_ld_wait();
+        float* dst = strip + (m * kBM + quarter * 32 + lane) * ld;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < ncol) dst[j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+    named_bar_sync(2, 256);
+    if (lane == 0) mbar_arrive(tempty_bar);              // the MMAs of the next tile may overwrite the accumulator
+    const int halo = (p.tap_nshift - 1) >> 1;
+    const int et = (int)threadIdx.x - 64;
+    const long long img_rows = (long long)p.tap_hp * p.tap_wp, hw = (long long)p.tap_H * p.tap_W;
+    for (int r = halo + et; r < MT * kBM - halo; r += 256) {
+        const long long q = row0 + r;
+        if (q < 0 || q >= p.rows) continue;
+        const int n = (int)(q / img_rows);
+        const int rem = (int)(q - n * img_rows);
+        const int Y = rem / p.tap_wp, X = rem - Y * p.tap_wp;
+        const int y = Y - p.tap_oy, x = X - p.tap_ox;
+        if (y < 0 || y >= p.tap_H || x < 0 || x >= p.tap_W) continue;
+        for (int co = 0; co < p.tap_nco; ++co) {
+            float acc = p.bias ? __ldg(p.bias + co) : 0.f;
+            for (int j = 0; j < p.tap_nshift; ++j) acc += strip[(r + j - halo) * ld + j * p.tap_nco + co];
+            if (p.tap_act == 3) acc = tanhf(acc);
+            p.tap_out[((long long)n * p.tap_nco + co) * hw + (long long)y * p.tap_W + x] = acc;
+        }
     }
 }
 
@@ -242,7 +324,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constan
     uint8_t* stg = smem + (size_t)S * stage_bytes + 1024;      // 2 x 16 KB staging tiles of the TMA-store epilogue
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long m_tiles = (p.rows + tile_rows - 1) / tile_rows;
+    const long long m_tiles = (p.rows + p.tile_stride - 1) / p.tile_stride;
     const uint32_t acc_cols = (uint32_t)(MT * p.bn);      // TMEM columns of one accumulator buffer
     const long long total_tiles = m_tiles * p.n_tiles;
     const int num_kb = p.ntaps * p.k_chunks;
@@ -268,7 +350,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constan
         {
             int stage = 0; uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const long long row0 = (tile / p.n_tiles) * tile_rows;
+                const long long row0 = (tile / p.n_tiles) * p.tile_stride + p.row_bias;
                 const int n0 = (int)(tile % p.n_tiles) * p.bn;
                 for (int t = 0; t < p.ntaps; ++t) {
                     const long long arow = row0 + p.taps[t];
@@ -340,10 +422,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constan
             const int n0 = (int)(tile % p.n_tiles) * p.bn;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
+            if (p.tap_out) {
+                epilogue_tapsum<MT>(p, (tile / p.n_tiles) * p.tile_stride + p.row_bias, tmem_base + (uint32_t)acc * acc_cols, quarter, half,
+                                    reinterpret_cast<float*>(stg), &tempty[acc]);
+                if (++acc == p.nbuf) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
 #pragma unroll 1
             for (int m = 0; m < MT; ++m) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(m * p.bn);
-                const long long srow0 = (tile / p.n_tiles) * tile_rows + m * kBM;
+                const long long srow0 = (tile / p.n_tiles) * p.tile_stride + p.row_bias + m * kBM;
                 if (p.tma_store) epilogue_subtile_staged(p, e, &tmOut, srow0, r_in_tile, n0, taddr, half, stg, stg_iter, store_thread);
                 else epilogue_subtile(p, e, srow0 + r_in_tile, n0, taddr, half);
             }
@@ -840,6 +928,34 @@ int auto_tpc(int bn, int ntaps) {
     return 1;
 }
 
+// stats[n][c] = (sum, sum of squares) of image n: its sub-tiles' slot-0 partials in sub-tile order, preceded by the edge
+// partial when the image starts inside a sub-tile.  Block = 64 channels x 16 segments of the sub-tile range.
+__global__ void __launch_bounds__(1024) conv_stats_finalize_kernel(const float* __restrict__ part, const float* __restrict__ edge, int rows_per_img, int n_out,
+                                                                   float* __restrict__ stats) {
+    irc::pdl_prologue();
+    __shared__ float2 seg[16][64];
+    const int n = blockIdx.x, c = blockIdx.y * 64 + (threadIdx.x & 63), sg = threadIdx.x >> 6;
+    const long long first_row = (long long)n * rows_per_img, end_row = first_row + rows_per_img;
+    const long long s_begin = (first_row + kBM - 1) / kBM, s_end = (end_row + kBM - 1) / kBM;      // sub-tiles whose slot 0 is image n
+    const long long cnt = s_end - s_begin, per = (cnt + 15) / 16;
+    long long s0 = s_begin + sg * per, s1 = s0 + per; if (s1 > s_end) s1 = s_end;
+    float a = 0.f, b = 0.f;
+    if (c < n_out) {
+        for (long long sidx = s0; sidx < s1; ++sidx) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(part + (sidx * n_out + c) * 2));
+            a += v.x; b += v.y;
+        }
+    }
+    seg[sg][threadIdx.x & 63] = make_float2(a, b);
+    __syncthreads();
+    if (sg == 0 && c < n_out) {
+        float x = 0.f, y = 0.f;
+        if (first_row % kBM) { const float2 v = __ldg(reinterpret_cast<const float2*>(edge + ((long long)n * n_out + c) * 2)); x = v.x; y = v.y; }
+        for (int g = 0; g < 16; ++g) { x += seg[g][threadIdx.x & 63].x; y += seg[g][threadIdx.x & 63].y; }
+        *reinterpret_cast<float2*>(stats + ((long long)n * n_out + c) * 2) = make_float2(x, y);
+    }
+}
+
 // group the taps into runs of consecutive row shifts (ascending), at most 8 long
 void build_runs(const int* taps, int ntaps, RunParams& rp) {
     int order[IRC_MAX_TAPS];
@@ -892,6 +1008,13 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
         for (int c = 4; c > 1; c >>= 1)
             if (2 * c * bn <= 512 && ((a->a_rows + c * kBM - 1) / (c * kBM)) * (a->n_out / bn) >= sms) { mt = c; break; }
     }
+    const bool tapsum = a->tap_out != nullptr;
+    if (tapsum) {
+        if (a->tap_nshift < 1 || !(a->tap_nshift & 1) || a->tap_nshift * a->tap_nco > 32 || a->n_out != 32 || a->tap_nco < 1 || a->mask || a->addend || a->row_img ||
+            (long long)a->tap_hp * a->tap_wp <= 0 || a->a_rows % ((long long)a->tap_hp * a->tap_wp) || (a->tap_act != 0 && a->tap_act != 3))
+            return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm(tap mode): needs an odd number of horizontal taps with nshift * nco <= 32 = n_out, frames of hp x wp rows, act 0 or 3 (tanh)");
+        if (mt != 1) mt = 2;
+    }
     if (mt != 1 && mt != 2 && mt != 4) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: mt must be 0, 1, 2 or 4");
     if (mt * bn > 512) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: mt * bn exceeds the 512 TMEM columns");
     CUtensorMap tmA, tmB;
@@ -917,9 +1040,22 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     p.addend = (const bf16*)a->addend; p.addend_ld = a->addend_ld; p.addend_chan_off = a->addend_chan_off;
     if (a->addend && (((uintptr_t)a->addend & 15) || (a->addend_ld % 8) || (a->addend_chan_off % 8)))
         return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: addend rows must be 16-byte aligned");
-    p.stats = nullptr; p.n_out = a->n_out;
+    p.n_out = a->n_out;
+    p.tile_stride = kBM * mt; p.row_bias = 0;
+    p.stats_part = a->stats_part; p.stats_edge = a->stats_edge; p.rows_per_img = a->rows_per_img;
+    p.tap_out = a->tap_out; p.tap_nshift = a->tap_nshift; p.tap_nco = a->tap_nco; p.tap_H = a->tap_H; p.tap_W = a->tap_W; p.tap_hp = a->tap_hp;
+    p.tap_wp = a->tap_wp; p.tap_oy = a->tap_oy; p.tap_ox = a->tap_ox; p.tap_act = a->tap_act;
+    if (tapsum) {
+        const int halo = (a->tap_nshift - 1) / 2;
+        p.tile_stride = kBM * mt - 2 * halo; p.row_bias = -halo;
+    }
     // coalesced TMA-store epilogue for bf16 outputs whose tile width is a multiple of one 64-channel swizzle row
-    p.tma_store = (!a->out_fp32 && bn % 64 == 0 && a->epilogue_direct == 0) ? 1 : 0;
+    p.tma_store = (!tapsum && !a->out_fp32 && bn % 64 == 0 && a->epilogue_direct == 0) ? 1 : 0;
+    if (p.stats_part) {
+        if (!p.tma_store || !a->row_img || !a->stats_edge || a->rows_per_img < kBM)
+            return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: epilogue statistics need the staged bf16 epilogue (tile width %% 64 == 0), a row_img table "
+                                                  "(ring rows stored as zeros), an edge buffer and images of at least 128 rows");
+    }
     CUtensorMap tmOut = tmB;
     if (p.tma_store) {
         rc = make_map(&tmOut, a->out, a->a_rows, (int)a->out_ld, kBM);
@@ -930,7 +1066,7 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     p.nstg = 2;
     if (p.tma_store && (kMaxSmem - kStatic - 2048 - (2 * kBM * 128 + 1024)) / stage_bytes < 4 &&
         (kMaxSmem - kStatic - 2048 - (kBM * 128 + 1024)) / stage_bytes >= 4) p.nstg = 1;
-    const int stg_bytes = p.tma_store ? p.nstg * kBM * 128 + 1024 : 0;
+    const int stg_bytes = tapsum ? kBM * mt * ((a->tap_nshift * a->tap_nco) | 1) * 4 + 1024 : (p.tma_store ? p.nstg * kBM * 128 + 1024 : 0);
     int stages = (kMaxSmem - kStatic - 2048 - stg_bytes) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: tile does not fit shared memory");
@@ -943,7 +1079,7 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
             return irc_check_launch("cudaFuncSetAttribute(conv_gemm)");
         g_attr_conv = true;
     }
-    const long long tiles = ((a->a_rows + kBM * mt - 1) / (kBM * mt)) * p.n_tiles;
+    const long long tiles = ((a->a_rows + p.tile_stride - 1) / p.tile_stride) * p.n_tiles;
     const int grid = (int)(tiles < sms ? tiles : sms);
     // tap-run variant: worthwhile when taps form runs (kw > 1); reuse = 0 off, 1 on, -1/auto
     RunParams rp;
@@ -951,7 +1087,7 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     int max_len = 1;
     for (int r = 0; r < rp.nruns; ++r) if (rp.run_len[r] > max_len) max_len = rp.run_len[r];
     const int reuse = a->reuse < 0 ? (max_len > 1 ? 1 : 0) : a->reuse;
-    if (reuse && max_len > 1) {
+    if (reuse && max_len > 1 && !tapsum && !p.stats_part) {
         rp.a_box_rows = kBM + max_len - 1;
         rp.a_stage_bytes = ((rp.a_box_rows * 128 + 1023) / 1024) * 1024;
         rp.base_off_mode = a->reuse == 3 ? 1 : 0;      // 3 = the (wrong) base-offset encoding, kept for the experiment script
@@ -1085,4 +1221,16 @@ extern "C" int irc_tn_gemm_ctas(int m, int n, int ntaps, int same_a_shift) {
     }
     const int tpc = same_a_shift ? auto_tpc(bn, ntaps) : 1;
     return ((m + kBM - 1) / kBM) * ((n + bn - 1) / bn) * ((ntaps + tpc - 1) / tpc);
+}
+
+// floats of the per-sub-tile statistics partials irc_conv_gemm writes for a [rows][n_out] output (args->stats_part); the edge
+// buffer (args->stats_edge) needs (n_img + 1) * n_out * 2 floats
+extern "C" long long irc_conv_stats_workspace_floats(long long rows, int n_out) {
+    return ((rows + kBM - 1) / kBM) * (long long)n_out * 2;
+}
+
+extern "C" int irc_conv_stats_finalize(const float* part, const float* edge, int n_img, int rows_per_img, int n_out, float* stats, void* stream) {
+    if (!part || !edge || !stats || n_img <= 0 || rows_per_img < kBM || n_out <= 0) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_stats_finalize: bad args");
+    irc::launch(conv_stats_finalize_kernel, dim3(n_img, (n_out + 63) / 64), 1024, 0, (cudaStream_t)stream, part, edge, rows_per_img, n_out, stats);
+    return irc_check_launch("irc_conv_stats_finalize");
 }

@@ -81,6 +81,16 @@ class ConvOp:
     def bias(self):
         return self.arena.view(self.bias_name) if self.bias_name else None
 
+    def fwd_stats(self, a, a_chan_off, out, stats, row_img, n_img, rows_per_img, z_view, C, H, W, **kw):
+        """forward convolution followed by the InstanceNorm statistics of its output (irc:161): from the GEMM epilogue when the
+        layer is deep enough for the epilogue to hide behind the MMAs (be.stats_epilogue_min_k) and the frame geometry allows
+        it, else by a separate pass over the output"""
+        if self.lay.T * self.lay.K >= self.be.stats_epilogue_min_k and rows_per_img >= 128 and self.lay.N % 64 == 0 and row_img is not None:
+            self.fwd(a, a_chan_off, out, row_img=row_img, in_stats=(stats, n_img, rows_per_img), **kw)
+        else:
+            self.fwd(a, a_chan_off, out, **kw)
+            self.be.in_stats(z_view, C, n_img, H, W, stats)
+
     def fwd(self, a, a_chan_off, out, **kw):
         self.be.note = (self.name, "fwd", self.flops)
         self.be.conv_gemm(a, a_chan_off, self.lay.K, self.taps, self.lay.w_f.t, self.lay.w_f.rows, out, **kw)
@@ -129,13 +139,19 @@ class GeneratorEngine:
         self.Z3 = F(H2, W2, 1, 128)
         self.Z4 = F(H, W, 1, 64)
         self.y4 = F(H, W, 3, 64)
-        self.P = torch.zeros(self.y4.rows, 32, device=device)
+        # per-vertical-tap partial products of the output head: only materialised when the tap reduction is NOT fused into the GEMM
+        self.P = torch.zeros(8 if getattr(be, "fused_outc", False) else self.y4.rows, 32, device=device)
         self.fake = torch.zeros(B, 3, H, W, device=device)
         st = lambda c: torch.zeros(B, c, 2, device=device)
         self.st0, self.st1, self.st2, self.st3, self.st4 = st(64), st(128), st(256), st(128), st(64)
         self.sta = [st(256) for _ in range(n_blocks)]
         self.stb = [st(256) for _ in range(n_blocks)]
         self.bsum = st(256)
+        # image index of every frame row (-1 = padding ring) for the convolutions that emit InstanceNorm statistics
+        self.ri_full = torch.zeros(self.Z1.rows, device=device, dtype=torch.int16)
+        self.ri_half = torch.zeros(self.Z2.rows, device=device, dtype=torch.int16)
+        be.row_index(self.ri_full, B, H + 2, W + 2, 1, H + 1, 1, W + 1)
+        be.row_index(self.ri_half, B, H2 + 2, W2 + 2, 1, H2 + 1, 1, W2 + 1)
         # ---- stencil tables
         mk = lambda my, mx: L.make_tables(my, mx, device)
         self.t_down1 = mk(L.down_matrix(H), L.down_matrix(W))
@@ -203,12 +219,10 @@ class GeneratorEngine:
         be.in_stats(self.Z0.view(), 64, B, H, W, self.st0)
         be.gather(self.Z0.view(), self.cat2.view(128), 64, B, H, W, 1, 0, stats=self.st0, cnt=H * W, eps=EPS, act=ACT_RELU)
         # down1: 3x3 zero-pad conv at full resolution, then IN + ReLU + blur-downsample fused
-        self.down1.fwd(self.cat2.t, 128, self.Z1.t)
-        be.in_stats(self.Z1.view(), 128, B, H, W, self.st1)
+        self.down1.fwd_stats(self.cat2.t, 128, self.Z1.t, self.st1, self.ri_full, B, self.Z1.hp * self.Z1.wp, self.Z1.view(), 128, H, W)
         be.gather(self.Z1.view(), self.cat1.view(256), 128, B, H2, W2, 1, 0, tables=self.t_down1, stats=self.st1, cnt=H * W, eps=EPS, act=ACT_RELU)
         # down2
-        self.down2.fwd(self.cat1.t, 256, self.Z2.t)
-        be.in_stats(self.Z2.view(), 256, B, H2, W2, self.st2)
+        self.down2.fwd_stats(self.cat1.t, 256, self.Z2.t, self.st2, self.ri_half, B, self.Z2.hp * self.Z2.wp, self.Z2.view(), 256, H2, W2)
         be.gather(self.Z2.view(), self.X[0].view(), 256, B, H4, W4, 1, 1, tables=self.t_down2, stats=self.st2, cnt=H2 * W2, eps=EPS, act=ACT_RELU)
         # 9 ResNet blocks (irc:362-418): reflect halo written by the apply pass
         n4 = H4 * W4
@@ -220,17 +234,23 @@ class GeneratorEngine:
             be.in_apply(self.Zb[b].view(), self.X[b + 1].view(), 256, B, H4, W4, 1, 1, self.stb[b], eps=EPS, act=ACT_NONE, res=self.X[b].view())
         # up1: UpsampleAA into cat1[0:256), conv on the concatenation
         be.gather(self.X[self.nb].view(), self.cat1.view(0), 256, B, H2, W2, 1, 0, tables=self.t_up1)
-        self.up1.fwd(self.cat1.t, 0, self.Z3.t)
-        be.in_stats(self.Z3.view(), 128, B, H2, W2, self.st3)
+        self.up1.fwd_stats(self.cat1.t, 0, self.Z3.t, self.st3, self.ri_half, B, self.Z3.hp * self.Z3.wp, self.Z3.view(), 128, H2, W2)
         # up2: IN + ReLU + UpsampleAA fused into cat2[0:128)
         be.gather(self.Z3.view(), self.cat2.view(0), 128, B, H, W, 1, 0, tables=self.t_up2, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU)
-        self.up2.fwd(self.cat2.t, 0, self.Z4.t)
-        be.in_stats(self.Z4.view(), 64, B, H, W, self.st4)
+        self.up2.fwd_stats(self.cat2.t, 0, self.Z4.t, self.st4, self.ri_full, B, self.Z4.hp * self.Z4.wp, self.Z4.view(), 64, H, W)
         be.gather(self.Z4.view(), self.y4.view(), 64, B, H, W, 3, 1, stats=self.st4, cnt=H * W, eps=EPS, act=ACT_RELU)
-        # outc: 7x7 reflect conv 64->3 as a GEMM over the 7 vertical taps (21 of 32 outputs), then the
-        # horizontal tap reduction + bias + tanh
-        self.outc.fwd(self.y4.t, 0, self.P)
-        be.tap_reduce(self.P, self.outc_shifts, 3, B, H, W, self.y4.hp, self.y4.wp, 3, 3, self.outc.bias(), ACT_TANH, self.fake)
+        return self.output_head()
+
+    def output_head(self) -> torch.Tensor:
+        """outc (irc:527-531) on the frame y4: 7x7 reflect conv 64->3 as a GEMM over the 7 vertical taps (21 of 32 outputs), then
+        the horizontal tap reduction + bias + tanh - inside the GEMM epilogue (tiles overlap by 6 rows), or as a second pass"""
+        be, B, H, W = self.be, self.B, self.H, self.W
+        if getattr(be, "fused_outc", False):
+            self.outc.fwd(self.y4.t, 0, self.P, bias=self.outc.bias(),
+                          tap=dict(out=self.fake, nshift=7, nco=3, H=H, W=W, hp=self.y4.hp, wp=self.y4.wp, oy=3, ox=3, act=ACT_TANH))
+        else:
+            self.outc.fwd(self.y4.t, 0, self.P)
+            be.tap_reduce(self.P, self.outc_shifts, 3, B, H, W, self.y4.hp, self.y4.wp, 3, 3, self.outc.bias(), ACT_TANH, self.fake)
         return self.fake
 
     # ------------------------------------------------------------------ backward
@@ -335,6 +355,8 @@ class DiscriminatorEngine:
         self.pred = torch.zeros(n, 1, self.Ho, self.Wo, device=device)
         st = lambda c: torch.zeros(n, c, 2, device=device)
         self.st2, self.st5, self.st8, self.bsum = st(128), st(256), st(512), st(512)
+        self.ri2 = torch.zeros(n * self.hb0 * self.wb0, device=device, dtype=torch.int16)      # live rows of the model.2 output grid
+        be.row_index(self.ri2, n, self.hb0, self.wb0, 0, H2, 0, W2)
         # weights (shared between the 2B-image and B-image instances)
         if layouts is None:
             layouts = dict(
@@ -394,8 +416,7 @@ class DiscriminatorEngine:
             assert n1 == n
         self.c0.fwd(self.E0, 0, self.S0, bias=self.c0.bias(), act=ACT_LRELU, slope=0.2, row_img=self.row_img0)
         # model.2
-        self.c2.fwd(self.S0v, 0, self.Z2)
-        be.in_stats(self._vZ2(self.Z2), 128, n, self.H2, self.W2, self.st2)
+        self.c2.fwd_stats(self.S0v, 0, self.Z2, self.st2, self.ri2, n, self.hb0 * self.wb0, self._vZ2(self.Z2), 128, self.H2, self.W2)
         be.gather(self._vZ2(self.Z2), View(self.S2, 0, self.hb2, self.wb2), 128, n, self.H2, self.W2, 1, 0, stats=self.st2,
                   cnt=self.H2 * self.W2, eps=EPS, act=ACT_LRELU, slope=0.2, dst_s2d=1)
         # model.5

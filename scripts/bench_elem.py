@@ -106,3 +106,42 @@ from irc_b200.train_step import gaussian_window
 win = gaussian_window(); ga, gb, gc = (torch.empty_like(f) for _ in range(3))
 timeit("ssim_fwd (+3 maps)", lambda: be.ssim_fwd(f, r, .5, .5, win, sums[8:], ga, gb, gc), f.numel() * 4 * 5)
 timeit("ssim_bwd", lambda: be.ssim_bwd(f, r, .5, .5, win, ga, gb, gc, 1.0, d, True), f.numel() * 4 * 7)
+
+# ---- round 2: L2-resident single-launch InstanceNorm backward (image groups) against the two-pass version
+print("\n# in_bwd large maps: two-pass (groups=0) vs L2-resident single launch with K image groups in flight")
+Z2f, g2f, dZ2f = F(H // 2, W // 2, 1, 256), F(H // 2, W // 2, 0, 256), F(H // 2, W // 2, 1, 256)
+s256b = st(256); be.in_stats(Z2f.view(), 256, B, H // 2, W // 2, s256b)
+Z3f, g3f, dZ3f = F(H // 2, W // 2, 1, 128), F(H // 2, W // 2, 0, 128), F(H // 2, W // 2, 1, 128)
+s128b = st(128); be.in_stats(Z3f.view(), 128, B, H // 2, W // 2, s128b)
+for grp in (0, 4, 8, 16):
+    be.inbwd_l2_groups = grp
+    timeit(f"[K={grp}] in_bwd 2src 64ch 256^2", lambda: be.in_bwd(Z0.view(), G1.view(128), dZ0.view(), 64, B, H, W, stats=s64, cnt=H * W, act=1, g2=G2.view(), bsum=bs),
+           n * 64 * 2 * 4)
+    timeit(f"[K={grp}] in_bwd 1src 64ch 256^2", lambda: be.in_bwd(Z4.view(), G4.view(), dZ4.view(), 64, B, H, W, stats=s64, cnt=H * W, act=1, bsum=bs), n * 64 * 2 * 3)
+    timeit(f"[K={grp}] in_bwd 1src 128ch 256^2", lambda: be.in_bwd(Z1.view(), g1.view(), dZ1.view(), 128, B, H, W, stats=s128, cnt=H * W, act=1, bsum=bs), n * 128 * 2 * 3)
+    timeit(f"[K={grp}] in_bwd 1src 256ch 128^2", lambda: be.in_bwd(Z2f.view(), g2f.view(), dZ2f.view(), 256, B, H // 2, W // 2, stats=s256b, cnt=H * W // 4, act=1, bsum=bs), n // 4 * 256 * 2 * 3)
+    timeit(f"[K={grp}] in_bwd 1src 128ch 128^2", lambda: be.in_bwd(Z3f.view(), g3f.view(), dZ3f.view(), 128, B, H // 2, W // 2, stats=s128b, cnt=H * W // 4, act=1, bsum=bs), n // 4 * 128 * 2 * 3)
+be.inbwd_l2_groups = 4
+print("\n# cluster InstanceNorm backward of the ResNet bottleneck with / without the reflection fold (algorithmic: 3 units)")
+timeit("in_bwd fused 256ch 64^2, fold_pad=1", lambda: be.in_bwd(Zb.view(), Gh.view(), dZa.view(), 256, B, 64, 64, stats=s256, cnt=4096, act=1, bsum=bs, fold_pad=1), B * 4096 * 256 * 2 * 3)
+timeit("in_bwd fused 256ch 64^2, no fold", lambda: be.in_bwd(Zb.view(), Gh.view(), dZa.view(), 256, B, 64, 64, stats=s256, cnt=4096, act=1, bsum=bs), B * 4096 * 256 * 2 * 3)
+timeit("in_apply fused 256ch 64^2 (+res, reflect ring)", lambda: be.in_apply(Zb.view(), Y.view(), 256, B, 64, 64, 1, 1, s256, act=0, res=X.view()), B * 4096 * 256 * 2 * 3)
+be.fused_in_bwd = False
+for grp in (4, 8, 16):
+    be.inbwd_l2_groups = grp
+    timeit(f"[K={grp}] in_bwd L2 kernel 256ch 64^2, no fold", lambda: be.in_bwd(Zb.view(), Gh.view(), dZa.view(), 256, B, 64, 64, stats=s256, cnt=4096, act=1, bsum=bs), B * 4096 * 256 * 2 * 3)
+    timeit(f"[K={grp}] fold_inplace + in_bwd L2 kernel 256ch 64^2", lambda: be.in_bwd(Zb.view(), Gh.view(), dZa.view(), 256, B, 64, 64, stats=s256, cnt=4096, act=1, bsum=bs, fold_pad=1), B * 4096 * 256 * 2 * 3)
+be.fused_in_bwd = True; be.inbwd_l2_groups = 16
+# warm L2 variant: the gradient was just written by the previous kernel (as inside the step): no flush between producer and consumer
+def warm(name, prod, fn, bytes_, reps=5):
+    fn(); torch.cuda.synchronize(); ts = []
+    for _ in range(reps):
+        flush.sum(); prod()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    t = sorted(ts)[len(ts) // 2]
+    print(f"{name:52s} {t * 1e3:8.1f} us  {bytes_ / t / 1e6:7.0f} GB/s")
+warm("in_bwd fused, fold, g just written (L2-warm)", lambda: Gh.t.mul_(1.0), lambda: be.in_bwd(Zb.view(), Gh.view(), dZa.view(), 256, B, 64, 64, stats=s256, cnt=4096, act=1, bsum=bs, fold_pad=1), B * 4096 * 256 * 2 * 3)
+be.fused_in_bwd = False
+warm("in_bwd L2 kernel (+fold pass), g just written", lambda: Gh.t.mul_(1.0), lambda: be.in_bwd(Zb.view(), Gh.view(), dZa.view(), 256, B, 64, 64, stats=s256, cnt=4096, act=1, bsum=bs, fold_pad=1), B * 4096 * 256 * 2 * 3)
+be.fused_in_bwd = True

@@ -90,9 +90,21 @@ class RefBackend:
         return acc
 
     # ------------------------------------------------------------------ GEMMs
+    stats_epilogue_min_k = 1024
+    fused_outc = True
+
     def conv_gemm(self, a, a_chan_off, cin, taps, w, n_out, out, out_chan_off=0, bias=None, act=0, slope=0.0,
-                  row_img=None, mask=None, mask_slope=0.0, addend=None):
+                  row_img=None, mask=None, mask_slope=0.0, addend=None, in_stats=None, tap=None):
         self.launches += 1
+        if tap is not None:
+            # horizontal tap reduction + bias + activation fused into the epilogue: the bias belongs to the reduced output
+            P = torch.zeros(a.shape[0], n_out, device=a.device)
+            self.conv_gemm(a, a_chan_off, cin, taps, w, n_out, P)
+            h = (tap["nshift"] - 1) // 2
+            n_img = a.shape[0] // (tap["hp"] * tap["wp"])
+            self.tap_reduce(P, [(0, j - h) for j in range(tap["nshift"])], tap["nco"], n_img, tap["H"], tap["W"], tap["hp"], tap["wp"],
+                            tap["oy"], tap["ox"], bias, tap["act"], tap["out"])
+            return
         rows = a.shape[0]
         A = a[:, a_chan_off:a_chan_off + cin].float()
         acc = torch.zeros(rows, n_out, device=a.device)
@@ -112,6 +124,11 @@ class RefBackend:
         if row_img is not None:
             acc = acc * (row_img >= 0).float().unsqueeze(1)
         out[:, out_chan_off:out_chan_off + n_out] = acc.to(out.dtype)
+        if in_stats is not None:
+            stats, n_img, rows_per_img = in_stats
+            assert row_img is not None
+            st = out[:, out_chan_off:out_chan_off + n_out].float().view(n_img, rows_per_img, n_out)      # the stored (rounded) values
+            stats.copy_(torch.stack([st.sum(1), (st * st).sum(1)], -1))
 
     def tn_gemm(self, a, a_chan_off, m, b, b_chan_off, n, k_rows, a_shift, b_shift, out, tap_stride, m_stride, n_stride,
                 splits, split_stride):

@@ -132,3 +132,64 @@ def test_tn_gemm(rows, m, n, lda, ldb, a_off, b_off, shifts, splits):
         ref = Af.t() @ (Bf[idx.clamp(0, rows - 1)] * ok)
         err = (got[:, t, :] - ref).norm() / ref.norm()
         assert err < 1e-4, (t, err)
+
+
+@pytest.mark.parametrize("n_img,hp,wp,cin,n_out,taps", [
+    (5, 34, 34, 64, 64, [-35, -34, -33, -1, 0, 1, 33, 34, 35]),      # 1156 rows per image: images start inside sub-tiles
+    (4, 32, 32, 128, 128, [-1, 0, 1]),                               # 1024 rows per image: boundaries on sub-tile edges
+    (3, 66, 66, 64, 256, [-67, -66, -65, -1, 0, 1, 65, 66, 67]),
+    (2, 20, 13, 64, 192, [0, 1, 13, 14]),                            # 260 rows per image, three 64-wide column chunks
+])
+@pytest.mark.parametrize("mt", [0, 1, 2, 4])
+def test_conv_gemm_epilogue_instance_norm_statistics(n_img, hp, wp, cin, n_out, taps, mt):
+    """north star (1): InstanceNorm statistics from the GEMM epilogue == sums over the live rows of the stored bf16 output,
+    per image and channel, for every tiling; bit-reproducible across launches"""
+    from irc_b200._native import CudaBackend
+    if mt * min(n_out, 256) > 512:
+        pytest.skip("mt * bn exceeds TMEM")
+    be = CudaBackend(); be.conv_mt = mt
+    g = torch.Generator(device="cuda").manual_seed(n_img * 100 + n_out)
+    rows = n_img * hp * wp
+    A = torch.randn(rows, cin, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(n_out, len(taps) * cin, device="cuda", generator=g) * 0.05).bfloat16()
+    ri = torch.zeros(rows, device="cuda", dtype=torch.int16)
+    be.row_index(ri, n_img, hp, wp, 1, hp - 1, 1, wp - 1)
+    out = torch.full((rows, n_out), float("nan"), device="cuda", dtype=torch.bfloat16)
+    st = [torch.full((n_img, n_out, 2), float("nan"), device="cuda") for _ in range(2)]
+    for s_ in st:
+        be.conv_gemm(A, 0, cin, taps, W, n_out, out, row_img=ri, in_stats=(s_, n_img, hp * wp))
+    torch.cuda.synchronize()
+    assert torch.equal(st[0], st[1])
+    ref = _conv_ref(A, taps, W, cin, 0) * (ri >= 0)[:, None]
+    assert (out.float() - ref).norm() / ref.norm() < 4e-3
+    o = out.float().view(n_img, hp * wp, n_out)
+    want = torch.stack([o.sum(1), (o * o).sum(1)], -1)
+    err = (st[0] - want).abs().max() / want.abs().max()
+    assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("n_img,H,W", [(3, 20, 24), (1, 64, 40), (2, 37, 129)])
+def test_conv_gemm_fused_horizontal_taps_bias_tanh(n_img, H, W):
+    """output head (irc:527-531): GEMM over the 7 kernel rows with the 7-tap horizontal reduction, bias and tanh in the
+    epilogue (overlapping tiles) == per-tap partial products + separate reduction"""
+    from irc_b200._native import CudaBackend
+    be = CudaBackend()
+    g = torch.Generator(device="cuda").manual_seed(H * W)
+    hp, wp = H + 6, W + 6
+    rows = n_img * hp * wp
+    A = torch.randn(rows, 64, device="cuda", generator=g).bfloat16()
+    Wt = torch.zeros(32, 7 * 64, device="cuda")
+    Wt[:21] = torch.randn(21, 7 * 64, device="cuda", generator=g) * 0.03
+    Wt = Wt.bfloat16()
+    bias = torch.randn(3, device="cuda", generator=g) * 0.1
+    taps = [(r - 3) * wp for r in range(7)]
+    P = torch.zeros(rows, 32, device="cuda")
+    be.conv_gemm(A, 0, 64, taps, Wt, 32, P)
+    want = torch.zeros(n_img, 3, H, W, device="cuda")
+    be.tap_reduce(P, [(0, s - 3) for s in range(7)], 3, n_img, H, W, hp, wp, 3, 3, bias, 3, want)
+    got = torch.full((n_img, 3, H, W), float("nan"), device="cuda")
+    be.conv_gemm(A, 0, 64, taps, Wt, 32, torch.zeros(8, 32, device="cuda"), bias=bias,
+                 tap=dict(out=got, nshift=7, nco=3, H=H, W=W, hp=hp, wp=wp, oy=3, ox=3, act=3))
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max() < 2e-6, (got - want).abs().max()

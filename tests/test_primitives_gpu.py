@@ -242,6 +242,38 @@ def test_in_bwd_fused_cluster(bes, C, H, W, act, fold):
     assert torch.equal(outs[0].view(n, dz.hp, dz.wp, C)[:, 0], dz.t.view(n, dz.hp, dz.wp, C)[:, 0])     # ring of dz untouched
 
 
+@pytest.mark.parametrize("C,H,W,two,groups,n", [(64, 80, 72, True, 3, 5), (128, 72, 80, False, 4, 5), (256, 66, 70, False, 2, 3), (64, 128, 96, False, 8, 16)])
+def test_in_bwd_l2_resident(bes, C, H, W, two, groups, n):
+    """single-launch, L2-resident InstanceNorm backward for large maps (image groups + counter barrier) == the two-pass
+    kernels bit for bit in the reductions' inputs (same formula; summation order differs) == the torch restatement;
+    uneven images per group, launched twice (the barrier counters must re-arm), one and two gradient sources"""
+    from irc_b200._native import View
+    g = gen(17)
+    z = frame(n, H, W, 1, C, g)
+    st = torch.zeros(n, C, 2, device="cuda")
+    bes[1].in_stats(z.view(), C, n, H, W, st)
+    g1 = frame(n, H, W, 1, 2 * C, g); g2 = frame(n, H, W, 0, C, g)
+    dz = frame(n, H, W, 1, C, g)
+    outs, sums = [], []
+    for be, grp in ((bes[0], groups), (bes[0], groups), (bes[0], 0), (bes[1], 0)):
+        d = dz.t.clone(); bs = torch.zeros(n, C, 2, device="cuda")
+        old = getattr(be, "inbwd_l2_groups", None)
+        if old is not None:
+            be.inbwd_l2_groups = grp
+        try:
+            be.in_bwd(z.view(), g1.view(C), View(d, 0, dz.hp, dz.wp, 1, 1), C, n, H, W, stats=st, cnt=H * W, act=1, bsum=bs,
+                      g2=g2.view() if two else None)
+        finally:
+            if old is not None:
+                be.inbwd_l2_groups = old
+        torch.cuda.synchronize()
+        outs.append(d); sums.append(bs)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(sums[0], sums[1])          # deterministic, counters re-armed
+    close(sums[0], sums[2], 1e-4, "bsum l2 vs two-pass"); close(sums[0], sums[3], 1e-3, "bsum l2 vs torch")
+    close(outs[0], outs[2], 4e-3, "l2 vs two-pass"); close(outs[0], outs[3], 1e-2, "l2 vs torch")
+    assert torch.equal(outs[0].view(n, dz.hp, dz.wp, C)[:, 0], dz.t.view(n, dz.hp, dz.wp, C)[:, 0])     # ring of dz untouched
+
+
 @pytest.mark.parametrize("mode", ["norm_relu_fold", "norm_none_two", "plain_lrelu", "upT", "s2d_src"])
 def test_in_bwd(bes, mode):
     from irc_b200 import layout as L
