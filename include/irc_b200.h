@@ -261,6 +261,20 @@ int irc_quantize_metrics(const float* fake, const float* gt, int n_img, int C, i
  * synchronisation): acc[j] += coef[j][n] + sum_i coef[j][i] * s[i], coef is [rows][n+1] fp32, rows <= 32. */
 int irc_accumulate(const float* s, int n, const float* coef, int rows, double* acc, void* stream);
 
+/* ---- input pipeline (after the image file has been decoded) ---------------------------------------------------------- */
+
+/* cv2.resize(src, (Wd, Hd), interpolation=cv2.INTER_AREA) of n_img 8-bit frames [n][Hs][Ws][C] (C = 1..4), bit-exact with
+ * OpenCV's implementation (KAISTPairDataset._read_ir / _read_rgb, irc:1132-1158; load_ir_image / load_rgb_image, irc:803-852).
+ * mode 0: general scale factors, separable tables (xi/xw: [Wd][kx], yi/yw: [Hd][ky] from computeResizeAreaTab, weight 0 =
+ * unused slot); mode 1: integer factors; mode 2: exactly 2 x 2.  img_max (optional, [n_img]) receives the maximum byte of
+ * each resized frame (the reference divides an IR frame by 255 only if its maximum exceeds 1, irc:1142). */
+int irc_resize_area_u8(const unsigned char* src, int n_img, int Hs, int Ws, int C, int Hd, int Wd, const int* xi, const float* xw, int kx,
+                       const int* yi, const float* yw, int ky, int mode, unsigned char* dst, int* img_max, void* stream);
+/* uint8 [n][H][W][C] -> fp32 [n][C][H][W] in [-1, 1]: x / 255 (skipped for images with img_max <= 1 when img_max is given), clip,
+ * channel swap for BGR frames, per-image horizontal flip (the paired augmentation of irc:1166-1168), x * 2 - 1 (irc:1174-1175). */
+int irc_u8_to_pm1(const unsigned char* src, int n_img, int H, int W, int C, int swap_rb, const unsigned char* flip, const int* img_max, float* out,
+                  void* stream);
+
 /* ---- optimizer / parameter layout ------------------------------------------------------ */
 
 /* torch.optim.Adam step (irc:1651, :1681; defaults of irc:1601-1604) over a flat arena.

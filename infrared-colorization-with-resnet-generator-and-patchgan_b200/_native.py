@@ -22,6 +22,7 @@ EXPORTS = [
     "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
     "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics",
     "irc_adam", "irc_accumulate", "irc_pack_bf16", "irc_gather_sum", "irc_gather_sum_multi", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
+    "irc_resize_area_u8", "irc_u8_to_pm1",
 ]
 
 
@@ -285,7 +286,7 @@ class CudaBackend:
         self._stats_ws = {}
         # InstanceNorm statistics in the conv epilogue for layers with at least this many reduction elements per output (below it
         # the epilogue is on the critical path of the tile loop): IRC_STATS_EPI=0 all layers, =1000000 none
-        self.stats_epilogue_min_k = int(os.environ.get("IRC_STATS_EPI", "1024"))
+        self.stats_epilogue_min_k = int(os.environ.get("IRC_STATS_EPI", "0"))
         self.fused_outc = os.environ.get("IRC_FUSED_OUTC", "1") != "0"      # tap reduction + bias + tanh in the GEMM epilogue of the output head
         self.gather_mode = os.environ.get("IRC_GATHER", "auto")     # lean | tiled | generic (stencil gather kernel choice)
         self.conv_epilogue_direct = int(os.environ.get("IRC_EPI_DIRECT", "0"))
@@ -619,6 +620,22 @@ class CudaBackend:
             return
         check(self.L.irc_stencil_nchw(_p(x), _p(out), n * c, hi, wi, ho, wo, _p(tables.ty_idx), _p(tables.ty_w), tables.ky,
                                       _p(tables.tx_idx), _p(tables.tx_w), tables.kx, int(accumulate), _stream())); self.launches += 1
+
+    # ---- input pipeline
+    def resize_area_u8(self, src, dst, tables, mode, img_max=None):
+        """src uint8 [n, Hs, Ws, C] -> dst uint8 [n, Hd, Wd, C], cv2.INTER_AREA; tables = (xi, xw, yi, yw) device tensors (mode 0)"""
+        n, hs, ws, c = src.shape
+        hd, wd = dst.shape[1], dst.shape[2]
+        assert src.dtype == torch.uint8 and dst.dtype == torch.uint8 and src.is_contiguous() and dst.is_contiguous() and dst.shape[3] == c
+        xi, xw, yi, yw = tables if tables is not None else (None, None, None, None)
+        kx = 0 if xi is None else xi.shape[1]; ky = 0 if yi is None else yi.shape[1]
+        check(self.L.irc_resize_area_u8(_p(src), n, hs, ws, c, hd, wd, _p(xi), _p(xw), kx, _p(yi), _p(yw), ky, mode, _p(dst), _p(img_max), _stream()))
+        self.launches += 1
+
+    def u8_to_pm1(self, src, out, swap_rb=False, flip=None, img_max=None):
+        n, h, w, c = src.shape
+        assert src.dtype == torch.uint8 and out.dtype == torch.float32 and out.shape == (n, c, h, w) and src.is_contiguous() and out.is_contiguous()
+        check(self.L.irc_u8_to_pm1(_p(src), n, h, w, c, int(swap_rb), _p(flip), _p(img_max), _p(out), _stream())); self.launches += 1
 
     def zero_(self, t):
         t.zero_(); self.launches += 1

@@ -1,393 +1,39 @@
-"""Teacher-forced per-layer parity at the REAL layer shapes (256 x 256 input, B = 1): every kernel of the generator's
-forward and backward plan is fed the ORACLE's activations / gradients (rounded to the bf16 the frames store) and its
-output is compared with the oracle's fp32 result on the same inputs.  Tolerance: the north star's per-layer figure for
-bf16, rel-L2 <= 1e-2 (measured: 2e-3 .. 5e-3, i.e. bf16 rounding of the operands and of the stored output).
-
-Why teacher-forced: one D+G iteration chains 24 convolutions with ReLU / sign() decisions in between; a whole-step
-gradient comparison mixes every kernel's error with mask flips inherited from upstream (tests/test_step_gpu.py bounds
-those loosely).  Here each kernel sees exactly the values the oracle saw, so a wrong tap, a missing fold on a border
-or a mis-indexed weight shows up as an O(1) error on that layer alone.
-
-The oracle side is local fp32 autograd of the reference's own operator sequence (oracle/irc_oracle.py primitives) on the
-CPU.  All CUDA work goes through the C ABI via the engine's launch methods."""
-import numpy as np
+"""Teacher-forced per-layer parity of the generator's forward AND backward kernels at the real layer shapes
+(256 x 256 input, B = 1), through the C ABI on the GPU.  The checks live in tests/teacher_forced.py (read its
+docstring): each kernel is fed the oracle's activations / gradients and must reproduce the oracle's fp32 result
+to the north star's per-layer bf16 tolerance, rel-L2 <= 1e-2 (measured: 1.7e-3, the rounding of the stored bf16 output)."""
 import pytest
-import torch
-import torch.nn.functional as F
+
+import teacher_forced as T
 
 pytestmark = pytest.mark.gpu
-
-TOL = 1e-2
-B, H, W = 1, 256, 256
-
-
-def rel(a, b):
-    a, b = a.detach().float().cpu(), b.detach().float().cpu()
-    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
-
-
-def r16(t):
-    """the value a bf16 frame stores"""
-    return t.detach().to(torch.bfloat16).float()
-
-
-def put(fr, x, chan_off=0, ring="zero"):
-    """NCHW fp32 -> interior of a frame (channels chan_off..), ring zero / reflected / untouched"""
-    n, c, h, w = x.shape
-    p = fr.p
-    v = fr.t.view(fr.N, fr.hp, fr.wp, fr.C)
-    if ring == "reflect" and p:
-        x = F.pad(x, (p, p, p, p), mode="reflect")
-        v[:, :, :, chan_off:chan_off + c].copy_(x.permute(0, 2, 3, 1))
-    else:
-        if ring == "zero" and p:
-            v[:, :, :, chan_off:chan_off + c].zero_()
-        v[:, p:p + h, p:p + w, chan_off:chan_off + c].copy_(x.permute(0, 2, 3, 1))
-
-
-def put_full(fr, xp, chan_off=0):
-    """NCHW fp32 of the PADDED size -> whole frame"""
-    c = xp.shape[1]
-    fr.t.view(fr.N, fr.hp, fr.wp, fr.C)[:, :, :, chan_off:chan_off + c].copy_(xp.permute(0, 2, 3, 1))
-
-
-def get(fr, c, chan_off=0, full=False):
-    v = fr.t.view(fr.N, fr.hp, fr.wp, fr.C)
-    if not full:
-        v = v[:, fr.p:fr.p + fr.H, fr.p:fr.p + fr.W]
-    return v[:, :, :, chan_off:chan_off + c].permute(0, 3, 1, 2).float().cpu()
-
-
-class Ctx:
-    pass
 
 
 @pytest.fixture(scope="module")
 def ctx():
-    """oracle forward + backward of the full generator loss at 256 x 256 with every tap's gradient retained, and a
-    generator engine holding the same weights"""
-    import irc_oracle as O
     import irc_b200  # noqa: F401
-    from irc_b200 import engine as E
     from irc_b200._native import CudaBackend
-    torch.manual_seed(0)
-    pG = O.seeded_params(O.generator_shapes(), 1234, bias_std=0.02)
-    pD = O.seeded_params(O.discriminator_shapes(), 1235, bias_std=0.02)
-    pV = O.seeded_params(O.vgg_shapes(), 1236, kaiming=True, bias_std=0.05)
-    ir, rgb = O.synthetic_pair(B, H, W)
-    leaves = {k: v.clone().requires_grad_(True) for k, v in pG.items()}
-    taps = {}
-    fake = O.generator_forward(leaves, ir, taps=taps)
-    for t in taps.values():
-        t.retain_grad()
-    lam = O.LAMBDAS
-    total = (lam["gan"] * -O.discriminator_forward(pD, torch.cat([ir, fake], 1)).mean() + lam["L1"] * (fake - rgb).abs().mean()
-             + lam["perc"] * (O.vgg_forward(pV, fake) - O.vgg_forward(pV, rgb)).abs().mean() + lam["tv"] * O.tv_loss(fake)
-             + lam["ssim"] * O.ssim_loss((fake + 1) / 2, (rgb + 1) / 2))
-    total.backward()
-    c = Ctx()
-    c.O, c.E = O, E
-    c.p = pG
-    c.ir = ir
-    c.act = {k: v.detach() for k, v in taps.items()}
-    c.grad = {k: v.grad.detach() for k, v in taps.items()}
-    c.wgrad = {k: v.grad.detach() for k, v in leaves.items()}
-    c.be = CudaBackend()
-    c.eng = E.GeneratorEngine(c.be, B, H, W, "cuda")
-    c.eng.arena.load(pG)
-    c.eng.refresh_weights()
-    # scale gradients into a bf16-friendly range per tensor (the kernels are linear in g; raw loss gradients at 256 x 256
-    # are ~1e-6 and would sit in bf16's normal range anyway, this only keeps the printed numbers readable)
-    return c
+    T.Cfg.TOL, T.Cfg.B, T.Cfg.H, T.Cfg.W, T.Cfg.dev, T.Cfg.round_bf16 = 1e-2, 1, 256, 256, "cuda", True
+    return T.make_ctx(CudaBackend())
 
 
-def conv_local(x, w, dz, pad=0, reflect=0):
-    """fp32 CPU: z = conv(x), and the vector-Jacobian products of dz"""
-    x = x.clone().requires_grad_(True); w = w.clone().requires_grad_(True)
-    xin = F.pad(x, (reflect,) * 4, mode="reflect") if reflect else x
-    z = F.conv2d(xin, w, None, padding=pad)
-    gx, gw = torch.autograd.grad(z, (x, w), dz)
-    return z.detach(), gx, gw
-
-
-def norm_act_local(z, g, O, act="relu", res=None):
-    """a = act(IN(z)) (+res);  dz = vjp(g)"""
-    z = z.clone().requires_grad_(True)
-    a = O.instance_norm(z)
-    if act == "relu":
-        a = torch.relu(a)
-    (dz,) = torch.autograd.grad(a, z, g)
-    out = a.detach() + (res if res is not None else 0)
-    return out, dz
-
-
-def scaled(g):
-    """unit-RMS copy of a gradient tensor (kernels are linear in it)"""
-    return g / g.pow(2).mean().sqrt().clamp_min(1e-30)
-
-
-def zero_wgrad(eng):
-    eng.arena.grad.zero_()
-
-
-# ----------------------------------------------------------------------------------------------------------
 def test_inc_7x7_reflect(ctx):
-    """inc.1: ReflectionPad2d(3) + Conv2d(1, 64, 7) (irc:458-463) forward and weight gradient; IN + ReLU apply"""
-    O, eng, be = ctx.O, ctx.eng, ctx.be
-    w = ctx.p["inc.1.weight"]
-    ir = ctx.ir
-    z_ref, _, _ = conv_local(ir, r16(w), torch.zeros(B, 64, H, W), reflect=3)
-    be.im2col(ir.cuda(), None, None, None, B, H, W, 7, 1, 3, 1, H, W, 0, eng.E_in)
-    eng.inc.fwd(eng.E_in, 0, eng.Z0.t)
-    e = rel(get(eng.Z0, 64), z_ref)
-    print("inc fwd", e); assert e < TOL
-    # IN + ReLU into cat2[128:192) with a zero ring
-    z = r16(z_ref)
-    put(eng.Z0, z)
-    be.in_stats(eng.Z0.view(), 64, B, H, W, eng.st0)
-    be.gather(eng.Z0.view(), eng.cat2.view(128), 64, B, H, W, 1, 0, stats=eng.st0, cnt=H * W, eps=1e-5, act=1)
-    a_ref, _ = norm_act_local(z, torch.zeros_like(z), O)
-    e = rel(get(eng.cat2, 64, 128), a_ref)
-    print("inc IN+ReLU", e); assert e < TOL
-    ring = get(eng.cat2, 64, 128, full=True)
-    assert ring[:, :, 0].abs().max() == 0 and ring[:, :, :, -1].abs().max() == 0
-    # backward: IN+ReLU^T with two gradient sources (skip connection + down1), then the weight gradient
-    g = scaled(ctx.grad["x0"])
-    ga, gb = r16(g * 0.25), r16(g * 0.75)
-    put(eng.Gcat2, ga, 128); put(eng.Gx0, gb)
-    be.in_bwd(eng.Z0.view(), eng.Gcat2.view(128), eng.dZ0.view(), 64, B, H, W, stats=eng.st0, cnt=H * W, eps=1e-5, act=1,
-              g2=eng.Gx0.view(), bsum=eng.bsum)
-    _, dz_ref = norm_act_local(z, ga + gb, O)
-    e = rel(get(eng.dZ0, 64), dz_ref)
-    print("inc IN+ReLU bwd (2 sources)", e); assert e < TOL
-    dz = r16(dz_ref)
-    put(eng.dZ0, dz)
-    zero_wgrad(eng)
-    eng.inc.wgrad(eng.dZ0.t, eng.E_in, 0, eng.dZ0.rows); be.flush_sums()
-    _, _, gw = conv_local(r16(ir), w, dz, reflect=3)
-    e = rel(eng.arena.view("inc.1.weight", eng.arena.grad), gw)
-    print("inc wgrad", e); assert e < TOL
+    T.check_inc_7x7_reflect(ctx)
 
 
 @pytest.mark.parametrize("name", ["down1", "down2", "up1", "up2"])
 def test_3x3_zero_pad_layers(ctx, name):
-    """down1.0 / down2.0 / up1_conv.0 / up2_conv.0 (irc:469-524): conv forward, IN+ReLU fused with the following
-    Downsample / UpsampleAA stencil (or the reflect-3 ring for up2), their transposes, IN backward, dgrad, wgrad"""
-    O, eng, be = ctx.O, ctx.eng, ctx.be
-    A, G = ctx.act, ctx.grad
-    H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
-    cfg = {
-        # conv op, input frame, channel offset, input tensor, Z frame, stats, output channels, (h, w) of the conv
-        "down1": (eng.down1, eng.cat2, 128, A["x0"], eng.Z1, eng.st1, 128, (H, W), "down1.0.weight"),
-        "down2": (eng.down2, eng.cat1, 256, A["x1"], eng.Z2, eng.st2, 256, (H2, W2), "down2.0.weight"),
-        "up1": (eng.up1, eng.cat1, 0, torch.cat([A["up1_up"], A["x1"]], 1), eng.Z3, eng.st3, 128, (H2, W2), "up1_conv.0.weight"),
-        "up2": (eng.up2, eng.cat2, 0, torch.cat([A["up2_up"], A["x0"]], 1), eng.Z4, eng.st4, 64, (H, W), "up2_conv.0.weight"),
-    }[name]
-    op, fin, off, x, Zf, st, co, (h, w_), wname = cfg
-    wt = ctx.p[wname]
-    x = r16(x)
-    ci = x.shape[1]
-    fin.t.zero_()
-    put(fin, x, off)
-    op.fwd(fin.t, off, Zf.t)
-    z_ref, _, _ = conv_local(x, r16(wt), torch.zeros(B, co, h, w_), pad=1)
-    e = rel(get(Zf, co), z_ref)
-    print(name, "fwd", e); assert e < TOL
-    # ---- IN + ReLU + what follows it in the plan
-    z = r16(z_ref)
-    put(Zf, z)
-    be.in_stats(Zf.view(), co, B, h, w_, st)
-    if name == "down1":
-        be.gather(Zf.view(), eng.cat1.view(256), co, B, H2, W2, 1, 0, tables=eng.t_down1, stats=st, cnt=h * w_, eps=1e-5, act=1)
-        got = get(eng.cat1, co, 256); post = O.blur_down
-    elif name == "down2":
-        be.gather(Zf.view(), eng.X[0].view(), co, B, H4, W4, 1, 1, tables=eng.t_down2, stats=st, cnt=h * w_, eps=1e-5, act=1)
-        got = get(eng.X[0], co); post = O.blur_down
-    elif name == "up1":
-        be.gather(Zf.view(), eng.cat2.view(0), co, B, H, W, 1, 0, tables=eng.t_up2, stats=st, cnt=h * w_, eps=1e-5, act=1)
-        got = get(eng.cat2, co, 0); post = O.upsample_aa
-    else:
-        be.gather(Zf.view(), eng.y4.view(), co, B, H, W, 3, 1, stats=st, cnt=h * w_, eps=1e-5, act=1)
-        got = get(eng.y4, co); post = lambda t: t
-    zz = z.clone().requires_grad_(True)
-    a = torch.relu(O.instance_norm(zz))
-    out_ref = post(a)
-    e = rel(got, out_ref)
-    print(name, "IN+ReLU+stencil fwd", e); assert e < TOL
-    if name == "down2":       # reflect ring of the bottleneck input
-        full = get(eng.X[0], co, full=True)
-        assert rel(full, F.pad(got, (1, 1, 1, 1), mode="reflect")) < 1e-6
-    if name == "up2":
-        full = get(eng.y4, co, full=True)
-        assert rel(full, F.pad(got, (3, 3, 3, 3), mode="reflect")) < 1e-6
-    # ---- backward of the same group: stencil^T (or reflection fold), IN+ReLU^T
-    key = {"down1": "x1", "down2": "x2", "up1": "up2_up", "up2": "up2"}[name]
-    g_out = r16(scaled(G[key]))
-    if name == "down1":
-        ga, gb = r16(g_out * 0.5), r16(g_out * 0.5)
-        put(eng.Gcat1, ga, 256); put(eng.Gx1, gb)
-        be.gather(eng.Gcat1.view(256), eng.g1.view(), co, B, H, W, 0, 0, tables=eng.t_down1_T, src2=eng.Gx1.view())
-        gfr = eng.g1; g_out = ga + gb
-    elif name == "down2":
-        gfr = eng.g2
-        cur = eng.dOut[0]
-        put(cur, g_out)
-        be.gather(cur.view(), gfr.view(), co, B, H2, W2, 0, 0, tables=eng.t_down2_T)
-    elif name == "up1":
-        put(eng.Gcat2, g_out, 0)
-        gfr = eng.g3
-        be.gather(eng.Gcat2.view(0), gfr.view(), co, B, H2, W2, 0, 0, tables=eng.t_up2_T)
-    else:
-        # gradient w.r.t. the reflect-padded y4 arrives over the whole frame; ReflectionPad2d(3)^T folds it
-        gp = r16(F.pad(g_out, (3, 3, 3, 3)) + 0.3 * scaled(torch.randn(B, co, H + 6, W + 6, generator=torch.Generator().manual_seed(5))))
-        put_full(eng.G4, gp)
-        be.fold_inplace(eng.G4.t, 0, co, B, H, W, 3)
-        gfr = eng.G4
-        y = torch.zeros(B, co, H, W, requires_grad=True)
-        (g_out,) = torch.autograd.grad(F.pad(y, (3, 3, 3, 3), mode="reflect"), y, gp)
-    (g_ref,) = torch.autograd.grad(out_ref, a, g_out, retain_graph=True) if name != "up2" else (g_out,)
-    e = rel(get(gfr, co), g_ref)
-    print(name, "stencil^T / fold", e); assert e < TOL
-    g_in = r16(get(gfr, co))              # what the plan hands to the InstanceNorm backward
-    dZ = {"down1": eng.dZ1, "down2": eng.dZ2, "up1": eng.dZ3, "up2": eng.dZ4}[name]
-    be.in_bwd(Zf.view(), gfr.view(), dZ.view(), co, B, h, w_, stats=st, cnt=h * w_, eps=1e-5, act=1, bsum=eng.bsum)
-    (dz_ref,) = torch.autograd.grad(a, zz, g_in)
-    e = rel(get(dZ, co), dz_ref)
-    print(name, "IN+ReLU bwd", e); assert e < TOL
-    # ---- conv data / weight gradients
-    dz = r16(dz_ref)
-    put(dZ, dz)
-    zero_wgrad(eng)
-    op.wgrad(dZ.t, fin.t, off, fin.rows); be.flush_sums()
-    Gout = {"down1": eng.Gx0, "down2": eng.Gx1, "up1": eng.Gcat1, "up2": eng.Gcat2}[name]
-    op.dgrad(dZ.t, Gout.t)
-    _, gx, gw = conv_local(x, wt, dz, pad=1)
-    e = rel(eng.arena.view(wname, eng.arena.grad), gw)
-    print(name, "wgrad", e); assert e < TOL
-    _, gx16, _ = conv_local(x, r16(wt), dz, pad=1)
-    e = rel(get(Gout, ci), gx16)
-    print(name, "dgrad", e); assert e < TOL
+    T.check_3x3_zero_pad_layers(ctx, name)
 
 
 @pytest.mark.parametrize("b", [0, 8])
 def test_resnet_block(ctx, b):
-    """ResnetBlock (irc:362-418) at 256 ch, 64 x 64: both convs forward, cluster InstanceNorm forward (stats + apply +
-    residual + reflect ring), and the whole backward chain with the reflection folds deferred to the consumer"""
-    O, eng, be = ctx.O, ctx.eng, ctx.be
-    A, G = ctx.act, ctx.grad
-    H4, W4 = H // 4, W // 4
-    xin = r16(A["x2"] if b == 0 else A[f"res{b - 1}"])
-    w1, w2 = ctx.p[f"resblocks.{b}.conv_block.1.weight"], ctx.p[f"resblocks.{b}.conv_block.5.weight"]
-    c1, c2 = eng.res[b]
-    put(eng.X[b], xin, ring="reflect")
-    c1.fwd(eng.X[b].t, 0, eng.Za[b].t)
-    za_ref, _, _ = conv_local(xin, r16(w1), torch.zeros(B, 256, H4, W4), reflect=1)
-    e = rel(get(eng.Za[b], 256), za_ref); print("res conv1 fwd", e); assert e < TOL
-    za = r16(za_ref); put(eng.Za[b], za)
-    be.in_apply(eng.Za[b].view(), eng.Hh[b].view(), 256, B, H4, W4, 1, 1, eng.sta[b], eps=1e-5, act=1)
-    zza = za.clone().requires_grad_(True)
-    hh = torch.relu(O.instance_norm(zza))
-    e = rel(get(eng.Hh[b], 256, full=True), F.pad(hh.detach(), (1, 1, 1, 1), mode="reflect")); print("res IN+ReLU (ring incl.)", e); assert e < TOL
-    h16 = r16(hh); put(eng.Hh[b], h16, ring="reflect")
-    c2.fwd(eng.Hh[b].t, 0, eng.Zb[b].t)
-    zb_ref, _, _ = conv_local(h16, r16(w2), torch.zeros(B, 256, H4, W4), reflect=1)
-    e = rel(get(eng.Zb[b], 256), zb_ref); print("res conv2 fwd", e); assert e < TOL
-    zb = r16(zb_ref); put(eng.Zb[b], zb)
-    be.in_apply(eng.Zb[b].view(), eng.X[b + 1].view(), 256, B, H4, W4, 1, 1, eng.stb[b], eps=1e-5, act=0, res=eng.X[b].view())
-    zzb = zb.clone().requires_grad_(True)
-    nb_ = O.instance_norm(zzb)
-    e = rel(get(eng.X[b + 1], 256), xin + nb_.detach()); print("res IN + residual", e); assert e < TOL
-    # ---- backward: gradient w.r.t. the padded block output arrives with its ring (unfolded)
-    gen = torch.Generator().manual_seed(40 + b)
-    g_int = scaled(G[f"res{b}"])
-    gp = r16(F.pad(g_int, (1, 1, 1, 1)) + 0.2 * torch.randn(B, 256, H4 + 2, W4 + 2, generator=gen))
-    cur, nxt = eng.dOut[0], eng.dOut[1]
-    put_full(cur, gp)
-    y = torch.zeros(B, 256, H4, W4, requires_grad=True)
-    (g_fold,) = torch.autograd.grad(F.pad(y, (1, 1, 1, 1), mode="reflect"), y, gp)
-    g_fold = r16(g_fold)          # the fused kernel rounds the folded gradient to bf16 like the stand-alone fold does
-    be.in_bwd(eng.Zb[b].view(), cur.view(), eng.dZb.view(), 256, B, H4, W4, stats=eng.stb[b], cnt=H4 * W4, eps=1e-5, act=0, bsum=eng.bsum, fold_pad=1)
-    (dzb_ref,) = torch.autograd.grad(nb_, zzb, g_fold)
-    e = rel(get(eng.dZb, 256), dzb_ref); print("res IN bwd + fold", e); assert e < TOL
-    dzb = r16(dzb_ref); put(eng.dZb, dzb)
-    zero_wgrad(eng)
-    c2.wgrad(eng.dZb.t, eng.Hh[b].t, 0, eng.dZb.rows)
-    c2.dgrad(eng.dZb.t, eng.Gh.t)
-    hp = F.pad(h16, (1, 1, 1, 1), mode="reflect").requires_grad_(True)
-    wv = w2.clone().requires_grad_(True)
-    zloc = F.conv2d(hp, wv)
-    (gw2,) = torch.autograd.grad(zloc, wv, dzb, retain_graph=True)
-    (ghp,) = torch.autograd.grad(F.conv2d(hp, r16(w2)), hp, dzb)
-    e = rel(get(eng.Gh, 256, full=True), ghp); print("res conv2 dgrad (frame)", e); assert e < TOL
-    gh16 = r16(get(eng.Gh, 256, full=True))
-    (gh_fold,) = torch.autograd.grad(F.pad(y, (1, 1, 1, 1), mode="reflect"), y, gh16)
-    gh_fold = r16(gh_fold)
-    be.in_bwd(eng.Za[b].view(), eng.Gh.view(), eng.dZa.view(), 256, B, H4, W4, stats=eng.sta[b], cnt=H4 * W4, eps=1e-5, act=1, bsum=eng.bsum, fold_pad=1)
-    (dza_ref,) = torch.autograd.grad(hh, zza, gh_fold)
-    e = rel(get(eng.dZa, 256), dza_ref); print("res IN+ReLU bwd + fold", e); assert e < TOL
-    dza = r16(dza_ref); put(eng.dZa, dza)
-    c1.wgrad(eng.dZa.t, eng.X[b].t, 0, eng.dZa.rows)
-    from irc_b200._native import View
-    c1.dgrad(eng.dZa.t, nxt.t, addend=View(cur.t, 0, 0, 0))
-    be.flush_sums()
-    xp = F.pad(xin, (1, 1, 1, 1), mode="reflect").requires_grad_(True)
-    w1v = w1.clone().requires_grad_(True)
-    (gw1,) = torch.autograd.grad(F.conv2d(xp, w1v), w1v, dza)
-    (gxp,) = torch.autograd.grad(F.conv2d(xp, r16(w1)), xp, dza)
-    e = rel(eng.arena.view(f"resblocks.{b}.conv_block.5.weight", eng.arena.grad), gw2); print("res conv2 wgrad", e); assert e < TOL
-    e = rel(eng.arena.view(f"resblocks.{b}.conv_block.1.weight", eng.arena.grad), gw1); print("res conv1 wgrad", e); assert e < TOL
-    e = rel(get(nxt, 256, full=True), gxp + gp); print("res conv1 dgrad + residual gradient (frame)", e); assert e < TOL
-    # leaving the blocks: one in-place fold of the residual-stream gradient
-    nx16 = r16(get(nxt, 256, full=True))
-    be.fold_inplace(nxt.t, 0, 256, B, H4, W4, 1)
-    (fold_ref,) = torch.autograd.grad(F.pad(y, (1, 1, 1, 1), mode="reflect"), y, nx16)
-    e = rel(get(nxt, 256), fold_ref); print("fold_inplace(1)", e); assert e < TOL
+    T.check_resnet_block(ctx, b)
 
 
 def test_upsample_into_concat_and_transpose(ctx):
-    """up1_up (irc:500-501): UpsampleAA of the bottleneck output into cat1[0:256), and its transpose"""
-    O, eng, be = ctx.O, ctx.eng, ctx.be
-    H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
-    x = r16(ctx.act["res8"])
-    put(eng.X[9], x, ring="reflect")
-    be.gather(eng.X[9].view(), eng.cat1.view(0), 256, B, H2, W2, 1, 0, tables=eng.t_up1)
-    xx = x.clone().requires_grad_(True)
-    up = O.upsample_aa(xx)
-    e = rel(get(eng.cat1, 256, 0), up); print("UpsampleAA 64->128", e); assert e < TOL
-    g = r16(scaled(ctx.grad["up1_up"]))
-    put(eng.Gcat1, g, 0)
-    be.gather(eng.Gcat1.view(0), eng.dOut[0].view(), 256, B, H4, W4, 1, 0, tables=eng.t_up1_T)
-    (gr,) = torch.autograd.grad(up, xx, g)
-    e = rel(get(eng.dOut[0], 256), gr); print("UpsampleAA^T", e); assert e < TOL
+    T.check_upsample_into_concat_and_transpose(ctx)
 
 
 def test_outc_7x7_tanh(ctx):
-    """outc.1 + tanh (irc:527-531): forward, tanh' + bias gradient, weight and data gradients"""
-    O, eng, be = ctx.O, ctx.eng, ctx.be
-    w, bias = ctx.p["outc.1.weight"], ctx.p["outc.1.bias"]
-    x = r16(ctx.act["up2"])
-    put(eng.y4, x, ring="reflect")
-    eng.outc.fwd(eng.y4.t, 0, eng.P)
-    be.tap_reduce(eng.P, eng.outc_shifts, 3, B, H, W, eng.y4.hp, eng.y4.wp, 3, 3, eng.outc.bias(), 3, eng.fake)
-    xx = x.clone().requires_grad_(True)
-    wv = r16(w).requires_grad_(True)
-    bv = bias.clone().requires_grad_(True)
-    out = torch.tanh(F.conv2d(F.pad(xx, (3, 3, 3, 3), mode="reflect"), wv, bv))
-    e = rel(eng.fake, out); print("outc fwd + tanh", e); assert e < 2e-3          # fp32 accumulate, fp32 output
-    g = scaled(ctx.grad["out"]).contiguous()
-    zero_wgrad(eng)
-    # tanh' uses the engine's own output (what the plan does); feed it the oracle's so that both sides see one value
-    eng.fake.copy_(out.detach())
-    be.tap_expand(g.cuda(), eng.fake, eng.outc_shifts, 3, B, H, W, eng.y4.hp, eng.y4.wp, 3, 3, eng.E_out,
-                  dbias=eng.arena.view("outc.1.bias", eng.arena.grad))
-    eng.outc.wgrad(eng.E_out, eng.y4.t, 0, eng.y4.rows)
-    eng.outc.dgrad(eng.E_out, eng.G4.t)
-    be.flush_sums()
-    xp = F.pad(x, (3, 3, 3, 3), mode="reflect").requires_grad_(True)
-    w32 = w.clone().requires_grad_(True)
-    o2 = torch.tanh(F.conv2d(xp, w32, bv))
-    gw, gb = torch.autograd.grad(o2, (w32, bv), g, retain_graph=True)
-    (gxp,) = torch.autograd.grad(torch.tanh(F.conv2d(xp, r16(w), bias)), xp, g)
-    e = rel(eng.arena.view("outc.1.bias", eng.arena.grad), gb); print("outc bias grad", e); assert e < TOL
-    e = rel(eng.arena.view("outc.1.weight", eng.arena.grad), gw); print("outc wgrad", e); assert e < TOL
-    e = rel(get(eng.G4, 64, full=True), gxp); print("outc dgrad (frame)", e); assert e < TOL
+    T.check_outc_7x7_tanh(ctx)
