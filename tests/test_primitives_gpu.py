@@ -421,9 +421,10 @@ def test_losses_vs_reference_golden(bes):
     assert torch.equal(d, torch.sign(a - b))
 
 
-@pytest.mark.parametrize("h,w", [(20, 32), (17, 30), (64, 260)])
+@pytest.mark.parametrize("h,w", [(20, 32), (17, 30), (64, 260), (70, 640), (5, 132), (1, 8)])
 def test_pixel_loss_paths(bes, h, w):
-    """fused L1 + TV (irc:686-694, :1664): the float4 kernel (W % 4 == 0) and the scalar one against torch autograd"""
+    """fused L1 + TV (irc:686-694, :1664): the streaming kernel (W % 4 == 0: several column tiles, strips that do not divide H,
+    a single row) and the scalar one against torch autograd; TV alone (no target) through the same kernel"""
     be = bes[0]
     g = gen(9)
     a = torch.randn(3, 3, h, w, device="cuda", generator=g); b = torch.randn(3, 3, h, w, device="cuda", generator=g)
@@ -435,6 +436,12 @@ def test_pixel_loss_paths(bes, h, w):
     for got, ref in zip(sums.tolist(), (l1.item(), tvv.item(), tvh.item())):
         assert abs(got - ref) <= 1e-4 * abs(ref)
     close(d, x.grad, 1e-6, "pixel_loss grad")
+    x2 = a.clone().requires_grad_(True)
+    (0.3 * (x2[:, :, 1:] - x2[:, :, :-1]).abs().sum() + 0.2 * (x2[:, :, :, 1:] - x2[:, :, :, :-1]).abs().sum()).backward()
+    sums2 = torch.zeros(3, device="cuda"); d2 = torch.zeros_like(a)
+    be.pixel_loss(a, None, 0.0, 0.3, 0.2, sums2, d2)
+    assert sums2[0].item() == 0 and abs(sums2[1].item() - tvv.item()) <= 1e-4 * max(abs(tvv.item()), 1e-6)
+    close(d2, x2.grad, 1e-6, "tv grad") if h > 1 or w > 1 else None
 
 
 def test_hinge_featl1(bes):
@@ -461,6 +468,18 @@ def test_quantize_metrics_bit_exact(bes):
     psnr = -10.0 * np.log10(mse + 1e-12)
     for got, ref in zip((mae, mse, psnr), gold["metrics"]):
         assert abs(got - ref) < 5e-7 * max(1, abs(ref)), (got, ref)
+    # batched, odd pixel count (scalar kernel) and 4-pixel vector kernel against the oracle's numpy formulas
+    import irc_oracle as O
+    for (n, hh, ww) in ((3, 12, 20), (2, 7, 9)):
+        f = torch.tanh(torch.randn(n, 3, hh, ww, device="cuda", generator=gen(4))) * 1.2
+        t = torch.rand(n, 3, hh, ww, device="cuda", generator=gen(5))
+        u = torch.zeros(n, hh, ww, 3, device="cuda", dtype=torch.uint8); sm = torch.zeros(n, 2, device="cuda", dtype=torch.float64)
+        be.quantize_metrics(f, t, u, sm)
+        for i in range(n):
+            q = O.quantize_u8(f[i].cpu())
+            assert np.array_equal(u[i].cpu().numpy(), q)
+            m = O.compute_metrics(q.astype(np.float32) / 255.0, t[i].permute(1, 2, 0).cpu().numpy())
+            assert abs(sm[i, 0].item() / (3 * hh * ww) - m[0]) < 1e-6 and abs(sm[i, 1].item() / (3 * hh * ww) - m[1]) < 1e-6
     probe = torch.full((1, 3, 4, 4), 254.87 / 255.0 * 2 - 1, device="cuda")
     u = torch.zeros(1, 4, 4, 3, device="cuda", dtype=torch.uint8)
     be.quantize_metrics(probe, None, u, None)
