@@ -284,9 +284,11 @@ class CudaBackend:
         self.batch_sums = os.environ.get("IRC_BATCH_SUMS", "1") != "0"      # one launch for all split-K weight-gradient reductions
         self._pending, self._sum_tables = [], {}
         self._stats_ws = {}
-        # InstanceNorm statistics in the conv epilogue for layers with at least this many reduction elements per output (below it
-        # the epilogue is on the critical path of the tile loop): IRC_STATS_EPI=0 all layers, =1000000 none
-        self.stats_epilogue_min_k = int(os.environ.get("IRC_STATS_EPI", "0"))
+        # InstanceNorm statistics in the conv epilogue for layers with at least this many reduction elements per output.  Measured
+        # (profiles/): performance-neutral at K >= 1024 (the column sums cost the epilogue about what the separate pass cost),
+        # a loss below it (down1, K = 576: the epilogue is on the critical path, +0.13 ms for a 0.07 ms pass).  IRC_STATS_EPI=0
+        # all layers, =1000000 none
+        self.stats_epilogue_min_k = int(os.environ.get("IRC_STATS_EPI", "1024"))
         self.fused_outc = os.environ.get("IRC_FUSED_OUTC", "1") != "0"      # tap reduction + bias + tanh in the GEMM epilogue of the output head
         self.gather_mode = os.environ.get("IRC_GATHER", "auto")     # lean | tiled | generic (stencil gather kernel choice)
         self.conv_epilogue_direct = int(os.environ.get("IRC_EPI_DIRECT", "0"))

@@ -450,6 +450,146 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constan
 
 
 // ------------------------------------------------------------------------------------
+// conv_gemm on CTA pairs: tcgen05.mma.cta_group::2, tile = 256 rows x bn columns per pair
+// ------------------------------------------------------------------------------------
+// Same roles and the same epilogue as conv_gemm_kernel<1>; per pipeline stage each CTA stages its own 128 rows of A and HALF of
+// the weight tile (bn / 2 rows of B), so a stage costs 16 KB + bn * 64 B instead of 16 KB + bn * 128 B: a third less TMA / L2
+// traffic at bn = 256 and room for more stages.  Barrier protocol (all barriers live at the same offset in both CTAs):
+//   full[s]   (leader's; count 1 + tx)   both CTAs' TMA loads report their bytes to the LEADER's barrier
+//   empty[s]  (one per CTA; count 1)     tcgen05.commit multicast to both CTAs when the MMAs that read stage s are done
+//   tfull[a]  (one per CTA; count 1)     commit multicast: accumulator a complete (each CTA drains its own 128 TMEM lanes)
+//   tempty[a] (leader's; count 16)       the 8 epilogue warps of BOTH CTAs arrive (the peer's remotely)
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+    irc::pdl_prologue();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int stage_a = kBM * 128;
+    const int half_bn = p.bn >> 1;
+    const int stage_b = half_bn * 128;
+    const int stage_bytes = stage_a + stage_b;
+    const int S = p.stages;
+    uint64_t* bars = (uint64_t*)(smem + (size_t)S * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tfull = bars + 2 * S;
+    uint64_t* tempty = bars + 2 * S + 2;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
+    uint8_t* stg = smem + (size_t)S * stage_bytes + 1024;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const long long m_tiles = (p.rows + 2 * kBM - 1) / (2 * kBM);
+    const long long total_tiles = m_tiles * p.n_tiles;
+    const uint32_t acc_cols = (uint32_t)p.bn;
+    const int num_kb = p.ntaps * p.k_chunks;
+    const long long pair0 = blockIdx.x >> 1, pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (p.tma_store) tma_prefetch_desc(&tmOut);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 16); }
+        fence_barrier_init();
+    }
+    __shared__ __align__(16) float sbias[512];
+    if (p.bias) for (int i = threadIdx.x; i < p.n_out; i += blockDim.x) sbias[i] = p.bias[i];
+    if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // both CTAs' barriers are initialised before any remote arrival / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        int stage = 0; uint32_t phase = 0;
+        for (long long tile = pair0; tile < total_tiles; tile += pairs) {
+            const long long row0 = (tile / p.n_tiles) * (2 * kBM) + (long long)rank * kBM;
+            const int n0 = (int)(tile % p.n_tiles) * p.bn + (int)rank * half_bn;
+            for (int t = 0; t < p.ntaps; ++t) {
+                const long long arow = row0 + p.taps[t];
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (elect_one()) {
+                        const uint32_t fb = mapa_u32(smem_u32(&full[stage]), 0);
+                        if (leader) mbar_expect_tx(&full[stage], 2 * stage_bytes);
+                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                        tma_load_2d_pair(sa, &tmA, fb, p.a_chan_off + kc * kBK, (int)arow);
+                        tma_load_2d_pair(sa + stage_a, &tmB, fb, (t * p.k_chunks + kc) * kBK, n0);
+                    }
+                    __syncwarp();
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            const uint32_t idesc = umma_idesc_bf16(2 * kBM, p.bn, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (long long tile = pair0; tile < total_tiles; tile += pairs) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t adesc = umma_desc_sw128(sa, 16);
+                    const uint64_t bdesc = umma_desc_sw128(sa + stage_a, 16);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k)
+                            umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_pair(&empty[stage]);
+                    }
+                    __syncwarp();
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+                if (elect_one()) umma_commit_pair(&tfull[acc]);
+                __syncwarp();
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (both CTAs: own 128 accumulator rows) =====================
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int r_in_tile = quarter * 32 + lane;
+        EpiCtx e;
+        e.slope_eff = p.act == 1 ? 0.f : (p.act == 2 ? p.slope : 1.f);
+        e.sbias = p.bias ? sbias : nullptr;
+        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t stg_iter = 0;
+        const bool store_thread = warp == 2 && lane == 0;
+        const uint32_t tempty_leader[2] = {mapa_u32(smem_u32(&tempty[0]), 0), mapa_u32(smem_u32(&tempty[1]), 0)};
+        for (long long tile = pair0; tile < total_tiles; tile += pairs) {
+            const int n0 = (int)(tile % p.n_tiles) * p.bn;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols;
+            const long long srow0 = (tile / p.n_tiles) * (2 * kBM) + (long long)rank * kBM;
+            if (p.tma_store) epilogue_subtile_staged(p, e, &tmOut, srow0, r_in_tile, n0, taddr, half, stg, stg_iter, store_thread);
+            else epilogue_subtile(p, e, srow0 + r_in_tile, n0, taddr, half);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tempty_leader[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    if (p.tma_store && warp == 2 && lane == 0) bulk_wait_group<0>();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // the peer's shared memory and TMEM are read by the leader's MMAs until its last commit
+    if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------
 // conv_gemm with A-tile reuse across horizontal taps ("tap runs")
 // ------------------------------------------------------------------------------------
 // Taps whose row shifts are consecutive integers (the kw taps of one kernel row) read the same pixels shifted by one
@@ -1114,6 +1254,41 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
         const long long tiles1 = ((a->a_rows + kBM - 1) / kBM) * p.n_tiles;
         irc::launch<1>(conv_gemm_runs_kernel, (int)(tiles1 < sms ? tiles1 : sms), kThreads, smem2, (cudaStream_t)stream, tmA2, tmB, q, rp);
         return irc_check_launch("irc_conv_gemm(runs)");
+    }
+    // CTA pairs (cta_group::2): IRC_CONV_PAIR=1 all eligible launches, =0 never, default: auto (see pair_auto)
+    static int pair_mode = -2;
+    if (pair_mode == -2) { const char* e = getenv("IRC_CONV_PAIR"); pair_mode = e ? atoi(e) : -1; }
+    const bool pair_ok = !tapsum && (bn == 64 || bn == 128 || bn == 256) && a->mt <= 1 && sms >= 2;
+    // measured per layer (profiles/gemm_breakdown_r2_pair.csv): pairs win where the weight tile is wide and the reduction deep
+    // (ResNet blocks 0.84 -> 0.93 of the sustained peak, VGG conv3_x 0.91 -> 1.00, up1 0.77 -> 0.82); the narrow N = 64 layers
+    // keep the single-CTA kernel, whose several row sub-tiles per weight stage serve them better
+    const int kred = a->ntaps * a->cin;
+    const bool pair_auto = ((bn == 256 && kred >= 1024) || (bn == 128 && kred >= 2048)) && a->a_rows >= (long long)sms * 128;
+    if (pair_ok && (pair_mode == 1 || (pair_mode == -1 && pair_auto))) {
+        ConvParams q = p; q.mt = 1; q.nbuf = 2; q.tile_stride = 2 * kBM; q.row_bias = 0;
+        CUtensorMap tmA1, tmBh;
+        rc = make_map(&tmA1, a->a, a->a_rows, a->a_ld, kBM);
+        if (rc) return rc;
+        rc = make_map(&tmBh, a->w, a->n_out, a->ntaps * a->cin, bn / 2);
+        if (rc) return rc;
+        const int sb2 = kBM * 128 + (bn / 2) * 128;
+        q.nstg = 2;
+        const int stg2 = q.tma_store ? q.nstg * kBM * 128 + 1024 : 0;
+        int st2 = (kMaxSmem - kStatic - 2048 - stg2) / sb2;
+        if (st2 > 8) st2 = 8;
+        q.stages = st2;
+        const size_t smem2 = (size_t)st2 * sb2 + 2048 + stg2;
+        static bool attr2 = false;
+        if (!attr2) {
+            if (cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 2048) != cudaSuccess)
+                return irc_check_launch("cudaFuncSetAttribute(conv_gemm_pair)");
+            attr2 = true;
+        }
+        const long long tiles2 = ((a->a_rows + 2 * kBM - 1) / (2 * kBM)) * q.n_tiles;
+        const long long max_pairs = sms / 2;
+        const unsigned grid2 = 2u * (unsigned)(tiles2 < max_pairs ? tiles2 : max_pairs);
+        irc::launch_cluster(conv_gemm_pair_kernel, grid2, kConvThreads, smem2, (cudaStream_t)stream, 2, tmOut, tmA1, tmBh, q);
+        return irc_check_launch("irc_conv_gemm(pair)");
     }
     if (mt == 1) irc::launch<1>(conv_gemm_kernel<1>, grid, kConvThreads, smem, (cudaStream_t)stream, tmOut, tmA, tmB, p);
     else if (mt == 2) irc::launch<1>(conv_gemm_kernel<2>, grid, kConvThreads, smem, (cudaStream_t)stream, tmOut, tmA, tmB, p);

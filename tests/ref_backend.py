@@ -90,7 +90,7 @@ class RefBackend:
         return acc
 
     # ------------------------------------------------------------------ GEMMs
-    stats_epilogue_min_k = 0
+    stats_epilogue_min_k = 1024
     fused_outc = True
 
     def conv_gemm(self, a, a_chan_off, cin, taps, w, n_out, out, out_chan_off=0, bias=None, act=0, slope=0.0,
