@@ -900,6 +900,150 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// Weight-gradient GEMM on CTA pairs (cta_group::2, M = 256): CTA r of a pair stages output-gradient channels
+// [256 mt + 128 r, +128) (its own A tile) and HALF of the bn input channels of every tap's B tile; each CTA ends up with its 128
+// accumulator rows in its own TMEM.  Same barrier protocol as conv_gemm_pair_kernel.  Used when the layer has >= 256 output
+// channels (ResNet blocks, down2, PatchGAN model.5 / model.8).
+template <int TPC>
+__global__ void __launch_bounds__(kThreads, 1)
+tn_gemm_cta2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnParams p) {
+    irc::pdl_prologue();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int stage_a = kBK * 128 * 2;             // 2 groups of 64 channels x 64 rows (this CTA's 128 channels)
+    const int groups_h = p.bn / 128;               // 64-channel groups of this CTA's half of the B tile
+    const int tile_b = kBK * 128 * groups_h;
+    const int stage_bytes = stage_a + TPC * tile_b;
+    const int S = p.stages;
+    uint64_t* bars = (uint64_t*)(smem + (size_t)S * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tfull = bars + 2 * S;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    int w = blockIdx.x >> 1;
+    const int n_tile = w % p.n_tiles; w /= p.n_tiles;
+    const int m_tile = w % p.m_tiles; w /= p.m_tiles;          // 256-channel tiles
+    const int group = w % p.groups; w /= p.groups;
+    const int split = w;
+    const int tap0 = group * TPC;
+    const int ntap = (p.ntaps - tap0) < TPC ? (p.ntaps - tap0) : TPC;
+    const long long kb_total = (p.k_rows + kBK - 1) / kBK;
+    const long long kb_per = (kb_total + p.splits - 1) / p.splits;
+    const long long kb_begin = (long long)split * kb_per;
+    long long kb_end = kb_begin + kb_per; if (kb_end > kb_total) kb_end = kb_total;
+    const long long my_kb = kb_end > kb_begin ? kb_end - kb_begin : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t bytes = 2u * (uint32_t)(stage_a + ntap * tile_b);
+        const int a_c0 = p.a_chan_off + m_tile * 2 * kBM + (int)rank * kBM;
+        const int b_c0 = p.b_chan_off + n_tile * p.bn + (int)rank * (p.bn >> 1);
+        for (long long kb = kb_begin; kb < kb_begin + my_kb; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (elect_one()) {
+                const uint32_t fb = mapa_u32(smem_u32(&full[stage]), 0);
+                if (leader) mbar_expect_tx(&full[stage], bytes);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                const long long r0 = kb * kBK;
+                for (int g = 0; g < 2; ++g)
+                    tma_load_2d_pair(sa + g * (kBK * 128), &tmA, fb, a_c0 + g * 64, (int)(r0 + p.a_shift[tap0]));
+                for (int t = 0; t < ntap; ++t)
+                    for (int g = 0; g < groups_h; ++g)
+                        tma_load_2d_pair(sa + stage_a + t * tile_b + g * (kBK * 128), &tmB, fb, b_c0 + g * 64, (int)(r0 + p.b_shift[tap0 + t]));
+            }
+            __syncwarp();
+            if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            const uint32_t idesc = umma_idesc_bf16(2 * kBM, p.bn, 1, 1);
+            int stage = 0; uint32_t phase = 0;
+            for (long long kb = 0; kb < my_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint64_t adesc = umma_desc_sw128(sa, kBK * 128);
+                const uint32_t accum = kb != 0;
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+#pragma unroll
+                        for (int t = 0; t < TPC; ++t) {
+                            if (t < ntap) {
+                                const uint64_t bdesc = umma_desc_sw128(sa + stage_a + t * tile_b, kBK * 128);
+                                umma_bf16_pair(tmem_base + (uint32_t)(t * p.bn), adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, k == 0 ? accum : 1u);
+                            }
+                        }
+                    }
+                    umma_commit_pair(&empty[stage]);
+                }
+                __syncwarp();
+                if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) umma_commit_pair(tfull);
+            __syncwarp();
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int m = m_tile * 2 * kBM + (int)rank * kBM + quarter * 32 + lane;
+        if (my_kb > 0) {
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+        }
+        for (int t = 0; t < ntap; ++t) {
+            float* obase = p.out + (long long)split * p.out_split_stride + (long long)(tap0 + t) * p.out_tap_stride + (long long)m * p.out_m_stride;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * p.bn);
+            for (int c0 = 0; c0 < p.bn; c0 += 32) {
+                uint32_t r[32];
+                if (my_kb > 0) {
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+                if (m < p.m) {
+                    const int nb = n_tile * p.bn + c0;
+                    if (p.out_n_stride == 1 && nb + 32 <= p.n && ((((uintptr_t)(obase + nb)) & 15) == 0)) {
+                        float4* o4 = reinterpret_cast<float4*>(obase + nb);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            o4[g] = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]), __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = nb + j;
+                            if (n < p.n) obase[(long long)n * p.out_n_stride] = __uint_as_float(r[j]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_pair(tmem_base, p.tmem_cols);
+}
+
 // Weight gradients of layers with at most 64 output channels (up2_conv, inc, model.0): a 64-row A tile would leave half of
 // every M=128 MMA idle.  Since  dW_t[m][n] = sum_q dz[q][m] x[q + s_t][n] = sum_q' dz[q' - s_t][m] x[q'][n],  the shift can be
 // put on dz instead of x: the two 64-channel groups of one A tile are then loaded at the (negated) shifts of TWO taps, the
@@ -1056,6 +1200,21 @@ int auto_pairs(int bn, int ntaps) {
 bool tn_pair_mode(int m, int ntaps, bool zero_a_shift) { return m <= 64 && ntaps >= 2 && zero_a_shift; }
 
 bool g_attr_conv = false, g_attr_tn = false, g_attr_runs = false;
+
+// taps per CTA pair of the cta_group::2 weight-gradient GEMM.  Measured (profiles/gemm_breakdown_r2_tnpair*.csv): one tap per
+// pair wins (ResNet blocks 0.81 -> 0.86 of the sustained peak, model.8 0.80 -> 0.84); two taps per pair halve the number of
+// pairs per split, so the one-wave rule doubles the split count and the partial traffic (0.72).  IRC_TN_PAIR=2 forces two.
+int tn_pair_taps(int bn, int ntaps) {
+    const char* e = getenv("IRC_TN_PAIR");
+    if (e && atoi(e) == 2) return (2 * bn <= 512 && ntaps >= 2) ? 2 : 1;
+    return 1;
+}
+// pairs pay off for 256-wide tiles; with 128 input channels (down2) the single-CTA kernel with several taps per CTA is faster
+bool tn_pair_shape(int m, int n, int bn, bool same_a) {
+    const char* e = getenv("IRC_TN_PAIR");
+    if (e && atoi(e) == 0) return false;
+    return same_a && m % (2 * kBM) == 0 && bn == 256 && n % 256 == 0;
+}
 
 // taps per CTA of the weight-gradient GEMM: as many independent accumulation chains as keep >= 4 pipeline stages
 // (16 KB + tpc * bn * 128 B per stage), preferring an exact divisor of the tap count
@@ -1357,6 +1516,33 @@ extern "C" int irc_tn_gemm(const irc_tn_gemm_args* a, void* stream) {
     }
     if (!(tpc == 1 || tpc == 2 || tpc == 3 || tpc == 4 || tpc == 8) || tpc * bn > 512 || (tpc > 1 && !same_a))
         return irc_set_error(IRC_ERR_BAD_ARG, "irc_tn_gemm: unsupported taps-per-CTA %d for tile width %d", tpc, bn);
+    // CTA pairs (cta_group::2) for layers with >= 256 output channels and a tile width that splits into two 64-channel-group halves
+    static int tn_pair_mode = -2;
+    if (tn_pair_mode == -2) { const char* e = getenv("IRC_TN_PAIR"); tn_pair_mode = e ? atoi(e) : -1; }
+    if (tn_pair_mode != 0 && a->tpc <= 0 && tn_pair_shape(a->m, a->n, bn, same_a) && irc_num_sms() >= 2) {
+        int tp = tn_pair_taps(bn, a->ntaps);
+        p.groups = (a->ntaps + tp - 1) / tp;
+        p.m_tiles = a->m / (2 * kBM);
+        int cols2 = 32; while (cols2 < tp * bn) cols2 <<= 1;
+        p.tmem_cols = cols2;
+        const int sb = kBK * 128 * 2 + tp * kBK * 128 * (bn / 128);
+        int st = (kMaxSmem - 2048) / sb;
+        if (st > 8) st = 8;
+        p.stages = st;
+        const size_t smem2 = (size_t)st * sb + 2048;
+        static bool attr2 = false;
+        if (!attr2) {
+            if (cudaFuncSetAttribute(tn_gemm_cta2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
+                cudaFuncSetAttribute(tn_gemm_cta2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess)
+                return irc_check_launch("cudaFuncSetAttribute(tn_gemm_cta2)");
+            attr2 = true;
+        }
+        const unsigned grid2 = 2u * (unsigned)((long long)p.m_tiles * p.n_tiles * p.groups * p.splits);
+        cudaStream_t st_ = (cudaStream_t)stream;
+        if (tp == 2) irc::launch_cluster(tn_gemm_cta2_kernel<2>, grid2, kThreads, smem2, st_, 2, tmA, tmB, p);
+        else irc::launch_cluster(tn_gemm_cta2_kernel<1>, grid2, kThreads, smem2, st_, 2, tmA, tmB, p);
+        return irc_check_launch("irc_tn_gemm(cta pair)");
+    }
     p.groups = (a->ntaps + tpc - 1) / tpc;
     int cols = 32; while (cols < tpc * bn) cols <<= 1;
     p.tmem_cols = cols;
@@ -1393,6 +1579,10 @@ extern "C" int irc_tn_gemm_ctas(int m, int n, int ntaps, int same_a_shift) {
     if (tn_pair_mode(m, ntaps, same_a_shift != 0) && !getenv("IRC_TN_NOPAIR")) {
         const int P = auto_pairs(bn, ntaps);
         return ((n + bn - 1) / bn) * (((ntaps + 1) / 2 + P - 1) / P);
+    }
+    if (tn_pair_shape(m, n, bn, same_a_shift != 0)) {
+        const int tp = tn_pair_taps(bn, ntaps);
+        return 2 * (m / (2 * kBM)) * (n / bn) * ((ntaps + tp - 1) / tp);       // CTAs (two per pair)
     }
     const int tpc = same_a_shift ? auto_tpc(bn, ntaps) : 1;
     return ((m + kBM - 1) / kBM) * ((n + bn - 1) / bn) * ((ntaps + tpc - 1) / tpc);
