@@ -75,6 +75,16 @@ typedef struct irc_conv_gemm_args {
     int tap_nshift, tap_nco, tap_H, tap_W, tap_hp, tap_wp, tap_oy, tap_ox, tap_act;
 } irc_conv_gemm_args;
 int irc_conv_gemm(const irc_conv_gemm_args* args, void* stream);
+/* nn.ConvTranspose2d(cin, cout, 3, stride=2, padding=1, output_padding=1) forward (the generator's up-sampling layers with
+ * no_antialias_up=True, irc:495-499 / :512-516) on a framed input with a ZERO ring: one stride-1 implicit GEMM with the four
+ * taps {0, 1, wp, wp + 1}; the 4 * cout output columns of input row q = (n, y, x) are the four sub-pixel phases of the output,
+ * column (a * 2 + b) * cout + co = output pixel (2y + a, 2x + b) (depth-to-space order; read it back with an irc_view whose
+ * s2d_c = cout).  w: bf16 [4 * cout][4 * cin] = (phase, co) x (tap dy * 2 + dx, ci) holding kernel element
+ * (a + 1 - 2 dy, b + 1 - 2 dx) of the (cin, cout, 3, 3) PyTorch weight, or zero when that index leaves [0, 2];
+ * bias4: fp32 [4 * cout] (bias repeated per phase) or NULL.  The data gradient is irc_conv_gemm with negated taps and the
+ * transposed operand, the weight gradient irc_tn_gemm - exactly as for a forward convolution. */
+int irc_convT2d_fwd(const void* x, long long rows, int x_ld, int x_chan_off, int cin, int wp, const void* w, int cout, const float* bias4,
+                    void* out, long long out_ld, int out_chan_off, void* stream);
 long long irc_conv_stats_workspace_floats(long long rows, int n_out);
 int irc_conv_stats_finalize(const float* part, const float* edge, int n_img, int rows_per_img, int n_out, float* stats, void* stream);
 
@@ -283,6 +293,8 @@ int irc_u8_to_pm1(const unsigned char* src, int n_img, int H, int W, int C, int 
  * step_count (device): optimizer steps taken so far; the bias corrections use *step_count + 1 and a second tiny launch
  * on the same stream advances it, so a captured CUDA graph replays correctly without host writes. */
 int irc_adam(float* p, const float* g, float* m, float* v, long long n, const double* hyper, long long* step_count, void* stream);
+/* dst[i] = map[i] >= 0 ? src[map[i]] : 0 in fp32 (per-phase copies of a transposed-conv bias for the GEMM epilogue). */
+int irc_gather_f32(const float* src, const int* map, long long n, float* dst, void* stream);
 /* dst[i] = bf16(map[i] >= 0 ? src[map[i]] : 0): OIHW fp32 parameters -> packed GEMM operands. */
 int irc_pack_bf16(const float* src, const int* map, long long n, void* dst, void* stream);
 /* dst[i] = sum_s src[s*split_stride + map[i]]: split weight-gradient partials -> OIHW fp32. */

@@ -21,7 +21,7 @@ EXPORTS = [
     "irc_in_stats", "irc_gather", "irc_in_apply_fused", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_in_bwd_fused", "irc_in_bwd_l2", "irc_maxpool2", "irc_maxpool2_bwd",
     "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
     "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics",
-    "irc_adam", "irc_accumulate", "irc_pack_bf16", "irc_gather_sum", "irc_gather_sum_multi", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
+    "irc_adam", "irc_accumulate", "irc_gather_f32", "irc_convT2d_fwd", "irc_pack_bf16", "irc_gather_sum", "irc_gather_sum_multi", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
     "irc_resize_area_u8", "irc_u8_to_pm1",
 ]
 
@@ -579,6 +579,10 @@ class CudaBackend:
     def accumulate(self, sums, coef, acc):
         assert sums.dtype == torch.float32 and coef.dtype == torch.float32 and acc.dtype == torch.float64 and coef.shape[1] == sums.numel() + 1
         check(self.L.irc_accumulate(_p(sums), sums.numel(), _p(coef), coef.shape[0], _p(acc), _stream())); self.launches += 1
+
+    def gather_f32(self, src, map_, dst):
+        assert src.dtype == torch.float32 and dst.dtype == torch.float32 and map_.dtype == torch.int32 and map_.numel() == dst.numel()
+        check(self.L.irc_gather_f32(_p(src), _p(map_), C.c_longlong(map_.numel()), _p(dst), _stream())); self.launches += 1
 
     def pack_bf16(self, src, map_, dst):
         check(self.L.irc_pack_bf16(_p(src), _p(map_), C.c_longlong(map_.numel()), _p(dst), _stream())); self.launches += 1

@@ -13,6 +13,7 @@
 // Both: one CTA = 192 threads = TMA producer warp, MMA issuer warp, 4 epilogue warps;
 // operands staged by TMA into SWIZZLE_128B shared memory, accumulators in TMEM.
 #include <stdlib.h>
+#include <string.h>
 
 #include "irc_common.cuh"
 #include "../../include/irc_b200.h"
@@ -1598,4 +1599,32 @@ extern "C" int irc_conv_stats_finalize(const float* part, const float* edge, int
     if (!part || !edge || !stats || n_img <= 0 || rows_per_img < kBM || n_out <= 0) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_stats_finalize: bad args");
     irc::launch(conv_stats_finalize_kernel, dim3(n_img, (n_out + 63) / 64), 1024, 0, (cudaStream_t)stream, part, edge, rows_per_img, n_out, stats);
     return irc_check_launch("irc_conv_stats_finalize");
+}
+
+// nn.ConvTranspose2d(Cin, Cout, 3, stride=2, padding=1, output_padding=1) forward (irc:495-499, :512-516) on a framed input
+// (pad >= 1, ZERO ring): output pixel (2y + a, 2x + b) only sees inputs (y + dy, x + dx), dy, dx in {0, 1}, so the transposed
+// convolution is ONE stride-1 implicit GEMM with four taps whose 4 * Cout output columns are the four sub-pixel phases
+// (depth-to-space order: column (a * 2 + b) * Cout + co).  w: bf16 [4 * cout][4 * cin] packed as (phase, co) x (tap dy * 2 + dx, ci)
+// with the kernel element (a + 1 - 2 dy, b + 1 - 2 dx) or zero; bias4: fp32 [4 * cout] (the bias repeated per phase) or NULL;
+// out: bf16 [rows][out_ld], columns [out_chan_off, out_chan_off + 4 * cout).  Launched as ceil(4 * cout / 512) irc_conv_gemm calls.
+extern "C" int irc_convT2d_fwd(const void* x, long long rows, int x_ld, int x_chan_off, int cin, int wp, const void* w, int cout, const float* bias4,
+                               void* out, long long out_ld, int out_chan_off, void* stream) {
+    if (!x || !w || !out || cin <= 0 || cin % 64 || cout <= 0 || (4 * cout) % 32 || wp < 2)
+        return irc_set_error(IRC_ERR_BAD_ARG, "irc_convT2d_fwd: cin must be a multiple of 64, 4 * cout a multiple of 32, wp >= 2");
+    const int n_total = 4 * cout;
+    int blk = n_total;
+    if (blk > 512) { blk = 512; while (n_total % blk) blk -= 32; }
+    for (int c0 = 0; c0 < n_total; c0 += blk) {
+        irc_conv_gemm_args g;
+        memset(&g, 0, sizeof(g));
+        g.a = x; g.a_rows = rows; g.a_ld = x_ld; g.a_chan_off = x_chan_off; g.cin = cin;
+        g.ntaps = 4; g.taps[0] = 0; g.taps[1] = 1; g.taps[2] = wp; g.taps[3] = wp + 1;
+        g.w = (const char*)w + (size_t)c0 * 4 * cin * 2; g.n_out = blk;
+        g.out = out; g.out_ld = out_ld; g.out_chan_off = out_chan_off + c0;
+        g.bias = bias4 ? bias4 + c0 : nullptr;
+        g.reuse = 0;
+        const int rc = irc_conv_gemm(&g, stream);
+        if (rc) return rc;
+    }
+    return IRC_OK;
 }

@@ -68,6 +68,14 @@ __global__ void pack8_kernel(const float* __restrict__ src, const int* __restric
     }
 }
 
+__global__ void gather_f32_kernel(const float* __restrict__ src, const int* __restrict__ map, long long n, float* __restrict__ dst) {
+    irc::pdl_prologue();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int j = map[i];
+        dst[i] = j >= 0 ? src[j] : 0.f;
+    }
+}
+
 __global__ void gather_sum_kernel(const float* __restrict__ src, const int* __restrict__ map, long long n, int splits, long long split_stride,
                                   float* __restrict__ dst) {
     irc::pdl_prologue();
@@ -144,4 +152,10 @@ extern "C" int irc_gather_sum_multi(const irc_sum_job* jobs_dev, int njobs, long
     if (!jobs_dev || njobs <= 0 || total <= 0) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather_sum_multi: empty job table");
     irc::launch(gather_sum_multi_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, jobs_dev, njobs, total);
     return irc_check_launch("irc_gather_sum_multi");
+}
+
+extern "C" int irc_gather_f32(const float* src, const int* map, long long n, float* dst, void* stream) {
+    if (!src || !map || !dst) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather_f32: null");
+    irc::launch(gather_f32_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, src, map, n, dst);
+    return irc_check_launch("irc_gather_f32");
 }

@@ -22,8 +22,9 @@ IMAGENET_MEAN = (0.485, 0.456, 0.406)   # irc:667-668
 IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
-def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9) -> Dict[str, tuple]:
-    """state_dict parameter shapes of ResnetUNetGenerator with the default config (irc:457-531)"""
+def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9, no_antialias_up=False) -> Dict[str, tuple]:
+    """state_dict parameter shapes of ResnetUNetGenerator (irc:457-531).  no_antialias_up: the two UpsampleAA modules (buffers
+    only) become nn.ConvTranspose2d(C, C, 3, 2, 1, 1) with parameters up{1,2}_up.{weight (Cin, Cout, 3, 3), bias} (irc:495-516)"""
     s = {"inc.1.weight": (ngf, input_nc, 7, 7), "inc.1.bias": (ngf,),
          "down1.0.weight": (2 * ngf, ngf, 3, 3), "down1.0.bias": (2 * ngf,),
          "down2.0.weight": (4 * ngf, 2 * ngf, 3, 3), "down2.0.bias": (4 * ngf,)}
@@ -31,7 +32,11 @@ def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9) -> Dict[str, t
         for j in (1, 5):
             s[f"resblocks.{b}.conv_block.{j}.weight"] = (4 * ngf, 4 * ngf, 3, 3)
             s[f"resblocks.{b}.conv_block.{j}.bias"] = (4 * ngf,)
+    if no_antialias_up:
+        s["up1_up.weight"] = (4 * ngf, 4 * ngf, 3, 3); s["up1_up.bias"] = (4 * ngf,)
     s["up1_conv.0.weight"] = (2 * ngf, 6 * ngf, 3, 3); s["up1_conv.0.bias"] = (2 * ngf,)
+    if no_antialias_up:
+        s["up2_up.weight"] = (2 * ngf, 2 * ngf, 3, 3); s["up2_up.bias"] = (2 * ngf,)
     s["up2_conv.0.weight"] = (ngf, 3 * ngf, 3, 3); s["up2_conv.0.bias"] = (ngf,)
     s["outc.1.weight"] = (output_nc, ngf, 7, 7); s["outc.1.bias"] = (output_nc,)
     return s
@@ -92,8 +97,18 @@ class ConvOp:
             self.be.in_stats(z_view, C, n_img, H, W, stats)
 
     def fwd(self, a, a_chan_off, out, **kw):
+        n = self.lay.w_f.rows
+        if n > 512:
+            # the GEMM takes at most 512 output columns per launch: wide outputs (transposed conv: 4 phases x Cout) go in blocks
+            assert n % 512 == 0 and not kw.get("in_stats") and not kw.get("tap")
+            bias = kw.pop("bias", None)
+            for c0 in range(0, n, 512):
+                self.be.note = (self.name, "fwd", self.flops * 512 / n)
+                self.be.conv_gemm(a, a_chan_off, self.lay.K, self.taps, self.lay.w_f.t[c0:c0 + 512], 512, out, out_chan_off=c0,
+                                  bias=None if bias is None else bias[c0:c0 + 512], **kw)
+            return
         self.be.note = (self.name, "fwd", self.flops)
-        self.be.conv_gemm(a, a_chan_off, self.lay.K, self.taps, self.lay.w_f.t, self.lay.w_f.rows, out, **kw)
+        self.be.conv_gemm(a, a_chan_off, self.lay.K, self.taps, self.lay.w_f.t, n, out, **kw)
 
     def dgrad(self, dz, out, **kw):
         """out[q][k] = sum_t dz[q - tap_t][:] . W[:, t, k]   (gradient w.r.t. the conv input frame)"""
@@ -109,18 +124,61 @@ class ConvOp:
         self.be.gather_sum_deferred(self.partial, lay.unpack, self.splits, lay.N * lay.T * lay.K, self.grad_flat)
 
 
+class TransposedUp:
+    """nn.ConvTranspose2d(C, C, 3, stride=2, padding=1, output_padding=1) (the generator's up-sampling with no_antialias_up=True,
+    irc:495-499 / :512-516) between an input frame `src` (pad 1, ZERO ring) and C channels of a frame at twice the resolution.
+    Forward = one stride-1 implicit GEMM over the input frame with 4 taps and 4 C output columns (the four sub-pixel phases, see
+    layout.layout_convT) + a depth-to-space read; backward = the same layout run through the data- / weight-gradient GEMMs."""
+
+    def __init__(self, be, packer: L.Packer, arena: L.ParamArena, key: str, C: int, src: L.Frame, device, name: str):
+        self.be, self.C, self.src, self.arena, self.key = be, C, src, arena, key
+        lay = L.layout_convT(packer, arena, key + ".weight", C, C)
+        self.op = ConvOp(be, lay, L.taps_convT(src.wp), arena, src.rows, pixels=src.N * src.H * src.W, name=name)
+        self.T = L.act_zeros(src.rows, 4 * C, device)          # forward output, depth-to-space order
+        self.dT = L.act_zeros(src.rows, 4 * C, device)         # gradient w.r.t. it
+        self.bias4 = torch.zeros(4 * C, device=device)
+        off = arena.offset[key + ".bias"]
+        self.bias_map = (off + torch.arange(4 * C, dtype=torch.int32) % C).to(torch.int32).to(device)
+        self.colsum = torch.zeros(4 * C, device=device)
+        self.cmap = torch.arange(C, dtype=torch.int32, device=device)
+        self.ri = torch.zeros(src.rows, device=device, dtype=torch.int16)      # ring rows of the input frame
+        be.row_index(self.ri, src.N, src.hp, src.wp, src.p, src.p + src.H, src.p, src.p + src.W)
+
+    def refresh(self):
+        self.be.gather_f32(self.arena.flat, self.bias_map, self.bias4)
+
+    def forward(self, dst: L.Frame, dst_off: int):
+        src, C = self.src, self.C
+        self.op.fwd(src.t, 0, self.T, bias=self.bias4)
+        # output pixel (2y + a, 2x + b) = column group a * 2 + b of input row (y, x): read the GEMM output as 2x2 blocks
+        self.be.gather(View(self.T, 0, src.hp, src.wp, 2 * src.p, 2 * src.p, C), dst.view(dst_off), C, src.N, 2 * src.H, 2 * src.W, dst.p, 0)
+
+    def backward(self, g: L.Frame, g_off: int, dx_out: torch.Tensor):
+        """g: gradient w.r.t. the up-sampled map (channels [g_off, g_off + C) of frame g); dx_out [src.rows, C] receives the
+        gradient w.r.t. the input frame (ring rows zeroed: they are padding, not reflected pixels)"""
+        be, src, C = self.be, self.src, self.C
+        be.gather(g.view(g_off), View(self.dT, 0, src.hp, src.wp), C, src.N, 2 * src.H, 2 * src.W, 2 * src.p, 0, dst_s2d=1)
+        be.colsum(self.dT, 0, 4 * C, self.colsum)
+        be.gather_sum(self.colsum, self.cmap, 4, C, self.arena.view(self.key + ".bias", self.arena.grad))
+        self.op.wgrad(self.dT, src.t, 0, src.rows)
+        self.op.dgrad(self.dT, dx_out, row_img=self.ri)
+
+
 # ==========================================================================================
 # generator (irc:425-569)
 # ==========================================================================================
 class GeneratorEngine:
     def __init__(self, be, B: int, H: int, W: int, device, ngf: int = 64, n_blocks: int = 9, training: bool = True,
-                 arena: L.ParamArena = None):
+                 arena: L.ParamArena = None, no_antialias_up: bool = False):
         if H % 4 or W % 4:
             raise NotImplementedError("H and W must be multiples of 4 (the reference's odd-size bilinear fix-up, irc:555-563, is not built yet)")
         if ngf != 64:
             raise NotImplementedError("ngf must be 64 (channel counts are tiled in units of 64)")
         self.be, self.B, self.H, self.W, self.dev, self.nb, self.training = be, B, H, W, device, n_blocks, training
-        self.arena = arena or L.ParamArena(generator_shapes(1, 3, ngf, n_blocks), device)
+        self.convT = bool(no_antialias_up)
+        self.arena = arena or L.ParamArena(generator_shapes(1, 3, ngf, n_blocks, no_antialias_up), device)
+        if self.convT and "up1_up.weight" not in self.arena.offset:
+            raise ValueError("no_antialias_up=True needs an arena with the ConvTranspose2d parameters up{1,2}_up.{weight,bias}")
         self.packer = L.Packer(self.arena)
         A, P = self.arena, self.packer
         H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
@@ -178,6 +236,11 @@ class GeneratorEngine:
         self.outc = ConvOp(be, L.layout_outc(P, A, "outc.1.weight", 3, 64, 7), [(r - 3) * wp3 for r in range(7)], A, self.y4.rows,
                            bias_name="outc.1.bias", pixels=B * H * W, name="G.outc")
         self.outc_shifts = [(0, s - 3) for s in range(7)]      # (dy, dx) of the horizontal taps
+        if self.convT:
+            # up-sampling by transposed convolutions (irc:495-499, :512-516): up2_up needs the activated map as a frame of its own
+            self.A3 = F(H2, W2, 1, 128)
+            self.up1_t = TransposedUp(be, P, A, "up1_up", 256, self.X[n_blocks], device, "G.up1_up")
+            self.up2_t = TransposedUp(be, P, A, "up2_up", 128, self.A3, device, "G.up2_up")
         P.finish()
         if training:
             self._alloc_backward()
@@ -203,10 +266,14 @@ class GeneratorEngine:
         self.g3 = F(H2, W2, 0, 128)
         self.g2 = F(H2, W2, 0, 256)
         self.g1 = F(H, W, 0, 128)
+        if self.convT:
+            self.GA3 = F(H2, W2, 1, 128)
 
     # ------------------------------------------------------------------ forward
     def refresh_weights(self):
         self.packer.refresh(self.be)
+        if self.convT:
+            self.up1_t.refresh(); self.up2_t.refresh()
 
     def forward(self, ir: torch.Tensor) -> torch.Tensor:
         """ir: fp32 [B,1,H,W] -> fake fp32 [B,3,H,W] (irc:533-569)"""
@@ -231,12 +298,21 @@ class GeneratorEngine:
             c1.fwd(self.X[b].t, 0, self.Za[b].t)
             be.in_apply(self.Za[b].view(), self.Hh[b].view(), 256, B, H4, W4, 1, 1, self.sta[b], eps=EPS, act=ACT_RELU)
             c2.fwd(self.Hh[b].t, 0, self.Zb[b].t)
-            be.in_apply(self.Zb[b].view(), self.X[b + 1].view(), 256, B, H4, W4, 1, 1, self.stb[b], eps=EPS, act=ACT_NONE, res=self.X[b].view())
-        # up1: UpsampleAA into cat1[0:256), conv on the concatenation
-        be.gather(self.X[self.nb].view(), self.cat1.view(0), 256, B, H2, W2, 1, 0, tables=self.t_up1)
-        self.up1.fwd_stats(self.cat1.t, 0, self.Z3.t, self.st3, self.ri_half, B, self.Z3.hp * self.Z3.wp, self.Z3.view(), 128, H2, W2)
-        # up2: IN + ReLU + UpsampleAA fused into cat2[0:128)
-        be.gather(self.Z3.view(), self.cat2.view(0), 128, B, H, W, 1, 0, tables=self.t_up2, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU)
+            # the last block output feeds only the up-sampling: a transposed convolution wants a ZERO ring, not the reflected one
+            halo = 0 if (self.convT and b == self.nb - 1) else 1
+            be.in_apply(self.Zb[b].view(), self.X[b + 1].view(), 256, B, H4, W4, 1, halo, self.stb[b], eps=EPS, act=ACT_NONE, res=self.X[b].view())
+        if self.convT:
+            # up1 / up2 by ConvTranspose2d (irc:495-499, :512-516)
+            self.up1_t.forward(self.cat1, 0)
+            self.up1.fwd_stats(self.cat1.t, 0, self.Z3.t, self.st3, self.ri_half, B, self.Z3.hp * self.Z3.wp, self.Z3.view(), 128, H2, W2)
+            be.gather(self.Z3.view(), self.A3.view(), 128, B, H2, W2, 1, 0, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU)
+            self.up2_t.forward(self.cat2, 0)
+        else:
+            # up1: UpsampleAA into cat1[0:256), conv on the concatenation
+            be.gather(self.X[self.nb].view(), self.cat1.view(0), 256, B, H2, W2, 1, 0, tables=self.t_up1)
+            self.up1.fwd_stats(self.cat1.t, 0, self.Z3.t, self.st3, self.ri_half, B, self.Z3.hp * self.Z3.wp, self.Z3.view(), 128, H2, W2)
+            # up2: IN + ReLU + UpsampleAA fused into cat2[0:128)
+            be.gather(self.Z3.view(), self.cat2.view(0), 128, B, H, W, 1, 0, tables=self.t_up2, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU)
         self.up2.fwd_stats(self.cat2.t, 0, self.Z4.t, self.st4, self.ri_full, B, self.Z4.hp * self.Z4.wp, self.Z4.view(), 64, H, W)
         be.gather(self.Z4.view(), self.y4.view(), 64, B, H, W, 3, 1, stats=self.st4, cnt=H * W, eps=EPS, act=ACT_RELU)
         return self.output_head()
@@ -270,15 +346,23 @@ class GeneratorEngine:
         be.in_bwd(self.Z4.view(), self.G4.view(), self.dZ4.view(), 64, B, H, W, stats=self.st4, cnt=H * W, eps=EPS, act=ACT_RELU, bsum=self.bsum)
         self.up2.wgrad(self.dZ4.t, self.cat2.t, 0, self.cat2.rows)
         self.up2.dgrad(self.dZ4.t, self.Gcat2.t)
-        # up1_conv (through UpsampleAA^T)
-        be.gather(self.Gcat2.view(0), self.g3.view(), 128, B, H2, W2, 0, 0, tables=self.t_up2_T)
-        be.in_bwd(self.Z3.view(), self.g3.view(), self.dZ3.view(), 128, B, H2, W2, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
+        # up1_conv (through UpsampleAA^T, or the transposed convolution's data gradient)
+        if self.convT:
+            self.up2_t.backward(self.Gcat2, 0, self.GA3.t)
+            g_up1 = self.GA3
+        else:
+            be.gather(self.Gcat2.view(0), self.g3.view(), 128, B, H2, W2, 0, 0, tables=self.t_up2_T)
+            g_up1 = self.g3
+        be.in_bwd(self.Z3.view(), g_up1.view(), self.dZ3.view(), 128, B, H2, W2, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
                   bsum=self.bsum)
         self.up1.wgrad(self.dZ3.t, self.cat1.t, 0, self.cat1.rows)
         self.up1.dgrad(self.dZ3.t, self.Gcat1.t)
         # gradient w.r.t. the last ResNet block output = UpsampleAA^T of Gcat1[0:256)
         cur = self.dOut[0]
-        be.gather(self.Gcat1.view(0), cur.view(), 256, B, H4, W4, 1, 0, tables=self.t_up1_T)
+        if self.convT:
+            self.up1_t.backward(self.Gcat1, 0, cur.t)
+        else:
+            be.gather(self.Gcat1.view(0), cur.view(), 256, B, H4, W4, 1, 0, tables=self.t_up1_T)
         n4 = H4 * W4
         for b in reversed(range(self.nb)):
             c1, c2 = self.res[b]

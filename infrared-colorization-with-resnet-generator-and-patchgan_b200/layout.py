@@ -278,3 +278,27 @@ def layout_pointwise_taps(packer, arena, name, Cin, k) -> WeightLayout:
     r, s, ci = np.meshgrid(np.arange(k), np.arange(k), np.arange(Cin), indexing="ij")
     idx[(r * k + s).reshape(-1), 0, ci.reshape(-1)] = oihw_index(arena.offset[name], 0, ci, r, s, Cin, k, k).reshape(-1)
     return WeightLayout(packer, idx, arena.offset[name], arena.numel(name), n_pad=32, k_pad_d=64)
+
+
+def layout_convT(packer, arena, name, Cin, Cout) -> WeightLayout:
+    """nn.ConvTranspose2d(Cin, Cout, 3, stride=2, padding=1, output_padding=1) (irc:495-499, :512-516) as a stride-1 GEMM over
+    the INPUT frame: output pixel (2y + a, 2x + b) only sees inputs (y + dy, x + dx), dy, dx in {0, 1}, through kernel element
+    (a + 1 - 2 dy, b + 1 - 2 dx) when that lies in [0, 2].  Output slot n = (a * 2 + b) * Cout + co (depth-to-space order),
+    tap t = dy * 2 + dx (row shift dy * wp + dx), channel slot k = ci.  PyTorch stores the weight as (Cin, Cout, 3, 3)."""
+    idx = np.full((4 * Cout, 4, Cin), -1, np.int64)
+    base = arena.offset[name]
+    ci = np.arange(Cin)
+    for a in range(2):
+        for b in range(2):
+            for dy in range(2):
+                for dx in range(2):
+                    r, s = a + 1 - 2 * dy, b + 1 - 2 * dx
+                    if not (0 <= r <= 2 and 0 <= s <= 2):
+                        continue
+                    for co in range(Cout):
+                        idx[(a * 2 + b) * Cout + co, dy * 2 + dx, :] = base + ((ci * Cout + co) * 3 + r) * 3 + s
+    return WeightLayout(packer, idx, base, arena.numel(name))
+
+
+def taps_convT(wp: int) -> List[int]:
+    return [dy * wp + dx for dy in range(2) for dx in range(2)]

@@ -281,7 +281,8 @@ class _GenFn(torch.autograd.Function):
         # the pool in inference and be rebuilt (0.3 s of host work) on every call
         grad = mod._grad_on and any(ctx.needs_input_grad)
         key = (B, H, W, grad)                  # inference engines carry no backward buffers
-        eng = mod._acquire(key, lambda: E.GeneratorEngine(backend(), B, H, W, x.device, arena=mod.arena, training=grad))
+        eng = mod._acquire(key, lambda: E.GeneratorEngine(backend(), B, H, W, x.device, arena=mod.arena, training=grad,
+                                                          no_antialias_up=mod.no_antialias_up))
         eng.refresh_weights()
         out = eng.forward(x.contiguous().float()).clone()
         if grad:
@@ -312,12 +313,14 @@ class ResnetUNetGenerator(_ArenaModule):
         super().__init__()
         assert n_blocks >= 0                                          # irc:449
         if (input_nc, output_nc, ngf) != (1, 3, 64) or norm_layer is not nn.InstanceNorm2d or use_dropout or padding_type != "reflect" \
-                or no_antialias or no_antialias_up:
-            raise NotImplementedError("only the default generator graph (1->3, ngf 64, instance norm, reflect padding, anti-aliased "
-                                      "down/up-sampling) is built; see SURVEY.md §8f-4 for the variants queued next")
+                or no_antialias:
+            raise NotImplementedError("built: the default generator graph (1->3, ngf 64, instance norm, reflect padding, anti-aliased "
+                                      "down-sampling) with UpsampleAA or - no_antialias_up=True - ConvTranspose2d up-sampling; stride-2 "
+                                      "down-sampling convolutions (no_antialias=True) and other norms are not (SURVEY.md §8f-4)")
         self.n_blocks = n_blocks
+        self.no_antialias_up = bool(no_antialias_up)
         dev = torch.device("cuda" if torch.cuda.is_available() else "cpu")
-        self._init_arena(E.generator_shapes(input_nc, output_nc, ngf, n_blocks), dev)
+        self._init_arena(E.generator_shapes(input_nc, output_nc, ngf, n_blocks, self.no_antialias_up), dev)
         A = self.arena
         hold = lambda k: _ConvParams(A.view(k + ".weight"), A.view(k + ".bias"))
         self.inc = nn.ModuleDict({"1": hold("inc.1")})
@@ -326,9 +329,10 @@ class ResnetUNetGenerator(_ArenaModule):
         self.down2 = nn.ModuleDict({"0": hold("down2.0")})
         self.down2_down = _Filt(4 * ngf)
         self.resblocks = nn.ModuleList([_ResBlockHolder(A, b) for b in range(n_blocks)])
-        self.up1_up = _Filt(4 * ngf)
+        # UpsampleAA carries only its `filt` buffer; nn.ConvTranspose2d (irc:495-499, :512-516) carries weight (Cin, Cout, 3, 3) + bias
+        self.up1_up = hold("up1_up") if self.no_antialias_up else _Filt(4 * ngf)
         self.up1_conv = nn.ModuleDict({"0": hold("up1_conv.0")})
-        self.up2_up = _Filt(2 * ngf)
+        self.up2_up = hold("up2_up") if self.no_antialias_up else _Filt(2 * ngf)
         self.up2_conv = nn.ModuleDict({"0": hold("up2_conv.0")})
         self.outc = nn.ModuleDict({"1": hold("outc.1")})
 

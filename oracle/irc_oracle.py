@@ -36,8 +36,8 @@ Params = Dict[str, torch.Tensor]
 # deterministic weight / input recipes (shared by oracle, tests, bench)
 # ----------------------------------------------------------------------------
 
-def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9):
-    """Parameter shapes of the default (anti-aliased, instance-norm) generator, irc:457-531."""
+def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9, no_antialias_up=False):
+    """Parameter shapes of the instance-norm generator, irc:457-531 (no_antialias_up: ConvTranspose2d up-sampling, irc:495-516)."""
     s = {
         "inc.1.weight": (ngf, input_nc, 7, 7), "inc.1.bias": (ngf,),
         "down1.0.weight": (2 * ngf, ngf, 3, 3), "down1.0.bias": (2 * ngf,),
@@ -47,6 +47,9 @@ def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9):
         for j in (1, 5):
             s[f"resblocks.{b}.conv_block.{j}.weight"] = (4 * ngf, 4 * ngf, 3, 3)
             s[f"resblocks.{b}.conv_block.{j}.bias"] = (4 * ngf,)
+    if no_antialias_up:
+        s["up1_up.weight"] = (4 * ngf, 4 * ngf, 3, 3); s["up1_up.bias"] = (4 * ngf,)
+        s["up2_up.weight"] = (2 * ngf, 2 * ngf, 3, 3); s["up2_up.bias"] = (2 * ngf,)
     s["up1_conv.0.weight"] = (2 * ngf, 6 * ngf, 3, 3); s["up1_conv.0.bias"] = (2 * ngf,)
     s["up2_conv.0.weight"] = (ngf, 3 * ngf, 3, 3); s["up2_conv.0.bias"] = (ngf,)
     s["outc.1.weight"] = (output_nc, ngf, 7, 7); s["outc.1.bias"] = (output_nc,)
@@ -221,12 +224,15 @@ def generator_forward(p: Params, x: torch.Tensor, n_blocks: int = 9, taps: Optio
     h = x2
     for b in range(n_blocks):
         h = tap(f"res{b}", resnet_block(p, f"resblocks.{b}.", h))
-    y = tap("up1_up", upsample_aa(h))
+    convT = "up1_up.weight" in p          # no_antialias_up=True: nn.ConvTranspose2d(C, C, 3, 2, 1, 1) instead of UpsampleAA (irc:495-499)
+    up = (lambda t, k: F.conv_transpose2d(t, p[k + ".weight"], p[k + ".bias"], stride=2, padding=1, output_padding=1)) if convT \
+        else (lambda t, k: upsample_aa(t))
+    y = tap("up1_up", up(h, "up1_up"))
     if y.shape[-2:] != x1.shape[-2:]:  # irc:555-556
         y = F.interpolate(y, size=x1.shape[-2:], mode="bilinear", align_corners=True)
     y = torch.cat([y, x1], dim=1)
     y = tap("up1", torch.relu(instance_norm(_conv(y, p["up1_conv.0.weight"], p["up1_conv.0.bias"], pad=1))))
-    y = tap("up2_up", upsample_aa(y))
+    y = tap("up2_up", up(y, "up2_up"))
     if y.shape[-2:] != x0.shape[-2:]:  # irc:562-563
         y = F.interpolate(y, size=x0.shape[-2:], mode="bilinear", align_corners=True)
     y = torch.cat([y, x0], dim=1)

@@ -1,0 +1,59 @@
+"""Golden vectors of the NON-DEFAULT generator graph the build supports: no_antialias_up=True, i.e.
+nn.ConvTranspose2d(C, C, 3, stride=2, padding=1, output_padding=1) instead of UpsampleAA (irc:495-499, :512-516), from the
+UNMODIFIED reference.  Build container only.  Writes tests/golden/ref_variants.npz; asserts the oracle restatement on the way."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_golden as MG  # noqa: E402
+
+R, O = MG.R, MG.O
+
+
+def main():
+    B, H, W = 2, 32, 32
+    gold = {}
+    pG = O.seeded_params(O.generator_shapes(no_antialias_up=True), 4321, bias_std=0.02)
+    ir, rgb = O.synthetic_pair(B, H, W)
+    cfg = R.Config(); cfg.device = "cpu"; cfg.no_antialias_up = True
+    m = R.IRColorizationModel(cfg)
+    keys = set(m.netG.state_dict().keys())
+    assert "up1_up.weight" in keys and "up2_up.bias" in keys and "up1_up.filt" not in keys
+    assert tuple(m.netG.state_dict()["up1_up.weight"].shape) == (256, 256, 3, 3)
+    missing = m.netG.load_state_dict(pG, strict=False)
+    assert not missing.unexpected_keys and all(k.endswith("filt") for k in missing.missing_keys), missing
+    fake = m(ir)
+    g = torch.randn(fake.shape, generator=torch.Generator().manual_seed(9))
+    fake.backward(g)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in pG.items()}
+    fo = O.generator_forward(leaves, ir)
+    MG.close(fo, fake.detach(), 2e-5, "variant forward")
+    fo.backward(g)
+    for k, p_ in m.netG.named_parameters():
+        noise = k.endswith("bias") and not (k.startswith("outc") or k.startswith("up1_up") or k.startswith("up2_up"))   # bias in front of a non-affine InstanceNorm
+        if p_.grad.abs().max() > 1e-4 and not noise:
+            rel = ((leaves[k].grad - p_.grad).norm() / p_.grad.norm()).item()
+            assert rel < 5e-3, (k, rel)
+        gold["grad_norm/" + k] = p_.grad.norm().item(); gold["grad_sample/" + k] = MG.sample(p_.grad); gold["grad_absmax/" + k] = p_.grad.abs().max().item()
+    gold["fake"] = fake.detach().numpy(); gold["upstream"] = g.numpy()
+    # the transposed convolution alone (irc:495-499): input, weight, bias, output, gradients
+    ct = torch.nn.ConvTranspose2d(64, 64, 3, stride=2, padding=1, output_padding=1)
+    gen = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        ct.weight.copy_(torch.randn(64, 64, 3, 3, generator=gen) * 0.05); ct.bias.copy_(torch.randn(64, generator=gen) * 0.1)
+    x = torch.randn(2, 64, 6, 10, generator=gen, requires_grad=True)
+    y = ct(x)
+    gy = torch.randn(y.shape, generator=gen)
+    y.backward(gy)
+    gold.update(ct_x=x.detach().numpy(), ct_w=ct.weight.detach().numpy(), ct_b=ct.bias.detach().numpy(), ct_y=y.detach().numpy(), ct_gy=gy.numpy(),
+                ct_gx=x.grad.numpy(), ct_gw=ct.weight.grad.numpy(), ct_gb=ct.bias.grad.numpy())
+    np.savez_compressed(os.path.join(MG.OUT, "ref_variants.npz"), **gold)
+    print("wrote ref_variants.npz keys:", len(gold))
+
+
+if __name__ == "__main__":
+    main()

@@ -429,6 +429,11 @@ class RefBackend:
         v.mul_(b2).addcmul_(gg, gg, value=1 - b2)
         p.addcdiv_(m, (v.sqrt() / math.sqrt(bc2)).add_(eps), value=-lr / bc1)
 
+    def gather_f32(self, src, map_, dst):
+        self.launches += 1
+        m = map_.long()
+        dst.copy_(torch.where(m >= 0, src[m.clamp_min(0)], torch.zeros_like(src[m.clamp_min(0)])))
+
     def pack_bf16(self, src, map_, dst):
         self.launches += 1
         m = map_.long()

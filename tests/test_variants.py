@@ -1,0 +1,154 @@
+"""Non-default generator graph: no_antialias_up=True - nn.ConvTranspose2d up-sampling (irc:495-499, :512-516) -
+against golden vectors produced by the unmodified reference (tests/golden/ref_variants.npz, oracle/make_golden_variants.py).
+CPU: the oracle and the product's plan (torch restatement of the primitives, float32 frames).  GPU: the CUDA path, incl. the
+transposed convolution through its C-ABI entry point irc_convT2d_fwd."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import irc_oracle as O
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_variants.npz"))
+B, H, W = 2, 32, 32
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def sample(t, n=256):
+    f = t.detach().float().cpu().reshape(-1)
+    return f[torch.linspace(0, f.numel() - 1, min(n, f.numel())).long()].numpy()
+
+
+def _params():
+    return O.seeded_params(O.generator_shapes(no_antialias_up=True), 4321, bias_std=0.02)
+
+
+def test_oracle_variant_forward_and_grads():
+    pG = _params()
+    ir, _ = O.synthetic_pair(B, H, W)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in pG.items()}
+    fake = O.generator_forward(leaves, ir)
+    assert np.abs(fake.detach().numpy() - GOLD["fake"]).max() < 5e-5
+    fake.backward(torch.from_numpy(GOLD["upstream"]))
+    for k in ("up1_up.weight", "up2_up.weight", "up1_up.bias", "up2_up.bias", "outc.1.weight", "up1_conv.0.weight"):
+        assert abs(leaves[k].grad.norm().item() - float(GOLD["grad_norm/" + k])) < 2e-3 * float(GOLD["grad_norm/" + k]), k
+
+
+def _check_engine(be, dev, tol_fwd, tol_dec, tol_enc):
+    import irc_b200  # noqa: F401
+    from irc_b200 import engine as E
+    pG = _params()
+    ir, _ = O.synthetic_pair(B, H, W)
+    eng = E.GeneratorEngine(be, B, H, W, dev, no_antialias_up=True)
+    eng.arena.load(pG); eng.refresh_weights()
+    fake = eng.forward(ir.to(dev))
+    e = rel(fake, torch.from_numpy(GOLD["fake"]))
+    print("variant fake rel", e)
+    assert e < tol_fwd
+    eng.arena.grad.zero_()
+    eng.backward(torch.from_numpy(GOLD["upstream"]).to(dev).contiguous())
+    worst = {}
+    for k in pG:
+        if float(GOLD["grad_absmax/" + k]) <= 1e-4 or (k.endswith("bias") and not k.startswith(("outc", "up1_up", "up2_up"))):
+            continue
+        got = sample(eng.arena.view(k, eng.arena.grad)); want = GOLD["grad_sample/" + k]
+        worst[k] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    print({k: round(v, 4) for k, v in worst.items() if not k.startswith("resblocks") or k.startswith("resblocks.8")})
+    for k, v in worst.items():
+        decoder = k.startswith(("outc", "up2", "up1"))
+        assert v < (tol_dec if decoder else tol_enc), (k, v)
+
+
+def test_plan_with_transposed_conv_upsampling_matches_reference():
+    """host logic of the variant (weight layout of the 4-phase GEMM, depth-to-space reads, zero ring, gradient routing) in
+    float32; the encoder-side gradients pass through 18 ReLU masks evaluated in a different summation order (2e-3 fp32 noise)"""
+    import irc_b200  # noqa: F401
+    from irc_b200 import layout as L
+    from ref_backend import RefBackend
+    old = L.ACT_DTYPE
+    L.ACT_DTYPE = torch.float32
+    try:
+        _check_engine(RefBackend(), "cpu", 1e-5, 1e-4, 1e-2)
+    finally:
+        L.ACT_DTYPE = old
+
+
+def test_module_surface_of_the_variant():
+    """state_dict keys of the reference with no_antialias_up=True: ConvTranspose2d parameters, no up*_up.filt buffers"""
+    import irc_b200 as R
+    from irc_b200 import layout as L, modules as M
+    from ref_backend import RefBackend
+    old, oldbe = L.ACT_DTYPE, M._BACKEND
+    L.ACT_DTYPE = torch.float32; M.set_backend(RefBackend())
+    try:
+        cfg = R.Config(); cfg.device = "cpu"; cfg.no_antialias_up = True
+        m = R.IRColorizationModel(cfg)
+        sd = m.netG.state_dict()
+        assert tuple(sd["up1_up.weight"].shape) == (256, 256, 3, 3) and tuple(sd["up2_up.bias"].shape) == (128,)
+        assert "up1_up.filt" not in sd and "down1_down.filt" in sd
+        m.netG.load_state_dict(_params(), strict=False)
+        ir, _ = O.synthetic_pair(B, H, W)
+        with torch.no_grad():
+            assert rel(m(ir), torch.from_numpy(GOLD["fake"])) < 1e-5
+    finally:
+        L.ACT_DTYPE = old; M.set_backend(oldbe)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_gpu_generator_with_transposed_conv_upsampling():
+    """whole-network bf16 run: forward 1e-2; gradients inherit the ReLU-mask flips of the bf16 forward exactly like the default
+    graph (tests/test_step_gpu.py bounds them at 0.35); the tight 1e-2 bound of the new layer is the C-ABI test below"""
+    from irc_b200._native import CudaBackend
+    _check_engine(CudaBackend(), "cuda", 3e-2, 0.25, 0.35)
+
+
+@pytest.mark.gpu
+def test_gpu_convT2d_fwd_through_the_c_abi():
+    """irc_convT2d_fwd + the data / weight gradients through irc_conv_gemm / irc_tn_gemm against nn.ConvTranspose2d (reference
+    run: ct_* fixtures), on a zero-ringed frame"""
+    import irc_b200  # noqa: F401
+    from irc_b200 import _native as nat, layout as L, engine as E
+    from irc_b200._native import CudaBackend, View
+    be = CudaBackend()
+    x = torch.from_numpy(GOLD["ct_x"]); w = torch.from_numpy(GOLD["ct_w"]); b = torch.from_numpy(GOLD["ct_b"])
+    n, c, h, wd = x.shape
+    arena = L.ParamArena({"up.weight": (c, c, 3, 3), "up.bias": (c,)}, "cuda")
+    arena.load({"up.weight": w, "up.bias": b})
+    packer = L.Packer(arena)
+    src = L.Frame(n, h, wd, 1, c, "cuda")
+    up = E.TransposedUp(be, packer, arena, "up", c, src, "cuda", "ct")
+    packer.finish(); packer.refresh(be); up.refresh()
+    src.t.view(n, src.hp, src.wp, c)[:, 1:-1, 1:-1].copy_(x.permute(0, 2, 3, 1))
+    # forward through the C entry point itself
+    out = torch.zeros(src.rows, 4 * c, device="cuda", dtype=torch.bfloat16)
+    nat.check(nat.lib().irc_convT2d_fwd(C.c_void_p(src.t.data_ptr()), C.c_longlong(src.rows), c, 0, c, src.wp, C.c_void_p(up.op.lay.w_f.t.data_ptr()), c,
+                                        C.c_void_p(up.bias4.data_ptr()), C.c_void_p(out.data_ptr()), C.c_longlong(4 * c), 0,
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    dst = L.Frame(n, 2 * h, 2 * wd, 1, c, "cuda")
+    be.gather(View(out, 0, src.hp, src.wp, 2, 2, c), dst.view(0), c, n, 2 * h, 2 * wd, 1, 0)
+    y = dst.t.view(n, dst.hp, dst.wp, c)[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().cpu()
+    e = rel(y, torch.from_numpy(GOLD["ct_y"]))
+    print("convT fwd rel", e)
+    assert e < 1e-2
+    # the engine path gives the same bits
+    up.forward(dst, 0)
+    assert torch.equal(dst.t.view(n, dst.hp, dst.wp, c)[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().cpu(), y)
+    # backward
+    g = L.Frame(n, 2 * h, 2 * wd, 1, c, "cuda")
+    g.t.view(n, g.hp, g.wp, c)[:, 1:-1, 1:-1].copy_(torch.from_numpy(GOLD["ct_gy"]).permute(0, 2, 3, 1))
+    dx = torch.zeros(src.rows, c, device="cuda", dtype=torch.bfloat16)
+    arena.grad.zero_()
+    up.backward(g, 0, dx); be.flush_sums()
+    gx = dx.view(n, src.hp, src.wp, c)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+    assert rel(gx, torch.from_numpy(GOLD["ct_gx"])) < 1e-2
+    assert rel(arena.view("up.weight", arena.grad), torch.from_numpy(GOLD["ct_gw"])) < 1e-2
+    assert rel(arena.view("up.bias", arena.grad), torch.from_numpy(GOLD["ct_gb"])) < 1e-2
+    ring = dx.view(n, src.hp, src.wp, c)
+    assert ring[:, 0].abs().max() == 0 and ring[:, :, -1].abs().max() == 0
