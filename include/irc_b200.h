@@ -70,9 +70,13 @@ typedef struct irc_conv_gemm_args {
      * GEMM over the k kernel ROWS (n_out = 32 columns = (kernel column j, output channel co) -> j * tap_nco + co):
      *   tap_out[n][co][y][x] = act(bias[co] + sum_j acc[q + j - (tap_nshift-1)/2][j * tap_nco + co]),  q = frame row of (n, y, x)
      * fp32 NCHW out (the generator's output head, irc:527-531: 7 x 7 reflect conv 64 -> 3 + tanh).  Tiles overlap by
-     * tap_nshift - 1 rows; `out` is not written.  tap_act: 0 none, 3 tanh.  NULL = off. */
+     * tap_nshift - 1 rows; `out` is not written.  tap_act: 0 none, 3 tanh.  NULL = off.
+     * The same mode computes the data gradient of a k x k convolution with a tiny Cin (VGG conv1_1, irc:664 under irc:1680):
+     * tap_scale (fp32 [tap_nco] or NULL) multiplies the result per output plane and tap_accumulate != 0 adds it to tap_out. */
     float* tap_out;
     int tap_nshift, tap_nco, tap_H, tap_W, tap_hp, tap_wp, tap_oy, tap_ox, tap_act;
+    const float* tap_scale;
+    int tap_accumulate;
 } irc_conv_gemm_args;
 int irc_conv_gemm(const irc_conv_gemm_args* args, void* stream);
 /* nn.ConvTranspose2d(cin, cout, 3, stride=2, padding=1, output_padding=1) forward (the generator's up-sampling layers with
@@ -214,6 +218,13 @@ typedef struct irc_im2col_args {
 } irc_im2col_args;
 long long irc_im2col_rows(int row_mode, int n_img, int Ho, int Wo);
 int irc_im2col(const irc_im2col_args* args, void* stream);
+
+/* The same three layers WITHOUT the operand round trip (replaces nn.Conv2d of irc:458-463, :600, :664 outright): the block
+ * stages the image rows in shared memory, gathers the 64-slot operand rows straight into mma.sync fragments and applies
+ * out[q][0..64) = act(bias + sum_k E[q][k] * w[n][k]), rows outside the image stored as zeros.  w: bf16 [64][64] (slot order of
+ * irc_im2col); out: bf16 [rows][64] in the row order of args->row_mode.  args->dst may be NULL; when given it ALSO receives the
+ * operand E (kept for the weight gradient).  act: 0 none, 1 ReLU, 2 LeakyReLU(slope). */
+int irc_smallk_conv_fwd(const irc_im2col_args* args, const void* w, const float* bias, int act, float slope, void* out, void* stream);
 
 /* Transpose of irc_im2col (zero padding only): out[n][c][y][x] (+)= sum de[row][(r*k+s)*C+c]. */
 typedef struct irc_col2im_args {

@@ -19,7 +19,7 @@ MAX_TAPS = 64
 EXPORTS = [
     "irc_version", "irc_arch_check", "irc_last_error", "irc_conv_gemm", "irc_conv_stats_workspace_floats", "irc_conv_stats_finalize", "irc_tn_gemm", "irc_tn_gemm_ctas", "irc_row_index",
     "irc_in_stats", "irc_gather", "irc_in_apply_fused", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_in_bwd_fused", "irc_in_bwd_l2", "irc_maxpool2", "irc_maxpool2_bwd",
-    "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
+    "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_smallk_conv_fwd", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
     "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics",
     "irc_adam", "irc_accumulate", "irc_gather_f32", "irc_convT2d_fwd", "irc_pack_bf16", "irc_gather_sum", "irc_gather_sum_multi", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
     "irc_resize_area_u8", "irc_u8_to_pm1",
@@ -44,6 +44,7 @@ class ConvGemmArgs(C.Structure):
         ("stats_part", C.c_void_p), ("stats_edge", C.c_void_p), ("rows_per_img", C.c_int),
         ("tap_out", C.c_void_p), ("tap_nshift", C.c_int), ("tap_nco", C.c_int), ("tap_H", C.c_int), ("tap_W", C.c_int), ("tap_hp", C.c_int),
         ("tap_wp", C.c_int), ("tap_oy", C.c_int), ("tap_ox", C.c_int), ("tap_act", C.c_int),
+        ("tap_scale", C.c_void_p), ("tap_accumulate", C.c_int),
     ]
 
 
@@ -292,7 +293,10 @@ class CudaBackend:
         self.fused_outc = os.environ.get("IRC_FUSED_OUTC", "1") != "0"      # tap reduction + bias + tanh in the GEMM epilogue of the output head
         self.gather_mode = os.environ.get("IRC_GATHER", "auto")     # lean | tiled | generic (stencil gather kernel choice)
         self.conv_epilogue_direct = int(os.environ.get("IRC_EPI_DIRECT", "0"))
-        self.conv_reuse = int(os.environ.get("IRC_CONV_REUSE", "0"))
+        # tap-run conv_gemm (one staged A box per kernel row of taps): -1 = the library decides per layer, 0 never, 1 wherever taps form runs
+        self.conv_reuse = int(os.environ.get("IRC_CONV_REUSE", "-1"))
+        # inc / VGG conv1_1 / D model.0 as direct convolutions (no im2col operand round trip); 0 = im2col + one-tap GEMM
+        self.direct_smallk = os.environ.get("IRC_DIRECT_SMALLK", "1") != "0"
 
     def time_all_launchers(self):
         """bench.py --breakdown-all: bracket EVERY launcher call with CUDA events (eager mode) so that the memory-bound
@@ -300,7 +304,7 @@ class CudaBackend:
         self.timers_all = []
         names = ["in_stats", "gather", "in_apply", "in_bwd", "fold_inplace", "maxpool2", "maxpool2_bwd", "colsum", "im2col", "col2im",
                  "tap_reduce", "tap_expand", "pixel_loss", "ssim_fwd", "ssim_bwd", "hinge", "feat_l1", "adam", "pack_bf16", "gather_sum",
-                 "conv_gemm", "tn_gemm", "zero_"]
+                 "conv_gemm", "tn_gemm", "zero_", "smallk_conv_fwd"]
         for name in names:
             orig = getattr(self, name)
 
@@ -308,7 +312,7 @@ class CudaBackend:
                 if self.timers_all is None:
                     return _orig(*a, **k)
                 tag = ",".join(str(v) for v in a if isinstance(v, int) and not isinstance(v, bool))[:40]
-                if _name in ("conv_gemm", "tn_gemm"):
+                if _name in ("conv_gemm", "tn_gemm", "smallk_conv_fwd"):
                     tag = self.note[0] + ":" + self.note[1]
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(); r = _orig(*a, **k); e1.record()
@@ -360,6 +364,7 @@ class CudaBackend:
         if tap is not None:
             g.tap_out = tap["out"].data_ptr(); g.tap_nshift = tap["nshift"]; g.tap_nco = tap["nco"]; g.tap_H = tap["H"]; g.tap_W = tap["W"]
             g.tap_hp = tap["hp"]; g.tap_wp = tap["wp"]; g.tap_oy = tap["oy"]; g.tap_ox = tap["ox"]; g.tap_act = tap["act"]
+            g.tap_scale = _p(tap.get("scale")); g.tap_accumulate = int(bool(tap.get("accumulate", False)))
         self._timed("conv_gemm", lambda: check(self.L.irc_conv_gemm(C.byref(g), _stream()))); self.launches += 1
         if fin is not None:
             part, edge, n_img, rows_per_img, n_out_, stats = fin
@@ -510,6 +515,23 @@ class CudaBackend:
         assert dst.shape[1] == 64 and dst.shape[0] == self.im2col_rows(row_mode, n_img, Ho, Wo)
         g.dst = dst.data_ptr(); g.row_img = None if row_img is None else row_img.data_ptr()
         check(self.L.irc_im2col(C.byref(g), _stream())); self.launches += 1
+
+    def smallk_conv_fwd(self, src1, src2, scale, shift, n_img, H, W, k, stride, pad, pad_mode, Ho, Wo, row_mode, w, out, bias=None, act=0,
+                        slope=0.0, E=None, row_img=None):
+        """direct small-K convolution (inc, VGG conv1_1, D model.0): im2col geometry of `im2col`, weights w [64, 64] bf16, bf16 rows
+        out [rows, 64]; E (optional) also receives the im2col operand for the weight gradient"""
+        g = Im2colArgs()
+        g.src1 = src1.data_ptr(); g.c1 = src1.shape[1]
+        g.src2 = None if src2 is None else src2.data_ptr(); g.c2 = 0 if src2 is None else src2.shape[1]
+        g.scale = None if scale is None else scale.data_ptr(); g.shift = None if shift is None else shift.data_ptr()
+        g.n_img = n_img; g.H = H; g.W = W; g.k = k; g.stride = stride; g.pad = pad; g.pad_mode = pad_mode
+        g.Ho = Ho; g.Wo = Wo; g.row_mode = row_mode
+        rows = self.im2col_rows(row_mode, n_img, Ho, Wo)
+        assert out.shape == (rows, 64) and out.is_contiguous() and tuple(w.shape) == (64, 64) and w.is_contiguous()
+        assert E is None or (E.shape == (rows, 64) and E.is_contiguous())
+        g.dst = None if E is None else E.data_ptr(); g.row_img = None if row_img is None else row_img.data_ptr()
+        self._timed("smallk_conv", lambda: check(self.L.irc_smallk_conv_fwd(C.byref(g), _p(w), _p(bias), int(act), C.c_float(slope), _p(out), _stream())))
+        self.launches += 1
 
     def col2im(self, de, C_, c_first, c_out, n_img, H, W, k, stride, pad, Ho, Wo, row_mode, scale, out, accumulate):
         g = Col2imArgs()

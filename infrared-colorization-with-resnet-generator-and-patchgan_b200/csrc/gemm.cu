@@ -101,6 +101,8 @@ struct ConvParams {
     // out[n][co][y][x] = act(bias[co] + sum_j acc[q + j - halo][j * nco + co]); tiles overlap by 2 * halo rows
     float* tap_out;
     int tap_nshift, tap_nco, tap_H, tap_W, tap_hp, tap_wp, tap_oy, tap_ox, tap_act;
+    const float* tap_scale;  // optional per-plane factor
+    int tap_accumulate;      // 1: tap_out += result
     int nstg;       // staging tiles of the TMA-store epilogue (2, or 1 when shared memory is needed for pipeline stages)
     int tma_store;  // 1: bf16 rows leave through a swizzled shared-memory staging tile and TMA stores (coalesced)
 };
@@ -299,8 +301,50 @@ __device__ __forceinline__ void epilogue_tapsum(const ConvParams& p, long long r
             float acc = p.bias ? __ldg(p.bias + co) : 0.f;
             for (int j = 0; j < p.tap_nshift; ++j) acc += strip[(r + j - halo) * ld + j * p.tap_nco + co];
             if (p.tap_act == 3) acc = tanhf(acc);
-            p.tap_out[((long long)n * p.tap_nco + co) * hw + (long long)y * p.tap_W + x] = acc;
+            if (p.tap_scale) acc *= __ldg(p.tap_scale + co);
+            float* o = p.tap_out + ((long long)n * p.tap_nco + co) * hw + (long long)y * p.tap_W + x;
+            *o = p.tap_accumulate ? *o + acc : acc;
         }
+    }
+}
+
+// Epilogue role of the persistent conv kernels: 8 warps (two per TMEM lane quarter) drain the accumulator of every tile this
+// CTA owns - staged TMA-store epilogue, direct stores, or the horizontal tap reduction - and hand the buffer back to the MMA warp.
+template <int MT>
+__device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, const CUtensorMap* tmOut, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
+                                                   uint8_t* stg, const float* sbias, long long total_tiles) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t acc_cols = (uint32_t)(MT * p.bn);
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;             // which of the two warps of the quarter
+    const int r_in_tile = quarter * 32 + lane;
+    EpiCtx e;
+    e.slope_eff = p.act == 1 ? 0.f : (p.act == 2 ? p.slope : 1.f);
+    e.sbias = p.bias ? sbias : nullptr;
+    int acc = 0; uint32_t acc_phase = 0;
+    uint32_t stg_iter = 0;
+    const bool store_thread = warp == 2 && lane == 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (int)(tile % p.n_tiles) * p.bn;
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        if (p.tap_out) {
+            epilogue_tapsum<MT>(p, (tile / p.n_tiles) * p.tile_stride + p.row_bias, tmem_base + (uint32_t)acc * acc_cols, quarter, half,
+                                reinterpret_cast<float*>(stg), &tempty[acc]);
+            if (++acc == p.nbuf) { acc = 0; acc_phase ^= 1; }
+            continue;
+        }
+#pragma unroll 1
+        for (int m = 0; m < MT; ++m) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(m * p.bn);
+            const long long srow0 = (tile / p.n_tiles) * p.tile_stride + p.row_bias + m * kBM;
+            if (p.tma_store) epilogue_subtile_staged(p, e, tmOut, srow0, r_in_tile, n0, taddr, half, stg, stg_iter, store_thread);
+            else epilogue_subtile(p, e, srow0 + r_in_tile, n0, taddr, half);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (++acc == p.nbuf) { acc = 0; acc_phase ^= 1; }
     }
 }
 
@@ -409,38 +453,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constan
             }
         }
     } else {
-        // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
-        const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;             // which of the two warps of the quarter
-        const int r_in_tile = quarter * 32 + lane;
-        EpiCtx e;
-        e.slope_eff = p.act == 1 ? 0.f : (p.act == 2 ? p.slope : 1.f);
-        e.sbias = p.bias ? sbias : nullptr;
-        int acc = 0; uint32_t acc_phase = 0;
-        uint32_t stg_iter = 0;
-        const bool store_thread = warp == 2 && lane == 0;
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n0 = (int)(tile % p.n_tiles) * p.bn;
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
-            if (p.tap_out) {
-                epilogue_tapsum<MT>(p, (tile / p.n_tiles) * p.tile_stride + p.row_bias, tmem_base + (uint32_t)acc * acc_cols, quarter, half,
-                                    reinterpret_cast<float*>(stg), &tempty[acc]);
-                if (++acc == p.nbuf) { acc = 0; acc_phase ^= 1; }
-                continue;
-            }
-#pragma unroll 1
-            for (int m = 0; m < MT; ++m) {
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(m * p.bn);
-                const long long srow0 = (tile / p.n_tiles) * p.tile_stride + p.row_bias + m * kBM;
-                if (p.tma_store) epilogue_subtile_staged(p, e, &tmOut, srow0, r_in_tile, n0, taddr, half, stg, stg_iter, store_thread);
-                else epilogue_subtile(p, e, srow0 + r_in_tile, n0, taddr, half);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (++acc == p.nbuf) { acc = 0; acc_phase ^= 1; }
-        }
+        conv_epilogue_loop<MT>(p, &tmOut, tmem_base, tfull, tempty, stg, sbias, total_tiles);
     }
 
     if (p.tma_store && warp == 2 && lane == 0) bulk_wait_group<0>();      // all output tiles have left shared memory
@@ -594,15 +607,18 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_co
 // conv_gemm with A-tile reuse across horizontal taps ("tap runs")
 // ------------------------------------------------------------------------------------
 // Taps whose row shifts are consecutive integers (the kw taps of one kernel row) read the same pixels shifted by one
-// frame row each.  One TMA box of 128 + L - 1 rows is staged per (run, channel chunk) and the L taps issue their MMAs
-// from it through descriptors whose start address is advanced by 128 bytes (one pixel row) per tap; the swizzle phase
-// of the shifted start goes into the descriptor's base-offset field.  A and B travel through separate rings.
+// frame row each.  The plain kernel fetches the A tile once per tap: with Cout <= 128 that is 9 x 16 KB of L2 -> shared-memory
+// traffic per 128 x 64-channel block for only 64..128 MMA columns, and the layer runs at the L2 slice bandwidth
+// (~6300 B/clk chip-wide), not at the tensor rate (V.2 forward: 2.96 GB in 242 us = 12.2 TB/s, 0.47 of the bf16 peak).
+// Here ONE box of 128 * MT + 8 rows is staged per (run, channel chunk) and the L taps of the run issue their MMAs from it
+// through descriptors whose start address is advanced by 128 bytes (one pixel row) per tap: a third of the A traffic for
+// 3 x 3 kernels.  The weight tiles travel through their own ring (one stage per tap and channel chunk).
 struct RunParams {
     int nruns;
     int run_first[IRC_MAX_TAPS];   // smallest row shift of the run
     int run_len[IRC_MAX_TAPS];
     int run_tap[IRC_MAX_TAPS][8];  // original tap index (-> weight K offset) of each member, ascending shift
-    int sa_stages, sb_stages, a_stage_bytes, a_box_rows, base_off_mode;
+    int sa_stages, sb_stages, a_stage_bytes, base_off_mode;
 };
 
 // Measured on B200 (scripts/try_reuse.py): the 128-byte swizzle phase is taken from the absolute shared-memory
@@ -614,12 +630,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_shifted(uint32_t smem_addr, 
     return d;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
-conv_gemm_runs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p,
-                      const RunParams rp) {
+template <int MT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_runs_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA8,
+                      const __grid_constant__ CUtensorMap tmB, const ConvParams p, const RunParams rp) {
     irc::pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int tile_rows = kBM * MT;
+    constexpr int a_box = tile_rows > 256 ? 256 : tile_rows;
     const int SA = rp.sa_stages, SB = rp.sb_stages;
     const int stage_b = p.bn * 128;
     uint8_t* smA = smem;
@@ -632,18 +651,21 @@ conv_gemm_runs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint64_t* tfull = emptyB + SB;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    uint8_t* stg = (uint8_t*)bars + 1024;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long m_tiles = (p.rows + kBM - 1) / kBM;
+    const long long m_tiles = (p.rows + p.tile_stride - 1) / p.tile_stride;
     const long long total_tiles = m_tiles * p.n_tiles;
-    const uint32_t acc_cols = (uint32_t)p.bn;
+    const uint32_t acc_cols = (uint32_t)(MT * p.bn);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmA8);
         tma_prefetch_desc(&tmB);
+        if (p.tma_store) tma_prefetch_desc(&tmOut);
         for (int s = 0; s < SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
         for (int s = 0; s < SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         fence_barrier_init();
     }
     __shared__ __align__(16) float sbias[512];
@@ -655,93 +677,86 @@ conv_gemm_runs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        {
-            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            const uint32_t a_bytes = (uint32_t)rp.a_box_rows * 128u;
-            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const long long row0 = (tile / p.n_tiles) * kBM;
-                const int n0 = (int)(tile % p.n_tiles) * p.bn;
-                for (int r = 0; r < rp.nruns; ++r) {
-                    for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        mbar_wait(&emptyA[sa], pa ^ 1);
+        // ===================== TMA producer =====================
+        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+        const uint32_t a_bytes = (uint32_t)(tile_rows + 8) * 128u;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const long long row0 = (tile / p.n_tiles) * p.tile_stride + p.row_bias;
+            const int n0 = (int)(tile % p.n_tiles) * p.bn;
+            for (int r = 0; r < rp.nruns; ++r) {
+                const int arow = (int)(row0 + rp.run_first[r]);
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(&emptyA[sa], pa ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&fullA[sa], a_bytes);
+                        uint8_t* dst = smA + (size_t)sa * rp.a_stage_bytes;
+                        for (int q = 0; q < tile_rows; q += a_box)
+                            tma_load_2d(dst + q * 128, &tmA, &fullA[sa], p.a_chan_off + kc * kBK, arow + q);
+                        tma_load_2d(dst + tile_rows * 128, &tmA8, &fullA[sa], p.a_chan_off + kc * kBK, arow + tile_rows);   // the rows the shifted taps reach into
+                    }
+                    __syncwarp();
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                    for (int j = 0; j < rp.run_len[r]; ++j) {
+                        mbar_wait(&emptyB[sb], pb ^ 1);
                         if (elect_one()) {
-                            mbar_expect_tx(&fullA[sa], a_bytes);
-                            tma_load_2d(smA + (size_t)sa * rp.a_stage_bytes, &tmA, &fullA[sa], p.a_chan_off + kc * kBK, (int)(row0 + rp.run_first[r]));
+                            mbar_expect_tx(&fullB[sb], stage_b);
+                            tma_load_2d(smB + (size_t)sb * stage_b, &tmB, &fullB[sb], (rp.run_tap[r][j] * p.k_chunks + kc) * kBK, n0);
                         }
                         __syncwarp();
-                        if (++sa == SA) { sa = 0; pa ^= 1; }
-                        for (int j = 0; j < rp.run_len[r]; ++j) {
-                            mbar_wait(&emptyB[sb], pb ^ 1);
-                            if (elect_one()) {
-                                mbar_expect_tx(&fullB[sb], stage_b);
-                                tma_load_2d(smB + (size_t)sb * stage_b, &tmB, &fullB[sb], (rp.run_tap[r][j] * p.k_chunks + kc) * kBK, n0);
-                            }
-                            __syncwarp();
-                            if (++sb == SB) { sb = 0; pb ^= 1; }
-                        }
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        {
-            const uint32_t idesc = umma_idesc_bf16(kBM, p.bn, 0, 0);
-            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
-                uint32_t first = 1;
-                for (int r = 0; r < rp.nruns; ++r) {
-                    for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        mbar_wait(&fullA[sa], pa);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(smA + (size_t)sa * rp.a_stage_bytes);
-                        for (int j = 0; j < rp.run_len[r]; ++j) {
-                            mbar_wait(&fullB[sb], pb);
-                            tc_fence_after();
-                            const uint64_t adesc = umma_desc_sw128_shifted(a_addr + (uint32_t)j * 128u, rp.base_off_mode);
-                            const uint64_t bdesc = umma_desc_sw128(smem_u32(smB + (size_t)sb * stage_b), 16);
-                            if (elect_one()) {
-#pragma unroll
-                                for (int k = 0; k < kBK / 16; ++k)
-                                    umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (first && k == 0) ? 0u : 1u);
-                                umma_commit(&emptyB[sb]);
-                            }
-                            __syncwarp();
-                            first = 0;
-                            if (++sb == SB) { sb = 0; pb ^= 1; }
-                        }
-                        if (elect_one()) umma_commit(&emptyA[sa]);
-                        __syncwarp();
-                        if (++sa == SA) { sa = 0; pa ^= 1; }
-                    }
-                }
-                if (elect_one()) umma_commit(&tfull[acc]);
-                __syncwarp();
-                acc ^= 1; if (acc == 0) acc_phase ^= 1;
-            }
-        }
-    } else {
-        const int quarter = warp & 3;
-        const int r_in_tile = quarter * 32 + lane;
-        EpiCtx e;
-        e.slope_eff = p.act == 1 ? 0.f : (p.act == 2 ? p.slope : 1.f);
-        e.sbias = p.bias ? sbias : nullptr;
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = umma_idesc_bf16(kBM, p.bn, 0, 0);
+        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n0 = (int)(tile % p.n_tiles) * p.bn;
-            mbar_wait(&tfull[acc], acc_phase);
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
             tc_fence_after();
-            epilogue_subtile(p, e, (tile / p.n_tiles) * kBM + r_in_tile, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols, 0);
-            if (p.bn > 32) epilogue_subtile(p, e, (tile / p.n_tiles) * kBM + r_in_tile, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols, 1);
-            tc_fence_before();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
+            uint32_t started = 0;
+            for (int r = 0; r < rp.nruns; ++r) {
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(&fullA[sa], pa);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smA + (size_t)sa * rp.a_stage_bytes);
+                    for (int j = 0; j < rp.run_len[r]; ++j) {
+                        mbar_wait(&fullB[sb], pb);
+                        tc_fence_after();
+                        const uint64_t adesc = umma_desc_sw128_shifted(a_addr + (uint32_t)j * 128u, rp.base_off_mode);
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(smB + (size_t)sb * stage_b), 16);
+                        if (elect_one()) {
+                            // consecutive MMAs go to different accumulators (independent chains, see conv_gemm_kernel)
+#pragma unroll
+                            for (int k = 0; k < kBK / 16; ++k) {
+#pragma unroll
+                                for (int m = 0; m < MT; ++m)
+                                    umma_bf16(d_tmem + (uint32_t)(m * p.bn), adesc + (uint64_t)(m * (kBM * 128 / 16) + k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                              k == 0 ? started : 1u);
+                            }
+                            umma_commit(&emptyB[sb]);
+                        }
+                        __syncwarp();
+                        started = 1;
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                    }
+                    if (elect_one()) umma_commit(&emptyA[sa]);
+                    __syncwarp();
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                }
+            }
+            if (elect_one()) umma_commit(&tfull[acc]);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            if (++acc == p.nbuf) { acc = 0; acc_phase ^= 1; }
         }
+    } else {
+        conv_epilogue_loop<MT>(p, &tmOut, tmem_base, tfull, tempty, stg, sbias, total_tiles);
     }
+
+    if (p.tma_store && warp == 2 && lane == 0) bulk_wait_group<0>();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -1345,6 +1360,7 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     p.stats_part = a->stats_part; p.stats_edge = a->stats_edge; p.rows_per_img = a->rows_per_img;
     p.tap_out = a->tap_out; p.tap_nshift = a->tap_nshift; p.tap_nco = a->tap_nco; p.tap_H = a->tap_H; p.tap_W = a->tap_W; p.tap_hp = a->tap_hp;
     p.tap_wp = a->tap_wp; p.tap_oy = a->tap_oy; p.tap_ox = a->tap_ox; p.tap_act = a->tap_act;
+    p.tap_scale = a->tap_scale; p.tap_accumulate = a->tap_accumulate;
     if (tapsum) {
         const int halo = (a->tap_nshift - 1) / 2;
         p.tile_stride = kBM * mt - 2 * halo; p.row_bias = -halo;
@@ -1381,49 +1397,53 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     }
     const long long tiles = ((a->a_rows + p.tile_stride - 1) / p.tile_stride) * p.n_tiles;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    // tap-run variant: worthwhile when taps form runs (kw > 1); reuse = 0 off, 1 on, -1/auto
+    // CTA pairs (cta_group::2) win where the weight tile is wide and the reduction deep (measured per layer,
+    // profiles/gemm_breakdown_r2_pair.csv: ResNet blocks 0.84 -> 0.93 of the sustained peak, VGG conv3_x 0.91 -> 1.00, up1 0.77 -> 0.82)
+    const int kred = a->ntaps * a->cin;
+    const bool pair_auto = ((bn == 256 && kred >= 1024) || (bn == 128 && kred >= 2048)) && a->a_rows >= (long long)sms * 128;
+    // tap-run variant: taps with consecutive row shifts share one staged A box (reuse = 0 off, 1 on wherever taps form runs,
+    // -1 auto: the layers the pair kernel does not take, i.e. the L2-bandwidth-bound ones with <= 128 output columns)
     RunParams rp;
     build_runs(a->taps, a->ntaps, rp);
     int max_len = 1;
     for (int r = 0; r < rp.nruns; ++r) if (rp.run_len[r] > max_len) max_len = rp.run_len[r];
-    const int reuse = a->reuse < 0 ? (max_len > 1 ? 1 : 0) : a->reuse;
-    if (reuse && max_len > 1 && !tapsum && !p.stats_part) {
-        rp.a_box_rows = kBM + max_len - 1;
-        rp.a_stage_bytes = ((rp.a_box_rows * 128 + 1023) / 1024) * 1024;
+    const bool runs_auto = max_len > 1 && !pair_auto && bn <= 128 && a->a_rows >= (long long)sms * 128;
+    if (max_len > 1 && !tapsum && (a->reuse > 0 || (a->reuse < 0 && runs_auto))) {
+        rp.a_stage_bytes = (kBM * mt + 8) * 128;
         rp.base_off_mode = a->reuse == 3 ? 1 : 0;      // 3 = the (wrong) base-offset encoding, kept for the experiment script
         const int stage_b = bn * 128;
-        // split shared memory: enough B stages for ~2 A stages worth of taps, the rest to A
+        const int stg_b = p.tma_store ? 2 * kBM * 128 + 1024 : 0;
+        const int budget = kMaxSmem - kStatic - 2048 - stg_b;
         int sb = 2 * max_len; if (sb > 8) sb = 8;
-        while (sb > 2 && (size_t)sb * stage_b + 2 * rp.a_stage_bytes > (size_t)kMaxSmem - 4096) --sb;
-        int sa = (int)(((size_t)kMaxSmem - 4096 - (size_t)sb * stage_b) / rp.a_stage_bytes);
+        while (sb > 2 && budget - sb * stage_b < 2 * rp.a_stage_bytes) --sb;
+        int sa = (budget - sb * stage_b) / rp.a_stage_bytes;
         if (sa > 6) sa = 6;
         if (sa < 2) return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: tap-run tile does not fit shared memory");
-        int extra = (int)(((size_t)kMaxSmem - 4096 - (size_t)sa * rp.a_stage_bytes) / stage_b);
+        const int extra = (budget - sa * rp.a_stage_bytes) / stage_b;
         if (extra > sb) sb = extra > 8 ? 8 : extra;
         rp.sa_stages = sa; rp.sb_stages = sb;
-        CUtensorMap tmA2;
-        rc = make_map(&tmA2, a->a, a->a_rows, a->a_ld, rp.a_box_rows);
+        CUtensorMap tmA8;
+        rc = make_map(&tmA8, a->a, a->a_rows, a->a_ld, 8);
         if (rc) return rc;
-        ConvParams q = p; q.mt = 1; q.nbuf = 2;
-        const size_t smem2 = (size_t)sa * rp.a_stage_bytes + (size_t)sb * stage_b + 2048;
+        ConvParams q = p; q.nstg = 2;
+        const size_t smem2 = (size_t)sa * rp.a_stage_bytes + (size_t)sb * stage_b + 2048 + stg_b;
         if (!g_attr_runs) {
-            if (cudaFuncSetAttribute(conv_gemm_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 2048) != cudaSuccess)
+            if (cudaFuncSetAttribute(conv_gemm_runs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 2048) != cudaSuccess ||
+                cudaFuncSetAttribute(conv_gemm_runs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 2048) != cudaSuccess ||
+                cudaFuncSetAttribute(conv_gemm_runs_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 2048) != cudaSuccess)
                 return irc_check_launch("cudaFuncSetAttribute(conv_gemm_runs)");
             g_attr_runs = true;
         }
-        const long long tiles1 = ((a->a_rows + kBM - 1) / kBM) * p.n_tiles;
-        irc::launch<1>(conv_gemm_runs_kernel, (int)(tiles1 < sms ? tiles1 : sms), kThreads, smem2, (cudaStream_t)stream, tmA2, tmB, q, rp);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (mt == 1) irc::launch<1>(conv_gemm_runs_kernel<1>, grid, kConvThreads, smem2, st, tmOut, tmA, tmA8, tmB, q, rp);
+        else if (mt == 2) irc::launch<1>(conv_gemm_runs_kernel<2>, grid, kConvThreads, smem2, st, tmOut, tmA, tmA8, tmB, q, rp);
+        else irc::launch<1>(conv_gemm_runs_kernel<4>, grid, kConvThreads, smem2, st, tmOut, tmA, tmA8, tmB, q, rp);
         return irc_check_launch("irc_conv_gemm(runs)");
     }
     // CTA pairs (cta_group::2): IRC_CONV_PAIR=1 all eligible launches, =0 never, default: auto (see pair_auto)
     static int pair_mode = -2;
     if (pair_mode == -2) { const char* e = getenv("IRC_CONV_PAIR"); pair_mode = e ? atoi(e) : -1; }
     const bool pair_ok = !tapsum && (bn == 64 || bn == 128 || bn == 256) && a->mt <= 1 && sms >= 2;
-    // measured per layer (profiles/gemm_breakdown_r2_pair.csv): pairs win where the weight tile is wide and the reduction deep
-    // (ResNet blocks 0.84 -> 0.93 of the sustained peak, VGG conv3_x 0.91 -> 1.00, up1 0.77 -> 0.82); the narrow N = 64 layers
-    // keep the single-CTA kernel, whose several row sub-tiles per weight stage serve them better
-    const int kred = a->ntaps * a->cin;
-    const bool pair_auto = ((bn == 256 && kred >= 1024) || (bn == 128 && kred >= 2048)) && a->a_rows >= (long long)sms * 128;
     if (pair_ok && (pair_mode == 1 || (pair_mode == -1 && pair_auto))) {
         ConvParams q = p; q.mt = 1; q.nbuf = 2; q.tile_stride = 2 * kBM; q.row_bias = 0;
         CUtensorMap tmA1, tmBh;

@@ -136,6 +136,189 @@ __global__ void __launch_bounds__(256) im2col_kernel(const Im2colP p, int R, int
     }
 }
 
+// ------------------------------------------------------------------------------------
+// Direct small-K convolution (inc 1->64 7x7 irc:458-463, VGG conv1_1 3->64 3x3 irc:664, D model.0 4->64 4x4 s2 irc:600)
+// ------------------------------------------------------------------------------------
+// The im2col operand of these layers (64 bf16 slots per output pixel) is 16..30x larger than the image it is built from;
+// writing it to HBM and reading it back in a one-tap GEMM makes the layer a pair of layout passes (VGG conv1_1 at 2 x 16
+// images of 256 x 256: 272 MB written, 272 MB read, 272 MB written: 0.32 ms).  Here the block stages the input rows of a group
+// of output lines in shared memory exactly as im2col_kernel does, and every warp multiplies 16 output pixels x K slots,
+// gathered from that tile straight into mma.sync A fragments, with the [64][K] weight matrix held in registers as B fragments;
+// bias / activation / ring zeroing happen on the accumulators and the [16][64] bf16 tile leaves through a per-warp
+// shared-memory transpose as whole 128-byte rows.  HBM traffic = the image once + the output once.  The operand itself is
+// only written (same pass, same fragments) when the caller wants it for the weight gradient (dst != NULL).
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all_() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int kSkPitch = 36;      // u32 per staged output row (32 + 4): conflict-free fragment stores and 16-byte row reads
+
+template <int KS, int MODE, bool KEEP>      // K = 16 * KS slots; row order of RowMap; KEEP: also write the operand E
+__global__ void __launch_bounds__(256, 2) smallk_conv_fwd_kernel(const Im2colP p, const bf16* __restrict__ w, const float* __restrict__ bias, int act, float slope,
+                                                                 bf16* __restrict__ out, int R, int Wp, int LPB) {
+    irc::pdl_prologue();
+    extern __shared__ float tile[];                 // [C][R][Wp] fp32, then 8 warps x (1 + KEEP) x [16][kSkPitch] u32 staging
+    const int C = p.c1 + p.c2;
+    const int K = p.k * p.k * C;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    uint32_t* stage_o = reinterpret_cast<uint32_t*>(tile + (size_t)C * R * Wp) + warp * ((KEEP ? 2 : 1) * 16 * kSkPitch);
+    uint32_t* stage_e = stage_o + 16 * kSkPitch;
+    // operand columns this thread gathers: per k-step the pairs (2t, 2t+1) and (2t+8, 2t+9); columns >= K meet zero weights
+    // (their tile reads stay inside the tile: offset 0), and are masked out of the operand copy
+    int off[KS][4]; uint32_t cmask[KS][2];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = ks * 16 + 2 * t + (j & 1) + (j >> 1) * 8;
+            off[ks][j] = 0;
+            if ((j & 1) == 0) cmask[ks][j >> 1] = 0u;
+            if (col < K) {
+                const int c = col % C, rs = col / C, r = rs / p.k, s_ = rs % p.k;
+                off[ks][j] = (c * R + r) * Wp + s_;
+                cmask[ks][j >> 1] |= (j & 1) ? 0xffff0000u : 0x0000ffffu;
+            }
+        }
+    // B fragments: B[k][n] = w[n][k]; (b0, b1) of n-tile j, k-step ks = w[8j + g][16ks + 2t .. +1], [.. + 8 .. +9]
+    uint32_t bf[KS][8][2];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t* wr = reinterpret_cast<const uint32_t*>(w + (size_t)(8 * j + g) * 64 + ks * 16 + 2 * t);
+            bf[ks][j][0] = __ldg(wr); bf[ks][j][1] = __ldg(wr + 4);
+        }
+    const float slope_eff = act == 1 ? 0.f : (act == 2 ? slope : 1.f);
+    const int Ho = p.rm.Ho, Wo = p.rm.Wo;
+    const int nl = p.rm.lines(), ll = p.rm.line_len();
+    const int ngrp = (nl + LPB - 1) / LPB;
+    const long long hw = (long long)p.H * p.W;
+    const int sWp = p.stride * Wp;
+    for (int bg = blockIdx.x; bg < p.rm.n_img * ngrp; bg += gridDim.x) {
+        const int n = bg / ngrp, line0 = (bg - n * ngrp) * LPB;
+        const int nlines = min(LPB, nl - line0);
+        const int oy0 = MODE == 0 ? line0 : (MODE == 1 ? line0 - 1 : 2 * line0 - 1);
+        const int y_lo = oy0 * p.stride - p.pad;
+        __syncthreads();                            // the previous group's readers are done with the tile
+        // tile fill with 4-byte cp.async: no load -> store dependence, every copy of the block is in flight at once (with plain
+        // loads the ~10 dependent global-load latencies per warp cost more than the arithmetic of the whole group)
+        for (int tt = warp; tt < C * R; tt += 8) {
+            const int c = tt / R, r = tt - c * R;
+            int y = y_lo + r;
+            if (p.pad_mode == 1) y = reflect_idx(y, p.H);
+            const bool oky = y >= 0 && y < p.H;
+            const float* srow = (c < p.c1 ? p.src1 + ((long long)n * p.c1 + c) * hw : p.src2 + ((long long)n * p.c2 + (c - p.c1)) * hw) + (long long)(oky ? y : 0) * p.W;
+            float* trow = tile + tt * Wp;
+            for (int xx = lane; xx < Wp; xx += 32) {
+                int x = xx - p.pad;
+                if (p.pad_mode == 1) x = reflect_idx(x, p.W);
+                if (oky && x >= 0 && x < p.W) cp_async4(trow + xx, srow + x);
+                else trow[xx] = 0.f;
+            }
+        }
+        cp_async_wait_all_();
+        if (p.scale) {
+            // per-channel affine (VGG input normalisation) on the cells this thread copied itself; padding cells stay zero
+            for (int tt = warp; tt < C * R; tt += 8) {
+                const int c = tt / R, r = tt - c * R;
+                const int y = y_lo + r;
+                if (p.pad_mode != 1 && (y < 0 || y >= p.H)) continue;          // reflected cells are image values, zero padding is not
+                const float sc = __ldg(p.scale + c), sh = __ldg(p.shift + c);
+                float* trow = tile + tt * Wp;
+                for (int xx = lane; xx < Wp; xx += 32) {
+                    const int x = xx - p.pad;
+                    if (p.pad_mode == 1 || (x >= 0 && x < p.W)) trow[xx] = fmaf(trow[xx], sc, sh);
+                }
+            }
+        }
+        __syncthreads();
+        // the group's rows are one contiguous range of the flat row order: chunks of 16 rows go round-robin over the warps;
+        // (l, ii) = (line within the group, position in the line) of this thread's first row, advanced without divisions
+        const int nrows = nlines * ll;
+        const long long qbase = ((long long)n * nl + line0) * ll;
+        int l = 0, ii = warp * 16 + g;
+        while (ii >= ll) { ii -= ll; ++l; }
+        for (int i0 = warp * 16; i0 < nrows; i0 += 8 * 16) {
+            int base[2]; bool live[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int lh = l, ih = ii + 8 * h;
+                if (ih >= ll) { ih -= ll; ++lh; }
+                int ry, ox;                          // output row relative to oy0, output column
+                if (MODE == 0) { ry = lh; ox = ih; }
+                else if (MODE == 1) { ry = lh; ox = ih - 1; }
+                else { const int sub = ih & 3; ry = 2 * lh + (sub >> 1); ox = 2 * (ih >> 2) + (sub & 1) - 1; }
+                const int oy = oy0 + ry;
+                live[h] = (i0 + g + 8 * h < nrows) && (MODE == 0 || (oy >= 0 && oy < Ho && ox >= 0 && ox < Wo));
+                base[h] = live[h] ? ry * sWp + ox * p.stride : 0;
+                if (t == 0 && p.row_img && i0 + g + 8 * h < nrows) p.row_img[qbase + i0 + g + 8 * h] = live[h] ? (short)n : (short)-1;
+            }
+            float acc[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const float* t0 = tile + base[0];
+                const float* t1 = tile + base[1];
+                const uint32_t a[4] = {pack_bf16x2(t0[off[ks][0]], t0[off[ks][1]]), pack_bf16x2(t1[off[ks][0]], t1[off[ks][1]]),
+                                       pack_bf16x2(t0[off[ks][2]], t0[off[ks][3]]), pack_bf16x2(t1[off[ks][2]], t1[off[ks][3]])};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mma_bf16_16816(acc[j], a, bf[ks][j][0], bf[ks][j][1]);
+                if (KEEP) {
+                    const uint32_t m0 = live[0] ? 0xffffffffu : 0u, m1 = live[1] ? 0xffffffffu : 0u;
+                    stage_e[g * kSkPitch + ks * 8 + t] = a[0] & cmask[ks][0] & m0; stage_e[(g + 8) * kSkPitch + ks * 8 + t] = a[1] & cmask[ks][0] & m1;
+                    stage_e[g * kSkPitch + ks * 8 + 4 + t] = a[2] & cmask[ks][1] & m0; stage_e[(g + 8) * kSkPitch + ks * 8 + 4 + t] = a[3] & cmask[ks][1] & m1;
+                }
+            }
+            if (KEEP && KS < 4) {
+#pragma unroll
+                for (int ks = KS; ks < 4; ++ks) {
+                    stage_e[g * kSkPitch + ks * 8 + t] = 0u; stage_e[(g + 8) * kSkPitch + ks * 8 + t] = 0u;
+                    stage_e[g * kSkPitch + ks * 8 + 4 + t] = 0u; stage_e[(g + 8) * kSkPitch + ks * 8 + 4 + t] = 0u;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float c0 = acc[j][0], c1 = acc[j][1], c2 = acc[j][2], c3 = acc[j][3];
+                if (bias) {
+                    const float2 bv = __ldg(reinterpret_cast<const float2*>(bias + 8 * j + 2 * t));
+                    c0 += bv.x; c1 += bv.y; c2 += bv.x; c3 += bv.y;
+                }
+                if (act) {
+                    c0 = fmaxf(c0, 0.f) + slope_eff * fminf(c0, 0.f); c1 = fmaxf(c1, 0.f) + slope_eff * fminf(c1, 0.f);
+                    c2 = fmaxf(c2, 0.f) + slope_eff * fminf(c2, 0.f); c3 = fmaxf(c3, 0.f) + slope_eff * fminf(c3, 0.f);
+                }
+                stage_o[g * kSkPitch + j * 4 + t] = live[0] ? pack_bf16x2(c0, c1) : 0u;
+                stage_o[(g + 8) * kSkPitch + j * 4 + t] = live[1] ? pack_bf16x2(c2, c3) : 0u;
+            }
+            __syncwarp();
+            // 16 rows x 128 bytes: lane -> (row, 16-byte chunk), four rows per instruction, consecutive rows are consecutive in memory
+            {
+                const int r = lane >> 3, ch = lane & 7;
+                bf16* op = out + (qbase + i0 + r) * 64 + ch * 8;
+                bf16* ep = KEEP ? p.dst + (qbase + i0 + r) * 64 + ch * 8 : nullptr;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    if (i0 + it * 4 + r < nrows) {
+                        *reinterpret_cast<uint4*>(op + it * 4 * 64) = *reinterpret_cast<const uint4*>(stage_o + (it * 4 + r) * kSkPitch + ch * 4);
+                        if (KEEP) *reinterpret_cast<uint4*>(ep + it * 4 * 64) = *reinterpret_cast<const uint4*>(stage_e + (it * 4 + r) * kSkPitch + ch * 4);
+                    }
+                }
+            }
+            __syncwarp();
+            ii += 8 * 16;
+            while (ii >= ll) { ii -= ll; ++l; }
+        }
+    }
+}
+
 struct Col2imP {
     const bf16* de; long long ld;
     int C, c_first, c_out, H, W, k, stride, pad;
@@ -372,6 +555,46 @@ extern "C" int irc_im2col(const irc_im2col_args* a, void* stream) {
     const long long nblk = (long long)p.rm.n_img * ((p.rm.lines() + LPB - 1) / LPB);
     irc::launch(im2col_kernel, (unsigned)(nblk < 1048576 ? nblk : 1048576), 256, smem, (cudaStream_t)stream, p, R, Wp, LPB);
     return irc_check_launch("irc_im2col");
+}
+
+/* Direct small-K convolution: same geometry arguments as irc_im2col; computes out[q][0..64) = act(bias + sum_k E[q][k] * w[n][k])
+ * for the im2col operand E without materialising it (args->dst may be NULL; when given it ALSO receives E, for the weight gradient). */
+extern "C" int irc_smallk_conv_fwd(const irc_im2col_args* a, const void* w, const float* bias, int act, float slope, void* out, void* stream) {
+    if (!a || !a->src1 || !w || !out) return irc_set_error(IRC_ERR_BAD_ARG, "irc_smallk_conv_fwd: null");
+    const int C = a->c1 + (a->src2 ? a->c2 : 0);
+    const int K = a->k * a->k * C;
+    if (K > 64) return irc_set_error(IRC_ERR_BAD_ARG, "irc_smallk_conv_fwd: k*k*C must be <= 64");
+    if (a->row_mode == 2 && ((a->Ho | a->Wo) & 1)) return irc_set_error(IRC_ERR_BAD_ARG, "irc_smallk_conv_fwd: row_mode 2 needs even output extents");
+    if (((uintptr_t)out & 15) || ((uintptr_t)a->dst & 15) || ((uintptr_t)w & 3)) return irc_set_error(IRC_ERR_BAD_ARG, "irc_smallk_conv_fwd: misaligned operand");
+    Im2colP p;
+    p.src1 = a->src1; p.src2 = a->src2; p.c1 = a->c1; p.c2 = a->src2 ? a->c2 : 0;
+    p.scale = a->scale; p.shift = a->shift;
+    p.H = a->H; p.W = a->W; p.k = a->k; p.stride = a->stride; p.pad = a->pad; p.pad_mode = a->pad_mode;
+    p.rm.mode = a->row_mode; p.rm.n_img = a->n_img; p.rm.Ho = a->Ho; p.rm.Wo = a->Wo;
+    p.dst = (bf16*)a->dst; p.row_img = a->row_img;
+    const int LPB = a->row_mode == 2 ? 2 : 4;
+    const int rows_out = LPB * (a->row_mode == 2 ? 2 : 1);
+    const int R = (rows_out - 1) * a->stride + a->k, Wp = a->W + 2 * a->pad;
+    const bool keep = a->dst != nullptr;
+    const size_t smem = (size_t)C * R * Wp * sizeof(float) + 8 * (keep ? 2 : 1) * 16 * kSkPitch * sizeof(uint32_t);
+    if (smem > 100 * 1024) return irc_set_error(IRC_ERR_BAD_ARG, "irc_smallk_conv_fwd: line tile does not fit shared memory");
+    const long long nblk = (long long)p.rm.n_img * ((p.rm.lines() + LPB - 1) / LPB);
+    const unsigned grid = (unsigned)(nblk < 1048576 ? nblk : 1048576);
+    const int ks = K <= 32 ? 2 : 4;
+    bool ok = false;
+#define IRC_SMALLK_CASE(KS_, MODE_, KEEP_)                                                                                                         \
+    if (!ok && ks == KS_ && a->row_mode == MODE_ && keep == KEEP_) {                                                                              \
+        static bool attr = false;                                                                                                                  \
+        if (!attr) { cudaFuncSetAttribute(smallk_conv_fwd_kernel<KS_, MODE_, KEEP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
+        irc::launch(smallk_conv_fwd_kernel<KS_, MODE_, KEEP_>, grid, 256, smem, (cudaStream_t)stream, p, (const bf16*)w, bias, act, slope, (bf16*)out, R, Wp, LPB); \
+        ok = true;                                                                                                                                 \
+    }
+    IRC_SMALLK_CASE(2, 0, false) IRC_SMALLK_CASE(2, 0, true) IRC_SMALLK_CASE(2, 1, false) IRC_SMALLK_CASE(2, 1, true)
+    IRC_SMALLK_CASE(2, 2, false) IRC_SMALLK_CASE(2, 2, true) IRC_SMALLK_CASE(4, 0, false) IRC_SMALLK_CASE(4, 0, true)
+    IRC_SMALLK_CASE(4, 1, false) IRC_SMALLK_CASE(4, 1, true) IRC_SMALLK_CASE(4, 2, false) IRC_SMALLK_CASE(4, 2, true)
+#undef IRC_SMALLK_CASE
+    if (!ok) return irc_set_error(IRC_ERR_BAD_ARG, "irc_smallk_conv_fwd: bad row_mode %d", a->row_mode);
+    return irc_check_launch("irc_smallk_conv_fwd");
 }
 
 extern "C" int irc_col2im(const irc_col2im_args* a, void* stream) {

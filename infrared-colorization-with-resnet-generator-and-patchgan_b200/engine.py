@@ -280,9 +280,14 @@ class GeneratorEngine:
         be, B, H, W = self.be, self.B, self.H, self.W
         H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
         assert ir.shape == (B, 1, H, W) and ir.dtype == torch.float32 and ir.is_contiguous()
-        # inc: reflect-pad 3 + 7x7 conv as im2col (49 of 64 slots) + one-tap GEMM, IN + ReLU into cat2[128:192)
-        be.im2col(ir, None, None, None, B, H, W, 7, 1, 3, 1, H, W, 0, self.E_in)
-        self.inc.fwd(self.E_in, 0, self.Z0.t)
+        # inc: reflect-pad 3 + 7x7 conv over 49 of 64 operand slots, IN + ReLU into cat2[128:192)
+        if getattr(be, "direct_smallk", False):
+            # direct convolution from the fp32 image; the im2col operand is only written when the weight gradient will read it
+            be.note = ("G.inc", "fwd", self.inc.flops)
+            be.smallk_conv_fwd(ir, None, None, None, B, H, W, 7, 1, 3, 1, H, W, 0, self.inc.lay.w_f.t, self.Z0.t, E=self.E_in if self.training else None)
+        else:
+            be.im2col(ir, None, None, None, B, H, W, 7, 1, 3, 1, H, W, 0, self.E_in)
+            self.inc.fwd(self.E_in, 0, self.Z0.t)
         be.in_stats(self.Z0.view(), 64, B, H, W, self.st0)
         be.gather(self.Z0.view(), self.cat2.view(128), 64, B, H, W, 1, 0, stats=self.st0, cnt=H * W, eps=EPS, act=ACT_RELU)
         # down1: 3x3 zero-pad conv at full resolution, then IN + ReLU + blur-downsample fused
@@ -483,22 +488,28 @@ class DiscriminatorEngine:
     def _vZ8(self, t):
         return View(t, 0, self.X8.hp, self.X8.wp, 0, 0)
 
-    def forward(self, ir: torch.Tensor, img: torch.Tensor, ir_b: torch.Tensor = None, img_b: torch.Tensor = None) -> torch.Tensor:
+    def forward(self, ir: torch.Tensor, img: torch.Tensor, ir_b: torch.Tensor = None, img_b: torch.Tensor = None, keep_operand: bool = True) -> torch.Tensor:
         """D(cat[ir, img]) -> fp32 [n,1,Ho,Wo] raw scores (irc:632-635).  (ir_b, img_b), if given, is a second
         batch processed behind the first in the same launches (real and fake halves of the D step; InstanceNorm
-        is per sample, so batching is exact)."""
+        is per sample, so batching is exact).  keep_operand=False: the backward pass will not ask for weight gradients
+        (generator step), so model.0's im2col operand need not be written."""
         be, n, H, W = self.be, self.n, self.H, self.W
         # model.0: 4x4 s2 conv on 4 channels = im2col with exactly 64 slots, rows in 2x2 sub-pixel order so the
         # GEMM output *is* the space-to-depth operand of model.2; bias + LeakyReLU in the epilogue
         n1 = ir.shape[0]
         r1 = n1 * (self.H1 + 2) * (self.W1 + 2)
-        be.im2col(ir, img, None, None, n1, H, W, 4, 2, 1, 0, self.H1, self.W1, 2, self.E0[:r1], row_img=self.row_img0[:r1])
-        if ir_b is not None:
-            assert n1 + ir_b.shape[0] == n
-            be.im2col(ir_b, img_b, None, None, n - n1, H, W, 4, 2, 1, 0, self.H1, self.W1, 2, self.E0[r1:], row_img=self.row_img0[r1:])
+        assert n1 == n if ir_b is None else n1 + ir_b.shape[0] == n
+        parts = [(ir, img, n1, slice(0, r1))] + ([] if ir_b is None else [(ir_b, img_b, n - n1, slice(r1, None))])
+        if getattr(be, "direct_smallk", False):
+            # direct convolution (bias + LeakyReLU on the accumulators); the operand E0 is kept only for the weight gradient
+            for a_, b_, k_, sl in parts:
+                be.note = ("D.0", "fwd", self.c0.flops * k_ / n)
+                be.smallk_conv_fwd(a_, b_, None, None, k_, H, W, 4, 2, 1, 0, self.H1, self.W1, 2, self.c0.lay.w_f.t, self.S0[sl], bias=self.c0.bias(),
+                                   act=ACT_LRELU, slope=0.2, E=self.E0[sl] if keep_operand else None, row_img=self.row_img0[sl])
         else:
-            assert n1 == n
-        self.c0.fwd(self.E0, 0, self.S0, bias=self.c0.bias(), act=ACT_LRELU, slope=0.2, row_img=self.row_img0)
+            for a_, b_, k_, sl in parts:
+                be.im2col(a_, b_, None, None, k_, H, W, 4, 2, 1, 0, self.H1, self.W1, 2, self.E0[sl], row_img=self.row_img0[sl])
+            self.c0.fwd(self.E0, 0, self.S0, bias=self.c0.bias(), act=ACT_LRELU, slope=0.2, row_img=self.row_img0)
         # model.2
         self.c2.fwd_stats(self.S0v, 0, self.Z2, self.st2, self.ri2, n, self.hb0 * self.wb0, self._vZ2(self.Z2), 128, self.H2, self.W2)
         be.gather(self._vZ2(self.Z2), View(self.S2, 0, self.hb2, self.wb2), 128, n, self.H2, self.W2, 1, 0, stats=self.st2,
@@ -581,9 +592,22 @@ class VggEngine:
                 taps = L.taps_centered(3, 3, fr.wp)
             self.convs.append(ConvOp(be, lay, taps, A, 64, bias_name=f"features.{idx}.bias", pixels=n_img * h * w, name=f"V.{idx}"))
             self.convs[-1].flops_bwd = 2.0 * lay.param_numel * n_bwd * h * w
+        # data gradient of conv1_1 (64 -> 3 input planes) as a GEMM over the kernel rows + horizontal tap reduction in the epilogue:
+        # column j * 3 + c of tap r holds W[k][c][r][2 - j]  (dx[c][y][x] = sum_{r,s,k} dz[y + 1 - r][x + 1 - s][k] W[k][c][r][s])
+        self.fused_dgrad0 = bool(getattr(be, "direct_smallk", False)) and n_bwd > 0
+        if self.fused_dgrad0:
+            idx = np.full((32, 3, 64), -1, np.int64)
+            base = A.offset["features.0.weight"]
+            for j in range(3):
+                for c in range(3):
+                    for r in range(3):
+                        idx[j * 3 + c, r, :] = L.oihw_index(base, np.arange(64), c, r, 2 - j, 3, 3, 3)
+            self.w0_dg = P.add(idx.reshape(32, 3 * 64))
+            self.P0 = torch.zeros(8, 32, device=device)
         P.finish()
         self.pool = {1: L.Frame(n_img, H // 2, W // 2, 1, 64, device), 3: L.Frame(n_img, H // 4, W // 4, 1, 128, device)}
-        self.E = L.act_zeros(self.act[0].rows, 64, device)
+        # im2col operand of conv1_1: only materialised on the im2col + one-tap GEMM path
+        self.E = None if getattr(be, "direct_smallk", False) else L.act_zeros(self.act[0].rows, 64, device)
         self.row_img = []
         for (h, w) in ((H, W), (H // 2, W // 2), (H // 4, W // 4)):
             ri = torch.zeros(n_img * (h + 2) * (w + 2), device=device, dtype=torch.int16)
@@ -595,7 +619,7 @@ class VggEngine:
         if n_bwd:
             self.dz = [L.Frame(n_bwd, h, w, 1, co, device) for (h, w), (_, _, co) in zip(res, VGG_CFG)]
             self.dpool = {1: L.Frame(n_bwd, H // 2, W // 2, 1, 64, device), 3: L.Frame(n_bwd, H // 4, W // 4, 1, 128, device)}
-            self.dE = L.act_zeros(self.dz[0].rows, 64, device)
+            self.dE = None if self.fused_dgrad0 else L.act_zeros(self.dz[0].rows, 64, device)
 
     def refresh_weights(self):
         self.packer.refresh(self.be)
@@ -609,13 +633,21 @@ class VggEngine:
         n1 = x1.shape[0]
         H, W = self.H, self.W
         rows1 = self.act[0].rows_of(n1)
-        be.im2col(x1, None, self.scale, self.shift, n1, H, W, 3, 1, 1, 0, H, W, 1, self.E[:rows1])
-        if x2 is not None:
-            be.im2col(x2, None, self.scale, self.shift, x2.shape[0], H, W, 3, 1, 1, 0, H, W, 1, self.E[rows1:])
+        parts = [(x1, n1, slice(0, rows1))] + ([] if x2 is None else [(x2, x2.shape[0], slice(rows1, None))])
+        direct = getattr(be, "direct_smallk", False)
+        c0 = self.convs[0]
+        for x_, k_, sl in parts:
+            if direct:
+                # conv1_1 straight from the fp32 image (input normalisation folded into the tile fill), bias + ReLU, zero ring
+                be.note = (c0.name, "fwd", c0.flops * k_ / self.n)
+                be.smallk_conv_fwd(x_, None, self.scale, self.shift, k_, H, W, 3, 1, 1, 0, H, W, 1, c0.lay.w_f.t, self.act[0].t[sl], bias=c0.bias(), act=ACT_RELU)
+            else:
+                be.im2col(x_, None, self.scale, self.shift, k_, H, W, 3, 1, 1, 0, H, W, 1, self.E[sl])
         src = self.E
         for i, conv in enumerate(self.convs):
             fr = self.act[i]
-            conv.fwd(src, 0, fr.t, bias=conv.bias(), act=ACT_RELU, row_img=self._ri(i))
+            if not (direct and i == 0):
+                conv.fwd(src, 0, fr.t, bias=conv.bias(), act=ACT_RELU, row_img=self._ri(i))
             if i in self.pool:
                 h, w = self.res[i + 1]
                 be.maxpool2(fr.view(), self.pool[i].view(), fr.C, self.n, h, w)
@@ -641,5 +673,11 @@ class VggEngine:
             else:
                 prev = self.act[i - 1]
                 conv.dgrad(dz, self.dz[i - 1].t, mask=View(prev.t[:prev.rows_of(nb)], 0, 0, 0), mask_slope=0.0)
-        self.convs[0].dgrad(self.dz[0].t, self.dE)
-        be.col2im(self.dE, 3, 0, 3, nb, self.H, self.W, 3, 1, 1, self.H, self.W, 1, self.scale, dfake, True)
+        if self.fused_dgrad0:
+            d0 = self.dz[0]
+            be.note = (self.convs[0].name, "dgrad", self.convs[0].flops_bwd)
+            be.conv_gemm(d0.t, 0, 64, [d0.wp, 0, -d0.wp], self.w0_dg.t, 32, self.P0,
+                         tap=dict(out=dfake, nshift=3, nco=3, H=self.H, W=self.W, hp=d0.hp, wp=d0.wp, oy=1, ox=1, act=ACT_NONE, scale=self.scale, accumulate=True))
+        else:
+            self.convs[0].dgrad(self.dz[0].t, self.dE)
+            be.col2im(self.dE, 3, 0, 3, nb, self.H, self.W, 3, 1, 1, self.H, self.W, 1, self.scale, dfake, True)

@@ -189,7 +189,7 @@ class TrainStep:
         A = self.D2.arena
         be.adam(A.flat, A.grad, A.m, A.v, self.optD.dev, self.optD.step_dev)                       # irc:1651
         self.D2.refresh_weights()
-        pred_f = self.D1.forward(ir, fake)                                     # irc:1659
+        pred_f = self.D1.forward(ir, fake, keep_operand=False)                                     # irc:1659
         be.hinge(pred_f, 0, 1, lam["gan"] / cnt, 0.0, self.sums[0:3], self.D1.dpred)   # irc:1662, :1679
         self.D1.backward(self.D1.dpred, False, self.dfake)
         # ---------------- generator backward (irc:1680); gradients of everything past the encoder are final once

@@ -102,8 +102,16 @@ class RefBackend:
             self.conv_gemm(a, a_chan_off, cin, taps, w, n_out, P)
             h = (tap["nshift"] - 1) // 2
             n_img = a.shape[0] // (tap["hp"] * tap["wp"])
+            res = torch.zeros_like(tap["out"]) if (tap.get("accumulate") or tap.get("scale") is not None) else tap["out"]
             self.tap_reduce(P, [(0, j - h) for j in range(tap["nshift"])], tap["nco"], n_img, tap["H"], tap["W"], tap["hp"], tap["wp"],
-                            tap["oy"], tap["ox"], bias, tap["act"], tap["out"])
+                            tap["oy"], tap["ox"], bias, tap["act"], res)
+            if res is not tap["out"]:
+                if tap.get("scale") is not None:
+                    res = res * tap["scale"].view(1, -1, 1, 1)
+                if tap.get("accumulate"):
+                    tap["out"] += res
+                else:
+                    tap["out"].copy_(res)
             return
         rows = a.shape[0]
         A = a[:, a_chan_off:a_chan_off + cin].float()
@@ -294,6 +302,21 @@ class RefBackend:
         if row_img is not None:
             row_img.fill_(-1)
             row_img[rm.reshape(-1)] = torch.arange(n_img, device=x.device).view(-1, 1, 1).expand_as(rm).reshape(-1).short()
+
+    direct_smallk = True
+
+    def smallk_conv_fwd(self, src1, src2, scale, shift, n_img, H, W, k, stride, pad, pad_mode, Ho, Wo, row_mode, w, out, bias=None, act=0,
+                        slope=0.0, E=None, row_img=None):
+        e = torch.zeros_like(out) if E is None else E
+        ri = torch.zeros(out.shape[0], dtype=torch.int16, device=out.device)
+        self.im2col(src1, src2, scale, shift, n_img, H, W, k, stride, pad, pad_mode, Ho, Wo, row_mode, e, row_img=ri)
+        v = e.float() @ w.float().t()
+        if bias is not None:
+            v = v + bias.view(1, -1)
+        v = _act(v, act, slope) * (ri >= 0).view(-1, 1)
+        out.copy_(v.to(out.dtype))
+        if row_img is not None:
+            row_img.copy_(ri)
 
     def col2im(self, de, C, c_first, c_out, n_img, H, W, k, stride, pad, Ho, Wo, row_mode, scale, out, accumulate):
         self.launches += 1

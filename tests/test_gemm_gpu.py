@@ -31,7 +31,9 @@ def _conv_ref(A, taps, W, cin, a_off):
     (148 * 256 * 2 + 77, 64, 0, 64, [-1, 0, 1], 128, False),
 ])
 @pytest.mark.parametrize("mt", [1, 2, 4])
-def test_conv_gemm(rows, ld, a_off, cin, taps, n_out, fp32, mt):
+@pytest.mark.parametrize("reuse", [0, 1])
+def test_conv_gemm(rows, ld, a_off, cin, taps, n_out, fp32, mt, reuse):
+    """reuse = 1: the tap-run kernel (one staged A box per kernel row of taps, shifted descriptors) wherever taps form runs"""
     import irc_b200
     from irc_b200 import _native as nat
     nat.arch_check()
@@ -48,7 +50,7 @@ def test_conv_gemm(rows, ld, a_off, cin, taps, n_out, fp32, mt):
         a.taps[i] = t
     a.w = W.data_ptr(); a.n_out = n_out
     a.out = out.data_ptr(); a.out_ld = n_out; a.out_chan_off = 0; a.out_fp32 = int(fp32)
-    a.bias = None; a.act = 0; a.slope = 0.0; a.row_img = None; a.mask = None; a.bn = 0; a.mt = mt
+    a.bias = None; a.act = 0; a.slope = 0.0; a.row_img = None; a.mask = None; a.bn = 0; a.mt = mt; a.reuse = reuse
     nat.check(nat.lib().irc_conv_gemm(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     ref = _conv_ref(A, taps, W, cin, a_off)
@@ -69,9 +71,10 @@ def test_conv_gemm_epilogue():
     img = (torch.arange(rows, device="cuda") // 500).short()
     img[::7] = -1
     addend = torch.randn(rows, 128, device="cuda", generator=g).bfloat16()
-    for mode in ("bias_lrelu_rows", "mask", "addend"):
+    for mode, reuse in [(m, r) for m in ("bias_lrelu_rows", "mask", "addend") for r in (0, 1)]:
         out = torch.full((rows, n_out), float("nan"), device="cuda", dtype=torch.bfloat16)
         a = nat.ConvGemmArgs()
+        a.reuse = reuse
         a.a = A.data_ptr(); a.a_rows = rows; a.a_ld = cin; a.a_chan_off = 0; a.cin = cin; a.ntaps = 3
         for i, t in enumerate(taps):
             a.taps[i] = t

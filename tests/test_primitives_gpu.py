@@ -368,6 +368,60 @@ def test_im2col_col2im(bes, cfg):
         close(a[0], b[0], 1e-5, "col2im")
 
 
+@pytest.mark.parametrize("cfg", [dict(c1=1, c2=0, k=7, s=1, p=3, pm=1, rm=0, act=0), dict(c1=3, c2=0, k=3, s=1, p=1, pm=0, rm=1, aff=True, act=1, bias=True),
+                                 dict(c1=1, c2=3, k=4, s=2, p=1, pm=0, rm=2, act=2, bias=True)])
+@pytest.mark.parametrize("keep", [False, True])
+@pytest.mark.parametrize("size", [(2, 16, 24), (3, 36, 20)])
+def test_smallk_conv_fwd(bes, cfg, keep, size):
+    """direct small-K convolution (inc irc:458-463, VGG conv1_1 irc:664, D model.0 irc:600) == im2col operand x weights in fp32 of
+    the same bf16 values, to one bf16 rounding; the operand by-product is bit-identical to irc_im2col's"""
+    g = gen(16)
+    n, H, W = size
+    s1 = torch.randn(n, cfg["c1"], H, W, device="cuda", generator=g)
+    s2 = torch.randn(n, cfg["c2"], H, W, device="cuda", generator=g) if cfg["c2"] else None
+    C = cfg["c1"] + cfg["c2"]
+    Ho, Wo = H // cfg["s"], W // cfg["s"]
+    sc = torch.rand(C, device="cuda", generator=g) + 0.5 if cfg.get("aff") else None
+    sh = torch.randn(C, device="cuda", generator=g) if cfg.get("aff") else None
+    rows = bes[0].im2col_rows(cfg["rm"], n, Ho, Wo)
+    w = (torch.randn(64, 64, device="cuda", generator=g) * 0.2).bfloat16()
+    w[:, cfg["k"] * cfg["k"] * C:] = 0
+    bias = torch.randn(64, device="cuda", generator=g) if cfg.get("bias") else None
+
+    def fn(be, out, E, ri):
+        be.smallk_conv_fwd(s1, s2, sc, sh, n, H, W, cfg["k"], cfg["s"], cfg["p"], cfg["pm"], Ho, Wo, cfg["rm"], w, out, bias=bias, act=cfg["act"],
+                           slope=0.2, E=E if keep else None, row_img=ri)
+    a, b = both(bes, fn, [torch.full((rows, 64), 7.0, device="cuda", dtype=torch.bfloat16), torch.full((rows, 64), 5.0, device="cuda", dtype=torch.bfloat16),
+                          torch.zeros(rows, device="cuda", dtype=torch.int16)])
+    assert torch.equal(a[2], b[2])
+    if keep:
+        assert torch.equal(a[1], b[1])
+    # both sides round an fp32 value to bf16: agreement to one bf16 ulp of the largest magnitude
+    err = (a[0].float() - b[0].float()).abs().max().item()
+    assert err <= 2 ** -7 * b[0].float().abs().max().item() + 1e-6, err
+    assert ((a[0].float() - b[0].float()).norm() / b[0].float().norm()).item() < 3e-3
+    assert (a[0][a[2] < 0] == 0).all()
+
+
+def test_conv_gemm_tap_mode_scale_accumulate(bes):
+    """data gradient of a 3 x 3 convolution with 3 input planes (VGG conv1_1) through the horizontal-tap epilogue: += scale * (...)"""
+    g = gen(17)
+    n, H, W = 2, 20, 28
+    hp, wp = H + 2, W + 2
+    dz = torch.zeros(n, hp, wp, 64, device="cuda")
+    dz[:, 1:-1, 1:-1] = torch.randn(n, H, W, 64, device="cuda", generator=g)
+    dz = dz.view(-1, 64).bfloat16()
+    wt = (torch.randn(32, 3 * 64, device="cuda", generator=g) * 0.1).bfloat16()
+    wt[9:] = 0
+    scale = torch.rand(3, device="cuda", generator=g) + 0.5
+    out0 = torch.randn(n, 3, H, W, device="cuda", generator=g)
+    dummy = torch.zeros(8, 32, device="cuda")
+    fn = lambda be, o: be.conv_gemm(dz, 0, 64, [wp, 0, -wp], wt, 32, dummy,
+                                    tap=dict(out=o, nshift=3, nco=3, H=H, W=W, hp=hp, wp=wp, oy=1, ox=1, act=0, scale=scale, accumulate=True))
+    a, b = both(bes, fn, [out0])
+    close(a[0], b[0], 2e-5, "tap-mode dgrad")
+
+
 def test_taps(bes):
     g = gen(7)
     n, H, W, p = 2, 10, 12, 3
