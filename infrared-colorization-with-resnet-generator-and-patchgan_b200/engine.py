@@ -169,13 +169,14 @@ class TransposedUp:
 # ==========================================================================================
 class GeneratorEngine:
     def __init__(self, be, B: int, H: int, W: int, device, ngf: int = 64, n_blocks: int = 9, training: bool = True,
-                 arena: L.ParamArena = None, no_antialias_up: bool = False):
+                 arena: L.ParamArena = None, no_antialias_up: bool = False, no_antialias: bool = False):
         if H % 4 or W % 4:
             raise NotImplementedError("H and W must be multiples of 4 (the reference's odd-size bilinear fix-up, irc:555-563, is not built yet)")
         if ngf != 64:
             raise NotImplementedError("ngf must be 64 (channel counts are tiled in units of 64)")
         self.be, self.B, self.H, self.W, self.dev, self.nb, self.training = be, B, H, W, device, n_blocks, training
         self.convT = bool(no_antialias_up)
+        self.noaa = bool(no_antialias)          # stride-2 down-sampling convolutions instead of conv + blur (irc:468, :474, :482)
         self.arena = arena or L.ParamArena(generator_shapes(1, 3, ngf, n_blocks, no_antialias_up), device)
         if self.convT and "up1_up.weight" not in self.arena.offset:
             raise ValueError("no_antialias_up=True needs an arena with the ConvTranspose2d parameters up{1,2}_up.{weight,bias}")
@@ -187,9 +188,16 @@ class GeneratorEngine:
         self.E_in = L.act_zeros(B * H * W, 64, device)
         self.Z0 = F(H, W, 0, 64)
         self.cat2 = F(H, W, 1, 192)       # [0:128) up2_up output, [128:192) x0
-        self.Z1 = F(H, W, 1, 128)
         self.cat1 = F(H2, W2, 1, 384)     # [0:256) up1_up output, [256:384) x1
-        self.Z2 = F(H2, W2, 1, 256)
+        if self.noaa:
+            # stride-2 convolutions read 2x2 space-to-depth copies of the padded x0 / x1 frames and write on the block grid
+            self.hb1, self.wb1, self.hb2, self.wb2 = (H + 2) // 2, (W + 2) // 2, (H2 + 2) // 2, (W2 + 2) // 2
+            r1, r2 = B * self.hb1 * self.wb1, B * self.hb2 * self.wb2
+            self.Sx0, self.Z1s = L.act_zeros(r1, 256, device), L.act_zeros(r1, 128, device)
+            self.Sx1, self.Z2s = L.act_zeros(r2, 512, device), L.act_zeros(r2, 256, device)
+        else:
+            self.Z1 = F(H, W, 1, 128)
+            self.Z2 = F(H2, W2, 1, 256)
         self.X = [F(H4, W4, 1, 256) for _ in range(n_blocks + 1)]
         self.Za = [F(H4, W4, 1, 256) for _ in range(n_blocks)]
         self.Hh = [F(H4, W4, 1, 256) for _ in range(n_blocks)]
@@ -206,8 +214,8 @@ class GeneratorEngine:
         self.stb = [st(256) for _ in range(n_blocks)]
         self.bsum = st(256)
         # image index of every frame row (-1 = padding ring) for the convolutions that emit InstanceNorm statistics
-        self.ri_full = torch.zeros(self.Z1.rows, device=device, dtype=torch.int16)
-        self.ri_half = torch.zeros(self.Z2.rows, device=device, dtype=torch.int16)
+        self.ri_full = torch.zeros(self.Z4.rows, device=device, dtype=torch.int16)
+        self.ri_half = torch.zeros(self.Z3.rows, device=device, dtype=torch.int16)
         be.row_index(self.ri_full, B, H + 2, W + 2, 1, H + 1, 1, W + 1)
         be.row_index(self.ri_half, B, H2 + 2, W2 + 2, 1, H2 + 1, 1, W2 + 1)
         # ---- stencil tables
@@ -225,8 +233,14 @@ class GeneratorEngine:
         # ---- weights
         wp1, wp2, wp4, wp3 = self.cat2.wp, self.cat1.wp, self.X[0].wp, self.y4.wp
         self.inc = ConvOp(be, L.layout_im2col(P, A, "inc.1.weight", 64, 1, 7), [0], A, self.Z0.rows, pixels=B * H * W, name="G.inc")
-        self.down1 = ConvOp(be, L.layout_std(P, A, "down1.0.weight", 128, 64, 3, 3), L.taps_centered(3, 3, wp1), A, self.Z1.rows, pixels=B * H * W, name="G.down1")
-        self.down2 = ConvOp(be, L.layout_std(P, A, "down2.0.weight", 256, 128, 3, 3), L.taps_centered(3, 3, wp2), A, self.Z2.rows, pixels=B * H2 * W2, name="G.down2")
+        if self.noaa:
+            self.down1 = ConvOp(be, L.layout_s2d_k3(P, A, "down1.0.weight", 128, 64), [0, 1, self.wb1, self.wb1 + 1], A, self.Z1s.shape[0],
+                                pixels=B * H2 * W2, name="G.down1")
+            self.down2 = ConvOp(be, L.layout_s2d_k3(P, A, "down2.0.weight", 256, 128), [0, 1, self.wb2, self.wb2 + 1], A, self.Z2s.shape[0],
+                                pixels=B * H4 * W4, name="G.down2")
+        else:
+            self.down1 = ConvOp(be, L.layout_std(P, A, "down1.0.weight", 128, 64, 3, 3), L.taps_centered(3, 3, wp1), A, self.Z1.rows, pixels=B * H * W, name="G.down1")
+            self.down2 = ConvOp(be, L.layout_std(P, A, "down2.0.weight", 256, 128, 3, 3), L.taps_centered(3, 3, wp2), A, self.Z2.rows, pixels=B * H2 * W2, name="G.down2")
         self.res = []
         for b in range(n_blocks):
             self.res.append(tuple(ConvOp(be, L.layout_std(P, A, f"resblocks.{b}.conv_block.{j}.weight", 256, 256, 3, 3),
@@ -257,15 +271,19 @@ class GeneratorEngine:
         self.Gcat1 = F(H2, W2, 1, 384)
         self.dOut = [F(H4, W4, 1, 256), F(H4, W4, 1, 256)]
         self.dZb, self.Gh, self.dZa, self.Gx = (F(H4, W4, 1, 256) for _ in range(4))
-        self.dZ2 = F(H2, W2, 1, 256)
-        self.Gx1 = F(H2, W2, 1, 128)
-        self.dZ1 = F(H, W, 1, 128)
-        self.Gx0 = F(H, W, 1, 64)
         self.dZ0 = F(H, W, 0, 64)
         # gradients w.r.t. the activated layer outputs, after the transposed stencil / reflection fold
         self.g3 = F(H2, W2, 0, 128)
-        self.g2 = F(H2, W2, 0, 256)
-        self.g1 = F(H, W, 0, 128)
+        if self.noaa:
+            self.dZ1s, self.dZ2s = torch.zeros_like(self.Z1s), torch.zeros_like(self.Z2s)
+            self.dSx0, self.dSx1 = torch.zeros_like(self.Sx0), torch.zeros_like(self.Sx1)
+        else:
+            self.dZ2 = F(H2, W2, 1, 256)
+            self.Gx1 = F(H2, W2, 1, 128)
+            self.dZ1 = F(H, W, 1, 128)
+            self.Gx0 = F(H, W, 1, 64)
+            self.g2 = F(H2, W2, 0, 256)
+            self.g1 = F(H, W, 0, 128)
         if self.convT:
             self.GA3 = F(H2, W2, 1, 128)
 
@@ -290,12 +308,48 @@ class GeneratorEngine:
             self.inc.fwd(self.E_in, 0, self.Z0.t)
         be.in_stats(self.Z0.view(), 64, B, H, W, self.st0)
         be.gather(self.Z0.view(), self.cat2.view(128), 64, B, H, W, 1, 0, stats=self.st0, cnt=H * W, eps=EPS, act=ACT_RELU)
+        if self.noaa:
+            self._encoder_strided()
+        else:
+            self._encoder_antialiased()
+        self._bottleneck_and_decoder()
+        return self.output_head()
+
+    def _vZ1s(self, t):
+        return View(t, 0, self.hb1, self.wb1, 0, 0)
+
+    def _vZ2s(self, t):
+        return View(t, 0, self.hb2, self.wb2, 0, 0)
+
+    def _encoder_strided(self):
+        """no_antialias=True (irc:468): down1 / down2 are 3x3 stride-2 convolutions = 2x2 convolutions over space-to-depth copies of
+        the padded x0 / x1 frames; their InstanceNorm + ReLU output IS x1 / x2 (no blur module, irc:474, :482)"""
+        be, B, H, W = self.be, self.B, self.H, self.W
+        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        be.gather(self.Z0.view(), View(self.Sx0, 0, self.hb1, self.wb1), 64, B, H, W, 1, 0, stats=self.st0, cnt=H * W, eps=EPS, act=ACT_RELU, dst_s2d=1)
+        self.down1.fwd(self.Sx0, 0, self.Z1s)
+        v1 = self._vZ1s(self.Z1s)
+        be.in_stats(v1, 128, B, H2, W2, self.st1)
+        be.gather(v1, self.cat1.view(256), 128, B, H2, W2, 1, 0, stats=self.st1, cnt=H2 * W2, eps=EPS, act=ACT_RELU)
+        be.gather(v1, View(self.Sx1, 0, self.hb2, self.wb2), 128, B, H2, W2, 1, 0, stats=self.st1, cnt=H2 * W2, eps=EPS, act=ACT_RELU, dst_s2d=1)
+        self.down2.fwd(self.Sx1, 0, self.Z2s)
+        v2 = self._vZ2s(self.Z2s)
+        be.in_stats(v2, 256, B, H4, W4, self.st2)
+        be.gather(v2, self.X[0].view(), 256, B, H4, W4, 1, 1, stats=self.st2, cnt=H4 * W4, eps=EPS, act=ACT_RELU)
+
+    def _encoder_antialiased(self):
+        be, B, H, W = self.be, self.B, self.H, self.W
+        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
         # down1: 3x3 zero-pad conv at full resolution, then IN + ReLU + blur-downsample fused
         self.down1.fwd_stats(self.cat2.t, 128, self.Z1.t, self.st1, self.ri_full, B, self.Z1.hp * self.Z1.wp, self.Z1.view(), 128, H, W)
         be.gather(self.Z1.view(), self.cat1.view(256), 128, B, H2, W2, 1, 0, tables=self.t_down1, stats=self.st1, cnt=H * W, eps=EPS, act=ACT_RELU)
         # down2
         self.down2.fwd_stats(self.cat1.t, 256, self.Z2.t, self.st2, self.ri_half, B, self.Z2.hp * self.Z2.wp, self.Z2.view(), 256, H2, W2)
         be.gather(self.Z2.view(), self.X[0].view(), 256, B, H4, W4, 1, 1, tables=self.t_down2, stats=self.st2, cnt=H2 * W2, eps=EPS, act=ACT_RELU)
+
+    def _bottleneck_and_decoder(self):
+        be, B, H, W = self.be, self.B, self.H, self.W
+        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
         # 9 ResNet blocks (irc:362-418): reflect halo written by the apply pass
         n4 = H4 * W4
         for b in range(self.nb):
@@ -320,7 +374,6 @@ class GeneratorEngine:
             be.gather(self.Z3.view(), self.cat2.view(0), 128, B, H, W, 1, 0, tables=self.t_up2, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU)
         self.up2.fwd_stats(self.cat2.t, 0, self.Z4.t, self.st4, self.ri_full, B, self.Z4.hp * self.Z4.wp, self.Z4.view(), 64, H, W)
         be.gather(self.Z4.view(), self.y4.view(), 64, B, H, W, 3, 1, stats=self.st4, cnt=H * W, eps=EPS, act=ACT_RELU)
-        return self.output_head()
 
     def output_head(self) -> torch.Tensor:
         """outc (irc:527-531) on the frame y4: 7x7 reflect conv 64->3 as a GEMM over the 7 vertical taps (21 of 32 outputs), then
@@ -390,6 +443,23 @@ class GeneratorEngine:
         be.flush_sums()                   # weight gradients of outc, up2, up1 and the ResNet blocks are final
         if after_blocks is not None:
             after_blocks()
+        if self.noaa:
+            # stride-2 encoder: x2 is the activated down2 output itself; the data gradients come back in space-to-depth order
+            v1, v2 = self._vZ1s, self._vZ2s
+            be.in_bwd(v2(self.Z2s), cur.view(), v2(self.dZ2s), 256, B, H4, W4, stats=self.st2, cnt=H4 * W4, eps=EPS, act=ACT_RELU, bsum=self.bsum)
+            self.down2.wgrad(self.dZ2s, self.Sx1, 0, self.Sx1.shape[0])
+            self.down2.dgrad(self.dZ2s, self.dSx1)
+            # x1 feeds down2 and the up1 skip connection
+            be.in_bwd(v1(self.Z1s), self.Gcat1.view(256), v1(self.dZ1s), 128, B, H2, W2, stats=self.st1, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
+                      g2=View(self.dSx1, 0, self.hb2, self.wb2, 1, 1, 128), bsum=self.bsum)
+            self.down1.wgrad(self.dZ1s, self.Sx0, 0, self.Sx0.shape[0])
+            self.down1.dgrad(self.dZ1s, self.dSx0)
+            # inc: x0 feeds down1 and the up2 skip connection
+            be.in_bwd(self.Z0.view(), self.Gcat2.view(128), self.dZ0.view(), 64, B, H, W, stats=self.st0, cnt=H * W, eps=EPS, act=ACT_RELU,
+                      g2=View(self.dSx0, 0, self.hb1, self.wb1, 1, 1, 64), bsum=self.bsum)
+            self.inc.wgrad(self.dZ0.t, self.E_in, 0, self.dZ0.rows)
+            be.flush_sums()
+            return
         # down2 (through Downsample^T)
         be.gather(cur.view(), self.g2.view(), 256, B, H2, W2, 0, 0, tables=self.t_down2_T)
         be.in_bwd(self.Z2.view(), self.g2.view(), self.dZ2.view(), 256, B, H2, W2, stats=self.st2, cnt=H2 * W2, eps=EPS, act=ACT_RELU,

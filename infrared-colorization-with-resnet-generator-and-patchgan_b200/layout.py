@@ -254,6 +254,23 @@ def layout_s2d(packer, arena, name, Cout, Cin) -> WeightLayout:
     return WeightLayout(packer, idx, arena.offset[name], arena.numel(name))
 
 
+def layout_s2d_k3(packer, arena, name, Cout, Cin) -> WeightLayout:
+    """3x3 stride-2 pad-1 conv (the generator's down-sampling convolutions with no_antialias=True, irc:468) as a 2x2 conv over the
+    2x2 space-to-depth blocks of the padded frame: kernel element (r, s) = (2a + dy, 2b + dx); the elements with r = 3 or s = 3 of
+    the enclosing 4x4 kernel are structural zeros"""
+    idx = np.full((Cout, 4, 4 * Cin), -1, np.int64)
+    base = arena.offset[name]
+    co = np.arange(Cout).reshape(-1, 1); ci = np.arange(Cin).reshape(1, -1)
+    for a in range(2):
+        for b in range(2):
+            for dy in range(2):
+                for dx in range(2):
+                    r, s = 2 * a + dy, 2 * b + dx
+                    if r < 3 and s < 3:
+                        idx[:, a * 2 + b, (dy * 2 + dx) * Cin:(dy * 2 + dx + 1) * Cin] = oihw_index(base, co, ci, r, s, Cin, 3, 3)
+    return WeightLayout(packer, idx, base, arena.numel(name))
+
+
 def layout_im2col(packer, arena, name, Cout, Cin, k) -> WeightLayout:
     """one tap, 64 slots: slot (r*k+s)*Cin + ci"""
     idx = np.full((Cout, 1, 64), -1, np.int64)

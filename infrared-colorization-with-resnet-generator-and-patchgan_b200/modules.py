@@ -282,7 +282,7 @@ class _GenFn(torch.autograd.Function):
         grad = mod._grad_on and any(ctx.needs_input_grad)
         key = (B, H, W, grad)                  # inference engines carry no backward buffers
         eng = mod._acquire(key, lambda: E.GeneratorEngine(backend(), B, H, W, x.device, arena=mod.arena, training=grad,
-                                                          no_antialias_up=mod.no_antialias_up))
+                                                          no_antialias_up=mod.no_antialias_up, no_antialias=mod.no_antialias))
         eng.refresh_weights()
         out = eng.forward(x.contiguous().float()).clone()
         if grad:
@@ -312,22 +312,22 @@ class ResnetUNetGenerator(_ArenaModule):
                  padding_type="reflect", no_antialias=False, no_antialias_up=False):
         super().__init__()
         assert n_blocks >= 0                                          # irc:449
-        if (input_nc, output_nc, ngf) != (1, 3, 64) or norm_layer is not nn.InstanceNorm2d or use_dropout or padding_type != "reflect" \
-                or no_antialias:
-            raise NotImplementedError("built: the default generator graph (1->3, ngf 64, instance norm, reflect padding, anti-aliased "
-                                      "down-sampling) with UpsampleAA or - no_antialias_up=True - ConvTranspose2d up-sampling; stride-2 "
-                                      "down-sampling convolutions (no_antialias=True) and other norms are not (SURVEY.md §8f-4)")
+        if (input_nc, output_nc, ngf) != (1, 3, 64) or norm_layer is not nn.InstanceNorm2d or use_dropout or padding_type != "reflect":
+            raise NotImplementedError("built: the generator graph 1->3, ngf 64, instance norm, reflect padding; anti-aliased (Downsample) or "
+                                      "- no_antialias=True - stride-2 down-sampling, UpsampleAA or - no_antialias_up=True - ConvTranspose2d "
+                                      "up-sampling; other norms / dropout are not (SURVEY.md §8f-4)")
         self.n_blocks = n_blocks
         self.no_antialias_up = bool(no_antialias_up)
+        self.no_antialias = bool(no_antialias)
         dev = torch.device("cuda" if torch.cuda.is_available() else "cpu")
         self._init_arena(E.generator_shapes(input_nc, output_nc, ngf, n_blocks, self.no_antialias_up), dev)
         A = self.arena
         hold = lambda k: _ConvParams(A.view(k + ".weight"), A.view(k + ".bias"))
         self.inc = nn.ModuleDict({"1": hold("inc.1")})
         self.down1 = nn.ModuleDict({"0": hold("down1.0")})
-        self.down1_down = _Filt(2 * ngf)
+        self.down1_down = None if self.no_antialias else _Filt(2 * ngf)          # irc:474: no blur module, no `filt` buffer
         self.down2 = nn.ModuleDict({"0": hold("down2.0")})
-        self.down2_down = _Filt(4 * ngf)
+        self.down2_down = None if self.no_antialias else _Filt(4 * ngf)          # irc:482
         self.resblocks = nn.ModuleList([_ResBlockHolder(A, b) for b in range(n_blocks)])
         # UpsampleAA carries only its `filt` buffer; nn.ConvTranspose2d (irc:495-499, :512-516) carries weight (Cin, Cout, 3, 3) + bias
         self.up1_up = hold("up1_up") if self.no_antialias_up else _Filt(4 * ngf)

@@ -207,8 +207,10 @@ def resnet_block(p: Params, prefix: str, x: torch.Tensor) -> torch.Tensor:
     return x + instance_norm(h)
 
 
-def generator_forward(p: Params, x: torch.Tensor, n_blocks: int = 9, taps: Optional[dict] = None) -> torch.Tensor:
-    """ResnetUNetGenerator.forward with the default config (irc:540-569); returns the image only.
+def generator_forward(p: Params, x: torch.Tensor, n_blocks: int = 9, taps: Optional[dict] = None, no_antialias: bool = False) -> torch.Tensor:
+    """ResnetUNetGenerator.forward (irc:540-569); returns the image only.  Default config; ConvTranspose2d up-sampling when the
+    parameters carry up{1,2}_up.weight (no_antialias_up=True, irc:495-516); stride-2 down-sampling convolutions without the blur
+    modules when no_antialias=True (irc:468, :474, :482).
 
     ``taps`` (optional dict) receives named intermediate activations for per-layer parity."""
     def tap(name, t):
@@ -217,10 +219,11 @@ def generator_forward(p: Params, x: torch.Tensor, n_blocks: int = 9, taps: Optio
         return t
 
     x0 = tap("x0", torch.relu(instance_norm(_conv(x, p["inc.1.weight"], p["inc.1.bias"], reflect=3))))
-    d1 = tap("down1", torch.relu(instance_norm(_conv(x0, p["down1.0.weight"], p["down1.0.bias"], pad=1))))
-    x1 = tap("x1", blur_down(d1))
-    d2 = tap("down2", torch.relu(instance_norm(_conv(x1, p["down2.0.weight"], p["down2.0.bias"], pad=1))))
-    x2 = tap("x2", blur_down(d2))
+    sd = 2 if no_antialias else 1
+    d1 = tap("down1", torch.relu(instance_norm(_conv(x0, p["down1.0.weight"], p["down1.0.bias"], stride=sd, pad=1))))
+    x1 = tap("x1", d1 if no_antialias else blur_down(d1))
+    d2 = tap("down2", torch.relu(instance_norm(_conv(x1, p["down2.0.weight"], p["down2.0.bias"], stride=sd, pad=1))))
+    x2 = tap("x2", d2 if no_antialias else blur_down(d2))
     h = x2
     for b in range(n_blocks):
         h = tap(f"res{b}", resnet_block(p, f"resblocks.{b}.", h))

@@ -51,6 +51,31 @@ def main():
     y.backward(gy)
     gold.update(ct_x=x.detach().numpy(), ct_w=ct.weight.detach().numpy(), ct_b=ct.bias.detach().numpy(), ct_y=y.detach().numpy(), ct_gy=gy.numpy(),
                 ct_gx=x.grad.numpy(), ct_gw=ct.weight.grad.numpy(), ct_gb=ct.bias.grad.numpy())
+    # no_antialias=True (irc:468, :474, :482): stride-2 down-sampling convolutions, no blur modules; alone and together with
+    # the transposed-convolution up-sampling ("na/" and "nab/" fixtures)
+    for tag, up in (("na", False), ("nab", True)):
+        pV = O.seeded_params(O.generator_shapes(no_antialias_up=up), 777 + int(up), bias_std=0.02)
+        cfg = R.Config(); cfg.device = "cpu"; cfg.no_antialias = True; cfg.no_antialias_up = up
+        m = R.IRColorizationModel(cfg)
+        keys = set(m.netG.state_dict().keys())
+        assert "down1_down.filt" not in keys and "down2_down.filt" not in keys and ("up1_up.filt" in keys) == (not up)
+        missing = m.netG.load_state_dict(pV, strict=False)
+        assert not missing.unexpected_keys and all(k.endswith("filt") for k in missing.missing_keys), missing
+        fake = m(ir)
+        gv = torch.randn(fake.shape, generator=torch.Generator().manual_seed(11))
+        fake.backward(gv)
+        leaves = {k: v.clone().requires_grad_(True) for k, v in pV.items()}
+        fo = O.generator_forward(leaves, ir, no_antialias=True)
+        MG.close(fo, fake.detach(), 2e-5, tag + " forward")
+        fo.backward(gv)
+        for k, p_ in m.netG.named_parameters():
+            noise = k.endswith("bias") and not (k.startswith("outc") or k.startswith("up1_up") or k.startswith("up2_up"))
+            if p_.grad.abs().max() > 1e-4 and not noise:
+                rel = ((leaves[k].grad - p_.grad).norm() / p_.grad.norm()).item()
+                assert rel < 5e-3, (tag, k, rel)
+            gold[f"{tag}/grad_norm/" + k] = p_.grad.norm().item(); gold[f"{tag}/grad_sample/" + k] = MG.sample(p_.grad)
+            gold[f"{tag}/grad_absmax/" + k] = p_.grad.abs().max().item()
+        gold[f"{tag}/fake"] = fake.detach().numpy(); gold[f"{tag}/upstream"] = gv.numpy()
     np.savez_compressed(os.path.join(MG.OUT, "ref_variants.npz"), **gold)
     print("wrote ref_variants.npz keys:", len(gold))
 

@@ -1,4 +1,5 @@
-"""Non-default generator graph: no_antialias_up=True - nn.ConvTranspose2d up-sampling (irc:495-499, :512-516) -
+"""Non-default generator graphs: no_antialias_up=True - nn.ConvTranspose2d up-sampling (irc:495-499, :512-516) - and
+no_antialias=True - stride-2 down-sampling convolutions without the blur modules (irc:468, :474, :482) - and both together,
 against golden vectors produced by the unmodified reference (tests/golden/ref_variants.npz, oracle/make_golden_variants.py).
 CPU: the oracle and the product's plan (torch restatement of the primitives, float32 frames).  GPU: the CUDA path, incl. the
 transposed convolution through its C-ABI entry point irc_convT2d_fwd."""
@@ -40,24 +41,46 @@ def test_oracle_variant_forward_and_grads():
         assert abs(leaves[k].grad.norm().item() - float(GOLD["grad_norm/" + k])) < 2e-3 * float(GOLD["grad_norm/" + k]), k
 
 
-def _check_engine(be, dev, tol_fwd, tol_dec, tol_enc):
+# variant tag -> (fixture prefix, no_antialias_up, no_antialias, parameter seed of make_golden_variants.py)
+VARIANTS = {"up": ("", True, False, 4321), "na": ("na/", False, True, 777), "nab": ("nab/", True, True, 778)}
+
+
+def _variant_params(tag):
+    pre, up, na, seed = VARIANTS[tag]
+    return O.seeded_params(O.generator_shapes(no_antialias_up=up), seed, bias_std=0.02)
+
+
+@pytest.mark.parametrize("tag", ["na", "nab"])
+def test_oracle_no_antialias_forward_and_grads(tag):
+    pre, up, na, _ = VARIANTS[tag]
+    ir, _ = O.synthetic_pair(B, H, W)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in _variant_params(tag).items()}
+    fake = O.generator_forward(leaves, ir, no_antialias=True)
+    assert np.abs(fake.detach().numpy() - GOLD[pre + "fake"]).max() < 5e-5
+    fake.backward(torch.from_numpy(GOLD[pre + "upstream"]))
+    for k in ("down1.0.weight", "down2.0.weight", "inc.1.weight", "outc.1.weight", "up1_conv.0.weight"):
+        assert abs(leaves[k].grad.norm().item() - float(GOLD[pre + "grad_norm/" + k])) < 2e-3 * float(GOLD[pre + "grad_norm/" + k]), k
+
+
+def _check_engine(be, dev, tol_fwd, tol_dec, tol_enc, tag="up"):
     import irc_b200  # noqa: F401
     from irc_b200 import engine as E
-    pG = _params()
+    pre, up, na, _ = VARIANTS[tag]
+    pG = _variant_params(tag)
     ir, _ = O.synthetic_pair(B, H, W)
-    eng = E.GeneratorEngine(be, B, H, W, dev, no_antialias_up=True)
+    eng = E.GeneratorEngine(be, B, H, W, dev, no_antialias_up=up, no_antialias=na)
     eng.arena.load(pG); eng.refresh_weights()
     fake = eng.forward(ir.to(dev))
-    e = rel(fake, torch.from_numpy(GOLD["fake"]))
-    print("variant fake rel", e)
+    e = rel(fake, torch.from_numpy(GOLD[pre + "fake"]))
+    print("variant", tag, "fake rel", e)
     assert e < tol_fwd
     eng.arena.grad.zero_()
-    eng.backward(torch.from_numpy(GOLD["upstream"]).to(dev).contiguous())
+    eng.backward(torch.from_numpy(GOLD[pre + "upstream"]).to(dev).contiguous())
     worst = {}
     for k in pG:
-        if float(GOLD["grad_absmax/" + k]) <= 1e-4 or (k.endswith("bias") and not k.startswith(("outc", "up1_up", "up2_up"))):
+        if float(GOLD[pre + "grad_absmax/" + k]) <= 1e-4 or (k.endswith("bias") and not k.startswith(("outc", "up1_up", "up2_up"))):
             continue
-        got = sample(eng.arena.view(k, eng.arena.grad)); want = GOLD["grad_sample/" + k]
+        got = sample(eng.arena.view(k, eng.arena.grad)); want = GOLD[pre + "grad_sample/" + k]
         worst[k] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
     print({k: round(v, 4) for k, v in worst.items() if not k.startswith("resblocks") or k.startswith("resblocks.8")})
     for k, v in worst.items():
@@ -77,6 +100,43 @@ def test_plan_with_transposed_conv_upsampling_matches_reference():
         _check_engine(RefBackend(), "cpu", 1e-5, 1e-4, 1e-2)
     finally:
         L.ACT_DTYPE = old
+
+
+@pytest.mark.parametrize("tag", ["na", "nab"])
+def test_plan_with_strided_downsampling_matches_reference(tag):
+    """host logic of no_antialias=True in float32: 3x3 stride-2 convolutions as 2x2 convolutions over space-to-depth blocks (weight
+    layout with structural zeros), InstanceNorm on the block grid, gradients returning in space-to-depth order into the two-source
+    InstanceNorm backward of the layer below"""
+    import irc_b200  # noqa: F401
+    from irc_b200 import layout as L
+    from ref_backend import RefBackend
+    old = L.ACT_DTYPE
+    L.ACT_DTYPE = torch.float32
+    try:
+        _check_engine(RefBackend(), "cpu", 1e-5, 1e-4, 1e-2, tag=tag)
+    finally:
+        L.ACT_DTYPE = old
+
+
+def test_module_surface_of_the_strided_variant():
+    """no_antialias=True: the reference's state_dict has no down{1,2}_down.filt buffers (the modules are None, irc:474, :482)"""
+    import irc_b200 as R
+    from irc_b200 import layout as L, modules as M
+    from ref_backend import RefBackend
+    old, oldbe = L.ACT_DTYPE, M._BACKEND
+    L.ACT_DTYPE = torch.float32; M.set_backend(RefBackend())
+    try:
+        cfg = R.Config(); cfg.device = "cpu"; cfg.no_antialias = True
+        m = R.IRColorizationModel(cfg)
+        sd = m.netG.state_dict()
+        assert "down1_down.filt" not in sd and "down2_down.filt" not in sd and "up1_up.filt" in sd and len(sd) == 50
+        assert m.netG.down1_down is None and m.netG.down2_down is None
+        m.netG.load_state_dict(_variant_params("na"), strict=False)
+        ir, _ = O.synthetic_pair(B, H, W)
+        with torch.no_grad():
+            assert rel(m(ir), torch.from_numpy(GOLD["na/fake"])) < 1e-5
+    finally:
+        L.ACT_DTYPE = old; M.set_backend(oldbe)
 
 
 def test_module_surface_of_the_variant():
@@ -107,6 +167,14 @@ def test_gpu_generator_with_transposed_conv_upsampling():
     graph (tests/test_step_gpu.py bounds them at 0.35); the tight 1e-2 bound of the new layer is the C-ABI test below"""
     from irc_b200._native import CudaBackend
     _check_engine(CudaBackend(), "cuda", 3e-2, 0.25, 0.35)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["na", "nab"])
+def test_gpu_generator_with_strided_downsampling(tag):
+    """no_antialias=True on the CUDA path (bf16): same bounds as the other whole-network runs"""
+    from irc_b200._native import CudaBackend
+    _check_engine(CudaBackend(), "cuda", 3e-2, 0.25, 0.35, tag=tag)
 
 
 @pytest.mark.gpu
