@@ -278,6 +278,12 @@ int irc_feat_l1(const void* feat, long long rows_half, long long ld, int C, floa
  * u8[n][y][x][c] = trunc(clip((fake+1)/2,0,1)*255); sums[n] = (sum|u8/255-gt|, sum(u8/255-gt)^2). */
 int irc_quantize_metrics(const float* fake, const float* gt, int n_img, int C, int H, int W, unsigned char* u8, double* sums, void* stream);
 
+/* The SSIM column of compute_metrics (irc:1208-1215): skimage.metrics.structural_similarity(gt, pred, data_range=1.0,
+ * channel_axis=2) with its defaults (7 x 7 uniform window, sample covariance, K1 = 0.01, K2 = 0.03, float64, 3-pixel crop),
+ * batched on device.  u8: [n][H][W][3] predictions (irc_quantize_metrics), gt: fp32 [n][3][H][W] in [0, 1];
+ * sums[n] = sum over the 3 channels and the (H - 6) x (W - 6) valid positions of the SSIM map (divide by their count). */
+int irc_ssim_metric(const unsigned char* u8, const float* gt, int n_img, int H, int W, double* sums, void* stream);
+
 /* Running loss sums on the device (irc:1683-1697 averages every step of an epoch; this removes the per-step .item()
  * synchronisation): acc[j] += coef[j][n] + sum_i coef[j][i] * s[i], coef is [rows][n+1] fp32, rows <= 32. */
 int irc_accumulate(const float* s, int n, const float* coef, int rows, double* acc, void* stream);

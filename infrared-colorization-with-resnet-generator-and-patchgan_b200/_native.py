@@ -20,7 +20,7 @@ EXPORTS = [
     "irc_version", "irc_arch_check", "irc_last_error", "irc_conv_gemm", "irc_conv_stats_workspace_floats", "irc_conv_stats_finalize", "irc_tn_gemm", "irc_tn_gemm_ctas", "irc_row_index",
     "irc_in_stats", "irc_gather", "irc_in_apply_fused", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_in_bwd_fused", "irc_in_bwd_l2", "irc_maxpool2", "irc_maxpool2_bwd",
     "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_smallk_conv_fwd", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
-    "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics",
+    "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics", "irc_ssim_metric",
     "irc_adam", "irc_accumulate", "irc_gather_f32", "irc_convT2d_fwd", "irc_pack_bf16", "irc_gather_sum", "irc_gather_sum_multi", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
     "irc_resize_area_u8", "irc_u8_to_pm1",
 ]
@@ -591,6 +591,12 @@ class CudaBackend:
     def quantize_metrics(self, fake, gt, u8, sums):
         n, c, h, w = fake.shape
         check(self.L.irc_quantize_metrics(_p(fake), _p(gt), n, c, h, w, _p(u8), _p(sums), _stream())); self.launches += 1
+
+    def ssim_metric(self, u8, gt, sums):
+        """skimage-style SSIM metric (irc:1208-1215): u8 [n, H, W, 3] uint8 predictions, gt fp32 [n, 3, H, W] in [0, 1], sums fp64 [n]"""
+        n, h, w, c = u8.shape
+        assert c == 3 and u8.dtype == torch.uint8 and gt.dtype == torch.float32 and tuple(gt.shape) == (n, 3, h, w) and sums.dtype == torch.float64
+        check(self.L.irc_ssim_metric(_p(u8), _p(gt), n, h, w, _p(sums), _stream())); self.launches += 1
 
     # ---- optimizer / layout
     def adam(self, p, g, m, v, hyper, step_dev):

@@ -570,6 +570,68 @@ __global__ void __launch_bounds__(256) quantize_metrics3_kernel(const float* __r
     }
 }
 
+// ---------------------------------------------------------------- SSIM metric (irc:1208-1215)
+// skimage.metrics.structural_similarity(gt, pred, data_range=1.0, channel_axis=2) with its defaults: 7 x 7 uniform window,
+// sample covariance (N / (N - 1)), K1 = 0.01, K2 = 0.03, float64 arithmetic, mean over the map cropped by 3 pixels, mean over
+// channels.  Only the cropped (valid) region is evaluated, so the filter's border mode never matters.  pred = u8 / 255 as
+// float32 (irc:1413), gt float32 in [0, 1].  sums[n] += sum over channels and valid pixels of S.
+constexpr int kSmW = 32, kSmH = 16, kSmWin = 7;
+__global__ void __launch_bounds__(256) ssim_metric_kernel(const unsigned char* __restrict__ u8, const float* __restrict__ gt, int H, int W, double* sums) {
+    irc::pdl_prologue();
+    __shared__ float tx[kSmH + kSmWin - 1][kSmW + kSmWin - 1], ty[kSmH + kSmWin - 1][kSmW + kSmWin - 1];
+    __shared__ double hs[5][kSmH + kSmWin - 1][kSmW];
+    __shared__ double red[8];
+    const int n = blockIdx.z / 3, c = blockIdx.z % 3;
+    const int x0 = blockIdx.x * kSmW, y0 = blockIdx.y * kSmH;          // first valid-region output of the tile = input offset
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const long long hw = (long long)H * W;
+    for (int i = tid; i < (kSmH + 6) * (kSmW + 6); i += 256) {
+        const int r = i / (kSmW + 6), q = i - r * (kSmW + 6);
+        const int y = y0 + r, x = x0 + q;
+        float a = 0.f, b = 0.f;
+        if (y < H && x < W) {
+            a = __ldg(gt + ((long long)n * 3 + c) * hw + (long long)y * W + x);
+            b = __fdiv_rn((float)u8[((long long)n * hw + (long long)y * W + x) * 3 + c], 255.0f);
+        }
+        tx[r][q] = a; ty[r][q] = b;
+    }
+    __syncthreads();
+    for (int i = tid; i < (kSmH + 6) * kSmW; i += 256) {
+        const int r = i / kSmW, q = i - r * kSmW;
+        double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+#pragma unroll
+        for (int k = 0; k < kSmWin; ++k) {
+            const double a = (double)tx[r][q + k], b = (double)ty[r][q + k];
+            sx += a; sy += b; sxx += a * a; syy += b * b; sxy += a * b;
+        }
+        hs[0][r][q] = sx; hs[1][r][q] = sy; hs[2][r][q] = sxx; hs[3][r][q] = syy; hs[4][r][q] = sxy;
+    }
+    __syncthreads();
+    const double NP = 49.0, cov_norm = NP / (NP - 1.0), C1 = 1e-4, C2 = 9e-4;
+    double acc = 0.0;
+    for (int rr = threadIdx.y; rr < kSmH; rr += 8) {
+        const int oy = y0 + rr, ox = x0 + threadIdx.x;
+        if (oy >= H - 6 || ox >= W - 6) continue;
+        double s[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < kSmWin; ++k)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) s[j] += hs[j][rr + k][threadIdx.x];
+        const double ux = s[0] / NP, uy = s[1] / NP, uxx = s[2] / NP, uyy = s[3] / NP, uxy = s[4] / NP;
+        const double vx = cov_norm * (uxx - ux * ux), vy = cov_norm * (uyy - uy * uy), vxy = cov_norm * (uxy - ux * uy);
+        acc += ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) red[threadIdx.y] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        atomicAdd(sums + n, t);
+    }
+}
+
 int grid_for(long long total, int threads, int per_sm) {
     long long b = (total + threads - 1) / threads;
     const long long cap = (long long)irc_num_sms() * per_sm;
@@ -658,6 +720,15 @@ extern "C" int irc_quantize_metrics(const float* fake, const float* gt, int n_im
     int bx = grid_for((long long)C * H * W, 256, 4);
     irc::launch(quantize_metrics_kernel, dim3(bx, n_img), 256, 0, (cudaStream_t)stream, fake, gt, C, H, W, u8, sums);
     return irc_check_launch("irc_quantize_metrics");
+}
+
+extern "C" int irc_ssim_metric(const unsigned char* u8, const float* gt, int n_img, int H, int W, double* sums, void* stream) {
+    if (!u8 || !gt || !sums || n_img <= 0) return irc_set_error(IRC_ERR_BAD_ARG, "irc_ssim_metric: null");
+    if (H < kSmWin || W < kSmWin) return irc_set_error(IRC_ERR_BAD_ARG, "irc_ssim_metric: images must be at least 7 x 7 (the window of structural_similarity)");
+    if ((long long)n_img * 3 > 65535) return irc_set_error(IRC_ERR_BAD_ARG, "irc_ssim_metric: too many images in one call");
+    cudaMemsetAsync(sums, 0, sizeof(double) * n_img, (cudaStream_t)stream);
+    irc::launch(ssim_metric_kernel, dim3((W - 6 + kSmW - 1) / kSmW, (H - 6 + kSmH - 1) / kSmH, n_img * 3), dim3(32, 8), 0, (cudaStream_t)stream, u8, gt, H, W, sums);
+    return irc_check_launch("irc_ssim_metric");
 }
 
 extern "C" int irc_accumulate(const float* s, int n, const float* coef, int rows, double* acc, void* stream) {

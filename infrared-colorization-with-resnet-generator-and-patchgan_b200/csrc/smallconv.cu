@@ -572,12 +572,20 @@ extern "C" int irc_smallk_conv_fwd(const irc_im2col_args* a, const void* w, cons
     p.H = a->H; p.W = a->W; p.k = a->k; p.stride = a->stride; p.pad = a->pad; p.pad_mode = a->pad_mode;
     p.rm.mode = a->row_mode; p.rm.n_img = a->n_img; p.rm.Ho = a->Ho; p.rm.Wo = a->Wo;
     p.dst = (bf16*)a->dst; p.row_img = a->row_img;
-    const int LPB = a->row_mode == 2 ? 2 : 4;
-    const int rows_out = LPB * (a->row_mode == 2 ? 2 : 1);
-    const int R = (rows_out - 1) * a->stride + a->k, Wp = a->W + 2 * a->pad;
+    // lines per block: as many as keep the tile within half of the shared memory (two resident blocks overlap one block's
+    // tile fill with the other's arithmetic); wide images fall back to fewer lines, then to one block per SM
     const bool keep = a->dst != nullptr;
-    const size_t smem = (size_t)C * R * Wp * sizeof(float) + 8 * (keep ? 2 : 1) * 16 * kSkPitch * sizeof(uint32_t);
-    if (smem > 100 * 1024) return irc_set_error(IRC_ERR_BAD_ARG, "irc_smallk_conv_fwd: line tile does not fit shared memory");
+    const int Wp = a->W + 2 * a->pad;
+    const size_t stage_bytes = 8 * (keep ? 2 : 1) * 16 * kSkPitch * sizeof(uint32_t);
+    int LPB = a->row_mode == 2 ? 2 : 4, R = 0;
+    size_t smem = 0;
+    for (;; LPB >>= 1) {
+        const int rows_out = LPB * (a->row_mode == 2 ? 2 : 1);
+        R = (rows_out - 1) * a->stride + a->k;
+        smem = (size_t)C * R * Wp * sizeof(float) + stage_bytes;
+        if (smem <= 100 * 1024 || LPB == 1) break;
+    }
+    if (smem > 200 * 1024) return irc_set_error(IRC_ERR_BAD_ARG, "irc_smallk_conv_fwd: line tile does not fit shared memory");
     const long long nblk = (long long)p.rm.n_img * ((p.rm.lines() + LPB - 1) / LPB);
     const unsigned grid = (unsigned)(nblk < 1048576 ? nblk : 1048576);
     const int ks = K <= 32 ? 2 : 4;
@@ -585,7 +593,7 @@ extern "C" int irc_smallk_conv_fwd(const irc_im2col_args* a, const void* w, cons
 #define IRC_SMALLK_CASE(KS_, MODE_, KEEP_)                                                                                                         \
     if (!ok && ks == KS_ && a->row_mode == MODE_ && keep == KEEP_) {                                                                              \
         static bool attr = false;                                                                                                                  \
-        if (!attr) { cudaFuncSetAttribute(smallk_conv_fwd_kernel<KS_, MODE_, KEEP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
+        if (!attr) { cudaFuncSetAttribute(smallk_conv_fwd_kernel<KS_, MODE_, KEEP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; } \
         irc::launch(smallk_conv_fwd_kernel<KS_, MODE_, KEEP_>, grid, 256, smem, (cudaStream_t)stream, p, (const bf16*)w, bias, act, slope, (bf16*)out, R, Wp, LPB); \
         ok = true;                                                                                                                                 \
     }

@@ -170,11 +170,20 @@ class TransposedUp:
 class GeneratorEngine:
     def __init__(self, be, B: int, H: int, W: int, device, ngf: int = 64, n_blocks: int = 9, training: bool = True,
                  arena: L.ParamArena = None, no_antialias_up: bool = False, no_antialias: bool = False):
-        if H % 4 or W % 4:
-            raise NotImplementedError("H and W must be multiples of 4 (the reference's odd-size bilinear fix-up, irc:555-563, is not built yet)")
+        if min(H, W) < 8:
+            raise ValueError("the generator needs at least 8 x 8 pixels (ReflectionPad2d(1) at a quarter of the resolution)")
+        if no_antialias and (H % 4 or W % 4):
+            raise NotImplementedError("no_antialias=True (space-to-depth stride-2 convolutions) needs H and W to be multiples of 4")
         if ngf != 64:
             raise NotImplementedError("ngf must be 64 (channel counts are tiled in units of 64)")
         self.be, self.B, self.H, self.W, self.dev, self.nb, self.training = be, B, H, W, device, n_blocks, training
+        # Downsample halves with ceil (irc:307-310); the up-sampling doubles, so for sizes that are not multiples of 4 the
+        # decoder maps are resized onto the skip-connection grids (irc:555-556, :562-563)
+        self.H2, self.W2 = (H + 1) // 2, (W + 1) // 2
+        self.H4, self.W4 = (self.H2 + 1) // 2, (self.W2 + 1) // 2
+        if no_antialias_up and (2 * self.H4 != self.H2 or 2 * self.W4 != self.W2 or 2 * self.H2 != H or 2 * self.W2 != W):
+            raise NotImplementedError("no_antialias_up=True with sizes that are not multiples of 4 (a bilinear resize behind the transposed "
+                                      "convolution, irc:555-556) is not built")
         self.convT = bool(no_antialias_up)
         self.noaa = bool(no_antialias)          # stride-2 down-sampling convolutions instead of conv + blur (irc:468, :474, :482)
         self.arena = arena or L.ParamArena(generator_shapes(1, 3, ngf, n_blocks, no_antialias_up), device)
@@ -182,7 +191,7 @@ class GeneratorEngine:
             raise ValueError("no_antialias_up=True needs an arena with the ConvTranspose2d parameters up{1,2}_up.{weight,bias}")
         self.packer = L.Packer(self.arena)
         A, P = self.arena, self.packer
-        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        H2, W2, H4, W4 = self.H2, self.W2, self.H4, self.W4
         F = lambda h, w, p, c: L.Frame(B, h, w, p, c, device)
         # ---- buffers (forward)
         self.E_in = L.act_zeros(B * H * W, 64, device)
@@ -222,12 +231,16 @@ class GeneratorEngine:
         mk = lambda my, mx: L.make_tables(my, mx, device)
         self.t_down1 = mk(L.down_matrix(H), L.down_matrix(W))
         self.t_down2 = mk(L.down_matrix(H2), L.down_matrix(W2))
-        self.t_up1 = mk(L.up_matrix(H4), L.up_matrix(W4))
-        self.t_up2 = mk(L.up_matrix(H2), L.up_matrix(W2))
+        # UpsampleAA (irc:350-355), followed - only where the doubled size misses the skip connection's - by the bilinear
+        # align_corners resize of irc:555-556 / :562-563, composed into ONE separable operator per axis
+        up_to = lambda n, m: L.up_matrix(n) if 2 * n == m else L.resize_matrix(m, 2 * n) @ L.up_matrix(n)
+        m_up1, m_up2 = (up_to(H4, H2), up_to(W4, W2)), (up_to(H2, H), up_to(W2, W))
+        self.t_up1 = mk(*m_up1)
+        self.t_up2 = mk(*m_up2)
         self.t_down1_T = mk(L.down_matrix(H).T, L.down_matrix(W).T)
         self.t_down2_T = mk(L.down_matrix(H2).T, L.down_matrix(W2).T)
-        self.t_up1_T = mk(L.up_matrix(H4).T, L.up_matrix(W4).T)      # 6 x 6 taps, taken from a shared-memory patch
-        self.t_up2_T = mk(L.up_matrix(H2).T, L.up_matrix(W2).T)
+        self.t_up1_T = mk(m_up1[0].T, m_up1[1].T)      # 6 x 6 taps, taken from a shared-memory patch
+        self.t_up2_T = mk(m_up2[0].T, m_up2[1].T)
         self.t_fold1 = mk(L.fold_matrix(H4, 1), L.fold_matrix(W4, 1))
         self.t_fold3 = mk(L.fold_matrix(H, 3), L.fold_matrix(W, 3))
         # ---- weights
@@ -261,7 +274,7 @@ class GeneratorEngine:
 
     def _alloc_backward(self):
         B, H, W, dev = self.B, self.H, self.W, self.dev
-        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        H2, W2, H4, W4 = self.H2, self.W2, self.H4, self.W4
         F = lambda h, w, p, c: L.Frame(B, h, w, p, c, dev)
         self.E_out = L.act_zeros(self.y4.rows, 64, dev)
         self.G4 = F(H, W, 3, 64)
@@ -296,7 +309,7 @@ class GeneratorEngine:
     def forward(self, ir: torch.Tensor) -> torch.Tensor:
         """ir: fp32 [B,1,H,W] -> fake fp32 [B,3,H,W] (irc:533-569)"""
         be, B, H, W = self.be, self.B, self.H, self.W
-        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        H2, W2, H4, W4 = self.H2, self.W2, self.H4, self.W4
         assert ir.shape == (B, 1, H, W) and ir.dtype == torch.float32 and ir.is_contiguous()
         # inc: reflect-pad 3 + 7x7 conv over 49 of 64 operand slots, IN + ReLU into cat2[128:192)
         if getattr(be, "direct_smallk", False):
@@ -325,7 +338,7 @@ class GeneratorEngine:
         """no_antialias=True (irc:468): down1 / down2 are 3x3 stride-2 convolutions = 2x2 convolutions over space-to-depth copies of
         the padded x0 / x1 frames; their InstanceNorm + ReLU output IS x1 / x2 (no blur module, irc:474, :482)"""
         be, B, H, W = self.be, self.B, self.H, self.W
-        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        H2, W2, H4, W4 = self.H2, self.W2, self.H4, self.W4
         be.gather(self.Z0.view(), View(self.Sx0, 0, self.hb1, self.wb1), 64, B, H, W, 1, 0, stats=self.st0, cnt=H * W, eps=EPS, act=ACT_RELU, dst_s2d=1)
         self.down1.fwd(self.Sx0, 0, self.Z1s)
         v1 = self._vZ1s(self.Z1s)
@@ -339,7 +352,7 @@ class GeneratorEngine:
 
     def _encoder_antialiased(self):
         be, B, H, W = self.be, self.B, self.H, self.W
-        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        H2, W2, H4, W4 = self.H2, self.W2, self.H4, self.W4
         # down1: 3x3 zero-pad conv at full resolution, then IN + ReLU + blur-downsample fused
         self.down1.fwd_stats(self.cat2.t, 128, self.Z1.t, self.st1, self.ri_full, B, self.Z1.hp * self.Z1.wp, self.Z1.view(), 128, H, W)
         be.gather(self.Z1.view(), self.cat1.view(256), 128, B, H2, W2, 1, 0, tables=self.t_down1, stats=self.st1, cnt=H * W, eps=EPS, act=ACT_RELU)
@@ -349,7 +362,7 @@ class GeneratorEngine:
 
     def _bottleneck_and_decoder(self):
         be, B, H, W = self.be, self.B, self.H, self.W
-        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        H2, W2, H4, W4 = self.H2, self.W2, self.H4, self.W4
         # 9 ResNet blocks (irc:362-418): reflect halo written by the apply pass
         n4 = H4 * W4
         for b in range(self.nb):
@@ -392,7 +405,7 @@ class GeneratorEngine:
         """dfake: fp32 [B,3,H,W] = dL/dfake.  Fills arena.grad for every generator parameter.  `after_blocks`
         (optional callable) runs once the gradients of outc, up2, up1 and all ResNet blocks are final."""
         be, B, H, W = self.be, self.B, self.H, self.W
-        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        H2, W2, H4, W4 = self.H2, self.W2, self.H4, self.W4
         y4 = self.y4
         # outc: tanh' and horizontal tap expansion, then weight / data gradients over the vertical taps
         be.tap_expand(dfake, self.fake, self.outc_shifts, 3, B, H, W, y4.hp, y4.wp, 3, 3, self.E_out,

@@ -96,6 +96,21 @@ def bilinear_matrix(n: int) -> np.ndarray:
     return m
 
 
+def resize_matrix(m: int, n: int) -> np.ndarray:
+    """F.interpolate(size=m, mode='bilinear', align_corners=True) of an axis of n samples (irc:555-556, :562-563), m x n;
+    float32 index arithmetic as in ATen's area_pixel_compute_source_index"""
+    a = np.zeros((m, n))
+    scale = np.float32(n - 1) / np.float32(m - 1) if m > 1 else np.float32(0)
+    for o in range(m):
+        s = np.float32(scale * np.float32(o))
+        i0 = min(int(np.floor(s)), n - 1)
+        i1 = min(i0 + 1, n - 1)
+        l1 = float(np.float32(s - np.float32(i0)))
+        a[o, i0] += 1.0 - l1
+        a[o, i1] += l1
+    return a
+
+
 def up_matrix(n: int) -> np.ndarray:
     return blur_matrix(2 * n) @ bilinear_matrix(n)
 

@@ -127,17 +127,25 @@ def compute_metrics(pred_01, gt_01):
     return mae, mse, psnr, ssim_val
 
 
-def batch_metrics(fake: torch.Tensor, gt_01: torch.Tensor):
+def batch_metrics(fake: torch.Tensor, gt_01: torch.Tensor, with_ssim: bool = False):
     """Batched device version of tensor_to_rgb_image + compute_metrics: fake Bx3xHxW in [-1,1], gt Bx3xHxW in [0,1].
-    Returns (uint8 BxHxWx3 predictions, per-image mae, mse, psnr lists)."""
+    Returns (uint8 BxHxWx3 predictions, per-image mae, mse, psnr lists) and - with_ssim - the per-image SSIM list
+    (structural_similarity with the defaults the reference uses, irc:1208-1215, evaluated on the device)."""
     B, C, H, W = fake.shape
     u8 = torch.empty(B, H, W, C, device=fake.device, dtype=torch.uint8)
     sums = torch.zeros(B, 2, device=fake.device, dtype=torch.float64)
-    M.backend().quantize_metrics(fake.contiguous().float(), gt_01.contiguous().float(), u8, sums)
+    gt = gt_01.contiguous().float()
+    M.backend().quantize_metrics(fake.contiguous().float(), gt, u8, sums)
+    ssum = None
+    if with_ssim:
+        ssum = torch.zeros(B, device=fake.device, dtype=torch.float64)
+        M.backend().ssim_metric(u8, gt, ssum)
     s = (sums / (C * H * W)).cpu().numpy()
     mae = [float(np.float32(v)) for v in s[:, 0]]
     mse = [float(np.float32(v)) for v in s[:, 1]]
     psnr = [float("inf") if m == 0 else -10.0 * math.log10(m + 1e-12) for m in mse]
+    if with_ssim:
+        return u8, mae, mse, psnr, [float(v) for v in (ssum / (3 * (H - 6) * (W - 6))).cpu().numpy()]
     return u8, mae, mse, psnr
 
 
@@ -264,8 +272,10 @@ def summarize_rows(rows: List[Dict]) -> Optional[Dict]:
     if not rows:
         return None
     count = len(rows)
+    have_ssim = any(r.get("ssim") is not None for r in rows)
     return dict(count=count, mean_mae=sum(r["mae"] for r in rows) / count, mean_mse=sum(r["mse"] for r in rows) / count,
-                mean_psnr=sum(r["psnr"] for r in rows if np.isfinite(r["psnr"])) / count)
+                mean_psnr=sum(r["psnr"] for r in rows if np.isfinite(r["psnr"])) / count,
+                mean_ssim=(sum(r["ssim"] for r in rows if r.get("ssim") is not None) / count) if have_ssim else None)
 
 
 def write_topk_ranking(cfg: M.Config, rows: List[Dict]) -> Optional[str]:
@@ -325,9 +335,14 @@ def run_test(cfg: M.Config, loader=None):
             names = batch.get("name") or [f"img_{bi:05d}_{j}.png" for j in range(ir.shape[0])]
             if "rgb" in batch and batch["rgb"] is not None:
                 gt01 = (batch["rgb"].to(device).float() + 1.0) * 0.5 if batch.get("rgb_range", "pm1") == "pm1" else batch["rgb"].to(device).float()
-                u8, mae, mse, psnr = batch_metrics(fake, gt01)
-                for j, (n_, a, b, c) in enumerate(zip(names, mae, mse, psnr)):
-                    rows.append({"file": n_, "mae": a, "mse": b, "psnr": c, "ssim": None, "_order": (bi, j)})
+                # the SSIM column needs scikit-image in the reference (None without it, irc:1208-1215); here it is evaluated on
+                # the device with the same defaults unless cfg.ssim_metric is False
+                want_ssim = bool(getattr(cfg, "ssim_metric", True)) and min(fake.shape[2], fake.shape[3]) >= 7
+                res = batch_metrics(fake, gt01, with_ssim=want_ssim)
+                u8, mae, mse, psnr = res[:4]
+                ssim_vals = res[4] if want_ssim else [None] * len(mae)
+                for j, (n_, a, b, c, s_) in enumerate(zip(names, mae, mse, psnr, ssim_vals)):
+                    rows.append({"file": n_, "mae": a, "mse": b, "psnr": c, "ssim": s_, "_order": (bi, j)})
             else:
                 u8 = torch.empty(ir.shape[0], H, W, 3, device=device, dtype=torch.uint8)
                 M.backend().quantize_metrics(fake.contiguous().float(), None, u8, None)
@@ -342,18 +357,23 @@ def run_test(cfg: M.Config, loader=None):
         print(f"Mean MAE   : {mean_mae:.6f}")
         print(f"Mean MSE   : {mean_mse:.6f}")
         print(f"Mean PSNR  : {mean_psnr:.4f} dB")
-        print("Mean SSIM  : None (scikit-image not installed)")
+        mean_ssim = summary["mean_ssim"]
+        print(f"Mean SSIM  : {mean_ssim:.6f}" if mean_ssim is not None else "Mean SSIM  : None (scikit-image not installed)")
         finite = [r for r in rows if np.isfinite(r["psnr"])]
         best = max(finite, key=lambda r: r["psnr"]) if finite else None        # first maximum, like the running `>` of irc:1437-1439
         print(f"Best PSNR  : {best['psnr']:.4f} ({best['file']})" if best else "Best PSNR  : N/A")
-        print("Best SSIM  : N/A")
+        with_s = [r for r in rows if r.get("ssim") is not None]
+        best_s = max(with_s, key=lambda r: r["ssim"]) if with_s else None      # irc:1440-1442
+        print(f"Best SSIM  : {best_s['ssim']:.6f} ({best_s['file']})" if best_s else "Best SSIM  : N/A")
         path = os.path.join(cfg.output_dir, "metrics_test.csv")
         with open(path, "w", encoding="utf-8") as f:
             f.write("file,mae,mse,psnr,ssim\n")
             for m in rows:
-                f.write(f"{m['file']},{m['mae']:.8f},{m['mse']:.8f},{m['psnr']:.6f},\n")
+                ssim_str = "" if m.get("ssim") is None else f"{m['ssim']:.6f}"
+                f.write(f"{m['file']},{m['mae']:.8f},{m['mse']:.8f},{m['psnr']:.6f},{ssim_str}\n")
             f.write("\n# Summary\n")
-            f.write(f"# count,{count}\n# mean_mae,{mean_mae:.8f}\n# mean_mse,{mean_mse:.8f}\n# mean_psnr,{mean_psnr:.6f}\n# mean_ssim,\n")
+            ms = "" if mean_ssim is None else f"{mean_ssim:.6f}"
+            f.write(f"# count,{count}\n# mean_mae,{mean_mae:.8f}\n# mean_mse,{mean_mse:.8f}\n# mean_psnr,{mean_psnr:.6f}\n# mean_ssim,{ms}\n")
         print(f"\nMetrics saved to: {path}")
         write_topk_ranking(cfg, rows)
     elif summary is None:

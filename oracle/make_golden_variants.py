@@ -76,6 +76,31 @@ def main():
             gold[f"{tag}/grad_norm/" + k] = p_.grad.norm().item(); gold[f"{tag}/grad_sample/" + k] = MG.sample(p_.grad)
             gold[f"{tag}/grad_absmax/" + k] = p_.grad.abs().max().item()
         gold[f"{tag}/fake"] = fake.detach().numpy(); gold[f"{tag}/upstream"] = gv.numpy()
+    # default graph at a size that is not a multiple of 4 (29 x 38): Downsample rounds up (15 x 19, 8 x 10), UpsampleAA doubles
+    # (16 x 20, 30 x 38), and the decoder maps are resized onto the skip connections by F.interpolate(..., align_corners=True)
+    # (irc:555-556 in both axes, irc:562-563 in the vertical axis only)
+    pO = O.seeded_params(O.generator_shapes(), 999, bias_std=0.02)
+    irO, _ = O.synthetic_pair(2, 29, 38)
+    cfg = R.Config(); cfg.device = "cpu"
+    m = R.IRColorizationModel(cfg)
+    missing = m.netG.load_state_dict(pO, strict=False)
+    assert not missing.unexpected_keys and all(k.endswith("filt") for k in missing.missing_keys), missing
+    fake = m(irO)
+    assert tuple(fake.shape) == (2, 3, 29, 38)
+    gv = torch.randn(fake.shape, generator=torch.Generator().manual_seed(12))
+    fake.backward(gv)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in pO.items()}
+    fo = O.generator_forward(leaves, irO)
+    MG.close(fo, fake.detach(), 2e-5, "odd-size forward")
+    fo.backward(gv)
+    for k, p_ in m.netG.named_parameters():
+        noise = k.endswith("bias") and not k.startswith("outc")
+        if p_.grad.abs().max() > 1e-4 and not noise:
+            rel = ((leaves[k].grad - p_.grad).norm() / p_.grad.norm()).item()
+            assert rel < 5e-3, ("odd", k, rel)
+        gold["odd/grad_norm/" + k] = p_.grad.norm().item(); gold["odd/grad_sample/" + k] = MG.sample(p_.grad)
+        gold["odd/grad_absmax/" + k] = p_.grad.abs().max().item()
+    gold["odd/fake"] = fake.detach().numpy(); gold["odd/upstream"] = gv.numpy()
     np.savez_compressed(os.path.join(MG.OUT, "ref_variants.npz"), **gold)
     print("wrote ref_variants.npz keys:", len(gold))
 

@@ -436,6 +436,17 @@ class RefBackend:
             sums.copy_(torch.stack([d.abs().double().sum((1, 2, 3)), (d * d).double().sum((1, 2, 3))], -1))
 
     # ------------------------------------------------------------------ optimizer / layout
+    def ssim_metric(self, u8, gt, sums):
+        """7x7 uniform-window SSIM in float64 over the valid region (skimage defaults), summed over channels and positions"""
+        self.launches += 1
+        x = gt.double(); y = (u8.permute(0, 3, 1, 2).float() / 255.0).double()
+        box = lambda t: F.avg_pool2d(t, 7, 1)
+        ux, uy, uxx, uyy, uxy = box(x), box(y), box(x * x), box(y * y), box(x * y)
+        cn = 49.0 / 48.0
+        vx, vy, vxy = cn * (uxx - ux * ux), cn * (uyy - uy * uy), cn * (uxy - ux * uy)
+        S = ((2 * ux * uy + 1e-4) * (2 * vxy + 9e-4)) / ((ux * ux + uy * uy + 1e-4) * (vx + vy + 9e-4))
+        sums.copy_(S.sum((1, 2, 3)))
+
     def accumulate(self, sums, coef, acc):
         self.launches += 1
         n = sums.numel()

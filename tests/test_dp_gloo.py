@@ -93,7 +93,7 @@ def _fake_rows():
         for j in range(3):
             mse = float(torch.rand(1, generator=g)) * 0.1 + 1e-3
             rows.append({"file": f"img_{bi}_{j}.png", "mae": float(torch.rand(1, generator=g)), "mse": mse,
-                         "psnr": -10.0 * __import__("math").log10(mse), "ssim": None, "_order": (bi, j)})
+                         "psnr": -10.0 * __import__("math").log10(mse), "ssim": float(torch.rand(1, generator=g)), "_order": (bi, j)})
     return rows
 
 

@@ -42,7 +42,8 @@ def test_oracle_variant_forward_and_grads():
 
 
 # variant tag -> (fixture prefix, no_antialias_up, no_antialias, parameter seed of make_golden_variants.py)
-VARIANTS = {"up": ("", True, False, 4321), "na": ("na/", False, True, 777), "nab": ("nab/", True, True, 778)}
+VARIANTS = {"up": ("", True, False, 4321), "na": ("na/", False, True, 777), "nab": ("nab/", True, True, 778), "odd": ("odd/", False, False, 999)}
+SIZES = {"odd": (29, 38)}          # default graph at a size that is not a multiple of 4: bilinear fix-up of irc:555-556, :562-563
 
 
 def _variant_params(tag):
@@ -67,8 +68,9 @@ def _check_engine(be, dev, tol_fwd, tol_dec, tol_enc, tag="up"):
     from irc_b200 import engine as E
     pre, up, na, _ = VARIANTS[tag]
     pG = _variant_params(tag)
-    ir, _ = O.synthetic_pair(B, H, W)
-    eng = E.GeneratorEngine(be, B, H, W, dev, no_antialias_up=up, no_antialias=na)
+    h, w = SIZES.get(tag, (H, W))
+    ir, _ = O.synthetic_pair(B, h, w)
+    eng = E.GeneratorEngine(be, B, h, w, dev, no_antialias_up=up, no_antialias=na)
     eng.arena.load(pG); eng.refresh_weights()
     fake = eng.forward(ir.to(dev))
     e = rel(fake, torch.from_numpy(GOLD[pre + "fake"]))
@@ -114,6 +116,26 @@ def test_plan_with_strided_downsampling_matches_reference(tag):
     L.ACT_DTYPE = torch.float32
     try:
         _check_engine(RefBackend(), "cpu", 1e-5, 1e-4, 1e-2, tag=tag)
+    finally:
+        L.ACT_DTYPE = old
+
+
+def test_oracle_odd_size_forward():
+    ir, _ = O.synthetic_pair(B, *SIZES["odd"])
+    fake = O.generator_forward(_variant_params("odd"), ir)
+    assert np.abs(fake.numpy() - GOLD["odd/fake"]).max() < 5e-5
+
+
+def test_plan_at_a_size_that_is_not_a_multiple_of_4_matches_reference():
+    """29 x 38: Downsample rounds up, the decoder maps are resized onto the skip-connection grids (irc:555-556, :562-563); the
+    resize is composed with UpsampleAA into one separable operator per axis (layout.resize_matrix @ layout.up_matrix)"""
+    import irc_b200  # noqa: F401
+    from irc_b200 import layout as L
+    from ref_backend import RefBackend
+    old = L.ACT_DTYPE
+    L.ACT_DTYPE = torch.float32
+    try:
+        _check_engine(RefBackend(), "cpu", 1e-5, 1e-4, 1e-2, tag="odd")
     finally:
         L.ACT_DTYPE = old
 
@@ -170,9 +192,10 @@ def test_gpu_generator_with_transposed_conv_upsampling():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag", ["na", "nab"])
+@pytest.mark.parametrize("tag", ["na", "nab", "odd"])
 def test_gpu_generator_with_strided_downsampling(tag):
-    """no_antialias=True on the CUDA path (bf16): same bounds as the other whole-network runs"""
+    """no_antialias=True, and the default graph at 29 x 38 (odd-size bilinear fix-up), on the CUDA path (bf16): same bounds as the
+    other whole-network runs"""
     from irc_b200._native import CudaBackend
     _check_engine(CudaBackend(), "cuda", 3e-2, 0.25, 0.35, tag=tag)
 
