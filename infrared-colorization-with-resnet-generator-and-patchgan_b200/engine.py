@@ -22,9 +22,10 @@ IMAGENET_MEAN = (0.485, 0.456, 0.406)   # irc:667-668
 IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
-def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9, no_antialias_up=False) -> Dict[str, tuple]:
+def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9, no_antialias_up=False, norm="instance") -> Dict[str, tuple]:
     """state_dict parameter shapes of ResnetUNetGenerator (irc:457-531).  no_antialias_up: the two UpsampleAA modules (buffers
-    only) become nn.ConvTranspose2d(C, C, 3, 2, 1, 1) with parameters up{1,2}_up.{weight (Cin, Cout, 3, 3), bias} (irc:495-516)"""
+    only) become nn.ConvTranspose2d(C, C, 3, 2, 1, 1) with parameters up{1,2}_up.{weight (Cin, Cout, 3, 3), bias} (irc:495-516).
+    norm='none': get_norm_layer returns a lambda, so use_bias is False (irc:452-455) and every convolution but outc loses its bias"""
     s = {"inc.1.weight": (ngf, input_nc, 7, 7), "inc.1.bias": (ngf,),
          "down1.0.weight": (2 * ngf, ngf, 3, 3), "down1.0.bias": (2 * ngf,),
          "down2.0.weight": (4 * ngf, 2 * ngf, 3, 3), "down2.0.bias": (4 * ngf,)}
@@ -39,15 +40,19 @@ def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9, no_antialias_u
         s["up2_up.weight"] = (2 * ngf, 2 * ngf, 3, 3); s["up2_up.bias"] = (2 * ngf,)
     s["up2_conv.0.weight"] = (ngf, 3 * ngf, 3, 3); s["up2_conv.0.bias"] = (ngf,)
     s["outc.1.weight"] = (output_nc, ngf, 7, 7); s["outc.1.bias"] = (output_nc,)
+    if norm != "instance":
+        s = {k: v for k, v in s.items() if not k.endswith(".bias") or k == "outc.1.bias"}
     return s
 
 
-def discriminator_shapes(input_nc=4, ndf=64) -> Dict[str, tuple]:
-    """NLayerDiscriminator(n_layers=3) parameter shapes (irc:598-630)"""
+def discriminator_shapes(input_nc=4, ndf=64, norm="instance") -> Dict[str, tuple]:
+    """NLayerDiscriminator(n_layers=3) parameter shapes (irc:598-630); without InstanceNorm model.2/5/8 have no bias (irc:590-593)"""
     chans = [(input_nc, ndf), (ndf, 2 * ndf), (2 * ndf, 4 * ndf), (4 * ndf, 8 * ndf), (8 * ndf, 1)]
     s = {}
     for idx, (ci, co) in zip((0, 2, 5, 8, 11), chans):
-        s[f"model.{idx}.weight"] = (co, ci, 4, 4); s[f"model.{idx}.bias"] = (co,)
+        s[f"model.{idx}.weight"] = (co, ci, 4, 4)
+        if norm == "instance" or idx in (0, 11):
+            s[f"model.{idx}.bias"] = (co,)
     return s
 
 
@@ -90,6 +95,10 @@ class ConvOp:
         """forward convolution followed by the InstanceNorm statistics of its output (irc:161): from the GEMM epilogue when the
         layer is deep enough for the epilogue to hide behind the MMAs (be.stats_epilogue_min_k) and the frame geometry allows
         it, else by a separate pass over the output"""
+        if stats is None:
+            # norm='none' (irc:158-163): no statistics, the activation is applied by the GEMM epilogue instead (kw carries it)
+            self.fwd(a, a_chan_off, out, **kw)
+            return
         if self.lay.T * self.lay.K >= self.be.stats_epilogue_min_k and rows_per_img >= 128 and self.lay.N % 64 == 0 and row_img is not None:
             self.fwd(a, a_chan_off, out, row_img=row_img, in_stats=(stats, n_img, rows_per_img), **kw)
         else:
@@ -169,7 +178,12 @@ class TransposedUp:
 # ==========================================================================================
 class GeneratorEngine:
     def __init__(self, be, B: int, H: int, W: int, device, ngf: int = 64, n_blocks: int = 9, training: bool = True,
-                 arena: L.ParamArena = None, no_antialias_up: bool = False, no_antialias: bool = False):
+                 arena: L.ParamArena = None, no_antialias_up: bool = False, no_antialias: bool = False, norm: str = "instance"):
+        if norm not in ("instance", "none"):
+            raise NotImplementedError(f"norm '{norm}': the generator engine builds nn.InstanceNorm2d (default) and Identity ('none'), irc:148-165")
+        if norm == "none" and no_antialias_up:
+            raise NotImplementedError("norm='none' together with no_antialias_up=True (bias-free transposed convolutions) is not built")
+        self.norm_on = norm == "instance"
         if min(H, W) < 8:
             raise ValueError("the generator needs at least 8 x 8 pixels (ReflectionPad2d(1) at a quarter of the resolution)")
         if no_antialias and (H % 4 or W % 4):
@@ -186,7 +200,9 @@ class GeneratorEngine:
                                       "convolution, irc:555-556) is not built")
         self.convT = bool(no_antialias_up)
         self.noaa = bool(no_antialias)          # stride-2 down-sampling convolutions instead of conv + blur (irc:468, :474, :482)
-        self.arena = arena or L.ParamArena(generator_shapes(1, 3, ngf, n_blocks, no_antialias_up), device)
+        self.arena = arena or L.ParamArena(generator_shapes(1, 3, ngf, n_blocks, no_antialias_up, norm), device)
+        if ("inc.1.bias" in self.arena.offset) != self.norm_on:
+            raise ValueError("the parameter arena does not match norm=%r (convolution biases exist exactly with InstanceNorm, irc:452-455)" % norm)
         if self.convT and "up1_up.weight" not in self.arena.offset:
             raise ValueError("no_antialias_up=True needs an arena with the ConvTranspose2d parameters up{1,2}_up.{weight,bias}")
         self.packer = L.Packer(self.arena)
@@ -272,6 +288,17 @@ class GeneratorEngine:
         if training:
             self._alloc_backward()
 
+    # ---- norm='none' (irc:158-163): no statistics; the ReLU moves from the normalise-and-activate pass into the GEMM epilogue
+    def _st(self, st):
+        return st if self.norm_on else None
+
+    def _na(self, st, cnt, act=ACT_RELU):
+        """keyword arguments of an apply pass: InstanceNorm + activation, or a plain copy when the map is already activated"""
+        return dict(stats=st, cnt=cnt, eps=EPS, act=act) if self.norm_on else {}
+
+    def _epi(self):
+        return {} if self.norm_on else dict(act=ACT_RELU)
+
     def _alloc_backward(self):
         B, H, W, dev = self.B, self.H, self.W, self.dev
         H2, W2, H4, W4 = self.H2, self.W2, self.H4, self.W4
@@ -315,12 +342,14 @@ class GeneratorEngine:
         if getattr(be, "direct_smallk", False):
             # direct convolution from the fp32 image; the im2col operand is only written when the weight gradient will read it
             be.note = ("G.inc", "fwd", self.inc.flops)
-            be.smallk_conv_fwd(ir, None, None, None, B, H, W, 7, 1, 3, 1, H, W, 0, self.inc.lay.w_f.t, self.Z0.t, E=self.E_in if self.training else None)
+            be.smallk_conv_fwd(ir, None, None, None, B, H, W, 7, 1, 3, 1, H, W, 0, self.inc.lay.w_f.t, self.Z0.t, E=self.E_in if self.training else None,
+                               **self._epi())
         else:
             be.im2col(ir, None, None, None, B, H, W, 7, 1, 3, 1, H, W, 0, self.E_in)
-            self.inc.fwd(self.E_in, 0, self.Z0.t)
-        be.in_stats(self.Z0.view(), 64, B, H, W, self.st0)
-        be.gather(self.Z0.view(), self.cat2.view(128), 64, B, H, W, 1, 0, stats=self.st0, cnt=H * W, eps=EPS, act=ACT_RELU)
+            self.inc.fwd(self.E_in, 0, self.Z0.t, **self._epi())
+        if self.norm_on:
+            be.in_stats(self.Z0.view(), 64, B, H, W, self.st0)
+        be.gather(self.Z0.view(), self.cat2.view(128), 64, B, H, W, 1, 0, **self._na(self.st0, H * W))
         if self.noaa:
             self._encoder_strided()
         else:
@@ -339,26 +368,28 @@ class GeneratorEngine:
         the padded x0 / x1 frames; their InstanceNorm + ReLU output IS x1 / x2 (no blur module, irc:474, :482)"""
         be, B, H, W = self.be, self.B, self.H, self.W
         H2, W2, H4, W4 = self.H2, self.W2, self.H4, self.W4
-        be.gather(self.Z0.view(), View(self.Sx0, 0, self.hb1, self.wb1), 64, B, H, W, 1, 0, stats=self.st0, cnt=H * W, eps=EPS, act=ACT_RELU, dst_s2d=1)
-        self.down1.fwd(self.Sx0, 0, self.Z1s)
+        be.gather(self.Z0.view(), View(self.Sx0, 0, self.hb1, self.wb1), 64, B, H, W, 1, 0, **self._na(self.st0, H * W), dst_s2d=1)
+        self.down1.fwd(self.Sx0, 0, self.Z1s, **self._epi())
         v1 = self._vZ1s(self.Z1s)
-        be.in_stats(v1, 128, B, H2, W2, self.st1)
-        be.gather(v1, self.cat1.view(256), 128, B, H2, W2, 1, 0, stats=self.st1, cnt=H2 * W2, eps=EPS, act=ACT_RELU)
-        be.gather(v1, View(self.Sx1, 0, self.hb2, self.wb2), 128, B, H2, W2, 1, 0, stats=self.st1, cnt=H2 * W2, eps=EPS, act=ACT_RELU, dst_s2d=1)
-        self.down2.fwd(self.Sx1, 0, self.Z2s)
+        if self.norm_on:
+            be.in_stats(v1, 128, B, H2, W2, self.st1)
+        be.gather(v1, self.cat1.view(256), 128, B, H2, W2, 1, 0, **self._na(self.st1, H2 * W2))
+        be.gather(v1, View(self.Sx1, 0, self.hb2, self.wb2), 128, B, H2, W2, 1, 0, **self._na(self.st1, H2 * W2), dst_s2d=1)
+        self.down2.fwd(self.Sx1, 0, self.Z2s, **self._epi())
         v2 = self._vZ2s(self.Z2s)
-        be.in_stats(v2, 256, B, H4, W4, self.st2)
-        be.gather(v2, self.X[0].view(), 256, B, H4, W4, 1, 1, stats=self.st2, cnt=H4 * W4, eps=EPS, act=ACT_RELU)
+        if self.norm_on:
+            be.in_stats(v2, 256, B, H4, W4, self.st2)
+        be.gather(v2, self.X[0].view(), 256, B, H4, W4, 1, 1, **self._na(self.st2, H4 * W4))
 
     def _encoder_antialiased(self):
         be, B, H, W = self.be, self.B, self.H, self.W
         H2, W2, H4, W4 = self.H2, self.W2, self.H4, self.W4
         # down1: 3x3 zero-pad conv at full resolution, then IN + ReLU + blur-downsample fused
-        self.down1.fwd_stats(self.cat2.t, 128, self.Z1.t, self.st1, self.ri_full, B, self.Z1.hp * self.Z1.wp, self.Z1.view(), 128, H, W)
-        be.gather(self.Z1.view(), self.cat1.view(256), 128, B, H2, W2, 1, 0, tables=self.t_down1, stats=self.st1, cnt=H * W, eps=EPS, act=ACT_RELU)
+        self.down1.fwd_stats(self.cat2.t, 128, self.Z1.t, self._st(self.st1), self.ri_full, B, self.Z1.hp * self.Z1.wp, self.Z1.view(), 128, H, W, **self._epi())
+        be.gather(self.Z1.view(), self.cat1.view(256), 128, B, H2, W2, 1, 0, tables=self.t_down1, **self._na(self.st1, H * W))
         # down2
-        self.down2.fwd_stats(self.cat1.t, 256, self.Z2.t, self.st2, self.ri_half, B, self.Z2.hp * self.Z2.wp, self.Z2.view(), 256, H2, W2)
-        be.gather(self.Z2.view(), self.X[0].view(), 256, B, H4, W4, 1, 1, tables=self.t_down2, stats=self.st2, cnt=H2 * W2, eps=EPS, act=ACT_RELU)
+        self.down2.fwd_stats(self.cat1.t, 256, self.Z2.t, self._st(self.st2), self.ri_half, B, self.Z2.hp * self.Z2.wp, self.Z2.view(), 256, H2, W2, **self._epi())
+        be.gather(self.Z2.view(), self.X[0].view(), 256, B, H4, W4, 1, 1, tables=self.t_down2, **self._na(self.st2, H2 * W2))
 
     def _bottleneck_and_decoder(self):
         be, B, H, W = self.be, self.B, self.H, self.W
@@ -367,26 +398,32 @@ class GeneratorEngine:
         n4 = H4 * W4
         for b in range(self.nb):
             c1, c2 = self.res[b]
-            c1.fwd(self.X[b].t, 0, self.Za[b].t)
-            be.in_apply(self.Za[b].view(), self.Hh[b].view(), 256, B, H4, W4, 1, 1, self.sta[b], eps=EPS, act=ACT_RELU)
+            c1.fwd(self.X[b].t, 0, self.Za[b].t, **self._epi())
+            if self.norm_on:
+                be.in_apply(self.Za[b].view(), self.Hh[b].view(), 256, B, H4, W4, 1, 1, self.sta[b], eps=EPS, act=ACT_RELU)
+            else:
+                be.gather(self.Za[b].view(), self.Hh[b].view(), 256, B, H4, W4, 1, 1)          # reflected ring around the activated map
             c2.fwd(self.Hh[b].t, 0, self.Zb[b].t)
             # the last block output feeds only the up-sampling: a transposed convolution wants a ZERO ring, not the reflected one
             halo = 0 if (self.convT and b == self.nb - 1) else 1
-            be.in_apply(self.Zb[b].view(), self.X[b + 1].view(), 256, B, H4, W4, 1, halo, self.stb[b], eps=EPS, act=ACT_NONE, res=self.X[b].view())
+            if self.norm_on:
+                be.in_apply(self.Zb[b].view(), self.X[b + 1].view(), 256, B, H4, W4, 1, halo, self.stb[b], eps=EPS, act=ACT_NONE, res=self.X[b].view())
+            else:
+                be.gather(self.Zb[b].view(), self.X[b + 1].view(), 256, B, H4, W4, 1, halo, res=self.X[b].view())
         if self.convT:
             # up1 / up2 by ConvTranspose2d (irc:495-499, :512-516)
             self.up1_t.forward(self.cat1, 0)
-            self.up1.fwd_stats(self.cat1.t, 0, self.Z3.t, self.st3, self.ri_half, B, self.Z3.hp * self.Z3.wp, self.Z3.view(), 128, H2, W2)
-            be.gather(self.Z3.view(), self.A3.view(), 128, B, H2, W2, 1, 0, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU)
+            self.up1.fwd_stats(self.cat1.t, 0, self.Z3.t, self._st(self.st3), self.ri_half, B, self.Z3.hp * self.Z3.wp, self.Z3.view(), 128, H2, W2, **self._epi())
+            be.gather(self.Z3.view(), self.A3.view(), 128, B, H2, W2, 1, 0, **self._na(self.st3, H2 * W2))
             self.up2_t.forward(self.cat2, 0)
         else:
             # up1: UpsampleAA into cat1[0:256), conv on the concatenation
             be.gather(self.X[self.nb].view(), self.cat1.view(0), 256, B, H2, W2, 1, 0, tables=self.t_up1)
-            self.up1.fwd_stats(self.cat1.t, 0, self.Z3.t, self.st3, self.ri_half, B, self.Z3.hp * self.Z3.wp, self.Z3.view(), 128, H2, W2)
+            self.up1.fwd_stats(self.cat1.t, 0, self.Z3.t, self._st(self.st3), self.ri_half, B, self.Z3.hp * self.Z3.wp, self.Z3.view(), 128, H2, W2, **self._epi())
             # up2: IN + ReLU + UpsampleAA fused into cat2[0:128)
-            be.gather(self.Z3.view(), self.cat2.view(0), 128, B, H, W, 1, 0, tables=self.t_up2, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU)
-        self.up2.fwd_stats(self.cat2.t, 0, self.Z4.t, self.st4, self.ri_full, B, self.Z4.hp * self.Z4.wp, self.Z4.view(), 64, H, W)
-        be.gather(self.Z4.view(), self.y4.view(), 64, B, H, W, 3, 1, stats=self.st4, cnt=H * W, eps=EPS, act=ACT_RELU)
+            be.gather(self.Z3.view(), self.cat2.view(0), 128, B, H, W, 1, 0, tables=self.t_up2, **self._na(self.st3, H2 * W2))
+        self.up2.fwd_stats(self.cat2.t, 0, self.Z4.t, self._st(self.st4), self.ri_full, B, self.Z4.hp * self.Z4.wp, self.Z4.view(), 64, H, W, **self._epi())
+        be.gather(self.Z4.view(), self.y4.view(), 64, B, H, W, 3, 1, **self._na(self.st4, H * W))
 
     def output_head(self) -> torch.Tensor:
         """outc (irc:527-531) on the frame y4: 7x7 reflect conv 64->3 as a GEMM over the 7 vertical taps (21 of 32 outputs), then
@@ -414,7 +451,7 @@ class GeneratorEngine:
         self.outc.dgrad(self.E_out, self.G4.t)
         # up2_conv
         be.fold_inplace(self.G4.t, 0, 64, B, H, W, 3)             # ReflectionPad2d(3)^T on the border pixels only
-        be.in_bwd(self.Z4.view(), self.G4.view(), self.dZ4.view(), 64, B, H, W, stats=self.st4, cnt=H * W, eps=EPS, act=ACT_RELU, bsum=self.bsum)
+        be.in_bwd(self.Z4.view(), self.G4.view(), self.dZ4.view(), 64, B, H, W, stats=self._st(self.st4), cnt=H * W, eps=EPS, act=ACT_RELU, bsum=self.bsum)
         self.up2.wgrad(self.dZ4.t, self.cat2.t, 0, self.cat2.rows)
         self.up2.dgrad(self.dZ4.t, self.Gcat2.t)
         # up1_conv (through UpsampleAA^T, or the transposed convolution's data gradient)
@@ -424,7 +461,7 @@ class GeneratorEngine:
         else:
             be.gather(self.Gcat2.view(0), self.g3.view(), 128, B, H2, W2, 0, 0, tables=self.t_up2_T)
             g_up1 = self.g3
-        be.in_bwd(self.Z3.view(), g_up1.view(), self.dZ3.view(), 128, B, H2, W2, stats=self.st3, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
+        be.in_bwd(self.Z3.view(), g_up1.view(), self.dZ3.view(), 128, B, H2, W2, stats=self._st(self.st3), cnt=H2 * W2, eps=EPS, act=ACT_RELU,
                   bsum=self.bsum)
         self.up1.wgrad(self.dZ3.t, self.cat1.t, 0, self.cat1.rows)
         self.up1.dgrad(self.dZ3.t, self.Gcat1.t)
@@ -439,13 +476,13 @@ class GeneratorEngine:
             c1, c2 = self.res[b]
             # `cur` (gradient w.r.t. the reflection-padded X[b+1]) still carries its ring: the fold is linear, so it is applied
             # where the gradient is consumed (here, on load) and once more when the stream leaves the blocks
-            be.in_bwd(self.Zb[b].view(), cur.view(), self.dZb.view(), 256, B, H4, W4, stats=self.stb[b], cnt=n4, eps=EPS, act=ACT_NONE, bsum=self.bsum,
+            be.in_bwd(self.Zb[b].view(), cur.view(), self.dZb.view(), 256, B, H4, W4, stats=self._st(self.stb[b]), cnt=n4, eps=EPS, act=ACT_NONE, bsum=self.bsum,
                       fold_pad=1)
             c2.wgrad(self.dZb.t, self.Hh[b].t, 0, self.dZb.rows)
             c2.dgrad(self.dZb.t, self.Gh.t)
             # ReflectionPad2d(1)^T of Gh is folded inside the backward pass (or by a separate in-place pass when the map is
             # too large for the single-pass cluster kernel)
-            be.in_bwd(self.Za[b].view(), self.Gh.view(), self.dZa.view(), 256, B, H4, W4, stats=self.sta[b], cnt=n4, eps=EPS, act=ACT_RELU,
+            be.in_bwd(self.Za[b].view(), self.Gh.view(), self.dZa.view(), 256, B, H4, W4, stats=self._st(self.sta[b]), cnt=n4, eps=EPS, act=ACT_RELU,
                       bsum=self.bsum, fold_pad=1)
             c1.wgrad(self.dZa.t, self.X[b].t, 0, self.dZa.rows)
             # data gradient of conv1 + the residual-stream gradient, ring included (unfolded: fold(a + b) = fold(a) + fold(b))
@@ -459,34 +496,34 @@ class GeneratorEngine:
         if self.noaa:
             # stride-2 encoder: x2 is the activated down2 output itself; the data gradients come back in space-to-depth order
             v1, v2 = self._vZ1s, self._vZ2s
-            be.in_bwd(v2(self.Z2s), cur.view(), v2(self.dZ2s), 256, B, H4, W4, stats=self.st2, cnt=H4 * W4, eps=EPS, act=ACT_RELU, bsum=self.bsum)
+            be.in_bwd(v2(self.Z2s), cur.view(), v2(self.dZ2s), 256, B, H4, W4, stats=self._st(self.st2), cnt=H4 * W4, eps=EPS, act=ACT_RELU, bsum=self.bsum)
             self.down2.wgrad(self.dZ2s, self.Sx1, 0, self.Sx1.shape[0])
             self.down2.dgrad(self.dZ2s, self.dSx1)
             # x1 feeds down2 and the up1 skip connection
-            be.in_bwd(v1(self.Z1s), self.Gcat1.view(256), v1(self.dZ1s), 128, B, H2, W2, stats=self.st1, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
+            be.in_bwd(v1(self.Z1s), self.Gcat1.view(256), v1(self.dZ1s), 128, B, H2, W2, stats=self._st(self.st1), cnt=H2 * W2, eps=EPS, act=ACT_RELU,
                       g2=View(self.dSx1, 0, self.hb2, self.wb2, 1, 1, 128), bsum=self.bsum)
             self.down1.wgrad(self.dZ1s, self.Sx0, 0, self.Sx0.shape[0])
             self.down1.dgrad(self.dZ1s, self.dSx0)
             # inc: x0 feeds down1 and the up2 skip connection
-            be.in_bwd(self.Z0.view(), self.Gcat2.view(128), self.dZ0.view(), 64, B, H, W, stats=self.st0, cnt=H * W, eps=EPS, act=ACT_RELU,
+            be.in_bwd(self.Z0.view(), self.Gcat2.view(128), self.dZ0.view(), 64, B, H, W, stats=self._st(self.st0), cnt=H * W, eps=EPS, act=ACT_RELU,
                       g2=View(self.dSx0, 0, self.hb1, self.wb1, 1, 1, 64), bsum=self.bsum)
             self.inc.wgrad(self.dZ0.t, self.E_in, 0, self.dZ0.rows)
             be.flush_sums()
             return
         # down2 (through Downsample^T)
         be.gather(cur.view(), self.g2.view(), 256, B, H2, W2, 0, 0, tables=self.t_down2_T)
-        be.in_bwd(self.Z2.view(), self.g2.view(), self.dZ2.view(), 256, B, H2, W2, stats=self.st2, cnt=H2 * W2, eps=EPS, act=ACT_RELU,
+        be.in_bwd(self.Z2.view(), self.g2.view(), self.dZ2.view(), 256, B, H2, W2, stats=self._st(self.st2), cnt=H2 * W2, eps=EPS, act=ACT_RELU,
                   bsum=self.bsum)
         self.down2.wgrad(self.dZ2.t, self.cat1.t, 256, self.cat1.rows)
         self.down2.dgrad(self.dZ2.t, self.Gx1.t)
         # down1: x1 feeds down2 and the up1 skip connection
         be.gather(self.Gcat1.view(256), self.g1.view(), 128, B, H, W, 0, 0, tables=self.t_down1_T, src2=self.Gx1.view())
-        be.in_bwd(self.Z1.view(), self.g1.view(), self.dZ1.view(), 128, B, H, W, stats=self.st1, cnt=H * W, eps=EPS, act=ACT_RELU,
+        be.in_bwd(self.Z1.view(), self.g1.view(), self.dZ1.view(), 128, B, H, W, stats=self._st(self.st1), cnt=H * W, eps=EPS, act=ACT_RELU,
                   bsum=self.bsum)
         self.down1.wgrad(self.dZ1.t, self.cat2.t, 128, self.cat2.rows)
         self.down1.dgrad(self.dZ1.t, self.Gx0.t)
         # inc: x0 feeds down1 and the up2 skip connection
-        be.in_bwd(self.Z0.view(), self.Gcat2.view(128), self.dZ0.view(), 64, B, H, W, stats=self.st0, cnt=H * W, eps=EPS, act=ACT_RELU,
+        be.in_bwd(self.Z0.view(), self.Gcat2.view(128), self.dZ0.view(), 64, B, H, W, stats=self._st(self.st0), cnt=H * W, eps=EPS, act=ACT_RELU,
                   g2=self.Gx0.view(), bsum=self.bsum)
         self.inc.wgrad(self.dZ0.t, self.E_in, 0, self.dZ0.rows)
         be.flush_sums()
@@ -496,12 +533,18 @@ class GeneratorEngine:
 # discriminator (irc:576-635)
 # ==========================================================================================
 class DiscriminatorEngine:
-    def __init__(self, be, n_img: int, H: int, W: int, device, arena: L.ParamArena = None, packer: L.Packer = None, layouts=None):
+    def __init__(self, be, n_img: int, H: int, W: int, device, arena: L.ParamArena = None, packer: L.Packer = None, layouts=None,
+                 norm: str = "instance"):
+        if norm not in ("instance", "none"):
+            raise NotImplementedError(f"norm '{norm}': the discriminator engine builds nn.InstanceNorm2d (default) and Identity ('none'), irc:148-165")
+        self.norm_on = norm == "instance"
         if H % 16 or W % 16 or H < 32 or W < 32:
             raise NotImplementedError("discriminator engine needs H, W multiples of 16 and >= 32 (70x70 PatchGAN receptive field)")
         self.be, self.n, self.H, self.W, self.dev = be, n_img, H, W, device
         own = packer is None
-        self.arena = arena or L.ParamArena(discriminator_shapes(4, 64), device)
+        self.arena = arena or L.ParamArena(discriminator_shapes(4, 64, norm), device)
+        if ("model.2.bias" in self.arena.offset) != self.norm_on:
+            raise ValueError("the parameter arena does not match norm=%r (model.2/5/8 have biases exactly with InstanceNorm, irc:590-593)" % norm)
         self.packer = packer or L.Packer(self.arena)
         A, P = self.arena, self.packer
         n = n_img
@@ -594,6 +637,18 @@ class DiscriminatorEngine:
                 be.im2col(a_, b_, None, None, k_, H, W, 4, 2, 1, 0, self.H1, self.W1, 2, self.E0[sl], row_img=self.row_img0[sl])
             self.c0.fwd(self.E0, 0, self.S0, bias=self.c0.bias(), act=ACT_LRELU, slope=0.2, row_img=self.row_img0)
         # model.2
+        if not self.norm_on:
+            # norm='none' (irc:158-163): LeakyReLU in the GEMM epilogues, the apply passes become plain copies into the next frame
+            lr = dict(act=ACT_LRELU, slope=0.2)
+            self.c2.fwd(self.S0v, 0, self.Z2, **lr)
+            be.gather(self._vZ2(self.Z2), View(self.S2, 0, self.hb2, self.wb2), 128, n, self.H2, self.W2, 1, 0, dst_s2d=1)
+            self.c5.fwd(self.S2, 0, self.Z5, **lr)
+            be.gather(self._vZ5(self.Z5), self.X8.view(), 256, n, self.H3, self.W3, 1, 0)
+            self.c8.fwd(self.X8.t, 0, self.Z8, **lr)
+            be.gather(self._vZ8(self.Z8), self.X11.view(), 512, n, self.H8o, self.W8o, 1, 0)
+            self.c11.fwd(self.X11.t, 0, self.P11)
+            be.tap_reduce(self.P11, self.shifts11, 1, n, self.Ho, self.Wo, self.X11.hp, self.X11.wp, 0, 0, self.c11.bias(), ACT_NONE, self.pred)
+            return self.pred
         self.c2.fwd_stats(self.S0v, 0, self.Z2, self.st2, self.ri2, n, self.hb0 * self.wb0, self._vZ2(self.Z2), 128, self.H2, self.W2)
         be.gather(self._vZ2(self.Z2), View(self.S2, 0, self.hb2, self.wb2), 128, n, self.H2, self.W2, 1, 0, stats=self.st2,
                   cnt=self.H2 * self.W2, eps=EPS, act=ACT_LRELU, slope=0.2, dst_s2d=1)
@@ -619,18 +674,18 @@ class DiscriminatorEngine:
         if want_wgrad:
             self.c11.wgrad(self.E11, self.X11.t, 0, self.X11.rows)
         self.c11.dgrad(self.E11, self.G11.t)
-        be.in_bwd(self._vZ8(self.Z8), self.G11.view(), self._vZ8(self.dZ8), 512, n, self.H8o, self.W8o, stats=self.st8,
+        be.in_bwd(self._vZ8(self.Z8), self.G11.view(), self._vZ8(self.dZ8), 512, n, self.H8o, self.W8o, stats=self.st8 if self.norm_on else None,
                   cnt=self.H8o * self.W8o, eps=EPS, act=ACT_LRELU, slope=0.2, bsum=self.bsum)
         if want_wgrad:
             self.c8.wgrad(self.dZ8, self.X8.t, 0, self.X8.rows)
         self.c8.dgrad(self.dZ8, self.G8.t)
-        be.in_bwd(self._vZ5(self.Z5), self.G8.view(), self._vZ5(self.dZ5), 256, n, self.H3, self.W3, stats=self.st5,
+        be.in_bwd(self._vZ5(self.Z5), self.G8.view(), self._vZ5(self.dZ5), 256, n, self.H3, self.W3, stats=self.st5 if self.norm_on else None,
                   cnt=self.H3 * self.W3, eps=EPS, act=ACT_LRELU, slope=0.2, bsum=self.bsum)
         if want_wgrad:
             self.c5.wgrad(self.dZ5, self.S2, 0, self.S2.shape[0])
         self.c5.dgrad(self.dZ5, self.dS2)
         be.in_bwd(self._vZ2(self.Z2), View(self.dS2, 0, self.hb2, self.wb2, 1, 1, 128), self._vZ2(self.dZ2), 128, n, self.H2, self.W2,
-                  stats=self.st2, cnt=self.H2 * self.W2, eps=EPS, act=ACT_LRELU, slope=0.2, bsum=self.bsum)
+                  stats=self.st2 if self.norm_on else None, cnt=self.H2 * self.W2, eps=EPS, act=ACT_LRELU, slope=0.2, bsum=self.bsum)
         if want_wgrad:
             self.c2.wgrad(self.dZ2, self.S0v, 0, self.S0v.shape[0])
         # data gradient of model.2 lands in space-to-depth order == the row order of model.0's output; the

@@ -91,11 +91,37 @@ class Config:
         self.synthetic_steps = 0      # >0: train/test on synthetic pairs (the KAIST image I/O layer is out of scope)
 
 
+class Identity(nn.Module):
+    """irc:148-151: pass-through layer used when normalisation is disabled"""
+
+    def forward(self, x):
+        return x
+
+
+def _no_norm(num_features):
+    return Identity()
+
+
 def get_norm_layer(norm_type="instance"):
-    """irc:148-165.  Only 'instance' is built natively; the returned class is only used as a tag."""
+    """irc:154-165.  The returned object is only used as a tag by the engines: nn.InstanceNorm2d (the default graph) or - 'none' /
+    None - a factory of Identity layers, which also switches off the convolution biases exactly like the reference's
+    `use_bias = (norm_layer == nn.InstanceNorm2d)` (irc:452-455, :590-593).  'batch' (nn.BatchNorm2d with affine parameters and
+    running statistics) is not built."""
     if norm_type == "instance":
         return nn.InstanceNorm2d
-    raise NotImplementedError(f"norm '{norm_type}' is not built: only the default 'instance' path is (SURVEY.md §8f-4)")
+    if norm_type == "none" or norm_type is None:
+        return _no_norm
+    if norm_type == "batch":
+        raise NotImplementedError("norm 'batch' is not built: 'instance' (default) and 'none' are (SURVEY.md §8f-4)")
+    raise NotImplementedError(f"Normalization type [{norm_type}] not supported")
+
+
+def _norm_tag(norm_layer) -> str:
+    if norm_layer is nn.InstanceNorm2d:
+        return "instance"
+    if norm_layer is _no_norm:
+        return "none"
+    raise NotImplementedError("norm_layer must come from get_norm_layer('instance' | 'none'); nn.BatchNorm2d is not built (SURVEY.md §8f-4)")
 
 
 def get_lr_lambda(cfg):
@@ -144,10 +170,13 @@ def init_net(net, init_type="normal", init_gain=0.02, device="cuda", initialize_
 class _ConvParams(nn.Module):
     """holds `weight` / `bias` of one convolution under the reference's key"""
 
-    def __init__(self, w: torch.Tensor, b: torch.Tensor):
+    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor]):
         super().__init__()
         self.weight = nn.Parameter(w)
-        self.bias = nn.Parameter(b)
+        if b is None:
+            self.register_parameter("bias", None)          # nn.Conv2d(bias=False): no `bias` key in the state_dict
+        else:
+            self.bias = nn.Parameter(b)
 
 
 class _Filt(nn.Module):
@@ -190,7 +219,8 @@ class _ArenaModule(nn.Module):
     def _rebind(self):
         for key, holder in self._named_holders():
             holder.weight = nn.Parameter(self.arena.view(key + ".weight"))
-            holder.bias = nn.Parameter(self.arena.view(key + ".bias"))
+            if key + ".bias" in self.arena.offset:
+                holder.bias = nn.Parameter(self.arena.view(key + ".bias"))
 
     def _acquire(self, key, make):
         pool = self._free.setdefault(key, [])
@@ -282,7 +312,7 @@ class _GenFn(torch.autograd.Function):
         grad = mod._grad_on and any(ctx.needs_input_grad)
         key = (B, H, W, grad)                  # inference engines carry no backward buffers
         eng = mod._acquire(key, lambda: E.GeneratorEngine(backend(), B, H, W, x.device, arena=mod.arena, training=grad,
-                                                          no_antialias_up=mod.no_antialias_up, no_antialias=mod.no_antialias))
+                                                          no_antialias_up=mod.no_antialias_up, no_antialias=mod.no_antialias, norm=mod.norm))
         eng.refresh_weights()
         out = eng.forward(x.contiguous().float()).clone()
         if grad:
@@ -303,8 +333,8 @@ class _GenFn(torch.autograd.Function):
 class _ResBlockHolder(nn.Module):
     def __init__(self, arena, b):
         super().__init__()
-        self.conv_block = nn.ModuleDict({str(j): _ConvParams(arena.view(f"resblocks.{b}.conv_block.{j}.weight"),
-                                                             arena.view(f"resblocks.{b}.conv_block.{j}.bias")) for j in (1, 5)})
+        bias = lambda j: arena.view(f"resblocks.{b}.conv_block.{j}.bias") if f"resblocks.{b}.conv_block.{j}.bias" in arena.offset else None
+        self.conv_block = nn.ModuleDict({str(j): _ConvParams(arena.view(f"resblocks.{b}.conv_block.{j}.weight"), bias(j)) for j in (1, 5)})
 
 
 class ResnetUNetGenerator(_ArenaModule):
@@ -312,17 +342,18 @@ class ResnetUNetGenerator(_ArenaModule):
                  padding_type="reflect", no_antialias=False, no_antialias_up=False):
         super().__init__()
         assert n_blocks >= 0                                          # irc:449
-        if (input_nc, output_nc, ngf) != (1, 3, 64) or norm_layer is not nn.InstanceNorm2d or use_dropout or padding_type != "reflect":
-            raise NotImplementedError("built: the generator graph 1->3, ngf 64, instance norm, reflect padding; anti-aliased (Downsample) or "
-                                      "- no_antialias=True - stride-2 down-sampling, UpsampleAA or - no_antialias_up=True - ConvTranspose2d "
-                                      "up-sampling; other norms / dropout are not (SURVEY.md §8f-4)")
+        self.norm = _norm_tag(norm_layer)
+        if (input_nc, output_nc, ngf) != (1, 3, 64) or use_dropout or padding_type != "reflect":
+            raise NotImplementedError("built: the generator graph 1->3, ngf 64, reflect padding, InstanceNorm or no normalisation; "
+                                      "anti-aliased (Downsample) or - no_antialias=True - stride-2 down-sampling, UpsampleAA or "
+                                      "- no_antialias_up=True - ConvTranspose2d up-sampling; dropout / BatchNorm are not (SURVEY.md §8f-4)")
         self.n_blocks = n_blocks
         self.no_antialias_up = bool(no_antialias_up)
         self.no_antialias = bool(no_antialias)
         dev = torch.device("cuda" if torch.cuda.is_available() else "cpu")
-        self._init_arena(E.generator_shapes(input_nc, output_nc, ngf, n_blocks, self.no_antialias_up), dev)
+        self._init_arena(E.generator_shapes(input_nc, output_nc, ngf, n_blocks, self.no_antialias_up, self.norm), dev)
         A = self.arena
-        hold = lambda k: _ConvParams(A.view(k + ".weight"), A.view(k + ".bias"))
+        hold = lambda k: _ConvParams(A.view(k + ".weight"), A.view(k + ".bias") if k + ".bias" in A.offset else None)
         self.inc = nn.ModuleDict({"1": hold("inc.1")})
         self.down1 = nn.ModuleDict({"0": hold("down1.0")})
         self.down1_down = None if self.no_antialias else _Filt(2 * ngf)          # irc:474: no blur module, no `filt` buffer
@@ -454,7 +485,7 @@ class _DiscFn(torch.autograd.Function):
     def forward(ctx, mod, x, *params):
         n, _, H, W = x.shape
         key = (n, H, W)
-        eng = mod._acquire(key, lambda: E.DiscriminatorEngine(backend(), n, H, W, x.device, arena=mod.arena))
+        eng = mod._acquire(key, lambda: E.DiscriminatorEngine(backend(), n, H, W, x.device, arena=mod.arena, norm=mod.norm))
         eng.refresh_weights()
         xf = x.float()
         out = eng.forward(xf[:, 0:1].contiguous(), xf[:, 1:4].contiguous()).clone()
@@ -479,12 +510,14 @@ class _DiscFn(torch.autograd.Function):
 class NLayerDiscriminator(_ArenaModule):
     def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=nn.InstanceNorm2d):
         super().__init__()
-        if (input_nc, ndf, n_layers) != (4, 64, 3) or norm_layer is not nn.InstanceNorm2d:
-            raise NotImplementedError("only NLayerDiscriminator(4, 64, 3, InstanceNorm2d) (irc:1590-1595) is built")
+        self.norm = _norm_tag(norm_layer)
+        if (input_nc, ndf, n_layers) != (4, 64, 3):
+            raise NotImplementedError("only NLayerDiscriminator(4, 64, 3, ...) (irc:1590-1595) is built")
         dev = torch.device("cuda" if torch.cuda.is_available() else "cpu")
-        self._init_arena(E.discriminator_shapes(input_nc, ndf), dev)
+        self._init_arena(E.discriminator_shapes(input_nc, ndf, self.norm), dev)
         A = self.arena
-        self.model = nn.ModuleDict({str(i): _ConvParams(A.view(f"model.{i}.weight"), A.view(f"model.{i}.bias")) for i in (0, 2, 5, 8, 11)})
+        self.model = nn.ModuleDict({str(i): _ConvParams(A.view(f"model.{i}.weight"), A.view(f"model.{i}.bias") if f"model.{i}.bias" in A.offset else None)
+                                    for i in (0, 2, 5, 8, 11)})
 
     def _named_holders(self):
         for i in ("0", "2", "5", "8", "11"):

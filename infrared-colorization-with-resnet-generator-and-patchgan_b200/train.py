@@ -206,7 +206,7 @@ def train_kaist(cfg: M.Config, train_loader=None, val_loader=None, use_graph: bo
     lam = dict(L1=cfg.lambda_L1, perc=cfg.lambda_perc, tv=cfg.lambda_tv, ssim=cfg.lambda_ssim, gan=cfg.lambda_gan)
     ts = TrainStep(M.backend(), cfg.batch_size, H, W, device, cfg.lr_G, cfg.lr_D, cfg.beta1, cfg.beta2, lam, world_size=world,
                    use_graph=use_graph and device.type == "cuda", arenas=(model.netG.arena, netD.arena, vgg.arena),
-                   no_antialias_up=cfg.no_antialias_up, no_antialias=cfg.no_antialias)
+                   no_antialias_up=cfg.no_antialias_up, no_antialias=cfg.no_antialias, norm=model.netG.norm)
     ts.refresh_weights()
     start_epoch = 1
     resume = getattr(cfg, "resume_from", None)          # not in the reference: full-state checkpoints (D + both Adam states + epoch)

@@ -59,13 +59,13 @@ class TrainStep:
 
     def __init__(self, be, B: int, H: int, W: int, device, lr_G=2e-4, lr_D=2e-4, beta1=0.5, beta2=0.999, lambdas=LAMBDAS,
                  world_size: int = 1, process_group=None, use_graph: bool = False, arenas=(None, None, None), no_antialias_up: bool = False,
-                 no_antialias: bool = False):
+                 no_antialias: bool = False, norm: str = "instance"):
         self.be, self.B, self.H, self.W, self.dev = be, B, H, W, device
         self.lam = dict(lambdas)
         self.world, self.pg = world_size, process_group
-        self.G = GeneratorEngine(be, B, H, W, device, arena=arenas[0], no_antialias_up=no_antialias_up, no_antialias=no_antialias)
-        self.D2 = DiscriminatorEngine(be, 2 * B, H, W, device, arena=arenas[1])
-        self.D1 = DiscriminatorEngine(be, B, H, W, device, arena=self.D2.arena, packer=self.D2.packer, layouts=self.D2.layouts)
+        self.G = GeneratorEngine(be, B, H, W, device, arena=arenas[0], no_antialias_up=no_antialias_up, no_antialias=no_antialias, norm=norm)
+        self.D2 = DiscriminatorEngine(be, 2 * B, H, W, device, arena=arenas[1], norm=norm)
+        self.D1 = DiscriminatorEngine(be, B, H, W, device, arena=self.D2.arena, packer=self.D2.packer, layouts=self.D2.layouts, norm=norm)
         self.V = VggEngine(be, 2 * B, B, H, W, device, arena=arenas[2])
         self.optG = AdamHyper(device, lr_G, beta1, beta2)
         self.optD = AdamHyper(device, lr_D, beta1, beta2)

@@ -36,8 +36,9 @@ Params = Dict[str, torch.Tensor]
 # deterministic weight / input recipes (shared by oracle, tests, bench)
 # ----------------------------------------------------------------------------
 
-def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9, no_antialias_up=False):
-    """Parameter shapes of the instance-norm generator, irc:457-531 (no_antialias_up: ConvTranspose2d up-sampling, irc:495-516)."""
+def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9, no_antialias_up=False, norm="instance"):
+    """Parameter shapes of the generator, irc:457-531 (no_antialias_up: ConvTranspose2d up-sampling, irc:495-516; norm='none':
+    get_norm_layer returns a lambda, so use_bias is False and only outc keeps its bias, irc:452-455)."""
     s = {
         "inc.1.weight": (ngf, input_nc, 7, 7), "inc.1.bias": (ngf,),
         "down1.0.weight": (2 * ngf, ngf, 3, 3), "down1.0.bias": (2 * ngf,),
@@ -53,16 +54,19 @@ def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9, no_antialias_u
     s["up1_conv.0.weight"] = (2 * ngf, 6 * ngf, 3, 3); s["up1_conv.0.bias"] = (2 * ngf,)
     s["up2_conv.0.weight"] = (ngf, 3 * ngf, 3, 3); s["up2_conv.0.bias"] = (ngf,)
     s["outc.1.weight"] = (output_nc, ngf, 7, 7); s["outc.1.bias"] = (output_nc,)
+    if norm != "instance":
+        s = {k: v for k, v in s.items() if not k.endswith(".bias") or k == "outc.1.bias"}
     return s
 
 
-def discriminator_shapes(input_nc=4, ndf=64):
-    """irc:598-630 with n_layers=3."""
+def discriminator_shapes(input_nc=4, ndf=64, norm="instance"):
+    """irc:598-630 with n_layers=3 (without InstanceNorm model.2/5/8 are built with bias=False, irc:590-593)."""
     chans = [(input_nc, ndf), (ndf, 2 * ndf), (2 * ndf, 4 * ndf), (4 * ndf, 8 * ndf), (8 * ndf, 1)]
     s = {}
     for idx, (ci, co) in zip((0, 2, 5, 8, 11), chans):
         s[f"model.{idx}.weight"] = (co, ci, 4, 4)
-        s[f"model.{idx}.bias"] = (co,)
+        if norm == "instance" or idx in (0, 11):
+            s[f"model.{idx}.bias"] = (co,)
     return s
 
 
@@ -199,12 +203,12 @@ def _conv(x, w, b, stride=1, pad=0, reflect=0):
     return F.conv2d(x, w, b, stride=stride, padding=pad)
 
 
-def resnet_block(p: Params, prefix: str, x: torch.Tensor) -> torch.Tensor:
-    """irc:417-418 with reflect padding and instance norm."""
-    h = _conv(x, p[prefix + "conv_block.1.weight"], p[prefix + "conv_block.1.bias"], reflect=1)
-    h = torch.relu(instance_norm(h))
-    h = _conv(h, p[prefix + "conv_block.5.weight"], p[prefix + "conv_block.5.bias"], reflect=1)
-    return x + instance_norm(h)
+def resnet_block(p: Params, prefix: str, x: torch.Tensor, nrm=instance_norm) -> torch.Tensor:
+    """irc:417-418 with reflect padding; nrm = instance norm (default) or the identity (norm='none': no biases either)."""
+    h = _conv(x, p[prefix + "conv_block.1.weight"], p.get(prefix + "conv_block.1.bias"), reflect=1)
+    h = torch.relu(nrm(h))
+    h = _conv(h, p[prefix + "conv_block.5.weight"], p.get(prefix + "conv_block.5.bias"), reflect=1)
+    return x + nrm(h)
 
 
 def generator_forward(p: Params, x: torch.Tensor, n_blocks: int = 9, taps: Optional[dict] = None, no_antialias: bool = False) -> torch.Tensor:
@@ -218,28 +222,30 @@ def generator_forward(p: Params, x: torch.Tensor, n_blocks: int = 9, taps: Optio
             taps[name] = t
         return t
 
-    x0 = tap("x0", torch.relu(instance_norm(_conv(x, p["inc.1.weight"], p["inc.1.bias"], reflect=3))))
+    # norm='none' (irc:158-163) shows in the parameters: no convolution bias in front of the (absent) normalisation
+    nrm = instance_norm if "inc.1.bias" in p else (lambda t: t)
+    x0 = tap("x0", torch.relu(nrm(_conv(x, p["inc.1.weight"], p.get("inc.1.bias"), reflect=3))))
     sd = 2 if no_antialias else 1
-    d1 = tap("down1", torch.relu(instance_norm(_conv(x0, p["down1.0.weight"], p["down1.0.bias"], stride=sd, pad=1))))
+    d1 = tap("down1", torch.relu(nrm(_conv(x0, p["down1.0.weight"], p.get("down1.0.bias"), stride=sd, pad=1))))
     x1 = tap("x1", d1 if no_antialias else blur_down(d1))
-    d2 = tap("down2", torch.relu(instance_norm(_conv(x1, p["down2.0.weight"], p["down2.0.bias"], stride=sd, pad=1))))
+    d2 = tap("down2", torch.relu(nrm(_conv(x1, p["down2.0.weight"], p.get("down2.0.bias"), stride=sd, pad=1))))
     x2 = tap("x2", d2 if no_antialias else blur_down(d2))
     h = x2
     for b in range(n_blocks):
-        h = tap(f"res{b}", resnet_block(p, f"resblocks.{b}.", h))
+        h = tap(f"res{b}", resnet_block(p, f"resblocks.{b}.", h, nrm))
     convT = "up1_up.weight" in p          # no_antialias_up=True: nn.ConvTranspose2d(C, C, 3, 2, 1, 1) instead of UpsampleAA (irc:495-499)
-    up = (lambda t, k: F.conv_transpose2d(t, p[k + ".weight"], p[k + ".bias"], stride=2, padding=1, output_padding=1)) if convT \
+    up = (lambda t, k: F.conv_transpose2d(t, p[k + ".weight"], p.get(k + ".bias"), stride=2, padding=1, output_padding=1)) if convT \
         else (lambda t, k: upsample_aa(t))
     y = tap("up1_up", up(h, "up1_up"))
     if y.shape[-2:] != x1.shape[-2:]:  # irc:555-556
         y = F.interpolate(y, size=x1.shape[-2:], mode="bilinear", align_corners=True)
     y = torch.cat([y, x1], dim=1)
-    y = tap("up1", torch.relu(instance_norm(_conv(y, p["up1_conv.0.weight"], p["up1_conv.0.bias"], pad=1))))
+    y = tap("up1", torch.relu(nrm(_conv(y, p["up1_conv.0.weight"], p.get("up1_conv.0.bias"), pad=1))))
     y = tap("up2_up", up(y, "up2_up"))
     if y.shape[-2:] != x0.shape[-2:]:  # irc:562-563
         y = F.interpolate(y, size=x0.shape[-2:], mode="bilinear", align_corners=True)
     y = torch.cat([y, x0], dim=1)
-    y = tap("up2", torch.relu(instance_norm(_conv(y, p["up2_conv.0.weight"], p["up2_conv.0.bias"], pad=1))))
+    y = tap("up2", torch.relu(nrm(_conv(y, p["up2_conv.0.weight"], p.get("up2_conv.0.bias"), pad=1))))
     return tap("out", torch.tanh(_conv(y, p["outc.1.weight"], p["outc.1.bias"], reflect=3)))
 
 
@@ -249,10 +255,11 @@ def discriminator_forward(p: Params, x: torch.Tensor, taps: Optional[dict] = Non
         if taps is not None:
             taps[name] = t
         return t
+    nrm = instance_norm if "model.2.bias" in p else (lambda t: t)      # norm='none': Identity and bias-free convolutions (irc:590-593)
     h = tap("d0", F.leaky_relu(_conv(x, p["model.0.weight"], p["model.0.bias"], stride=2, pad=1), 0.2))
-    h = tap("d2", F.leaky_relu(instance_norm(_conv(h, p["model.2.weight"], p["model.2.bias"], stride=2, pad=1)), 0.2))
-    h = tap("d5", F.leaky_relu(instance_norm(_conv(h, p["model.5.weight"], p["model.5.bias"], stride=2, pad=1)), 0.2))
-    h = tap("d8", F.leaky_relu(instance_norm(_conv(h, p["model.8.weight"], p["model.8.bias"], stride=1, pad=1)), 0.2))
+    h = tap("d2", F.leaky_relu(nrm(_conv(h, p["model.2.weight"], p.get("model.2.bias"), stride=2, pad=1)), 0.2))
+    h = tap("d5", F.leaky_relu(nrm(_conv(h, p["model.5.weight"], p.get("model.5.bias"), stride=2, pad=1)), 0.2))
+    h = tap("d8", F.leaky_relu(nrm(_conv(h, p["model.8.weight"], p.get("model.8.bias"), stride=1, pad=1)), 0.2))
     return tap("d11", _conv(h, p["model.11.weight"], p["model.11.bias"], stride=1, pad=1))
 
 

@@ -101,6 +101,44 @@ def main():
         gold["odd/grad_norm/" + k] = p_.grad.norm().item(); gold["odd/grad_sample/" + k] = MG.sample(p_.grad)
         gold["odd/grad_absmax/" + k] = p_.grad.abs().max().item()
     gold["odd/fake"] = fake.detach().numpy(); gold["odd/upstream"] = gv.numpy()
+    # norm='none' (irc:158-163, :452-455, :590-593): Identity layers and bias-free convolutions, generator and discriminator
+    pN = O.seeded_params(O.generator_shapes(norm="none"), 555, bias_std=0.02)
+    cfg = R.Config(); cfg.device = "cpu"; cfg.norm = "none"
+    m = R.IRColorizationModel(cfg)
+    keys = set(m.netG.state_dict().keys())
+    assert "inc.1.bias" not in keys and "resblocks.0.conv_block.1.bias" not in keys and "outc.1.bias" in keys and len(keys) == len(pN) + 4, len(keys)
+    missing = m.netG.load_state_dict(pN, strict=False)
+    assert not missing.unexpected_keys and all(k.endswith("filt") for k in missing.missing_keys), missing
+    fake = m(ir)
+    gv = torch.randn(fake.shape, generator=torch.Generator().manual_seed(13))
+    fake.backward(gv)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in pN.items()}
+    fo = O.generator_forward(leaves, ir)
+    MG.close(fo, fake.detach(), 2e-5, "norm none forward")
+    fo.backward(gv)
+    for k, p_ in m.netG.named_parameters():
+        rel = ((leaves[k].grad - p_.grad).norm() / p_.grad.norm()).item()
+        assert rel < 5e-3, ("nn", k, rel)
+        gold["nn/grad_norm/" + k] = p_.grad.norm().item(); gold["nn/grad_sample/" + k] = MG.sample(p_.grad); gold["nn/grad_absmax/" + k] = p_.grad.abs().max().item()
+    gold["nn/fake"] = fake.detach().numpy(); gold["nn/upstream"] = gv.numpy()
+    pDn = O.seeded_params(O.discriminator_shapes(norm="none"), 556, bias_std=0.02)
+    netD = R.NLayerDiscriminator(4, 64, 3, R.get_norm_layer("none"))
+    assert set(netD.state_dict().keys()) == set(pDn.keys())
+    netD.load_state_dict(pDn)
+    xd = torch.cat([ir, rgb], 1).clone().requires_grad_(True)
+    pred = netD(xd)
+    gp = torch.randn(pred.shape, generator=torch.Generator().manual_seed(14))
+    pred.backward(gp)
+    leavesD = {k: v.clone().requires_grad_(True) for k, v in pDn.items()}
+    xo = torch.cat([ir, rgb], 1).clone().requires_grad_(True)
+    po = O.discriminator_forward(leavesD, xo)
+    MG.close(po, pred.detach(), 2e-5, "norm none D forward")
+    po.backward(gp)
+    MG.close(xo.grad, xd.grad, 1e-4, "norm none D input grad")
+    for k, p_ in netD.named_parameters():
+        assert ((leavesD[k].grad - p_.grad).norm() / p_.grad.norm()).item() < 5e-3, k
+        gold["nnD/grad/" + k] = MG.sample(p_.grad, 512)
+    gold["nnD/pred"] = pred.detach().numpy(); gold["nnD/upstream"] = gp.numpy(); gold["nnD/dx"] = xd.grad.numpy()
     np.savez_compressed(os.path.join(MG.OUT, "ref_variants.npz"), **gold)
     print("wrote ref_variants.npz keys:", len(gold))
 

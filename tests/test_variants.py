@@ -42,13 +42,15 @@ def test_oracle_variant_forward_and_grads():
 
 
 # variant tag -> (fixture prefix, no_antialias_up, no_antialias, parameter seed of make_golden_variants.py)
-VARIANTS = {"up": ("", True, False, 4321), "na": ("na/", False, True, 777), "nab": ("nab/", True, True, 778), "odd": ("odd/", False, False, 999)}
+VARIANTS = {"up": ("", True, False, 4321), "na": ("na/", False, True, 777), "nab": ("nab/", True, True, 778), "odd": ("odd/", False, False, 999),
+            "nn": ("nn/", False, False, 555)}
 SIZES = {"odd": (29, 38)}          # default graph at a size that is not a multiple of 4: bilinear fix-up of irc:555-556, :562-563
+NORM = {"nn": "none"}              # norm='none' (irc:158-163): Identity layers, bias-free convolutions
 
 
 def _variant_params(tag):
     pre, up, na, seed = VARIANTS[tag]
-    return O.seeded_params(O.generator_shapes(no_antialias_up=up), seed, bias_std=0.02)
+    return O.seeded_params(O.generator_shapes(no_antialias_up=up, norm=NORM.get(tag, "instance")), seed, bias_std=0.02)
 
 
 @pytest.mark.parametrize("tag", ["na", "nab"])
@@ -70,7 +72,7 @@ def _check_engine(be, dev, tol_fwd, tol_dec, tol_enc, tag="up"):
     pG = _variant_params(tag)
     h, w = SIZES.get(tag, (H, W))
     ir, _ = O.synthetic_pair(B, h, w)
-    eng = E.GeneratorEngine(be, B, h, w, dev, no_antialias_up=up, no_antialias=na)
+    eng = E.GeneratorEngine(be, B, h, w, dev, no_antialias_up=up, no_antialias=na, norm=NORM.get(tag, "instance"))
     eng.arena.load(pG); eng.refresh_weights()
     fake = eng.forward(ir.to(dev))
     e = rel(fake, torch.from_numpy(GOLD[pre + "fake"]))
@@ -140,6 +142,83 @@ def test_plan_at_a_size_that_is_not_a_multiple_of_4_matches_reference():
         L.ACT_DTYPE = old
 
 
+def test_oracle_norm_none_forward():
+    ir, _ = O.synthetic_pair(B, H, W)
+    fake = O.generator_forward(_variant_params("nn"), ir)
+    assert np.abs(fake.numpy() - GOLD["nn/fake"]).max() < 5e-5
+
+
+def test_plan_without_normalisation_matches_reference():
+    """norm='none' in float32: no statistics, ReLU in the GEMM epilogues, plain copies into the next frame (ring / stencil /
+    residual), mask-only backward passes; every parameter gradient against the reference (no InstanceNorm -> no ReLU-mask noise
+    amplification, hence the tight encoder bound)"""
+    import irc_b200  # noqa: F401
+    from irc_b200 import layout as L
+    from ref_backend import RefBackend
+    old = L.ACT_DTYPE
+    L.ACT_DTYPE = torch.float32
+    try:
+        _check_engine(RefBackend(), "cpu", 1e-5, 1e-4, 1e-3, tag="nn")
+    finally:
+        L.ACT_DTYPE = old
+
+
+def _check_discriminator_none(be, dev, tol_fwd, tol_grad):
+    import irc_b200  # noqa: F401
+    from irc_b200 import engine as E
+    pD = O.seeded_params(O.discriminator_shapes(norm="none"), 556, bias_std=0.02)
+    ir, rgb = O.synthetic_pair(B, H, W)
+    eng = E.DiscriminatorEngine(be, B, H, W, dev, norm="none")
+    eng.arena.load(pD); eng.refresh_weights()
+    pred = eng.forward(ir.to(dev).contiguous(), rgb.to(dev).contiguous())
+    assert rel(pred, torch.from_numpy(GOLD["nnD/pred"])) < tol_fwd
+    eng.arena.grad.zero_()
+    dx = torch.zeros(B, 4, H, W, device=dev)
+    eng.backward(torch.from_numpy(GOLD["nnD/upstream"]).to(dev).contiguous(), True, dx, c_first=0, accumulate=False)
+    assert rel(dx, torch.from_numpy(GOLD["nnD/dx"])) < tol_grad
+    for k in pD:
+        got = sample(eng.arena.view(k, eng.arena.grad), 512); want = GOLD["nnD/grad/" + k]
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < tol_grad, k
+
+
+def test_discriminator_plan_without_normalisation_matches_reference():
+    import irc_b200  # noqa: F401
+    from irc_b200 import layout as L
+    from ref_backend import RefBackend
+    old = L.ACT_DTYPE
+    L.ACT_DTYPE = torch.float32
+    try:
+        _check_discriminator_none(RefBackend(), "cpu", 1e-5, 1e-4)
+    finally:
+        L.ACT_DTYPE = old
+
+
+def test_module_surface_without_normalisation():
+    """get_norm_layer('none') (irc:154-165): Identity factory; the generator / discriminator state_dicts lose the biases of the
+    convolutions that sit in front of a norm layer (use_bias False, irc:452-455, :590-593); 'batch' says that it is not built"""
+    import irc_b200 as R
+    from irc_b200 import layout as L, modules as M
+    from ref_backend import RefBackend
+    old, oldbe = L.ACT_DTYPE, M._BACKEND
+    L.ACT_DTYPE = torch.float32; M.set_backend(RefBackend())
+    try:
+        assert isinstance(R.get_norm_layer("none")(64), R.Identity) and isinstance(R.get_norm_layer(None)(8), R.Identity)
+        with pytest.raises(NotImplementedError):
+            R.get_norm_layer("batch")
+        cfg = R.Config(); cfg.device = "cpu"; cfg.norm = "none"
+        m = R.IRColorizationModel(cfg)
+        sd = m.netG.state_dict()
+        assert set(k for k in sd if not k.endswith("filt")) == set(O.generator_shapes(norm="none")) and "outc.1.bias" in sd
+        m.netG.load_state_dict(_variant_params("nn"), strict=False)
+        ir, _ = O.synthetic_pair(B, H, W)
+        with torch.no_grad():
+            assert rel(m(ir), torch.from_numpy(GOLD["nn/fake"])) < 1e-5
+        netD = R.NLayerDiscriminator(4, 64, 3, R.get_norm_layer("none"))
+        assert set(netD.state_dict()) == set(O.discriminator_shapes(norm="none"))
+    finally:
+        L.ACT_DTYPE = old; M.set_backend(oldbe)
+
+
 def test_module_surface_of_the_strided_variant():
     """no_antialias=True: the reference's state_dict has no down{1,2}_down.filt buffers (the modules are None, irc:474, :482)"""
     import irc_b200 as R
@@ -189,6 +268,16 @@ def test_gpu_generator_with_transposed_conv_upsampling():
     graph (tests/test_step_gpu.py bounds them at 0.35); the tight 1e-2 bound of the new layer is the C-ABI test below"""
     from irc_b200._native import CudaBackend
     _check_engine(CudaBackend(), "cuda", 3e-2, 0.25, 0.35)
+
+
+@pytest.mark.gpu
+@pytest.mark.gpu
+def test_gpu_networks_without_normalisation():
+    """norm='none' on the CUDA path (bf16): without InstanceNorm the forward error stays at the bf16 level and the gradients do not
+    see amplified ReLU-mask flips"""
+    from irc_b200._native import CudaBackend
+    _check_engine(CudaBackend(), "cuda", 2e-2, 0.15, 0.2, tag="nn")
+    _check_discriminator_none(CudaBackend(), "cuda", 2e-2, 0.12)      # four LeakyReLU masks evaluated on bf16 pre-activations
 
 
 @pytest.mark.gpu
