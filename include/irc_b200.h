@@ -56,7 +56,8 @@ typedef struct irc_conv_gemm_args {
     int addend_chan_off;
     int bn;                 /* tile width, 0 = auto */
     int mt;                 /* 128-row sub-tiles per tile sharing each weight stage: 1, 2, 0 = auto */
-    int reuse;              /* taps with consecutive shifts share one staged A tile: 0 off, 1 on, -1 auto */
+    int reuse;              /* taps with consecutive shifts: 1 = share one staged A box (tap runs), 2 = pack the three taps of a kernel
+                             * row along N with a shifted sum in the epilogue (64 outputs, 3 x 3), 0 = neither, -1 = auto */
     int epilogue_direct;    /* 1 = store rows straight from registers (default 0: swizzled smem staging + TMA stores) */
     /* InstanceNorm statistics from the epilogue (nn.InstanceNorm2d after the convolution, irc:161): per 128-row sub-tile and
      * output channel the (sum, sum of squares) of the stored bf16 values; needs row_img (ring rows are stored as zeros) and

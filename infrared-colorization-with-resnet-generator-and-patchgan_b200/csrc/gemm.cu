@@ -763,6 +763,193 @@ conv_gemm_runs_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------
+// conv_gemm with the kw taps of a kernel row packed along N ("packed taps", 64 output channels, 3 x 3 kernels)
+// ------------------------------------------------------------------------------------
+// In SS mode every tcgen05.mma re-reads its 4 KB A slab from shared memory, so an M128 x N64 x K16 MMA costs ~94 cycles
+// against a 32-cycle tensor floor (profiles/r3/ncu_narrow_v2_*): the N = 64 layers sit at half of the sustained peak no matter
+// how the operands reach shared memory.  Here the three taps of one kernel row share ONE unshifted A slab: their weight tiles
+// are stacked along N (3 x 64 = 192 accumulator columns: P_j[q] = sum_k A[q + mid][k] W_j[k], j = 0..2) and the epilogue adds
+// the three column groups shifted by one row each: out[q] = P_0[q - 1] + P_1[q] + P_2[q + 1].  Rows = TMEM lanes, so the shift is
+// a warp shuffle; the rows next to a lane-quarter boundary travel through a small shared-memory exchange buffer and tiles
+// overlap by two rows (126 outputs per 128-row tile).  A third of the A reads per FLOP and a third of the MMA instructions.
+constexpr int kPackRows = kBM - 2;      // outputs per tile
+
+struct PackParams {
+    int nruns;
+    int run_mid[IRC_MAX_TAPS / 3];     // row shift of the middle tap of each run
+    int run_tap[IRC_MAX_TAPS / 3][3];  // original tap indices (-> weight K offset), ascending shift
+};
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_pack_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p,
+                      const PackParams pk) {
+    irc::pdl_prologue();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int stage_a = kBM * 128;             // 128 rows x 64 channels
+    constexpr int tap_b = 64 * 128;                // one tap's weight tile: 64 output channels x 64 channels
+    constexpr int stage_bytes = stage_a + 3 * tap_b;
+    constexpr uint32_t acc_cols = 192;
+    const int S = p.stages;
+    uint64_t* bars = (uint64_t*)(smem + (size_t)S * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tfull = bars + 2 * S;
+    uint64_t* tempty = bars + 2 * S + 2;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
+    float* xbuf = reinterpret_cast<float*>((uint8_t*)bars + 256);              // [2][4 quarters][2 halves][32] boundary rows
+    uint8_t* stg = smem + (size_t)S * stage_bytes + 4096;                      // 2 x 16 KB staging tiles
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long total_tiles = (p.rows + kPackRows - 1) / kPackRows;
+    const int num_kb = pk.nruns * p.k_chunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmOut);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+        fence_barrier_init();
+    }
+    __shared__ __align__(16) float sbias[512];
+    if (p.bias) for (int i = threadIdx.x; i < p.n_out; i += blockDim.x) sbias[i] = p.bias[i];
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0; uint32_t phase = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const long long row0 = tile * kPackRows - 1;
+            for (int r = 0; r < pk.nruns; ++r) {
+                const int arow = (int)(row0 + pk.run_mid[r]);
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full[stage], stage_bytes);
+                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                        tma_load_2d(sa, &tmA, &full[stage], p.a_chan_off + kc * kBK, arow);
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                            tma_load_2d(sa + stage_a + j * tap_b, &tmB, &full[stage], (pk.run_tap[r][j] * p.k_chunks + kc) * kBK, 0);
+                    }
+                    __syncwarp();
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = umma_idesc_bf16(kBM, 192, 0, 0);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint64_t adesc = umma_desc_sw128(sa, 16);
+                const uint64_t bdesc = umma_desc_sw128(sa + stage_a, 16);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k)
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty[stage]);
+                }
+                __syncwarp();
+                if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) umma_commit(&tfull[acc]);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue: shifted sum of the three column groups, then the usual per-row math =====================
+        const int quarter = warp & 3;                 // TMEM lane quarter
+        const int half = (warp - 2) >> 2;             // 32 of the 64 output channels
+        const int r_in_tile = quarter * 32 + lane;
+        EpiCtx e;
+        e.slope_eff = p.act == 1 ? 0.f : (p.act == 2 ? p.slope : 1.f);
+        e.sbias = p.bias ? sbias : nullptr;
+        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t stg_iter = 0;
+        const bool store_thread = warp == 2 && lane == 0;
+        float* x_up = xbuf + (quarter * 2 + half) * 32;             // this warp's lane-31 P_0 row, read by quarter + 1
+        float* x_dn = xbuf + 256 + (quarter * 2 + half) * 32;       // this warp's lane-0 P_2 row, read by quarter - 1
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const long long row0 = tile * kPackRows - 1;
+            const long long row = row0 + r_in_tile;
+            const bool valid = r_in_tile >= 1 && r_in_tile <= kPackRows && row < p.rows;
+            int img = 0;
+            if (p.row_img) img = valid ? (int)p.row_img[row] : -1;      // issued before the accumulator wait: latency hidden
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(half * 32);
+            uint32_t r0[32], r1[32], r2[32];
+            tmem_ld32(taddr, r0);
+            tmem_ld32(taddr + 64, r1);
+            tmem_ld32(taddr + 128, r2);
+            tmem_ld_wait();
+            tc_fence_before();
+            if (lane == 31) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x_up[j] = __uint_as_float(r0[j]);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x_dn[j] = __uint_as_float(r2[j]);
+            }
+            uint8_t* buf = stg + (stg_iter & 1) * (kBM * 128);
+            if (store_thread) bulk_wait_group_read<1>();           // the staging tile of two tiles ago has left
+            named_bar_sync(1, 256);
+            if (lane == 0) mbar_arrive(&tempty[acc]);              // all eight warps hold their accumulator columns in registers
+            uint32_t c[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);
+                float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);
+                if (lane == 0 && quarter > 0) up = xbuf[((quarter - 1) * 2 + half) * 32 + j];
+                if (lane == 31 && quarter < 3) dn = xbuf[256 + ((quarter + 1) * 2 + half) * 32 + j];
+                c[j] = __float_as_uint(up + __uint_as_float(r1[j]) + dn);
+            }
+            const bool live = valid && img >= 0;
+            float v[32];
+            epi_math32(p, e, c, v, row, half * 32, live);
+            if (r_in_tile >= 1 && r_in_tile <= kPackRows) {
+                const int sr = r_in_tile - 1;                      // staging row: the 126 outputs of the tile start at row 0
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int chunk = (half * 4 + g) ^ (sr & 7);
+                    *reinterpret_cast<uint4*>(buf + sr * 128 + chunk * 16) =
+                        make_uint4(pack_bf16x2(v[g * 8], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                                   pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+                }
+            }
+            fence_proxy_async();
+            named_bar_sync(1, 256);
+            if (store_thread) {
+                tma_store_2d(&tmOut, buf, p.out_chan_off, (int)(row0 + 1));
+                bulk_commit_group();
+            }
+            ++stg_iter;
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    if (warp == 2 && lane == 0) bulk_wait_group<0>();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------
 // tn_gemm (weight gradients)
 // ------------------------------------------------------------------------------------
 struct TnParams {
@@ -1407,8 +1594,44 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     build_runs(a->taps, a->ntaps, rp);
     int max_len = 1;
     for (int r = 0; r < rp.nruns; ++r) if (rp.run_len[r] > max_len) max_len = rp.run_len[r];
+    // packed taps (reuse = 2, or auto): 64 output channels, every run exactly three taps long (3 x 3 kernels in either role)
+    bool pack_ok = a->n_out == 64 && bn == 64 && !tapsum && p.tma_store && !p.stats_part && rp.nruns * 3 == a->ntaps && rp.nruns <= IRC_MAX_TAPS / 3;
+    for (int r = 0; r < rp.nruns && pack_ok; ++r) pack_ok = rp.run_len[r] == 3;
+    // auto: only with >= 2 channel chunks per tap - with one, the 12 MMAs of a tile (~1900 cycles) finish before the epilogue has
+    // read its 128 x 192 fp32 accumulator columns out of TMEM (~1500 cycles at 64 B/clk) and done the shifted sum (measured: VGG
+    // conv1_2 forward 208 -> 269 us, while up2 192 -> 64 goes 272 -> 214 us and down1's data gradient 197 -> 142 us)
+    if (pack_ok && (a->reuse == 2 || (a->reuse < 0 && a->cin >= 128 && a->a_rows >= (long long)sms * 128))) {
+        PackParams pk;
+        pk.nruns = rp.nruns;
+        for (int r = 0; r < rp.nruns; ++r) {
+            pk.run_mid[r] = rp.run_first[r] + 1;
+            for (int j = 0; j < 3; ++j) pk.run_tap[r][j] = rp.run_tap[r][j];
+        }
+        CUtensorMap tmA1, tmB64, tmOut126;
+        rc = make_map(&tmA1, a->a, a->a_rows, a->a_ld, kBM);
+        if (rc) return rc;
+        rc = make_map(&tmB64, a->w, a->n_out, a->ntaps * a->cin, 64);
+        if (rc) return rc;
+        rc = make_map(&tmOut126, a->out, a->a_rows, (int)a->out_ld, kPackRows);
+        if (rc) return rc;
+        ConvParams q = p; q.mt = 1; q.nbuf = 2; q.nstg = 2;
+        const int sbytes = kBM * 128 + 3 * 64 * 128;
+        int st = (kMaxSmem - kStatic - 1024 - 4096 - 2 * kBM * 128) / sbytes;
+        if (st > 6) st = 6;
+        q.stages = st;
+        const size_t smem2 = (size_t)st * sbytes + 4096 + 2 * kBM * 128 + 1024;
+        static bool attr_pack = false;
+        if (!attr_pack) {
+            if (cudaFuncSetAttribute(conv_gemm_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 2048) != cudaSuccess)
+                return irc_check_launch("cudaFuncSetAttribute(conv_gemm_pack)");
+            attr_pack = true;
+        }
+        const long long tiles_p = (a->a_rows + kPackRows - 1) / kPackRows;
+        irc::launch<1>(conv_gemm_pack_kernel, (int)(tiles_p < sms ? tiles_p : sms), kConvThreads, smem2, (cudaStream_t)stream, tmOut126, tmA1, tmB64, q, pk);
+        return irc_check_launch("irc_conv_gemm(packed taps)");
+    }
     const bool runs_auto = max_len > 1 && !pair_auto && bn <= 128 && a->a_rows >= (long long)sms * 128;
-    if (max_len > 1 && !tapsum && (a->reuse > 0 || (a->reuse < 0 && runs_auto))) {
+    if (max_len > 1 && !tapsum && (a->reuse == 1 || a->reuse == 3 || (a->reuse < 0 && runs_auto))) {
         rp.a_stage_bytes = (kBM * mt + 8) * 128;
         rp.base_off_mode = a->reuse == 3 ? 1 : 0;      // 3 = the (wrong) base-offset encoding, kept for the experiment script
         const int stage_b = bn * 128;

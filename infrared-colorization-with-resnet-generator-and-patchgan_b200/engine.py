@@ -99,7 +99,10 @@ class ConvOp:
             # norm='none' (irc:158-163): no statistics, the activation is applied by the GEMM epilogue instead (kw carries it)
             self.fwd(a, a_chan_off, out, **kw)
             return
-        if self.lay.T * self.lay.K >= self.be.stats_epilogue_min_k and rows_per_img >= 128 and self.lay.N % 64 == 0 and row_img is not None:
+        # a 64-channel 3 x 3 layer with >= 128 input channels runs on the packed-taps GEMM (a third of the MMA instructions), which
+        # has no statistics epilogue: the separate pass over its narrow output costs less than the packing saves (up2: -45 us)
+        packed = self.lay.N == 64 and self.lay.T == 9 and self.lay.K >= 128 and getattr(self.be, "conv_reuse", 0) in (-1, 2)
+        if not packed and self.lay.T * self.lay.K >= self.be.stats_epilogue_min_k and rows_per_img >= 128 and self.lay.N % 64 == 0 and row_img is not None:
             self.fwd(a, a_chan_off, out, row_img=row_img, in_stats=(stats, n_img, rows_per_img), **kw)
         else:
             self.fwd(a, a_chan_off, out, **kw)

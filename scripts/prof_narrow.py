@@ -42,3 +42,4 @@ else:
         for reuse in (0, 1):
             for mt in (1, 2, 4):
                 run(reuse, mt, epi)
+        run(2, 0, epi)          # packed taps

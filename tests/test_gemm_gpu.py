@@ -29,11 +29,17 @@ def _conv_ref(A, taps, W, cin, a_off):
     (150 * 128 + 5, 64, 0, 64, [-1, 0, 1], 192, False),
     (2500, 512, 0, 512, [0, 1, 2, 3], 512, False),
     (148 * 256 * 2 + 77, 64, 0, 64, [-1, 0, 1], 128, False),
+    (148 * 126 * 2 + 50, 64, 0, 64, [-259, -258, -257, -1, 0, 1, 257, 258, 259], 64, False),       # packed-taps shapes (64 outputs, 3 x 3)
+    (5000, 256, 64, 192, [67, 66, 65, 1, 0, -1, -65, -66, -67], 64, False),                        # ... data-gradient tap order, channel offset
+    (126 * 3, 64, 0, 64, [-1, 0, 1], 64, False),                                                   # ... rows == a whole number of 126-row tiles
 ])
 @pytest.mark.parametrize("mt", [1, 2, 4])
-@pytest.mark.parametrize("reuse", [0, 1])
+@pytest.mark.parametrize("reuse", [0, 1, 2])
 def test_conv_gemm(rows, ld, a_off, cin, taps, n_out, fp32, mt, reuse):
-    """reuse = 1: the tap-run kernel (one staged A box per kernel row of taps, shifted descriptors) wherever taps form runs"""
+    """reuse = 1: the tap-run kernel (one staged A box per kernel row of taps, shifted descriptors) wherever taps form runs;
+    reuse = 2: packed taps (the three taps of a kernel row stacked along N, shifted sum in the epilogue) where eligible"""
+    if reuse == 2 and mt != 1:
+        pytest.skip("the packed-taps kernel has no M sub-tiling")
     import irc_b200
     from irc_b200 import _native as nat
     nat.arch_check()
@@ -71,7 +77,7 @@ def test_conv_gemm_epilogue():
     img = (torch.arange(rows, device="cuda") // 500).short()
     img[::7] = -1
     addend = torch.randn(rows, 128, device="cuda", generator=g).bfloat16()
-    for mode, reuse in [(m, r) for m in ("bias_lrelu_rows", "mask", "addend") for r in (0, 1)]:
+    for mode, reuse in [(m, r) for m in ("bias_lrelu_rows", "mask", "addend") for r in (0, 1, 2)]:
         out = torch.full((rows, n_out), float("nan"), device="cuda", dtype=torch.bfloat16)
         a = nat.ConvGemmArgs()
         a.reuse = reuse
