@@ -29,6 +29,10 @@ int irc_num_sms() {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
+        // IRC_SM_LIMIT: persistent grids use at most this many SMs (leaves room for NCCL's CTAs next to the 1-CTA-per-SM GEMMs when
+        // gradient all-reduces overlap the backward pass)
+        const char* e = getenv("IRC_SM_LIMIT");
+        if (e && atoi(e) > 0 && atoi(e) < sms) sms = atoi(e);
     }
     return sms;
 }
