@@ -188,6 +188,18 @@ int irc_in_bwd_fused(const irc_in_bwd_args* args, int fold_pad, void* stream);
  * C in {64, 128, 256}; args->work must hold 4 * groups * ctas_per_group * C floats + 512 (zero-initialised once). */
 int irc_in_bwd_l2(const irc_in_bwd_args* args, int groups, void* stream);
 
+/* nn.BatchNorm2d (get_norm_layer('batch'), irc:158-159) on the same kernels.  irc_bn_finalize turns the per-image (sum, sum of
+ * squares) of irc_in_stats / the conv epilogue into effective moments eff[n][c] = (mean_eff, rs_eff) with
+ * gamma * (x - mean_B) * rstd_B + beta == (x - mean_eff) * rs_eff - batch statistics over groups of `group` consecutive images
+ * (one group per forward call of the reference), or the running statistics when training == 0 - and updates running_mean /
+ * running_var (momentum, unbiased variance) `updates` times.  Pass eff as `stats` with eps < 0 to irc_gather,
+ * irc_in_bwd_reduce and irc_in_bwd_apply (cnt = group * H * W).  irc_bn_bwd_fix goes between the reduce and the apply pass: it
+ * sums the per-image partials of bsum over each group, writes the gradients of gamma and beta, and replaces bsum by the pair the
+ * apply pass needs for the batch-norm input gradient. */
+int irc_bn_finalize(const float* stats, int n_img, int group, int C, float cnt_per_img, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float momentum, float eps, int training, int updates, float* eff, void* stream);
+int irc_bn_bwd_fix(float* bsum, int n_img, int group, int C, const float* gamma, const float* beta, float* dgamma, float* dbeta, int accumulate, void* stream);
+
 /* Backward of nn.ReflectionPad2d(p) in place on a frame holding the gradient w.r.t. the padded tensor: interior pixels
  * within p of the border receive the ring pixels that mirror onto them; the ring is cleared. */
 int irc_fold_inplace(void* g, long long ld, int chan_off, int C, int n_img, int H, int W, int p, void* stream);

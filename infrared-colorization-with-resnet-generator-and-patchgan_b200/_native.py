@@ -18,7 +18,7 @@ MAX_TAPS = 64
 
 EXPORTS = [
     "irc_version", "irc_arch_check", "irc_last_error", "irc_conv_gemm", "irc_conv_stats_workspace_floats", "irc_conv_stats_finalize", "irc_tn_gemm", "irc_tn_gemm_ctas", "irc_row_index",
-    "irc_in_stats", "irc_gather", "irc_in_apply_fused", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_in_bwd_fused", "irc_in_bwd_l2", "irc_maxpool2", "irc_maxpool2_bwd",
+    "irc_in_stats", "irc_gather", "irc_in_apply_fused", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_in_bwd_fused", "irc_in_bwd_l2", "irc_bn_finalize", "irc_bn_bwd_fix", "irc_maxpool2", "irc_maxpool2_bwd",
     "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_smallk_conv_fwd", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
     "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics", "irc_ssim_metric",
     "irc_adam", "irc_accumulate", "irc_gather_f32", "irc_convT2d_fwd", "irc_pack_bf16", "irc_gather_sum", "irc_gather_sum_multi", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
@@ -461,11 +461,31 @@ class CudaBackend:
         g.work = self.work.data_ptr(); g.work_floats = self.work.numel()
         return g
 
+    def bn_finalize(self, stats, n_img, group, C_, cnt_per_img, gamma, beta, running_mean, running_var, eff, momentum=0.1, eps=1e-5, training=True,
+                    updates=1):
+        """nn.BatchNorm2d on the InstanceNorm kernels: per-image sums -> effective moments eff [n_img, C, 2] (see irc_bn_finalize)"""
+        assert eff.shape == (n_img, C_, 2) and eff.dtype == torch.float32 and gamma.numel() == C_ and running_mean.numel() == C_
+        check(self.L.irc_bn_finalize(_p(stats), n_img, group, C_, C.c_float(cnt_per_img), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                                     C.c_float(momentum), C.c_float(eps), int(bool(training)), int(updates), _p(eff), _stream()))
+        self.launches += 1
+
     def in_bwd(self, z: View, g1: View, dz: View, C_, n_img, H, W, stats=None, cnt=0.0, eps=1e-5, act=0, slope=0.0,
-               tables: Tables = IDENTITY, g2=None, bsum=None, fold_pad=0):
+               tables: Tables = IDENTITY, g2=None, bsum=None, fold_pad=0, bn=None):
         """reduce (when normalised) + apply.  fold_pad > 0: g1 is the view of a frame holding the gradient w.r.t. the
-        reflection-padded map (ring included); the fold happens inside (fused kernel) or as a separate in-place pass."""
+        reflection-padded map (ring included); the fold happens inside (fused kernel) or as a separate in-place pass.
+        bn = dict(group, gamma, beta, dgamma, dbeta, accumulate): BatchNorm backward - `stats` holds the effective moments of
+        bn_finalize (eps < 0), the two passes run separately with irc_bn_bwd_fix between them."""
         g = self._bwd_args(z, g1, g2, dz, C_, n_img, H, W, stats, cnt, eps, act, slope, tables, bsum)
+        if bn is not None:
+            assert stats is not None and eps < 0 and bsum is not None
+            if fold_pad:
+                self.fold_inplace(g1.t, g1.chan_off, C_, n_img, H, W, fold_pad)
+            check(self.L.irc_in_bwd_reduce(C.byref(g), _stream()))
+            check(self.L.irc_bn_bwd_fix(_p(bsum), n_img, int(bn["group"]), C_, _p(bn["gamma"]), _p(bn["beta"]), _p(bn["dgamma"]), _p(bn["dbeta"]),
+                                        int(bool(bn.get("accumulate", False))), _stream()))
+            check(self.L.irc_in_bwd_apply(C.byref(g), _stream()))
+            self.launches += 3
+            return
         fused = (self.fused_in_bwd and stats is not None and g2 is None and tables.ty_idx is None and tables.tx_idx is None
                  and C_ % 32 == 0 and H * W <= 4096 and not (z.s2d_c or g1.s2d_c or dz.s2d_c))
         if fused:

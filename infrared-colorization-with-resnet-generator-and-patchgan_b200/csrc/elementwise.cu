@@ -45,8 +45,18 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
     return i;
 }
 // mean / rstd of 8 channels from the (sum, sum of squares) pairs
+// eps < 0: `stats` already holds (mean, 1/std) pairs - the effective moments irc_bn_finalize builds for nn.BatchNorm2d (batch
+// statistics and the affine parameters folded into one subtract-and-scale), so every normalise / backward kernel serves both norms
 __device__ __forceinline__ void moments8(const float* stats, int n, int C, int c, float inv_cnt, float eps, float (&mu)[8], float (&rs)[8]) {
     const float4* sp = reinterpret_cast<const float4*>(stats + ((long long)n * C + c) * 2);
+    if (eps < 0.f) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float4 s = __ldg(sp + g);
+            mu[g * 2] = s.x; rs[g * 2] = s.y; mu[g * 2 + 1] = s.z; rs[g * 2 + 1] = s.w;
+        }
+        return;
+    }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         const float4 s = __ldg(sp + g);
@@ -1696,6 +1706,64 @@ void reduce_shape(int C, int H, int W, int n_img, long long work_floats, int& th
     smem = (size_t)L * C8 * 16 * sizeof(float);
 }
 
+// ---------------------------------------------------------------------------------
+// nn.BatchNorm2d (norm='batch', irc:158-159) on top of the InstanceNorm kernels
+// ---------------------------------------------------------------------------------
+// Forward: y = gamma * (x - mean_B) * rstd_B + beta = (x - mean_eff) * rs_eff with rs_eff = gamma * rstd_B and
+// mean_eff = mean_B - beta / rs_eff, the same for every image of a batch-statistics group.  One thread per channel turns the
+// per-image (sum, sum of squares) into those effective moments, and updates the running statistics as PyTorch does
+// (momentum, unbiased variance), `updates` times (the reference runs the generator twice per iteration on the same batch).
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int n_img, int group, int C, float cnt_per_img, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean, float* running_var, float momentum, float eps, int training,
+                                   int updates, float* __restrict__ eff) {
+    irc::pdl_prologue();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float M = (float)group * cnt_per_img;
+    float rm = running_mean[c], rv = running_var[c];
+    for (int g0 = 0; g0 < n_img; g0 += group) {
+        float mean, var;
+        if (training) {
+            float s1 = 0.f, s2 = 0.f;
+            for (int n = g0; n < g0 + group; ++n) { s1 += stats[((long long)n * C + c) * 2]; s2 += stats[((long long)n * C + c) * 2 + 1]; }
+            mean = s1 / M; var = fmaxf(s2 / M - mean * mean, 0.f);
+            for (int u = 0; u < updates; ++u) {
+                rm = (1.f - momentum) * rm + momentum * mean;
+                rv = (1.f - momentum) * rv + momentum * var * (M / fmaxf(M - 1.f, 1.f));
+            }
+        } else { mean = rm; var = rv; }
+        float sc = gamma[c] * rsqrtf(var + eps);
+        if (fabsf(sc) < 1e-20f) sc = sc < 0.f ? -1e-20f : 1e-20f;
+        const float me = mean - beta[c] / sc;
+        for (int n = g0; n < g0 + group; ++n) { eff[((long long)n * C + c) * 2] = me; eff[((long long)n * C + c) * 2 + 1] = sc; }
+    }
+    if (training) { running_mean[c] = rm; running_var[c] = rv; }
+}
+
+// Backward: the reduce pass leaves per image s1 = sum gd, s2 = sum gd * y (y = the affine output, gd = g * act'(y)).  With
+// S1, S2 their sums over the group: dbeta = S1, dgamma = (S2 - beta S1) / gamma, and
+// dx = rs_eff * (gd - S1/M - xhat * dgamma/M), xhat = (y - beta) / gamma  ==  rs_eff * (gd - A/M - y * B/M) with
+// B = (S2 - beta S1) / gamma^2, A = S1 - beta B: exactly the apply pass's formula, so it only needs (A, B) in place of (s1, s2).
+__global__ void bn_bwd_fix_kernel(float* __restrict__ bsum, int n_img, int group, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+    irc::pdl_prologue();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float ga = gamma[c];
+    if (fabsf(ga) < 1e-20f) ga = ga < 0.f ? -1e-20f : 1e-20f;
+    const float be = beta[c];
+    float dg = 0.f, db = 0.f;
+    for (int g0 = 0; g0 < n_img; g0 += group) {
+        float S1 = 0.f, S2 = 0.f;
+        for (int n = g0; n < g0 + group; ++n) { S1 += bsum[((long long)n * C + c) * 2]; S2 += bsum[((long long)n * C + c) * 2 + 1]; }
+        const float dgam = (S2 - be * S1) / ga;
+        const float B = dgam / ga, A = S1 - be * B;
+        for (int n = g0; n < g0 + group; ++n) { bsum[((long long)n * C + c) * 2] = A; bsum[((long long)n * C + c) * 2 + 1] = B; }
+        dg += dgam; db += S1;
+    }
+    if (accumulate) { dgamma[c] += dg; dbeta[c] += db; } else { dgamma[c] = dg; dbeta[c] = db; }
+}
+
 }  // namespace
 
 extern "C" int irc_row_index(short* row_img, int n_img, int hp, int wp, int y0, int y1, int x0, int x1, void* stream) {
@@ -2025,4 +2093,21 @@ extern "C" int irc_fold_inplace(void* g, long long ld, int chan_off, int C, int 
     const long long items = 2LL * p * W + (long long)(H - 2 * p) * 2 * p;
     irc::launch(fold_inplace_kernel, dim3((unsigned)((items + L - 1) / L), n_img), threads, 0, (cudaStream_t)stream, (bf16*)g, ld, chan_off, C, n_img, H, W, p);
     return irc_check_launch("irc_fold_inplace");
+}
+
+extern "C" int irc_bn_finalize(const float* stats, int n_img, int group, int C, float cnt_per_img, const float* gamma, const float* beta, float* running_mean,
+                               float* running_var, float momentum, float eps, int training, int updates, float* eff, void* stream) {
+    if (!gamma || !beta || !running_mean || !running_var || !eff || (training && !stats) || n_img <= 0 || group <= 0 || n_img % group || C <= 0)
+        return irc_set_error(IRC_ERR_BAD_ARG, "irc_bn_finalize: bad args (n_img must be a multiple of the statistics group)");
+    irc::launch(bn_finalize_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream, stats, n_img, group, C, cnt_per_img, gamma, beta, running_mean, running_var,
+                momentum, eps, training, updates < 1 ? 1 : updates, eff);
+    return irc_check_launch("irc_bn_finalize");
+}
+
+extern "C" int irc_bn_bwd_fix(float* bsum, int n_img, int group, int C, const float* gamma, const float* beta, float* dgamma, float* dbeta, int accumulate,
+                              void* stream) {
+    if (!bsum || !gamma || !beta || !dgamma || !dbeta || n_img <= 0 || group <= 0 || n_img % group || C <= 0)
+        return irc_set_error(IRC_ERR_BAD_ARG, "irc_bn_bwd_fix: bad args");
+    irc::launch(bn_bwd_fix_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream, bsum, n_img, group, C, gamma, beta, dgamma, dbeta, accumulate);
+    return irc_check_launch("irc_bn_bwd_fix");
 }

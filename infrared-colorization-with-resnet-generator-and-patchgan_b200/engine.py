@@ -42,7 +42,26 @@ def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9, no_antialias_u
     s["outc.1.weight"] = (output_nc, ngf, 7, 7); s["outc.1.bias"] = (output_nc,)
     if norm != "instance":
         s = {k: v for k, v in s.items() if not k.endswith(".bias") or k == "outc.1.bias"}
+    if norm == "batch":
+        for key, c in generator_bn_sites(ngf, n_blocks):      # nn.BatchNorm2d affine parameters (running statistics are buffers)
+            s[key + ".weight"] = (c,); s[key + ".bias"] = (c,)
     return s
+
+
+def generator_bn_sites(ngf=64, n_blocks=9) -> List[tuple]:
+    """(state_dict prefix, channels) of the norm layers of ResnetUNetGenerator in network order (irc:457-524, :388-412)"""
+    sites = [("inc.2", ngf), ("down1.1", 2 * ngf), ("down2.1", 4 * ngf)]
+    for b in range(n_blocks):
+        sites += [(f"resblocks.{b}.conv_block.2", 4 * ngf), (f"resblocks.{b}.conv_block.6", 4 * ngf)]
+    return sites + [("up1_conv.1", 2 * ngf), ("up2_conv.1", ngf)]
+
+
+DISCRIMINATOR_BN_SITES = [("model.3", 128), ("model.6", 256), ("model.9", 512)]      # irc:611-624 (n_layers 3, ndf 64)
+
+
+def new_bn_state(sites, device) -> Dict[str, tuple]:
+    """running_mean = 0, running_var = 1 per norm site (nn.BatchNorm2d defaults)"""
+    return {k: (torch.zeros(c, device=device), torch.ones(c, device=device)) for k, c in sites}
 
 
 def discriminator_shapes(input_nc=4, ndf=64, norm="instance") -> Dict[str, tuple]:
@@ -53,6 +72,9 @@ def discriminator_shapes(input_nc=4, ndf=64, norm="instance") -> Dict[str, tuple
         s[f"model.{idx}.weight"] = (co, ci, 4, 4)
         if norm == "instance" or idx in (0, 11):
             s[f"model.{idx}.bias"] = (co,)
+    if norm == "batch":
+        for key, c in DISCRIMINATOR_BN_SITES:
+            s[key + ".weight"] = (c,); s[key + ".bias"] = (c,)
     return s
 
 
@@ -182,11 +204,14 @@ class TransposedUp:
 class GeneratorEngine:
     def __init__(self, be, B: int, H: int, W: int, device, ngf: int = 64, n_blocks: int = 9, training: bool = True,
                  arena: L.ParamArena = None, no_antialias_up: bool = False, no_antialias: bool = False, norm: str = "instance"):
-        if norm not in ("instance", "none"):
-            raise NotImplementedError(f"norm '{norm}': the generator engine builds nn.InstanceNorm2d (default) and Identity ('none'), irc:148-165")
-        if norm == "none" and no_antialias_up:
-            raise NotImplementedError("norm='none' together with no_antialias_up=True (bias-free transposed convolutions) is not built")
-        self.norm_on = norm == "instance"
+        if norm not in ("instance", "none", "batch"):
+            raise NotImplementedError(f"Normalization type [{norm}] not supported")          # irc:165
+        if norm != "instance" and no_antialias_up:
+            raise NotImplementedError("norm='none' / 'batch' together with no_antialias_up=True (bias-free transposed convolutions) is not built")
+        self.norm = norm
+        self.norm_on = norm != "none"            # statistics are needed (InstanceNorm2d or BatchNorm2d)
+        self.bn = norm == "batch"
+        self.bn_training, self.bn_updates = True, 1      # train()/eval() mode of the caller; forward calls the reference makes per iteration
         if min(H, W) < 8:
             raise ValueError("the generator needs at least 8 x 8 pixels (ReflectionPad2d(1) at a quarter of the resolution)")
         if no_antialias and (H % 4 or W % 4):
@@ -204,7 +229,7 @@ class GeneratorEngine:
         self.convT = bool(no_antialias_up)
         self.noaa = bool(no_antialias)          # stride-2 down-sampling convolutions instead of conv + blur (irc:468, :474, :482)
         self.arena = arena or L.ParamArena(generator_shapes(1, 3, ngf, n_blocks, no_antialias_up, norm), device)
-        if ("inc.1.bias" in self.arena.offset) != self.norm_on:
+        if ("inc.1.bias" in self.arena.offset) != (norm == "instance") or ("inc.2.weight" in self.arena.offset) != self.bn:
             raise ValueError("the parameter arena does not match norm=%r (convolution biases exist exactly with InstanceNorm, irc:452-455)" % norm)
         if self.convT and "up1_up.weight" not in self.arena.offset:
             raise ValueError("no_antialias_up=True needs an arena with the ConvTranspose2d parameters up{1,2}_up.{weight,bias}")
@@ -241,6 +266,14 @@ class GeneratorEngine:
         self.sta = [st(256) for _ in range(n_blocks)]
         self.stb = [st(256) for _ in range(n_blocks)]
         self.bsum = st(256)
+        if self.bn:
+            # nn.BatchNorm2d (irc:158-159): running statistics (the module surface swaps in its registered buffers), effective
+            # moments per site, and which statistics buffer belongs to which state_dict prefix
+            self.bn_state = new_bn_state(generator_bn_sites(ngf, n_blocks), device)
+            sts = [self.st0, self.st1, self.st2] + [s_ for b in range(n_blocks) for s_ in (self.sta[b], self.stb[b])] + [self.st3, self.st4]
+            self._bn_site = {id(s_): (k, c) for s_, (k, c) in zip(sts, generator_bn_sites(ngf, n_blocks))}
+            self.eff = {k: torch.zeros(B, c, 2, device=device) for k, c in generator_bn_sites(ngf, n_blocks)}
+            self._bn_done = set()
         # image index of every frame row (-1 = padding ring) for the convolutions that emit InstanceNorm statistics
         self.ri_full = torch.zeros(self.Z4.rows, device=device, dtype=torch.int16)
         self.ri_half = torch.zeros(self.Z3.rows, device=device, dtype=torch.int16)
@@ -295,9 +328,33 @@ class GeneratorEngine:
     def _st(self, st):
         return st if self.norm_on else None
 
+    def _bn_eff(self, st, cnt):
+        """BatchNorm: per-image sums -> effective moments of the whole batch (once per forward pass and site), running statistics"""
+        key, c = self._bn_site[id(st)]
+        if key not in self._bn_done:
+            A = self.arena
+            rm, rv = self.bn_state[key]
+            self.be.bn_finalize(st, self.B, self.B, c, float(cnt), A.view(key + ".weight"), A.view(key + ".bias"), rm, rv, self.eff[key],
+                                training=self.bn_training, updates=self.bn_updates)
+            self._bn_done.add(key)
+        return key, self.eff[key]
+
     def _na(self, st, cnt, act=ACT_RELU):
-        """keyword arguments of an apply pass: InstanceNorm + activation, or a plain copy when the map is already activated"""
+        """keyword arguments of an apply pass: normalise (InstanceNorm2d / BatchNorm2d) + activation, or a plain copy when there is
+        no norm layer and the map is already activated"""
+        if self.bn:
+            return dict(stats=self._bn_eff(st, cnt)[1], cnt=self.B * cnt, eps=-1.0, act=act)
         return dict(stats=st, cnt=cnt, eps=EPS, act=act) if self.norm_on else {}
+
+    def _nb(self, st, cnt, act=ACT_RELU):
+        """keyword arguments of a norm + activation backward pass"""
+        if self.bn:
+            key, _ = self._bn_site[id(st)]
+            A = self.arena
+            return dict(stats=self.eff[key], cnt=self.B * cnt, eps=-1.0, act=act,
+                        bn=dict(group=self.B, gamma=A.view(key + ".weight"), beta=A.view(key + ".bias"),
+                                dgamma=A.view(key + ".weight", A.grad), dbeta=A.view(key + ".bias", A.grad)))
+        return dict(stats=st if self.norm_on else None, cnt=cnt, eps=EPS, act=act)
 
     def _epi(self):
         return {} if self.norm_on else dict(act=ACT_RELU)
@@ -341,6 +398,8 @@ class GeneratorEngine:
         be, B, H, W = self.be, self.B, self.H, self.W
         H2, W2, H4, W4 = self.H2, self.W2, self.H4, self.W4
         assert ir.shape == (B, 1, H, W) and ir.dtype == torch.float32 and ir.is_contiguous()
+        if self.bn:
+            self._bn_done.clear()
         # inc: reflect-pad 3 + 7x7 conv over 49 of 64 operand slots, IN + ReLU into cat2[128:192)
         if getattr(be, "direct_smallk", False):
             # direct convolution from the fp32 image; the im2col operand is only written when the weight gradient will read it
@@ -402,15 +461,21 @@ class GeneratorEngine:
         for b in range(self.nb):
             c1, c2 = self.res[b]
             c1.fwd(self.X[b].t, 0, self.Za[b].t, **self._epi())
-            if self.norm_on:
+            if self.norm == "instance":
                 be.in_apply(self.Za[b].view(), self.Hh[b].view(), 256, B, H4, W4, 1, 1, self.sta[b], eps=EPS, act=ACT_RELU)
+            elif self.bn:
+                be.in_stats(self.Za[b].view(), 256, B, H4, W4, self.sta[b])
+                be.gather(self.Za[b].view(), self.Hh[b].view(), 256, B, H4, W4, 1, 1, **self._na(self.sta[b], n4))
             else:
                 be.gather(self.Za[b].view(), self.Hh[b].view(), 256, B, H4, W4, 1, 1)          # reflected ring around the activated map
             c2.fwd(self.Hh[b].t, 0, self.Zb[b].t)
             # the last block output feeds only the up-sampling: a transposed convolution wants a ZERO ring, not the reflected one
             halo = 0 if (self.convT and b == self.nb - 1) else 1
-            if self.norm_on:
+            if self.norm == "instance":
                 be.in_apply(self.Zb[b].view(), self.X[b + 1].view(), 256, B, H4, W4, 1, halo, self.stb[b], eps=EPS, act=ACT_NONE, res=self.X[b].view())
+            elif self.bn:
+                be.in_stats(self.Zb[b].view(), 256, B, H4, W4, self.stb[b])
+                be.gather(self.Zb[b].view(), self.X[b + 1].view(), 256, B, H4, W4, 1, halo, res=self.X[b].view(), **self._na(self.stb[b], n4, ACT_NONE))
             else:
                 be.gather(self.Zb[b].view(), self.X[b + 1].view(), 256, B, H4, W4, 1, halo, res=self.X[b].view())
         if self.convT:
@@ -454,7 +519,7 @@ class GeneratorEngine:
         self.outc.dgrad(self.E_out, self.G4.t)
         # up2_conv
         be.fold_inplace(self.G4.t, 0, 64, B, H, W, 3)             # ReflectionPad2d(3)^T on the border pixels only
-        be.in_bwd(self.Z4.view(), self.G4.view(), self.dZ4.view(), 64, B, H, W, stats=self._st(self.st4), cnt=H * W, eps=EPS, act=ACT_RELU, bsum=self.bsum)
+        be.in_bwd(self.Z4.view(), self.G4.view(), self.dZ4.view(), 64, B, H, W, **self._nb(self.st4, H * W, ACT_RELU), bsum=self.bsum)
         self.up2.wgrad(self.dZ4.t, self.cat2.t, 0, self.cat2.rows)
         self.up2.dgrad(self.dZ4.t, self.Gcat2.t)
         # up1_conv (through UpsampleAA^T, or the transposed convolution's data gradient)
@@ -464,7 +529,7 @@ class GeneratorEngine:
         else:
             be.gather(self.Gcat2.view(0), self.g3.view(), 128, B, H2, W2, 0, 0, tables=self.t_up2_T)
             g_up1 = self.g3
-        be.in_bwd(self.Z3.view(), g_up1.view(), self.dZ3.view(), 128, B, H2, W2, stats=self._st(self.st3), cnt=H2 * W2, eps=EPS, act=ACT_RELU,
+        be.in_bwd(self.Z3.view(), g_up1.view(), self.dZ3.view(), 128, B, H2, W2, **self._nb(self.st3, H2 * W2, ACT_RELU),
                   bsum=self.bsum)
         self.up1.wgrad(self.dZ3.t, self.cat1.t, 0, self.cat1.rows)
         self.up1.dgrad(self.dZ3.t, self.Gcat1.t)
@@ -479,13 +544,13 @@ class GeneratorEngine:
             c1, c2 = self.res[b]
             # `cur` (gradient w.r.t. the reflection-padded X[b+1]) still carries its ring: the fold is linear, so it is applied
             # where the gradient is consumed (here, on load) and once more when the stream leaves the blocks
-            be.in_bwd(self.Zb[b].view(), cur.view(), self.dZb.view(), 256, B, H4, W4, stats=self._st(self.stb[b]), cnt=n4, eps=EPS, act=ACT_NONE, bsum=self.bsum,
+            be.in_bwd(self.Zb[b].view(), cur.view(), self.dZb.view(), 256, B, H4, W4, **self._nb(self.stb[b], n4, ACT_NONE), bsum=self.bsum,
                       fold_pad=1)
             c2.wgrad(self.dZb.t, self.Hh[b].t, 0, self.dZb.rows)
             c2.dgrad(self.dZb.t, self.Gh.t)
             # ReflectionPad2d(1)^T of Gh is folded inside the backward pass (or by a separate in-place pass when the map is
             # too large for the single-pass cluster kernel)
-            be.in_bwd(self.Za[b].view(), self.Gh.view(), self.dZa.view(), 256, B, H4, W4, stats=self._st(self.sta[b]), cnt=n4, eps=EPS, act=ACT_RELU,
+            be.in_bwd(self.Za[b].view(), self.Gh.view(), self.dZa.view(), 256, B, H4, W4, **self._nb(self.sta[b], n4, ACT_RELU),
                       bsum=self.bsum, fold_pad=1)
             c1.wgrad(self.dZa.t, self.X[b].t, 0, self.dZa.rows)
             # data gradient of conv1 + the residual-stream gradient, ring included (unfolded: fold(a + b) = fold(a) + fold(b))
@@ -499,34 +564,34 @@ class GeneratorEngine:
         if self.noaa:
             # stride-2 encoder: x2 is the activated down2 output itself; the data gradients come back in space-to-depth order
             v1, v2 = self._vZ1s, self._vZ2s
-            be.in_bwd(v2(self.Z2s), cur.view(), v2(self.dZ2s), 256, B, H4, W4, stats=self._st(self.st2), cnt=H4 * W4, eps=EPS, act=ACT_RELU, bsum=self.bsum)
+            be.in_bwd(v2(self.Z2s), cur.view(), v2(self.dZ2s), 256, B, H4, W4, **self._nb(self.st2, H4 * W4, ACT_RELU), bsum=self.bsum)
             self.down2.wgrad(self.dZ2s, self.Sx1, 0, self.Sx1.shape[0])
             self.down2.dgrad(self.dZ2s, self.dSx1)
             # x1 feeds down2 and the up1 skip connection
-            be.in_bwd(v1(self.Z1s), self.Gcat1.view(256), v1(self.dZ1s), 128, B, H2, W2, stats=self._st(self.st1), cnt=H2 * W2, eps=EPS, act=ACT_RELU,
+            be.in_bwd(v1(self.Z1s), self.Gcat1.view(256), v1(self.dZ1s), 128, B, H2, W2, **self._nb(self.st1, H2 * W2, ACT_RELU),
                       g2=View(self.dSx1, 0, self.hb2, self.wb2, 1, 1, 128), bsum=self.bsum)
             self.down1.wgrad(self.dZ1s, self.Sx0, 0, self.Sx0.shape[0])
             self.down1.dgrad(self.dZ1s, self.dSx0)
             # inc: x0 feeds down1 and the up2 skip connection
-            be.in_bwd(self.Z0.view(), self.Gcat2.view(128), self.dZ0.view(), 64, B, H, W, stats=self._st(self.st0), cnt=H * W, eps=EPS, act=ACT_RELU,
+            be.in_bwd(self.Z0.view(), self.Gcat2.view(128), self.dZ0.view(), 64, B, H, W, **self._nb(self.st0, H * W, ACT_RELU),
                       g2=View(self.dSx0, 0, self.hb1, self.wb1, 1, 1, 64), bsum=self.bsum)
             self.inc.wgrad(self.dZ0.t, self.E_in, 0, self.dZ0.rows)
             be.flush_sums()
             return
         # down2 (through Downsample^T)
         be.gather(cur.view(), self.g2.view(), 256, B, H2, W2, 0, 0, tables=self.t_down2_T)
-        be.in_bwd(self.Z2.view(), self.g2.view(), self.dZ2.view(), 256, B, H2, W2, stats=self._st(self.st2), cnt=H2 * W2, eps=EPS, act=ACT_RELU,
+        be.in_bwd(self.Z2.view(), self.g2.view(), self.dZ2.view(), 256, B, H2, W2, **self._nb(self.st2, H2 * W2, ACT_RELU),
                   bsum=self.bsum)
         self.down2.wgrad(self.dZ2.t, self.cat1.t, 256, self.cat1.rows)
         self.down2.dgrad(self.dZ2.t, self.Gx1.t)
         # down1: x1 feeds down2 and the up1 skip connection
         be.gather(self.Gcat1.view(256), self.g1.view(), 128, B, H, W, 0, 0, tables=self.t_down1_T, src2=self.Gx1.view())
-        be.in_bwd(self.Z1.view(), self.g1.view(), self.dZ1.view(), 128, B, H, W, stats=self._st(self.st1), cnt=H * W, eps=EPS, act=ACT_RELU,
+        be.in_bwd(self.Z1.view(), self.g1.view(), self.dZ1.view(), 128, B, H, W, **self._nb(self.st1, H * W, ACT_RELU),
                   bsum=self.bsum)
         self.down1.wgrad(self.dZ1.t, self.cat2.t, 128, self.cat2.rows)
         self.down1.dgrad(self.dZ1.t, self.Gx0.t)
         # inc: x0 feeds down1 and the up2 skip connection
-        be.in_bwd(self.Z0.view(), self.Gcat2.view(128), self.dZ0.view(), 64, B, H, W, stats=self._st(self.st0), cnt=H * W, eps=EPS, act=ACT_RELU,
+        be.in_bwd(self.Z0.view(), self.Gcat2.view(128), self.dZ0.view(), 64, B, H, W, **self._nb(self.st0, H * W, ACT_RELU),
                   g2=self.Gx0.view(), bsum=self.bsum)
         self.inc.wgrad(self.dZ0.t, self.E_in, 0, self.dZ0.rows)
         be.flush_sums()
@@ -538,15 +603,18 @@ class GeneratorEngine:
 class DiscriminatorEngine:
     def __init__(self, be, n_img: int, H: int, W: int, device, arena: L.ParamArena = None, packer: L.Packer = None, layouts=None,
                  norm: str = "instance"):
-        if norm not in ("instance", "none"):
-            raise NotImplementedError(f"norm '{norm}': the discriminator engine builds nn.InstanceNorm2d (default) and Identity ('none'), irc:148-165")
-        self.norm_on = norm == "instance"
+        if norm not in ("instance", "none", "batch"):
+            raise NotImplementedError(f"Normalization type [{norm}] not supported")          # irc:165
+        self.norm = norm
+        self.norm_on = norm != "none"
+        self.bn = norm == "batch"
+        self.bn_training = True
         if H % 16 or W % 16 or H < 32 or W < 32:
             raise NotImplementedError("discriminator engine needs H, W multiples of 16 and >= 32 (70x70 PatchGAN receptive field)")
         self.be, self.n, self.H, self.W, self.dev = be, n_img, H, W, device
         own = packer is None
         self.arena = arena or L.ParamArena(discriminator_shapes(4, 64, norm), device)
-        if ("model.2.bias" in self.arena.offset) != self.norm_on:
+        if ("model.2.bias" in self.arena.offset) != (norm == "instance") or ("model.3.weight" in self.arena.offset) != self.bn:
             raise ValueError("the parameter arena does not match norm=%r (model.2/5/8 have biases exactly with InstanceNorm, irc:590-593)" % norm)
         self.packer = packer or L.Packer(self.arena)
         A, P = self.arena, self.packer
@@ -573,6 +641,12 @@ class DiscriminatorEngine:
         self.pred = torch.zeros(n, 1, self.Ho, self.Wo, device=device)
         st = lambda c: torch.zeros(n, c, 2, device=device)
         self.st2, self.st5, self.st8, self.bsum = st(128), st(256), st(512), st(512)
+        if self.bn:
+            # nn.BatchNorm2d (irc:158-159): batch statistics per forward CALL of the reference (real and fake halves are separate calls)
+            self.bn_state = new_bn_state(DISCRIMINATOR_BN_SITES, device)
+            self._bn_site = {id(s_): kc for s_, kc in zip((self.st2, self.st5, self.st8), DISCRIMINATOR_BN_SITES)}
+            self.eff = {k: torch.zeros(n, c, 2, device=device) for k, c in DISCRIMINATOR_BN_SITES}
+            self.group = n
         self.ri2 = torch.zeros(n * self.hb0 * self.wb0, device=device, dtype=torch.int16)      # live rows of the model.2 output grid
         be.row_index(self.ri2, n, self.hb0, self.wb0, 0, H2, 0, W2)
         # weights (shared between the 2B-image and B-image instances)
@@ -594,6 +668,7 @@ class DiscriminatorEngine:
             P.finish()
         # backward buffers
         self.dpred = torch.zeros_like(self.pred)
+        self._scratch = torch.zeros(2, 512, device=device)
         self.E11 = bf(self.X11.rows, 64)
         self.G11 = L.Frame(n, self.H8o, self.W8o, 1, 512, device)
         self.dZ8 = bf(self.X8.rows, 512)
@@ -607,6 +682,27 @@ class DiscriminatorEngine:
 
     def refresh_weights(self):
         self.packer.refresh(self.be)
+
+    def _na(self, st, cnt):
+        """keyword arguments of a normalise + LeakyReLU apply pass (InstanceNorm2d or BatchNorm2d)"""
+        if not self.bn:
+            return dict(stats=st, cnt=cnt, eps=EPS, act=ACT_LRELU, slope=0.2)
+        key, c = self._bn_site[id(st)]
+        A = self.arena
+        rm, rv = self.bn_state[key]
+        self.be.bn_finalize(st, self.n, self.group, c, float(cnt), A.view(key + ".weight"), A.view(key + ".bias"), rm, rv, self.eff[key],
+                            training=self.bn_training)
+        return dict(stats=self.eff[key], cnt=self.group * cnt, eps=-1.0, act=ACT_LRELU, slope=0.2)
+
+    def _nb(self, st, cnt, want_wgrad):
+        if not self.bn:
+            return dict(stats=st if self.norm_on else None, cnt=cnt, eps=EPS, act=ACT_LRELU, slope=0.2)
+        key, _ = self._bn_site[id(st)]
+        A = self.arena
+        # without want_wgrad (generator step) the parameter gradients land in a scratch row of bsum's sibling buffer
+        dg, db = (A.view(key + ".weight", A.grad), A.view(key + ".bias", A.grad)) if want_wgrad else (self._scratch[0, :st.shape[1]], self._scratch[1, :st.shape[1]])
+        return dict(stats=self.eff[key], cnt=self.group * cnt, eps=-1.0, act=ACT_LRELU, slope=0.2,
+                    bn=dict(group=self.group, gamma=A.view(key + ".weight"), beta=A.view(key + ".bias"), dgamma=dg, dbeta=db))
 
     def _vZ2(self, t):
         return View(t, 0, self.hb0, self.wb0, 0, 0)
@@ -652,15 +748,24 @@ class DiscriminatorEngine:
             self.c11.fwd(self.X11.t, 0, self.P11)
             be.tap_reduce(self.P11, self.shifts11, 1, n, self.Ho, self.Wo, self.X11.hp, self.X11.wp, 0, 0, self.c11.bias(), ACT_NONE, self.pred)
             return self.pred
+        if self.bn:
+            self.group = n1          # one set of batch statistics per forward call of the reference (irc:1642, :1643, :1659)
         self.c2.fwd_stats(self.S0v, 0, self.Z2, self.st2, self.ri2, n, self.hb0 * self.wb0, self._vZ2(self.Z2), 128, self.H2, self.W2)
-        be.gather(self._vZ2(self.Z2), View(self.S2, 0, self.hb2, self.wb2), 128, n, self.H2, self.W2, 1, 0, stats=self.st2,
-                  cnt=self.H2 * self.W2, eps=EPS, act=ACT_LRELU, slope=0.2, dst_s2d=1)
+        be.gather(self._vZ2(self.Z2), View(self.S2, 0, self.hb2, self.wb2), 128, n, self.H2, self.W2, 1, 0, dst_s2d=1, **self._na(self.st2, self.H2 * self.W2))
         # model.5
         self.c5.fwd(self.S2, 0, self.Z5)
-        be.in_apply(self._vZ5(self.Z5), self.X8.view(), 256, n, self.H3, self.W3, 1, 0, self.st5, eps=EPS, act=ACT_LRELU, slope=0.2)
+        if self.bn:
+            be.in_stats(self._vZ5(self.Z5), 256, n, self.H3, self.W3, self.st5)
+            be.gather(self._vZ5(self.Z5), self.X8.view(), 256, n, self.H3, self.W3, 1, 0, **self._na(self.st5, self.H3 * self.W3))
+        else:
+            be.in_apply(self._vZ5(self.Z5), self.X8.view(), 256, n, self.H3, self.W3, 1, 0, self.st5, eps=EPS, act=ACT_LRELU, slope=0.2)
         # model.8 (stride 1)
         self.c8.fwd(self.X8.t, 0, self.Z8)
-        be.in_apply(self._vZ8(self.Z8), self.X11.view(), 512, n, self.H8o, self.W8o, 1, 0, self.st8, eps=EPS, act=ACT_LRELU, slope=0.2)
+        if self.bn:
+            be.in_stats(self._vZ8(self.Z8), 512, n, self.H8o, self.W8o, self.st8)
+            be.gather(self._vZ8(self.Z8), self.X11.view(), 512, n, self.H8o, self.W8o, 1, 0, **self._na(self.st8, self.H8o * self.W8o))
+        else:
+            be.in_apply(self._vZ8(self.Z8), self.X11.view(), 512, n, self.H8o, self.W8o, 1, 0, self.st8, eps=EPS, act=ACT_LRELU, slope=0.2)
         # model.11: 512->1, per-tap partial products then the 16-tap shifted reduction
         self.c11.fwd(self.X11.t, 0, self.P11)
         be.tap_reduce(self.P11, self.shifts11, 1, n, self.Ho, self.Wo, self.X11.hp, self.X11.wp, 0, 0, self.c11.bias(), ACT_NONE, self.pred)
@@ -677,18 +782,18 @@ class DiscriminatorEngine:
         if want_wgrad:
             self.c11.wgrad(self.E11, self.X11.t, 0, self.X11.rows)
         self.c11.dgrad(self.E11, self.G11.t)
-        be.in_bwd(self._vZ8(self.Z8), self.G11.view(), self._vZ8(self.dZ8), 512, n, self.H8o, self.W8o, stats=self.st8 if self.norm_on else None,
-                  cnt=self.H8o * self.W8o, eps=EPS, act=ACT_LRELU, slope=0.2, bsum=self.bsum)
+        be.in_bwd(self._vZ8(self.Z8), self.G11.view(), self._vZ8(self.dZ8), 512, n, self.H8o, self.W8o, bsum=self.bsum,
+                  **self._nb(self.st8, self.H8o * self.W8o, want_wgrad))
         if want_wgrad:
             self.c8.wgrad(self.dZ8, self.X8.t, 0, self.X8.rows)
         self.c8.dgrad(self.dZ8, self.G8.t)
-        be.in_bwd(self._vZ5(self.Z5), self.G8.view(), self._vZ5(self.dZ5), 256, n, self.H3, self.W3, stats=self.st5 if self.norm_on else None,
-                  cnt=self.H3 * self.W3, eps=EPS, act=ACT_LRELU, slope=0.2, bsum=self.bsum)
+        be.in_bwd(self._vZ5(self.Z5), self.G8.view(), self._vZ5(self.dZ5), 256, n, self.H3, self.W3, bsum=self.bsum,
+                  **self._nb(self.st5, self.H3 * self.W3, want_wgrad))
         if want_wgrad:
             self.c5.wgrad(self.dZ5, self.S2, 0, self.S2.shape[0])
         self.c5.dgrad(self.dZ5, self.dS2)
         be.in_bwd(self._vZ2(self.Z2), View(self.dS2, 0, self.hb2, self.wb2, 1, 1, 128), self._vZ2(self.dZ2), 128, n, self.H2, self.W2,
-                  stats=self.st2 if self.norm_on else None, cnt=self.H2 * self.W2, eps=EPS, act=ACT_LRELU, slope=0.2, bsum=self.bsum)
+                  bsum=self.bsum, **self._nb(self.st2, self.H2 * self.W2, want_wgrad))
         if want_wgrad:
             self.c2.wgrad(self.dZ2, self.S0v, 0, self.S0v.shape[0])
         # data gradient of model.2 lands in space-to-depth order == the row order of model.0's output; the

@@ -105,14 +105,14 @@ def _no_norm(num_features):
 def get_norm_layer(norm_type="instance"):
     """irc:154-165.  The returned object is only used as a tag by the engines: nn.InstanceNorm2d (the default graph) or - 'none' /
     None - a factory of Identity layers, which also switches off the convolution biases exactly like the reference's
-    `use_bias = (norm_layer == nn.InstanceNorm2d)` (irc:452-455, :590-593).  'batch' (nn.BatchNorm2d with affine parameters and
-    running statistics) is not built."""
+    `use_bias = (norm_layer == nn.InstanceNorm2d)` (irc:452-455, :590-593); or nn.BatchNorm2d ('batch': affine parameters in the
+    arena, running statistics as buffers, batch statistics in train() mode and running statistics in eval() mode)."""
     if norm_type == "instance":
         return nn.InstanceNorm2d
     if norm_type == "none" or norm_type is None:
         return _no_norm
     if norm_type == "batch":
-        raise NotImplementedError("norm 'batch' is not built: 'instance' (default) and 'none' are (SURVEY.md §8f-4)")
+        return nn.BatchNorm2d
     raise NotImplementedError(f"Normalization type [{norm_type}] not supported")
 
 
@@ -121,7 +121,9 @@ def _norm_tag(norm_layer) -> str:
         return "instance"
     if norm_layer is _no_norm:
         return "none"
-    raise NotImplementedError("norm_layer must come from get_norm_layer('instance' | 'none'); nn.BatchNorm2d is not built (SURVEY.md §8f-4)")
+    if norm_layer is nn.BatchNorm2d:
+        return "batch"
+    raise NotImplementedError("norm_layer must come from get_norm_layer('instance' | 'batch' | 'none')")
 
 
 def get_lr_lambda(cfg):
@@ -149,8 +151,11 @@ def init_weights(net, init_type="normal", init_gain=0.02):
     if init_type != "normal":
         raise NotImplementedError("only init_type='normal' is used by the reference path")
     with torch.no_grad():
+        bn_weights = {id(mod.weight) for mod in net.modules() if isinstance(mod, _BNParams)}
         for name, p in net.named_parameters():
-            if name.endswith("weight"):
+            if id(p) in bn_weights:
+                p.normal_(1.0, init_gain)                     # irc:190-194: norm layers N(1, gain)
+            elif name.endswith("weight"):
                 p.normal_(0.0, init_gain)
             elif name.endswith("bias"):
                 p.zero_()
@@ -177,6 +182,18 @@ class _ConvParams(nn.Module):
             self.register_parameter("bias", None)          # nn.Conv2d(bias=False): no `bias` key in the state_dict
         else:
             self.bias = nn.Parameter(b)
+
+
+class _BNParams(nn.Module):
+    """affine parameters (arena views) and running-statistics buffers of one nn.BatchNorm2d under the reference's keys"""
+
+    def __init__(self, w: torch.Tensor, b: torch.Tensor):
+        super().__init__()
+        self.weight = nn.Parameter(w)
+        self.bias = nn.Parameter(b)
+        self.register_buffer("running_mean", torch.zeros(w.numel(), device=w.device))
+        self.register_buffer("running_var", torch.ones(w.numel(), device=w.device))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long, device=w.device))
 
 
 class _Filt(nn.Module):
@@ -221,6 +238,15 @@ class _ArenaModule(nn.Module):
             holder.weight = nn.Parameter(self.arena.view(key + ".weight"))
             if key + ".bias" in self.arena.offset:
                 holder.bias = nn.Parameter(self.arena.view(key + ".bias"))
+
+    def _bn_state(self):
+        """{state_dict prefix: (running_mean, running_var)} of the BatchNorm holders, handed to the engine for each forward pass"""
+        return {name: (h.running_mean, h.running_var) for name, h in self.named_modules() if isinstance(h, _BNParams)}
+
+    def _bn_tick(self, calls: int = 1):
+        for h in self.modules():
+            if isinstance(h, _BNParams):
+                h.num_batches_tracked += calls
 
     def _acquire(self, key, make):
         pool = self._free.setdefault(key, [])
@@ -314,6 +340,11 @@ class _GenFn(torch.autograd.Function):
         eng = mod._acquire(key, lambda: E.GeneratorEngine(backend(), B, H, W, x.device, arena=mod.arena, training=grad,
                                                           no_antialias_up=mod.no_antialias_up, no_antialias=mod.no_antialias, norm=mod.norm))
         eng.refresh_weights()
+        if mod.norm == "batch":
+            # train(): batch statistics + running-statistics update (irc:1622); eval(): running statistics (irc:1357, :1527)
+            eng.bn_state, eng.bn_training, eng.bn_updates = mod._bn_state(), mod.training, 1
+            if mod.training:
+                mod._bn_tick()
         out = eng.forward(x.contiguous().float()).clone()
         if grad:
             ctx.mod, ctx.eng, ctx.key = mod, eng, key
@@ -335,6 +366,9 @@ class _ResBlockHolder(nn.Module):
         super().__init__()
         bias = lambda j: arena.view(f"resblocks.{b}.conv_block.{j}.bias") if f"resblocks.{b}.conv_block.{j}.bias" in arena.offset else None
         self.conv_block = nn.ModuleDict({str(j): _ConvParams(arena.view(f"resblocks.{b}.conv_block.{j}.weight"), bias(j)) for j in (1, 5)})
+        for j in (2, 6):                       # nn.BatchNorm2d behind each convolution (norm='batch')
+            if f"resblocks.{b}.conv_block.{j}.weight" in arena.offset:
+                self.conv_block[str(j)] = _BNParams(arena.view(f"resblocks.{b}.conv_block.{j}.weight"), arena.view(f"resblocks.{b}.conv_block.{j}.bias"))
 
 
 class ResnetUNetGenerator(_ArenaModule):
@@ -354,22 +388,23 @@ class ResnetUNetGenerator(_ArenaModule):
         self._init_arena(E.generator_shapes(input_nc, output_nc, ngf, n_blocks, self.no_antialias_up, self.norm), dev)
         A = self.arena
         hold = lambda k: _ConvParams(A.view(k + ".weight"), A.view(k + ".bias") if k + ".bias" in A.offset else None)
-        self.inc = nn.ModuleDict({"1": hold("inc.1")})
-        self.down1 = nn.ModuleDict({"0": hold("down1.0")})
+        bn = lambda k: {k.rsplit(".", 1)[1]: _BNParams(A.view(k + ".weight"), A.view(k + ".bias"))} if self.norm == "batch" else {}
+        self.inc = nn.ModuleDict({"1": hold("inc.1"), **bn("inc.2")})
+        self.down1 = nn.ModuleDict({"0": hold("down1.0"), **bn("down1.1")})
         self.down1_down = None if self.no_antialias else _Filt(2 * ngf)          # irc:474: no blur module, no `filt` buffer
-        self.down2 = nn.ModuleDict({"0": hold("down2.0")})
+        self.down2 = nn.ModuleDict({"0": hold("down2.0"), **bn("down2.1")})
         self.down2_down = None if self.no_antialias else _Filt(4 * ngf)          # irc:482
         self.resblocks = nn.ModuleList([_ResBlockHolder(A, b) for b in range(n_blocks)])
         # UpsampleAA carries only its `filt` buffer; nn.ConvTranspose2d (irc:495-499, :512-516) carries weight (Cin, Cout, 3, 3) + bias
         self.up1_up = hold("up1_up") if self.no_antialias_up else _Filt(4 * ngf)
-        self.up1_conv = nn.ModuleDict({"0": hold("up1_conv.0")})
+        self.up1_conv = nn.ModuleDict({"0": hold("up1_conv.0"), **bn("up1_conv.1")})
         self.up2_up = hold("up2_up") if self.no_antialias_up else _Filt(2 * ngf)
-        self.up2_conv = nn.ModuleDict({"0": hold("up2_conv.0")})
+        self.up2_conv = nn.ModuleDict({"0": hold("up2_conv.0"), **bn("up2_conv.1")})
         self.outc = nn.ModuleDict({"1": hold("outc.1")})
 
     def _named_holders(self):
         for name, m in self.named_modules():
-            if isinstance(m, _ConvParams):
+            if isinstance(m, (_ConvParams, _BNParams)):
                 yield name, m
 
     def forward(self, x, layers=None, encode_only=False):
@@ -487,6 +522,10 @@ class _DiscFn(torch.autograd.Function):
         key = (n, H, W)
         eng = mod._acquire(key, lambda: E.DiscriminatorEngine(backend(), n, H, W, x.device, arena=mod.arena, norm=mod.norm))
         eng.refresh_weights()
+        if mod.norm == "batch":
+            eng.bn_state, eng.bn_training = mod._bn_state(), mod.training
+            if mod.training:
+                mod._bn_tick()
         xf = x.float()
         out = eng.forward(xf[:, 0:1].contiguous(), xf[:, 1:4].contiguous()).clone()
         need_p = any(ctx.needs_input_grad[2:])
@@ -518,9 +557,12 @@ class NLayerDiscriminator(_ArenaModule):
         A = self.arena
         self.model = nn.ModuleDict({str(i): _ConvParams(A.view(f"model.{i}.weight"), A.view(f"model.{i}.bias") if f"model.{i}.bias" in A.offset else None)
                                     for i in (0, 2, 5, 8, 11)})
+        if self.norm == "batch":
+            for i in (3, 6, 9):
+                self.model[str(i)] = _BNParams(A.view(f"model.{i}.weight"), A.view(f"model.{i}.bias"))
 
     def _named_holders(self):
-        for i in ("0", "2", "5", "8", "11"):
+        for i in self.model:
             yield f"model.{i}", self.model[i]
 
     def forward(self, x):

@@ -206,7 +206,8 @@ def train_kaist(cfg: M.Config, train_loader=None, val_loader=None, use_graph: bo
     lam = dict(L1=cfg.lambda_L1, perc=cfg.lambda_perc, tv=cfg.lambda_tv, ssim=cfg.lambda_ssim, gan=cfg.lambda_gan)
     ts = TrainStep(M.backend(), cfg.batch_size, H, W, device, cfg.lr_G, cfg.lr_D, cfg.beta1, cfg.beta2, lam, world_size=world,
                    use_graph=use_graph and device.type == "cuda", arenas=(model.netG.arena, netD.arena, vgg.arena),
-                   no_antialias_up=cfg.no_antialias_up, no_antialias=cfg.no_antialias, norm=model.netG.norm)
+                   no_antialias_up=cfg.no_antialias_up, no_antialias=cfg.no_antialias, norm=model.netG.norm,
+                   bn_states=(model.netG._bn_state(), netD._bn_state()) if model.netG.norm == "batch" else (None, None))
     ts.refresh_weights()
     start_epoch = 1
     resume = getattr(cfg, "resume_from", None)          # not in the reference: full-state checkpoints (D + both Adam states + epoch)
@@ -230,6 +231,9 @@ def train_kaist(cfg: M.Config, train_loader=None, val_loader=None, use_graph: bo
                 say(f"Epoch [{epoch}/{cfg.epochs}] Step [{i}/{len(train_loader)}] D: {l['D']:.4f} | G: {l['G']:.4f} "
                     f"(GAN {l['GAN']:.4f} + L1 {l['L1']:.4f} + Perc {l['perc']:.4f} + TV {l['TV']:.6f} + SSIM {l['SSIM']:.4f})")
         avg_d, avg_g, _ = ts.epoch_means()      # every step of the epoch, accumulated on the device (irc:1683-1697)
+        if model.netG.norm == "batch":
+            # num_batches_tracked of the BatchNorm holders: two generator and three discriminator forward calls per iteration
+            model.netG._bn_tick(2 * i); netD._bn_tick(3 * i)
         val_l1 = validate_kaist(model, val_loader, device) if val_loader is not None else float("nan")
         say(f"Epoch [{epoch}/{cfg.epochs}] DONE | avg D: {avg_d:.4f} | avg G: {avg_g:.4f} | val L1: {val_l1:.4f}")
         history.append((avg_d, avg_g, val_l1))

@@ -59,13 +59,23 @@ class TrainStep:
 
     def __init__(self, be, B: int, H: int, W: int, device, lr_G=2e-4, lr_D=2e-4, beta1=0.5, beta2=0.999, lambdas=LAMBDAS,
                  world_size: int = 1, process_group=None, use_graph: bool = False, arenas=(None, None, None), no_antialias_up: bool = False,
-                 no_antialias: bool = False, norm: str = "instance"):
+                 no_antialias: bool = False, norm: str = "instance", bn_states=(None, None)):
         self.be, self.B, self.H, self.W, self.dev = be, B, H, W, device
         self.lam = dict(lambdas)
         self.world, self.pg = world_size, process_group
         self.G = GeneratorEngine(be, B, H, W, device, arena=arenas[0], no_antialias_up=no_antialias_up, no_antialias=no_antialias, norm=norm)
         self.D2 = DiscriminatorEngine(be, 2 * B, H, W, device, arena=arenas[1], norm=norm)
         self.D1 = DiscriminatorEngine(be, B, H, W, device, arena=self.D2.arena, packer=self.D2.packer, layouts=self.D2.layouts, norm=norm)
+        if norm == "batch":
+            # nn.BatchNorm2d: the reference runs the generator twice per iteration on the same batch with the same weights
+            # (irc:1638, :1657: two identical running-statistics updates) and the discriminator three times (irc:1642, :1643,
+            # :1659: real and fake halves are separate batches); bn_states = the module surface's registered buffers
+            self.G.bn_updates = 2
+            if bn_states[0] is not None:
+                self.G.bn_state = bn_states[0]
+            if bn_states[1] is not None:
+                self.D2.bn_state = bn_states[1]
+            self.D1.bn_state = self.D2.bn_state
         self.V = VggEngine(be, 2 * B, B, H, W, device, arena=arenas[2])
         self.optG = AdamHyper(device, lr_G, beta1, beta2)
         self.optD = AdamHyper(device, lr_D, beta1, beta2)
@@ -136,6 +146,9 @@ class TrainStep:
         for name, arena, opt in (("optG", self.G.arena, self.optG), ("optD", self.D2.arena, self.optD)):
             out[name] = dict(step=opt.t, lr=opt.lr, betas=(opt.b1, opt.b2), eps=opt.eps, exp_avg=arena.m.detach().clone(),
                              exp_avg_sq=arena.v.detach().clone())
+        for name, eng in (("bnG", self.G), ("bnD", self.D2)):          # running statistics of nn.BatchNorm2d networks (norm='batch')
+            if getattr(eng, "bn", False):
+                out[name] = {k: (rm.detach().clone(), rv.detach().clone()) for k, (rm, rv) in eng.bn_state.items()}
         return out
 
     def load_state_dict(self, state: Dict) -> None:
@@ -148,6 +161,9 @@ class TrainStep:
                 raise ValueError(f"{name}: optimizer state of {st['exp_avg'].numel()} elements does not fit the arena ({arena.m.numel()})")
             arena.m.copy_(st["exp_avg"]); arena.v.copy_(st["exp_avg_sq"])
             opt.set_step(int(st["step"])); opt._staged = None; opt.lr = float(st["lr"]); opt.b1, opt.b2 = (float(b) for b in st["betas"]); opt.eps = float(st["eps"])
+        for name, eng in (("bnG", self.G), ("bnD", self.D2)):
+            for k, (rm, rv) in state.get(name, {}).items():
+                eng.bn_state[k][0].copy_(rm); eng.bn_state[k][1].copy_(rv)
         self.refresh_weights()
 
     # ------------------------------------------------------------------ the iteration
@@ -217,6 +233,8 @@ class TrainStep:
             # warm-up on a side stream (sets kernel attributes, primes allocators), undo its effect on
             # the optimizer state, then capture
             state = [t for a in (self.G.arena, self.D2.arena) for t in (a.flat, a.m, a.v)] + [self.optG.step_dev, self.optD.step_dev, self.acc]
+            for eng in (self.G, self.D2):          # BatchNorm running statistics are advanced by the warm-up run as well
+                state += [t for pair in getattr(eng, "bn_state", {}).values() for t in pair]
             snap = [t.clone() for t in state]
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())

@@ -56,7 +56,27 @@ def generator_shapes(input_nc=1, output_nc=3, ngf=64, n_blocks=9, no_antialias_u
     s["outc.1.weight"] = (output_nc, ngf, 7, 7); s["outc.1.bias"] = (output_nc,)
     if norm != "instance":
         s = {k: v for k, v in s.items() if not k.endswith(".bias") or k == "outc.1.bias"}
+    if norm == "batch":
+        # nn.BatchNorm2d(C) behind every convolution but outc: affine weight / bias (running statistics are buffers, not listed)
+        for key, c in generator_bn_sites(ngf, n_blocks):
+            s[key + ".weight"] = (c,); s[key + ".bias"] = (c,)
     return s
+
+
+def generator_bn_sites(ngf=64, n_blocks=9):
+    """(state_dict prefix, channels) of the norm layers of ResnetUNetGenerator (irc:457-524, :388-412)"""
+    sites = [("inc.2", ngf), ("down1.1", 2 * ngf), ("down2.1", 4 * ngf)]
+    for b in range(n_blocks):
+        sites += [(f"resblocks.{b}.conv_block.2", 4 * ngf), (f"resblocks.{b}.conv_block.6", 4 * ngf)]
+    return sites + [("up1_conv.1", 2 * ngf), ("up2_conv.1", ngf)]
+
+
+DISCRIMINATOR_BN_SITES = [("model.3", 128), ("model.6", 256), ("model.9", 512)]      # irc:611-624 with n_layers=3, ndf=64
+
+
+def new_bn_state(sites):
+    """running_mean = 0, running_var = 1 per norm site (nn.BatchNorm2d defaults)"""
+    return {k: (torch.zeros(c), torch.ones(c)) for k, c in sites}
 
 
 def discriminator_shapes(input_nc=4, ndf=64, norm="instance"):
@@ -67,6 +87,9 @@ def discriminator_shapes(input_nc=4, ndf=64, norm="instance"):
         s[f"model.{idx}.weight"] = (co, ci, 4, 4)
         if norm == "instance" or idx in (0, 11):
             s[f"model.{idx}.bias"] = (co,)
+    if norm == "batch":
+        for key, c in DISCRIMINATOR_BN_SITES:
+            s[key + ".weight"] = (c,); s[key + ".bias"] = (c,)
     return s
 
 
@@ -92,7 +115,9 @@ def seeded_params(shapes, seed, std=0.02, bias_std=0.0, kaiming=False) -> Params
     out = {}
     for k in sorted(shapes):
         shp = shapes[k]
-        if k.endswith("weight"):
+        if k.endswith("weight") and len(shp) == 1:
+            out[k] = 1.0 + torch.randn(shp, generator=g) * 0.1          # BatchNorm scale: N(1, .) (irc:191-193 uses N(1, 0.02))
+        elif k.endswith("weight"):
             sd = math.sqrt(2.0 / (shp[0] * shp[2] * shp[3])) if kaiming else std
             out[k] = torch.randn(shp, generator=g) * sd
         else:
@@ -197,21 +222,31 @@ def instance_norm(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     return (x - m) / torch.sqrt(v + eps)
 
 
+def _norm_at(p: Params, conv_bias_key: str, bn_key: str, bn_state, training: bool):
+    """the layer get_norm_layer(cfg.norm) puts behind a convolution, recognised from the parameters (irc:148-165): BatchNorm2d when
+    its affine weight exists, InstanceNorm2d when the convolution kept its bias, Identity otherwise"""
+    if bn_key + ".weight" in p:
+        rm, rv = bn_state[bn_key]
+        return lambda t: F.batch_norm(t, rm, rv, p[bn_key + ".weight"], p[bn_key + ".bias"], training, 0.1, 1e-5)
+    return instance_norm if conv_bias_key in p else (lambda t: t)
+
+
 def _conv(x, w, b, stride=1, pad=0, reflect=0):
     if reflect:
         x = F.pad(x, (reflect,) * 4, mode="reflect")
     return F.conv2d(x, w, b, stride=stride, padding=pad)
 
 
-def resnet_block(p: Params, prefix: str, x: torch.Tensor, nrm=instance_norm) -> torch.Tensor:
-    """irc:417-418 with reflect padding; nrm = instance norm (default) or the identity (norm='none': no biases either)."""
+def resnet_block(p: Params, prefix: str, x: torch.Tensor, nrm1=instance_norm, nrm2=None) -> torch.Tensor:
+    """irc:417-418 with reflect padding; nrm1 / nrm2 = the two norm layers (instance norm by default)."""
     h = _conv(x, p[prefix + "conv_block.1.weight"], p.get(prefix + "conv_block.1.bias"), reflect=1)
-    h = torch.relu(nrm(h))
+    h = torch.relu(nrm1(h))
     h = _conv(h, p[prefix + "conv_block.5.weight"], p.get(prefix + "conv_block.5.bias"), reflect=1)
-    return x + nrm(h)
+    return x + (nrm2 or nrm1)(h)
 
 
-def generator_forward(p: Params, x: torch.Tensor, n_blocks: int = 9, taps: Optional[dict] = None, no_antialias: bool = False) -> torch.Tensor:
+def generator_forward(p: Params, x: torch.Tensor, n_blocks: int = 9, taps: Optional[dict] = None, no_antialias: bool = False,
+                      bn_state: Optional[dict] = None, training: bool = True) -> torch.Tensor:
     """ResnetUNetGenerator.forward (irc:540-569); returns the image only.  Default config; ConvTranspose2d up-sampling when the
     parameters carry up{1,2}_up.weight (no_antialias_up=True, irc:495-516); stride-2 down-sampling convolutions without the blur
     modules when no_antialias=True (irc:468, :474, :482).
@@ -222,17 +257,19 @@ def generator_forward(p: Params, x: torch.Tensor, n_blocks: int = 9, taps: Optio
             taps[name] = t
         return t
 
-    # norm='none' (irc:158-163) shows in the parameters: no convolution bias in front of the (absent) normalisation
-    nrm = instance_norm if "inc.1.bias" in p else (lambda t: t)
-    x0 = tap("x0", torch.relu(nrm(_conv(x, p["inc.1.weight"], p.get("inc.1.bias"), reflect=3))))
+    # the norm layer shows in the parameters (irc:148-165): BatchNorm2d affine weights (bn_state: running statistics, updated in
+    # place when training), a convolution bias in front of InstanceNorm2d, or neither (norm='none')
+    N = lambda conv, bn: _norm_at(p, conv + ".bias", bn, bn_state, training)
+    x0 = tap("x0", torch.relu(N("inc.1", "inc.2")(_conv(x, p["inc.1.weight"], p.get("inc.1.bias"), reflect=3))))
     sd = 2 if no_antialias else 1
-    d1 = tap("down1", torch.relu(nrm(_conv(x0, p["down1.0.weight"], p.get("down1.0.bias"), stride=sd, pad=1))))
+    d1 = tap("down1", torch.relu(N("down1.0", "down1.1")(_conv(x0, p["down1.0.weight"], p.get("down1.0.bias"), stride=sd, pad=1))))
     x1 = tap("x1", d1 if no_antialias else blur_down(d1))
-    d2 = tap("down2", torch.relu(nrm(_conv(x1, p["down2.0.weight"], p.get("down2.0.bias"), stride=sd, pad=1))))
+    d2 = tap("down2", torch.relu(N("down2.0", "down2.1")(_conv(x1, p["down2.0.weight"], p.get("down2.0.bias"), stride=sd, pad=1))))
     x2 = tap("x2", d2 if no_antialias else blur_down(d2))
     h = x2
     for b in range(n_blocks):
-        h = tap(f"res{b}", resnet_block(p, f"resblocks.{b}.", h, nrm))
+        pre = f"resblocks.{b}.conv_block."
+        h = tap(f"res{b}", resnet_block(p, f"resblocks.{b}.", h, N(pre + "1", pre + "2"), N(pre + "5", pre + "6")))
     convT = "up1_up.weight" in p          # no_antialias_up=True: nn.ConvTranspose2d(C, C, 3, 2, 1, 1) instead of UpsampleAA (irc:495-499)
     up = (lambda t, k: F.conv_transpose2d(t, p[k + ".weight"], p.get(k + ".bias"), stride=2, padding=1, output_padding=1)) if convT \
         else (lambda t, k: upsample_aa(t))
@@ -240,26 +277,26 @@ def generator_forward(p: Params, x: torch.Tensor, n_blocks: int = 9, taps: Optio
     if y.shape[-2:] != x1.shape[-2:]:  # irc:555-556
         y = F.interpolate(y, size=x1.shape[-2:], mode="bilinear", align_corners=True)
     y = torch.cat([y, x1], dim=1)
-    y = tap("up1", torch.relu(nrm(_conv(y, p["up1_conv.0.weight"], p.get("up1_conv.0.bias"), pad=1))))
+    y = tap("up1", torch.relu(N("up1_conv.0", "up1_conv.1")(_conv(y, p["up1_conv.0.weight"], p.get("up1_conv.0.bias"), pad=1))))
     y = tap("up2_up", up(y, "up2_up"))
     if y.shape[-2:] != x0.shape[-2:]:  # irc:562-563
         y = F.interpolate(y, size=x0.shape[-2:], mode="bilinear", align_corners=True)
     y = torch.cat([y, x0], dim=1)
-    y = tap("up2", torch.relu(nrm(_conv(y, p["up2_conv.0.weight"], p.get("up2_conv.0.bias"), pad=1))))
+    y = tap("up2", torch.relu(N("up2_conv.0", "up2_conv.1")(_conv(y, p["up2_conv.0.weight"], p.get("up2_conv.0.bias"), pad=1))))
     return tap("out", torch.tanh(_conv(y, p["outc.1.weight"], p["outc.1.bias"], reflect=3)))
 
 
-def discriminator_forward(p: Params, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+def discriminator_forward(p: Params, x: torch.Tensor, taps: Optional[dict] = None, bn_state: Optional[dict] = None, training: bool = True) -> torch.Tensor:
     """NLayerDiscriminator.forward, irc:598-635 (n_layers=3, instance norm)."""
     def tap(name, t):
         if taps is not None:
             taps[name] = t
         return t
-    nrm = instance_norm if "model.2.bias" in p else (lambda t: t)      # norm='none': Identity and bias-free convolutions (irc:590-593)
+    N = lambda conv, bn: _norm_at(p, conv + ".bias", bn, bn_state, training)      # BatchNorm2d / InstanceNorm2d / Identity (irc:590-593)
     h = tap("d0", F.leaky_relu(_conv(x, p["model.0.weight"], p["model.0.bias"], stride=2, pad=1), 0.2))
-    h = tap("d2", F.leaky_relu(nrm(_conv(h, p["model.2.weight"], p.get("model.2.bias"), stride=2, pad=1)), 0.2))
-    h = tap("d5", F.leaky_relu(nrm(_conv(h, p["model.5.weight"], p.get("model.5.bias"), stride=2, pad=1)), 0.2))
-    h = tap("d8", F.leaky_relu(nrm(_conv(h, p["model.8.weight"], p.get("model.8.bias"), stride=1, pad=1)), 0.2))
+    h = tap("d2", F.leaky_relu(N("model.2", "model.3")(_conv(h, p["model.2.weight"], p.get("model.2.bias"), stride=2, pad=1)), 0.2))
+    h = tap("d5", F.leaky_relu(N("model.5", "model.6")(_conv(h, p["model.5.weight"], p.get("model.5.bias"), stride=2, pad=1)), 0.2))
+    h = tap("d8", F.leaky_relu(N("model.8", "model.9")(_conv(h, p["model.8.weight"], p.get("model.8.bias"), stride=1, pad=1)), 0.2))
     return tap("d11", _conv(h, p["model.11.weight"], p["model.11.bias"], stride=1, pad=1))
 
 
@@ -344,23 +381,23 @@ class AdamState:
             p.addcdiv_(self.m[k], denom, value=-(self.lr * lr_scale) / bc1)
 
 
-def d_loss_and_grads(pD: Params, ir, rgb, fake_detached):
-    """irc:1639-1650."""
+def d_loss_and_grads(pD: Params, ir, rgb, fake_detached, bn_state=None):
+    """irc:1639-1650 (bn_state: running statistics of a BatchNorm discriminator, updated by each of the two calls)."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in pD.items()}
-    pred_real = discriminator_forward(leaves, torch.cat([ir, rgb], 1))
-    pred_fake = discriminator_forward(leaves, torch.cat([ir, fake_detached], 1))
+    pred_real = discriminator_forward(leaves, torch.cat([ir, rgb], 1), bn_state=bn_state)
+    pred_fake = discriminator_forward(leaves, torch.cat([ir, fake_detached], 1), bn_state=bn_state)
     loss = 0.5 * (torch.relu(1.0 - pred_real).mean() + torch.relu(1.0 + pred_fake).mean())
     grads = torch.autograd.grad(loss, list(leaves.values()))
     return loss.detach(), dict(zip(leaves.keys(), grads))
 
 
-def g_loss_and_grads(pG: Params, pD: Params, pV: Params, ir, rgb, lambdas=LAMBDAS, want_fake_grad=False):
-    """irc:1657-1680. Returns (loss dict, grads wrt G params[, dL/dfake])."""
+def g_loss_and_grads(pG: Params, pD: Params, pV: Params, ir, rgb, lambdas=LAMBDAS, want_fake_grad=False, bn=(None, None)):
+    """irc:1657-1680. Returns (loss dict, grads wrt G params[, dL/dfake]).  bn = (generator, discriminator) BatchNorm states."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in pG.items()}
-    fake = generator_forward(leaves, ir)
+    fake = generator_forward(leaves, ir, bn_state=bn[0])
     if want_fake_grad:
         fake.retain_grad()
-    gan = -discriminator_forward(pD, torch.cat([ir, fake], 1)).mean()
+    gan = -discriminator_forward(pD, torch.cat([ir, fake], 1), bn_state=bn[1]).mean()
     l1 = (fake - rgb).abs().mean() * lambdas["L1"]
     perc = (vgg_forward(pV, fake) - vgg_forward(pV, rgb)).abs().mean() * lambdas["perc"]
     tv = tv_loss(fake) * lambdas["tv"]
@@ -375,14 +412,15 @@ def g_loss_and_grads(pG: Params, pD: Params, pV: Params, ir, rgb, lambdas=LAMBDA
 
 
 def train_step(pG: Params, pD: Params, pV: Params, optG: AdamState, optD: AdamState, ir, rgb,
-               lr_scale: float = 1.0, lambdas=LAMBDAS):
-    """One iteration of the hot loop, irc:1636-1681, mutating pG/pD and the Adam states in place."""
+               lr_scale: float = 1.0, lambdas=LAMBDAS, bn=(None, None)):
+    """One iteration of the hot loop, irc:1636-1681, mutating pG/pD and the Adam states in place.  With norm='batch' the
+    running statistics in bn = (generator state, discriminator state) see two generator and three discriminator forward calls."""
     with torch.no_grad():
-        fake_d = generator_forward(pG, ir)
-    loss_D, gD = d_loss_and_grads(pD, ir, rgb, fake_d)
+        fake_d = generator_forward(pG, ir, bn_state=bn[0])
+    loss_D, gD = d_loss_and_grads(pD, ir, rgb, fake_d, bn_state=bn[1])
     with torch.no_grad():
         optD.step(pD, gD, lr_scale)
-    losses, gG = g_loss_and_grads(pG, pD, pV, ir, rgb, lambdas)
+    losses, gG = g_loss_and_grads(pG, pD, pV, ir, rgb, lambdas, bn=bn)
     with torch.no_grad():
         optG.step(pG, gG, lr_scale)
     losses["D"] = loss_D

@@ -67,6 +67,8 @@ class RefBackend:
 
     @staticmethod
     def _moments(stats, cnt, eps):
+        if eps < 0:          # effective (mean, 1/std) pairs of bn_finalize
+            return stats[..., 0][:, None, None, :], stats[..., 1][:, None, None, :]
         s = stats[..., 0] / cnt
         var = (stats[..., 1] / cnt - s * s).clamp_min(0)
         return s[:, None, None, :], torch.rsqrt(var + eps)[:, None, None, :]
@@ -209,8 +211,26 @@ class RefBackend:
         self.in_stats(z, C, n_img, H, W, stats)
         self.gather(z, dst, C, n_img, H, W, pad, halo_mode, stats=stats, cnt=H * W, eps=eps, act=act, slope=slope, res=res, dst_s2d=dst_s2d)
 
+    def bn_finalize(self, stats, n_img, group, C, cnt_per_img, gamma, beta, running_mean, running_var, eff, momentum=0.1, eps=1e-5, training=True,
+                    updates=1):
+        self.launches += 1
+        M = group * cnt_per_img
+        for g0 in range(0, n_img, group):
+            if training:
+                s = stats[g0:g0 + group].sum(0)                     # [C, 2]
+                mean = s[:, 0] / M; var = (s[:, 1] / M - mean * mean).clamp_min(0)
+                for _ in range(updates):
+                    running_mean.mul_(1 - momentum).add_(momentum * mean)
+                    running_var.mul_(1 - momentum).add_(momentum * var * (M / max(M - 1, 1)))
+            else:
+                mean, var = running_mean.clone(), running_var.clone()
+            sc = gamma.reshape(-1) * torch.rsqrt(var + eps)
+            sc = torch.where(sc.abs() < 1e-20, torch.full_like(sc, 1e-20), sc)
+            eff[g0:g0 + group, :, 0] = mean - beta.reshape(-1) / sc
+            eff[g0:g0 + group, :, 1] = sc
+
     def in_bwd(self, z, g1, dz, C, n_img, H, W, stats=None, cnt=0.0, eps=1e-5, act=0, slope=0.0, tables=None, g2=None, bsum=None,
-               fold_pad=0):
+               fold_pad=0, bn=None):
         from irc_b200._native import IDENTITY
         tables = tables or IDENTITY
         if fold_pad:
@@ -225,6 +245,21 @@ class RefBackend:
             xh = (zv - mu) * rs
             gd = g * _dact(xh, act, slope)
             s1 = gd.sum((1, 2)); s2 = (gd * xh).sum((1, 2))
+            if bn is not None:
+                # BatchNorm: xh is the affine output y; group sums -> parameter gradients and the (A, B) pair of the apply formula
+                grp = int(bn["group"]); ga = bn["gamma"].reshape(-1); be_ = bn["beta"].reshape(-1)
+                ga = torch.where(ga.abs() < 1e-20, torch.full_like(ga, 1e-20), ga)
+                dg = torch.zeros_like(ga); db = torch.zeros_like(ga)
+                for g0 in range(0, n_img, grp):
+                    S1 = s1[g0:g0 + grp].sum(0); S2 = s2[g0:g0 + grp].sum(0)
+                    dgam = (S2 - be_ * S1) / ga
+                    Bq = dgam / ga; Aq = S1 - be_ * Bq
+                    s1[g0:g0 + grp] = Aq; s2[g0:g0 + grp] = Bq
+                    dg += dgam; db += S1
+                if bn.get("accumulate"):
+                    bn["dgamma"].add_(dg.view_as(bn["dgamma"])); bn["dbeta"].add_(db.view_as(bn["dbeta"]))
+                else:
+                    bn["dgamma"].copy_(dg.view_as(bn["dgamma"])); bn["dbeta"].copy_(db.view_as(bn["dbeta"]))
             if bsum is not None:
                 bsum.view(-1)[:n_img * C * 2] = torch.stack([s1, s2], -1).reshape(-1)
             o = rs * (gd - s1[:, None, None, :] / cnt - xh * s2[:, None, None, :] / cnt)

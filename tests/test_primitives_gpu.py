@@ -446,6 +446,47 @@ def test_ssim_metric(bes, size):
         assert abs(a[0][i].item() / cnt - want) < 1e-10, (i, a[0][i].item() / cnt, want)
 
 
+@pytest.mark.parametrize("training", [True, False])
+def test_batch_norm_on_the_instance_norm_kernels(bes, training):
+    """nn.BatchNorm2d (irc:158-159): irc_bn_finalize (batch / running statistics + affine -> effective moments, running-statistics
+    update), apply through irc_gather with eps < 0, backward = reduce + irc_bn_bwd_fix + apply; against torch's own batch_norm"""
+    g = gen(31)
+    n, C, H, W, grp = 4, 64, 12, 20, 2
+    z = frame(n, H, W, 1, C, g)
+    gam = torch.randn(C, device="cuda", generator=g) * 0.3 + 1.0; bet = torch.randn(C, device="cuda", generator=g) * 0.2
+    rm0 = torch.randn(C, device="cuda", generator=g) * 0.1; rv0 = torch.rand(C, device="cuda", generator=g) + 0.5
+    gup = frame(n, H, W, 0, C, g)
+
+    def fn(be, st, eff, rm, rv, dst, dz, bsum, dg, db):
+        be.in_stats(z.view(), C, n, H, W, st)
+        be.bn_finalize(st, n, grp, C, float(H * W), gam, bet, rm, rv, eff, training=training, updates=2)
+        be.gather(z.view(), View(dst, 0, H + 2, W + 2, 1, 1), C, n, H, W, 1, 0, stats=eff, cnt=grp * H * W, eps=-1.0, act=2, slope=0.2)
+        be.in_bwd(z.view(), gup.view(), View(dz, 0, H + 2, W + 2, 1, 1), C, n, H, W, stats=eff, cnt=grp * H * W, eps=-1.0, act=2, slope=0.2, bsum=bsum,
+                  bn=dict(group=grp, gamma=gam, beta=bet, dgamma=dg, dbeta=db))
+    from irc_b200._native import View
+    rows = n * (H + 2) * (W + 2)
+    outs = [torch.zeros(n, C, 2, device="cuda"), torch.zeros(n, C, 2, device="cuda"), rm0.clone(), rv0.clone(),
+            torch.zeros(rows, C, device="cuda", dtype=torch.bfloat16), torch.zeros(rows, C, device="cuda", dtype=torch.bfloat16),
+            torch.zeros(n, C, 2, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")]
+    a, b = both(bes, fn, outs)
+    for i, (x, y, tol, what) in enumerate(zip(a, b, (1e-5, 1e-4, 1e-5, 1e-5, 1e-2, 2e-2, 1e-3, 2e-3, 2e-3),
+                                            ("sums", "eff", "running_mean", "running_var", "y", "dx", "bsum", "dgamma", "dbeta"))):
+        close(x, y, tol, what)
+    # and against torch.nn.functional.batch_norm itself (group by group), in fp32 on the bf16-rounded input
+    x = z.t.view(n, H + 2, W + 2, C)[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().clone().requires_grad_(True)
+    rm, rv = rm0.clone(), rv0.clone()
+    ys = []
+    for g0 in range(0, n, grp):
+        for _ in range(2 if training else 1):
+            yy = torch.nn.functional.batch_norm(x[g0:g0 + grp], rm, rv, gam, bet, training, 0.1, 1e-5)
+        ys.append(torch.nn.functional.leaky_relu(yy, 0.2))
+    y = torch.cat(ys)
+    got = a[4].view(n, H + 2, W + 2, C)[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float()
+    assert ((got - y).norm() / y.norm()).item() < 5e-3
+    if training:
+        close(a[2], rm, 1e-5, "running_mean vs torch"); close(a[3], rv, 1e-5, "running_var vs torch")
+
+
 def test_taps(bes):
     g = gen(7)
     n, H, W, p = 2, 10, 12, 3

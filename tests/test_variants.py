@@ -43,14 +43,15 @@ def test_oracle_variant_forward_and_grads():
 
 # variant tag -> (fixture prefix, no_antialias_up, no_antialias, parameter seed of make_golden_variants.py)
 VARIANTS = {"up": ("", True, False, 4321), "na": ("na/", False, True, 777), "nab": ("nab/", True, True, 778), "odd": ("odd/", False, False, 999),
-            "nn": ("nn/", False, False, 555)}
+            "nn": ("nn/", False, False, 555), "bn": ("bn/", False, False, 333)}
 SIZES = {"odd": (29, 38)}          # default graph at a size that is not a multiple of 4: bilinear fix-up of irc:555-556, :562-563
-NORM = {"nn": "none"}              # norm='none' (irc:158-163): Identity layers, bias-free convolutions
+NORM = {"nn": "none", "bn": "batch"}   # norm='none': Identity layers, bias-free convolutions; 'batch': nn.BatchNorm2d (irc:158-163)
+BIAS_STD = {"bn": 0.05}
 
 
 def _variant_params(tag):
     pre, up, na, seed = VARIANTS[tag]
-    return O.seeded_params(O.generator_shapes(no_antialias_up=up, norm=NORM.get(tag, "instance")), seed, bias_std=0.02)
+    return O.seeded_params(O.generator_shapes(no_antialias_up=up, norm=NORM.get(tag, "instance")), seed, bias_std=BIAS_STD.get(tag, 0.02))
 
 
 @pytest.mark.parametrize("tag", ["na", "nab"])
@@ -82,7 +83,8 @@ def _check_engine(be, dev, tol_fwd, tol_dec, tol_enc, tag="up"):
     eng.backward(torch.from_numpy(GOLD[pre + "upstream"]).to(dev).contiguous())
     worst = {}
     for k in pG:
-        if float(GOLD[pre + "grad_absmax/" + k]) <= 1e-4 or (k.endswith("bias") and not k.startswith(("outc", "up1_up", "up2_up"))):
+        conv_bias_in_front_of_instance_norm = tag not in NORM and k.endswith("bias") and not k.startswith(("outc", "up1_up", "up2_up"))
+        if float(GOLD[pre + "grad_absmax/" + k]) <= 1e-4 or conv_bias_in_front_of_instance_norm:
             continue
         got = sample(eng.arena.view(k, eng.arena.grad)); want = GOLD[pre + "grad_sample/" + k]
         worst[k] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
@@ -163,22 +165,23 @@ def test_plan_without_normalisation_matches_reference():
         L.ACT_DTYPE = old
 
 
-def _check_discriminator_none(be, dev, tol_fwd, tol_grad):
+def _check_discriminator_none(be, dev, tol_fwd, tol_grad, norm="none", pre="nnD/", seed=556, bias_std=0.02):
     import irc_b200  # noqa: F401
     from irc_b200 import engine as E
-    pD = O.seeded_params(O.discriminator_shapes(norm="none"), 556, bias_std=0.02)
+    pD = O.seeded_params(O.discriminator_shapes(norm=norm), seed, bias_std=bias_std)
     ir, rgb = O.synthetic_pair(B, H, W)
-    eng = E.DiscriminatorEngine(be, B, H, W, dev, norm="none")
+    eng = E.DiscriminatorEngine(be, B, H, W, dev, norm=norm)
     eng.arena.load(pD); eng.refresh_weights()
     pred = eng.forward(ir.to(dev).contiguous(), rgb.to(dev).contiguous())
-    assert rel(pred, torch.from_numpy(GOLD["nnD/pred"])) < tol_fwd
+    assert rel(pred, torch.from_numpy(GOLD[pre + "pred"])) < tol_fwd
     eng.arena.grad.zero_()
     dx = torch.zeros(B, 4, H, W, device=dev)
-    eng.backward(torch.from_numpy(GOLD["nnD/upstream"]).to(dev).contiguous(), True, dx, c_first=0, accumulate=False)
-    assert rel(dx, torch.from_numpy(GOLD["nnD/dx"])) < tol_grad
+    eng.backward(torch.from_numpy(GOLD[pre + "upstream"]).to(dev).contiguous(), True, dx, c_first=0, accumulate=False)
+    assert rel(dx, torch.from_numpy(GOLD[pre + "dx"])) < tol_grad
     for k in pD:
-        got = sample(eng.arena.view(k, eng.arena.grad), 512); want = GOLD["nnD/grad/" + k]
+        got = sample(eng.arena.view(k, eng.arena.grad), 512); want = GOLD[pre + "grad/" + k]
         assert np.linalg.norm(got - want) / np.linalg.norm(want) < tol_grad, k
+    return eng
 
 
 def test_discriminator_plan_without_normalisation_matches_reference():
@@ -193,6 +196,103 @@ def test_discriminator_plan_without_normalisation_matches_reference():
         L.ACT_DTYPE = old
 
 
+def test_plan_with_batch_norm_matches_reference():
+    """norm='batch' in float32: batch statistics folded with the affine parameters into effective moments (irc_bn_finalize), the
+    InstanceNorm kernels doing the rest, parameter gradients and the input-gradient correction of irc_bn_bwd_fix, running statistics;
+    then eval(): running statistics instead of batch statistics"""
+    import irc_b200  # noqa: F401
+    from irc_b200 import engine as E, layout as L
+    from ref_backend import RefBackend
+    old = L.ACT_DTYPE
+    L.ACT_DTYPE = torch.float32
+    try:
+        _check_engine(RefBackend(), "cpu", 1e-5, 2e-4, 2e-3, tag="bn")
+        # running statistics after one training forward, and the eval-mode output
+        eng = E.GeneratorEngine(RefBackend(), B, H, W, "cpu", norm="batch", training=False)
+        eng.arena.load(_variant_params("bn")); eng.refresh_weights()
+        ir, _ = O.synthetic_pair(B, H, W)
+        eng.forward(ir)
+        for k in ("inc.2", "down2.1", "resblocks.4.conv_block.6", "up2_conv.1"):
+            assert np.abs(eng.bn_state[k][0].numpy() - GOLD["bn/rm/" + k]).max() < 1e-5 and np.abs(eng.bn_state[k][1].numpy() - GOLD["bn/rv/" + k]).max() < 1e-5, k
+        eng.bn_training = False
+        assert rel(eng.forward(ir), torch.from_numpy(GOLD["bn/fake_eval"])) < 1e-5
+        d = _check_discriminator_none(RefBackend(), "cpu", 1e-5, 2e-4, norm="batch", pre="bnD/", seed=334, bias_std=0.05)
+        assert np.abs(d.bn_state["model.6"][0].numpy() - GOLD["bnD/rm/model.6"]).max() < 1e-5
+        assert np.abs(d.bn_state["model.6"][1].numpy() - GOLD["bnD/rv/model.6"]).max() < 1e-5
+    finally:
+        L.ACT_DTYPE = old
+
+
+def test_full_train_step_with_batch_norm_matches_reference():
+    """one fused D + G iteration with norm='batch' against the reference's own iteration (irc:1636-1681, fixture bnstep/*): the
+    discriminator normalises the real and the fake half of its batched pass separately (two calls in the reference), the single
+    generator forward stands for the reference's two (two running-statistics updates), three discriminator updates; losses,
+    post-Adam parameters (BatchNorm affine parameters included) and running statistics"""
+    import irc_b200  # noqa: F401
+    from irc_b200 import layout as L
+    from irc_b200.train_step import TrainStep
+    from ref_backend import RefBackend
+    old = L.ACT_DTYPE
+    L.ACT_DTYPE = torch.float32
+    try:
+        pG = _variant_params("bn")
+        pD = O.seeded_params(O.discriminator_shapes(norm="batch"), 334, bias_std=0.05)
+        pV = O.seeded_params(O.vgg_shapes(), 13, kaiming=True, bias_std=0.05)
+        ir, rgb = O.synthetic_pair(B, H, W)
+        ts = TrainStep(RefBackend(), B, H, W, "cpu", norm="batch")
+        ts.load(pG, pD, pV)
+        ts.step(ir, rgb)
+        los = ts.losses()
+        for k in ("D", "G", "GAN", "L1", "perc", "SSIM"):
+            ref = float(GOLD["bnstep/loss_" + k])
+            assert abs(los[k] - ref) < 5e-5 * max(1.0, abs(ref)), (k, los[k], ref)
+        for k in ("model.3", "model.6", "model.9"):
+            assert np.abs(ts.D2.bn_state[k][0].numpy() - GOLD["bnstep/rmD/" + k]).max() < 2e-5, k
+            assert np.abs(ts.D2.bn_state[k][1].numpy() - GOLD["bnstep/rvD/" + k]).max() < 2e-5, k
+        for k in ("inc.2", "resblocks.0.conv_block.2", "up1_conv.1"):
+            assert np.abs(ts.G.bn_state[k][0].numpy() - GOLD["bnstep/rmG/" + k]).max() < 2e-5, k
+            assert np.abs(ts.G.bn_state[k][1].numpy() - GOLD["bnstep/rvG/" + k]).max() < 2e-5, k
+        # first Adam step moves every element by +-lr (sign of the gradient): elements whose gradient is ~eps are rounding-sensitive
+        for k in pD:
+            got = sample(ts.D2.arena.view(k)); want = GOLD["bnstep/pD_after/" + k]
+            assert (np.abs(got - want) > 5e-5).mean() < 0.02, k
+        for k in ("outc.1.weight", "up2_conv.1.weight", "up2_conv.1.bias", "inc.2.weight"):
+            got = sample(ts.G.arena.view(k)); want = GOLD["bnstep/pG_after/" + k]
+            assert (np.abs(got - want) > 5e-5).mean() < 0.02, k
+    finally:
+        L.ACT_DTYPE = old
+
+
+def test_module_surface_with_batch_norm():
+    """get_norm_layer('batch') (irc:158-159): nn.BatchNorm2d keys in the state_dict (affine parameters + running statistics +
+    num_batches_tracked), train() / eval() semantics through the module, N(1, gain) initialisation of the norm weights (irc:190-194)"""
+    import irc_b200 as R
+    from irc_b200 import layout as L, modules as M
+    from ref_backend import RefBackend
+    old, oldbe = L.ACT_DTYPE, M._BACKEND
+    L.ACT_DTYPE = torch.float32; M.set_backend(RefBackend())
+    try:
+        cfg = R.Config(); cfg.device = "cpu"; cfg.norm = "batch"
+        m = R.IRColorizationModel(cfg)
+        sd = m.netG.state_dict()
+        assert {"inc.2.weight", "inc.2.running_var", "down1.1.num_batches_tracked", "resblocks.8.conv_block.6.bias", "up2_conv.1.running_mean"} <= set(sd)
+        assert "inc.1.bias" not in sd and abs(sd["down2.1.weight"].mean().item() - 1.0) < 0.02 and sd["inc.2.bias"].abs().max() == 0
+        m.netG.load_state_dict(_variant_params("bn"), strict=False)
+        ir, _ = O.synthetic_pair(B, H, W)
+        m.train()
+        with torch.no_grad():
+            assert rel(m(ir), torch.from_numpy(GOLD["bn/fake"])) < 1e-5
+        assert int(m.netG.state_dict()["inc.2.num_batches_tracked"]) == 1
+        assert np.abs(m.netG.state_dict()["inc.2.running_mean"].numpy() - GOLD["bn/rm/inc.2"]).max() < 1e-5
+        m.eval()
+        with torch.no_grad():
+            assert rel(m(ir), torch.from_numpy(GOLD["bn/fake_eval"])) < 1e-5
+        netD = R.NLayerDiscriminator(4, 64, 3, R.get_norm_layer("batch"))
+        assert {"model.3.weight", "model.6.running_mean", "model.9.num_batches_tracked"} <= set(netD.state_dict()) and "model.2.bias" not in netD.state_dict()
+    finally:
+        L.ACT_DTYPE = old; M.set_backend(oldbe)
+
+
 def test_module_surface_without_normalisation():
     """get_norm_layer('none') (irc:154-165): Identity factory; the generator / discriminator state_dicts lose the biases of the
     convolutions that sit in front of a norm layer (use_bias False, irc:452-455, :590-593); 'batch' says that it is not built"""
@@ -204,7 +304,7 @@ def test_module_surface_without_normalisation():
     try:
         assert isinstance(R.get_norm_layer("none")(64), R.Identity) and isinstance(R.get_norm_layer(None)(8), R.Identity)
         with pytest.raises(NotImplementedError):
-            R.get_norm_layer("batch")
+            R.get_norm_layer("layer")
         cfg = R.Config(); cfg.device = "cpu"; cfg.norm = "none"
         m = R.IRColorizationModel(cfg)
         sd = m.netG.state_dict()
@@ -272,11 +372,45 @@ def test_gpu_generator_with_transposed_conv_upsampling():
 
 @pytest.mark.gpu
 @pytest.mark.gpu
+def test_gpu_full_train_step_with_batch_norm():
+    """norm='batch' through the fused CUDA iteration (bf16): losses and running statistics against the reference's iteration, and
+    CUDA-graph replay == eager, bit for bit, over two iterations (the BatchNorm helper launches are captured like everything else)"""
+    from irc_b200._native import CudaBackend
+    from irc_b200.train_step import TrainStep
+    pG = _variant_params("bn")
+    pD = O.seeded_params(O.discriminator_shapes(norm="batch"), 334, bias_std=0.05)
+    pV = O.seeded_params(O.vgg_shapes(), 13, kaiming=True, bias_std=0.05)
+    ir, rgb = O.synthetic_pair(B, H, W)
+    res = []
+    for graph in (False, True):
+        ts = TrainStep(CudaBackend(), B, H, W, "cuda", norm="batch", use_graph=graph)
+        ts.load(pG, pD, pV)
+        ts.step(ir.cuda(), rgb.cuda())
+        if not graph:
+            los = ts.losses()
+            for k, tol in (("D", 2e-2), ("G", 1e-2), ("L1", 1e-2), ("perc", 3e-2), ("SSIM", 1e-2)):
+                ref = float(GOLD["bnstep/loss_" + k])
+                assert abs(los[k] - ref) < tol * max(1.0, abs(ref)), (k, los[k], ref)
+            for k in ("model.3", "model.6", "model.9"):
+                assert rel(ts.D2.bn_state[k][1], torch.from_numpy(GOLD["bnstep/rvD/" + k])) < 3e-2, k
+            for k in ("inc.2", "resblocks.0.conv_block.2", "up1_conv.1"):
+                assert rel(ts.G.bn_state[k][0], torch.from_numpy(GOLD["bnstep/rmG/" + k])) < 5e-2, k
+                assert rel(ts.G.bn_state[k][1], torch.from_numpy(GOLD["bnstep/rvG/" + k])) < 3e-2, k
+        ts.step(ir.cuda(), rgb.cuda())
+        torch.cuda.synchronize()
+        res.append((ts.G.arena.flat.clone(), ts.D2.arena.flat.clone(), ts.G.bn_state["up2_conv.1"][1].clone(), ts.D2.bn_state["model.9"][0].clone()))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
 def test_gpu_networks_without_normalisation():
     """norm='none' on the CUDA path (bf16): without InstanceNorm the forward error stays at the bf16 level and the gradients do not
     see amplified ReLU-mask flips"""
     from irc_b200._native import CudaBackend
     _check_engine(CudaBackend(), "cuda", 2e-2, 0.15, 0.2, tag="nn")
+    _check_engine(CudaBackend(), "cuda", 3e-2, 0.25, 0.35, tag="bn")          # nn.BatchNorm2d: same whole-network bounds as InstanceNorm
+    _check_discriminator_none(CudaBackend(), "cuda", 3e-2, 0.2, norm="batch", pre="bnD/", seed=334, bias_std=0.05)
     _check_discriminator_none(CudaBackend(), "cuda", 2e-2, 0.12)      # four LeakyReLU masks evaluated on bf16 pre-activations
 
 
