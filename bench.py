@@ -338,13 +338,19 @@ def main():
         if (name, tag) in agg:
             n, t = agg[(name, tag)]
             gbs = nbytes / (t * 1e-3) / 1e9
-            hbm_kernels.append(dict(kernel=label, launches=n, algorithmic_mb=round(nbytes / 1e6, 1), us=round(t * 1e3, 1), gb_s=round(gbs, 0),
-                                    frac=round(gbs / pk["hbm"], 3)))
+            row = dict(kernel=label, launches=n, algorithmic_mb=round(nbytes / 1e6, 1), us=round(t * 1e3, 1), gb_s=round(gbs, 0),
+                       frac=round(gbs / pk["hbm"], 3))
+            if name in ("ssim_fwd", "ssim_bwd"):
+                # five (forward) / three (backward) separable 11-tap filters per pixel-channel: the fp32 pipe, not HBM, bounds them
+                fma = (110 if name == "ssim_fwd" else 66) * B * 3 * H * W
+                row.update(bound="fp32 pipe", tfma_s=round(fma / (t * 1e-3) / 1e12, 2),
+                           note="110 / 66 FMA per pixel-channel put the floor 2.3x above the HBM floor; frac is against the HBM peak")
+            hbm_kernels.append(row)
     if ("conv_gemm", "G.res:fwd") in agg:
         n, t = agg[("conv_gemm", "G.res:fwd")]
         fl = 2.0 * 256 * 256 * 9 * B * (H // 4) * (W // 4)
-        dom = dict(kernel="conv_gemm_kernel, ResNet-block shape (M=B*H/4*W/4, N=256, K=2304): 18 of the 80 conv launches, same shape as the "
-                          "18 data-gradient launches", launches=n, gflop_per_launch=fl / 1e9, us_per_launch=t / n * 1e3,
+        dom = dict(kernel="conv_gemm_kernel, ResNet-block shape (M=B*H/4*W/4, N=256, K=2304): 18 of the conv launches, same shape as the "
+                          "18 data-gradient launches (CTA-pair kernel, tcgen05.mma.cta_group::2)", launches=n, gflop_per_launch=fl / 1e9, us_per_launch=t / n * 1e3,
                    achieved=fl / (t / n * 1e-3) / 1e12, peak=pk["tf"], unit="TFLOP/s", frac=fl / (t / n * 1e-3) / 1e12 / pk["tf"],
                    traffic=None,
                    traffic_note="not measured in this run (DRAM counters need ncu): see profiles/ for the ncu --set full capture of this shape")

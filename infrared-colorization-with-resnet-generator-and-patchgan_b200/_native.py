@@ -290,6 +290,7 @@ class CudaBackend:
         # a loss below it (down1, K = 576: the epilogue is on the critical path, +0.13 ms for a 0.07 ms pass).  IRC_STATS_EPI=0
         # all layers, =1000000 none
         self.stats_epilogue_min_k = int(os.environ.get("IRC_STATS_EPI", "1024"))
+        self.res_epilogue_stats = os.environ.get("IRC_RES_EPI_STATS", "0") != "0"   # ResNet blocks: epilogue statistics + streaming apply instead of the cluster kernel
         self.fused_outc = os.environ.get("IRC_FUSED_OUTC", "1") != "0"      # tap reduction + bias + tanh in the GEMM epilogue of the output head
         self.gather_mode = os.environ.get("IRC_GATHER", "auto")     # lean | tiled | generic (stencil gather kernel choice)
         self.conv_epilogue_direct = int(os.environ.get("IRC_EPI_DIRECT", "0"))

@@ -119,8 +119,26 @@ struct EpiCtx {
     const float* sbias;  // bias staged in shared memory, or null
 };
 
+// mask / addend rows of one 32-column chunk, fetched EARLY (before the barrier and the TMEM wait of the staged epilogue) so that
+// their global-load latency overlaps that wait instead of sitting on the per-chunk critical path of shallow-K layers
+struct EpiPre { uint4 m[4]; uint4 a[4]; };
+
+__device__ __forceinline__ void epi_prefetch(const ConvParams& p, EpiPre& pre, long long row, int col, bool in_range) {
+    const bool live = in_range;
+    if (p.mask && live) {
+        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + row * p.mask_ld + p.mask_chan_off + col);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pre.m[g] = __ldg(mp + g);
+    }
+    if (p.addend && live) {
+        const uint4* ap = reinterpret_cast<const uint4*>(p.addend + row * p.addend_ld + p.addend_chan_off + col);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pre.a[g] = __ldg(ap + g);
+    }
+}
+
 __device__ __forceinline__ void epi_math32(const ConvParams& p, const EpiCtx& e, const uint32_t (&r)[32], float (&v)[32], long long row, int col,
-                                           bool live) {
+                                           bool live, const EpiPre* pre = nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
     if (e.sbias) {
@@ -134,7 +152,7 @@ __device__ __forceinline__ void epi_math32(const ConvParams& p, const EpiCtx& e,
         const uint4* mp = reinterpret_cast<const uint4*>(p.mask + row * p.mask_ld + p.mask_chan_off + col);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-            const uint4 mv = __ldg(mp + g);
+            const uint4 mv = pre ? pre->m[g] : __ldg(mp + g);
             const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -148,7 +166,7 @@ __device__ __forceinline__ void epi_math32(const ConvParams& p, const EpiCtx& e,
         const uint4* ap = reinterpret_cast<const uint4*>(p.addend + row * p.addend_ld + p.addend_chan_off + col);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-            const uint4 av = __ldg(ap + g);
+            const uint4 av = pre ? pre->a[g] : __ldg(ap + g);
             const uint32_t w[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -214,11 +232,14 @@ __device__ __forceinline__ void epilogue_subtile_staged(const ConvParams& p, con
         const int cc = c0 + half * 32;
         uint32_t r[32];
         tmem_ld32(taddr + cc, r);                         // TMEM read overlaps the wait for the staging tile
+        EpiPre pre;
+        epi_prefetch(p, pre, row, n0 + cc, in_range);     // ... and so do the mask / addend rows of this chunk (ring rows included:
+                                                          // no dependence on the row_img load)
         if (store_thread) { if (p.nstg == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>(); }   // buffer drained by its last TMA store
         named_bar_sync(1, 256);
         tmem_ld_wait();
         float v[32];
-        epi_math32(p, e, r, v, row, n0 + cc, live);
+        epi_math32(p, e, r, v, row, n0 + cc, live, &pre);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int chunk = (half * 4 + g) ^ (r_in_tile & 7);           // 128-byte swizzle: 16-byte chunk index XOR row % 8

@@ -279,6 +279,12 @@ class GeneratorEngine:
         self.ri_half = torch.zeros(self.Z3.rows, device=device, dtype=torch.int16)
         be.row_index(self.ri_full, B, H + 2, W + 2, 1, H + 1, 1, W + 1)
         be.row_index(self.ri_half, B, H2 + 2, W2 + 2, 1, H2 + 1, 1, W2 + 1)
+        # ResNet blocks: InstanceNorm statistics from the GEMM epilogue + a streaming apply pass, instead of the cluster kernel that
+        # computes them itself (be.res_epilogue_stats; measured per box, see profiles/)
+        self.res_epi = bool(getattr(be, "res_epilogue_stats", False)) and self.norm == "instance"
+        if self.res_epi:
+            self.ri_quarter = torch.zeros(self.X[0].rows, device=device, dtype=torch.int16)
+            be.row_index(self.ri_quarter, B, H4 + 2, W4 + 2, 1, H4 + 1, 1, W4 + 1)
         # ---- stencil tables
         mk = lambda my, mx: L.make_tables(my, mx, device)
         self.t_down1 = mk(L.down_matrix(H), L.down_matrix(W))
@@ -460,6 +466,14 @@ class GeneratorEngine:
         n4 = H4 * W4
         for b in range(self.nb):
             c1, c2 = self.res[b]
+            if self.res_epi:
+                fr = self.X[b]
+                c1.fwd_stats(fr.t, 0, self.Za[b].t, self.sta[b], self.ri_quarter, B, fr.hp * fr.wp, self.Za[b].view(), 256, H4, W4)
+                be.gather(self.Za[b].view(), self.Hh[b].view(), 256, B, H4, W4, 1, 1, stats=self.sta[b], cnt=n4, eps=EPS, act=ACT_RELU)
+                c2.fwd_stats(self.Hh[b].t, 0, self.Zb[b].t, self.stb[b], self.ri_quarter, B, fr.hp * fr.wp, self.Zb[b].view(), 256, H4, W4)
+                halo = 0 if (self.convT and b == self.nb - 1) else 1
+                be.gather(self.Zb[b].view(), self.X[b + 1].view(), 256, B, H4, W4, 1, halo, stats=self.stb[b], cnt=n4, eps=EPS, act=ACT_NONE, res=self.X[b].view())
+                continue
             c1.fwd(self.X[b].t, 0, self.Za[b].t, **self._epi())
             if self.norm == "instance":
                 be.in_apply(self.Za[b].view(), self.Hh[b].view(), 256, B, H4, W4, 1, 1, self.sta[b], eps=EPS, act=ACT_RELU)
