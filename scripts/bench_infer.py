@@ -88,7 +88,7 @@ def main():
                 res[name] = ms
         imgs = B * (world if total > 1 else 1)
         gflop = 136.94 * H * W / 65536
-        tf = gflop * B / res["resident"] / 1e3          # per GPU
+        tf = gflop * B / res["resident"]                # GFLOP per ms == TFLOP/s, per GPU
         lines.append(dict(metric="test_mode_img_per_s", value=imgs / (res["resident"] * 1e-3), unit="img/s", n_gpus=world if total > 1 else 1,
                           steps=args.reps, warmup=3, ms_per_step=res["resident"], higher_is_better=True, scaling="strong", vs_baseline=None,
                           dtype="bf16", data="synthetic",
