@@ -157,18 +157,31 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all_() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit_() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 constexpr int kSkPitch = 36;      // u32 per staged output row (32 + 4): conflict-free fragment stores and 16-byte row reads
 
-template <int KS, int MODE, bool KEEP>      // K = 16 * KS slots; row order of RowMap; KEEP: also write the operand E
+// activation on a packed bf16 pair AFTER the fp32 -> bf16 rounding (ReLU and LeakyReLU with 0 <= slope < 1 commute with it up to the
+// rounding of slope * v, far below the bf16 step of the stored value): one or two packed instructions instead of six scalar ones
+__device__ __forceinline__ uint32_t act_bf16x2(uint32_t v, int act, __nv_bfloat162 slope2) {
+    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&v);
+    if (act == 1) x = __hmax2(x, __float2bfloat162_rn(0.f));
+    else if (act == 2) x = __hmax2(x, __hmul2(x, slope2));
+    return *reinterpret_cast<uint32_t*>(&x);
+}
+
+template <int KS, int MODE, bool KEEP, bool EPI>      // K = 16 * KS slots; row order of RowMap; KEEP: also write the operand E; EPI: bias / activation
 __global__ void __launch_bounds__(256, 2) smallk_conv_fwd_kernel(const Im2colP p, const bf16* __restrict__ w, const float* __restrict__ bias, int act, float slope,
-                                                                 bf16* __restrict__ out, int R, int Wp, int LPB) {
+                                                                 bf16* __restrict__ out, int R, int Wp, int LPB, int nbuf) {
     irc::pdl_prologue();
-    extern __shared__ float tile[];                 // [C][R][Wp] fp32, then 8 warps x (1 + KEEP) x [16][kSkPitch] u32 staging
+    extern __shared__ float tile_base[];            // NBUF x [C][R][Wp] fp32 tiles, then 8 warps x (1 + KEEP) x [16][kSkPitch] u32 staging
     const int C = p.c1 + p.c2;
     const int K = p.k * p.k * C;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    uint32_t* stage_o = reinterpret_cast<uint32_t*>(tile + (size_t)C * R * Wp) + warp * ((KEEP ? 2 : 1) * 16 * kSkPitch);
+    const int tile_floats = C * R * Wp;
+    uint32_t* stage_o = reinterpret_cast<uint32_t*>(tile_base + (size_t)nbuf * tile_floats) + warp * ((KEEP ? 2 : 1) * 16 * kSkPitch);
     uint32_t* stage_e = stage_o + 16 * kSkPitch;
     // operand columns this thread gathers: per k-step the pairs (2t, 2t+1) and (2t+8, 2t+9); columns >= K meet zero weights
     // (their tile reads stay inside the tile: offset 0), and are masked out of the operand copy
@@ -195,49 +208,68 @@ __global__ void __launch_bounds__(256, 2) smallk_conv_fwd_kernel(const Im2colP p
             const uint32_t* wr = reinterpret_cast<const uint32_t*>(w + (size_t)(8 * j + g) * 64 + ks * 16 + 2 * t);
             bf[ks][j][0] = __ldg(wr); bf[ks][j][1] = __ldg(wr + 4);
         }
-    const float slope_eff = act == 1 ? 0.f : (act == 2 ? slope : 1.f);
+    const __nv_bfloat162 slope2 = __float2bfloat162_rn(slope);
     const int Ho = p.rm.Ho, Wo = p.rm.Wo;
     const int nl = p.rm.lines(), ll = p.rm.line_len();
     const int ngrp = (nl + LPB - 1) / LPB;
     const long long hw = (long long)p.H * p.W;
     const int sWp = p.stride * Wp;
-    for (int bg = blockIdx.x; bg < p.rm.n_img * ngrp; bg += gridDim.x) {
+    // tile fill with 4-byte cp.async (no load -> store dependence: every copy of a tile is in flight at once); interior cells in a
+    // branch-free loop, the 2 * pad border columns (zeros or reflected pixels) by the first lanes.  With nbuf == 2 the NEXT group's
+    // tile is fetched while the current one is multiplied, so the global-load latency never sits between two barriers.
+    auto fill = [&](float* tile, int bg) {
         const int n = bg / ngrp, line0 = (bg - n * ngrp) * LPB;
-        const int nlines = min(LPB, nl - line0);
         const int oy0 = MODE == 0 ? line0 : (MODE == 1 ? line0 - 1 : 2 * line0 - 1);
         const int y_lo = oy0 * p.stride - p.pad;
-        __syncthreads();                            // the previous group's readers are done with the tile
-        // tile fill with 4-byte cp.async: no load -> store dependence, every copy of the block is in flight at once (with plain
-        // loads the ~10 dependent global-load latencies per warp cost more than the arithmetic of the whole group)
         for (int tt = warp; tt < C * R; tt += 8) {
             const int c = tt / R, r = tt - c * R;
             int y = y_lo + r;
             if (p.pad_mode == 1) y = reflect_idx(y, p.H);
-            const bool oky = y >= 0 && y < p.H;
-            const float* srow = (c < p.c1 ? p.src1 + ((long long)n * p.c1 + c) * hw : p.src2 + ((long long)n * p.c2 + (c - p.c1)) * hw) + (long long)(oky ? y : 0) * p.W;
             float* trow = tile + tt * Wp;
-            for (int xx = lane; xx < Wp; xx += 32) {
-                int x = xx - p.pad;
-                if (p.pad_mode == 1) x = reflect_idx(x, p.W);
-                if (oky && x >= 0 && x < p.W) cp_async4(trow + xx, srow + x);
+            if (y < 0 || y >= p.H) {
+                for (int xx = lane; xx < Wp; xx += 32) trow[xx] = 0.f;
+                continue;
+            }
+            const float* srow = (c < p.c1 ? p.src1 + ((long long)n * p.c1 + c) * hw : p.src2 + ((long long)n * p.c2 + (c - p.c1)) * hw) + (long long)y * p.W;
+            for (int x = lane; x < p.W; x += 32) cp_async4(trow + p.pad + x, srow + x);
+            if (lane < 2 * p.pad) {
+                const int xx = lane < p.pad ? lane : p.W + lane;                 // left / right border column of the padded row
+                if (p.pad_mode == 1) cp_async4(trow + xx, srow + reflect_idx(xx - p.pad, p.W));
                 else trow[xx] = 0.f;
             }
         }
-        cp_async_wait_all_();
-        if (p.scale) {
-            // per-channel affine (VGG input normalisation) on the cells this thread copied itself; padding cells stay zero
-            for (int tt = warp; tt < C * R; tt += 8) {
-                const int c = tt / R, r = tt - c * R;
-                const int y = y_lo + r;
-                if (p.pad_mode != 1 && (y < 0 || y >= p.H)) continue;          // reflected cells are image values, zero padding is not
-                const float sc = __ldg(p.scale + c), sh = __ldg(p.shift + c);
-                float* trow = tile + tt * Wp;
-                for (int xx = lane; xx < Wp; xx += 32) {
-                    const int x = xx - p.pad;
-                    if (p.pad_mode == 1 || (x >= 0 && x < p.W)) trow[xx] = fmaf(trow[xx], sc, sh);
-                }
-            }
+        cp_async_commit_();
+    };
+    auto affine = [&](float* tile, int bg) {
+        // per-channel affine (VGG input normalisation) on the cells this thread copied itself; zero padding stays zero
+        const int n = bg / ngrp, line0 = (bg - n * ngrp) * LPB;
+        const int oy0 = MODE == 0 ? line0 : (MODE == 1 ? line0 - 1 : 2 * line0 - 1);
+        const int y_lo = oy0 * p.stride - p.pad;
+        for (int tt = warp; tt < C * R; tt += 8) {
+            const int c = tt / R, r = tt - c * R;
+            const int y = y_lo + r;
+            if (p.pad_mode != 1 && (y < 0 || y >= p.H)) continue;
+            const float sc = __ldg(p.scale + c), sh = __ldg(p.shift + c);
+            float* trow = tile + tt * Wp;
+            for (int x = lane; x < p.W; x += 32) trow[p.pad + x] = fmaf(trow[p.pad + x], sc, sh);
+            if (p.pad_mode == 1 && lane < 2 * p.pad) { const int xx = lane < p.pad ? lane : p.W + lane; trow[xx] = fmaf(trow[xx], sc, sh); }
         }
+    };
+    const int total = p.rm.n_img * ngrp;
+    int cur = 0;
+    if ((int)blockIdx.x < total) fill(tile_base, blockIdx.x);
+    for (int bg = blockIdx.x; bg < total; bg += gridDim.x) {
+        const int n = bg / ngrp, line0 = (bg - n * ngrp) * LPB;
+        const int nlines = min(LPB, nl - line0);
+        const int oy0 = MODE == 0 ? line0 : (MODE == 1 ? line0 - 1 : 2 * line0 - 1);
+        float* tile = tile_base + (size_t)cur * tile_floats;
+        const int nxt = bg + gridDim.x;
+        if (nbuf == 2) {
+            if (nxt < total) { fill(tile_base + (size_t)(cur ^ 1) * tile_floats, nxt); cp_async_wait_<1>(); } else cp_async_wait_<0>();
+        } else {
+            cp_async_wait_<0>();
+        }
+        if (p.scale) affine(tile, bg);
         __syncthreads();
         // the group's rows are one contiguous range of the flat row order: chunks of 16 rows go round-robin over the warps;
         // (l, ii) = (line within the group, position in the line) of this thread's first row, advanced without divisions
@@ -286,17 +318,16 @@ __global__ void __launch_bounds__(256, 2) smallk_conv_fwd_kernel(const Im2colP p
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float c0 = acc[j][0], c1 = acc[j][1], c2 = acc[j][2], c3 = acc[j][3];
-                if (bias) {
-                    const float2 bv = __ldg(reinterpret_cast<const float2*>(bias + 8 * j + 2 * t));
-                    c0 += bv.x; c1 += bv.y; c2 += bv.x; c3 += bv.y;
+                uint32_t lo, hi;
+                if (EPI) {
+                    const float2 bv = bias ? __ldg(reinterpret_cast<const float2*>(bias + 8 * j + 2 * t)) : make_float2(0.f, 0.f);      // L1-resident
+                    lo = act_bf16x2(pack_bf16x2(acc[j][0] + bv.x, acc[j][1] + bv.y), act, slope2);
+                    hi = act_bf16x2(pack_bf16x2(acc[j][2] + bv.x, acc[j][3] + bv.y), act, slope2);
+                } else {
+                    lo = pack_bf16x2(acc[j][0], acc[j][1]); hi = pack_bf16x2(acc[j][2], acc[j][3]);
                 }
-                if (act) {
-                    c0 = fmaxf(c0, 0.f) + slope_eff * fminf(c0, 0.f); c1 = fmaxf(c1, 0.f) + slope_eff * fminf(c1, 0.f);
-                    c2 = fmaxf(c2, 0.f) + slope_eff * fminf(c2, 0.f); c3 = fmaxf(c3, 0.f) + slope_eff * fminf(c3, 0.f);
-                }
-                stage_o[g * kSkPitch + j * 4 + t] = live[0] ? pack_bf16x2(c0, c1) : 0u;
-                stage_o[(g + 8) * kSkPitch + j * 4 + t] = live[1] ? pack_bf16x2(c2, c3) : 0u;
+                stage_o[g * kSkPitch + j * 4 + t] = live[0] ? lo : 0u;
+                stage_o[(g + 8) * kSkPitch + j * 4 + t] = live[1] ? hi : 0u;
             }
             __syncwarp();
             // 16 rows x 128 bytes: lane -> (row, 16-byte chunk), four rows per instruction, consecutive rows are consecutive in memory
@@ -316,6 +347,9 @@ __global__ void __launch_bounds__(256, 2) smallk_conv_fwd_kernel(const Im2colP p
             ii += 8 * 16;
             while (ii >= ll) { ii -= ll; ++l; }
         }
+        __syncthreads();                            // every warp is done reading this tile
+        if (nbuf == 2) cur ^= 1;
+        else if (nxt < total) fill(tile_base, nxt);
     }
 }
 
@@ -577,30 +611,39 @@ extern "C" int irc_smallk_conv_fwd(const irc_im2col_args* a, const void* w, cons
     const bool keep = a->dst != nullptr;
     const int Wp = a->W + 2 * a->pad;
     const size_t stage_bytes = 8 * (keep ? 2 : 1) * 16 * kSkPitch * sizeof(uint32_t);
-    int LPB = a->row_mode == 2 ? 2 : 4, R = 0;
-    size_t smem = 0;
+    int LPB = a->row_mode == 2 ? 2 : 4, R = 0, nbuf = 2;
+    size_t smem = 0, tile_bytes = 0;
     for (;; LPB >>= 1) {
         const int rows_out = LPB * (a->row_mode == 2 ? 2 : 1);
         R = (rows_out - 1) * a->stride + a->k;
-        smem = (size_t)C * R * Wp * sizeof(float) + stage_bytes;
+        tile_bytes = (size_t)C * R * Wp * sizeof(float);
+        smem = 2 * tile_bytes + stage_bytes;
         if (smem <= 100 * 1024 || LPB == 1) break;
     }
+    if (smem > 100 * 1024) { nbuf = 1; smem = tile_bytes + stage_bytes; }        // wide images: one tile, filled between the groups
     if (smem > 200 * 1024) return irc_set_error(IRC_ERR_BAD_ARG, "irc_smallk_conv_fwd: line tile does not fit shared memory");
+    // persistent blocks (two per SM): each walks its groups of lines with the next tile in flight
     const long long nblk = (long long)p.rm.n_img * ((p.rm.lines() + LPB - 1) / LPB);
-    const unsigned grid = (unsigned)(nblk < 1048576 ? nblk : 1048576);
+    const long long cap = 2LL * irc_num_sms();
+    const unsigned grid = (unsigned)(nblk < cap ? nblk : cap);
     const int ks = K <= 32 ? 2 : 4;
     bool ok = false;
-#define IRC_SMALLK_CASE(KS_, MODE_, KEEP_)                                                                                                         \
-    if (!ok && ks == KS_ && a->row_mode == MODE_ && keep == KEEP_) {                                                                              \
+    const bool epi = bias != nullptr || act != 0;
+    if (act < 0 || act > 2 || (act == 2 && !(slope >= 0.f && slope < 1.f)))
+        return irc_set_error(IRC_ERR_BAD_ARG, "irc_smallk_conv_fwd: act must be 0, 1 (ReLU) or 2 (LeakyReLU with 0 <= slope < 1)");
+#define IRC_SMALLK_CASE2(KS_, MODE_, KEEP_, EPI_)                                                                                                  \
+    if (!ok && ks == KS_ && a->row_mode == MODE_ && keep == KEEP_ && epi == EPI_) {                                                               \
         static bool attr = false;                                                                                                                  \
-        if (!attr) { cudaFuncSetAttribute(smallk_conv_fwd_kernel<KS_, MODE_, KEEP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; } \
-        irc::launch(smallk_conv_fwd_kernel<KS_, MODE_, KEEP_>, grid, 256, smem, (cudaStream_t)stream, p, (const bf16*)w, bias, act, slope, (bf16*)out, R, Wp, LPB); \
+        if (!attr) { cudaFuncSetAttribute(smallk_conv_fwd_kernel<KS_, MODE_, KEEP_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; } \
+        irc::launch(smallk_conv_fwd_kernel<KS_, MODE_, KEEP_, EPI_>, grid, 256, smem, (cudaStream_t)stream, p, (const bf16*)w, bias, act, slope, (bf16*)out, R, Wp, LPB, nbuf); \
         ok = true;                                                                                                                                 \
     }
+#define IRC_SMALLK_CASE(KS_, MODE_, KEEP_) IRC_SMALLK_CASE2(KS_, MODE_, KEEP_, false) IRC_SMALLK_CASE2(KS_, MODE_, KEEP_, true)
     IRC_SMALLK_CASE(2, 0, false) IRC_SMALLK_CASE(2, 0, true) IRC_SMALLK_CASE(2, 1, false) IRC_SMALLK_CASE(2, 1, true)
     IRC_SMALLK_CASE(2, 2, false) IRC_SMALLK_CASE(2, 2, true) IRC_SMALLK_CASE(4, 0, false) IRC_SMALLK_CASE(4, 0, true)
     IRC_SMALLK_CASE(4, 1, false) IRC_SMALLK_CASE(4, 1, true) IRC_SMALLK_CASE(4, 2, false) IRC_SMALLK_CASE(4, 2, true)
 #undef IRC_SMALLK_CASE
+#undef IRC_SMALLK_CASE2
     if (!ok) return irc_set_error(IRC_ERR_BAD_ARG, "irc_smallk_conv_fwd: bad row_mode %d", a->row_mode);
     return irc_check_launch("irc_smallk_conv_fwd");
 }
