@@ -327,6 +327,11 @@ int irc_adam(float* p, const float* g, float* m, float* v, long long n, const do
 int irc_gather_f32(const float* src, const int* map, long long n, float* dst, void* stream);
 /* dst[i] = bf16(map[i] >= 0 ? src[map[i]] : 0): OIHW fp32 parameters -> packed GEMM operands. */
 int irc_pack_bf16(const float* src, const int* map, long long n, void* dst, void* stream);
+/* The same for the regular layers without the index map: OIHW fp32 -> W_f[n][t*K + k] and the data-gradient operand
+ * W_d[k][t*kd + n] (bf16) through a shared-memory transpose, all layers of a network in one launch.  jobs: device array of
+ * {long long src, dst_f, dst_d; int N, K, T, kd, first_block, nblocks} (element offsets into arena / packed; K % 64 == 0,
+ * N % 16 == 0, T <= 16; nblocks = N / 16 * K / 64, first_block = their running sum); max_taps = the largest T. */
+int irc_pack_std(const float* arena, void* packed, const void* jobs, int njobs, int total_blocks, int max_taps, void* stream);
 /* dst[i] = sum_s src[s*split_stride + map[i]]: split weight-gradient partials -> OIHW fp32. */
 int irc_gather_sum(const float* src, const int* map, long long n, int splits, long long split_stride, float* dst, void* stream);
 /* The same for a table of jobs in ONE launch (all weight gradients of a network, irc:1650 / :1680).  `jobs_dev` is a DEVICE

@@ -21,7 +21,7 @@ EXPORTS = [
     "irc_in_stats", "irc_gather", "irc_in_apply_fused", "irc_in_bwd_reduce", "irc_in_bwd_apply", "irc_in_bwd_fused", "irc_in_bwd_l2", "irc_bn_finalize", "irc_bn_bwd_fix", "irc_maxpool2", "irc_maxpool2_bwd",
     "irc_colsum", "irc_im2col_rows", "irc_im2col", "irc_smallk_conv_fwd", "irc_col2im", "irc_tap_reduce", "irc_tap_expand",
     "irc_pixel_loss", "irc_ssim_fwd", "irc_ssim_bwd", "irc_hinge", "irc_feat_l1", "irc_quantize_metrics", "irc_ssim_metric",
-    "irc_adam", "irc_accumulate", "irc_gather_f32", "irc_convT2d_fwd", "irc_pack_bf16", "irc_gather_sum", "irc_gather_sum_multi", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
+    "irc_adam", "irc_accumulate", "irc_gather_f32", "irc_convT2d_fwd", "irc_pack_bf16", "irc_pack_std", "irc_gather_sum", "irc_gather_sum_multi", "irc_stencil_nchw", "irc_stencil_nchw_stream", "irc_fold_inplace",
     "irc_resize_area_u8", "irc_u8_to_pm1",
 ]
 
@@ -305,7 +305,7 @@ class CudaBackend:
         self.timers_all = []
         names = ["in_stats", "gather", "in_apply", "in_bwd", "fold_inplace", "maxpool2", "maxpool2_bwd", "colsum", "im2col", "col2im",
                  "tap_reduce", "tap_expand", "pixel_loss", "ssim_fwd", "ssim_bwd", "hinge", "feat_l1", "adam", "pack_bf16", "gather_sum",
-                 "conv_gemm", "tn_gemm", "zero_", "smallk_conv_fwd"]
+                 "conv_gemm", "tn_gemm", "zero_", "smallk_conv_fwd", "pack_std"]
         for name in names:
             orig = getattr(self, name)
 
@@ -635,6 +635,10 @@ class CudaBackend:
 
     def pack_bf16(self, src, map_, dst):
         check(self.L.irc_pack_bf16(_p(src), _p(map_), C.c_longlong(map_.numel()), _p(dst), _stream())); self.launches += 1
+
+    def pack_std(self, arena_flat, packed, jobs, njobs, total_blocks, max_taps):
+        """structured packing of the standard convolution layers (layout.Packer): jobs = uint8 device tensor of PackStdJob records"""
+        check(self.L.irc_pack_std(_p(arena_flat), _p(packed), _p(jobs), njobs, total_blocks, max_taps, _stream())); self.launches += 1
 
     def gather_sum(self, src, map_, splits, split_stride, dst):
         check(self.L.irc_gather_sum(_p(src), _p(map_), C.c_longlong(map_.numel()), splits, C.c_longlong(split_stride), _p(dst),

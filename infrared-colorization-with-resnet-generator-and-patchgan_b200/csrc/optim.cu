@@ -123,6 +123,54 @@ int grid_for(long long total, int threads) {
     return (int)b;
 }
 
+// ---------------------------------------------------------------------------------
+// Structured packing of standard convolution weights (OIHW fp32 -> the two bf16 GEMM operands)
+// ---------------------------------------------------------------------------------
+// The generic pack gathers every operand slot through an index map: 4 bytes of map per slot, and - because the forward operand
+// W_f[n][t][k] walks the OIHW tensor with a stride of kh*kw floats - one 32-byte sector per 4-byte read.  For the regular layers
+// (all 3 x 3 / 4 x 4 convolutions of the generator's trunk and model.8) the permutation is a small transpose: a block stages the
+// [16 output channels][64 input channels][T taps] slab of one layer with coalesced reads and writes whole 128-byte rows of W_f and
+// 32-byte runs of the data-gradient operand W_d[k][t][n].  One launch covers every layer of a network through a job table.
+struct PackStdJob { long long src, dst_f, dst_d; int N, K, T, kd, first_block, nblocks; };
+
+__global__ void __launch_bounds__(256) pack_std_kernel(const float* __restrict__ arena, bf16* __restrict__ packed, const PackStdJob* __restrict__ jobs, int njobs) {
+    irc::pdl_prologue();
+    extern __shared__ float slab[];           // [16][64 * T + 1]
+    int j = 0;
+    while (j + 1 < njobs && (int)blockIdx.x >= jobs[j + 1].first_block) ++j;
+    const PackStdJob job = jobs[j];
+    const int b = blockIdx.x - job.first_block;
+    const int kblocks = job.K >> 6;
+    const int n0 = (b / kblocks) * 16, k0 = (b % kblocks) * 64;
+    const int T = job.T, run = 64 * T, pitch = run + 1;
+    // OIHW: element (n, k, t) at src + (n * K + k) * T + t; for fixed n the 64 k x T taps are one contiguous run
+    for (int i = threadIdx.x; i < 16 * run; i += 256) {
+        const int nn = i / run, r = i - nn * run;
+        slab[nn * pitch + r] = (n0 + nn < job.N) ? __ldg(arena + job.src + ((long long)(n0 + nn) * job.K + k0) * T + r) : 0.f;
+    }
+    __syncthreads();
+    // W_f[n][t * K + k]: rows of 64 k (128 bytes) per (n, t); one thread writes 8 k
+    for (int i = threadIdx.x; i < 16 * T * 8; i += 256) {
+        const int kg = i & 7, t = (i >> 3) % T, nn = (i >> 3) / T;
+        if (n0 + nn >= job.N) continue;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = slab[nn * pitch + (kg * 8 + q) * T + t];
+        *reinterpret_cast<uint4*>(packed + job.dst_f + ((long long)(n0 + nn) * T + t) * job.K + k0 + kg * 8) =
+            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+    // W_d[k][t * kd + n]: runs of 16 n (32 bytes) per (k, t); one thread writes 8 n
+    for (int i = threadIdx.x; i < 64 * T * 2; i += 256) {
+        const int ng = i & 1, t = (i >> 1) % T, kk = (i >> 1) / T;
+        if (n0 + ng * 8 >= job.N) continue;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = slab[(ng * 8 + q) * pitch + kk * T + t];
+        *reinterpret_cast<uint4*>(packed + job.dst_d + ((long long)(k0 + kk) * T + t) * job.kd + n0 + ng * 8) =
+            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+}
+
 }  // namespace
 
 extern "C" int irc_adam(float* p, const float* g, float* m, float* v, long long n, const double* hyper, long long* step_count, void* stream) {
@@ -158,4 +206,17 @@ extern "C" int irc_gather_f32(const float* src, const int* map, long long n, flo
     if (!src || !map || !dst) return irc_set_error(IRC_ERR_BAD_ARG, "irc_gather_f32: null");
     irc::launch(gather_f32_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, src, map, n, dst);
     return irc_check_launch("irc_gather_f32");
+}
+
+/* Structured packing of standard convolution layers (see pack_std_kernel): jobs = device array of `njobs` records
+ * {long long src, dst_f, dst_d; int N, K, T, kd, first_block, nblocks} (element offsets into `arena` / `packed`; K % 64 == 0,
+ * N % 8 == 0, T <= 16; first_block = running sum of nblocks = ceil(N / 16) * (K / 64)); total_blocks = their sum. */
+extern "C" int irc_pack_std(const float* arena, void* packed, const void* jobs, int njobs, int total_blocks, int max_taps, void* stream) {
+    if (!arena || !packed || !jobs || njobs <= 0 || total_blocks <= 0 || max_taps <= 0 || max_taps > 16)
+        return irc_set_error(IRC_ERR_BAD_ARG, "irc_pack_std: bad args");
+    const size_t smem = (size_t)16 * (64 * max_taps + 1) * sizeof(float);
+    static size_t attr = 48 * 1024;
+    if (smem > attr) { cudaFuncSetAttribute(pack_std_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024); attr = 80 * 1024; }
+    irc::launch(pack_std_kernel, total_blocks, 256, smem, (cudaStream_t)stream, arena, (bf16*)packed, (const PackStdJob*)jobs, njobs);
+    return irc_check_launch("irc_pack_std");
 }

@@ -185,41 +185,77 @@ class ParamArena:
 class PackedOperand:
     """A bf16 GEMM operand [rows, cols] filled from the arena through an index map."""
 
-    def __init__(self, index: np.ndarray):
+    def __init__(self, index: np.ndarray, std=None):
         self.index = index.astype(np.int64)     # [rows, cols] arena indices, -1 = zero
         self.rows, self.cols = index.shape
+        self.std = std                          # ("f" | "d", src offset, N, K, T, kd) for the operands of a standard layer
         self.t: torch.Tensor = None             # set by Packer.finish
 
 
 class Packer:
-    """Collects the packed operands of one network; one irc_pack_bf16 launch refreshes them all."""
+    """Collects the packed operands of one network.  Refresh = one irc_pack_bf16 launch through an index map for the irregular
+    operands + one irc_pack_std launch (shared-memory transposes, no map) for the two operands of every standard convolution."""
 
     def __init__(self, arena: ParamArena):
         self.arena = arena
         self.ops: List[PackedOperand] = []
 
-    def add(self, index: np.ndarray) -> PackedOperand:
-        op = PackedOperand(index)
+    def add(self, index: np.ndarray, std=None) -> PackedOperand:
+        op = PackedOperand(index, std)
         self.ops.append(op)
         return op
 
     def finish(self) -> None:
         dev = self.arena.device
-        offs, total = [], 0
-        for op in self.ops:
-            offs.append(total)
+        order = [op for op in self.ops if op.std is None] + [op for op in self.ops if op.std is not None]      # map-packed operands first
+        offs, total = {}, 0
+        for op in order:
+            offs[id(op)] = total
             total += (op.rows * op.cols + 63) // 64 * 64
-        m = np.full(total, -1, np.int64)
-        for op, o in zip(self.ops, offs):
-            m[o:o + op.rows * op.cols] = op.index.reshape(-1)
-        assert m.max() < 2 ** 31
+            if op.std is None:
+                self.n_mapped = total
+        if not any(op.std is None for op in order):
+            self.n_mapped = 0
+        self._offs, self._order, self._full_map = offs, order, None
+        m = np.full(self.n_mapped, -1, np.int64)
+        for op in order:
+            if op.std is None:
+                o = offs[id(op)]
+                m[o:o + op.rows * op.cols] = op.index.reshape(-1)
+        assert m.size == 0 or m.max() < 2 ** 31
         self.map = torch.from_numpy(m.astype(np.int32)).to(dev)
         self.packed = torch.zeros(total, device=dev, dtype=ACT_DTYPE)
-        for op, o in zip(self.ops, offs):
+        for op in order:
+            o = offs[id(op)]
             op.t = self.packed[o:o + op.rows * op.cols].view(op.rows, op.cols)
+        # job table of the structured launch: one record per standard layer (its forward and data-gradient operands)
+        layers = {}
+        for op in order:
+            if op.std is not None:
+                kind, src, N, K, T, kd = op.std
+                layers.setdefault((src, N, K, T, kd), {})[kind] = offs[id(op)]
+        recs, first = [], 0
+        for (src, N, K, T, kd), d in layers.items():
+            nb = (N // 16) * (K // 64)
+            recs.append(np.array([src, d["f"], d["d"]], np.int64).tobytes() + np.array([N, K, T, kd, first, nb], np.int32).tobytes())
+            first += nb
+        self.n_jobs, self.job_blocks = len(recs), first
+        self.max_taps = max((k[3] for k in layers), default=0)
+        self.jobs = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(dev) if recs else None
 
     def refresh(self, be) -> None:
-        be.pack_bf16(self.arena.flat, self.map, self.packed)
+        if self.n_jobs and hasattr(be, "pack_std") and self.packed.dtype == torch.bfloat16:
+            if self.n_mapped:
+                be.pack_bf16(self.arena.flat, self.map, self.packed[:self.n_mapped])
+            be.pack_std(self.arena.flat, self.packed, self.jobs, self.n_jobs, self.job_blocks, self.max_taps)
+            return
+        if self._full_map is None:                  # backends without the structured kernel: everything through the map
+            m = np.full(self.packed.numel(), -1, np.int64)
+            for op in self._order:
+                o = self._offs[id(op)]
+                m[o:o + op.rows * op.cols] = op.index.reshape(-1)
+            self._full_map = torch.from_numpy(m.astype(np.int32)).to(self.arena.device)
+        be.pack_bf16(self.arena.flat, self._full_map, self.packed)
 
 
 def oihw_index(base: int, co, ci, r, s, Cin: int, KH: int, KW: int):
@@ -236,15 +272,17 @@ class WeightLayout:
       weight-grad partial layout [n][t][k]   (what irc_tn_gemm writes), inverted by `unpack`."""
 
     def __init__(self, packer: Packer, fwd_index: np.ndarray, param_offset: int, param_numel: int, n_pad: int = None,
-                 k_pad_d: int = None):
+                 k_pad_d: int = None, std: bool = False):
         N, T, K = fwd_index.shape
         self.N, self.T, self.K = N, T, K
         n_pad = n_pad or N
         f = np.full((n_pad, T, K), -1, np.int64); f[:N] = fwd_index
-        self.w_f = packer.add(f.reshape(n_pad, T * K))
         kd = k_pad_d or N                      # reduction width of the data-grad GEMM (multiple of 64)
+        # `std`: the plain OIHW -> [n][t][k] / [k][t][n] permutation of a standard layer, packed without an index map
+        std = std and n_pad == N and kd == N and N % 16 == 0 and K % 64 == 0 and T <= 16
+        self.w_f = packer.add(f.reshape(n_pad, T * K), std=("f", param_offset, N, K, T, kd) if std else None)
         d = np.full((K, T, kd), -1, np.int64); d[:, :, :N] = np.transpose(fwd_index, (2, 1, 0))
-        self.w_d = packer.add(d.reshape(K, T * kd))
+        self.w_d = packer.add(d.reshape(K, T * kd), std=("d", param_offset, N, K, T, kd) if std else None)
         self.kd = kd
         # inverse map: OIHW element -> position in the [N][T][K] partial
         inv = np.full(param_numel, -1, np.int64)
@@ -259,7 +297,7 @@ class WeightLayout:
 def layout_std(packer, arena, name, Cout, Cin, KH, KW) -> WeightLayout:
     co, r, s, ci = np.meshgrid(np.arange(Cout), np.arange(KH), np.arange(KW), np.arange(Cin), indexing="ij")
     idx = oihw_index(arena.offset[name], co, ci, r, s, Cin, KH, KW).reshape(Cout, KH * KW, Cin)
-    return WeightLayout(packer, idx, arena.offset[name], arena.numel(name))
+    return WeightLayout(packer, idx, arena.offset[name], arena.numel(name), std=True)
 
 
 def layout_s2d(packer, arena, name, Cout, Cin) -> WeightLayout:

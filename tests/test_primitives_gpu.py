@@ -487,6 +487,39 @@ def test_batch_norm_on_the_instance_norm_kernels(bes, training):
         close(a[2], rm, 1e-5, "running_mean vs torch"); close(a[3], rv, 1e-5, "running_var vs torch")
 
 
+def test_structured_weight_packing_equals_the_index_map():
+    """irc_pack_std (shared-memory transposes of the standard layers, no index map) fills the forward and data-gradient operands with
+    exactly the bits irc_pack_bf16 produces through the host-built index maps; irregular layouts keep the map"""
+    import irc_b200  # noqa: F401
+    from irc_b200 import layout as L
+    from irc_b200._native import CudaBackend
+    be = CudaBackend()
+    shapes = {"a.weight": (128, 64, 3, 3), "b.weight": (256, 128, 3, 3), "c.weight": (512, 256, 4, 4), "d.weight": (64, 192, 3, 3),
+              "e.weight": (64, 1, 7, 7), "f.weight": (3, 64, 7, 7), "g.weight": (128, 64, 4, 4)}
+    arena = L.ParamArena(shapes, "cuda")
+    arena.flat.normal_(generator=gen(41))
+    P = L.Packer(arena)
+    lays = [L.layout_std(P, arena, "a.weight", 128, 64, 3, 3), L.layout_std(P, arena, "b.weight", 256, 128, 3, 3),
+            L.layout_im2col(P, arena, "e.weight", 64, 1, 7), L.layout_std(P, arena, "c.weight", 512, 256, 4, 4),
+            L.layout_outc(P, arena, "f.weight", 3, 64, 7), L.layout_std(P, arena, "d.weight", 64, 192, 3, 3), L.layout_s2d(P, arena, "g.weight", 128, 64)]
+    P.finish()
+    assert P.n_jobs == 4 and P.n_mapped > 0
+    P.refresh(be)
+    torch.cuda.synchronize()
+    got = P.packed.clone()
+    for lay in lays:
+        for op in (lay.w_f, lay.w_d):
+            idx = torch.from_numpy(op.index).cuda()
+            want = torch.where(idx >= 0, arena.flat[idx.clamp_min(0)], torch.zeros((), device="cuda")).bfloat16()
+            assert torch.equal(op.t, want), (op.rows, op.cols, op.std)
+    # everything through the map gives the same buffer
+    P.n_jobs = 0
+    P.packed.zero_()
+    P.refresh(be)
+    torch.cuda.synchronize()
+    assert torch.equal(P.packed, got)
+
+
 def test_taps(bes):
     g = gen(7)
     n, H, W, p = 2, 10, 12, 3
