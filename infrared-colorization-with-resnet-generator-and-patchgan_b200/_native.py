@@ -116,7 +116,7 @@ class SumJob(C.Structure):
 class TapArgs(C.Structure):
     _fields_ = [("nshift", C.c_int), ("nco", C.c_int), ("dy", C.c_int * MAX_TAPS), ("dx", C.c_int * MAX_TAPS),
                 ("n_img", C.c_int), ("H", C.c_int), ("W", C.c_int), ("hp", C.c_int), ("wp", C.c_int),
-                ("oy", C.c_int), ("ox", C.c_int)]
+                ("oy", C.c_int), ("ox", C.c_int), ("live_cols_only", C.c_int)]
 
 
 _lib = None
@@ -573,8 +573,10 @@ class CudaBackend:
         t = self._tap(shifts, nco, n_img, H, W, hp, wp, oy, ox)
         check(self.L.irc_tap_reduce(C.byref(t), _p(P), C.c_longlong(P.shape[1]), _p(bias), act, _p(out), _stream())); self.launches += 1
 
-    def tap_expand(self, g, y, shifts, nco, n_img, H, W, hp, wp, oy, ox, E, dbias=None):
+    def tap_expand(self, g, y, shifts, nco, n_img, H, W, hp, wp, oy, ox, E, dbias=None, live_cols_only=False):
+        """live_cols_only: E's columns beyond the tap columns (rounded up to 8) are never written - the caller's buffer holds zeros there"""
         t = self._tap(shifts, nco, n_img, H, W, hp, wp, oy, ox)
+        t.live_cols_only = int(bool(live_cols_only))
         assert E.shape == (n_img * hp * wp, 64)
         check(self.L.irc_tap_expand(C.byref(t), _p(g), _p(y), _p(E), _p(dbias), _p(self.work), C.c_longlong(self.work.numel()), _stream()))
         self.launches += 1 if dbias is None else 3

@@ -448,6 +448,7 @@ struct TapP {
     int shifts[IRC_MAX_TAPS];
     signed char dy[IRC_MAX_TAPS], dx[IRC_MAX_TAPS];   // shift = dy*wp + dx with |dx| < wp/2
     int n_img, H, W, hp, wp, oy, ox;
+    int live_cols_only;      // 1: only the 16-byte column groups that hold tap columns are written (the rest stays as the caller zeroed it)
 };
 
 // out[n][co][y][x] = act(bias[co] + sum_j P[q + shift_j][j*nco + co])
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(256) tap_reduce_kernel(const float* P, long lo
 // E[q][j*nco + co] = g'[pixel(q - shift_j)][co];  g' = g * (1 - yv^2) when yv is given (tanh').
 // A shifted position that leaves its frame line lands in the padding ring (the ring is at least as wide as the
 // largest horizontal shift), i.e. on a zero, so the (dy, dx) decomposition needs no wrap-around handling.
-__global__ void __launch_bounds__(256) tap_expand_kernel(const float* g, const float* yv, bf16* E, const TapP t, int ndy) {
+__global__ void __launch_bounds__(256) tap_expand_kernel(const float* g, const float* yv, bf16* E, const TapP t, int ndy, float* rowsum) {
     irc::pdl_prologue();
     // One block per (image, padded row).  The <= 8 distinct source rows the taps of this row read (one per distinct dy) are
     // staged in shared memory as g' = g * (1 - y^2), all channels, zero where the row falls outside the image; a thread
@@ -507,13 +508,22 @@ __global__ void __launch_bounds__(256) tap_expand_kernel(const float* g, const f
             const int y = Y - s_dy[sl] - t.oy;
             const bool ok = y >= 0 && y < t.H;
             const long long o = ((long long)n * t.nco + co) * hw + (long long)(ok ? y : 0) * t.W;
+            float acc = 0.f;
             for (int x = threadIdx.x & 31; x < t.W; x += 32) {
                 float v = 0.f;
                 if (ok) { v = __ldg(g + o + x); if (yv) { const float yy = __ldg(yv + o + x); v *= (1.f - yy * yy); } }
                 T[r * t.W + x] = v;
+                acc += v;
+            }
+            // bias gradient: every image row is staged exactly once in the slot of the first vertical shift (host-checked), so the
+            // per-(frame row, channel) sums of that slot add up to sum g' over the image; irc_tap_expand adds them in a fixed order
+            if (rowsum && sl == 0) {
+                acc = warp_sum(acc);
+                if ((threadIdx.x & 31) == 0) rowsum[(long long)row * t.nco + co] = acc;
             }
         }
         __syncthreads();
+        if (t.live_cols_only && !valid) continue;        // (uniform per 8-column group; the next iteration's barrier still sees every thread)
         for (int X = threadIdx.x >> 3; X < t.wp; X += blockDim.x >> 3) {
             float v[8];
 #pragma unroll
@@ -544,6 +554,23 @@ __global__ void chan_sum_kernel(const float* g, const float* yv, int n_img, int 
     }
     s = block_sum(s, sh);
     if (threadIdx.x == 0) part[(long long)blockIdx.x * C + c] = s;
+}
+// out[c] = sum over the rows of part[row][c]: thread t adds rows t, t + 1024, ... in order, then a fixed tree over the 1024 partials
+__global__ void __launch_bounds__(1024) rowsum_final_kernel(const float* __restrict__ part, int nrows, int C, float* __restrict__ out) {
+    irc::pdl_prologue();
+    __shared__ float sh[1024];
+    for (int c = 0; c < C; ++c) {
+        float a = 0.f;
+        for (int r = threadIdx.x; r < nrows; r += 1024) a += part[(long long)r * C + c];
+        sh[threadIdx.x] = a;
+        __syncthreads();
+        for (int o = 512; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[c] = sh[0];
+        __syncthreads();
+    }
 }
 __global__ void chan_sum_final(const float* part, int nb, int C, float* out) {
     irc::pdl_prologue();
@@ -684,6 +711,7 @@ static int fill_tap(const irc_tap_args* a, TapP& t) {
         t.dy[i] = (signed char)dy; t.dx[i] = (signed char)dx;
     }
     t.n_img = a->n_img; t.H = a->H; t.W = a->W; t.hp = a->hp; t.wp = a->wp; t.oy = a->oy; t.ox = a->ox;
+    t.live_cols_only = a->live_cols_only;
     return IRC_OK;
 }
 
@@ -709,9 +737,18 @@ extern "C" int irc_tap_expand(const irc_tap_args* a, const float* g, const float
     }
     const size_t smem = (size_t)ndy * t.nco * t.W * sizeof(float);
     if (smem > 48 * 1024) return irc_set_error(IRC_ERR_BAD_ARG, "irc_tap_expand: row tile does not fit shared memory");
-    irc::launch(tap_expand_kernel, (unsigned)(nrow < 1048576 ? nrow : 1048576), 256, smem, (cudaStream_t)stream, g, y, (bf16*)E, t, ndy);
+    // a block pays ~250 instructions per thread of column decoding before its first row: let it walk several rows
+    const long long cap = 8LL * irc_num_sms();
+    // bias gradient from the staged rows (no second read of g and y) when every image row is staged exactly once under the first
+    // vertical shift, i.e. its frame row y + dy0 + oy exists for all y, and the workspace holds one partial per (frame row, channel)
+    const int dy0 = t.dy[0];
+    const bool fused_dbias = dbias && work && work_floats >= nrow * t.nco && dy0 + t.oy >= 0 && t.H - 1 + dy0 + t.oy < t.hp;
+    irc::launch(tap_expand_kernel, (unsigned)(nrow < cap ? nrow : cap), 256, smem, (cudaStream_t)stream, g, y, (bf16*)E, t, ndy, fused_dbias ? work : nullptr);
     rc = irc_check_launch("irc_tap_expand"); if (rc) return rc;
-    if (dbias) {
+    if (fused_dbias) {
+        irc::launch(rowsum_final_kernel, 1, 1024, 0, (cudaStream_t)stream, (const float*)work, (int)nrow, t.nco, dbias);
+        rc = irc_check_launch("irc_tap_expand(dbias)");
+    } else if (dbias) {
         const long long hw = (long long)t.H * t.W;
         long long nb = ((long long)t.n_img * hw + 4095) / 4096;
         if (nb > 512) nb = 512;

@@ -528,7 +528,7 @@ class GeneratorEngine:
         y4 = self.y4
         # outc: tanh' and horizontal tap expansion, then weight / data gradients over the vertical taps
         be.tap_expand(dfake, self.fake, self.outc_shifts, 3, B, H, W, y4.hp, y4.wp, 3, 3, self.E_out,
-                      dbias=self.arena.view("outc.1.bias", self.arena.grad))
+                      dbias=self.arena.view("outc.1.bias", self.arena.grad), live_cols_only=True)      # E_out's other columns stay zero
         self.outc.wgrad(self.E_out, y4.t, 0, y4.rows)
         self.outc.dgrad(self.E_out, self.G4.t)
         # up2_conv
@@ -792,7 +792,7 @@ class DiscriminatorEngine:
         be, n = self.be, self.n
         G = self.arena.grad
         be.tap_expand(dpred, None, self.shifts11, 1, n, self.Ho, self.Wo, self.X11.hp, self.X11.wp, 0, 0, self.E11,
-                      dbias=self.arena.view("model.11.bias", G) if want_wgrad else None)
+                      dbias=self.arena.view("model.11.bias", G) if want_wgrad else None, live_cols_only=True)
         if want_wgrad:
             self.c11.wgrad(self.E11, self.X11.t, 0, self.X11.rows)
         self.c11.dgrad(self.E11, self.G11.t)

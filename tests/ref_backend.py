@@ -381,7 +381,7 @@ class RefBackend:
             acc = torch.tanh(acc)
         out.copy_(acc.permute(0, 3, 1, 2))
 
-    def tap_expand(self, g, y, shifts, nco, n_img, H, W, hp, wp, oy, ox, E, dbias=None):
+    def tap_expand(self, g, y, shifts, nco, n_img, H, W, hp, wp, oy, ox, E, dbias=None, live_cols_only=False):
         self.launches += 1
         dev = g.device
         gp = g if y is None else g * (1 - y * y)

@@ -28,7 +28,7 @@ def test_struct_sizes_match_header():
     """ctypes mirrors of the argument structs must have the C layout (spot-check through sizeof arithmetic)."""
     from irc_b200 import _native as n
     assert ctypes.sizeof(n.CView) == 40
-    assert ctypes.sizeof(n.TapArgs) == 4 * (2 + 128 + 7)
+    assert ctypes.sizeof(n.TapArgs) == 4 * (2 + 128 + 8)
     assert ctypes.sizeof(n.ConvGemmArgs) % 8 == 0 and ctypes.sizeof(n.TnGemmArgs) % 8 == 0
 
 
