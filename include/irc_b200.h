@@ -257,7 +257,8 @@ typedef struct irc_tap_args {
     int nshift, nco;
     int dy[IRC_MAX_TAPS], dx[IRC_MAX_TAPS];
     int n_img, H, W, hp, wp, oy, ox;
-    int live_cols_only;     /* expand: write only the 16-byte column groups that hold tap columns; the caller keeps the others zero */
+    int live_cols_only;     /* expand: write only the 32-byte column sectors that hold tap columns (zero-filled up to the sector end);
+                             * the caller keeps the other columns zero */
 } irc_tap_args;
 int irc_tap_reduce(const irc_tap_args* t, const float* P, long long ldp, const float* bias, int act, float* out, void* stream);
 int irc_tap_expand(const irc_tap_args* t, const float* g, const float* y, void* E, float* dbias, float* work, long long work_floats,

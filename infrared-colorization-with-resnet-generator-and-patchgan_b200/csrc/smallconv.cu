@@ -503,23 +503,40 @@ __global__ void __launch_bounds__(256) tap_expand_kernel(const float* g, const f
     for (int row = blockIdx.x; row < t.n_img * t.hp; row += gridDim.x) {
         const int n = row / t.hp, Y = row - n * t.hp;
         __syncthreads();
-        for (int r = threadIdx.x >> 5; r < ndy * t.nco; r += blockDim.x >> 5) {
-            const int sl = r / t.nco, co = r - sl * t.nco;
-            const int y = Y - s_dy[sl] - t.oy;
-            const bool ok = y >= 0 && y < t.H;
-            const long long o = ((long long)n * t.nco + co) * hw + (long long)(ok ? y : 0) * t.W;
-            float acc = 0.f;
-            for (int x = threadIdx.x & 31; x < t.W; x += 32) {
-                float v = 0.f;
-                if (ok) { v = __ldg(g + o + x); if (yv) { const float yy = __ldg(yv + o + x); v *= (1.f - yy * yy); } }
-                T[r * t.W + x] = v;
-                acc += v;
+        // staging with ALL threads and every global load of the row in flight at once (a warp per source row made the 8 dependent
+        // load latencies of its row the critical path: 45 % barrier stalls, profiles/r3); the row sums come from shared memory after
+        const int tot = ndy * t.nco * t.W;
+        for (int e0 = threadIdx.x; e0 < tot; e0 += 4 * 256) {
+            float gv[4], yy[4]; int er[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 256;
+                gv[u] = 0.f; yy[u] = 0.f; er[u] = -1;
+                if (e < tot) {
+                    const int r = e / t.W, x = e - r * t.W;
+                    const int sl = r / t.nco, co = r - sl * t.nco;
+                    const int y = Y - s_dy[sl] - t.oy;
+                    er[u] = e;
+                    if (y >= 0 && y < t.H) {
+                        const long long o = ((long long)n * t.nco + co) * hw + (long long)y * t.W + x;
+                        gv[u] = __ldg(g + o);
+                        if (yv) yy[u] = __ldg(yv + o);
+                    }
+                }
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (er[u] >= 0) T[er[u]] = gv[u] * (1.f - yy[u] * yy[u]);
+        }
+        if (rowsum) {
+            __syncthreads();
             // bias gradient: every image row is staged exactly once in the slot of the first vertical shift (host-checked), so the
             // per-(frame row, channel) sums of that slot add up to sum g' over the image; irc_tap_expand adds them in a fixed order
-            if (rowsum && sl == 0) {
+            const int r = threadIdx.x >> 5;
+            if (r < t.nco) {
+                float acc = 0.f;
+                for (int x = threadIdx.x & 31; x < t.W; x += 32) acc += T[r * t.W + x];
                 acc = warp_sum(acc);
-                if ((threadIdx.x & 31) == 0) rowsum[(long long)row * t.nco + co] = acc;
+                if ((threadIdx.x & 31) == 0) rowsum[(long long)row * t.nco + r] = acc;
             }
         }
         __syncthreads();
@@ -533,6 +550,77 @@ __global__ void __launch_bounds__(256) tap_expand_kernel(const float* g, const f
             }
             *reinterpret_cast<uint4*>(E + ((long long)row * t.wp + X) * 64 + grp * 8) =
                 make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+    }
+}
+
+// Horizontal taps only (one vertical shift), NS x NCO <= 24 columns known at compile time - the backward expansion of the generator's
+// output head (7 taps x 3 channels, irc:527-531).  One thread = one frame pixel: per tap one bounds test and NCO shared-memory reads
+// at compile-time register positions, three 16-byte stores (the generic kernel spends ~180 instructions per 8-column group on
+// per-column predicates: 62 us, issue-bound, profiles/r3).  Blocks walk frame rows; staging as in the generic kernel.
+template <int NS, int NCO>
+__global__ void __launch_bounds__(256) tap_expand_row_kernel(const float* __restrict__ g, const float* __restrict__ yv, bf16* __restrict__ E, const TapP t,
+                                                             float* rowsum) {
+    irc::pdl_prologue();
+    extern __shared__ float T[];                 // [NCO][W]
+    constexpr int NV = (NS * NCO + 7) / 8;       // 16-byte groups that hold tap columns
+    const long long hw = (long long)t.H * t.W;
+    const int dy0 = t.dy[0];
+    for (int row = blockIdx.x; row < t.n_img * t.hp; row += gridDim.x) {
+        const int n = row / t.hp, Y = row - n * t.hp;
+        const int y = Y - dy0 - t.oy;
+        const bool ok = y >= 0 && y < t.H;
+        __syncthreads();
+        const int tot = NCO * t.W;
+        for (int e0 = threadIdx.x; e0 < tot; e0 += 4 * 256) {
+            float gv[4], yy[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 256;
+                gv[u] = 0.f; yy[u] = 0.f;
+                if (ok && e < tot) {
+                    const int co = e / t.W, x = e - co * t.W;
+                    const long long o = ((long long)n * NCO + co) * hw + (long long)y * t.W + x;
+                    gv[u] = __ldg(g + o);
+                    if (yv) yy[u] = __ldg(yv + o);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (e0 + u * 256 < tot) T[e0 + u * 256] = gv[u] * (1.f - yy[u] * yy[u]);
+        }
+        __syncthreads();
+        if (rowsum && (threadIdx.x >> 5) < NCO) {
+            const int r = threadIdx.x >> 5;
+            float acc = 0.f;
+            for (int x = threadIdx.x & 31; x < t.W; x += 32) acc += T[r * t.W + x];
+            acc = warp_sum(acc);
+            if ((threadIdx.x & 31) == 0) rowsum[(long long)row * NCO + r] = acc;
+        }
+        for (int X = threadIdx.x; X < t.wp; X += 256) {
+            float v[NV * 8];
+#pragma unroll
+            for (int i = 0; i < NV * 8; ++i) v[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                const int x = X - t.dx[j] - t.ox;
+                if (x >= 0 && x < t.W) {
+#pragma unroll
+                    for (int co = 0; co < NCO; ++co) v[j * NCO + co] = T[co * t.W + x];
+                }
+            }
+            uint4* ep = reinterpret_cast<uint4*>(E + ((long long)row * t.wp + X) * 64);
+#pragma unroll
+            for (int q = 0; q < NV; ++q)
+                ep[q] = make_uint4(pack_bf16x2(v[q * 8], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]), pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]),
+                                   pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+            // whole 32-byte sectors: a half-written sector costs the L2 a read-modify-write
+            constexpr int NVS = (NV + 1) & ~1;
+#pragma unroll
+            for (int q = NV; q < (NVS < 8 ? NVS : 8); ++q) ep[q] = make_uint4(0, 0, 0, 0);
+            if (!t.live_cols_only) {
+#pragma unroll
+                for (int q = NVS; q < 8; ++q) ep[q] = make_uint4(0, 0, 0, 0);
+            }
         }
     }
 }
@@ -742,8 +830,11 @@ extern "C" int irc_tap_expand(const irc_tap_args* a, const float* g, const float
     // bias gradient from the staged rows (no second read of g and y) when every image row is staged exactly once under the first
     // vertical shift, i.e. its frame row y + dy0 + oy exists for all y, and the workspace holds one partial per (frame row, channel)
     const int dy0 = t.dy[0];
-    const bool fused_dbias = dbias && work && work_floats >= nrow * t.nco && dy0 + t.oy >= 0 && t.H - 1 + dy0 + t.oy < t.hp;
-    irc::launch(tap_expand_kernel, (unsigned)(nrow < cap ? nrow : cap), 256, smem, (cudaStream_t)stream, g, y, (bf16*)E, t, ndy, fused_dbias ? work : nullptr);
+    const bool fused_dbias = dbias && work && work_floats >= nrow * t.nco && t.nco <= 8 && dy0 + t.oy >= 0 && t.H - 1 + dy0 + t.oy < t.hp;
+    if (ndy == 1 && t.nshift == 7 && t.nco == 3)
+        irc::launch(tap_expand_row_kernel<7, 3>, (unsigned)(nrow < cap ? nrow : cap), 256, smem, (cudaStream_t)stream, g, y, (bf16*)E, t, fused_dbias ? work : nullptr);
+    else
+        irc::launch(tap_expand_kernel, (unsigned)(nrow < cap ? nrow : cap), 256, smem, (cudaStream_t)stream, g, y, (bf16*)E, t, ndy, fused_dbias ? work : nullptr);
     rc = irc_check_launch("irc_tap_expand"); if (rc) return rc;
     if (fused_dbias) {
         irc::launch(rowsum_final_kernel, 1, 1024, 0, (cudaStream_t)stream, (const float*)work, (int)nrow, t.nco, dbias);
