@@ -1651,7 +1651,9 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
         irc::launch<1>(conv_gemm_pack_kernel, (int)(tiles_p < sms ? tiles_p : sms), kConvThreads, smem2, (cudaStream_t)stream, tmOut126, tmA1, tmB64, q, pk);
         return irc_check_launch("irc_conv_gemm(packed taps)");
     }
-    const bool runs_auto = max_len > 1 && !pair_auto && bn <= 128 && a->a_rows >= (long long)sms * 128;
+    // (128 output columns: only with one channel chunk per tap - measured, same box: conv2_1 forward 109 -> 101 us, but conv2_2
+    // forward, two chunks, 143 -> 156..168 us)
+    const bool runs_auto = max_len > 1 && !pair_auto && (bn <= 64 || (bn <= 128 && a->cin == 64)) && a->a_rows >= (long long)sms * 128;
     if (max_len > 1 && !tapsum && (a->reuse == 1 || a->reuse == 3 || (a->reuse < 0 && runs_auto))) {
         rp.a_stage_bytes = (kBM * mt + 8) * 128;
         rp.base_off_mode = a->reuse == 3 ? 1 : 0;      // 3 = the (wrong) base-offset encoding, kept for the experiment script
