@@ -25,6 +25,7 @@ class Cfg:
 
 def rel(a, b):
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape and b.norm() > 0, (a.shape, b.shape)          # a comparison of two empty / all-zero tensors proves nothing
     return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
 
 
@@ -395,3 +396,299 @@ def check_outc_7x7_tanh(ctx):
     e = rel(eng.arena.view("outc.1.bias", eng.arena.grad), gb); print("outc bias grad", e); assert e < TOL
     e = rel(eng.arena.view("outc.1.weight", eng.arena.grad), gw); print("outc wgrad", e); assert e < TOL
     e = rel(get(eng.G4, 64, full=True), gxp); print("outc dgrad (frame)", e); assert e < TOL
+
+
+# ==========================================================================================================
+# PatchGAN discriminator and VGG trunk: the same per-layer teacher forcing (every launch of
+# DiscriminatorEngine.forward / .backward and VggEngine.forward / .backward, fed the oracle's tensors)
+# ==========================================================================================================
+def putv(v, x):
+    """NCHW fp32 -> pixels (0..h, 0..w) of a View (plain or space-to-depth), other elements untouched"""
+    from ref_backend import RefBackend
+    n, c, h, w = x.shape
+    dev = v.t.device
+    RefBackend()._write(v, n, torch.arange(h, device=dev), torch.arange(w, device=dev), c, x.permute(0, 2, 3, 1).to(dev))
+
+
+def getv(v, n, c, h, w):
+    from ref_backend import RefBackend
+    dev = v.t.device
+    return RefBackend()._read(v, n, torch.arange(h, device=dev), torch.arange(w, device=dev), c).permute(0, 3, 1, 2).float().cpu()
+
+
+def conv_s(x, w, dz, stride=1, pad=0, bias=None):
+    """fp32 CPU strided conv and its vector-Jacobian products (dz may be None: forward only)"""
+    x = x.clone().requires_grad_(True); w = w.clone().requires_grad_(True)
+    z = F.conv2d(x, w, bias, stride=stride, padding=pad)
+    if dz is None:
+        return z.detach(), None, None
+    gx, gw = torch.autograd.grad(z, (x, w), dz)
+    return z.detach(), gx, gw
+
+
+def in_lrelu_local(z, g, O):
+    z = z.clone().requires_grad_(True)
+    a = F.leaky_relu(O.instance_norm(z), 0.2)
+    dz = torch.autograd.grad(a, z, g)[0] if g is not None else None
+    return a.detach(), dz
+
+
+def make_dv_ctx(be):
+    """oracle forward / backward of the PatchGAN on (ir, rgb) + (ir, fake) and of the VGG trunk on (fake, rgb), every tap's
+    gradient retained; engines with the same weights"""
+    import irc_oracle as O
+    import irc_b200  # noqa: F401
+    from irc_b200 import engine as E
+    B, H, W = Cfg.B, Cfg.H, Cfg.W
+    pD = O.seeded_params(O.discriminator_shapes(), 1235, bias_std=0.02)
+    pV = O.seeded_params(O.vgg_shapes(), 1236, kaiming=True, bias_std=0.05)
+    ir, rgb = O.synthetic_pair(B, H, W)
+    _, fake = O.synthetic_pair(B, H, W, rank=3)
+    fake = (0.6 * fake + 0.4 * rgb).contiguous()
+    c = Ctx()
+    c.O, c.E, c.be = O, E, be
+    c.pD, c.pV, c.ir, c.rgb, c.fake = pD, pV, ir, rgb, fake
+    # ---- discriminator
+    xd = torch.cat([torch.cat([ir, rgb], 1), torch.cat([ir, fake], 1)], 0).requires_grad_(True)
+    taps = {}
+    pred = O.discriminator_forward(pD, xd, taps=taps)
+    for t in taps.values():
+        t.retain_grad()
+    c.g_pred = scaled(torch.randn(pred.shape, generator=torch.Generator().manual_seed(11)))
+    pred.backward(c.g_pred)
+    c.xd = xd.detach()
+    c.dact = {k: v.detach() for k, v in taps.items()}
+    c.dgrad = {k: v.grad.detach() for k, v in taps.items()}
+    c.deng = E.DiscriminatorEngine(be, 2 * B, H, W, Cfg.dev)
+    c.deng.arena.load(pD)
+    c.deng.refresh_weights()
+    # ---- VGG
+    c.veng = E.VggEngine(be, 2 * B, B, H, W, Cfg.dev)
+    c.veng.arena.load(pV)
+    c.veng.refresh_weights()
+    return c
+
+
+def check_discriminator_layers(ctx):
+    """NLayerDiscriminator (irc:598-635): model.0 (direct 4x4 s2 conv + LeakyReLU), model.2 / .5 (stride-2 convs over
+    space-to-depth blocks) and model.8 with InstanceNorm + LeakyReLU, model.11 (per-tap partial products + shifted reduction);
+    backward: tap expansion, every data / weight / bias gradient, the three InstanceNorm + LeakyReLU transposes, the
+    LeakyReLU mask of model.0 in the GEMM epilogue, col2im into the image gradient"""
+    B, H, W, TOL = Cfg.B, Cfg.H, Cfg.W, Cfg.TOL
+    O, E, be, eng, p = ctx.O, ctx.E, ctx.be, ctx.deng, ctx.pD
+    from irc_b200._native import View
+    n = 2 * B
+    A, G = ctx.dact, ctx.dgrad
+    dev = Cfg.dev
+    LR = dict(eps=E.EPS, act=E.ACT_LRELU, slope=0.2)
+    H1, W1, H2, W2, H3, W3, H8, W8, Ho, Wo = eng.H1, eng.W1, eng.H2, eng.W2, eng.H3, eng.W3, eng.H8o, eng.W8o, eng.Ho, eng.Wo
+    vS0 = View(eng.S0v, 0, eng.hb0, eng.wb0, 1, 1, 64)
+    vS2 = View(eng.S2, 0, eng.hb2, eng.wb2, 1, 1, 128)
+    vdS2 = View(eng.dS2, 0, eng.hb2, eng.wb2, 1, 1, 128)
+    vdZ0 = View(eng.dZ0v, 0, eng.hb0, eng.wb0, 1, 1, 64)
+    wgt = lambda k: p[f"model.{k}.weight"]
+    garena = lambda name: eng.arena.view(name, eng.arena.grad)
+    ir, rgb, fake = ctx.ir.to(dev), ctx.rgb.to(dev), ctx.fake.to(dev)
+    # ---- model.0 through the engine's own first launches (its input IS the oracle's input); fills E0 / row_img0
+    pred = eng.forward(ir, rgb, ir, fake)
+    x16 = r16(ctx.xd)
+    d0_ref = F.leaky_relu(F.conv2d(x16, r16(wgt(0)), p["model.0.bias"], stride=2, padding=1), 0.2)
+    e = rel(getv(vS0, n, 64, H1, W1), d0_ref); print("D.0 fwd + LeakyReLU (s2d rows)", e); assert e < TOL
+    e = rel(pred, A["d11"]); print("D whole forward (5 layers, not teacher-forced)", e); assert e < 5 * TOL
+    # ---- model.2: conv over the space-to-depth blocks, statistics (epilogue or pass), IN + LeakyReLU into the next s2d operand
+    d0 = r16(A["d0"])
+    eng.S0.zero_(); putv(vS0, d0)
+    eng.c2.fwd_stats(eng.S0v, 0, eng.Z2, eng.st2, eng.ri2, n, eng.hb0 * eng.wb0, eng._vZ2(eng.Z2), 128, H2, W2)
+    z2_ref, _, _ = conv_s(d0, r16(wgt(2)), None, 2, 1)
+    e = rel(getv(eng._vZ2(eng.Z2), n, 128, H2, W2), z2_ref); print("D.2 fwd", e); assert e < TOL
+    st_ref = torch.stack([z2_ref.sum((2, 3)), z2_ref.pow(2).sum((2, 3))], -1)
+    e = rel(eng.st2[..., 1], st_ref[..., 1]); print("D.2 InstanceNorm sum of squares", e); assert e < TOL
+    e = ((eng.st2[..., 0].cpu() - st_ref[..., 0]).abs().max() / st_ref[..., 1].sqrt().mean()).item(); print("D.2 InstanceNorm sums", e); assert e < TOL
+    z2 = r16(z2_ref); putv(eng._vZ2(eng.Z2), z2)
+    be.in_stats(eng._vZ2(eng.Z2), 128, n, H2, W2, eng.st2)
+    be.gather(eng._vZ2(eng.Z2), View(eng.S2, 0, eng.hb2, eng.wb2), 128, n, H2, W2, 1, 0, dst_s2d=1, **eng._na(eng.st2, H2 * W2))
+    a2_ref, _ = in_lrelu_local(z2, None, O)
+    got = getv(vS2, n, 128, H2, W2)
+    e = rel(got, a2_ref); print("D.2 IN + LeakyReLU -> s2d", e); assert e < TOL
+    assert abs(eng.S2.float().abs().sum().item() - got.abs().sum().item()) <= 1e-3 * got.abs().sum().item()      # zero ring
+    # ---- model.5
+    d2 = r16(A["d2"])
+    eng.S2.zero_(); putv(vS2, d2)
+    eng.c5.fwd(eng.S2, 0, eng.Z5)
+    z5_ref, _, _ = conv_s(d2, r16(wgt(5)), None, 2, 1)
+    e = rel(getv(eng._vZ5(eng.Z5), n, 256, H3, W3), z5_ref); print("D.5 fwd", e); assert e < TOL
+    z5 = r16(z5_ref); putv(eng._vZ5(eng.Z5), z5)
+    be.in_apply(eng._vZ5(eng.Z5), eng.X8.view(), 256, n, H3, W3, 1, 0, eng.st5, **LR)
+    a5_ref, _ = in_lrelu_local(z5, None, O)
+    e = rel(get(eng.X8, 256, full=True), F.pad(a5_ref, (1, 1, 1, 1))); print("D.5 IN + LeakyReLU (zero ring incl.)", e); assert e < TOL
+    # ---- model.8 (stride 1, k4 p1: the output shrinks by one)
+    d5 = r16(A["d5"])
+    put(eng.X8, d5)
+    eng.c8.fwd(eng.X8.t, 0, eng.Z8)
+    z8_ref, _, _ = conv_s(d5, r16(wgt(8)), None, 1, 1)
+    e = rel(getv(eng._vZ8(eng.Z8), n, 512, H8, W8), z8_ref); print("D.8 fwd", e); assert e < TOL
+    z8 = r16(z8_ref); putv(eng._vZ8(eng.Z8), z8)
+    be.in_apply(eng._vZ8(eng.Z8), eng.X11.view(), 512, n, H8, W8, 1, 0, eng.st8, **LR)
+    a8_ref, _ = in_lrelu_local(z8, None, O)
+    e = rel(get(eng.X11, 512, full=True), F.pad(a8_ref, (1, 1, 1, 1))); print("D.8 IN + LeakyReLU (zero ring incl.)", e); assert e < TOL
+    # ---- model.11: 512 -> 1
+    d8 = r16(A["d8"])
+    put(eng.X11, d8)
+    eng.c11.fwd(eng.X11.t, 0, eng.P11)
+    be.tap_reduce(eng.P11, eng.shifts11, 1, n, Ho, Wo, eng.X11.hp, eng.X11.wp, 0, 0, eng.c11.bias(), E.ACT_NONE, eng.pred)
+    b11 = p["model.11.bias"].clone().requires_grad_(True)
+    w11 = wgt(11).clone().requires_grad_(True)
+    x11 = d8.clone().requires_grad_(True)
+    e = rel(eng.pred, F.conv2d(d8, r16(wgt(11)), b11, padding=1)); print("D.11 fwd (tap partials + shifted sum)", e); assert e < TOL
+    # ======== backward
+    g = ctx.g_pred
+    zero_wgrad(eng)
+    be.tap_expand(g.to(dev).contiguous(), None, eng.shifts11, 1, n, Ho, Wo, eng.X11.hp, eng.X11.wp, 0, 0, eng.E11,
+                  dbias=garena("model.11.bias"), live_cols_only=True)
+    eng.c11.wgrad(eng.E11, eng.X11.t, 0, eng.X11.rows)
+    eng.c11.dgrad(eng.E11, eng.G11.t)
+    be.flush_sums()
+    gw, gb = torch.autograd.grad(F.conv2d(d8, w11, b11, padding=1), (w11, b11), g)
+    (gx,) = torch.autograd.grad(F.conv2d(x11, r16(wgt(11)), None, padding=1), x11, g)
+    e = rel(garena("model.11.bias"), gb); print("D.11 bias grad", e); assert e < TOL
+    e = rel(garena("model.11.weight"), gw); print("D.11 wgrad", e); assert e < TOL
+    e = rel(get(eng.G11, 512), gx); print("D.11 dgrad", e); assert e < TOL
+    # ---- model.8: IN + LeakyReLU transpose, weight / data gradients
+    g8 = r16(scaled(G["d8"]))
+    put(eng.G11, g8)
+    be.in_bwd(eng._vZ8(eng.Z8), eng.G11.view(), eng._vZ8(eng.dZ8), 512, n, H8, W8, bsum=eng.bsum, **eng._nb(eng.st8, H8 * W8, True))
+    _, dz8_ref = in_lrelu_local(z8, g8, O)
+    e = rel(getv(eng._vZ8(eng.dZ8), n, 512, H8, W8), dz8_ref); print("D.8 IN + LeakyReLU bwd", e); assert e < TOL
+    dz8 = r16(dz8_ref); eng.dZ8.zero_(); putv(eng._vZ8(eng.dZ8), dz8)
+    zero_wgrad(eng)
+    eng.c8.wgrad(eng.dZ8, eng.X8.t, 0, eng.X8.rows)
+    eng.c8.dgrad(eng.dZ8, eng.G8.t)
+    be.flush_sums()
+    _, _, gw = conv_s(d5, wgt(8), dz8, 1, 1)
+    _, gx, _ = conv_s(d5, r16(wgt(8)), dz8, 1, 1)
+    e = rel(garena("model.8.weight"), gw); print("D.8 wgrad", e); assert e < TOL
+    e = rel(get(eng.G8, 256), gx); print("D.8 dgrad", e); assert e < TOL
+    # ---- model.5
+    g5 = r16(scaled(G["d5"]))
+    put(eng.G8, g5)
+    be.in_bwd(eng._vZ5(eng.Z5), eng.G8.view(), eng._vZ5(eng.dZ5), 256, n, H3, W3, bsum=eng.bsum, **eng._nb(eng.st5, H3 * W3, True))
+    _, dz5_ref = in_lrelu_local(z5, g5, O)
+    e = rel(getv(eng._vZ5(eng.dZ5), n, 256, H3, W3), dz5_ref); print("D.5 IN + LeakyReLU bwd", e); assert e < TOL
+    dz5 = r16(dz5_ref); eng.dZ5.zero_(); putv(eng._vZ5(eng.dZ5), dz5)
+    zero_wgrad(eng)
+    eng.c5.wgrad(eng.dZ5, eng.S2, 0, eng.S2.shape[0])
+    eng.c5.dgrad(eng.dZ5, eng.dS2)
+    be.flush_sums()
+    _, _, gw = conv_s(d2, wgt(5), dz5, 2, 1)
+    _, gx, _ = conv_s(d2, r16(wgt(5)), dz5, 2, 1)
+    e = rel(garena("model.5.weight"), gw); print("D.5 wgrad", e); assert e < TOL
+    e = rel(getv(vdS2, n, 128, H2, W2), gx); print("D.5 dgrad (s2d)", e); assert e < TOL
+    # ---- model.2
+    g2 = r16(scaled(G["d2"]))
+    putv(vdS2, g2)
+    be.in_bwd(eng._vZ2(eng.Z2), vdS2, eng._vZ2(eng.dZ2), 128, n, H2, W2, bsum=eng.bsum, **eng._nb(eng.st2, H2 * W2, True))
+    _, dz2_ref = in_lrelu_local(z2, g2, O)
+    e = rel(getv(eng._vZ2(eng.dZ2), n, 128, H2, W2), dz2_ref); print("D.2 IN + LeakyReLU bwd (s2d gradient)", e); assert e < TOL
+    dz2 = r16(dz2_ref); eng.dZ2.zero_(); putv(eng._vZ2(eng.dZ2), dz2)
+    zero_wgrad(eng)
+    eng.c2.wgrad(eng.dZ2, eng.S0v, 0, eng.S0v.shape[0])
+    eng.c2.dgrad(eng.dZ2, eng.dZ0v, mask=View(eng.S0v, 0, 0, 0), mask_slope=0.2)
+    be.flush_sums()
+    _, _, gw = conv_s(d0, wgt(2), dz2, 2, 1)
+    _, gx, _ = conv_s(d0, r16(wgt(2)), dz2, 2, 1)
+    e = rel(garena("model.2.weight"), gw); print("D.2 wgrad", e); assert e < TOL
+    dz0_ref = gx * torch.where(d0 > 0, torch.ones_like(d0), torch.full_like(d0, 0.2))
+    e = rel(getv(vdZ0, n, 64, H1, W1), dz0_ref); print("D.2 dgrad + LeakyReLU mask of model.0 (s2d)", e); assert e < TOL
+    # ---- model.0: bias / weight gradient from the saved im2col operand, image gradient through col2im
+    dz0 = r16(dz0_ref); eng.dZ0.zero_(); putv(vdZ0, dz0)
+    zero_wgrad(eng)
+    be.colsum(eng.dZ0, 0, 64, garena("model.0.bias"), row_img=eng.row_img0)
+    eng.c0.wgrad(eng.dZ0, eng.E0, 0, eng.rows0)
+    be.flush_sums()
+    dimg = torch.zeros(n, 3, H, W, device=dev)
+    eng.c0.dgrad(eng.dZ0, eng.dE0)
+    be.col2im(eng.dE0, 4, 1, 3, n, H, W, 4, 2, 1, H1, W1, 2, None, dimg, False)
+    _, _, gw = conv_s(x16, wgt(0), dz0, 2, 1)
+    _, gx, _ = conv_s(x16, r16(wgt(0)), dz0, 2, 1)
+    e = rel(garena("model.0.bias"), dz0.sum((0, 2, 3))); print("D.0 bias grad", e); assert e < TOL
+    e = rel(garena("model.0.weight"), gw); print("D.0 wgrad", e); assert e < TOL
+    e = rel(dimg, gx[:, 1:4]); print("D.0 dgrad -> image gradient", e); assert e < TOL
+
+
+def check_vgg_layers(ctx):
+    """VGGPerceptual trunk features[:16] (irc:642-683): conv1_1 straight from the fp32 image with the ImageNet normalisation
+    folded in, six 3x3 convolutions with bias + ReLU in the epilogue, two max-pools; backward (data gradients of the first
+    n_bwd images only): data-gradient GEMMs with the ReLU mask in the epilogue, max-pool transposes, conv1_1's gradient
+    summed into d(fake)"""
+    B, H, W, TOL = Cfg.B, Cfg.H, Cfg.W, Cfg.TOL
+    O, E, be, eng, p = ctx.O, ctx.E, ctx.be, ctx.veng, ctx.pV
+    from irc_b200._native import View
+    dev = Cfg.dev
+    n = 2 * B
+    x = torch.cat([ctx.fake, ctx.rgb], 0)
+    eng.forward(ctx.fake.to(dev), ctx.rgb.to(dev))
+    mean = torch.tensor(O.IMAGENET_MEAN).view(1, 3, 1, 1); std = torch.tensor(O.IMAGENET_STD).view(1, 3, 1, 1)
+    h_in = ((x + 1) / 2 - mean) / std
+    gen = torch.Generator().manual_seed(21)
+    acts = []            # r16 of every conv's ReLU output (pre-pool), all n images
+    for i, (idx, ci, co) in enumerate(E.VGG_CFG):
+        conv, fr = eng.convs[i], eng.act[i]
+        w, b = p[f"features.{idx}.weight"], p[f"features.{idx}.bias"]
+        hi = r16(h_in)
+        a_ref = torch.relu(F.conv2d(hi, r16(w), b, padding=1))
+        if i > 0:
+            src = eng.pool[i - 1] if (i - 1) in eng.pool else eng.act[i - 1]
+            put(src, hi)
+            conv.fwd(src.t, 0, fr.t, bias=conv.bias(), act=E.ACT_RELU, row_img=eng._ri(i))
+        e = rel(get(fr, co, full=True), F.pad(a_ref, (1, 1, 1, 1))); print(f"V.{idx} fwd + bias + ReLU (zero ring incl.)", e); assert e < TOL
+        a16 = r16(a_ref)
+        acts.append(a16)
+        put(fr, a16)
+        if i in eng.pool:
+            h, w_ = eng.res[i + 1]
+            be.maxpool2(fr.view(), eng.pool[i].view(), fr.C, n, h, w_)
+            h_in = F.max_pool2d(a16, 2, 2)
+            e = rel(get(eng.pool[i], co, full=True), F.pad(h_in, (1, 1, 1, 1))); print(f"V.{idx} max-pool", e); assert e < 1e-6
+        else:
+            h_in = a16
+    # ======== backward on the first B images
+    nb = B
+    dfake = torch.zeros(nb, 3, H, W, device=dev)
+    for i in range(len(eng.convs) - 1, -1, -1):
+        idx, ci, co = E.VGG_CFG[i]
+        conv = eng.convs[i]
+        w = p[f"features.{idx}.weight"]
+        a_i = acts[i][:nb]
+        dz = r16(scaled(torch.randn(a_i.shape, generator=gen)) * (a_i > 0))        # gradient w.r.t. the pre-ReLU output of conv i
+        put(eng.dz[i], dz)
+        if i == 0:
+            hi = r16(((x[:nb] + 1) / 2 - mean) / std)
+            _, gx, _ = conv_s(hi, r16(w), dz, 1, 1)
+            ref = gx * (0.5 / std)
+            if eng.fused_dgrad0:
+                d0 = eng.dz[0]
+                be.conv_gemm(d0.t, 0, 64, [d0.wp, 0, -d0.wp], eng.w0_dg.t, 32, eng.P0,
+                             tap=dict(out=dfake, nshift=3, nco=3, H=H, W=W, hp=d0.hp, wp=d0.wp, oy=1, ox=1, act=E.ACT_NONE, scale=eng.scale, accumulate=True))
+            else:
+                conv.dgrad(eng.dz[0].t, eng.dE)
+                be.col2im(eng.dE, 3, 0, 3, nb, H, W, 3, 1, 1, H, W, 1, eng.scale, dfake, True)
+            e = rel(dfake, ref); print("V.0 dgrad -> d(fake)", e); assert e < TOL
+            break
+        prev = eng.act[i - 1]
+        a_prev = acts[i - 1][:nb]
+        if (i - 1) in eng.pool:
+            pooled = a_prev.clone().requires_grad_(True)
+            hin = F.max_pool2d(pooled, 2, 2)
+            _, gx, _ = conv_s(hin.detach(), r16(w), dz, 1, 1)
+            conv.dgrad(eng.dz[i].t, eng.dpool[i - 1].t)
+            e = rel(get(eng.dpool[i - 1], ci), gx); print(f"V.{idx} dgrad (to the pooled map)", e); assert e < TOL
+            gx16 = r16(gx); put(eng.dpool[i - 1], gx16)
+            h, w_ = eng.res[i]
+            be.maxpool2_bwd(View(prev.t[:prev.rows_of(nb)], 0, prev.hp, prev.wp, 1, 1), eng.dpool[i - 1].view(), eng.dz[i - 1].view(), prev.C, nb, h, w_)
+            (ref,) = torch.autograd.grad(hin, pooled, gx16)
+            ref = ref * (a_prev > 0)
+            e = rel(get(eng.dz[i - 1], ci), ref); print(f"V.{idx} max-pool^T + ReLU mask", e); assert e < 1e-6
+        else:
+            _, gx, _ = conv_s(a_prev, r16(w), dz, 1, 1)
+            conv.dgrad(eng.dz[i].t, eng.dz[i - 1].t, mask=View(prev.t[:prev.rows_of(nb)], 0, 0, 0), mask_slope=0.0)
+            e = rel(get(eng.dz[i - 1], ci), gx * (a_prev > 0)); print(f"V.{idx} dgrad + ReLU mask", e); assert e < TOL

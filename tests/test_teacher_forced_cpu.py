@@ -42,3 +42,17 @@ def test_upsample_into_concat_and_transpose(ctx):
 
 def test_outc_7x7_tanh(ctx):
     T.check_outc_7x7_tanh(ctx)
+
+
+@pytest.fixture(scope="module")
+def dv_ctx(ctx):
+    from ref_backend import RefBackend
+    return T.make_dv_ctx(RefBackend())
+
+
+def test_discriminator_layers(dv_ctx):
+    T.check_discriminator_layers(dv_ctx)
+
+
+def test_vgg_layers(dv_ctx):
+    T.check_vgg_layers(dv_ctx)

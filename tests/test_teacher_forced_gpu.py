@@ -37,3 +37,16 @@ def test_upsample_into_concat_and_transpose(ctx):
 
 def test_outc_7x7_tanh(ctx):
     T.check_outc_7x7_tanh(ctx)
+
+
+@pytest.fixture(scope="module")
+def dv_ctx(ctx):
+    return T.make_dv_ctx(ctx.be)
+
+
+def test_discriminator_layers(dv_ctx):
+    T.check_discriminator_layers(dv_ctx)
+
+
+def test_vgg_layers(dv_ctx):
+    T.check_vgg_layers(dv_ctx)
