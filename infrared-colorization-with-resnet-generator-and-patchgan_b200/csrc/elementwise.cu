@@ -386,6 +386,104 @@ __global__ void __launch_bounds__(256, 4) gather_ident_pipe_kernel(const GatherP
 }
 
 // ---------------------------------------------------------------------------------
+// Identity-table gather, register version: the cp.async-slot kernel above decodes (row, column) twice per 16-byte vector
+// (once to issue, once to consume) and spends ~200 instructions per vector - ncu: issue slots 78 % busy at 0.61 of the HBM peak
+// (profiles/r5/ncu_gathers_summary.txt).  Here a block owns whole padded frame rows: the row is decoded once (block-uniform), every
+// thread streams four interior pixels per step with its four (or eight) 16-byte loads issued back to back, the activation is a
+// template parameter, and the 2 * pad ring columns of the row are done afterwards by the first lanes (their sources are L1 / L2 hits).
+// ---------------------------------------------------------------------------------
+template <int kAct>      // 0: copy, 1: normalise + ReLU, 2: normalise + max(t, 0) + slope_eff * min(t, 0)
+__device__ __forceinline__ void ident_vec(const uint4& z, const float (&mu)[8], const float (&rs)[8], float slope_eff, float (&v)[8]) {
+    unpack8(z, v);
+    if (kAct == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], rs[k], mu[k]), 0.f);
+    } else if (kAct == 2) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float t = fmaf(v[k], rs[k], mu[k]); v[k] = fmaf(slope_eff, fminf(t, 0.f), fmaxf(t, 0.f)); }
+    }
+}
+
+template <bool kRes, int kAct>
+__global__ void __launch_bounds__(256, kRes ? 3 : 4) gather_ident_lean_kernel(const GatherP p) {
+    irc::pdl_prologue();
+    constexpr int U = 4;
+    const int C8 = p.C >> 3;
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int c = cv * 8;
+    const int pad = p.pad, H = p.H, W = p.W;
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const int rows = p.n_img * Hp;
+    const int sld = (int)p.src.ld, dld = (int)p.dst.ld, rld = kRes ? (int)p.res.ld : 0;
+    float mu[8], rs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { mu[k] = 0.f; rs[k] = 1.f; }
+    int cur_n = -1;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int n = row / Hp, Y = row - n * Hp;
+        int y = Y - pad;
+        const bool yhalo = y < 0 || y >= H;
+        if (yhalo) y = reflect_idx(y, H);
+        // padded pixel (Y, X) of the destination frame sits at drow + X * dld
+        bf16* drow = const_cast<bf16*>(p.dst.p) + ((long long)(n * p.dst.hp + Y - pad + p.dst.oy) * p.dst.wp + (p.dst.ox - pad)) * p.dst.ld + p.dst.off + c;
+        if (yhalo && p.halo_mode != 1) {
+            for (int X = lane; X < Wp; X += L) *reinterpret_cast<uint4*>(drow + X * dld) = make_uint4(0, 0, 0, 0);
+            continue;
+        }
+        if (kAct != 0 && n != cur_n) {
+            cur_n = n;
+            moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mu[k] = -mu[k] * rs[k];
+        }
+        const bf16* srow = p.src.at(n, y, 0, c);
+        const bf16* rrow = kRes ? p.res.at(n, y, 0, c) : nullptr;
+        for (int x0 = lane; x0 < W; x0 += U * L) {
+            uint4 z[U], r[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int x = x0 + u * L;
+                if (x < W) {
+                    z[u] = __ldg(reinterpret_cast<const uint4*>(srow + x * sld));
+                    if (kRes) r[u] = __ldg(reinterpret_cast<const uint4*>(rrow + x * rld));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int x = x0 + u * L;
+                if (x < W) {
+                    float v[8];
+                    ident_vec<kAct>(z[u], mu, rs, p.slope_eff, v);
+                    if (kRes) {
+                        float w[8];
+                        unpack8(r[u], w);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] += w[k];
+                    }
+                    store8(drow + (x + pad) * dld, v);
+                }
+            }
+        }
+        // ring columns of this row: X in [0, pad) and [W + pad, W + 2 pad)
+        for (int j = lane; j < 2 * pad; j += L) {
+            const int X = j < pad ? j : W + j;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (p.halo_mode == 1) {
+                const int x = reflect_idx(X - pad, W);
+                ident_vec<kAct>(__ldg(reinterpret_cast<const uint4*>(srow + x * sld)), mu, rs, p.slope_eff, v);
+                if (kRes) {
+                    float w[8];
+                    load8(rrow + x * rld, w);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] += w[k];
+                }
+            }
+            store8(drow + X * dld, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // Lean table gather: K x K taps with K a compile-time constant (2: reflection fold / Downsample^T, 3: Downsample and
 // UpsampleAA, 6: UpsampleAA^T).  One block per output row: the row's y-entries and source row pointers are computed once,
 // the x-entries of a pixel sit in registers, and the K*K 16-byte loads per output vector hit L1/L2 (every source pixel
@@ -1871,6 +1969,20 @@ extern "C" int irc_gather(const irc_gather_args* a, void* stream) {
     const long long rows = (long long)p.n_img * (p.H + 2 * p.pad);
     const unsigned grid = (unsigned)(rows < 65535 * 16 ? rows : 65535 * 16);
     if (!p.ty_idx && !p.tx_idx && !p.has2 && !p.dst_s2d && !p.src.s2d_c && !(p.has_res && p.res.s2d_c) && (p.stats || !p.act) && !getenv("IRC_NO_GATHER_PIPE")) {
+        static int lean_mode = -1;      // IRC_GATHER_IDENT=pipe: the cp.async-slot kernel (kept for the A/B in profiles/)
+        if (lean_mode < 0) { const char* e = getenv("IRC_GATHER_IDENT"); lean_mode = (e && e[0] == 'p') ? 0 : 1; }
+        if (lean_mode) {
+            const unsigned gl = (unsigned)(rows < (long long)irc_num_sms() * 8 ? rows : (long long)irc_num_sms() * 8);
+            const int am = !p.stats ? 0 : (p.act == 1 ? 1 : 2);
+            cudaStream_t st = (cudaStream_t)stream;
+#define IRC_IDENT(RES) do { \
+                if (am == 0) irc::launch(gather_ident_lean_kernel<RES, 0>, gl, threads, 0, st, p); \
+                else if (am == 1) irc::launch(gather_ident_lean_kernel<RES, 1>, gl, threads, 0, st, p); \
+                else irc::launch(gather_ident_lean_kernel<RES, 2>, gl, threads, 0, st, p); } while (0)
+            if (p.has_res) IRC_IDENT(true); else IRC_IDENT(false);
+#undef IRC_IDENT
+            return irc_check_launch("irc_gather(ident)");
+        }
         const size_t smem = (size_t)kPipeD * (p.has_res ? 2 : 1) * threads * 16;
         const unsigned gp = (unsigned)(rows < (long long)irc_num_sms() * 16 ? rows : (long long)irc_num_sms() * 16);
         if (p.has_res) irc::launch(gather_ident_pipe_kernel<true>, gp, threads, smem, (cudaStream_t)stream, p);
