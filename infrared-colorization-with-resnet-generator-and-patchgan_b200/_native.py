@@ -220,6 +220,23 @@ class Tables:
             self._stream = (kmax, k)
         return self._stream[1]
 
+    def x_bandwidth(self, L: int) -> int:
+        """largest span of source columns needed by L consecutive output columns (blocks aligned at multiples of L): the staged
+        row segment of the staged-rows stencil kernel"""
+        key = ("xbw", L)
+        if key not in self._tiling:
+            import numpy as np
+            _, _, ix, wx = self._load_host()
+            nz = wx != 0
+            lo = np.where(nz, ix, 1 << 30).min(1); hi = np.where(nz, ix, -1).max(1)
+            bw = 0
+            for s0 in range(0, len(lo), L):
+                m = hi[s0:s0 + L] >= 0
+                if m.any():
+                    bw = max(bw, int(hi[s0:s0 + L][m].max() - lo[s0:s0 + L][m].min() + 1))
+            self._tiling[key] = bw
+        return self._tiling[key]
+
     def _axis_extent(self, idx, w, n_out, pad, halo_mode, T):
         """largest source index span needed by any T-wide tile of the padded output axis"""
         import numpy as np
@@ -426,7 +443,8 @@ class CudaBackend:
                 lanes = max(1, 256 // (C_ // 8))
                 blocks_per_row = n_img * ((W + lanes - 1) // lanes)
                 strip = max(4, min(32, (blocks_per_row * H) // 1184))
-                g.tile_y, g.tile_x, g.patch_y, g.patch_x = -3, k, strip, 0
+                # patch_x = source-column span of a block's L output columns (staged-rows kernel; 0 selects the register-only one)
+                g.tile_y, g.tile_x, g.patch_y, g.patch_x = -3, k, strip, tables.x_bandwidth(min(lanes, W))
                 check(self.L.irc_gather(C.byref(g), _stream())); self.launches += 1
                 return
             # measured (scripts/bench_elem.py): the shared-memory tiled kernel wins for the up-sampling stencils and the

@@ -742,6 +742,204 @@ __global__ void __launch_bounds__(256, K <= 3 ? 3 : 2) gather_stream_kernel(cons
 }
 
 // ---------------------------------------------------------------------------------
+// Staged-rows variant of the streaming gather.  In the kernel above every output column issues its own kx 16-byte global loads per
+// new source row, one row ahead: ncu shows 2.4 - 4.4 long-scoreboard stall cycles per issue at 23 - 34 % occupancy (the register
+// windows), i.e. the DRAM latency is not covered (profiles/r5/ncu_gathers_summary.txt).  Here the block copies the source-row
+// segment its L output columns need with cp.async into a kRowsStg-deep shared-memory ring (raw bf16, no registers, three rows in
+// flight per block), one __syncthreads per source row; the x-taps are 16-byte shared-memory reads.  Each source pixel crosses
+// L2 -> SM once per block instead of kx / stride times.
+// ---------------------------------------------------------------------------------
+constexpr int kRowsNS = 3;      // staged vectors per thread and source row: the segment spans at most 3 L columns (host-checked bound)
+constexpr int kRowsStg = 4;     // ring depth
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t saddr, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem) : "memory");
+}
+
+template <int K, int kNorm, bool kTwo>      // kNorm: 0 raw, 1 normalise + ReLU, 2 normalise + max(t, 0) + slope_eff * min(t, 0)
+__global__ void __launch_bounds__(256, K <= 3 ? 3 : 2) gather_rows_kernel(const GatherP p, int strip, int sw_max) {
+    irc::pdl_prologue();
+    extern __shared__ uint4 s_ring[];            // [kRowsStg][kTwo ? 2 : 1][sw_max][C8]
+    __shared__ int s_hi[kMaxStrip];
+    __shared__ int s_lo0, s_cmin, s_cmax;
+    __shared__ float s_wd[kMaxStrip][K];
+    const int C8 = p.C >> 3;
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int c = cv * 8;
+    const int n = blockIdx.z;
+    const int ya = blockIdx.y * strip;
+    const int rows = min(strip, p.H - ya);
+    const int x = blockIdx.x * L + lane;
+    const bool xok = x < p.W;
+    if (threadIdx.x == 0) { s_cmin = 0x7fffffff; s_cmax = -1; }
+    if ((int)threadIdx.x < rows) {
+        const int y = ya + threadIdx.x;
+        int lo = 0x7fffffff, hi = -1;
+        for (int i = 0; i < p.ky; ++i)
+            if (__ldg(p.ty_w + y * p.ky + i) != 0.f) { const int q = __ldg(p.ty_idx + y * p.ky + i); lo = min(lo, q); hi = max(hi, q); }
+        s_hi[threadIdx.x] = hi;
+        if (threadIdx.x == 0) s_lo0 = lo;
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+            const int r = hi + 1 - K + s;
+            float w = 0.f;
+            for (int i = 0; i < p.ky; ++i) {
+                const float wi = __ldg(p.ty_w + y * p.ky + i);
+                if (wi != 0.f && __ldg(p.ty_idx + y * p.ky + i) == r) w += wi;
+            }
+            s_wd[threadIdx.x][s] = w;
+        }
+    }
+    // x entries of this output column (unused table slots: weight 0, staged column 0)
+    float wx[K]; int ix[K];
+    int mn = 0x7fffffff, mx = -1;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const bool h = xok && j < p.kx;
+        wx[j] = h ? __ldg(p.tx_w + x * p.kx + j) : 0.f;
+        ix[j] = h ? __ldg(p.tx_idx + x * p.kx + j) : 0;
+        if (wx[j] != 0.f) { mn = min(mn, ix[j]); mx = max(mx, ix[j]); }
+    }
+    __syncthreads();
+    if (cv == 0 && mx >= 0) { atomicMin(&s_cmin, mn); atomicMax(&s_cmax, mx); }
+    __syncthreads();
+    const int cmin = s_cmin, sw = s_cmax - cmin + 1;       // sw <= sw_max (checked by the host from the table bandwidth)
+    const uint32_t ring_s = smem_u32(s_ring);              // shared-space byte addresses, computed once
+    uint32_t xo[K];                                        // byte offsets of the taps inside a staged row
+#pragma unroll
+    for (int j = 0; j < K; ++j) xo[j] = (uint32_t)((wx[j] != 0.f ? ix[j] - cmin : 0) * C8 + cv) * 16u;
+    float mu[8], rs[8];
+    if (kNorm) {
+        moments8(p.stats, n, p.C, c, p.inv_cnt, p.eps, mu, rs);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mu[k] = -mu[k] * rs[k];
+    }
+    const int sld = (int)p.src.ld, sld2 = kTwo ? (int)p.src2.ld : 0;
+    const long long sstep = (long long)p.src.wp * p.src.ld;
+    const long long sstep2 = kTwo ? (long long)p.src2.wp * p.src2.ld : 0;
+    // destination
+    const int pad = p.pad, W = p.W, H = p.H;
+    int eX = -1;
+    if (pad && xok) {
+        if (p.halo_mode == 1) eX = (x >= 1 && x <= pad) ? pad - x : ((x >= W - 1 - pad && x <= W - 2) ? pad + 2 * (W - 1) - x : -1);
+        else eX = x < pad ? x : (x >= W - pad ? x + 2 * pad : -1);
+    }
+    bf16* dbase = const_cast<bf16*>(p.dst.p) + ((long long)(n * p.dst.hp + p.dst.oy - pad) * p.dst.wp + (p.dst.ox - pad)) * p.dst.ld + p.dst.off + c;
+    const long long dstep = (long long)p.dst.wp * p.dst.ld;
+    bf16* dptr = dbase + (ya + pad) * dstep + (long long)(x + pad) * p.dst.ld;
+    const long long dex = eX >= 0 ? (long long)(eX - (x + pad)) * p.dst.ld : 0;
+    float hb[K][8];
+#pragma unroll
+    for (int s = 0; s < K; ++s)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hb[s][k] = 0.f;
+    int top = s_lo0;
+    const int last = s_hi[rows - 1];
+    // staged columns of this thread: cmin + lane + i * L, channel vector cv (blockDim is a multiple of C8)
+    const bf16* rp = p.src.at(n, top, cmin + lane, c);
+    const bf16* rp2 = kTwo ? p.src2.at(n, top, cmin + lane, c) : nullptr;
+    const uint32_t slot_b = (uint32_t)((kTwo ? 2 : 1) * sw_max * C8) * 16u;      // bytes per ring slot
+    const uint32_t two_b = (uint32_t)(sw_max * C8) * 16u;                         // offset of the second source inside a slot
+    const uint32_t ring_end = ring_s + kRowsStg * slot_b;
+    const uint32_t step_b = (uint32_t)(L * C8) * 16u;                             // staged vector i of this thread: + i * step_b
+    const int gstep = L * sld, gstep2 = L * sld2;
+    bool on[kRowsNS];
+#pragma unroll
+    for (int i = 0; i < kRowsNS; ++i) on[i] = lane + i * L < sw;
+    int nxt = top;                                         // next source row to issue
+    uint32_t idst = ring_s + (uint32_t)(lane * C8 + cv) * 16u;      // ... and where its first vector goes
+    auto issue = [&]() {
+        if (nxt <= last) {
+#pragma unroll
+            for (int i = 0; i < kRowsNS; ++i)
+                if (on[i]) {
+                    cp_async16_s(idst + i * step_b, rp + i * gstep);
+                    if (kTwo) cp_async16_s(idst + two_b + i * step_b, rp2 + i * gstep2);
+                }
+            rp += sstep;
+            if (kTwo) rp2 += sstep2;
+            ++nxt;
+            idst += slot_b;
+            if (idst >= ring_end) idst -= kRowsStg * slot_b;
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < kRowsStg - 1; ++s) issue();
+    uint32_t cur = ring_s;                                 // slot of source row `top`
+    const float slope_eff = p.slope_eff;
+    for (int t = 0; t < rows; ++t) {
+        const int hi = s_hi[t];
+        while (top <= hi) {
+            cp_async_wait<kRowsStg - 2>();       // this thread's copies of row `top` have landed ...
+            __syncthreads();                     // ... and so have everyone else's; the slot read last iteration is free
+            issue();
+            float h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                float v[8];
+                unpack8(lds128(cur + xo[j]), v);
+                if (kNorm == 1) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], rs[k], mu[k]), 0.f);
+                } else if (kNorm == 2) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { const float u = fmaf(v[k], rs[k], mu[k]); v[k] = fmaf(slope_eff, fminf(u, 0.f), fmaxf(u, 0.f)); }
+                }
+                if (kTwo) {
+                    float u[8];
+                    unpack8(lds128(cur + two_b + xo[j]), u);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] += u[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) h[k] = fmaf(wx[j], v[k], h[k]);
+            }
+#pragma unroll
+            for (int s = 0; s + 1 < K; ++s)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) hb[s][k] = hb[s + 1][k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) hb[K - 1][k] = h[k];
+            ++top;
+            cur += slot_b;
+            if (cur >= ring_end) cur = ring_s;
+        }
+        if (xok) {
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                const float w = s_wd[t][s];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(w, hb[s][k], acc[k]);
+            }
+            const int y = ya + t;
+            const uint4 val = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+            *reinterpret_cast<uint4*>(dptr) = val;
+            if (pad && (eX >= 0 || y <= pad || y >= H - 1 - pad)) {
+                const uint4 ring = p.halo_mode == 1 ? val : make_uint4(0, 0, 0, 0);
+                int eY;
+                if (p.halo_mode == 1) eY = (y >= 1 && y <= pad) ? pad - y : ((y >= H - 1 - pad && y <= H - 2) ? pad + 2 * (H - 1) - y : -1);
+                else eY = y < pad ? y : (y >= H - pad ? y + 2 * pad : -1);
+                if (eX >= 0) *reinterpret_cast<uint4*>(dptr + dex) = ring;
+                if (eY >= 0) {
+                    bf16* erow = dptr + (long long)(eY - (y + pad)) * dstep;
+                    *reinterpret_cast<uint4*>(erow) = ring;
+                    if (eX >= 0) *reinterpret_cast<uint4*>(erow + dex) = ring;
+                }
+            }
+        }
+        dptr += dstep;
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------
 // Shared-memory tiled gather for real stencils (ky*kx > 1): one block = TY x TX output pixels x 32 channels.
 // The source patch the tile needs is loaded once (coalesced 16-byte loads), normalised / activated / summed with
 // src2 once per source pixel, kept in shared memory as fp32, and every output pixel then takes its taps from
@@ -1920,6 +2118,27 @@ extern "C" int irc_gather(const irc_gather_args* a, void* stream) {
         dim3 grid((p.W + L - 1) / L, (p.H + strip - 1) / strip, p.n_img);
         cudaStream_t st = (cudaStream_t)stream;
         const bool nrm = p.stats != nullptr;
+        // staged-rows kernel (default; IRC_GATHER_STREAM=regs selects the register-only one below): patch_x = bandwidth of the
+        // x-table (max over output columns x, x' with |x - x'| < L of the source-column span), which bounds the staged segment
+        static int rows_mode = -1;
+        if (rows_mode < 0) { const char* e = getenv("IRC_GATHER_STREAM"); rows_mode = (e && e[0] == 'r') ? 0 : 1; }
+        const int sw_max = a->patch_x;
+        // (normalise + up-sample stays on the register kernel: it is bound by the instructions of its output rows, not by load
+        // latency, and the ring's extra shared-memory traffic costs 3 % there - profiles/r5/gathers_rows_vs_regs.txt)
+        const bool up_norm = nrm && p.H > p.src.hp;
+        if (rows_mode && !up_norm && sw_max > 0 && sw_max <= kRowsNS * L) {
+            const size_t smem = (size_t)kRowsStg * (p.has2 ? 2 : 1) * sw_max * (p.C / 8) * 16;
+            if (smem <= 48 * 1024) {
+#define IRC_ROWS(KK) do { \
+            if (p.has2) irc::launch(gather_rows_kernel<KK, 0, true>, grid, threads, smem, st, p, strip, sw_max); \
+            else if (nrm && p.act == 1) irc::launch(gather_rows_kernel<KK, 1, false>, grid, threads, smem, st, p, strip, sw_max); \
+            else if (nrm) irc::launch(gather_rows_kernel<KK, 2, false>, grid, threads, smem, st, p, strip, sw_max); \
+            else irc::launch(gather_rows_kernel<KK, 0, false>, grid, threads, smem, st, p, strip, sw_max); } while (0)
+                if (K <= 2) IRC_ROWS(2); else if (K <= 3) IRC_ROWS(3); else if (K <= 4) IRC_ROWS(4); else IRC_ROWS(6);
+#undef IRC_ROWS
+                return irc_check_launch("irc_gather(rows)");
+            }
+        }
 #define IRC_STREAM(KK) do { \
             if (p.has2) irc::launch(gather_stream_kernel<KK, false, true>, grid, threads, 0, st, p, strip); \
             else if (nrm) irc::launch(gather_stream_kernel<KK, true, false>, grid, threads, 0, st, p, strip); \
