@@ -255,12 +255,19 @@ def main():
     losses = ts.losses()
 
     # ---- end to end through the public call with host buffers: H2D of the batch + D2H of the losses every step
+    # (public pipelined form: step() stages the pinned batch on a copy stream, losses_async() queues the 96-byte D2H read of
+    # THIS step's loss sums; the host reads the previous step's handle, so the copy of step i + 1 overlaps the kernels of step i)
+    pend = []
     def e2e_step():
         ts.step(ir_h, rgb_h)
-        ts.losses()
+        pend.append(ts.losses_async())
+        if len(pend) > 1:
+            pend.pop(0).get()
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, K)
+    e2e_losses = pend.pop().get()
+    assert all(v == v for v in e2e_losses.values())
 
     # ---- roofline of the dominant kernel: every tensor-core GEMM launch of one eager step bracketed by CUDA events
     pk = peaks()

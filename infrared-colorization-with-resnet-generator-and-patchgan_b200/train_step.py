@@ -53,6 +53,24 @@ class AdamHyper:
         self.step_dev.fill_(self.t)
 
 
+class LossHandle:
+    """result of TrainStep.losses_async(): the loss sums of one iteration on their way to the host"""
+
+    def __init__(self, ts, buf, ev):
+        self._ts, self._buf, self._ev, self._vals = ts, buf, ev, None
+
+    def _materialize(self):
+        if self._vals is None:
+            if self._ev is not None:
+                self._ev.synchronize()
+            self._vals = self._buf.tolist()
+            self._buf = None
+
+    def get(self) -> Dict[str, float]:
+        self._materialize()
+        return self._ts._loss_terms(self._vals)
+
+
 class TrainStep:
     """One process = one GPU = one replica.  With world_size > 1 the flat gradient arenas are
     all-reduced (sum) over NCCL and the 1/world_size average is folded into the Adam kernel."""
@@ -223,7 +241,10 @@ class TrainStep:
 
     def step(self, ir: torch.Tensor, rgb: torch.Tensor, lr_scale: float = 1.0) -> None:
         """One iteration on a device-resident batch (fp32 NCHW in [-1,1])."""
-        self.ir.copy_(ir, non_blocking=True); self.rgb.copy_(rgb, non_blocking=True)
+        if ir.device.type == "cpu" and self.ir.is_cuda:
+            self._stage_host_batch(ir, rgb)
+        else:
+            self.ir.copy_(ir, non_blocking=True); self.rgb.copy_(rgb, non_blocking=True)
         gs = 1.0 / self.world
         self.optD.advance(lr_scale, gs); self.optG.advance(lr_scale, gs)
         if not self.use_graph:
@@ -252,9 +273,54 @@ class TrainStep:
             self.launches_per_step = self.be.launches - n0
         self.graph.replay()
 
+    def _stage_host_batch(self, ir: torch.Tensor, rgb: torch.Tensor) -> None:
+        """Host (pinned) batch: the H2D copy runs on a copy stream into one of two staging buffers, so the copy of iteration
+        i + 1 overlaps the kernels of iteration i whenever the caller does not synchronise in between (`losses_async`); the
+        iteration's own stream then waits for the copy and moves the batch into the buffers the captured graph reads (a 17 MB
+        device-to-device copy, ~6 us).  Usual non_blocking contract: the host tensors must stay untouched until the copy ran."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = [(torch.empty_like(self.ir), torch.empty_like(self.rgb)) for _ in range(2)]
+            self._stage_ready = [torch.cuda.Event() for _ in range(2)]
+            self._stage_free = [torch.cuda.Event() for _ in range(2)]
+            self._stage_k = 0
+            for e in self._stage_free:
+                e.record()
+        k = self._stage_k
+        self._stage_k ^= 1
+        main, cs = torch.cuda.current_stream(), self._copy_stream
+        cs.wait_event(self._stage_free[k])          # the iteration that used this staging pair two calls ago has read it
+        with torch.cuda.stream(cs):
+            self._stage[k][0].copy_(ir, non_blocking=True); self._stage[k][1].copy_(rgb, non_blocking=True)
+            self._stage_ready[k].record(cs)
+        main.wait_event(self._stage_ready[k])
+        self.ir.copy_(self._stage[k][0], non_blocking=True); self.rgb.copy_(self._stage[k][1], non_blocking=True)
+        self._stage_free[k].record(main)
+
+    def losses_async(self) -> "LossHandle":
+        """Queue the device-to-host read of this iteration's loss sums (pinned ring slot + event) and return a handle; `get()`
+        on it synchronises with that read only.  A loop that calls `step(); h = losses_async()` and reads the previous handle
+        keeps one iteration of work queued, so host-side batch preparation and the H2D copy overlap the kernels."""
+        if not self.sums.is_cuda:
+            return LossHandle(self, self.sums.clone(), None)
+        if getattr(self, "_loss_ring", None) is None:
+            self._loss_ring = [[torch.empty(self.sums.shape, dtype=self.sums.dtype).pin_memory(), torch.cuda.Event(), None] for _ in range(4)]
+            self._loss_i = 0
+        slot = self._loss_ring[self._loss_i % len(self._loss_ring)]
+        self._loss_i += 1
+        if slot[2] is not None:
+            slot[2]._materialize()          # an unread handle still owns this pinned slot: take its values out first
+        buf, ev = slot[0], slot[1]
+        buf.copy_(self.sums, non_blocking=True)
+        ev.record()
+        slot[2] = LossHandle(self, buf, ev)
+        return slot[2]
+
     def losses(self) -> Dict[str, float]:
         """Loss terms of the last iteration, as printed by the reference (irc:1687-1694).  Synchronises."""
-        s = self.sums.tolist()
+        return self._loss_terms(self.sums.tolist())
+
+    def _loss_terms(self, s) -> Dict[str, float]:
         B, H, W, lam = self.B, self.H, self.W, self.lam
         cnt = B * self.n_pred
         npix = B * 3 * H * W
