@@ -818,8 +818,8 @@ conv_gemm_pack_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_co
     uint64_t* tfull = bars + 2 * S;
     uint64_t* tempty = bars + 2 * S + 2;
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
-    float* xbuf = reinterpret_cast<float*>((uint8_t*)bars + 256);              // [2][4 quarters][2 halves][32] boundary rows
-    uint8_t* stg = smem + (size_t)S * stage_bytes + 4096;                      // 2 x 16 KB staging tiles
+    float* xbuf = reinterpret_cast<float*>((uint8_t*)bars + 256);              // [2 groups][2 passes][2 dirs][4 quarters][32] boundary rows (4 KB)
+    uint8_t* stg = smem + (size_t)S * stage_bytes + 8192;                      // 2 x 16 KB staging tiles
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long total_tiles = (p.rows + kPackRows - 1) / kPackRows;
@@ -830,7 +830,7 @@ conv_gemm_pack_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_co
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmOut);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
         fence_barrier_init();
     }
     __shared__ __align__(16) float sbias[512];
@@ -893,75 +893,86 @@ conv_gemm_pack_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_co
         }
     } else {
         // ===================== epilogue: shifted sum of the three column groups, then the usual per-row math =====================
+        // Two groups of four warps; group g owns accumulator buffer g, i.e. every second tile of this CTA, and walks its 64 output
+        // channels in two passes of 32 (3 x 32 accumulator columns in registers per pass).  While one group is in its shuffle /
+        // pack / store phase the other one is reading TMEM, so the 64 B/clk TMEM read path (1536 cycles per tile) stays busy:
+        // with all eight warps on one tile the two phases alternated and a tile took ~4500 cycles against a 1900-cycle main
+        // loop at 64 input channels (profiles/r3/narrow_v2_with_packed.txt).
         const int quarter = warp & 3;                 // TMEM lane quarter
-        const int half = (warp - 2) >> 2;             // 32 of the 64 output channels
+        const int grp = (warp - 2) >> 2;              // epilogue group == accumulator buffer
         const int r_in_tile = quarter * 32 + lane;
+        const uint32_t bar_id = 1 + grp;
         EpiCtx e;
         e.slope_eff = p.act == 1 ? 0.f : (p.act == 2 ? p.slope : 1.f);
         e.sbias = p.bias ? sbias : nullptr;
-        int acc = 0; uint32_t acc_phase = 0;
-        uint32_t stg_iter = 0;
-        const bool store_thread = warp == 2 && lane == 0;
-        float* x_up = xbuf + (quarter * 2 + half) * 32;             // this warp's lane-31 P_0 row, read by quarter + 1
-        float* x_dn = xbuf + 256 + (quarter * 2 + half) * 32;       // this warp's lane-0 P_2 row, read by quarter - 1
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        uint32_t acc_phase = 0;
+        const bool st_thread = (warp == 2 + 4 * grp) && lane == 0;
+        uint8_t* buf = stg + grp * (kBM * 128);
+        float* xg = xbuf + grp * 512;                 // [pass][dir][quarter][32]
+        for (long long tile = blockIdx.x + (long long)grp * gridDim.x; tile < total_tiles; tile += 2LL * gridDim.x) {
             const long long row0 = tile * kPackRows - 1;
             const long long row = row0 + r_in_tile;
             const bool valid = r_in_tile >= 1 && r_in_tile <= kPackRows && row < p.rows;
             int img = 0;
             if (p.row_img) img = valid ? (int)p.row_img[row] : -1;      // issued before the accumulator wait: latency hidden
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(half * 32);
-            uint32_t r0[32], r1[32], r2[32];
-            tmem_ld32(taddr, r0);
-            tmem_ld32(taddr + 64, r1);
-            tmem_ld32(taddr + 128, r2);
-            tmem_ld_wait();
-            tc_fence_before();
-            if (lane == 31) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x_up[j] = __uint_as_float(r0[j]);
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x_dn[j] = __uint_as_float(r2[j]);
-            }
-            uint8_t* buf = stg + (stg_iter & 1) * (kBM * 128);
-            if (store_thread) bulk_wait_group_read<1>();           // the staging tile of two tiles ago has left
-            named_bar_sync(1, 256);
-            if (lane == 0) mbar_arrive(&tempty[acc]);              // all eight warps hold their accumulator columns in registers
-            uint32_t c[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);
-                float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);
-                if (lane == 0 && quarter > 0) up = xbuf[((quarter - 1) * 2 + half) * 32 + j];
-                if (lane == 31 && quarter < 3) dn = xbuf[256 + ((quarter + 1) * 2 + half) * 32 + j];
-                c[j] = __float_as_uint(up + __uint_as_float(r1[j]) + dn);
-            }
             const bool live = valid && img >= 0;
-            float v[32];
-            epi_math32(p, e, c, v, row, half * 32, live);
-            if (r_in_tile >= 1 && r_in_tile <= kPackRows) {
-                const int sr = r_in_tile - 1;                      // staging row: the 126 outputs of the tile start at row 0
+            mbar_wait(&tfull[grp], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)grp * acc_cols + (uint32_t)(half * 32);
+                uint32_t r0[32], r1[32], r2[32];
+                tmem_ld32(taddr, r0);
+                tmem_ld32(taddr + 64, r1);
+                tmem_ld32(taddr + 128, r2);
+                tmem_ld_wait();
+                if (half == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[grp]);          // this warp holds the last of its accumulator columns
+                }
+                float* xp = xg + half * 256;
+                if (lane == 31) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int chunk = (half * 4 + g) ^ (sr & 7);
-                    *reinterpret_cast<uint4*>(buf + sr * 128 + chunk * 16) =
-                        make_uint4(pack_bf16x2(v[g * 8], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
-                                   pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+                    for (int j = 0; j < 32; ++j) xp[quarter * 32 + j] = __uint_as_float(r0[j]);          // P_0 row read by quarter + 1
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) xp[128 + quarter * 32 + j] = __uint_as_float(r2[j]);    // P_2 row read by quarter - 1
+                }
+                if (half == 0 && st_thread) bulk_wait_group_read<0>();      // this group's staging tile of its previous tile has left
+                named_bar_sync(bar_id, 128);
+                uint32_t c[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);
+                    float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);
+                    if (lane == 0 && quarter > 0) up = xp[(quarter - 1) * 32 + j];
+                    if (lane == 31 && quarter < 3) dn = xp[128 + (quarter + 1) * 32 + j];
+                    c[j] = __float_as_uint(up + __uint_as_float(r1[j]) + dn);
+                }
+                float v[32];
+                epi_math32(p, e, c, v, row, half * 32, live);
+                if (r_in_tile >= 1 && r_in_tile <= kPackRows) {
+                    const int sr = r_in_tile - 1;                      // staging row: the 126 outputs of the tile start at row 0
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int chunk = (half * 4 + g) ^ (sr & 7);
+                        *reinterpret_cast<uint4*>(buf + sr * 128 + chunk * 16) =
+                            make_uint4(pack_bf16x2(v[g * 8], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                                       pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+                    }
                 }
             }
             fence_proxy_async();
-            named_bar_sync(1, 256);
-            if (store_thread) {
+            named_bar_sync(bar_id, 128);
+            if (st_thread) {
                 tma_store_2d(&tmOut, buf, p.out_chan_off, (int)(row0 + 1));
                 bulk_commit_group();
             }
-            ++stg_iter;
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            acc_phase ^= 1;
         }
+        if (st_thread) bulk_wait_group<0>();
     }
 
     if (warp == 2 && lane == 0) bulk_wait_group<0>();
@@ -1637,10 +1648,10 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
         if (rc) return rc;
         ConvParams q = p; q.mt = 1; q.nbuf = 2; q.nstg = 2;
         const int sbytes = kBM * 128 + 3 * 64 * 128;
-        int st = (kMaxSmem - kStatic - 1024 - 4096 - 2 * kBM * 128) / sbytes;
+        int st = (kMaxSmem - kStatic - 1024 - 8192 - 2 * kBM * 128) / sbytes;
         if (st > 6) st = 6;
         q.stages = st;
-        const size_t smem2 = (size_t)st * sbytes + 4096 + 2 * kBM * 128 + 1024;
+        const size_t smem2 = (size_t)st * sbytes + 8192 + 2 * kBM * 128 + 1024;
         static bool attr_pack = false;
         if (!attr_pack) {
             if (cudaFuncSetAttribute(conv_gemm_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 2048) != cudaSuccess)

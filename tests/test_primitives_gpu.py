@@ -577,6 +577,30 @@ def test_losses_vs_reference_golden(bes):
     assert torch.equal(d, torch.sign(a - b))
 
 
+@pytest.mark.parametrize("n,h,w", [(2, 45, 70), (1, 32, 64), (2, 256, 256), (1, 7, 5), (64, 128, 160)])
+def test_ssim_loss_paths(bes, n, h, w):
+    """ssim_loss_torch (irc:714-750) value and gradient against the oracle's autograd at sizes that do not divide the 64 x 32
+    32 x 16 tiles, at the train-step plane size, below the window size, and on the streaming kernels (large batch)"""
+    import irc_oracle as O
+    from irc_b200.train_step import gaussian_window
+    be = bes[0]
+    g = gen(31)
+    a = torch.tanh(torch.randn(n, 3, h, w, device="cuda", generator=g)); b = torch.rand(n, 3, h, w, device="cuda", generator=g) * 2 - 1
+    x = a.cpu().clone().requires_grad_(True)
+    loss = O.ssim_loss((x + 1) / 2, (b.cpu() + 1) / 2)
+    loss.backward()
+    win = gaussian_window()
+    ss = torch.zeros(n, device="cuda"); ga, gb, gc = (torch.zeros_like(a) for _ in range(3))
+    be.ssim_fwd(a, b, 0.5, 0.5, win, ss, ga, gb, gc)
+    assert abs(1.0 - ss.sum().item() / a.numel() - loss.item()) < 2e-5
+    d = torch.zeros_like(a)
+    be.ssim_bwd(a, b, 0.5, 0.5, win, ga, gb, gc, -1.0 / a.numel(), d, False)
+    close(d, x.grad.cuda(), 2e-3, "ssim grad")
+    d2 = d.clone()
+    be.ssim_bwd(a, b, 0.5, 0.5, win, ga, gb, gc, -1.0 / a.numel(), d2, True)
+    close(d2, 2.0 * x.grad.cuda(), 2e-3, "ssim grad (accumulate)")
+
+
 @pytest.mark.parametrize("h,w", [(20, 32), (17, 30), (64, 260), (70, 640), (5, 132), (1, 8)])
 def test_pixel_loss_paths(bes, h, w):
     """fused L1 + TV (irc:686-694, :1664): the streaming kernel (W % 4 == 0: several column tiles, strips that do not divide H,
