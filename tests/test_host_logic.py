@@ -52,6 +52,7 @@ def test_train_step_plan_matches_reference(fp32_frames):
     ts.load(pG, pD, pV)
     ts.step(ir, rgb)
     los = ts.losses()
+    assert ts.losses_async().get() == los          # the handle form returns the same terms (on the CPU it is a plain copy)
     for k in ("D", "G", "GAN", "L1", "perc", "TV", "SSIM"):
         ref = float(GOLD["loss_" + k])
         assert abs(los[k] - ref) < 3e-5 * max(1.0, abs(ref)), (k, los[k], ref)
