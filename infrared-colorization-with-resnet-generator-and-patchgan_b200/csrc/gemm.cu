@@ -220,8 +220,26 @@ __device__ __forceinline__ void epilogue_subtile(const ConvParams& p, const EpiC
 // Staged epilogue of one 128-row sub-tile (bf16 output, bn % 64 == 0): the eight epilogue warps convert 64 columns at a
 // time (two warps per 32-row quarter, 32 columns each) into a SWIZZLE_128B [128 rows][64 ch] shared-memory tile with
 // conflict-free 16-byte stores, and one thread hands it to the TMA store engine; two staging tiles alternate.
+// One-step-ahead prefetch of the epilogue's global operands (row_img entry, mask / addend rows).  They do not depend on the
+// accumulator, so prefetch instructions for the NEXT 64-column chunk / sub-tile / tile are issued while the current one is
+// converted (no registers held: the real loads then hit L2); the first ones of a kernel go out before the wait for the first
+// accumulator.  Measured need (scripts/prof_epi.py): with the loads
+// issued inside the chunk, a ReLU mask costs the 64 -> 64 full-resolution data gradient 93 us on top of 190, bias + ReLU + ring 34 us.
+struct EpiNext { bool on; };      // (no payload: the next step's operands are pulled into L2 / L1 by prefetch instructions, not registers)
+
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+// prefetch the epilogue operands of (row, 32-column chunk `col`): 64 bytes of mask / addend per thread, one row_img entry
+__device__ __forceinline__ void epi_fetch_next(const ConvParams& p, long long row, int col) {
+    if (row >= p.rows) return;
+    if (p.row_img) prefetch_l2(p.row_img + row);
+    if (p.mask) prefetch_l2(p.mask + row * p.mask_ld + p.mask_chan_off + col);
+    if (p.addend) prefetch_l2(p.addend + row * p.addend_ld + p.addend_chan_off + col);
+}
+
 __device__ __forceinline__ void epilogue_subtile_staged(const ConvParams& p, const EpiCtx& e, const CUtensorMap* tmOut, long long row0, int r_in_tile,
-                                                        int n0, uint32_t taddr, int half, uint8_t* stg, uint32_t& stg_iter, bool store_thread) {
+                                                        int n0, uint32_t taddr, int half, uint8_t* stg, uint32_t& stg_iter, bool store_thread,
+                                                        EpiNext* carry = nullptr, long long next_row0 = -1, int next_n0 = 0) {
     const long long row = row0 + r_in_tile;
     const bool in_range = row < p.rows;
     int img = 0;
@@ -234,7 +252,12 @@ __device__ __forceinline__ void epilogue_subtile_staged(const ConvParams& p, con
         tmem_ld32(taddr + cc, r);                         // TMEM read overlaps the wait for the staging tile
         EpiPre pre;
         epi_prefetch(p, pre, row, n0 + cc, in_range);     // ... and so do the mask / addend rows of this chunk (ring rows included:
-                                                          // no dependence on the row_img load)
+                                                          // no dependence on the row_img load); L2 hits when the step before prefetched them
+        if (carry != nullptr) {
+            // the step after this one: next chunk of this sub-tile (same row), else the first chunk of the next sub-tile / tile
+            if (c0 + 64 < p.bn) epi_fetch_next(p, row, n0 + cc + 64);
+            else if (next_row0 >= 0) epi_fetch_next(p, next_row0 + r_in_tile, next_n0 + half * 32);
+        }
         if (store_thread) { if (p.nstg == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>(); }   // buffer drained by its last TMA store
         named_bar_sync(1, 256);
         tmem_ld_wait();
@@ -345,6 +368,12 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, const CU
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t stg_iter = 0;
     const bool store_thread = warp == 2 && lane == 0;
+    EpiNext carry;
+    carry.on = true;
+    const bool use_carry = p.tma_store && !p.tap_out && (p.mask != nullptr || p.addend != nullptr || p.row_img != nullptr);
+    if (use_carry && (long long)blockIdx.x < total_tiles)
+        epi_fetch_next(p, ((long long)blockIdx.x / p.n_tiles) * p.tile_stride + p.row_bias + r_in_tile,
+                       (int)((long long)blockIdx.x % p.n_tiles) * p.bn + half * 32);
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (int)(tile % p.n_tiles) * p.bn;
         mbar_wait(&tfull[acc], acc_phase);
@@ -359,8 +388,18 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvParams& p, const CU
         for (int m = 0; m < MT; ++m) {
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(m * p.bn);
             const long long srow0 = (tile / p.n_tiles) * p.tile_stride + p.row_bias + m * kBM;
-            if (p.tma_store) epilogue_subtile_staged(p, e, tmOut, srow0, r_in_tile, n0, taddr, half, stg, stg_iter, store_thread);
-            else epilogue_subtile(p, e, srow0 + r_in_tile, n0, taddr, half);
+            if (p.tma_store) {
+                long long nrow0 = -1; int nn0 = n0;
+                if (use_carry) {
+                    if (m + 1 < MT) nrow0 = srow0 + kBM;
+                    else if (tile + gridDim.x < total_tiles) {
+                        const long long t2 = tile + gridDim.x;
+                        nrow0 = (t2 / p.n_tiles) * p.tile_stride + p.row_bias;
+                        nn0 = (int)(t2 % p.n_tiles) * p.bn;
+                    }
+                }
+                epilogue_subtile_staged(p, e, tmOut, srow0, r_in_tile, n0, taddr, half, stg, stg_iter, store_thread, use_carry ? &carry : nullptr, nrow0, nn0);
+            } else epilogue_subtile(p, e, srow0 + r_in_tile, n0, taddr, half);
         }
         tc_fence_before();
         __syncwarp();
@@ -602,14 +641,26 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_co
         uint32_t stg_iter = 0;
         const bool store_thread = warp == 2 && lane == 0;
         const uint32_t tempty_leader[2] = {mapa_u32(smem_u32(&tempty[0]), 0), mapa_u32(smem_u32(&tempty[1]), 0)};
+        EpiNext carry;
+        carry.on = true;
+        const bool use_carry = p.tma_store && (p.mask != nullptr || p.addend != nullptr || p.row_img != nullptr);
+        if (use_carry && pair0 < total_tiles)
+            epi_fetch_next(p, (pair0 / p.n_tiles) * (2 * kBM) + (long long)rank * kBM + r_in_tile, (int)(pair0 % p.n_tiles) * p.bn + half * 32);
         for (long long tile = pair0; tile < total_tiles; tile += pairs) {
             const int n0 = (int)(tile % p.n_tiles) * p.bn;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols;
             const long long srow0 = (tile / p.n_tiles) * (2 * kBM) + (long long)rank * kBM;
-            if (p.tma_store) epilogue_subtile_staged(p, e, &tmOut, srow0, r_in_tile, n0, taddr, half, stg, stg_iter, store_thread);
-            else epilogue_subtile(p, e, srow0 + r_in_tile, n0, taddr, half);
+            if (p.tma_store) {
+                long long nrow0 = -1; int nn0 = n0;
+                if (use_carry && tile + pairs < total_tiles) {
+                    const long long t2 = tile + pairs;
+                    nrow0 = (t2 / p.n_tiles) * (2 * kBM) + (long long)rank * kBM;
+                    nn0 = (int)(t2 % p.n_tiles) * p.bn;
+                }
+                epilogue_subtile_staged(p, e, &tmOut, srow0, r_in_tile, n0, taddr, half, stg, stg_iter, store_thread, use_carry ? &carry : nullptr, nrow0, nn0);
+            } else epilogue_subtile(p, e, srow0 + r_in_tile, n0, taddr, half);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(tempty_leader[acc]);

@@ -907,7 +907,9 @@ class VggEngine:
         for i, conv in enumerate(self.convs):
             fr = self.act[i]
             if not (direct and i == 0):
-                conv.fwd(src, 0, fr.t, bias=conv.bias(), act=ACT_RELU, row_img=self._ri(i))
+                # the frames that feed a max-pool (conv1_2, conv2_2) are only ever read at interior pixels: their ring rows need no
+                # zeroing, which spares the epilogue the row_img lookup (21 us at the conv1_2 shape, scripts/prof_epi.py)
+                conv.fwd(src, 0, fr.t, bias=conv.bias(), act=ACT_RELU, row_img=None if i in self.pool else self._ri(i))
             if i in self.pool:
                 h, w = self.res[i + 1]
                 be.maxpool2(fr.view(), self.pool[i].view(), fr.C, self.n, h, w)
