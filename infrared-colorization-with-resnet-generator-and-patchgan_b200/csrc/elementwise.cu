@@ -1844,56 +1844,86 @@ __global__ void __launch_bounds__(256, 3) in_apply_fused_kernel(const GatherP p,
 // ---------------------------------------------------------------------------------
 // 2x2 max pool (VGG trunk, irc:664) on frames, and its backward fused with the ReLU mask
 // ---------------------------------------------------------------------------------
-__global__ void maxpool_kernel(View src, View dst, int C, int n_img, int Ho, int Wo) {
+// One block row = one output row of one image (block-uniform decode, no per-element division); thread = (channel vector, pixel
+// lane); two output pixels per step with their eight 16-byte loads issued together.  Non space-to-depth views only.
+__global__ void __launch_bounds__(256, 4) maxpool_kernel(View src, View dst, int C, int n_img, int Ho, int Wo) {
     irc::pdl_prologue();
     const int C8 = C >> 3;
-    const long long total = (long long)n_img * Ho * Wo * C8;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % C8) * 8;
-        long long pix = idx / C8;
-        const int x = (int)(pix % Wo); pix /= Wo;
-        const int y = (int)(pix % Ho);
-        const int n = (int)(pix / Ho);
-        float m[8], v[8];
-        load8(src.at(n, 2 * y, 2 * x, c), m);
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int c = cv * 8;
+    const int sld = (int)src.ld, dld = (int)dst.ld;
+    const int srow = src.wp * sld;
+    for (int row = blockIdx.x; row < n_img * Ho; row += gridDim.x) {
+        const int n = row / Ho, y = row - n * Ho;
+        const bf16* s0 = src.at(n, 2 * y, 0, c);
+        bf16* d0 = const_cast<bf16*>(dst.at(n, y, 0, c));
+        for (int x0 = lane; x0 < Wo; x0 += 2 * L) {
+            uint4 u[2][4];
 #pragma unroll
-        for (int t = 1; t < 4; ++t) {
-            load8(src.at(n, 2 * y + (t >> 1), 2 * x + (t & 1), c), v);
+            for (int q = 0; q < 2; ++q) {
+                const int x = x0 + q * L;
+                if (x < Wo) {
+                    const bf16* sp = s0 + 2 * x * sld;
+                    u[q][0] = __ldg(reinterpret_cast<const uint4*>(sp));
+                    u[q][1] = __ldg(reinterpret_cast<const uint4*>(sp + sld));
+                    u[q][2] = __ldg(reinterpret_cast<const uint4*>(sp + srow));
+                    u[q][3] = __ldg(reinterpret_cast<const uint4*>(sp + srow + sld));
+                }
+            }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
+            for (int q = 0; q < 2; ++q) {
+                const int x = x0 + q * L;
+                if (x < Wo) {
+                    float m[8], v[8];
+                    unpack8(u[q][0], m);
+#pragma unroll
+                    for (int t = 1; t < 4; ++t) {
+                        unpack8(u[q][t], v);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
+                    }
+                    store8(d0 + x * dld, m);
+                }
+            }
         }
-        store8(const_cast<bf16*>(dst.at(n, y, x, c)), m);
     }
 }
 // dsrc[n, y, x] = g[n, y/2, x/2] if src[n,y,x] is the first maximum of its window and src > 0, else 0
-__global__ void maxpool_bwd_kernel(View src, View g, View dsrc, int C, int n_img, int Ho, int Wo) {
+__global__ void __launch_bounds__(256, 4) maxpool_bwd_kernel(View src, View g, View dsrc, int C, int n_img, int Ho, int Wo) {
     irc::pdl_prologue();
     const int C8 = C >> 3;
-    const long long total = (long long)n_img * Ho * Wo * C8;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % C8) * 8;
-        long long pix = idx / C8;
-        const int x = (int)(pix % Wo); pix /= Wo;
-        const int y = (int)(pix % Ho);
-        const int n = (int)(pix / Ho);
-        float v[4][8], gv[8];
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    const int c = cv * 8;
+    const int sld = (int)src.ld, gld = (int)g.ld, dld = (int)dsrc.ld;
+    const int srow = src.wp * sld, drow = dsrc.wp * dld;
+    for (int row = blockIdx.x; row < n_img * Ho; row += gridDim.x) {
+        const int n = row / Ho, y = row - n * Ho;
+        const bf16* s0 = src.at(n, 2 * y, 0, c);
+        const bf16* g0 = g.at(n, y, 0, c);
+        bf16* d0 = const_cast<bf16*>(dsrc.at(n, 2 * y, 0, c));
+        for (int x = lane; x < Wo; x += L) {
+            const bf16* sp = s0 + 2 * x * sld;
+            const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(sp)), u1 = __ldg(reinterpret_cast<const uint4*>(sp + sld));
+            const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(sp + srow)), u3 = __ldg(reinterpret_cast<const uint4*>(sp + srow + sld));
+            const uint4 ug = __ldg(reinterpret_cast<const uint4*>(g0 + x * gld));
+            float v[4][8], gv[8];
+            unpack8(u0, v[0]); unpack8(u1, v[1]); unpack8(u2, v[2]); unpack8(u3, v[3]); unpack8(ug, gv);
+            int arg[8];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) load8(src.at(n, 2 * y + (t >> 1), 2 * x + (t & 1), c), v[t]);
-        load8(g.at(n, y, x, c), gv);
-        int arg[8];
+            for (int k = 0; k < 8; ++k) {
+                int a = 0; float m = v[0][k];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            int a = 0; float m = v[0][k];
+                for (int t = 1; t < 4; ++t) if (v[t][k] > m) { m = v[t][k]; a = t; }
+                arg[k] = m > 0.f ? a : -1;
+            }
+            bf16* dp = d0 + 2 * x * dld;
 #pragma unroll
-            for (int t = 1; t < 4; ++t) if (v[t][k] > m) { m = v[t][k]; a = t; }
-            arg[k] = m > 0.f ? a : -1;
-        }
+            for (int t = 0; t < 4; ++t) {
+                float o[8];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            float o[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = arg[k] == t ? gv[k] : 0.f;
-            store8(const_cast<bf16*>(dsrc.at(n, 2 * y + (t >> 1), 2 * x + (t & 1), c)), o);
+                for (int k = 0; k < 8; ++k) o[k] = arg[k] == t ? gv[k] : 0.f;
+                store8(dp + (t >> 1) * drow + (t & 1) * dld, o);
+            }
         }
     }
 }
@@ -2386,8 +2416,12 @@ extern "C" int irc_in_bwd_fused(const irc_in_bwd_args* a, int fold_pad, void* st
 extern "C" int irc_maxpool2(const irc_view* src, const irc_view* dst, int C, int n_img, int Ho, int Wo, void* stream) {
     int rc = check_view(*src, "irc_maxpool2 src"); if (rc) return rc;
     rc = check_view(*dst, "irc_maxpool2 dst"); if (rc) return rc;
-    const long long total = (long long)n_img * Ho * Wo * (C / 8);
-    irc::launch(maxpool_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, mk(*src), mk(*dst), C, n_img, Ho, Wo);
+    if (C % 8 || src->s2d_c || dst->s2d_c) return irc_set_error(IRC_ERR_BAD_ARG, "irc_maxpool2: C %% 8 == 0, plain (not space-to-depth) views");
+    int threads, L;
+    row_block(C, Wo, threads, L);
+    const long long rows = (long long)n_img * Ho;
+    const unsigned grid = (unsigned)(rows < (long long)irc_num_sms() * 8 ? rows : (long long)irc_num_sms() * 8);
+    irc::launch(maxpool_kernel, grid, threads, 0, (cudaStream_t)stream, mk(*src), mk(*dst), C, n_img, Ho, Wo);
     return irc_check_launch("irc_maxpool2");
 }
 
@@ -2395,8 +2429,12 @@ extern "C" int irc_maxpool2_bwd(const irc_view* src, const irc_view* g, const ir
     int rc = check_view(*src, "irc_maxpool2_bwd src"); if (rc) return rc;
     rc = check_view(*g, "irc_maxpool2_bwd g"); if (rc) return rc;
     rc = check_view(*dsrc, "irc_maxpool2_bwd dsrc"); if (rc) return rc;
-    const long long total = (long long)n_img * Ho * Wo * (C / 8);
-    irc::launch(maxpool_bwd_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, mk(*src), mk(*g), mk(*dsrc), C, n_img, Ho, Wo);
+    if (C % 8 || src->s2d_c || g->s2d_c || dsrc->s2d_c) return irc_set_error(IRC_ERR_BAD_ARG, "irc_maxpool2_bwd: C %% 8 == 0, plain (not space-to-depth) views");
+    int threads, L;
+    row_block(C, Wo, threads, L);
+    const long long rows = (long long)n_img * Ho;
+    const unsigned grid = (unsigned)(rows < (long long)irc_num_sms() * 8 ? rows : (long long)irc_num_sms() * 8);
+    irc::launch(maxpool_bwd_kernel, grid, threads, 0, (cudaStream_t)stream, mk(*src), mk(*g), mk(*dsrc), C, n_img, Ho, Wo);
     return irc_check_launch("irc_maxpool2_bwd");
 }
 
