@@ -1947,6 +1947,45 @@ __global__ void colsum_kernel(const bf16* a, long long rows, long long ld, int o
     }
 }
 
+// Vectorised form (C, off, ld multiples of 8): thread = (channel vector, row lane), 16-byte loads, four rows in flight per thread;
+// the row lanes of a block are combined through shared memory in a fixed order.  (The scalar kernel above reads two bytes per
+// thread and row: 54 us for the 69 MB of model.0's bias gradient.)
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const bf16* __restrict__ a, long long rows, long long ld, int off, int C,
+                                                        const short* __restrict__ row_img, float* __restrict__ part) {
+    irc::pdl_prologue();
+    extern __shared__ float cs_sh[];          // [L][C]
+    const int C8 = C >> 3;
+    const int cv = threadIdx.x % C8, lane = threadIdx.x / C8, L = blockDim.x / C8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long long step = (long long)gridDim.x * L;
+    const bf16* base = a + off + cv * 8;
+    for (long long r0 = blockIdx.x * (long long)L + lane; r0 < rows; r0 += 4 * step) {
+        uint4 u[4]; bool on[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long r = r0 + q * step;
+            on[q] = r < rows && (!row_img || __ldg(row_img + r) >= 0);
+            if (on[q]) u[q] = __ldg(reinterpret_cast<const uint4*>(base + r * ld));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (on[q]) {
+                float v[8];
+                unpack8(u[q], v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += v[k];
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cs_sh[lane * C + cv * 8 + k] = acc[k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float t = 0.f;
+        for (int i = 0; i < L; ++i) t += cs_sh[i * C + c];
+        part[(long long)blockIdx.x * C + c] = t;
+    }
+}
+
 // In-place transpose of ReflectionPad2d(p) on a frame that holds the gradient w.r.t. the padded tensor: every interior
 // pixel within p of the border adds the ring pixels that mirror onto it (ring pixels are only read, each thread writes
 // its own pixel: race-free) and clears them.  Touches O(p * perimeter) pixels instead of a full pass.
@@ -2447,6 +2486,15 @@ extern "C" int irc_colsum(const void* a, long long rows, long long ld, int chan_
     if (bx <= 1) {
         irc::launch(colsum_kernel, dim3(1, (C + 31) / 32), 1024, 0, (cudaStream_t)stream, (const bf16*)a, rows, ld, chan_off, C, row_img, out);
         return irc_check_launch("irc_colsum");
+    }
+    if (C % 8 == 0 && chan_off % 8 == 0 && ld % 8 == 0 && !((uintptr_t)a & 15) && C <= 2048 && 256 % (C / 8) == 0) {
+        const int L = 256 / (C / 8);
+        long long bv = (rows + 4 * L - 1) / (4 * L); if (bv > irc_num_sms() * 4) bv = irc_num_sms() * 4;
+        if (bv > cap) bv = cap;
+        if (bv < 1) bv = 1;
+        irc::launch(colsum_vec_kernel, (unsigned)bv, 256, (size_t)L * C * sizeof(float), (cudaStream_t)stream, (const bf16*)a, rows, ld, chan_off, C, row_img, work);
+        irc::launch(sum_chunks_kernel, grid_for((long long)C * 32, 256), 256, 0, (cudaStream_t)stream, work, (int)bv, C, out);
+        return irc_check_launch("irc_colsum(vec)");
     }
     irc::launch(colsum_kernel, dim3((unsigned)bx, (C + 31) / 32), 1024, 0, (cudaStream_t)stream, (const bf16*)a, rows, ld, chan_off, C, row_img, work);
     irc::launch(sum_chunks_kernel, grid_for((long long)C * 32, 256), 256, 0, (cudaStream_t)stream, work, (int)bx, C, out);
