@@ -1743,7 +1743,7 @@ __global__ void __launch_bounds__(256, 3) in_bwd_fused_kernel(const InBwdP p, in
 // backward pass needs, and produces the activated frame - interior and ring - from the staged values.
 // ---------------------------------------------------------------------------------
 template <int kAct>
-__global__ void __launch_bounds__(256, 3) in_apply_fused_kernel(const GatherP p, float* stats_out) {
+__global__ void __launch_bounds__(256, 4) in_apply_fused_kernel(const GatherP p, float* stats_out) {
     irc::pdl_prologue();
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned CL = cluster.num_blocks(), rank = cluster.block_rank();
@@ -2301,12 +2301,14 @@ extern "C" int irc_in_apply_fused(const irc_gather_args* a, float* stats_out, vo
     unsigned cl = 1;
     while ((long long)cl * kFusedNP * kFusedLanes < hw) cl *= 2;
     const dim3 grid(cl, p.C / kFusedCC, p.n_img);
-    const size_t smem = 2 * kFusedNP * 256 * sizeof(uint4);
+    // without a residual only the z half of the staging area is used: 32 KB per CTA, four CTAs per SM instead of three
+    const size_t smem_max = 2 * kFusedNP * 256 * sizeof(uint4);
+    const size_t smem = (p.has_res ? 2 : 1) * kFusedNP * 256 * sizeof(uint4);
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(in_apply_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(in_apply_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(in_apply_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(in_apply_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        cudaFuncSetAttribute(in_apply_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        cudaFuncSetAttribute(in_apply_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         attr = true;
     }
     cudaStream_t st = (cudaStream_t)stream;

@@ -126,6 +126,7 @@ print("\n# cluster InstanceNorm backward of the ResNet bottleneck with / without
 timeit("in_bwd fused 256ch 64^2, fold_pad=1", lambda: be.in_bwd(Zb.view(), Gh.view(), dZa.view(), 256, B, 64, 64, stats=s256, cnt=4096, act=1, bsum=bs, fold_pad=1), B * 4096 * 256 * 2 * 3)
 timeit("in_bwd fused 256ch 64^2, no fold", lambda: be.in_bwd(Zb.view(), Gh.view(), dZa.view(), 256, B, 64, 64, stats=s256, cnt=4096, act=1, bsum=bs), B * 4096 * 256 * 2 * 3)
 timeit("in_apply fused 256ch 64^2 (+res, reflect ring)", lambda: be.in_apply(Zb.view(), Y.view(), 256, B, 64, 64, 1, 1, s256, act=0, res=X.view()), B * 4096 * 256 * 2 * 3)
+timeit("in_apply fused 256ch 64^2 (ReLU, no residual, reflect ring)", lambda: be.in_apply(Zb.view(), Y.view(), 256, B, 64, 64, 1, 1, s256, act=1), B * 4096 * 256 * 2 * 2)
 be.fused_in_bwd = False
 for grp in (4, 8, 16):
     be.inbwd_l2_groups = grp
