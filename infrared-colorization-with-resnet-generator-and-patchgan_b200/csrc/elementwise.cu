@@ -1747,7 +1747,7 @@ __global__ void __launch_bounds__(256, 4) in_apply_fused_kernel(const GatherP p,
     irc::pdl_prologue();
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned CL = cluster.num_blocks(), rank = cluster.block_rank();
-    extern __shared__ uint4 raw[];      // [2][kFusedNP][256]: z then the residual
+    extern __shared__ uint4 raw[];      // [kFusedNP][256]: z
     __shared__ float part[64];
     __shared__ float wsum[8][64];
     __shared__ float tot[64];
@@ -1758,7 +1758,6 @@ __global__ void __launch_bounds__(256, 4) in_apply_fused_kernel(const GatherP p,
     const int p0 = rank * P, p1 = min(p0 + P, HW);
     const int np = p0 + lane < p1 ? (p1 - p0 - lane + kFusedLanes - 1) / kFusedLanes : 0;
     uint4* zs = raw + tid;
-    uint4* rsd = raw + kFusedNP * 256 + tid;
     const int pad = p.pad, W = p.W, H = p.H;
     VStep vs, vr, vd;
     vs.init(p.src, n, c, W); vr.init(p.has_res ? p.res : p.src, n, c, W); vd.init(p.dst, n, c, W);
@@ -1768,7 +1767,8 @@ __global__ void __launch_bounds__(256, 4) in_apply_fused_kernel(const GatherP p,
         for (int i = 0; i < kFusedNP; ++i) {
             if (i < np) {
                 cp_async16(zs + i * 256, vs.base + w.o0);
-                if (p.has_res) cp_async16(rsd + i * 256, vr.base + w.o1);
+                // the residual is not staged (that would cost the fourth CTA per SM): pulled towards L2 now, read in the apply loop
+                if (p.has_res) asm volatile("prefetch.global.L2 [%0];" ::"l"(vr.base + w.o1));
             } else {
                 zs[i * 256] = make_uint4(0, 0, 0, 0);
             }
@@ -1811,7 +1811,7 @@ __global__ void __launch_bounds__(256, 4) in_apply_fused_kernel(const GatherP p,
         }
         if (p.has_res) {
             float u[8];
-            unpack8(rsd[i * 256], u);
+            load8(vr.base + w.o1, u);
 #pragma unroll
             for (int k = 0; k < 8; ++k) v[k] += u[k];
         }
@@ -2301,9 +2301,9 @@ extern "C" int irc_in_apply_fused(const irc_gather_args* a, float* stats_out, vo
     unsigned cl = 1;
     while ((long long)cl * kFusedNP * kFusedLanes < hw) cl *= 2;
     const dim3 grid(cl, p.C / kFusedCC, p.n_img);
-    // without a residual only the z half of the staging area is used: 32 KB per CTA, four CTAs per SM instead of three
-    const size_t smem_max = 2 * kFusedNP * 256 * sizeof(uint4);
-    const size_t smem = (p.has_res ? 2 : 1) * kFusedNP * 256 * sizeof(uint4);
+    // only z is staged: 32 KB per CTA, four CTAs per SM
+    const size_t smem_max = kFusedNP * 256 * sizeof(uint4);
+    const size_t smem = smem_max;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(in_apply_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
