@@ -332,12 +332,14 @@ __device__ __forceinline__ void epilogue_tapsum(const ConvParams& p, long long r
     if (lane == 0) mbar_arrive(tempty_bar);              // the MMAs of the next tile may overwrite the accumulator
     const int halo = (p.tap_nshift - 1) >> 1;
     const int et = (int)threadIdx.x - 64;
-    const long long img_rows = (long long)p.tap_hp * p.tap_wp, hw = (long long)p.tap_H * p.tap_W;
+    const long long hw = (long long)p.tap_H * p.tap_W;
+    const int img_rows = p.tap_hp * p.tap_wp;            // frame rows per image (the host checks rows < 2^31: 32-bit index math)
     for (int r = halo + et; r < MT * kBM - halo; r += 256) {
         const long long q = row0 + r;
         if (q < 0 || q >= p.rows) continue;
-        const int n = (int)(q / img_rows);
-        const int rem = (int)(q - n * img_rows);
+        const int qi = (int)q;
+        const int n = qi / img_rows;
+        const int rem = qi - n * img_rows;
         const int Y = rem / p.tap_wp, X = rem - Y * p.tap_wp;
         const int y = Y - p.tap_oy, x = X - p.tap_ox;
         if (y < 0 || y >= p.tap_H || x < 0 || x >= p.tap_W) continue;
@@ -347,7 +349,9 @@ __device__ __forceinline__ void epilogue_tapsum(const ConvParams& p, long long r
             if (p.tap_act == 3) acc = tanhf(acc);
             if (p.tap_scale) acc *= __ldg(p.tap_scale + co);
             float* o = p.tap_out + ((long long)n * p.tap_nco + co) * hw + (long long)y * p.tap_W + x;
-            *o = p.tap_accumulate ? *o + acc : acc;
+            // accumulate: every output element has exactly one producer in this launch, so a reduction instruction gives the same
+            // bits as load-add-store without putting a global-load round trip on every tile's critical path
+            if (p.tap_accumulate) atomicAdd(o, acc); else *o = acc;
         }
     }
 }
@@ -1596,7 +1600,8 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     const bool tapsum = a->tap_out != nullptr;
     if (tapsum) {
         if (a->tap_nshift < 1 || !(a->tap_nshift & 1) || a->tap_nshift * a->tap_nco > 32 || a->n_out != 32 || a->tap_nco < 1 || a->mask || a->addend || a->row_img ||
-            (long long)a->tap_hp * a->tap_wp <= 0 || a->a_rows % ((long long)a->tap_hp * a->tap_wp) || (a->tap_act != 0 && a->tap_act != 3))
+            (long long)a->tap_hp * a->tap_wp <= 0 || a->a_rows % ((long long)a->tap_hp * a->tap_wp) || a->a_rows >= (1LL << 31) ||
+            (a->tap_act != 0 && a->tap_act != 3))
             return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm(tap mode): needs an odd number of horizontal taps with nshift * nco <= 32 = n_out, frames of hp x wp rows, act 0 or 3 (tanh)");
         if (mt != 1) mt = 2;
     }
