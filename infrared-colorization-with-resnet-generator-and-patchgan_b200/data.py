@@ -92,3 +92,66 @@ class GpuPairPreprocessor:
         if rgb_u8 is not None:
             out["rgb"] = self._one(rgb_u8, 3, flip_dev, False)
         return out
+
+
+class DevicePrefetcher:
+    """Iterates a loader of dict batches one batch ahead of its consumer: the tensors of batch i + 1 are copied to the device on a
+    side stream (pinned first when they are pageable) while batch i is being processed, and the consumer's stream only waits for
+    the copy event.  Two persistent sets of device buffers alternate (no allocator traffic per batch); a yielded batch stays valid
+    until the consumer asks for the batch after the next one.  On a CPU device it is a plain pass-through.  Non-tensor entries
+    (names) are forwarded untouched.
+
+        for batch in DevicePrefetcher(loader, device):      # batch['ir'] etc. already live on `device`
+            fake = model(batch['ir'])"""
+
+    def __init__(self, loader, device, pin: bool = True):
+        self.loader, self.device, self.pin = loader, torch.device(device), pin
+        self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+
+    def __iter__(self):
+        if self.stream is None:
+            for batch in self.loader:
+                yield batch
+            return
+        bufs = [dict(), dict()]          # slot -> key -> device tensor (allocated on the consumer's stream)
+        free_ev = [None, None]           # consumer's work on the slot's previous batch has been queued up to here
+
+        def stage(batch, k):
+            out = {}
+            for key, v in batch.items():
+                if torch.is_tensor(v) and v.device.type == "cpu":
+                    t = bufs[k].get(key)
+                    if t is None or t.shape != v.shape or t.dtype != v.dtype:
+                        t = bufs[k][key] = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                    out[key] = (t, v.pin_memory() if (self.pin and not v.is_pinned()) else v)
+                else:
+                    out[key] = v
+            if free_ev[k] is not None:
+                self.stream.wait_event(free_ev[k])
+            with torch.cuda.stream(self.stream):
+                for key, tv in out.items():
+                    if isinstance(tv, tuple):
+                        tv[0].copy_(tv[1], non_blocking=True)
+                        out[key] = tv[0]
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            return out, ev
+
+        it = iter(self.loader)
+        k = 0
+        nxt = None
+        for batch in it:
+            nxt = stage(batch, k)
+            break
+        while nxt is not None:
+            cur, ev = nxt
+            nxt = None
+            for batch in it:                      # stage the next batch (other slot) before handing out the current one
+                nxt = stage(batch, k ^ 1)
+                break
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(ev)
+            yield cur
+            free_ev[k] = torch.cuda.Event()
+            free_ev[k].record(torch.cuda.current_stream(self.device))
+            k ^= 1

@@ -330,10 +330,19 @@ def run_test(cfg: M.Config, loader=None):
     model.eval()
     rows: List[Dict] = []
     preds = []
+    pending = []          # (pinned host buffer, event) of the predictions on their way back
+
+    def shard():          # images are independent: shard the batches, no data-path collective
+        for bi_, batch_ in enumerate(loader):
+            if bi_ % world == rank:
+                batch_ = dict(batch_); batch_["_bi"] = bi_
+                yield batch_
+
+    from .data import DevicePrefetcher
     with torch.no_grad():
-        for bi, batch in enumerate(loader):
-            if bi % world != rank:            # images are independent: shard the batches, no data-path collective
-                continue
+        # the H2D copy of batch i + 1 overlaps the generator pass of batch i; the uint8 predictions travel back asynchronously
+        for batch in DevicePrefetcher(shard(), device):
+            bi = batch["_bi"]
             ir = batch["ir"].to(device)
             fake = model(ir)
             names = batch.get("name") or [f"img_{bi:05d}_{j}.png" for j in range(ir.shape[0])]
@@ -350,7 +359,16 @@ def run_test(cfg: M.Config, loader=None):
             else:
                 u8 = torch.empty(ir.shape[0], H, W, 3, device=device, dtype=torch.uint8)
                 M.backend().quantize_metrics(fake.contiguous().float(), None, u8, None)
-            preds.append(u8.cpu())
+            if u8.is_cuda:
+                host = torch.empty(u8.shape, dtype=u8.dtype, pin_memory=True)
+                host.copy_(u8, non_blocking=True)
+                ev = torch.cuda.Event(); ev.record()
+                pending.append((host, ev, u8))            # u8 kept alive until its copy has run
+            else:
+                preds.append(u8)
+    for host, ev, _ in pending:
+        ev.synchronize()
+        preds.append(host)
     rows = merge_test_rows(rows)
     print("Test finished.")
     summary = summarize_rows(rows)
