@@ -1045,6 +1045,7 @@ struct TnParams {
     int bn;                  // tile N (multiple of 64)
     int m_tiles, n_tiles, ntaps, splits, stages;
     int groups;              // tap groups: one CTA accumulates TPC taps into TPC independent TMEM tiles
+    int merge_taps;          // bn == 64: the taps of a group go through one MMA of N = 64 * taps (IRC_TN_MERGE=0 turns it off)
     int tmem_cols;
     int a_chan_off, b_chan_off;
     int a_shift[IRC_MAX_TAPS];
@@ -1123,6 +1124,7 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         const uint32_t idesc = umma_idesc_bf16(kBM, p.bn, 1, 1);
+        const bool merge_taps = TPC > 1 && p.bn == 64 && p.merge_taps;
         int stage = 0; uint32_t phase = 0;
         for (long long kb = 0; kb < my_kb; ++kb) {
             mbar_wait(&full[stage], phase);
@@ -1131,13 +1133,29 @@ tn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t adesc = umma_desc_sw128(sa, kBK * 128);
             const uint32_t accum = kb != 0;
             if (elect_one()) {
+                if (merge_taps) {
+                    // bn == 64: the taps' B tiles are consecutive 8 KB blocks = the 64-channel groups of ONE wider MN-major operand, and
+                    // their accumulators are consecutive 64-column blocks: up to four taps go through a single MMA of N = 64 * taps.
+                    // Every MMA re-reads its A slab from shared memory (~64 B/clk), so 4 x (A + 64 columns of B) costs 4 x 96 cycles,
+                    // A + 256 columns 192.
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) {   // 16 reduction rows = 2048 bytes per step
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        for (int t0 = 0; t0 < ntap; t0 += 4) {
+                            const int nt = ntap - t0 < 4 ? ntap - t0 : 4;
+                            const uint64_t bdesc = umma_desc_sw128(sa + stage_a + t0 * tile_b, kBK * 128);
+                            umma_bf16(tmem_base + (uint32_t)(t0 * 64), adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128),
+                                      umma_idesc_bf16(kBM, 64 * nt, 1, 1), k == 0 ? accum : 1u);
+                        }
+                    }
+                } else {
 #pragma unroll
-                    for (int t = 0; t < TPC; ++t) {
-                        if (t < ntap) {
-                            const uint64_t bdesc = umma_desc_sw128(sa + stage_a + t * tile_b, kBK * 128);
-                            umma_bf16(tmem_base + (uint32_t)(t * p.bn), adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, k == 0 ? accum : 1u);
+                    for (int k = 0; k < kBK / 16; ++k) {   // 16 reduction rows = 2048 bytes per step
+#pragma unroll
+                        for (int t = 0; t < TPC; ++t) {
+                            if (t < ntap) {
+                                const uint64_t bdesc = umma_desc_sw128(sa + stage_a + t * tile_b, kBK * 128);
+                                umma_bf16(tmem_base + (uint32_t)(t * p.bn), adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, k == 0 ? accum : 1u);
+                            }
                         }
                     }
                 }
@@ -1810,6 +1828,9 @@ extern "C" int irc_tn_gemm(const irc_tn_gemm_args* a, void* stream) {
     for (int i = 0; i < a->ntaps; ++i) { p.a_shift[i] = a->a_shift[i]; p.b_shift[i] = a->b_shift[i]; }
     p.out = a->out; p.out_tap_stride = a->out_tap_stride; p.out_m_stride = a->out_m_stride;
     p.out_n_stride = a->out_n_stride; p.out_split_stride = a->out_split_stride;
+    static int merge_mode = -1;
+    if (merge_mode < 0) { const char* e = getenv("IRC_TN_MERGE"); merge_mode = (e && e[0] == '0') ? 0 : 1; }
+    p.merge_taps = merge_mode;
     bool zero_a = true;
     for (int i = 0; i < a->ntaps; ++i) zero_a = zero_a && a->a_shift[i] == 0;
     if (a->tpc <= 0 && tn_pair_mode(a->m, a->ntaps, zero_a) && !getenv("IRC_TN_NOPAIR")) {

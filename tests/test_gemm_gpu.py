@@ -111,6 +111,8 @@ def test_conv_gemm_epilogue():
     (3000, 128, 128, 384, 384, 256, 128, [0, 5], 2),
     (6000, 128, 64, 128, 64, 0, 0, [-71, -70, -69, -1, 0, 1, 69, 70, 71], 5),       # 3 taps per CTA
     (6000, 21, 64, 64, 64, 0, 0, [-210, -140, -70, 0, 70, 140, 210], 4),            # 7 taps in one ragged group of 8
+    (5000, 128, 64, 128, 64, 0, 0, [-35, -34, -33, -1, 1, 33, 34, 35], 3),           # 64-wide tiles, 4 taps per CTA: one N = 256 MMA per step
+    (5000, 100, 50, 128, 64, 0, 0, [-36, -35, -34, 0, 34, 35, 36], 2),              # 7 taps: groups of 4 and 3 (N = 256 and N = 192), ragged m / n
     (4000, 512, 256, 512, 256, 0, 0, [r * 34 + s for r in range(4) for s in range(4)], 2),   # 2 taps per CTA, 4 M tiles
     (7000, 64, 192, 64, 192, 0, 0, [-259, -258, -257, -1, 0, 1, 257, 258, 259], 3),          # paired taps (m <= 64): 5 pairs, last one half empty
     (2500, 64, 128, 192, 320, 128, 64, [-3, 4], 1),                                          # paired taps, channel offsets, one pair
