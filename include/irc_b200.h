@@ -78,6 +78,9 @@ typedef struct irc_conv_gemm_args {
     int tap_nshift, tap_nco, tap_H, tap_W, tap_hp, tap_wp, tap_oy, tap_ox, tap_act;
     const float* tap_scale;
     int tap_accumulate;
+    /* cin == 64 only: operand columns [k_live, 64) of `a` are structural zeros (e.g. the tap-expanded gradient of the 3-channel output
+     * head: 21 live columns), so only ceil(k_live / 16) of the four 16-column reduction steps are issued.  0 = all columns. */
+    int k_live;
 } irc_conv_gemm_args;
 int irc_conv_gemm(const irc_conv_gemm_args* args, void* stream);
 /* nn.ConvTranspose2d(cin, cout, 3, stride=2, padding=1, output_padding=1) forward (the generator's up-sampling layers with

@@ -44,7 +44,7 @@ class ConvGemmArgs(C.Structure):
         ("stats_part", C.c_void_p), ("stats_edge", C.c_void_p), ("rows_per_img", C.c_int),
         ("tap_out", C.c_void_p), ("tap_nshift", C.c_int), ("tap_nco", C.c_int), ("tap_H", C.c_int), ("tap_W", C.c_int), ("tap_hp", C.c_int),
         ("tap_wp", C.c_int), ("tap_oy", C.c_int), ("tap_ox", C.c_int), ("tap_act", C.c_int),
-        ("tap_scale", C.c_void_p), ("tap_accumulate", C.c_int),
+        ("tap_scale", C.c_void_p), ("tap_accumulate", C.c_int), ("k_live", C.c_int),
     ]
 
 
@@ -348,7 +348,7 @@ class CudaBackend:
 
     # ---- tensor-core GEMMs
     def conv_gemm(self, a, a_chan_off, cin, taps: Sequence[int], w, n_out, out, out_chan_off=0, bias=None, act=0, slope=0.0,
-                  row_img=None, mask: Optional[View] = None, mask_slope=0.0, addend: Optional[View] = None, in_stats=None, tap=None):
+                  row_img=None, mask: Optional[View] = None, mask_slope=0.0, addend: Optional[View] = None, in_stats=None, tap=None, k_live=0):
         """in_stats = (stats [n_img, n_out, 2], n_img, rows_per_img): InstanceNorm statistics of the output from the epilogue
         (needs row_img); tap = dict(out, nshift, nco, H, W, hp, wp, oy, ox, act): horizontal tap reduction + bias + activation
         fused into the epilogue, fp32 NCHW result in tap['out'] (`out` is then only a placeholder)."""
@@ -372,6 +372,7 @@ class CudaBackend:
             assert addend.t.shape[0] == a.shape[0]
             g.addend = addend.t.data_ptr(); g.addend_ld = addend.t.shape[1]; g.addend_chan_off = addend.chan_off
         g.bn = 0; g.mt = self.conv_mt; g.reuse = self.conv_reuse; g.epilogue_direct = self.conv_epilogue_direct
+        g.k_live = int(k_live)            # cin == 64: operand columns >= k_live are structural zeros
         fin = None
         if in_stats is not None:
             stats, n_img, rows_per_img = in_stats

@@ -70,6 +70,7 @@ int make_map(CUtensorMap* m, const void* base, long long rows, int ld, int box_r
 struct ConvParams {
     long long rows;
     int n_tiles, bn, k_chunks, a_chan_off, ntaps, stages;
+    int k16;         // 16-column reduction steps issued per 64-column chunk (4; fewer when the operand's last columns are structural zeros)
     int mt;          // M sub-tiles of 128 rows per tile (1 or 2): two sub-tiles share every B stage
     int nbuf;        // TMEM accumulator buffers (2 = epilogue overlaps the next tile's MMAs)
     int taps[IRC_MAX_TAPS];
@@ -501,6 +502,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constan
                         const uint32_t accum = kb != 0;
 #pragma unroll
                         for (int k = 0; k < kBK / 16; ++k) {
+                            if (k >= p.k16) break;              // operand columns past k_live are structural zeros (args.k_live)
 #pragma unroll
                             for (int m = 0; m < MT; ++m)
                                 umma_bf16(d_tmem + (uint32_t)(m * p.bn), adesc + (uint64_t)(m * (kBM * 128 / 16) + k * 2), bdesc + (uint64_t)(k * 2), idesc,
@@ -1638,6 +1640,9 @@ extern "C" int irc_conv_gemm(const irc_conv_gemm_args* a, void* stream) {
     p.bn = bn;
     p.n_tiles = a->n_out / bn;
     p.k_chunks = a->cin / 64;
+    if (a->k_live < 0 || a->k_live > 64 || (a->k_live > 0 && a->cin != 64))
+        return irc_set_error(IRC_ERR_BAD_ARG, "irc_conv_gemm: k_live (live operand columns, the rest structural zeros) needs cin == 64 and 0 <= k_live <= 64");
+    p.k16 = a->k_live > 0 ? (a->k_live + 15) / 16 : 4;
     p.a_chan_off = a->a_chan_off;
     p.ntaps = a->ntaps;
     for (int i = 0; i < a->ntaps; ++i) p.taps[i] = a->taps[i];

@@ -530,7 +530,7 @@ class GeneratorEngine:
         be.tap_expand(dfake, self.fake, self.outc_shifts, 3, B, H, W, y4.hp, y4.wp, 3, 3, self.E_out,
                       dbias=self.arena.view("outc.1.bias", self.arena.grad), live_cols_only=True)      # E_out's other columns stay zero
         self.outc.wgrad(self.E_out, y4.t, 0, y4.rows)
-        self.outc.dgrad(self.E_out, self.G4.t)
+        self.outc.dgrad(self.E_out, self.G4.t, k_live=21)      # E_out holds 7 taps x 3 channels; its other columns are zeros
         # up2_conv
         be.fold_inplace(self.G4.t, 0, 64, B, H, W, 3)             # ReflectionPad2d(3)^T on the border pixels only
         be.in_bwd(self.Z4.view(), self.G4.view(), self.dZ4.view(), 64, B, H, W, **self._nb(self.st4, H * W, ACT_RELU), bsum=self.bsum)

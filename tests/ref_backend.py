@@ -96,7 +96,7 @@ class RefBackend:
     fused_outc = True
 
     def conv_gemm(self, a, a_chan_off, cin, taps, w, n_out, out, out_chan_off=0, bias=None, act=0, slope=0.0,
-                  row_img=None, mask=None, mask_slope=0.0, addend=None, in_stats=None, tap=None):
+                  row_img=None, mask=None, mask_slope=0.0, addend=None, in_stats=None, tap=None, k_live=0):
         self.launches += 1
         if tap is not None:
             # horizontal tap reduction + bias + activation fused into the epilogue: the bias belongs to the reduced output

@@ -386,7 +386,7 @@ def check_outc_7x7_tanh(ctx):
     be.tap_expand(g.to(Cfg.dev), eng.fake, eng.outc_shifts, 3, B, H, W, eng.y4.hp, eng.y4.wp, 3, 3, eng.E_out,
                   dbias=eng.arena.view("outc.1.bias", eng.arena.grad))
     eng.outc.wgrad(eng.E_out, eng.y4.t, 0, eng.y4.rows)
-    eng.outc.dgrad(eng.E_out, eng.G4.t)
+    eng.outc.dgrad(eng.E_out, eng.G4.t, k_live=21)       # as in the plan: only the 21 tap columns of E_out are live
     be.flush_sums()
     xp = F.pad(x, (3, 3, 3, 3), mode="reflect").requires_grad_(True)
     w32 = w.clone().requires_grad_(True)
