@@ -2017,20 +2017,31 @@ __global__ void fold_inplace_kernel(bf16* g, long long ld, int off, int C, int n
     if (my < 0 && mx < 0) return;
     bf16* base = g + (long long)n * Hp * Wp * ld + off + c;
     float acc[8], v[8];
-    const float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bf16* self = base + ((long long)(y + p) * Wp + (x + p)) * ld;
-    load8(self, acc);
     // every ring pixel mirrors onto exactly one interior pixel, so the thread that consumes it also clears it
-    // (the folded frame can then serve as a zero-ring addend / operand)
-    if (my >= 0) { bf16* q = base + ((long long)my * Wp + (x + p)) * ld; load8(q, v); store8(q, zero);
+    // (the folded frame can then serve as a zero-ring addend / operand).  All (up to four) loads go out together; the
+    // additions keep the order self + row mirror + column mirror + corner.
+    bf16* q0 = my >= 0 ? base + ((long long)my * Wp + (x + p)) * ld : nullptr;
+    bf16* q1 = mx >= 0 ? base + ((long long)(y + p) * Wp + mx) * ld : nullptr;
+    bf16* q2 = (my >= 0 && mx >= 0) ? base + ((long long)my * Wp + mx) * ld : nullptr;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    const uint4 us = *reinterpret_cast<const uint4*>(self);
+    const uint4 u0 = q0 ? *reinterpret_cast<const uint4*>(q0) : zero4;
+    const uint4 u1 = q1 ? *reinterpret_cast<const uint4*>(q1) : zero4;
+    const uint4 u2 = q2 ? *reinterpret_cast<const uint4*>(q2) : zero4;
+    unpack8(us, acc);
+    unpack8(u0, v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
-    if (mx >= 0) { bf16* q = base + ((long long)(y + p) * Wp + mx) * ld; load8(q, v); store8(q, zero);
+    for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    unpack8(u1, v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
-    if (my >= 0 && mx >= 0) { bf16* q = base + ((long long)my * Wp + mx) * ld; load8(q, v); store8(q, zero);
+    for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    unpack8(u2, v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += v[k]; }
+    for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    if (q0) *reinterpret_cast<uint4*>(q0) = zero4;
+    if (q1) *reinterpret_cast<uint4*>(q1) = zero4;
+    if (q2) *reinterpret_cast<uint4*>(q2) = zero4;
     store8(self, acc);
 }
 
